@@ -25,6 +25,7 @@ static std::string show(const std::map<K, V>& m);
 template <class K>
 static std::string show(const std::set<K>& m);
 static std::string show(const uint8_t& v);
+static std::string show(const TargetedMarker& t);
 static std::string show(const VariantLocus& l) {
   return "(" + std::to_string(l.first) + "," + std::to_string(l.second) + ")";
 }
