@@ -1,0 +1,17 @@
+"""gramtools_b200 — B200-native quasimap back-end (host mirror of the C ABI in include/gq.h).
+
+The product is ``libgq.so`` (hand-written sm_100a CUDA + C++ host code, ``gramtools_b200/csrc``).
+This module is only the thin ctypes binding used by the tests, ``bench.py`` and the multi-GPU
+driver; names follow the reference's quasimap interface
+(libgramtools/include/genotype/quasimap/quasimap.hpp:17-32).
+
+There is no CPU fallback: importing works anywhere, but every compute call needs the built
+library and a CUDA device and raises otherwise.
+"""
+from .engine import (GqError, QuasimapIndex, QuasimapReadsStats, encode_reads, lib_path, load_library)  # noqa: F401
+from .synth import (make_snp_prg, make_nested_prg, sample_reads, master_seeds)  # noqa: F401
+
+__all__ = [
+    "GqError", "QuasimapIndex", "QuasimapReadsStats", "encode_reads", "lib_path", "load_library",
+    "make_snp_prg", "make_nested_prg", "sample_reads", "master_seeds",
+]

@@ -1,0 +1,724 @@
+// capi.cu — the C ABI of libgq.so (include/gq.h) over the host index builder and the sm_100a kernels.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/gq.h"
+#include "index_build.hpp"
+#include "kernels.cuh"
+
+namespace gq {
+void launch_stats(const uint8_t* status, const uint32_t* len, uint32_t n_reads, unsigned long long* stats,
+                  cudaStream_t st);
+}
+
+static thread_local std::string g_err;
+
+#define CUDA_OK(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      throw std::runtime_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                \
+  } while (0)
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;  // elements
+  void reserve(size_t n) {
+    if (n <= cap) return;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    CUDA_OK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+    cap = n;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  size_t bytes() const { return cap * sizeof(T); }
+};
+
+struct gq_index {
+  gq::HostIndex h;
+  int device = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::vector<void*> index_allocs;
+  size_t index_bytes = 0;
+  gq::IndexView dv{};
+  // coverage accumulators
+  DevBuf<uint32_t> counters;  // allele_sum | grouped_single | per_base
+  DevBuf<uint32_t> allele_off;
+  DevBuf<uint32_t> gtab, gcount, gpool, gsmall;  // gsmall: [gpool_used, error_flags]
+  DevBuf<unsigned long long> stats;
+  uint64_t n_alleles = 0, n_per_base = 0;
+  // batch
+  DevBuf<uint8_t> bases;
+  DevBuf<uint64_t> offsets;
+  DevBuf<uint32_t> word_off, packed, len, seeds;
+  uint32_t n_reads = 0;
+  uint32_t total_words = 0;
+  // search outputs
+  DevBuf<uint8_t> status;
+  DevBuf<uint32_t> st_off, st_words, st_count, pool, small;  // small: [pool_used, n_overflow, n_cov_overflow]
+  DevBuf<uint32_t> overflow_list, cov_overflow_list;
+  DevBuf<uint32_t> arena, big_arena;
+  // options
+  uint32_t arena_words = 256;
+  uint32_t n_threads = 148 * 1024;
+  uint32_t big_arena_words = 1u << 16;
+  uint32_t big_threads = 2048;
+  uint32_t pool_words_per_read = 48;
+  bool super_in_smem = true;
+  // run info
+  double info[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+template <class T>
+static const T* upload(gq_index* ix, const std::vector<T>& v) {
+  T* d = nullptr;
+  size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+  CUDA_OK(cudaMalloc(&d, bytes));
+  if (!v.empty()) CUDA_OK(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  ix->index_allocs.push_back(d);
+  ix->index_bytes += bytes;
+  return d;
+}
+
+static void upload_index(gq_index* ix) {
+  const gq::HostIndex& h = ix->h;
+  gq::IndexView& v = ix->dv;
+  v.n = h.n;
+  v.rank_blk = upload(ix, h.rank_blk);
+  v.super_cnt = upload(ix, h.super_cnt);
+  v.mrank_blk = upload(ix, h.mrank_blk);
+  v.marker_hit = upload(ix, h.marker_hit);
+  for (int i = 0; i < 4; ++i) v.c_base[i] = h.c_base[i];
+  v.n_slots = h.n_slots;
+  v.site_sa = upload(ix, h.site_sa);
+  v.allele_iv = upload(ix, h.allele_iv);
+  v.par = upload(ix, h.par);
+  v.tm_odd = upload(ix, h.tm_odd);
+  v.tm_even_off = upload(ix, h.tm_even_off);
+  v.tm_even = upload(ix, h.tm_even);
+  v.sa = upload(ix, h.sa);
+  v.pos2node = upload(ix, h.pos2node);
+  v.nodes = upload(ix, h.nodes);
+  v.edges = upload(ix, h.edges);
+  v.k = h.k;
+  v.kmer_bits = upload(ix, h.kmer_bits);
+  v.kmer_off = upload(ix, h.kmer_off);
+  v.kmer_states = upload(ix, h.kmer_states);
+  v.kmer_paths = upload(ix, h.kmer_paths);
+}
+
+static uint32_t next_pow2(uint64_t x) {
+  uint32_t p = 1;
+  while (p < x && p < (1u << 30)) p <<= 1;
+  return p;
+}
+
+static void alloc_coverage(gq_index* ix) {
+  const gq::HostIndex& h = ix->h;
+  ix->n_alleles = h.allele_off.back();
+  ix->n_per_base = h.n_per_base;
+  size_t nc = 2 * ix->n_alleles + ix->n_per_base;
+  ix->counters.reserve(nc + 1);
+  ix->allele_off.reserve(h.allele_off.size());
+  CUDA_OK(cudaMemcpy(ix->allele_off.p, h.allele_off.data(), h.allele_off.size() * 4, cudaMemcpyHostToDevice));
+  uint32_t cap = next_pow2(std::max<uint64_t>(1024, 4 * ix->n_alleles));
+  ix->gtab.reserve(cap);
+  ix->gcount.reserve(cap);
+  ix->gpool.reserve((size_t)cap * 4);
+  ix->gsmall.reserve(4);
+  ix->stats.reserve(8);
+}
+
+static void reset_coverage(gq_index* ix) {
+  CUDA_OK(cudaMemsetAsync(ix->counters.p, 0, ix->counters.bytes(), ix->stream));
+  CUDA_OK(cudaMemsetAsync(ix->gtab.p, 0, ix->gtab.bytes(), ix->stream));
+  CUDA_OK(cudaMemsetAsync(ix->gcount.p, 0, ix->gcount.bytes(), ix->stream));
+  CUDA_OK(cudaMemsetAsync(ix->gsmall.p, 0, ix->gsmall.bytes(), ix->stream));
+  CUDA_OK(cudaMemsetAsync(ix->stats.p, 0, ix->stats.bytes(), ix->stream));
+  CUDA_OK(cudaStreamSynchronize(ix->stream));
+}
+
+static gq::CoverageView cov_view(gq_index* ix) {
+  gq::CoverageView c{};
+  c.allele_sum = ix->counters.p;
+  c.grouped_single = ix->counters.p + ix->n_alleles;
+  c.per_base = ix->counters.p + 2 * ix->n_alleles;
+  c.gtab = ix->gtab.p;
+  c.gcount = ix->gcount.p;
+  c.gtab_cap = (uint32_t)ix->gtab.cap;
+  c.gpool = ix->gpool.p;
+  c.gpool_cap = (uint32_t)ix->gpool.cap;
+  c.gpool_used = ix->gsmall.p;
+  c.error_flags = ix->gsmall.p + 1;
+  c.stats = ix->stats.p;
+  c.allele_off = ix->allele_off.p;
+  return c;
+}
+
+static void do_upload(gq_index* ix, const uint8_t* bases, const uint64_t* off, uint64_t n_reads,
+                      const uint32_t* seeds) {
+  if (n_reads >= (1ull << 30)) throw std::runtime_error("batch too large (max 2^30 reads per batch)");
+  CUDA_OK(cudaSetDevice(ix->device));
+  ix->n_reads = (uint32_t)n_reads;
+  if (n_reads == 0) return;
+  uint64_t nb = off[n_reads] - off[0];
+  if (off[0] != 0) throw std::runtime_error("read_offsets[0] must be 0");
+  std::vector<uint32_t> word_off(n_reads + 1);
+  uint64_t w = 0;
+  for (uint64_t r = 0; r < n_reads; ++r) {
+    word_off[r] = (uint32_t)w;
+    w += (off[r + 1] - off[r] + 15) >> 4;
+    if (w >= (1ull << 32)) throw std::runtime_error("batch too large (packed words exceed 2^32)");
+  }
+  word_off[n_reads] = (uint32_t)w;
+  ix->total_words = (uint32_t)w;
+  cudaStream_t st = ix->stream;
+  ix->bases.reserve(nb + 16);
+  ix->offsets.reserve(n_reads + 1);
+  ix->word_off.reserve(n_reads + 1);
+  ix->packed.reserve(w + 1);
+  ix->len.reserve(n_reads);
+  ix->seeds.reserve(n_reads);
+  CUDA_OK(cudaMemcpyAsync(ix->bases.p, bases, nb, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(ix->offsets.p, off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(ix->word_off.p, word_off.data(), (n_reads + 1) * 4, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(ix->seeds.p, seeds, n_reads * 4, cudaMemcpyHostToDevice, st));
+  gq::launch_pack(ix->bases.p, ix->offsets.p, ix->word_off.p, ix->n_reads, ix->total_words, ix->packed.p, ix->len.p,
+                  st);
+  CUDA_OK(cudaGetLastError());
+  // word_off is a stack-local pageable buffer: wait for the copies before it goes away
+  CUDA_OK(cudaStreamSynchronize(st));
+  ix->info[5] = (double)(nb + (n_reads + 1) * 12 + n_reads * 4);  // H2D bytes of this upload
+}
+
+static void do_map(gq_index* ix) {
+  CUDA_OK(cudaSetDevice(ix->device));
+  const uint32_t n = ix->n_reads;
+  for (double& x : ix->info) x = (&x == &ix->info[5]) ? x : 0;
+  if (n == 0) return;
+  cudaStream_t st = ix->stream;
+  ix->status.reserve(2 * (size_t)n);
+  ix->st_off.reserve(2 * (size_t)n);
+  ix->st_words.reserve(2 * (size_t)n);
+  ix->st_count.reserve(2 * (size_t)n);
+  ix->overflow_list.reserve(2 * (size_t)n);
+  ix->cov_overflow_list.reserve(2 * (size_t)n);
+  ix->small.reserve(4);
+  size_t pool_need = std::max<size_t>((size_t)n * ix->pool_words_per_read, 1 << 16);
+  pool_need = std::min<size_t>(pool_need, 0xFFFFFFF0ull);
+  ix->pool.reserve(pool_need);
+  uint32_t threads = std::min<uint32_t>(ix->n_threads, ((n + 255) / 256) * 256);
+  // the coverage kernel walks strands: give it the same arena (2n strands over `threads2` threads)
+  uint32_t threads2 = std::min<uint32_t>(ix->n_threads, ((2 * n + 255) / 256) * 256);
+  ix->arena.reserve((size_t)std::max(threads, threads2) * ix->arena_words);
+  CUDA_OK(cudaMemsetAsync(ix->small.p, 0, 16, st));
+
+  gq::BatchView b{ix->packed.p, ix->word_off.p, ix->len.p, ix->seeds.p, n};
+  gq::SearchOut o{ix->status.p, ix->st_off.p, ix->st_words.p, ix->st_count.p, ix->pool.p, (uint32_t)ix->pool.cap,
+                  ix->small.p,  ix->overflow_list.p, ix->small.p + 1};
+  gq::CoverageView c = cov_view(ix);
+  int launches = 0;
+  CUDA_OK(cudaEventRecord(ix->ev[0], st));
+  gq::launch_search(ix->dv, b, o, ix->arena.p, ix->arena_words, threads, nullptr, 0, ix->super_in_smem, st);
+  ++launches;
+  CUDA_OK(cudaEventRecord(ix->ev[1], st));
+  gq::launch_coverage(ix->dv, b, o, c, ix->arena.p, ix->arena_words, threads2, nullptr, 0, ix->cov_overflow_list.p,
+                      ix->small.p + 2, st);
+  ++launches;
+  CUDA_OK(cudaEventRecord(ix->ev[2], st));
+  uint32_t small[4];
+  CUDA_OK(cudaMemcpyAsync(small, ix->small.p, 16, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  CUDA_OK(cudaGetLastError());
+  float ms_s = 0, ms_c = 0;
+  cudaEventElapsedTime(&ms_s, ix->ev[0], ix->ev[1]);
+  cudaEventElapsedTime(&ms_c, ix->ev[1], ix->ev[2]);
+  ix->info[2] = ms_s;
+  ix->info[3] = ms_c;
+  uint64_t rerun = 0;
+  // ---- overflow re-runs: same kernels, fewer threads, much larger per-thread arenas -------------
+  uint32_t big_words = ix->big_arena_words;
+  int guard = 0;
+  while (small[1] > 0) {
+    uint32_t n_list = small[1];
+    rerun += n_list;
+    if (++guard > 12) throw std::runtime_error("search state arena overflow persists at the largest arena size");
+    if (small[0] > ix->pool.cap) {  // the pool ran out: grow it, keeping what was written
+      size_t ncap = std::min<size_t>(std::max<size_t>((size_t)small[0] * 2, ix->pool.cap * 2), 0xFFFFFFF0ull);
+      if (ncap <= ix->pool.cap) throw std::runtime_error("final-state pool exceeds 2^32 words; use smaller batches");
+      uint32_t* np = nullptr;
+      CUDA_OK(cudaMalloc(&np, ncap * 4));
+      CUDA_OK(cudaMemcpyAsync(np, ix->pool.p, ix->pool.cap * 4, cudaMemcpyDeviceToDevice, st));
+      CUDA_OK(cudaStreamSynchronize(st));
+      uint32_t used = (uint32_t)ix->pool.cap;
+      cudaFree(ix->pool.p);
+      ix->pool.p = np;
+      ix->pool.cap = ncap;
+      CUDA_OK(cudaMemcpyAsync(ix->small.p, &used, 4, cudaMemcpyHostToDevice, st));
+      o.pool = np;
+      o.pool_cap = (uint32_t)ncap;
+    }
+    uint32_t bt = std::min<uint32_t>(ix->big_threads, ((n_list + 255) / 256) * 256);
+    ix->big_arena.reserve((size_t)bt * big_words);
+    // the kernel appends to the same list while reading it: read from a copy
+    DevBuf<uint32_t> list;
+    list.reserve(n_list);
+    CUDA_OK(cudaMemcpyAsync(list.p, ix->overflow_list.p, (size_t)n_list * 4, cudaMemcpyDeviceToDevice, st));
+    CUDA_OK(cudaMemsetAsync(ix->small.p + 1, 0, 4, st));
+    gq::launch_search(ix->dv, b, o, ix->big_arena.p, big_words, bt, list.p, n_list, ix->super_in_smem, st);
+    gq::launch_coverage(ix->dv, b, o, c, ix->big_arena.p, big_words, bt, list.p, n_list, ix->cov_overflow_list.p,
+                        ix->small.p + 2, st);
+    launches += 2;
+    CUDA_OK(cudaMemcpyAsync(small, ix->small.p, 16, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    CUDA_OK(cudaGetLastError());
+    list.release();
+    if (small[1] > 0) {
+      big_words *= 4;
+      ix->big_threads = std::max<uint32_t>(256, ix->big_threads / 4);
+    }
+  }
+  guard = 0;
+  while (small[2] > 0) {
+    uint32_t n_list = small[2];
+    rerun += n_list;
+    if (++guard > 12) throw std::runtime_error("coverage scratch overflow persists at the largest arena size");
+    uint32_t bt = std::min<uint32_t>(ix->big_threads, ((n_list + 255) / 256) * 256);
+    ix->big_arena.reserve((size_t)bt * big_words);
+    DevBuf<uint32_t> list;
+    list.reserve(n_list);
+    CUDA_OK(cudaMemcpyAsync(list.p, ix->cov_overflow_list.p, (size_t)n_list * 4, cudaMemcpyDeviceToDevice, st));
+    CUDA_OK(cudaMemsetAsync(ix->small.p + 2, 0, 4, st));
+    gq::launch_coverage(ix->dv, b, o, c, ix->big_arena.p, big_words, bt, list.p, n_list, ix->cov_overflow_list.p,
+                        ix->small.p + 2, st);
+    ++launches;
+    CUDA_OK(cudaMemcpyAsync(small, ix->small.p, 16, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    CUDA_OK(cudaGetLastError());
+    list.release();
+    if (small[2] > 0) {
+      big_words *= 4;
+      ix->big_threads = std::max<uint32_t>(256, ix->big_threads / 4);
+    }
+  }
+  gq::launch_stats(ix->status.p, ix->len.p, n, ix->stats.p, st);
+  ++launches;
+  uint32_t gs[2];
+  CUDA_OK(cudaMemcpyAsync(gs, ix->gsmall.p, 8, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  CUDA_OK(cudaGetLastError());
+  if (gs[1] & 1u) throw std::runtime_error("grouped allele count table is full");
+  if (gs[1] & 2u) throw std::runtime_error("inconsistent traversal while recording per-base coverage");
+  ix->info[0] = launches;
+  ix->info[1] = (double)rerun;
+  ix->info[4] = small[0];
+}
+
+// -------------------------------------------------------------------------------------------------
+#define GQ_TRY try {
+#define GQ_CATCH                    \
+  }                                 \
+  catch (const std::exception& e) { \
+    g_err = e.what();               \
+    return -1;                      \
+  }                                 \
+  return 0;
+
+extern "C" {
+
+const char* gq_last_error(void) { return g_err.c_str(); }
+
+int gq_index_build(const uint32_t* prg, uint64_t n_symbols, uint32_t kmer_size, int device, gq_index** out) {
+  gq_index* ix = nullptr;
+  GQ_TRY
+  if (!prg || !out) throw std::runtime_error("null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    throw std::runtime_error("no CUDA device: libgq has no CPU fallback");
+  if (device < 0 || device >= ndev) throw std::runtime_error("invalid device ordinal");
+  ix = new gq_index();
+  ix->device = device;
+  gq::build_host_index(prg, n_symbols, kmer_size, ix->h);
+  CUDA_OK(cudaSetDevice(device));
+  CUDA_OK(cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking));
+  ix->stream = ix->own_stream;
+  for (auto& e : ix->ev) CUDA_OK(cudaEventCreate(&e));
+  upload_index(ix);
+  alloc_coverage(ix);
+  reset_coverage(ix);
+  *out = ix;
+  }
+  catch (const std::exception& e) {
+    g_err = e.what();
+    if (ix) gq_index_destroy(ix);
+    return -1;
+  }
+  return 0;
+}
+
+int gq_index_destroy(gq_index* ix) {
+  if (!ix) return 0;
+  cudaSetDevice(ix->device);
+  for (void* p : ix->index_allocs) cudaFree(p);
+  ix->counters.release();
+  ix->allele_off.release();
+  ix->gtab.release();
+  ix->gcount.release();
+  ix->gpool.release();
+  ix->gsmall.release();
+  ix->stats.release();
+  ix->bases.release();
+  ix->offsets.release();
+  ix->word_off.release();
+  ix->packed.release();
+  ix->len.release();
+  ix->seeds.release();
+  ix->status.release();
+  ix->st_off.release();
+  ix->st_words.release();
+  ix->st_count.release();
+  ix->pool.release();
+  ix->small.release();
+  ix->overflow_list.release();
+  ix->cov_overflow_list.release();
+  ix->arena.release();
+  ix->big_arena.release();
+  for (auto& e : ix->ev)
+    if (e) cudaEventDestroy(e);
+  if (ix->own_stream) cudaStreamDestroy(ix->own_stream);
+  delete ix;
+  return 0;
+}
+
+int gq_index_describe(const gq_index* ix, gq_layout* out) {
+  GQ_TRY
+  if (!ix || !out) throw std::runtime_error("null argument");
+  out->n_symbols = ix->h.prg.size();
+  out->sa_size = ix->h.n;
+  out->kmer_size = ix->h.k;
+  out->n_sites = ix->h.n_sites;
+  out->n_site_slots = ix->h.n_slots;
+  out->is_nested = ix->h.is_nested;
+  out->n_alleles = ix->n_alleles;
+  out->n_per_base = ix->n_per_base;
+  out->n_kmer_states = ix->h.kmer_off.back();
+  out->device_bytes = ix->index_bytes;
+  GQ_CATCH
+}
+
+int gq_index_allele_offsets(const gq_index* ix, uint64_t* allele_off) {
+  GQ_TRY
+  if (!ix || !allele_off) throw std::runtime_error("null argument");
+  for (size_t i = 0; i < ix->h.allele_off.size(); ++i) allele_off[i] = ix->h.allele_off[i];
+  GQ_CATCH
+}
+
+int gq_index_per_base_layout(const gq_index* ix, uint64_t* off_len) {
+  GQ_TRY
+  if (!ix || !off_len) throw std::runtime_error("null argument");
+  const gq::HostIndex& h = ix->h;
+  for (uint32_t s = 0; s < h.n_slots; ++s) {
+    if (h.n_alleles[s] == 0) continue;
+    const gq::Node& sn = h.nodes[h.site_start_node[s]];
+    for (uint32_t a = 0; a < h.n_alleles[s]; ++a) {
+      const gq::Node& an = h.nodes[h.edges[sn.edge_off + a]];
+      uint64_t* d = off_len + 2 * ((uint64_t)h.allele_off[s] + a);
+      bool seq = an.len > 0 && an.cov_off != gq::kNoAllele && an.site == 5 + 2 * s;
+      d[0] = seq ? an.cov_off : 0;
+      d[1] = seq ? an.len : 0;
+    }
+  }
+  GQ_CATCH
+}
+
+int gq_batch_upload(gq_index* ix, const uint8_t* bases, const uint64_t* off, uint64_t n_reads, const uint32_t* seeds) {
+  GQ_TRY
+  if (!ix || (n_reads && (!bases || !off || !seeds))) throw std::runtime_error("null argument");
+  do_upload(ix, bases, off, n_reads, seeds);
+  GQ_CATCH
+}
+
+int gq_map_resident(gq_index* ix) {
+  GQ_TRY
+  if (!ix) throw std::runtime_error("null argument");
+  do_map(ix);
+  GQ_CATCH
+}
+
+int gq_map_batch(gq_index* ix, const uint8_t* bases, const uint64_t* off, uint64_t n_reads, const uint32_t* seeds) {
+  GQ_TRY
+  if (!ix || (n_reads && (!bases || !off || !seeds))) throw std::runtime_error("null argument");
+  do_upload(ix, bases, off, n_reads, seeds);
+  do_map(ix);
+  GQ_CATCH
+}
+
+int gq_batch_status(gq_index* ix, uint8_t* status) {
+  GQ_TRY
+  if (!ix || !status) throw std::runtime_error("null argument");
+  CUDA_OK(cudaSetDevice(ix->device));
+  if (ix->n_reads) CUDA_OK(cudaMemcpy(status, ix->status.p, 2 * (size_t)ix->n_reads, cudaMemcpyDeviceToHost));
+  GQ_CATCH
+}
+
+static void fetch_strand_tables(gq_index* ix, std::vector<uint32_t>& off, std::vector<uint32_t>& words,
+                                std::vector<uint32_t>& count, std::vector<uint8_t>& status) {
+  size_t m = 2 * (size_t)ix->n_reads;
+  off.resize(m);
+  words.resize(m);
+  count.resize(m);
+  status.resize(m);
+  if (!m) return;
+  CUDA_OK(cudaMemcpy(off.data(), ix->st_off.p, m * 4, cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(words.data(), ix->st_words.p, m * 4, cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(count.data(), ix->st_count.p, m * 4, cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(status.data(), ix->status.p, m, cudaMemcpyDeviceToHost));
+}
+
+int gq_batch_states_size(gq_index* ix, uint64_t* n_words) {
+  GQ_TRY
+  if (!ix || !n_words) throw std::runtime_error("null argument");
+  CUDA_OK(cudaSetDevice(ix->device));
+  std::vector<uint32_t> off, words, count;
+  std::vector<uint8_t> status;
+  fetch_strand_tables(ix, off, words, count, status);
+  uint64_t t = 0;
+  for (size_t i = 0; i < words.size(); ++i)
+    if (status[i] == gq::ST_MAPPED) t += words[i];
+  *n_words = t;
+  GQ_CATCH
+}
+
+int gq_batch_states(gq_index* ix, uint64_t* strand_off, uint32_t* strand_count, uint32_t* out_words) {
+  GQ_TRY
+  if (!ix || !strand_off || !strand_count) throw std::runtime_error("null argument");
+  CUDA_OK(cudaSetDevice(ix->device));
+  std::vector<uint32_t> off, words, count;
+  std::vector<uint8_t> status;
+  fetch_strand_tables(ix, off, words, count, status);
+  uint32_t used = 0;
+  if (ix->n_reads) CUDA_OK(cudaMemcpy(&used, ix->small.p, 4, cudaMemcpyDeviceToHost));
+  used = (uint32_t)std::min<size_t>(used, ix->pool.cap);
+  std::vector<uint32_t> pool(used);
+  if (used) CUDA_OK(cudaMemcpy(pool.data(), ix->pool.p, (size_t)used * 4, cudaMemcpyDeviceToHost));
+  uint64_t t = 0;
+  for (size_t i = 0; i < words.size(); ++i) {
+    strand_off[i] = t;
+    bool m = status[i] == gq::ST_MAPPED;
+    strand_count[i] = m ? count[i] : 0;
+    if (m) {
+      if (out_words) std::memcpy(out_words + t, pool.data() + off[i], (size_t)words[i] * 4);
+      t += words[i];
+    }
+  }
+  strand_off[words.size()] = t;
+  GQ_CATCH
+}
+
+int gq_coverage_fetch(gq_index* ix, uint16_t* allele_sum, uint16_t* per_base, uint64_t stats[5]) {
+  GQ_TRY
+  if (!ix) throw std::runtime_error("null argument");
+  CUDA_OK(cudaSetDevice(ix->device));
+  CUDA_OK(cudaStreamSynchronize(ix->stream));
+  if (allele_sum && ix->n_alleles) {
+    std::vector<uint32_t> t(ix->n_alleles);
+    CUDA_OK(cudaMemcpy(t.data(), ix->counters.p, ix->n_alleles * 4, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < t.size(); ++i) allele_sum[i] = (uint16_t)(t[i] & 0xFFFFu);  // uint16 wrap
+  }
+  if (per_base && ix->n_per_base) {
+    std::vector<uint32_t> t(ix->n_per_base);
+    CUDA_OK(cudaMemcpy(t.data(), ix->counters.p + 2 * ix->n_alleles, ix->n_per_base * 4, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < t.size(); ++i) per_base[i] = (uint16_t)std::min<uint32_t>(t[i], 65535u);  // saturate
+  }
+  if (stats) {
+    unsigned long long s[5];
+    CUDA_OK(cudaMemcpy(s, ix->stats.p, sizeof(s), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 5; ++i) stats[i] = s[i];
+  }
+  GQ_CATCH
+}
+
+// all groups of this handle as (slot, alleles) -> raw count; singles first from the dense array
+static void collect_groups(gq_index* ix, std::map<std::vector<uint32_t>, uint64_t>& out, bool multi_only) {
+  CUDA_OK(cudaSetDevice(ix->device));
+  CUDA_OK(cudaStreamSynchronize(ix->stream));
+  const gq::HostIndex& h = ix->h;
+  if (!multi_only && ix->n_alleles) {
+    std::vector<uint32_t> single(ix->n_alleles);
+    CUDA_OK(cudaMemcpy(single.data(), ix->counters.p + ix->n_alleles, ix->n_alleles * 4, cudaMemcpyDeviceToHost));
+    for (uint32_t s = 0; s < h.n_slots; ++s)
+      for (uint32_t a = 0; a < h.n_alleles[s]; ++a) {
+        uint32_t cnt = single[h.allele_off[s] + a];
+        if (cnt) out[{s, a}] += cnt;
+      }
+  }
+  uint32_t gs[2];
+  CUDA_OK(cudaMemcpy(gs, ix->gsmall.p, 8, cudaMemcpyDeviceToHost));
+  if (gs[0] == 0) return;
+  std::vector<uint32_t> tab(ix->gtab.cap), cnt(ix->gtab.cap), pool(std::min<size_t>(gs[0], ix->gpool.cap));
+  CUDA_OK(cudaMemcpy(tab.data(), ix->gtab.p, tab.size() * 4, cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(cnt.data(), ix->gcount.p, cnt.size() * 4, cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(pool.data(), ix->gpool.p, pool.size() * 4, cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < tab.size(); ++i) {
+    if (!tab[i] || !cnt[i]) continue;
+    const uint32_t* rec = pool.data() + (tab[i] - 1);
+    std::vector<uint32_t> key{rec[0]};
+    key.insert(key.end(), rec + 2, rec + 2 + rec[1]);
+    out[key] += cnt[i];
+  }
+}
+
+static int write_groups(const std::map<std::vector<uint32_t>, uint64_t>& g, uint32_t* words, uint64_t* n_words,
+                        bool wrap16) {
+  uint64_t t = 0;
+  for (auto& e : g) {
+    uint32_t cnt = wrap16 ? (uint32_t)(e.second & 0xFFFFu) : (uint32_t)e.second;
+    if (wrap16 && cnt == 0) {
+      // a key whose uint16 counter wrapped to exactly 0 still exists in the reference's map
+    }
+    if (words) {
+      words[t] = e.first[0];
+      words[t + 1] = cnt;
+      words[t + 2] = (uint32_t)e.first.size() - 1;
+      for (size_t i = 1; i < e.first.size(); ++i) words[t + 2 + i] = e.first[i];
+    }
+    t += 2 + e.first.size();
+  }
+  *n_words = t;
+  return 0;
+}
+
+int gq_coverage_grouped(gq_index* ix, uint32_t* words, uint64_t* n_words) {
+  GQ_TRY
+  if (!ix || !n_words) throw std::runtime_error("null argument");
+  std::map<std::vector<uint32_t>, uint64_t> g;
+  collect_groups(ix, g, false);
+  write_groups(g, words, n_words, true);
+  GQ_CATCH
+}
+
+int gq_coverage_groups_export(gq_index* ix, uint32_t* words, uint64_t* n_words) {
+  GQ_TRY
+  if (!ix || !n_words) throw std::runtime_error("null argument");
+  std::map<std::vector<uint32_t>, uint64_t> g;
+  collect_groups(ix, g, true);
+  write_groups(g, words, n_words, false);
+  GQ_CATCH
+}
+
+int gq_coverage_groups_import(gq_index* ix, const uint32_t* words, uint64_t n_words, int replace) {
+  GQ_TRY
+  if (!ix || (n_words && !words)) throw std::runtime_error("null argument");
+  CUDA_OK(cudaSetDevice(ix->device));
+  CUDA_OK(cudaStreamSynchronize(ix->stream));
+  std::map<std::vector<uint32_t>, uint64_t> g;
+  if (!replace) collect_groups(ix, g, true);
+  for (uint64_t t = 0; t < n_words;) {
+    uint32_t n = words[t + 2];
+    std::vector<uint32_t> key{words[t]};
+    key.insert(key.end(), words + t + 3, words + t + 3 + n);
+    g[key] += words[t + 1];
+    t += 3 + n;
+  }
+  // rebuild table + pool on the host with the device's hash, then upload
+  std::vector<uint32_t> tab(ix->gtab.cap, 0), cnt(ix->gtab.cap, 0), pool;
+  uint32_t maskc = (uint32_t)ix->gtab.cap - 1;
+  for (auto& e : g) {
+    uint32_t slot = e.first[0], n = (uint32_t)e.first.size() - 1;
+    uint32_t hsh = 2166136261u ^ slot;
+    hsh *= 16777619u;
+    for (uint32_t i = 0; i < n; ++i) {
+      hsh ^= e.first[1 + i];
+      hsh *= 16777619u;
+    }
+    hsh ^= hsh >> 15;
+    hsh &= maskc;
+    while (tab[hsh]) hsh = (hsh + 1) & maskc;
+    tab[hsh] = (uint32_t)pool.size() + 1;
+    cnt[hsh] = (uint32_t)e.second;
+    pool.push_back(slot);
+    pool.push_back(n);
+    pool.insert(pool.end(), e.first.begin() + 1, e.first.end());
+  }
+  if (pool.size() > ix->gpool.cap) throw std::runtime_error("grouped allele count pool is full");
+  CUDA_OK(cudaMemcpy(ix->gtab.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(ix->gcount.p, cnt.data(), cnt.size() * 4, cudaMemcpyHostToDevice));
+  if (!pool.empty()) CUDA_OK(cudaMemcpy(ix->gpool.p, pool.data(), pool.size() * 4, cudaMemcpyHostToDevice));
+  uint32_t used = (uint32_t)pool.size();
+  CUDA_OK(cudaMemcpy(ix->gsmall.p, &used, 4, cudaMemcpyHostToDevice));
+  GQ_CATCH
+}
+
+int gq_coverage_reset(gq_index* ix) {
+  GQ_TRY
+  if (!ix) throw std::runtime_error("null argument");
+  CUDA_OK(cudaSetDevice(ix->device));
+  reset_coverage(ix);
+  GQ_CATCH
+}
+
+int gq_coverage_device_ptrs(gq_index* ix, void** counters, uint64_t* n_counters, void** stats) {
+  GQ_TRY
+  if (!ix) throw std::runtime_error("null argument");
+  if (counters) *counters = ix->counters.p;
+  if (n_counters) *n_counters = 2 * ix->n_alleles + ix->n_per_base;
+  if (stats) *stats = ix->stats.p;
+  GQ_CATCH
+}
+
+int gq_set_stream(gq_index* ix, void* cuda_stream) {
+  GQ_TRY
+  if (!ix) throw std::runtime_error("null argument");
+  ix->stream = cuda_stream ? (cudaStream_t)cuda_stream : ix->own_stream;
+  GQ_CATCH
+}
+
+int gq_set_option(gq_index* ix, const char* name, int64_t value) {
+  GQ_TRY
+  if (!ix || !name) throw std::runtime_error("null argument");
+  std::string n(name);
+  if (n == "arena_words") {
+    if (value < 32) throw std::runtime_error("arena_words must be >= 32");
+    ix->arena_words = (uint32_t)value;
+    ix->arena.release();
+  } else if (n == "threads") {
+    if (value < 256) throw std::runtime_error("threads must be >= 256");
+    ix->n_threads = (uint32_t)(value / 256 * 256);
+    ix->arena.release();
+  } else if (n == "big_arena_words") {
+    ix->big_arena_words = (uint32_t)std::max<int64_t>(value, 64);
+    ix->big_arena.release();
+  } else if (n == "big_threads") {
+    ix->big_threads = (uint32_t)std::max<int64_t>(value / 256 * 256, 256);
+    ix->big_arena.release();
+  } else if (n == "pool_words_per_read") {
+    ix->pool_words_per_read = (uint32_t)std::max<int64_t>(value, 1);
+    ix->pool.release();
+  } else if (n == "super_in_smem") {
+    ix->super_in_smem = value != 0;
+  } else
+    throw std::runtime_error("unknown option: " + n);
+  GQ_CATCH
+}
+
+int gq_last_run_info(gq_index* ix, double info[8]) {
+  GQ_TRY
+  if (!ix || !info) throw std::runtime_error("null argument");
+  for (int i = 0; i < 8; ++i) info[i] = ix->info[i];
+  GQ_CATCH
+}
+
+}  // extern "C"

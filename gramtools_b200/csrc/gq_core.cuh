@@ -1,0 +1,380 @@
+// gq_core.cuh — flat index view + the vBWT search-state machine, shared by the sm_100a kernels
+// (device) and the host-side k-mer index builder (same code, compiled for the host).
+//
+// What this replaces in the reference (libgramtools/):
+//   * rank on the DNA BWT masks         src/genotype/quasimap/search/BWT_search.cpp:8-22,45-76
+//   * marker scan of an SA interval      src/genotype/quasimap/search/vBWT_jump.cpp:94-117
+//   * site entry / exit / direct deletion / double entry / double exit jumps
+//                                        src/genotype/quasimap/search/vBWT_jump.cpp:3-92,134-265
+//   * the per-base loop                  src/genotype/quasimap/quasimap.cpp:243-268
+// The reference keeps a std::list of SearchStates and walks it breadth-first per base. States never
+// interact, so here one thread walks the same tree depth-first over a private stack of
+// variable-length entries; the multiset of final states is identical.
+#pragma once
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define GQ_HD __host__ __device__ __forceinline__
+#else
+#define GQ_HD inline
+#endif
+
+namespace gq {
+
+constexpr uint32_t kBlkShift = 6;     // 64 BWT positions per rank block
+constexpr uint32_t kSuperShift = 15;  // 32768 positions per superblock (block counts fit u16)
+constexpr uint32_t kNoAllele = 0xFFFFFFFFu;
+
+// 32-byte rank block = one DRAM/L2 sector, fetched with a single 256-bit load.
+// Symbol at position j of the block: code = p0 | p1<<1 for A,C,G,T (p2 = 0); p2 = 1 marks a
+// non-nucleotide: p0 = 1 variant marker (BWT > 4), p0 = 0 the sentinel.
+struct alignas(32) RankBlk {
+  uint64_t cnt;  // 4 x u16: A,C,G,T occurrences in [superblock start, block start)
+  uint64_t p0, p1, p2;
+};
+
+struct Node {        // flat coverage-graph node (reference: include/prg/coverage_graph.hpp:40-124)
+  uint32_t site;     // 0 outside any site
+  int32_t allele;    // -1 for bubble start/end nodes and outside sites
+  uint32_t start;    // PRG position of the first base (sequence nodes)
+  uint32_t len;      // number of bases (0 for bubble start/end/root/sink)
+  uint32_t edge_off; // into edges[]
+  uint32_t n_edges;
+  uint32_t cov_off;  // offset into the flat per-base counters; kNoAllele if the node holds none
+  uint32_t pad;
+};
+
+struct KmerState {   // one seed SearchState (reference: kmer_index_types.hpp:24-27)
+  uint32_t lo, hi;
+  uint32_t path_off; // into kmer_paths: nt (site,allele) pairs then ng site ids
+  uint32_t counts;   // nt | ng << 16
+};
+
+struct IndexView {
+  uint32_t n;  // SA size = |prg| + 1
+  const RankBlk* rank_blk;
+  const uint32_t* super_cnt;   // 4 per superblock: A,C,G,T occurrences before the superblock
+  const uint32_t* mrank_blk;   // markers in BWT[0, block start)
+  const uint32_t* marker_hit;  // 2 per BWT marker occurrence: (marker', allele); see index_build.cpp
+  uint32_t c_base[4];          // first SA index of suffixes starting with A,C,G,T
+  // per site slot s = (site_id - 5) / 2
+  uint32_t n_slots;
+  const uint32_t* site_sa;     // SA index of the suffix starting with the odd (site entry) marker
+  const uint32_t* allele_iv;   // 2 per slot: SA interval [lo,hi] of the even marker
+  const uint32_t* par;         // 2 per slot: (parent site id or 0, parent allele)
+  const uint32_t* tm_odd;      // target_map[odd marker]: id of the marker just left of the site, or 0
+  const uint32_t* tm_even_off; // CSR over target_map[even marker]
+  const uint32_t* tm_even;     // 2 per entry: (marker id, direct deletion allele)
+  // end-of-read lookups
+  const uint32_t* sa;
+  const uint32_t* pos2node;
+  const Node* nodes;
+  const uint32_t* edges;
+  // k-mer index
+  uint32_t k;
+  const uint32_t* kmer_bits;   // 4^k bits: k-mer has >= 1 state
+  const uint32_t* kmer_off;    // 4^k + 1
+  const KmerState* kmer_states;
+  const uint32_t* kmer_paths;
+};
+
+GQ_HD int popc64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+  return __popcll(x);
+#else
+  return __builtin_popcountll(x);
+#endif
+}
+
+GQ_HD RankBlk load_blk(const RankBlk* p) {
+#if defined(__CUDA_ARCH__)
+  RankBlk b;
+  // one 256-bit read-only load (LDG.E.ENL2.256 on sm_100a) = exactly one 32 B sector
+  asm("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(b.cnt), "=l"(b.p0), "=l"(b.p1), "=l"(b.p2) : "l"(p));
+  return b;
+#else
+  return *p;
+#endif
+}
+
+// occurrences of base code c (0..3) in BWT[0, i), given the block holding position i
+GQ_HD uint32_t rank_in_blk(const RankBlk& b, const uint32_t* super4, uint32_t c, uint32_t i) {
+  uint64_t m = ~b.p2 & ((c & 1) ? b.p0 : ~b.p0) & ((c & 2) ? b.p1 : ~b.p1);
+  uint32_t r = i & 63u;
+  uint64_t below = r ? (m & (~0ull >> (64 - r))) : 0ull;
+  return super4[c] + ((uint32_t)(b.cnt >> (16 * c)) & 0xFFFFu) + (uint32_t)popc64(below);
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-thread work stack. Entry = 5 header words + 2*nt words of (site, allele) + ng site ids.
+//   w0: pos (bits 0..27: index of the next read base to consume + 1, so 0 means "read finished")
+//       | kind << 28
+//   w1: lo   (JUMP: marker id)      w2: hi   (JUMP: allele)
+//   w3: nt | ng << 16               w4: start offset of the entry below (kNoAllele at the bottom)
+// ------------------------------------------------------------------------------------------
+enum : uint32_t { K_SCAN = 0, K_READY = 1, K_JUMP = 2 };
+constexpr uint32_t kHdr = 5;
+
+struct Stack {
+  uint32_t* mem;   // arena base
+  uint32_t top;    // start of the top entry, kNoAllele when empty
+  uint32_t limit;  // first word NOT usable by the stack (staging area of final states starts here)
+  bool overflow;
+};
+
+GQ_HD uint32_t entry_words(uint32_t counts) { return kHdr + 2 * (counts & 0xFFFFu) + (counts >> 16); }
+
+GQ_HD bool stack_empty(const Stack& s) { return s.top == kNoAllele; }
+
+// push a copy of the top entry's paths with a new header; returns false on overflow
+GQ_HD bool push_copy_of_top(Stack& s, uint32_t w0, uint32_t w1, uint32_t w2) {
+  uint32_t* t = s.mem + s.top;
+  uint32_t counts = t[3];
+  uint32_t words = entry_words(counts);
+  uint32_t ns = s.top + words;
+  if (ns + words + 3 > s.limit) {  // +3: room for the in-place growth of one exit on the new top
+    s.overflow = true;
+    return false;
+  }
+  uint32_t* d = s.mem + ns;
+  d[0] = w0;
+  d[1] = w1;
+  d[2] = w2;
+  d[3] = counts;
+  d[4] = s.top;
+  for (uint32_t j = kHdr; j < words; ++j) d[j] = t[j];
+  s.top = ns;
+  return true;
+}
+
+GQ_HD void pop(Stack& s) { s.top = s.mem[s.top + 4]; }
+
+// ---- jumps, applied in place to the top entry ---------------------------------------------
+// Site exit (vBWT_jump.cpp:51-92): record the allele on the innermost entered site (or open a new
+// locus if the read started inside the site) and move to the site-entry marker's SA position.
+GQ_HD bool exit_site_in_place(Stack& s, const IndexView& v, uint32_t site, uint32_t allele) {
+  uint32_t* t = s.mem + s.top;
+  uint32_t nt = t[3] & 0xFFFFu, ng = t[3] >> 16;
+  if (s.top + kHdr + 2 * nt + ng + 2 > s.limit) {
+    s.overflow = true;
+    return false;
+  }
+  uint32_t* T = t + kHdr;
+  uint32_t* G = T + 2 * nt;
+  if (ng > 0) {
+    --ng;  // G[ng] is the site being left (asserted equal in the reference, :62-64)
+    for (uint32_t j = ng; j-- > 0;) G[j + 2] = G[j];
+  }
+  T[2 * nt] = site;
+  T[2 * nt + 1] = allele;
+  ++nt;
+  t[3] = nt | (ng << 16);
+  uint32_t slot = (site - 5) >> 1;
+  t[1] = t[2] = v.site_sa[slot];
+  return true;
+}
+
+// Process a pending locus sitting on top of the stack (kind K_JUMP). Mirrors the LIFO worklist of
+// search_state_vBWT_jumps (vBWT_jump.cpp:134-183) with extend_targets_site_exit (:185-228) and
+// extend_targets_site_entry (:230-265).
+GQ_HD void process_jump(Stack& s, const IndexView& v) {
+  uint32_t* t = s.mem + s.top;
+  uint32_t pos = t[0] & 0x0FFFFFFFu;
+  uint32_t marker = t[1], allele = t[2];
+  if (marker & 1u) {  // odd: leave a site leftwards
+    uint32_t site = marker;
+    if (!exit_site_in_place(s, v, site, allele)) return;
+    while (true) {
+      uint32_t nxt = v.tm_odd[(site - 5) >> 1];
+      if (nxt == 0) {  // plain exit: commit, nothing adjacent
+        t[0] = pos | (K_READY << 28);
+        return;
+      }
+      if ((nxt & 1u) == 0) {  // exit followed by an entry: not committed, the entry is processed next
+        t[0] = pos | (K_JUMP << 28);
+        t[1] = nxt;
+        t[2] = 0;
+        return;
+      }
+      // double exit: parent's allele from par_map
+      uint32_t slot = (site - 5) >> 1;
+      uint32_t pal = v.par[2 * slot + 1];
+      if (!exit_site_in_place(s, v, nxt, pal)) return;
+      site = nxt;
+    }
+  } else {  // even: enter a site from its right end
+    uint32_t site = marker - 1;
+    uint32_t slot = (site - 5) >> 1;
+    uint32_t nt = t[3] & 0xFFFFu, ng = t[3] >> 16;
+    if (s.top + kHdr + 2 * nt + ng + 1 > s.limit) {
+      s.overflow = true;
+      return;
+    }
+    t[kHdr + 2 * nt + ng] = site;
+    ++ng;
+    t[3] = nt | (ng << 16);
+    t[0] = pos | (K_READY << 28);
+    t[1] = v.allele_iv[2 * slot];
+    t[2] = v.allele_iv[2 * slot + 1];
+    // direct deletions and double entries hang off the entered state
+    uint32_t b = v.tm_even_off[slot], e = v.tm_even_off[slot + 1];
+    uint32_t base_top = s.top;
+    for (uint32_t j = b; j < e; ++j) {
+      uint32_t id = v.tm_even[2 * j], del = v.tm_even[2 * j + 1];
+      // copies must be taken from the entered state, which is no longer the top after the 1st push
+      uint32_t save_top = s.top;
+      uint32_t* src = s.mem + base_top;
+      uint32_t counts = src[3];
+      uint32_t words = entry_words(counts);
+      uint32_t ns = save_top + entry_words(s.mem[save_top + 3]);
+      if (ns + words + 3 > s.limit) {
+        s.overflow = true;
+        return;
+      }
+      uint32_t* d = s.mem + ns;
+      d[0] = pos | (K_JUMP << 28);
+      d[1] = id;
+      d[2] = (id & 1u) ? del : kNoAllele;
+      d[3] = counts;
+      d[4] = save_top;
+      for (uint32_t w = kHdr; w < words; ++w) d[w] = src[w];
+      s.top = ns;
+    }
+  }
+}
+
+// Marker scan of the top entry's SA interval (left_markers_search, vBWT_jump.cpp:94-117): every
+// BWT marker in [lo,hi] yields one pending locus pushed as a K_JUMP copy. `blo`/`bhi` are the
+// already-fetched blocks of lo and hi+1 when they cover the interval, so the common narrow interval
+// costs no extra loads.
+GQ_HD void scan_markers(Stack& s, const IndexView& v, uint32_t pos, uint32_t lo, uint32_t hi) {
+  uint32_t base_top = s.top;
+  for (uint32_t blk = lo >> kBlkShift; blk <= (hi >> kBlkShift); ++blk) {
+    RankBlk b = load_blk(v.rank_blk + blk);
+    uint64_t m = b.p2 & b.p0;
+    uint32_t first = blk << kBlkShift;
+    if (first < lo) m &= ~0ull << (lo - first);
+    if (hi - first < 63u) m &= ~0ull >> (63u - (hi - first));
+    if (!m) continue;
+    uint64_t all = b.p2 & b.p0;
+    uint32_t mr0 = v.mrank_blk[blk];
+    while (m) {
+#if defined(__CUDA_ARCH__)
+      uint32_t bit = __ffsll((long long)m) - 1;
+#else
+      uint32_t bit = (uint32_t)__builtin_ctzll(m);
+#endif
+      m &= m - 1;
+      uint32_t mr = mr0 + (bit ? (uint32_t)popc64(all & (~0ull >> (64 - bit))) : 0u);
+      uint32_t marker = v.marker_hit[2 * mr], allele = v.marker_hit[2 * mr + 1];
+      if (marker == 0) continue;
+      // copy of the scanned state (always at base_top) with the locus in the header
+      uint32_t* src = s.mem + base_top;
+      uint32_t counts = src[3];
+      uint32_t words = entry_words(counts);
+      uint32_t ns = s.top + entry_words(s.mem[s.top + 3]);
+      if (ns + words + 3 > s.limit) {
+        s.overflow = true;
+        return;
+      }
+      uint32_t* d = s.mem + ns;
+      d[0] = pos | (K_JUMP << 28);
+      d[1] = marker;
+      d[2] = allele;
+      d[3] = counts;
+      d[4] = s.top;
+      for (uint32_t w = kHdr; w < words; ++w) d[w] = src[w];
+      s.top = ns;
+    }
+  }
+}
+
+GQ_HD uint64_t marker_bits_in(const RankBlk& b, uint32_t first, uint32_t lo, uint32_t hi) {
+  // marker bits of block [first, first+64) restricted to [lo,hi]; caller guarantees overlap
+  uint64_t m = b.p2 & b.p0;
+  if (first < lo) m &= ~0ull << (lo - first);
+  if (hi - first < 63u) m &= ~0ull >> (63u - (hi - first));
+  return m;
+}
+
+// Does BWT[lo..hi] hold any variant marker? (bwt_markers_mask test of vBWT_jump.cpp:101)
+GQ_HD bool interval_has_marker(const IndexView& v, uint32_t lo, uint32_t hi) {
+  for (uint32_t blk = lo >> kBlkShift; blk <= (hi >> kBlkShift); ++blk) {
+    RankBlk b = load_blk(v.rank_blk + blk);
+    if (marker_bits_in(b, blk << kBlkShift, lo, hi)) return true;
+  }
+  return false;
+}
+
+// ------------------------------------------------------------------------------------------
+// The depth-first driver. `read(i)` returns the base code (0..3) at index i of the strand being
+// mapped; `emit(entry)` receives a finished state (all bases consumed). One iteration = one
+// transition of the top entry:
+//   K_JUMP  : apply the pending locus (may push further entries)
+//   K_SCAN  : marker-scan the interval; markers found -> entry becomes K_READY and the loci are
+//             pushed above it; none -> consume the next base right away (the hot path: registers
+//             only, one or two 32 B sectors per base)
+//   K_READY : consume the next base without scanning (committed jump states and already-scanned
+//             states; process_read_char_search_states, quasimap.cpp:258-268)
+// ------------------------------------------------------------------------------------------
+#if defined(__CUDACC__)
+#pragma nv_exec_check_disable
+#endif
+template <class ReadFn, class EmitFn>
+GQ_HD void run_stack(Stack& s, const IndexView& v, const uint32_t* super_cnt, ReadFn& read, EmitFn& emit) {
+  while (!stack_empty(s) && !s.overflow) {
+    uint32_t* t = s.mem + s.top;
+    uint32_t w0 = t[0];
+    uint32_t kind = w0 >> 28, pos = w0 & 0x0FFFFFFFu;
+    if (kind == K_JUMP) {
+      process_jump(s, v);
+      continue;
+    }
+    if (pos == 0) {
+      emit(t);
+      pop(s);
+      continue;
+    }
+    uint32_t lo = t[1], hi = t[2];
+    bool alive = true;
+    while (true) {
+      uint32_t b0 = lo >> kBlkShift, bh = hi >> kBlkShift, b1 = (hi + 1) >> kBlkShift;
+      RankBlk B0 = load_blk(v.rank_blk + b0);
+      RankBlk B1 = (b1 == b0) ? B0 : load_blk(v.rank_blk + b1);
+      if (kind == K_SCAN) {
+        bool mk;
+        if (bh == b0) mk = marker_bits_in(B0, b0 << kBlkShift, lo, hi) != 0;
+        else if (bh == b1 && b1 == b0 + 1)
+          mk = (marker_bits_in(B0, b0 << kBlkShift, lo, hi) | marker_bits_in(B1, b1 << kBlkShift, lo, hi)) != 0;
+        else mk = interval_has_marker(v, lo, hi);
+        if (mk) {
+          t[0] = pos | (K_READY << 28);
+          t[1] = lo;
+          t[2] = hi;
+          scan_markers(s, v, pos, lo, hi);
+          break;
+        }
+      }
+      uint32_t c = read(pos - 1);
+      uint32_t r0 = rank_in_blk(B0, super_cnt + 4 * (b0 >> (kSuperShift - kBlkShift)), c, lo);
+      uint32_t r1 = rank_in_blk(B1, super_cnt + 4 * (b1 >> (kSuperShift - kBlkShift)), c, hi + 1);
+      if (r1 <= r0) {
+        alive = false;
+        break;
+      }
+      lo = v.c_base[c] + r0;
+      hi = v.c_base[c] + r1 - 1;
+      --pos;
+      kind = K_SCAN;
+      if (pos == 0) {
+        t[0] = pos | (K_SCAN << 28);
+        t[1] = lo;
+        t[2] = hi;
+        break;
+      }
+    }
+    if (!alive) pop(s);
+  }
+}
+
+}  // namespace gq

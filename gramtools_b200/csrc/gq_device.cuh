@@ -1,0 +1,673 @@
+// gq_device.cuh — per-strand device functions of the quasimap kernels (search + coverage).
+//
+// Written once with GQ_DEV so that tests/emu can compile the very same functions for the host and
+// run them single-threaded for debugging (tests only — libgq.so contains the CUDA build alone and has
+// no CPU path). Reference citations are next to each function.
+#pragma once
+#include "gq_core.cuh"
+#include "kernels.cuh"
+
+#if defined(__CUDA_ARCH__)
+#define GQ_LDG(p) __ldg(p)
+#else
+#define GQ_LDG(p) (*(p))
+#endif
+#if defined(__CUDACC__)
+#define GQ_DEV __host__ __device__
+#else
+#define GQ_DEV
+#endif
+
+namespace gq {
+
+GQ_DEV inline uint32_t gq_atomic_add(uint32_t* p, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  return atomicAdd(p, v);
+#else
+  uint32_t o = *p;
+  *p += v;
+  return o;
+#endif
+}
+GQ_DEV inline uint32_t gq_atomic_cas(uint32_t* p, uint32_t cmp, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  return atomicCAS(p, cmp, v);
+#else
+  uint32_t o = *p;
+  if (o == cmp) *p = v;
+  return o;
+#endif
+}
+GQ_DEV inline void gq_atomic_or(uint32_t* p, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  atomicOr(p, v);
+#else
+  *p |= v;
+#endif
+}
+GQ_DEV inline void gq_threadfence() {
+#if defined(__CUDA_ARCH__)
+  __threadfence();
+#endif
+}
+
+// Strand cursor: base code i of the strand (forward, or reverse complement of the stored read;
+// reverse_complement_read, quasimap.cpp:273-298) with the current packed word cached in a register.
+struct ReadCursor {
+  const uint32_t* w;
+  uint32_t L;
+  bool rc;
+  uint32_t cw_idx, cw;
+  GQ_DEV inline uint32_t operator()(uint32_t i) {
+    uint32_t phys = rc ? (L - 1 - i) : i;
+    uint32_t wi = phys >> 4;
+    if (wi != cw_idx) {
+      cw = GQ_LDG(w + wi);
+      cw_idx = wi;
+    }
+    uint32_t c = (cw >> ((phys & 15u) * 2)) & 3u;
+    return rc ? 3u - c : c;
+  }
+};
+
+// Finished states are staged at the top of the thread's arena (growing down) as
+// [lo, hi, nt, ng, (site,allele)*nt, (site,-1)*ng]. Path-less states are split per SA index by the
+// site/allele of the node they start in (handle_allele_encapsulated_state,
+// encapsulated_search.cpp:30-88).
+struct EmitStage {
+  Stack* s;
+  const IndexView* v;
+  uint32_t n_states;
+
+  GQ_DEV inline bool reserve(uint32_t words, uint32_t*& dst) {
+    uint32_t top_end = s->top + entry_words(s->mem[s->top + 3]);
+    if (top_end + words > s->limit) {
+      s->overflow = true;
+      return false;
+    }
+    s->limit -= words;
+    dst = s->mem + s->limit;
+    return true;
+  }
+  GQ_DEV inline void put(uint32_t lo, uint32_t hi, uint32_t site, uint32_t allele, bool with_path) {
+    uint32_t* d;
+    if (!reserve(with_path ? 6 : 4, d)) return;
+    d[0] = lo;
+    d[1] = hi;
+    d[2] = with_path ? 1u : 0u;
+    d[3] = 0;
+    if (with_path) {
+      d[4] = site;
+      d[5] = allele;
+    }
+    ++n_states;
+  }
+  GQ_DEV void operator()(const uint32_t* t) {
+    uint32_t lo = t[1], hi = t[2], nt = t[3] & 0xFFFFu, ng = t[3] >> 16;
+    if (nt | ng) {
+      uint32_t* d;
+      if (!reserve(4 + 2 * nt + 2 * ng, d)) return;
+      d[0] = lo;
+      d[1] = hi;
+      d[2] = nt;
+      d[3] = ng;
+      const uint32_t* T = t + kHdr;
+      for (uint32_t j = 0; j < 2 * nt; ++j) d[4 + j] = T[j];
+      const uint32_t* G = T + 2 * nt;
+      for (uint32_t j = 0; j < ng; ++j) {
+        d[4 + 2 * nt + 2 * j] = G[j];
+        d[4 + 2 * nt + 2 * j + 1] = kNoAllele;
+      }
+      ++n_states;
+      return;
+    }
+    bool cached = false;
+    uint32_t c_lo = 0, c_hi = 0, c_site = 0, c_al = 0;
+    for (uint32_t i = lo;; ++i) {
+      uint32_t p = GQ_LDG(v->sa + i);
+      const Node& nd = v->nodes[GQ_LDG(v->pos2node + p)];
+      uint32_t site = nd.site, al = (uint32_t)nd.allele;
+      if (site == 0) {
+        if (cached) put(c_lo, c_hi, c_site, c_al, true);
+        cached = false;
+        put(i, i, 0, 0, false);
+      } else if (!cached) {
+        cached = true;
+        c_lo = c_hi = i;
+        c_site = site;
+        c_al = al;
+      } else if (site == c_site && al == c_al) {
+        c_hi = i;
+      } else {
+        put(c_lo, c_hi, c_site, c_al, true);
+        c_lo = c_hi = i;
+        c_site = site;
+        c_al = al;
+      }
+      if (s->overflow || i == hi) break;
+    }
+    if (cached) put(c_lo, c_hi, c_site, c_al, true);
+  }
+};
+
+GQ_DEV void map_strand(const IndexView& v, const uint32_t* super_cnt, const BatchView& b, const SearchOut& o,
+                           uint32_t strand, uint32_t* arena, uint32_t arena_words) {
+  const uint32_t r = strand >> 1;
+  const uint32_t L = b.len[r];
+  const uint32_t k = v.k;
+  if (L == 0) {  // non-ACGT read, emptied by the encoder: skipped (quasimap.cpp:108-113)
+    o.status[strand] = ST_SKIPPED;
+    o.st_count[strand] = 0;
+    return;
+  }
+  ReadCursor rd{b.packed + b.word_off[r], L, (strand & 1u) != 0, 0xFFFFFFFFu, 0};
+  o.st_count[strand] = 0;
+  o.st_words[strand] = 0;
+  // all_read_kmers_occur_in_index (quasimap.cpp:212-225); reads shorter than k cannot be seeded
+  if (L < k) {
+    o.status[strand] = ST_MISSING_KMER;
+    return;
+  }
+  const uint32_t mask = (k == 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
+  uint32_t code = 0;
+  bool missing = false;
+  for (uint32_t i = 0; i < L; ++i) {
+    code = ((code << 2) | rd(i)) & mask;
+    if (i + 1 >= k && !((GQ_LDG(v.kmer_bits + (code >> 5)) >> (code & 31u)) & 1u)) {
+      missing = true;
+      break;
+    }
+  }
+  if (missing) {
+    o.status[strand] = ST_MISSING_KMER;
+    return;
+  }
+  // seed with the index entry of the last k-mer (quasimap.cpp:178,235-241)
+  Stack s;
+  s.mem = arena;
+  s.limit = arena_words;
+  s.overflow = false;
+  s.top = kNoAllele;
+  uint32_t sb = GQ_LDG(v.kmer_off + code), se = GQ_LDG(v.kmer_off + code + 1);
+  uint32_t sp = 0;
+  for (uint32_t j = sb; j < se; ++j) {
+    KmerState ks = v.kmer_states[j];
+    uint32_t words = entry_words(ks.counts);
+    if (sp + words + 3 > s.limit) {
+      s.overflow = true;
+      break;
+    }
+    uint32_t* t = s.mem + sp;
+    t[0] = (L - k) | (K_SCAN << 28);
+    t[1] = ks.lo;
+    t[2] = ks.hi;
+    t[3] = ks.counts;
+    t[4] = s.top;
+    for (uint32_t w = kHdr; w < words; ++w) t[w] = GQ_LDG(v.kmer_paths + ks.path_off + (w - kHdr));
+    s.top = sp;
+    sp += words;
+  }
+  EmitStage emit{&s, &v, 0};
+  if (!s.overflow) run_stack(s, v, super_cnt, rd, emit);
+  uint32_t words = arena_words - s.limit;
+  if (!s.overflow && words) {
+    uint32_t off = gq_atomic_add(o.pool_used, words);
+    if (off + words > o.pool_cap) s.overflow = true;
+    else {
+      for (uint32_t w = 0; w < words; ++w) o.pool[off + w] = s.mem[s.limit + w];
+      o.st_off[strand] = off;
+      o.st_words[strand] = words;
+      o.st_count[strand] = emit.n_states;
+    }
+  }
+  if (s.overflow) {
+    o.status[strand] = ST_OVERFLOW;
+    o.overflow_list[gq_atomic_add(o.n_overflow, 1u)] = strand;
+    return;
+  }
+  o.status[strand] = emit.n_states ? ST_MAPPED : ST_NO_EXTENSION;
+}
+
+struct Scratch {
+  uint32_t* mem;
+  uint32_t used, cap;
+  bool overflow;
+  GQ_DEV inline uint32_t* alloc(uint32_t words) {
+    if (used + words > cap) {
+      overflow = true;
+      return nullptr;
+    }
+    uint32_t* p = mem + used;
+    used += words;
+    return p;
+  }
+};
+
+// std::mt19937 seeded with `seed`: j-th raw output (j < 227), from the init LCG alone
+// (reference: RandomInclusiveInt, src/common/random.cpp:4-19).
+GQ_DEV uint32_t mt19937_output(uint32_t seed, uint32_t j) {
+  uint32_t x = seed, mj = 0, mj1 = 0, mj397 = 0;
+  for (uint32_t i = 0;; ++i) {
+    if (i == j) mj = x;
+    if (i == j + 1) mj1 = x;
+    if (i == j + 397) {
+      mj397 = x;
+      break;
+    }
+    x = 1812433253u * (x ^ (x >> 30)) + (i + 1);
+  }
+  uint32_t y = (mj & 0x80000000u) | (mj1 & 0x7FFFFFFFu);
+  uint32_t z = mj397 ^ (y >> 1) ^ ((y & 1u) ? 0x9908B0DFu : 0u);
+  z ^= z >> 11;
+  z ^= (z << 7) & 0x9D2C5680u;
+  z ^= (z << 15) & 0xEFC60000u;
+  z ^= z >> 18;
+  return z;
+}
+
+// std::uniform_int_distribution<uint32_t>(1, range)(mt19937(seed)) as libstdc++ 13 computes it
+// (Lemire's multiply-shift with rejection, bits/uniform_int_dist.h `_S_nd`).
+GQ_DEV uint32_t uniform_1_to(uint32_t seed, uint32_t range) {
+  uint32_t j = 0;
+  uint64_t product = (uint64_t)mt19937_output(seed, j) * (uint64_t)range;
+  uint32_t low = (uint32_t)product;
+  if (low < range) {
+    uint32_t threshold = (0u - range) % range;
+    while (low < threshold && j < 200) {
+      ++j;
+      product = (uint64_t)mt19937_output(seed, j) * (uint64_t)range;
+      low = (uint32_t)product;
+    }
+  }
+  return (uint32_t)(product >> 32) + 1u;
+}
+
+struct StateRec {
+  uint32_t lo, hi, nt, ng;
+  const uint32_t* T;  // nt pairs
+  const uint32_t* G;  // ng pairs (site, -1)
+  GQ_DEV inline uint32_t words() const { return 4 + 2 * nt + 2 * ng; }
+};
+GQ_DEV inline StateRec parse_rec(const uint32_t* p) {
+  StateRec r{p[0], p[1], p[2], p[3], p + 4, p + 4 + 2 * p[2]};
+  return r;
+}
+
+// LocusFinder (coverage_common.cpp:10-83). Appends to `loci` (pairs, deduplicated) and `base`
+// (level-0 sites, deduplicated); `used` is per-state scratch.
+struct LocusLists {
+  uint32_t *loci, *base, *used;
+  uint32_t n_loci, n_base, n_used, cap;
+  bool overflow;
+};
+GQ_DEV void add_locus(LocusLists& l, uint32_t site, uint32_t allele) {
+  for (uint32_t i = 0; i < l.n_loci; ++i)
+    if (l.loci[2 * i] == site && l.loci[2 * i + 1] == allele) return;
+  if (l.n_loci >= l.cap) {
+    l.overflow = true;
+    return;
+  }
+  l.loci[2 * l.n_loci] = site;
+  l.loci[2 * l.n_loci + 1] = allele;
+  ++l.n_loci;
+}
+GQ_DEV void assign_nested(const IndexView& v, LocusLists& l, uint32_t site, uint32_t allele) {
+  while (true) {
+    for (uint32_t i = 0; i < l.n_used; ++i)
+      if (l.used[i] == site) return;
+    if (l.n_used >= l.cap || l.n_base >= l.cap) {
+      l.overflow = true;
+      return;
+    }
+    l.used[l.n_used++] = site;
+    add_locus(l, site, allele);
+    uint32_t slot = (site - 5) >> 1;
+    uint32_t ps = v.par[2 * slot];
+    if (ps == 0) {
+      bool seen = false;
+      for (uint32_t i = 0; i < l.n_base; ++i) seen |= l.base[i] == site;
+      if (!seen) l.base[l.n_base++] = site;
+      return;
+    }
+    allele = v.par[2 * slot + 1];
+    site = ps;
+  }
+}
+GQ_DEV void locus_finder(const IndexView& v, const StateRec& st, LocusLists& l) {
+  l.n_used = 0;
+  if (st.ng > 0) {  // assign_traversing_loci :52-74
+    uint32_t seed_site = st.G[2 * (st.ng - 1)];
+    uint32_t last_al = 0;
+    for (uint32_t i = st.lo;; ++i) {
+      uint32_t p = GQ_LDG(v.sa + i);
+      last_al = (uint32_t)v.nodes[GQ_LDG(v.pos2node + p)].allele;
+      add_locus(l, seed_site, last_al);
+      if (i == st.hi) break;
+    }
+    assign_nested(v, l, seed_site, last_al);
+  }
+  for (uint32_t j = 0; j < st.nt; ++j) assign_nested(v, l, st.T[2 * j], st.T[2 * j + 1]);  // :76-83
+}
+
+GQ_DEV void sort_u32(uint32_t* a, uint32_t n) {
+  for (uint32_t i = 1; i < n; ++i) {
+    uint32_t x = a[i], j = i;
+    while (j > 0 && a[j - 1] > x) {
+      a[j] = a[j - 1];
+      --j;
+    }
+    a[j] = x;
+  }
+}
+// lexicographic compare of two sorted site sets (std::set<Marker> ordering inside std::map)
+GQ_DEV int cmp_key(const uint32_t* a, uint32_t na, const uint32_t* b, uint32_t nb) {
+  uint32_t n = na < nb ? na : nb;
+  for (uint32_t i = 0; i < n; ++i) {
+    if (a[i] != b[i]) return a[i] < b[i] ? -1 : 1;
+  }
+  return na == nb ? 0 : (na < nb ? -1 : 1);
+}
+
+// Traverser (allele_base.cpp:137-219) over the flat graph.
+struct Trav {
+  const IndexView* v;
+  uint32_t cur;  // node id, kNoAllele = null
+  uint32_t remaining;
+  const uint32_t* T;
+  uint32_t ti;
+  bool first;
+  uint32_t start_pos, end_pos;
+  bool bad;
+  GQ_DEV inline const Node& node() const { return v->nodes[cur]; }
+  GQ_DEV void update_coordinates() {
+    const Node& nd = node();
+    end_pos = 0;
+    if (nd.len > 0) {
+      uint32_t a = nd.len - 1, bnd = start_pos + remaining - 1;
+      end_pos = a < bnd ? a : bnd;
+      remaining -= (end_pos - start_pos + 1);
+    }
+  }
+  GQ_DEV void go_to_next_site() {
+    start_pos = 0;
+    while (node().n_edges == 1) {
+      if (remaining == 0) {
+        cur = kNoAllele;
+        return;
+      }
+      cur = v->edges[node().edge_off];
+      update_coordinates();
+      const Node& nd = node();
+      if (nd.allele != -1 && nd.site != 0) return;
+    }
+    if (ti == 0 || node().n_edges == 0) {
+      bad = true;
+      cur = kNoAllele;
+      return;
+    }
+    --ti;
+    uint32_t allele = T[2 * ti + 1];
+    if (allele >= node().n_edges) {
+      bad = true;
+      cur = kNoAllele;
+      return;
+    }
+    cur = v->edges[node().edge_off + allele];
+    update_coordinates();
+  }
+  // returns false when the traversal is over
+  GQ_DEV bool next() {
+    if (first) {
+      first = false;
+      update_coordinates();
+      const Node& nd = node();
+      if (!(nd.allele != -1 && nd.site != 0)) go_to_next_site();
+      return cur != kNoAllele;
+    }
+    if (remaining == 0) return false;
+    go_to_next_site();
+    return cur != kNoAllele;
+  }
+};
+
+struct Hull {
+  uint32_t* e;  // triples (node, start, end)
+  uint32_t n, cap;
+  bool overflow;
+};
+GQ_DEV void hull_add(const IndexView& v, Hull& h, uint32_t node, uint32_t s, uint32_t e) {
+  if (v.nodes[node].len == 0) return;  // process_Node :282-287
+  for (uint32_t i = 0; i < h.n; ++i) {
+    if (h.e[3 * i] == node) {
+      if (s < h.e[3 * i + 1]) h.e[3 * i + 1] = s;
+      if (e > h.e[3 * i + 2]) h.e[3 * i + 2] = e;
+      return;
+    }
+  }
+  if (h.n >= h.cap) {
+    h.overflow = true;
+    return;
+  }
+  h.e[3 * h.n] = node;
+  h.e[3 * h.n + 1] = s;
+  h.e[3 * h.n + 2] = e;
+  ++h.n;
+}
+
+GQ_DEV uint32_t hash_group(uint32_t slot, const uint32_t* loci, uint32_t n) {
+  uint32_t h = 2166136261u ^ slot;
+  h *= 16777619u;
+  for (uint32_t i = 0; i < n; ++i) {
+    h ^= loci[2 * i + 1];
+    h *= 16777619u;
+  }
+  h ^= h >> 15;
+  return h;
+}
+
+// multi-allele group of one site: find-or-insert in the open-addressing table, then count
+GQ_DEV void grouped_insert(const CoverageView& c, uint32_t slot, const uint32_t* loci, uint32_t n) {
+  uint32_t maskc = c.gtab_cap - 1;
+  uint32_t h = hash_group(slot, loci, n) & maskc;
+  uint32_t mine = 0;  // offset + 1 of a record this thread allocated (lazily)
+  for (uint32_t probe = 0; probe < c.gtab_cap; ++probe, h = (h + 1) & maskc) {
+    uint32_t cur = gq_atomic_add(c.gtab + h, 0u);
+    if (cur == 0) {
+      if (!mine) {
+        uint32_t off = gq_atomic_add(c.gpool_used, n + 2);
+        if (off + n + 2 > c.gpool_cap) {
+          gq_atomic_or(c.error_flags, 1u);
+          return;
+        }
+        c.gpool[off] = slot;
+        c.gpool[off + 1] = n;
+        for (uint32_t i = 0; i < n; ++i) c.gpool[off + 2 + i] = loci[2 * i + 1];
+        gq_threadfence();
+        mine = off + 1;
+      }
+      cur = gq_atomic_cas(c.gtab + h, 0u, mine);
+      if (cur == 0) {
+        gq_atomic_add(c.gcount + h, 1u);
+        return;
+      }
+    }
+    // occupied: same key?
+    const volatile uint32_t* rec = c.gpool + (cur - 1);
+    bool same = rec[0] == slot && rec[1] == n;
+    for (uint32_t i = 0; same && i < n; ++i) same = rec[2 + i] == loci[2 * i + 1];
+    if (same) {
+      gq_atomic_add(c.gcount + h, 1u);
+      return;
+    }
+  }
+  gq_atomic_or(c.error_flags, 1u);
+}
+
+GQ_DEV bool record_strand(const IndexView& v, const BatchView& b, const SearchOut& o, const CoverageView& c,
+                              uint32_t strand, uint32_t* arena, uint32_t arena_words) {
+  const uint32_t ns = o.st_count[strand];
+  const uint32_t* recs = o.pool + o.st_off[strand];
+  const uint32_t L = b.len[strand >> 1];
+  Scratch sc{arena, 0, arena_words, false};
+
+  // ---- pass 1: non-variant mapping count, per-state class keys (MappingInstanceSelector) ----
+  uint32_t nonvar = 0, npath = 0;
+  {
+    const uint32_t* p = recs;
+    for (uint32_t j = 0; j < ns; ++j) {
+      StateRec st = parse_rec(p);
+      p += st.words();
+      if (st.nt | st.ng) ++npath;
+      else nonvar += st.hi - st.lo + 1;  // count_nonvar_search_states :137-148
+    }
+  }
+  if (npath == 0) return true;
+  // single pathful state and nothing else: one class, generate(1,1) == 1 -> skip the key machinery
+  uint32_t* key_off = sc.alloc(2 * ns);  // (offset, len) per state; len = 0xFFFFFFFF for path-less
+  if (!key_off) return false;
+  const uint32_t cap = (arena_words - sc.used) / 16;  // list capacities derive from the arena size
+  LocusLists ll;
+  ll.cap = cap;
+  ll.overflow = false;
+  ll.used = sc.alloc(cap);
+  ll.base = sc.alloc(cap);
+  ll.loci = sc.alloc(2 * cap);
+  if (sc.overflow) return false;
+  {
+    const uint32_t* p = recs;
+    for (uint32_t j = 0; j < ns; ++j) {
+      StateRec st = parse_rec(p);
+      p += st.words();
+      if (!(st.nt | st.ng)) {
+        key_off[2 * j] = 0;
+        key_off[2 * j + 1] = 0xFFFFFFFFu;
+        continue;
+      }
+      ll.n_loci = ll.n_base = 0;
+      locus_finder(v, st, ll);
+      if (ll.overflow) return false;
+      sort_u32(ll.base, ll.n_base);
+      uint32_t* k = sc.alloc(ll.n_base);
+      if (!k && ll.n_base) return false;
+      for (uint32_t i = 0; i < ll.n_base; ++i) k[i] = ll.base[i];
+      key_off[2 * j] = (uint32_t)(k - arena);
+      key_off[2 * j + 1] = ll.n_base;
+    }
+  }
+  // number of distinct classes, and for the first state of each class its rank among classes
+  uint32_t ncls = 0;
+  for (uint32_t j = 0; j < ns; ++j) {
+    if (key_off[2 * j + 1] == 0xFFFFFFFFu) continue;
+    bool dup = false;
+    for (uint32_t i = 0; i < j && !dup; ++i)
+      dup = key_off[2 * i + 1] != 0xFFFFFFFFu && cmp_key(arena + key_off[2 * i], key_off[2 * i + 1],
+                                                          arena + key_off[2 * j], key_off[2 * j + 1]) == 0;
+    if (!dup) ++ncls;
+  }
+  // random_select_entry :97-107
+  uint32_t total = nonvar + ncls;
+  uint32_t pick = total == 1 ? 1u : uniform_1_to(b.seeds[strand >> 1], total);
+  if (pick <= nonvar) return true;
+  uint32_t want = pick - nonvar - 1;
+  int chosen = -1;
+  for (uint32_t j = 0; j < ns && chosen < 0; ++j) {
+    if (key_off[2 * j + 1] == 0xFFFFFFFFu) continue;
+    bool dup = false;
+    uint32_t less = 0;
+    for (uint32_t i = 0; i < ns; ++i) {
+      if (i == j || key_off[2 * i + 1] == 0xFFFFFFFFu) continue;
+      int cm = cmp_key(arena + key_off[2 * i], key_off[2 * i + 1], arena + key_off[2 * j], key_off[2 * j + 1]);
+      if (cm == 0 && i < j) dup = true;
+      if (cm < 0) {  // count distinct smaller keys: only the first occurrence of each
+        bool first_occ = true;
+        for (uint32_t h = 0; h < i && first_occ; ++h)
+          first_occ = !(key_off[2 * h + 1] != 0xFFFFFFFFu &&
+                        cmp_key(arena + key_off[2 * h], key_off[2 * h + 1], arena + key_off[2 * i], key_off[2 * i + 1]) == 0);
+        if (first_occ) ++less;
+      }
+    }
+    if (!dup && less == want) chosen = (int)j;
+  }
+  if (chosen < 0) {
+    gq_atomic_or(c.error_flags, 2u);
+    return true;
+  }
+  // ---- pass 2: loci of the chosen class + per-node hulls (PbCovRecorder :221-296) ----
+  ll.n_loci = 0;
+  Hull hull;
+  hull.cap = (arena_words - sc.used) / 3;
+  hull.e = arena + sc.used;
+  hull.n = 0;
+  hull.overflow = false;
+  const uint32_t* ck = arena + key_off[2 * chosen];
+  const uint32_t cn = key_off[2 * chosen + 1];
+  {
+    const uint32_t* p = recs;
+    for (uint32_t j = 0; j < ns; ++j) {
+      StateRec st = parse_rec(p);
+      p += st.words();
+      if (key_off[2 * j + 1] == 0xFFFFFFFFu) continue;
+      if (cmp_key(arena + key_off[2 * j], key_off[2 * j + 1], ck, cn) != 0) continue;
+      ll.n_base = 0;
+      locus_finder(v, st, ll);  // loci accumulate across the class (set union)
+      if (ll.overflow) return false;
+      bool first = true;
+      for (uint32_t occ = st.lo;; ++occ) {
+        uint32_t pos = GQ_LDG(v.sa + occ);
+        uint32_t nid = GQ_LDG(v.pos2node + pos);
+        Trav t;
+        t.v = &v;
+        t.cur = nid;
+        t.remaining = L;
+        t.T = st.T;
+        t.ti = st.nt;
+        t.first = true;
+        const Node& nd = v.nodes[nid];
+        t.start_pos = nd.len > 1 ? pos - nd.start : 0;  // setup_random_access, coverage_graph.cpp:131-144
+        t.end_pos = 0;
+        t.bad = false;
+        if (first) {
+          first = false;
+          while (t.next()) hull_add(v, hull, t.cur, t.start_pos, t.end_pos);
+        } else if (t.next())
+          hull_add(v, hull, t.cur, t.start_pos, t.end_pos);
+        if (t.bad) gq_atomic_or(c.error_flags, 2u);
+        if (hull.overflow) return false;
+        if (occ == st.hi) break;
+      }
+    }
+  }
+  // ---- commit (nothing above touched the counters, so an overflow re-run cannot double count) ----
+  // sort loci by (site, allele) — std::set<VariantLocus> order
+  for (uint32_t i = 1; i < ll.n_loci; ++i) {
+    uint32_t s0 = ll.loci[2 * i], a0 = ll.loci[2 * i + 1], j = i;
+    while (j > 0 && (ll.loci[2 * (j - 1)] > s0 ||
+                     (ll.loci[2 * (j - 1)] == s0 && (int32_t)ll.loci[2 * (j - 1) + 1] > (int32_t)a0))) {
+      ll.loci[2 * j] = ll.loci[2 * (j - 1)];
+      ll.loci[2 * j + 1] = ll.loci[2 * (j - 1) + 1];
+      --j;
+    }
+    ll.loci[2 * j] = s0;
+    ll.loci[2 * j + 1] = a0;
+  }
+  for (uint32_t i = 0; i < ll.n_loci;) {
+    uint32_t site = ll.loci[2 * i], slot = (site - 5) >> 1;
+    uint32_t e = i;
+    while (e < ll.n_loci && ll.loci[2 * e] == site) {
+      gq_atomic_add(c.allele_sum + c.allele_off[slot] + ll.loci[2 * e + 1], 1u);  // allele_sum.cpp:31-43
+      ++e;
+    }
+    if (e - i == 1) gq_atomic_add(c.grouped_single + c.allele_off[slot] + ll.loci[2 * i + 1], 1u);
+    else grouped_insert(c, slot, ll.loci + 2 * i, e - i);  // grouped_allele_counts.cpp:17-49
+    i = e;
+  }
+  for (uint32_t i = 0; i < hull.n; ++i) {
+    const Node& nd = v.nodes[hull.e[3 * i]];
+    if (nd.cov_off == kNoAllele) continue;
+    for (uint32_t x = hull.e[3 * i + 1]; x <= hull.e[3 * i + 2]; ++x) gq_atomic_add(c.per_base + nd.cov_off + x, 1u);
+  }
+  return true;
+}
+
+
+}  // namespace gq

@@ -1,0 +1,508 @@
+// index_build.cpp — see index_build.hpp. Host-only; compiled with the rest of libgq.so.
+#include "index_build.hpp"
+
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <stdexcept>
+#include <string>
+
+#include "sais.hpp"
+
+namespace gq {
+
+IndexView HostIndex::view() const {
+  IndexView v{};
+  v.n = n;
+  v.rank_blk = rank_blk.data();
+  v.super_cnt = super_cnt.data();
+  v.mrank_blk = mrank_blk.data();
+  v.marker_hit = marker_hit.data();
+  for (int i = 0; i < 4; ++i) v.c_base[i] = c_base[i];
+  v.n_slots = n_slots;
+  v.site_sa = site_sa.data();
+  v.allele_iv = allele_iv.data();
+  v.par = par.data();
+  v.tm_odd = tm_odd.data();
+  v.tm_even_off = tm_even_off.data();
+  v.tm_even = tm_even.data();
+  v.sa = sa.data();
+  v.pos2node = pos2node.data();
+  v.nodes = nodes.data();
+  v.edges = edges.data();
+  v.k = k;
+  v.kmer_bits = kmer_bits.data();
+  v.kmer_off = kmer_off.data();
+  v.kmer_states = kmer_states.data();
+  v.kmer_paths = kmer_paths.data();
+  return v;
+}
+
+namespace {
+
+struct OpenSite {
+  uint32_t site;
+  uint32_t allele;
+};
+
+// One left-to-right pass over the PRG builds the flat graph, the parent map, both target maps and
+// the per-position marker targets. Reference semantics: cov_Graph_Builder
+// (libgramtools/src/prg/coverage_graph.cpp:82-379); see SURVEY.md Appendix A for the derivations.
+void build_graph(HostIndex& ix, std::vector<uint32_t>& hit_marker, std::vector<uint32_t>& hit_allele) {
+  const auto& prg = ix.prg;
+  const uint32_t L = (uint32_t)prg.size();
+  uint32_t maxm = 4;
+  for (auto m : prg) {
+    if (m < 1) throw std::runtime_error("PRG symbols must be >= 1");
+    maxm = std::max(maxm, m);
+  }
+  ix.n_slots = maxm > 4 ? ((maxm % 2 ? maxm : maxm - 1) - 5) / 2 + 1 : 0;
+  const uint32_t S = ix.n_slots;
+  // final (site end) position of every even marker; duplicate site-entry markers are an error
+  std::vector<uint32_t> last_pos(S, 0xFFFFFFFFu);
+  std::vector<uint8_t> seen(S, 0);
+  for (uint32_t p = 0; p < L; ++p) {
+    uint32_t m = prg[p];
+    if (m <= 4) continue;
+    if (m & 1u) {
+      uint32_t s = (m - 5) / 2;
+      if (seen[s])
+        throw std::runtime_error("PRG consistency error: site marker " + std::to_string(m) +
+                                 " used for two different sites");
+      seen[s] = 1;
+    } else {
+      if (m < 6) throw std::runtime_error("invalid marker");
+      last_pos[(m - 6) / 2] = p;
+    }
+  }
+  ix.n_sites = 0;
+  for (uint32_t s = 0; s < S; ++s) {
+    if (seen[s] && last_pos[s] == 0xFFFFFFFFu)
+      throw std::runtime_error("PRG consistency error: site " + std::to_string(5 + 2 * s) + " is never closed");
+    if (!seen[s] && last_pos[s] != 0xFFFFFFFFu)
+      throw std::runtime_error("PRG consistency error: allele marker without its site marker");
+    ix.n_sites += seen[s];
+  }
+
+  ix.par.assign(2 * (size_t)S, 0);
+  ix.tm_odd.assign(S, 0);
+  ix.n_alleles.assign(S, 0);
+  ix.site_start_node.assign(S, 0);
+  std::vector<std::vector<uint32_t>> tm_even(S);
+  ix.pos2node.assign(L, 0);
+  hit_marker.assign(L, 0);
+  hit_allele.assign(L, 0);
+  std::vector<uint32_t> site_end_node(S, 0);
+
+  // adjacency lists are built as (from,to) pairs in wiring order, then bucketed into CSR; the
+  // bubble-start node of a site receives exactly one edge per allele, in allele order.
+  std::vector<std::pair<uint32_t, uint32_t>> wires;
+  wires.reserve(L / 2 + 16);
+  auto new_node = [&](uint32_t site, int32_t allele, uint32_t start) {
+    Node nd{};
+    nd.site = site;
+    nd.allele = allele;
+    nd.start = start;
+    nd.len = 0;
+    nd.cov_off = kNoAllele;
+    ix.nodes.push_back(nd);
+    return (uint32_t)ix.nodes.size() - 1;
+  };
+  ix.nodes.clear();
+  uint32_t back = new_node(0, -1, 0);  // root
+  int64_t run = -1;                    // open sequence node
+  std::vector<OpenSite> open;
+  auto wire = [&](uint32_t target) {  // coverage_graph.cpp:260-266
+    if (run >= 0) {
+      wires.emplace_back(back, (uint32_t)run);
+      wires.emplace_back((uint32_t)run, target);
+    } else
+      wires.emplace_back(back, target);
+    run = -1;
+  };
+  enum { T_SEQ, T_ENTRY, T_ALLELE_END, T_SITE_END };
+  int prev_t = T_SEQ;
+  uint32_t prev_m = 0;
+  uint32_t n_per_base = 0;
+  for (uint32_t p = 0; p < L; ++p) {
+    uint32_t m = prg[p];
+    int t;
+    if (m <= 4) t = T_SEQ;
+    else if (m & 1u) t = T_ENTRY;
+    else t = (p < last_pos[(m - 6) / 2]) ? T_ALLELE_END : T_SITE_END;
+    const uint32_t cur_allele = open.empty() ? kNoAllele : open.back().allele;  // before this symbol
+    switch (t) {
+      case T_SEQ: {
+        if (run < 0) {
+          uint32_t site = open.empty() ? 0 : open.back().site;
+          int32_t allele = open.empty() ? -1 : (int32_t)open.back().allele;
+          run = new_node(site, allele, p);
+          if (site != 0) ix.nodes[run].cov_off = n_per_base;
+        }
+        ix.nodes[run].len++;
+        if (ix.nodes[run].cov_off != kNoAllele) n_per_base++;
+        ix.pos2node[p] = (uint32_t)run;
+        if (prev_t != T_SEQ) {  // map_targets, sequence case (:281-286) + left_markers_search conversion
+          if (prev_t == T_ALLELE_END) {
+            hit_marker[p] = prev_m - 1;  // an allele separator: leaving the site through this allele
+            hit_allele[p] = cur_allele;
+          } else {
+            hit_marker[p] = prev_m;  // odd: leave through allele 0; even (site end): enter the site
+            hit_allele[p] = cur_allele;
+          }
+        }
+        break;
+      }
+      case T_ENTRY: {
+        uint32_t s = (m - 5) / 2;
+        uint32_t sn = new_node(m, -1, p), en = new_node(m, -1, p);
+        ix.site_start_node[s] = sn;
+        site_end_node[s] = en;
+        wire(sn);
+        back = sn;
+        if (!open.empty()) {
+          ix.par[2 * s] = open.back().site;
+          ix.par[2 * s + 1] = open.back().allele;
+          ix.is_nested = true;
+        }
+        if (prev_t != T_SEQ)  // make_site_entry_target :313-328
+          ix.tm_odd[s] = (prev_t == T_ALLELE_END) ? prev_m - 1 : prev_m;
+        open.push_back({m, 0});
+        ix.pos2node[p] = sn;
+        break;
+      }
+      case T_ALLELE_END:
+      case T_SITE_END: {
+        uint32_t s = (m - 6) / 2;
+        if (open.empty() || open.back().site != m - 1)
+          throw std::runtime_error("PRG consistency error: allele marker " + std::to_string(m) +
+                                   " outside its site");
+        if (prev_t != T_SEQ) {
+          if (t == T_SITE_END) {  // make_site_exit_target :330-350
+            if (prev_t == T_ENTRY)
+              throw std::runtime_error("PRG consistency error: site number " + std::to_string(m) + " is empty");
+            if (prev_t == T_SITE_END) {
+              tm_even[s].push_back(prev_m);
+              tm_even[s].push_back(kNoAllele);
+            } else {
+              tm_even[s].push_back(prev_m - 1);
+              tm_even[s].push_back(cur_allele);
+            }
+          } else {  // make_allele_end_target :352-370
+            if (prev_t == T_ENTRY) {
+              tm_even[s].push_back(prev_m);
+              tm_even[s].push_back(cur_allele);
+            } else if (prev_t == T_SITE_END) {
+              tm_even[s].push_back(prev_m);
+              tm_even[s].push_back(kNoAllele);
+            } else {
+              tm_even[s].push_back(prev_m - 1);
+              tm_even[s].push_back(cur_allele);
+            }
+          }
+        }
+        wire(site_end_node[s]);
+        if (t == T_ALLELE_END) {
+          back = ix.site_start_node[s];
+          open.back().allele++;
+          ix.pos2node[p] = ix.site_start_node[s];
+        } else {
+          if (open.back().allele == 0)
+            throw std::runtime_error("Site numbered " + std::to_string(m) + " has only one allele");
+          ix.n_alleles[s] = open.back().allele + 1;
+          open.pop_back();
+          back = site_end_node[s];
+          ix.pos2node[p] = site_end_node[s];
+        }
+        break;
+      }
+    }
+    prev_t = t;
+    prev_m = m;
+  }
+  if (!open.empty()) throw std::runtime_error("PRG consistency error: unterminated site");
+  uint32_t sink = new_node(0, -1, L);
+  wire(sink);
+  ix.n_per_base = n_per_base;
+
+  // CSR edges (stable in wiring order)
+  std::vector<uint32_t> deg(ix.nodes.size() + 1, 0);
+  for (auto& w : wires) deg[w.first + 1]++;
+  for (size_t i = 0; i < ix.nodes.size(); ++i) deg[i + 1] += deg[i];
+  ix.edges.assign(wires.size(), 0);
+  std::vector<uint32_t> fill(deg.begin(), deg.end() - 1);
+  for (auto& w : wires) ix.edges[fill[w.first]++] = w.second;
+  for (size_t i = 0; i < ix.nodes.size(); ++i) {
+    ix.nodes[i].edge_off = deg[i];
+    ix.nodes[i].n_edges = deg[i + 1] - deg[i];
+  }
+  // target_map[even] CSR, allele_sum layout
+  ix.tm_even_off.assign(S + 1, 0);
+  for (uint32_t s = 0; s < S; ++s) ix.tm_even_off[s + 1] = ix.tm_even_off[s] + (uint32_t)tm_even[s].size() / 2;
+  ix.tm_even.clear();
+  for (uint32_t s = 0; s < S; ++s) ix.tm_even.insert(ix.tm_even.end(), tm_even[s].begin(), tm_even[s].end());
+  ix.allele_off.assign(S + 1, 0);
+  for (uint32_t s = 0; s < S; ++s) ix.allele_off[s + 1] = ix.allele_off[s] + ix.n_alleles[s];
+  if (ix.tm_even.empty()) ix.tm_even.assign(2, 0);
+}
+
+void build_fm(HostIndex& ix, const std::vector<uint32_t>& hit_marker, const std::vector<uint32_t>& hit_allele) {
+  const auto& prg = ix.prg;
+  const uint32_t n = (uint32_t)prg.size() + 1;
+  ix.n = n;
+  // compressed alphabet: rank among the symbols present (sdsl's char2comp)
+  std::vector<uint32_t> present(prg);
+  std::sort(present.begin(), present.end());
+  present.erase(std::unique(present.begin(), present.end()), present.end());
+  const int32_t sigma = (int32_t)present.size() + 1;
+  auto comp = [&](uint32_t sym) {
+    return (int32_t)(std::lower_bound(present.begin(), present.end(), sym) - present.begin()) + 1;
+  };
+  std::vector<int32_t> text(n);
+  {
+    // symbols are dense near 1..4 and markers; a direct table avoids n binary searches
+    uint32_t maxs = present.empty() ? 0 : present.back();
+    std::vector<int32_t> tab(maxs + 1, 0);
+    for (size_t i = 0; i < present.size(); ++i) tab[present[i]] = (int32_t)i + 1;
+    for (uint32_t i = 0; i + 1 < n; ++i) text[i] = tab[prg[i]];
+    text[n - 1] = 0;
+  }
+  std::vector<int32_t> sa = suffix_array(text, sigma);
+  ix.sa.assign(sa.begin(), sa.end());
+  // C array
+  std::vector<uint32_t> C(sigma + 1, 0);
+  for (uint32_t i = 0; i < n; ++i) C[text[i] + 1]++;
+  for (int32_t c = 0; c < sigma; ++c) C[c + 1] += C[c];
+  for (uint32_t b = 1; b <= 4; ++b) {
+    bool has = std::binary_search(present.begin(), present.end(), b);
+    int32_t cb = has ? comp(b) : (int32_t)(std::lower_bound(present.begin(), present.end(), b) - present.begin()) + 1;
+    ix.c_base[b - 1] = C[cb];
+  }
+  const uint32_t S = ix.n_slots;
+  ix.site_sa.assign(S, 0);
+  ix.allele_iv.assign(2 * (size_t)S, 0);
+  for (uint32_t s = 0; s < S; ++s) {
+    if (ix.n_alleles[s] == 0) continue;
+    int32_t co = comp(5 + 2 * s), ce = comp(6 + 2 * s);
+    ix.site_sa[s] = C[co];
+    ix.allele_iv[2 * s] = C[ce];          // get_allele_marker_sa_interval, vBWT_jump.cpp:3-21
+    ix.allele_iv[2 * s + 1] = C[ce + 1] - 1;
+  }
+  // rank blocks, marker ranks and marker targets in BWT order
+  const uint32_t nblk = (n >> kBlkShift) + 1;
+  const uint32_t nsuper = (n >> kSuperShift) + 1;
+  ix.rank_blk.assign(nblk, RankBlk{});
+  ix.super_cnt.assign(4 * (size_t)nsuper, 0);
+  ix.mrank_blk.assign(nblk, 0);
+  ix.marker_hit.clear();
+  uint32_t tot[4] = {0, 0, 0, 0}, sup[4] = {0, 0, 0, 0}, nmark = 0;
+  for (uint32_t i = 0; i <= n; ++i) {
+    if ((i & ((1u << kSuperShift) - 1)) == 0) {
+      for (int c = 0; c < 4; ++c) sup[c] = tot[c], ix.super_cnt[4 * (size_t)(i >> kSuperShift) + c] = tot[c];
+    }
+    if ((i & 63u) == 0) {
+      RankBlk& b = ix.rank_blk[i >> kBlkShift];
+      b.cnt = 0;
+      for (int c = 0; c < 4; ++c) b.cnt |= (uint64_t)((tot[c] - sup[c]) & 0xFFFFu) << (16 * c);
+      ix.mrank_blk[i >> kBlkShift] = nmark;
+    }
+    if (i == n) break;
+    uint32_t p = ix.sa[i];
+    uint32_t sym = p ? prg[p - 1] : 0;
+    RankBlk& b = ix.rank_blk[i >> kBlkShift];
+    uint64_t bit = 1ull << (i & 63u);
+    if (sym >= 1 && sym <= 4) {
+      uint32_t c = sym - 1;
+      if (c & 1) b.p0 |= bit;
+      if (c & 2) b.p1 |= bit;
+      tot[c]++;
+    } else {
+      b.p2 |= bit;
+      if (sym > 4) {
+        b.p0 |= bit;
+        ++nmark;
+        bool at_base = p < prg.size() && prg[p] <= 4;
+        ix.marker_hit.push_back(at_base ? hit_marker[p] : 0);
+        ix.marker_hit.push_back(at_base ? hit_allele[p] : 0);
+      }
+    }
+  }
+  if (ix.marker_hit.empty()) ix.marker_hit.assign(2, 0);
+}
+
+// ---- all-k-mers index (reference: src/build/kmer_index/build.cpp:18-148) ---------------------
+struct HState {
+  uint32_t lo, hi;
+  std::vector<uint32_t> path;  // nt pairs then ng sites
+  uint32_t counts;
+};
+
+struct OneBaseRead {
+  uint32_t c;
+  uint32_t operator()(uint32_t) const { return c; }
+};
+struct Collect {
+  std::vector<HState>* out;
+  void operator()(const uint32_t* t) {
+    HState h;
+    h.lo = t[1];
+    h.hi = t[2];
+    h.counts = t[3];
+    uint32_t w = entry_words(t[3]);
+    h.path.assign(t + kHdr, t + w);
+    out->push_back(std::move(h));
+  }
+};
+
+// all successors of `in` after consuming base code c (marker processing first unless `first`)
+void step_states(const IndexView& v, const std::vector<HState>& in, uint32_t c, bool first,
+                 std::vector<uint32_t>& arena, std::vector<HState>& out) {
+  out.clear();
+  for (const auto& st : in) {
+    while (true) {
+      Stack s;
+      s.mem = arena.data();
+      s.limit = (uint32_t)arena.size();
+      s.overflow = false;
+      s.top = 0;
+      uint32_t* t = s.mem;
+      t[0] = 1u | ((first ? K_READY : K_SCAN) << 28);
+      t[1] = st.lo;
+      t[2] = st.hi;
+      t[3] = st.counts;
+      t[4] = kNoAllele;
+      std::copy(st.path.begin(), st.path.end(), t + kHdr);
+      OneBaseRead rd{c};
+      size_t mark = out.size();
+      Collect col{&out};
+      run_stack(s, v, v.super_cnt, rd, col);
+      if (!s.overflow) break;
+      out.resize(mark);
+      arena.resize(arena.size() * 2);
+    }
+  }
+}
+
+struct KmerOut {
+  std::vector<uint32_t> codes;     // k-mer code of each run
+  std::vector<uint32_t> n_states;  // states in that run
+  std::vector<KmerState> states;   // path_off relative to this thread's `paths`
+  std::vector<uint32_t> paths;
+};
+
+void kmer_recurse(const IndexView& v, uint32_t k, uint32_t depth, uint32_t code, const std::vector<HState>& cur,
+                  std::vector<std::vector<HState>>& levels, std::vector<uint32_t>& arena, KmerOut& out) {
+  for (uint32_t c = 0; c < 4; ++c) {
+    std::vector<HState>& nxt = levels[depth];
+    step_states(v, cur, c, depth == 0, arena, nxt);
+    if (nxt.empty()) continue;
+    uint32_t ncode = code | (c << (2 * depth));
+    if (depth + 1 == k) {
+      out.codes.push_back(ncode);
+      out.n_states.push_back((uint32_t)nxt.size());
+      for (auto& h : nxt) {
+        KmerState ks{h.lo, h.hi, (uint32_t)out.paths.size(), h.counts};
+        out.paths.insert(out.paths.end(), h.path.begin(), h.path.end());
+        out.states.push_back(ks);
+      }
+    } else {
+      std::vector<HState> keep;
+      keep.swap(nxt);  // levels[depth] is reused by the siblings' children
+      kmer_recurse(v, k, depth + 1, ncode, keep, levels, arena, out);
+    }
+  }
+}
+
+void build_kmers(HostIndex& ix) {
+  const uint32_t k = ix.k;
+  if (k < 1 || k > 14) throw std::runtime_error("kmer_size must be in [1,14]");  // command_setup.py:97-99
+  const uint64_t nk = 1ull << (2 * k);
+  ix.kmer_bits.assign((nk + 31) / 32, 0);
+  ix.kmer_off.assign(nk + 1, 0);
+  IndexView v = ix.view();
+  // independent subtrees: the first min(k,2) bases (rightmost of the k-mer)
+  const uint32_t pre = std::min<uint32_t>(k, 2);
+  const uint32_t ntask = 1u << (2 * pre);
+  std::vector<KmerOut> outs(ntask);
+  std::string err;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int task = 0; task < (int)ntask; ++task) {
+    try {
+      std::vector<uint32_t> arena(1u << 16);
+      std::vector<std::vector<HState>> levels(k);
+      std::vector<HState> cur{HState{0, ix.n - 1, {}, 0}};
+      std::vector<HState> nxt;
+      uint32_t code = 0;
+      bool dead = false;
+      for (uint32_t d = 0; d < pre; ++d) {
+        uint32_t c = ((uint32_t)task >> (2 * d)) & 3u;
+        step_states(v, cur, c, d == 0, arena, nxt);
+        code |= c << (2 * d);
+        cur.swap(nxt);
+        if (cur.empty()) {
+          dead = true;
+          break;
+        }
+      }
+      if (dead) continue;
+      KmerOut& out = outs[task];
+      if (pre == k) {
+        out.codes.push_back(code);
+        out.n_states.push_back((uint32_t)cur.size());
+        for (auto& h : cur) {
+          KmerState ks{h.lo, h.hi, (uint32_t)out.paths.size(), h.counts};
+          out.paths.insert(out.paths.end(), h.path.begin(), h.path.end());
+          out.states.push_back(ks);
+        }
+      } else
+        kmer_recurse(v, k, pre, code, cur, levels, arena, out);
+    } catch (const std::exception& e) {
+#pragma omp critical
+      err = e.what();
+    }
+  }
+  if (!err.empty()) throw std::runtime_error(err);
+  // merge into CSR ordered by k-mer code
+  for (auto& o : outs)
+    for (size_t i = 0; i < o.codes.size(); ++i) ix.kmer_off[o.codes[i] + 1] += o.n_states[i];
+  for (uint64_t c = 0; c < nk; ++c) {
+    if (ix.kmer_off[c + 1]) ix.kmer_bits[c >> 5] |= 1u << (c & 31);
+    ix.kmer_off[c + 1] += ix.kmer_off[c];
+  }
+  ix.kmer_states.assign(ix.kmer_off[nk], KmerState{});
+  size_t total_paths = 0;
+  for (auto& o : outs) total_paths += o.paths.size();
+  ix.kmer_paths.clear();
+  ix.kmer_paths.reserve(total_paths + 1);
+  for (auto& o : outs) {
+    uint32_t base = (uint32_t)ix.kmer_paths.size();
+    ix.kmer_paths.insert(ix.kmer_paths.end(), o.paths.begin(), o.paths.end());
+    size_t si = 0;
+    for (size_t i = 0; i < o.codes.size(); ++i) {
+      uint32_t dst = ix.kmer_off[o.codes[i]];
+      for (uint32_t j = 0; j < o.n_states[i]; ++j, ++si) {
+        KmerState ks = o.states[si];
+        ks.path_off += base;
+        ix.kmer_states[dst + j] = ks;
+      }
+    }
+  }
+  if (ix.kmer_paths.empty()) ix.kmer_paths.push_back(0);
+  if (ix.kmer_states.empty()) ix.kmer_states.push_back(KmerState{});
+}
+
+}  // namespace
+
+void build_host_index(const uint32_t* prg, uint64_t n_symbols, uint32_t kmer_size, HostIndex& ix) {
+  if (n_symbols == 0) throw std::runtime_error("empty PRG");
+  if (n_symbols >= (1ull << 31) - 2) throw std::runtime_error("PRG too long for 32-bit suffix indices");
+  ix = HostIndex{};
+  ix.k = kmer_size;
+  ix.prg.assign(prg, prg + n_symbols);
+  std::vector<uint32_t> hit_marker, hit_allele;
+  build_graph(ix, hit_marker, hit_allele);
+  build_fm(ix, hit_marker, hit_allele);
+  build_kmers(ix);
+}
+
+}  // namespace gq

@@ -1,0 +1,51 @@
+// index_build.hpp — host-side construction of the flat quasimap index from a linearised PRG.
+//
+// Rebuilds, from the `prg` integer string alone, everything `gramtools build` leaves in gram_dir
+// for the quasimap path (reference: libgramtools/src/build/build.cpp:8-71): FM-index (SA, BWT,
+// C array, DNA + marker masks), coverage graph (nodes, random access, target map, parent map) and
+// the all-k-mers index — but laid out as flat arrays for HBM.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "gq_core.cuh"
+
+namespace gq {
+
+struct HostIndex {
+  uint32_t n = 0;  // SA size
+  uint32_t k = 0;
+  std::vector<uint32_t> prg;
+  // FM
+  std::vector<uint32_t> sa;
+  std::vector<RankBlk> rank_blk;
+  std::vector<uint32_t> super_cnt;
+  std::vector<uint32_t> mrank_blk;
+  std::vector<uint32_t> marker_hit;
+  uint32_t c_base[4] = {0, 0, 0, 0};
+  // sites
+  uint32_t n_slots = 0;   // (max site id - 5)/2 + 1
+  uint32_t n_sites = 0;   // sites actually present
+  std::vector<uint32_t> site_sa, allele_iv, par, tm_odd, tm_even_off, tm_even;
+  std::vector<uint32_t> n_alleles;   // per slot (0 if the slot is unused)
+  std::vector<uint32_t> allele_off;  // n_slots + 1: prefix sum of n_alleles (allele_sum layout)
+  bool is_nested = false;
+  // graph
+  std::vector<uint32_t> pos2node;
+  std::vector<Node> nodes;
+  std::vector<uint32_t> edges;
+  std::vector<uint32_t> site_start_node;  // per slot: bubble start node id
+  uint32_t n_per_base = 0;                // number of in-bubble bases (flat per-base layout)
+  // k-mer index
+  std::vector<uint32_t> kmer_bits, kmer_off, kmer_paths;
+  std::vector<KmerState> kmer_states;
+
+  IndexView view() const;
+};
+
+// Throws std::runtime_error on malformed PRGs (same conditions as the reference:
+// linearised_prg.cpp:52-80, coverage_graph.cpp:215-221,330-338).
+void build_host_index(const uint32_t* prg, uint64_t n_symbols, uint32_t kmer_size, HostIndex& out);
+
+}  // namespace gq

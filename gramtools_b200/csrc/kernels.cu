@@ -1,0 +1,171 @@
+// kernels.cu — hand-written sm_100a kernels for the quasimap hot path.
+//
+//   pack_kernel      uint8 bases -> 2-bit packed words (16 bases / word)
+//   search_kernel    k-mer filter + k-mer seeding + vBWT backward search with marker jumps
+//                    (reference: libgramtools/src/genotype/quasimap/quasimap.cpp:159-256,
+//                     search/BWT_search.cpp, search/vBWT_jump.cpp, search/encapsulated_search.cpp)
+//   coverage_kernel  equivalence classes, seeded selection, allele-sum / grouped / per-base recording
+//                    (reference: coverage/coverage_common.cpp, allele_sum.cpp,
+//                     grouped_allele_counts.cpp, allele_base.cpp)
+//   stats_kernel     the five QuasimapReadsStats counters (quasimap.hpp:17-24)
+//
+// Integer / bit arithmetic only; the bound is random 32 B sector traffic to the rank blocks (HBM, or
+// L2 when the index fits), so there is no tensor-core work here. Rank superblock counters are staged
+// into shared memory with one TMA bulk copy per CTA.
+#include "kernels.cuh"
+#include "gq_device.cuh"
+
+#include <cstdio>
+
+namespace gq {
+
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_kernel(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offsets,
+                            const uint32_t* __restrict__ word_off, uint32_t n_reads, uint32_t* __restrict__ packed,
+                            uint32_t* __restrict__ len) {
+  // one warp per read; lanes write consecutive words
+  uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t r = warp; r < n_reads; r += nwarps) {
+    uint64_t b0 = offsets[r];
+    uint32_t L = (uint32_t)(offsets[r + 1] - b0);
+    if (lane == 0) len[r] = L;
+    uint32_t w0 = word_off[r], nw = (L + 15) >> 4;
+    for (uint32_t w = lane; w < nw; w += 32) {
+      uint32_t x = 0;
+      uint32_t base = w << 4;
+      uint32_t cnt = min(16u, L - base);
+      for (uint32_t j = 0; j < cnt; ++j) x |= ((uint32_t)(bases[b0 + base + j] - 1) & 3u) << (2 * j);
+      packed[w0 + w] = x;
+    }
+  }
+}
+
+void launch_pack(const uint8_t* bases, const uint64_t* offsets, const uint32_t* word_off, uint32_t n_reads,
+                 uint32_t total_words, uint32_t* packed, uint32_t* len, cudaStream_t st) {
+  (void)total_words;
+  if (n_reads == 0) return;
+  uint32_t blocks = min((n_reads + 7) / 8, 148u * 16u);
+  pack_kernel<<<blocks, 256, 0, st>>>(bases, offsets, word_off, n_reads, packed, len);
+}
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_stage_super(uint32_t* s_super, const uint32_t* g_super, uint32_t bytes,
+                                                uint64_t* bar) {
+  // one elected thread arms an mbarrier and issues a single TMA bulk copy (UBLKCP) global -> shared
+  uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(bar);
+  uint32_t dst_a = (uint32_t)__cvta_generic_to_shared(s_super);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_a),
+                 "l"(g_super), "r"(bytes), "r"(bar_a)
+                 : "memory");
+  }
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(bar_a), "r"(0u)
+        : "memory");
+  }
+}
+
+constexpr int kSearchThreads = 256;
+constexpr int kMaxSuperSmem = 2048;  // superblocks (x16 B = 32 KB) staged in shared memory
+
+__global__ void __launch_bounds__(kSearchThreads)
+    search_kernel(IndexView v, BatchView b, SearchOut o, uint32_t* arena, uint32_t arena_words,
+                  const uint32_t* list, uint32_t n_list, uint32_t n_super_smem) {
+  __shared__ alignas(128) uint32_t s_super[kMaxSuperSmem * 4];
+  __shared__ alignas(8) uint64_t s_bar;
+  const uint32_t* super_cnt = v.super_cnt;
+  if (n_super_smem) {
+    tma_stage_super(s_super, v.super_cnt, n_super_smem * 16u, &s_bar);
+    super_cnt = s_super;
+  }
+  uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t nthreads = gridDim.x * blockDim.x;
+  uint32_t* my_arena = arena + (size_t)tid * arena_words;
+  if (list) {
+    for (uint32_t i = tid; i < n_list; i += nthreads) map_strand(v, super_cnt, b, o, list[i], my_arena, arena_words);
+  } else {
+    for (uint32_t r = tid; r < b.n_reads; r += nthreads) {
+      map_strand(v, super_cnt, b, o, 2 * r, my_arena, arena_words);
+      map_strand(v, super_cnt, b, o, 2 * r + 1, my_arena, arena_words);
+    }
+  }
+}
+
+int search_kernel_smem_limit_superblocks() { return kMaxSuperSmem; }
+
+void launch_search(const IndexView& v, const BatchView& b, const SearchOut& o, uint32_t* arena,
+                   uint32_t arena_words, uint32_t n_threads, const uint32_t* list, uint32_t n_list,
+                   bool super_in_smem, cudaStream_t st) {
+  uint32_t work = list ? n_list : b.n_reads;
+  if (work == 0) return;
+  uint32_t blocks = (min(work, n_threads) + kSearchThreads - 1) / kSearchThreads;
+  uint32_t n_super = (v.n >> kSuperShift) + 1;
+  uint32_t n_super_smem = (super_in_smem && n_super <= (uint32_t)kMaxSuperSmem) ? n_super : 0;
+  search_kernel<<<blocks, kSearchThreads, 0, st>>>(v, b, o, arena, arena_words, list, n_list, n_super_smem);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Coverage recording, one thread per mapped strand.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    coverage_kernel(IndexView v, BatchView b, SearchOut o, CoverageView c, uint32_t* arena, uint32_t arena_words,
+                    const uint32_t* list, uint32_t n_list, uint32_t* overflow_list, uint32_t* n_overflow) {
+  uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t nthreads = gridDim.x * blockDim.x;
+  uint32_t* my_arena = arena + (size_t)tid * arena_words;
+  uint32_t n = list ? n_list : 2 * b.n_reads;
+  for (uint32_t i = tid; i < n; i += nthreads) {
+    uint32_t strand = list ? list[i] : i;
+    if (o.status[strand] != ST_MAPPED) continue;
+    if (!record_strand(v, b, o, c, strand, my_arena, arena_words)) overflow_list[atomicAdd(n_overflow, 1u)] = strand;
+  }
+}
+
+void launch_coverage(const IndexView& v, const BatchView& b, const SearchOut& o, const CoverageView& c,
+                     uint32_t* arena, uint32_t arena_words, uint32_t n_threads, const uint32_t* list,
+                     uint32_t n_list, uint32_t* overflow_list, uint32_t* n_overflow, cudaStream_t st) {
+  uint32_t work = list ? n_list : 2 * b.n_reads;
+  if (work == 0) return;
+  uint32_t blocks = (min(work, n_threads) + 255) / 256;
+  coverage_kernel<<<blocks, 256, 0, st>>>(v, b, o, c, arena, arena_words, list, n_list, overflow_list, n_overflow);
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void stats_kernel(const uint8_t* status, const uint32_t* len, uint32_t n_reads, unsigned long long* stats) {
+  unsigned long long loc[5] = {0, 0, 0, 0, 0};
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += gridDim.x * blockDim.x) {
+    loc[0] += 2;
+    for (int s = 0; s < 2; ++s) {
+      uint8_t stt = status[2 * r + s];
+      if (stt == ST_SKIPPED) loc[1] += 1;
+      else if (stt == ST_MISSING_KMER) loc[2] += 1;
+      else if (stt == ST_NO_EXTENSION) loc[3] += 1;
+      else if (stt == ST_MAPPED) loc[4] += 1;
+    }
+  }
+  for (int i = 0; i < 5; ++i) {
+    unsigned long long x = loc[i];
+    for (int d = 16; d; d >>= 1) x += __shfl_down_sync(0xFFFFFFFFu, x, d);
+    if ((threadIdx.x & 31) == 0 && x) atomicAdd(stats + i, x);
+  }
+}
+
+void launch_stats(const uint8_t* status, const uint32_t* len, uint32_t n_reads, unsigned long long* stats,
+                  cudaStream_t st) {
+  if (n_reads == 0) return;
+  uint32_t blocks = min((n_reads + 255) / 256, 148u * 4u);
+  stats_kernel<<<blocks, 256, 0, st>>>(status, len, n_reads, stats);
+}
+
+}  // namespace gq

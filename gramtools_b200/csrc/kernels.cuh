@@ -1,0 +1,68 @@
+// kernels.cuh — launch interface of the sm_100a kernels (definitions in kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "gq_core.cuh"
+
+namespace gq {
+
+enum StrandStatus : uint8_t { ST_SKIPPED = 0, ST_MISSING_KMER = 1, ST_NO_EXTENSION = 2, ST_MAPPED = 3, ST_OVERFLOW = 255 };
+
+struct BatchView {               // one batch of reads, resident in HBM
+  const uint32_t* packed;        // 2-bit base codes, 16 per word, every read starts on a word
+  const uint32_t* word_off;      // n_reads + 1
+  const uint32_t* len;           // n_reads (0 = skipped read)
+  const uint32_t* seeds;         // n_reads (selection seed, shared by both strands)
+  uint32_t n_reads;
+};
+
+struct SearchOut {
+  uint8_t* status;      // 2 * n_reads
+  uint32_t* st_off;     // 2 * n_reads: word offset of the strand's records in `pool`
+  uint32_t* st_words;   // 2 * n_reads: words used
+  uint32_t* st_count;   // 2 * n_reads: number of final states
+  uint32_t* pool;       // final-state records: [lo, hi, nt, ng, (site,allele)*nt, (site,0xFFFFFFFF)*ng]
+  uint32_t pool_cap;
+  uint32_t* pool_used;      // bump pointer
+  uint32_t* overflow_list;  // strands that ran out of arena / pool
+  uint32_t* n_overflow;
+};
+
+struct CoverageView {
+  uint32_t* allele_sum;      // per (slot, allele): allele_off[slot] + allele
+  uint32_t* per_base;        // flat in-bubble bases, PRG order
+  uint32_t* grouped_single;  // per (slot, allele): reads whose allele set at the site is {allele}
+  // multi-allele sets: open-addressing table of offsets into gpool records [slot, n, alleles...]
+  uint32_t* gtab;            // gtab_cap entries: 0 = empty, else record offset + 1
+  uint32_t* gcount;          // gtab_cap counters
+  uint32_t gtab_cap;         // power of two
+  uint32_t* gpool;
+  uint32_t gpool_cap;
+  uint32_t* gpool_used;
+  unsigned long long* stats; // all_reads, skipped, missing_kmer, no_extension, exact_mapped
+  const uint32_t* allele_off;
+  uint32_t* error_flags;     // bit0: grouped table/pool full, bit1: inconsistent traversal
+};
+
+// bases (uint8 1..4, concatenated, device) -> packed 2-bit words
+void launch_pack(const uint8_t* bases, const uint64_t* offsets, const uint32_t* word_off, uint32_t n_reads,
+                 uint32_t total_words, uint32_t* packed, uint32_t* len, cudaStream_t st);
+
+// list == nullptr: all reads of the batch (one thread per read, both strands);
+// otherwise only the listed strands (overflow re-runs with a larger arena).
+void launch_search(const IndexView& v, const BatchView& b, const SearchOut& o, uint32_t* arena,
+                   uint32_t arena_words, uint32_t n_threads, const uint32_t* list, uint32_t n_list,
+                   bool super_in_smem, cudaStream_t st);
+
+void launch_coverage(const IndexView& v, const BatchView& b, const SearchOut& o, const CoverageView& c,
+                     uint32_t* arena, uint32_t arena_words, uint32_t n_threads, const uint32_t* list,
+                     uint32_t n_list, uint32_t* overflow_list, uint32_t* n_overflow, cudaStream_t st);
+
+void launch_stats(const uint8_t* status, const uint32_t* len, uint32_t n_reads, unsigned long long* stats,
+                  cudaStream_t st);
+
+int search_kernel_smem_limit_superblocks();
+
+}  // namespace gq

@@ -1,0 +1,190 @@
+"""Synthetic PRGs and reads of the shapes BASELINE.json names.
+
+PRGs are emitted directly as the integer string `gramtools build` would store in gram_dir/prg
+(1..4 = ACGT, odd >= 5 site entry, even = allele separator / site end;
+gramtools/commands/build/vcf_to_prg_string.py:81-101 for the `--vcf` route). Reads are error-free
+substrings of random haplotype paths, on a random strand.
+"""
+import numpy as np
+
+
+def master_seeds(seed, n):
+    """Per-read selection seeds: the first n raw outputs of std::mt19937(seed)
+    (handle_read_file, quasimap.cpp:136-137). numpy's MT19937 seeded with the same 32-bit integer via
+    `init_genrand` produces the identical stream."""
+    bg = np.random.MT19937()
+    st = bg.state
+    key = np.zeros(624, dtype=np.uint32)
+    x = np.uint64(seed & 0xFFFFFFFF)
+    key[0] = x
+    for i in range(1, 624):
+        x = (np.uint64(1812433253) * (x ^ (x >> np.uint64(30))) + np.uint64(i)) & np.uint64(0xFFFFFFFF)
+        key[i] = x
+    st["state"]["key"] = key
+    st["state"]["pos"] = 624
+    bg.state = st
+    return bg.random_raw(n).astype(np.uint32)
+
+
+def make_snp_prg(ref_len, n_sites, seed, min_spacing=2):
+    """Random reference + biallelic SNPs -> (prg uint32, ref uint8 codes 1..4, site_pos, alt)."""
+    rng = np.random.default_rng(seed)
+    ref = rng.integers(1, 5, size=ref_len, dtype=np.uint8)
+    # positions without replacement, not adjacent (adjacency is exercised by the nested generator)
+    cand = np.sort(rng.choice(ref_len - 2, size=min(n_sites * 2 + 16, ref_len - 2), replace=False)) + 1
+    keep = [cand[0]]
+    for p in cand[1:]:
+        if p - keep[-1] >= min_spacing:
+            keep.append(p)
+    pos = np.asarray(keep, dtype=np.int64)
+    if pos.size > n_sites:
+        pos = np.sort(rng.choice(pos, size=n_sites, replace=False))
+    n_sites = pos.size
+    alt = ((ref[pos].astype(np.int64) - 1 + rng.integers(1, 4, size=n_sites)) % 4 + 1).astype(np.uint8)
+    out = np.zeros(ref_len + 4 * n_sites, dtype=np.uint32)
+    is_site = np.zeros(ref_len, dtype=np.int64)
+    is_site[pos] = 1
+    before = np.cumsum(is_site) - is_site          # sites strictly before i
+    out_pos = np.arange(ref_len) + 4 * before + is_site  # ref base of a site sits after the odd marker
+    out[out_pos] = ref
+    sp = out_pos[pos]
+    ids = 5 + 2 * np.arange(n_sites, dtype=np.uint32)
+    out[sp - 1] = ids
+    out[sp + 1] = ids + 1
+    out[sp + 2] = alt
+    out[sp + 3] = ids + 1
+    return out, ref, pos, alt
+
+
+def snp_haplotypes(ref, pos, alt, n_hap, seed):
+    rng = np.random.default_rng(seed)
+    haps = []
+    for _ in range(n_hap):
+        h = ref.copy()
+        pick = rng.integers(0, 2, size=pos.size).astype(bool)
+        h[pos[pick]] = alt[pick]
+        haps.append(h)
+    return haps
+
+
+def make_nested_prg(n_loci, locus_len, seed, max_depth=3, spacer=200):
+    """Bracket-grammar PRG with nesting, empty alleles (direct deletions) and adjacent sites."""
+    rng = np.random.default_rng(seed)
+    out = []
+    next_id = [5]
+
+    def seq(n):
+        return [int(x) for x in rng.integers(1, 5, size=n)]
+
+    def site(depth, budget):
+        sid = next_id[0]
+        next_id[0] += 2
+        res = [sid]
+        n_all = int(rng.integers(2, 5))
+        empty_used = False
+        for a in range(n_all):
+            if a:
+                res.append(sid + 1)
+            r = rng.random()
+            if r < 0.12 and not empty_used and a > 0:
+                empty_used = True  # empty allele = direct deletion
+                continue
+            res += body(depth + 1, max(1, int(budget * rng.uniform(0.2, 0.6))))
+        res.append(sid + 1)
+        return res
+
+    def body(depth, budget):
+        res = []
+        if depth <= max_depth and budget >= 6 and rng.random() < 0.5:
+            if rng.random() < 0.7:
+                res += seq(int(rng.integers(1, max(2, budget // 3))))
+            res += site(depth, budget // 2)
+            if rng.random() < 0.25 and depth <= max_depth:  # adjacent sites `][`
+                res += site(depth, budget // 3)
+            if rng.random() < 0.7:
+                res += seq(int(rng.integers(1, max(2, budget // 3))))
+        else:
+            res += seq(int(rng.integers(1, max(2, min(budget, 12)))))
+        return res
+
+    out += seq(spacer)
+    for _ in range(n_loci):
+        remaining = locus_len
+        while remaining > 0:
+            step = int(rng.integers(8, 40))
+            out += seq(step)
+            out += site(1, 40)
+            remaining -= step + 40
+        out += seq(spacer)
+    return np.asarray(out, dtype=np.uint32)
+
+
+def random_haplotype(prg, rng):
+    """One random path through any (nested) PRG: uniform allele choice at every site."""
+    prg = np.asarray(prg)
+    n = prg.size
+    # number of alleles per site and matching positions
+    n_alleles = {}
+    last = {}
+    for i, m in enumerate(prg):
+        m = int(m)
+        if m > 4 and m % 2 == 0:
+            n_alleles[m - 1] = n_alleles.get(m - 1, 0) + 1
+            last[m] = i
+    out = []
+    # stack of [site, chosen allele, current allele]; `skip` depth counter for unchosen alleles
+    stack = []
+    active = True
+    act_stack = []
+    for i in range(n):
+        m = int(prg[i])
+        if m <= 4:
+            if active:
+                out.append(m)
+        elif m % 2 == 1:
+            act_stack.append(active)
+            chosen = int(rng.integers(0, n_alleles[m])) if active else -1
+            stack.append([m, chosen, 0])
+            active = active and chosen == 0
+        else:
+            s = stack[-1]
+            if i == last[m]:
+                stack.pop()
+                active = act_stack.pop()
+            else:
+                s[2] += 1
+                active = act_stack[-1] and s[1] == s[2]
+    return np.asarray(out, dtype=np.uint8)
+
+
+def sample_reads(haps, n_reads, read_len, seed, frac_garbage=0.0, frac_n=0.0):
+    """Error-free reads from random haplotypes, random strand. Returns (bases uint8 concatenated,
+    offsets uint64). `frac_garbage` adds uniformly random reads, `frac_n` empty reads (non-ACGT)."""
+    rng = np.random.default_rng(seed)
+    hap_idx = rng.integers(0, len(haps), size=n_reads)
+    L = read_len
+    reads = np.zeros((n_reads, L), dtype=np.uint8)
+    for h, hap in enumerate(haps):
+        sel = np.nonzero(hap_idx == h)[0]
+        if sel.size == 0:
+            continue
+        if hap.size < L:
+            raise ValueError("haplotype shorter than the read length")
+        starts = rng.integers(0, hap.size - L + 1, size=sel.size)
+        idx = starts[:, None] + np.arange(L)[None, :]
+        reads[sel] = hap[idx]
+    rc = rng.random(n_reads) < 0.5
+    reads[rc] = (5 - reads[rc])[:, ::-1]
+    if frac_garbage > 0:
+        g = rng.random(n_reads) < frac_garbage
+        reads[g] = rng.integers(1, 5, size=(int(g.sum()), L), dtype=np.uint8)
+    lens = np.full(n_reads, L, dtype=np.uint64)
+    if frac_n > 0:
+        lens[rng.random(n_reads) < frac_n] = 0
+    if (lens == L).all():
+        bases = reads.reshape(-1)
+    else:
+        bases = np.concatenate([reads[i, :int(lens[i])] for i in range(n_reads)]) if n_reads else np.zeros(0, np.uint8)
+    offsets = np.zeros(n_reads + 1, dtype=np.uint64)
+    np.cumsum(lens, out=offsets[1:])
+    return np.ascontiguousarray(bases), offsets

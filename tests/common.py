@@ -1,0 +1,256 @@
+"""Shared test plumbing: ctypes bindings of the CPU oracle (oracle/) and of the test-only host
+emulation of the device functions (tests/emu), canonicalisation of per-strand state records, and the
+parity comparator used by both the CPU and the GPU suites."""
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass, field
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+u8p, u16p, u32p, u64p = (C.POINTER(t) for t in (C.c_uint8, C.c_uint16, C.c_uint32, C.c_uint64))
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _make(target_dir):
+    env = dict(os.environ)
+    env.pop("CXX", None)
+    subprocess.run(["make", "-C", target_dir], check=True, env=env, stdout=subprocess.DEVNULL)
+
+
+_oracle = None
+_emu = None
+
+
+def oracle_lib():
+    global _oracle
+    if _oracle is None:
+        p = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
+        if not os.path.exists(p):
+            _make(os.path.join(ROOT, "oracle"))
+        lib = C.CDLL(p)
+        lib.gqo_new.restype = C.c_void_p
+        lib.gqo_new.argtypes = [u32p, C.c_uint64, C.c_uint32]
+        lib.gqo_free.argtypes = [C.c_void_p]
+        lib.gqo_last_error.restype = C.c_char_p
+        lib.gqo_master_seeds.argtypes = [C.c_uint32, C.c_uint64, u32p]
+        lib.gqo_sizes.argtypes = [C.c_void_p, u64p]
+        lib.gqo_map.argtypes = [C.c_void_p, u8p, u64p, C.c_uint64, u32p, C.c_int, C.c_int, C.c_int]
+        lib.gqo_last_seconds.argtypes = [C.c_void_p]
+        lib.gqo_last_seconds.restype = C.c_double
+        lib.gqo_status.argtypes = [C.c_void_p, u8p]
+        lib.gqo_states_size.argtypes = [C.c_void_p]
+        lib.gqo_states_size.restype = C.c_uint64
+        lib.gqo_states.argtypes = [C.c_void_p, u64p, u32p, u32p]
+        lib.gqo_allele_sum.argtypes = [C.c_void_p, u16p]
+        lib.gqo_per_base.argtypes = [C.c_void_p, u16p]
+        lib.gqo_grouped.argtypes = [C.c_void_p, u32p]
+        lib.gqo_grouped.restype = C.c_uint64
+        lib.gqo_stats.argtypes = [C.c_void_p, u64p]
+        lib.gqo_events.argtypes = [C.c_void_p, u64p]
+        _oracle = lib
+    return _oracle
+
+
+def emu_lib():
+    global _emu
+    if _emu is None:
+        p = os.path.join(ROOT, "tests", "_build", "libgq_emu.so")
+        _make(os.path.join(ROOT, "tests", "emu"))
+        lib = C.CDLL(p)
+        lib.emu_new.restype = C.c_void_p
+        lib.emu_new.argtypes = [u32p, C.c_uint64, C.c_uint32]
+        lib.emu_free.argtypes = [C.c_void_p]
+        lib.emu_last_error.restype = C.c_char_p
+        lib.emu_sizes.argtypes = [C.c_void_p, u64p]
+        lib.emu_kmer_states.argtypes = [C.c_void_p, u32p]
+        lib.emu_kmer_states.restype = C.c_uint64
+        lib.emu_sa.argtypes = [C.c_void_p, u32p]
+        lib.emu_map.argtypes = [C.c_void_p, u8p, u64p, C.c_uint64, u32p, C.c_uint32]
+        lib.emu_reruns.argtypes = [C.c_void_p]
+        lib.emu_reruns.restype = C.c_uint64
+        lib.emu_status.argtypes = [C.c_void_p, u8p]
+        lib.emu_states_size.argtypes = [C.c_void_p]
+        lib.emu_states_size.restype = C.c_uint64
+        lib.emu_states.argtypes = [C.c_void_p, u64p, u32p, u32p]
+        lib.emu_allele_sum.argtypes = [C.c_void_p, u16p]
+        lib.emu_per_base.argtypes = [C.c_void_p, u16p]
+        lib.emu_grouped.argtypes = [C.c_void_p, u32p]
+        lib.emu_grouped.restype = C.c_uint64
+        lib.emu_stats.argtypes = [C.c_void_p, u64p]
+        _emu = lib
+    return _emu
+
+
+@dataclass
+class Result:
+    status: np.ndarray
+    state_off: np.ndarray
+    state_count: np.ndarray
+    state_words: np.ndarray
+    allele_sum: np.ndarray
+    per_base: np.ndarray
+    grouped: np.ndarray
+    stats: list
+    extra: dict = field(default_factory=dict)
+
+
+def canonical_strand(words, count):
+    """Sort the `count` records [lo,hi,nt,ng,pairs...] of one strand lexicographically."""
+    recs, i = [], 0
+    words = [int(x) for x in words]
+    for _ in range(int(count)):
+        n = 4 + 2 * words[i + 2] + 2 * words[i + 3]
+        recs.append(tuple(words[i:i + n]))
+        i += n
+    assert i == len(words), "record stream does not match its count"
+    recs.sort()
+    return recs
+
+
+class Oracle:
+    def __init__(self, prg, k):
+        self.lib = oracle_lib()
+        prg = np.ascontiguousarray(prg, dtype=np.uint32)
+        self.h = self.lib.gqo_new(_ptr(prg, C.c_uint32), prg.size, k)
+        if not self.h:
+            raise RuntimeError(self.lib.gqo_last_error().decode())
+        s = np.zeros(6, dtype=np.uint64)
+        self.lib.gqo_sizes(self.h, _ptr(s, C.c_uint64))
+        self.n_sites, self.n_alleles, self.n_per_base, self.is_nested, self.sa_size, self.n_kmer_states = [int(x) for x in s]
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.gqo_free(self.h)
+            self.h = None
+
+    def map(self, bases, offsets, seeds, threads=1, want_states=True, count_events=False):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+        n = offsets.size - 1
+        rc = self.lib.gqo_map(self.h, _ptr(bases, C.c_uint8), _ptr(offsets, C.c_uint64), n, _ptr(seeds, C.c_uint32),
+                              threads, int(want_states), int(count_events))
+        if rc != 0:
+            raise RuntimeError(self.lib.gqo_last_error().decode())
+        self.n_reads = n
+        return self.lib.gqo_last_seconds(self.h)
+
+    def result(self, want_states=True):
+        n = self.n_reads
+        status = np.zeros(2 * n, dtype=np.uint8)
+        self.lib.gqo_status(self.h, _ptr(status, C.c_uint8))
+        off = np.zeros(2 * n + 1, dtype=np.uint64)
+        cnt = np.zeros(2 * n, dtype=np.uint32)
+        words = np.zeros(1, dtype=np.uint32)
+        if want_states:
+            nw = self.lib.gqo_states_size(self.h)
+            words = np.zeros(max(nw, 1), dtype=np.uint32)
+            self.lib.gqo_states(self.h, _ptr(off, C.c_uint64), _ptr(cnt, C.c_uint32), _ptr(words, C.c_uint32))
+            words = words[:nw]
+        a = np.zeros(max(self.n_alleles, 1), dtype=np.uint16)
+        self.lib.gqo_allele_sum(self.h, _ptr(a, C.c_uint16))
+        p = np.zeros(max(self.n_per_base, 1), dtype=np.uint16)
+        self.lib.gqo_per_base(self.h, _ptr(p, C.c_uint16))
+        ng = self.lib.gqo_grouped(self.h, None)
+        g = np.zeros(max(ng, 1), dtype=np.uint32)
+        self.lib.gqo_grouped(self.h, _ptr(g, C.c_uint32))
+        st = np.zeros(5, dtype=np.uint64)
+        self.lib.gqo_stats(self.h, _ptr(st, C.c_uint64))
+        return Result(status, off, cnt, words, a[:self.n_alleles], p[:self.n_per_base], g[:ng], [int(x) for x in st])
+
+    def events(self):
+        e = np.zeros(7, dtype=np.uint64)
+        self.lib.gqo_events(self.h, _ptr(e, C.c_uint64))
+        return dict(zip(["q_rank", "w_marker", "q_sa", "q_node", "a_cov", "strands", "bases"], [int(x) for x in e]))
+
+
+class Emu:
+    def __init__(self, prg, k):
+        self.lib = emu_lib()
+        prg = np.ascontiguousarray(prg, dtype=np.uint32)
+        self.h = self.lib.emu_new(_ptr(prg, C.c_uint32), prg.size, k)
+        if not self.h:
+            raise RuntimeError(self.lib.emu_last_error().decode())
+        s = np.zeros(6, dtype=np.uint64)
+        self.lib.emu_sizes(self.h, _ptr(s, C.c_uint64))
+        self.n_sites, self.n_alleles, self.n_per_base, self.is_nested, self.sa_size, self.n_kmer_states = [int(x) for x in s]
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.emu_free(self.h)
+            self.h = None
+
+    def sa(self):
+        out = np.zeros(self.sa_size, dtype=np.uint32)
+        self.lib.emu_sa(self.h, _ptr(out, C.c_uint32))
+        return out
+
+    def map(self, bases, offsets, seeds, arena_words=256):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+        n = offsets.size - 1
+        rc = self.lib.emu_map(self.h, _ptr(bases, C.c_uint8), _ptr(offsets, C.c_uint64), n, _ptr(seeds, C.c_uint32),
+                              arena_words)
+        if rc != 0:
+            raise RuntimeError(self.lib.emu_last_error().decode())
+        self.n_reads = n
+
+    def result(self):
+        n = self.n_reads
+        status = np.zeros(2 * n, dtype=np.uint8)
+        self.lib.emu_status(self.h, _ptr(status, C.c_uint8))
+        nw = self.lib.emu_states_size(self.h)
+        off = np.zeros(2 * n + 1, dtype=np.uint64)
+        cnt = np.zeros(2 * n, dtype=np.uint32)
+        words = np.zeros(max(nw, 1), dtype=np.uint32)
+        self.lib.emu_states(self.h, _ptr(off, C.c_uint64), _ptr(cnt, C.c_uint32), _ptr(words, C.c_uint32))
+        a = np.zeros(max(self.n_alleles, 1), dtype=np.uint16)
+        self.lib.emu_allele_sum(self.h, _ptr(a, C.c_uint16))
+        p = np.zeros(max(self.n_per_base, 1), dtype=np.uint16)
+        self.lib.emu_per_base(self.h, _ptr(p, C.c_uint16))
+        ng = self.lib.emu_grouped(self.h, None)
+        g = np.zeros(max(ng, 1), dtype=np.uint32)
+        self.lib.emu_grouped(self.h, _ptr(g, C.c_uint32))
+        st = np.zeros(5, dtype=np.uint64)
+        self.lib.emu_stats(self.h, _ptr(st, C.c_uint64))
+        return Result(status, off, cnt, words[:nw], a[:self.n_alleles], p[:self.n_per_base], g[:ng], [int(x) for x in st],
+                      dict(reruns=int(self.lib.emu_reruns(self.h))))
+
+
+def gpu_result(idx):
+    """Result of a gramtools_b200.QuasimapIndex after map_batch()."""
+    status = idx.batch_status()
+    off, cnt, words = idx.batch_states()
+    a, p, st = idx.coverage()
+    g = idx.grouped()
+    stats = [st.all_reads_count, st.skipped_reads_count, st.missing_kmer_reads_count, st.no_extension_reads_count,
+             st.exact_mapped_reads_count]
+    return Result(status, off, cnt, words, a, p, g, stats, idx.run_info())
+
+
+def assert_parity(got: Result, ref: Result, what="", check_states=True):
+    """Bit-exact comparison (integer path: no tolerance)."""
+    assert got.stats == ref.stats, f"{what}: stats {got.stats} != {ref.stats}"
+    bad = np.nonzero(got.status != ref.status)[0]
+    assert bad.size == 0, f"{what}: status differs at strands {bad[:10]}: {got.status[bad[:10]]} vs {ref.status[bad[:10]]}"
+    if check_states:
+        assert np.array_equal(got.state_count, ref.state_count), \
+            f"{what}: state counts differ at strands {np.nonzero(got.state_count != ref.state_count)[0][:10]}"
+        same = (got.state_off.size == ref.state_off.size and np.array_equal(got.state_off, ref.state_off)
+                and np.array_equal(got.state_words, ref.state_words))
+        if not same:  # unordered within a strand: canonicalise strand by strand
+            for s in range(got.status.size):
+                a = canonical_strand(got.state_words[int(got.state_off[s]):int(got.state_off[s + 1])], got.state_count[s])
+                b = canonical_strand(ref.state_words[int(ref.state_off[s]):int(ref.state_off[s + 1])], ref.state_count[s])
+                assert a == b, f"{what}: final SearchStates differ for strand {s}:\n got {a}\n ref {b}"
+    assert np.array_equal(got.allele_sum, ref.allele_sum), \
+        f"{what}: allele_sum differs at {np.nonzero(got.allele_sum != ref.allele_sum)[0][:10]}"
+    assert np.array_equal(got.per_base, ref.per_base), \
+        f"{what}: per-base coverage differs at {np.nonzero(got.per_base != ref.per_base)[0][:10]}"
+    assert np.array_equal(got.grouped, ref.grouped), f"{what}: grouped allele counts differ"

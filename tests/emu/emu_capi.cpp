@@ -1,0 +1,246 @@
+// emu_capi.cpp — TEST-ONLY host emulation of the device functions in gramtools_b200/csrc/gq_device.cuh.
+//
+// Compiles the exact per-strand code of the CUDA kernels (map_strand, record_strand) for the host and
+// runs it one strand at a time, so that the flat index + search/coverage logic can be checked against
+// the oracle in the GPU-less container (`pytest -m "not gpu"`). This is debugging infrastructure: it is
+// built into tests/_build/libgq_emu.so, never into libgq.so, and is not a supported CPU path.
+#include <cstring>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../gramtools_b200/csrc/gq_device.cuh"
+#include "../../gramtools_b200/csrc/index_build.hpp"
+
+using namespace gq;
+
+struct Emu {
+  HostIndex h;
+  std::vector<uint32_t> counters, gtab, gcount, gpool, gsmall;
+  unsigned long long stats[5] = {0, 0, 0, 0, 0};
+  // last batch
+  std::vector<uint8_t> status;
+  std::vector<uint32_t> st_off, st_words, st_count, pool;
+  uint32_t n_reads = 0;
+  uint64_t reruns = 0;
+};
+static thread_local std::string g_err;
+
+extern "C" {
+const char* emu_last_error() { return g_err.c_str(); }
+
+void* emu_new(const uint32_t* prg, uint64_t n, uint32_t k) {
+  try {
+    auto* e = new Emu();
+    build_host_index(prg, n, k, e->h);
+    uint64_t na = e->h.allele_off.back();
+    e->counters.assign(2 * na + e->h.n_per_base + 1, 0);
+    uint32_t cap = 1024;
+    while (cap < 4 * na) cap <<= 1;
+    e->gtab.assign(cap, 0);
+    e->gcount.assign(cap, 0);
+    e->gpool.assign((size_t)cap * 4, 0);
+    e->gsmall.assign(4, 0);
+    return e;
+  } catch (const std::exception& ex) {
+    g_err = ex.what();
+    return nullptr;
+  }
+}
+void emu_free(void* e) { delete (Emu*)e; }
+
+void emu_sizes(void* ev, uint64_t out[6]) {
+  auto* e = (Emu*)ev;
+  out[0] = e->h.n_sites;
+  out[1] = e->h.allele_off.back();
+  out[2] = e->h.n_per_base;
+  out[3] = e->h.is_nested;
+  out[4] = e->h.n;
+  out[5] = e->h.kmer_off.back();
+}
+
+// k-mer index dump for parity with the oracle's index: per k-mer code the canonical record list
+uint64_t emu_kmer_states(void* ev, uint32_t* words) {
+  auto* e = (Emu*)ev;
+  const HostIndex& h = e->h;
+  uint64_t t = 0;
+  uint64_t nk = 1ull << (2 * h.k);
+  for (uint64_t c = 0; c < nk; ++c) {
+    for (uint32_t j = h.kmer_off[c]; j < h.kmer_off[c + 1]; ++j) {
+      const KmerState& ks = h.kmer_states[j];
+      uint32_t nt = ks.counts & 0xFFFF, ng = ks.counts >> 16;
+      if (words) {
+        words[t] = (uint32_t)c;
+        words[t + 1] = ks.lo;
+        words[t + 2] = ks.hi;
+        words[t + 3] = nt;
+        words[t + 4] = ng;
+        for (uint32_t i = 0; i < 2 * nt; ++i) words[t + 5 + i] = h.kmer_paths[ks.path_off + i];
+        for (uint32_t i = 0; i < ng; ++i) {
+          words[t + 5 + 2 * nt + 2 * i] = h.kmer_paths[ks.path_off + 2 * nt + i];
+          words[t + 5 + 2 * nt + 2 * i + 1] = kNoAllele;
+        }
+      }
+      t += 5 + 2 * nt + 2 * ng;
+    }
+  }
+  return t;
+}
+void emu_sa(void* ev, uint32_t* out) {
+  auto* e = (Emu*)ev;
+  std::memcpy(out, e->h.sa.data(), e->h.sa.size() * 4);
+}
+
+int emu_map(void* ev, const uint8_t* bases, const uint64_t* off, uint64_t n_reads, const uint32_t* seeds,
+            uint32_t arena_words) {
+  auto* e = (Emu*)ev;
+  try {
+    const HostIndex& h = e->h;
+    IndexView v = h.view();
+    // pack as pack_kernel does
+    std::vector<uint32_t> word_off(n_reads + 1), len(n_reads), packed;
+    for (uint64_t r = 0; r < n_reads; ++r) {
+      word_off[r] = (uint32_t)packed.size();
+      uint32_t L = (uint32_t)(off[r + 1] - off[r]);
+      len[r] = L;
+      for (uint32_t w = 0; w < (L + 15) / 16; ++w) {
+        uint32_t x = 0;
+        for (uint32_t j = 0; j < 16 && w * 16 + j < L; ++j) x |= ((uint32_t)(bases[off[r] + w * 16 + j] - 1) & 3u) << (2 * j);
+        packed.push_back(x);
+      }
+    }
+    word_off[n_reads] = (uint32_t)packed.size();
+    packed.push_back(0);
+    e->n_reads = (uint32_t)n_reads;
+    e->status.assign(2 * n_reads, 0);
+    e->st_off.assign(2 * n_reads, 0);
+    e->st_words.assign(2 * n_reads, 0);
+    e->st_count.assign(2 * n_reads, 0);
+    e->pool.assign(std::max<size_t>(1 << 16, n_reads * 256), 0);
+    std::vector<uint32_t> small(4, 0), ovf(2 * n_reads + 1), cov_ovf(2 * n_reads + 1);
+    BatchView b{packed.data(), word_off.data(), len.data(), seeds, (uint32_t)n_reads};
+    SearchOut o{e->status.data(), e->st_off.data(), e->st_words.data(), e->st_count.data(), e->pool.data(),
+                (uint32_t)e->pool.size(), &small[0], ovf.data(), &small[1]};
+    CoverageView c{};
+    uint64_t na = h.allele_off.back();
+    c.allele_sum = e->counters.data();
+    c.grouped_single = e->counters.data() + na;
+    c.per_base = e->counters.data() + 2 * na;
+    c.gtab = e->gtab.data();
+    c.gcount = e->gcount.data();
+    c.gtab_cap = (uint32_t)e->gtab.size();
+    c.gpool = e->gpool.data();
+    c.gpool_cap = (uint32_t)e->gpool.size();
+    c.gpool_used = &e->gsmall[0];
+    c.error_flags = &e->gsmall[1];
+    c.stats = e->stats;
+    c.allele_off = h.allele_off.data();
+    std::vector<uint32_t> arena(arena_words), big;
+    for (uint32_t s = 0; s < 2 * n_reads; ++s) {
+      uint32_t aw = arena_words;
+      uint32_t* a = arena.data();
+      while (true) {  // same policy as the library: re-run the strand with a 4x larger arena
+        small[1] = 0;
+        map_strand(v, v.super_cnt, b, o, s, a, aw);
+        if (e->status[s] != ST_OVERFLOW) break;
+        e->reruns++;
+        aw *= 4;
+        if (aw > (1u << 28)) throw std::runtime_error("emu: arena overflow persists");
+        big.assign(aw, 0);
+        a = big.data();
+      }
+      if (e->status[s] != ST_MAPPED) continue;
+      while (!record_strand(v, b, o, c, s, a, aw)) {
+        e->reruns++;
+        aw *= 4;
+        if (aw > (1u << 28)) throw std::runtime_error("emu: coverage scratch overflow persists");
+        big.assign(aw, 0);
+        a = big.data();
+      }
+    }
+    for (uint64_t r = 0; r < n_reads; ++r) {
+      e->stats[0] += 2;
+      for (int s = 0; s < 2; ++s) {
+        uint8_t st = e->status[2 * r + s];
+        if (st == ST_SKIPPED) e->stats[1]++;
+        else if (st == ST_MISSING_KMER) e->stats[2]++;
+        else if (st == ST_NO_EXTENSION) e->stats[3]++;
+        else if (st == ST_MAPPED) e->stats[4]++;
+      }
+    }
+    if (e->gsmall[1]) throw std::runtime_error("emu: coverage error flags " + std::to_string(e->gsmall[1]));
+    return 0;
+  } catch (const std::exception& ex) {
+    g_err = ex.what();
+    return -1;
+  }
+}
+uint64_t emu_reruns(void* ev) { return ((Emu*)ev)->reruns; }
+void emu_status(void* ev, uint8_t* out) {
+  auto* e = (Emu*)ev;
+  std::memcpy(out, e->status.data(), e->status.size());
+}
+uint64_t emu_states_size(void* ev) {
+  auto* e = (Emu*)ev;
+  uint64_t t = 0;
+  for (size_t i = 0; i < e->st_words.size(); ++i)
+    if (e->status[i] == ST_MAPPED) t += e->st_words[i];
+  return t;
+}
+void emu_states(void* ev, uint64_t* off, uint32_t* count, uint32_t* words) {
+  auto* e = (Emu*)ev;
+  uint64_t t = 0;
+  for (size_t i = 0; i < e->st_words.size(); ++i) {
+    off[i] = t;
+    bool m = e->status[i] == ST_MAPPED;
+    count[i] = m ? e->st_count[i] : 0;
+    if (m) {
+      std::memcpy(words + t, e->pool.data() + e->st_off[i], (size_t)e->st_words[i] * 4);
+      t += e->st_words[i];
+    }
+  }
+  off[e->st_words.size()] = t;
+}
+void emu_allele_sum(void* ev, uint16_t* out) {
+  auto* e = (Emu*)ev;
+  uint64_t na = e->h.allele_off.back();
+  for (uint64_t i = 0; i < na; ++i) out[i] = (uint16_t)(e->counters[i] & 0xFFFF);
+}
+void emu_per_base(void* ev, uint16_t* out) {
+  auto* e = (Emu*)ev;
+  uint64_t na = e->h.allele_off.back();
+  for (uint64_t i = 0; i < e->h.n_per_base; ++i) out[i] = (uint16_t)std::min<uint32_t>(e->counters[2 * na + i], 65535u);
+}
+uint64_t emu_grouped(void* ev, uint32_t* words) {
+  auto* e = (Emu*)ev;
+  const HostIndex& h = e->h;
+  uint64_t na = h.allele_off.back();
+  std::map<std::vector<uint32_t>, uint64_t> g;
+  for (uint32_t s = 0; s < h.n_slots; ++s)
+    for (uint32_t a = 0; a < h.n_alleles[s]; ++a)
+      if (e->counters[na + h.allele_off[s] + a]) g[{s, a}] += e->counters[na + h.allele_off[s] + a];
+  for (size_t i = 0; i < e->gtab.size(); ++i) {
+    if (!e->gtab[i] || !e->gcount[i]) continue;
+    const uint32_t* rec = e->gpool.data() + (e->gtab[i] - 1);
+    std::vector<uint32_t> key{rec[0]};
+    key.insert(key.end(), rec + 2, rec + 2 + rec[1]);
+    g[key] += e->gcount[i];
+  }
+  uint64_t t = 0;
+  for (auto& kv : g) {
+    if (words) {
+      words[t] = kv.first[0];
+      words[t + 1] = (uint32_t)(kv.second & 0xFFFF);
+      words[t + 2] = (uint32_t)kv.first.size() - 1;
+      for (size_t i = 1; i < kv.first.size(); ++i) words[t + 2 + i] = kv.first[i];
+    }
+    t += 2 + kv.first.size();
+  }
+  return t;
+}
+void emu_stats(void* ev, uint64_t out[5]) {
+  auto* e = (Emu*)ev;
+  for (int i = 0; i < 5; ++i) out[i] = e->stats[i];
+}
+}
