@@ -548,7 +548,10 @@ void process_markers_search_states(const PRGInfo& info, SearchStates& states, Ev
 }
 
 SearchStates search_base_backwards(const PRGInfo& info, Base b, const SearchStates& states, Events* ev) {  // BWT_search.cpp:78-94
-  SA_Index first = (SA_Index)info.fm.C[info.fm.char2comp.at(b)];
+  // sdsl's int alphabet maps a symbol absent from the text to comp 0 (C[0] = 0); its rank is always 0,
+  // so every state then fails the validity test below.
+  auto cit = info.fm.char2comp.find(b);
+  SA_Index first = (SA_Index)info.fm.C[cit == info.fm.char2comp.end() ? 0 : cit->second];
   SearchStates out;
   for (const auto& s : states) {
     // base_next_sa_interval :45-76

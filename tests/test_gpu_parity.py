@@ -1,0 +1,126 @@
+"""GPU suite (`-m gpu`): the CUDA path through the C ABI (libgq.so) against the oracle on the same
+seeded inputs — final SearchStates (SA intervals + both paths), all three coverage structures and the
+five counters, bit-exact."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from common import ROOT, Oracle, assert_parity, gpu_result
+from gramtools_b200 import QuasimapIndex, encode_reads, master_seeds, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _reads_for(prg, n, L, seed, garbage=0.05, n_frac=0.02):
+    rng = np.random.default_rng(seed)
+    haps = [synth.random_haplotype(prg, rng) for _ in range(4)]
+    return synth.sample_reads(haps, n, L, seed, frac_garbage=garbage, frac_n=n_frac)
+
+
+def _check(prg, k, bases, offs, seed=42, what="", options=None, threads=1):
+    seeds = master_seeds(seed, offs.size - 1)
+    idx = QuasimapIndex(prg, k, device=0)
+    for name, val in (options or {}).items():
+        idx.set_option(name, val)
+    idx.map_batch(bases, offs, seeds)
+    got = gpu_result(idx)
+    o = Oracle(prg, k)
+    o.map(bases, offs, seeds, threads=threads)
+    ref = o.result()
+    assert_parity(got, ref, what)
+    idx.close()
+    return got, ref
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_snp_prg(built_lib, seed):
+    prg, _, _, _ = synth.make_snp_prg(2000, 120, seed)
+    bases, offs = _reads_for(prg, 3000, 60, seed)
+    got, ref = _check(prg, 5, bases, offs, what=f"snp{seed}")
+    assert ref.stats[4] > 1000
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_nested_prg(built_lib, seed):
+    prg = synth.make_nested_prg(4, 300, seed)
+    bases, offs = _reads_for(prg, 3000, 30, seed)
+    got, ref = _check(prg, 4, bases, offs, what=f"nested{seed}")
+    assert ref.grouped.size > 0
+
+
+def test_config1_toy(built_lib):
+    """BASELINE config 1: 1 kb ref + 50 biallelic SNPs, 10k x 100 bp reads, k=5."""
+    prg, ref, pos, alt = synth.make_snp_prg(1000, 50, 0x6772616D)
+    haps = synth.snp_haplotypes(ref, pos, alt, 8, 1)
+    bases, offs = synth.sample_reads(haps, 10000, 100, 2)
+    got, _ = _check(prg, 5, bases, offs, what="config1", threads=8)
+    assert got.stats[0] == 20000
+
+
+def test_overflow_reruns(built_lib):
+    prg = synth.make_nested_prg(3, 250, 11)
+    bases, offs = _reads_for(prg, 2000, 25, 11, garbage=0, n_frac=0)
+    got, _ = _check(prg, 3, bases, offs, what="tiny-arena", options={"arena_words": 40})
+    assert got.extra["rerun_strands"] > 0
+
+
+def test_edge_cases_and_accumulation(built_lib):
+    prg = np.asarray(synth.make_snp_prg(300, 20, 3)[0])
+    rng = np.random.default_rng(0)
+    hap = synth.random_haplotype(prg, rng)
+    s = lambda a: "".join("?ACGT"[x] for x in a)
+    reads = ["", "ACGTNACGTACGT", "ACG", s(hap[:5]), s(hap[10:16]), s(hap[:120]), s(hap[-40:]), s(hap[:40]), "A" * 30]
+    bases, offs = encode_reads(reads)
+    _check(prg, 5, bases, offs, what="edges")
+    # coverage accumulates across batches; empty batch is a no-op
+    idx = QuasimapIndex(prg, 5)
+    o = Oracle(prg, 5)
+    for b in range(3):
+        bb, oo = _reads_for(prg, 500, 40, 100 + b)
+        sd = master_seeds(7 + b, 500)
+        idx.map_batch(bb, oo, sd)
+        o.map(bb, oo, sd)
+    e_b, e_o = encode_reads([])
+    idx.map_batch(e_b, e_o, np.zeros(0, np.uint32))
+    got = gpu_result(idx)
+    ref = o.result()
+    assert got.stats == ref.stats
+    assert np.array_equal(got.allele_sum, ref.allele_sum) and np.array_equal(got.per_base, ref.per_base)
+    assert np.array_equal(got.grouped, ref.grouped)
+    idx.reset_coverage()
+    a, p, st = idx.coverage()
+    assert a.sum() == 0 and p.sum() == 0 and st.all_reads_count == 0
+
+
+def test_integration_fixtures(built_lib):
+    with open(os.path.join(ROOT, "tests", "golden", "it_fixtures.json")) as f:
+        fx = json.load(f)
+    for name, case in fx.items():
+        bases, offs = encode_reads(case["reads"])
+        got, _ = _check(np.asarray(case["prg"], dtype=np.uint32), case["kmer_size"], bases, offs, what=name)
+        if "allele_base_counts" in case:
+            flat = [c for site in case["allele_base_counts"] for allele in site for c in allele]
+            assert list(got.per_base) == flat
+
+
+def test_medium_snp_properties(built_lib):
+    """Larger than the oracle comfortably checks state-by-state: coverage parity without states plus
+    size-independent properties (counters add up; every error-free read maps on exactly one strand
+    or both; allele_sum >= grouped singles)."""
+    prg, ref, pos, alt = synth.make_snp_prg(200_000, 4000, 5)
+    haps = synth.snp_haplotypes(ref, pos, alt, 8, 6)
+    bases, offs = synth.sample_reads(haps, 100_000, 150, 7)
+    seeds = master_seeds(42, 100_000)
+    idx = QuasimapIndex(prg, 8)
+    idx.map_batch(bases, offs, seeds)
+    got = gpu_result(idx)
+    st = got.stats
+    assert st[0] == 200_000 and st[1] + st[2] + st[3] + st[4] == st[0]
+    status = got.status.reshape(-1, 2)
+    assert ((status == 3).sum(axis=1) >= 1).all(), "an error-free read failed to map on either strand"
+    o = Oracle(prg, 8)
+    o.map(bases, offs, seeds, threads=8, want_states=False)
+    ref_r = o.result(want_states=False)
+    assert_parity(got, ref_r, "medium", check_states=False)

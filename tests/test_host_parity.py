@@ -1,0 +1,153 @@
+"""CPU suite: the product's host code (flat index builder, k-mer index) and — through the test-only
+host emulation of the device functions (tests/emu) — the per-strand search/coverage logic, against
+the oracle. Bit-exact: integer path, no tolerance."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from common import ROOT, Emu, Oracle, assert_parity
+from gramtools_b200 import encode_reads, master_seeds, synth
+
+
+def _reads_for(prg, n, L, seed, garbage=0.05, n_frac=0.02):
+    rng = np.random.default_rng(seed)
+    haps = [synth.random_haplotype(prg, rng) for _ in range(4)]
+    return synth.sample_reads(haps, n, L, seed, frac_garbage=garbage, frac_n=n_frac)
+
+
+def _check(prg, k, bases, offs, seed=42, arena_words=256, what=""):
+    seeds = master_seeds(seed, offs.size - 1)
+    o, e = Oracle(prg, k), Emu(prg, k)
+    assert (o.n_sites, o.n_alleles, o.n_per_base, o.is_nested, o.sa_size, o.n_kmer_states) == \
+           (e.n_sites, e.n_alleles, e.n_per_base, e.is_nested, e.sa_size, e.n_kmer_states)
+    o.map(bases, offs, seeds)
+    e.map(bases, offs, seeds, arena_words=arena_words)
+    ro, re = o.result(), e.result()
+    assert_parity(re, ro, what)
+    return ro, re
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_snp_prg_parity(seed):
+    prg, _, _, _ = synth.make_snp_prg(800, 60, seed)
+    bases, offs = _reads_for(prg, 500, 50, seed)
+    ro, _ = _check(prg, 5, bases, offs, what=f"snp{seed}")
+    assert ro.stats[4] > 100 and ro.allele_sum.sum() > 0 and ro.per_base.sum() > 0
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_nested_prg_parity(seed):
+    prg = synth.make_nested_prg(3, 250, seed)
+    bases, offs = _reads_for(prg, 500, 30, seed)
+    ro, _ = _check(prg, 4, bases, offs, what=f"nested{seed}")
+    assert ro.stats[4] > 100 and ro.grouped.size > 0
+
+
+def test_tiny_arena_forces_overflow_reruns():
+    """Arena overflow must re-run the strand with a larger arena, never truncate."""
+    prg = synth.make_nested_prg(2, 200, 11)
+    bases, offs = _reads_for(prg, 300, 25, 11, garbage=0, n_frac=0)
+    _, re = _check(prg, 3, bases, offs, arena_words=40, what="tiny-arena")
+    assert re.extra["reruns"] > 0
+
+
+def test_edge_cases():
+    prg = np.asarray(synth.make_snp_prg(300, 20, 3)[0])
+    k = 5
+    rng = np.random.default_rng(0)
+    hap = synth.random_haplotype(prg, rng)
+    s = lambda a: "".join("?ACGT"[x] for x in a)
+    reads = [
+        "",                       # empty read -> skipped
+        "ACGTNACGTACGT",          # non-ACGT -> emptied -> skipped (utils.cpp:72-81)
+        "ACG",                    # shorter than k
+        s(hap[:k]),               # exactly k
+        s(hap[10:10 + k + 1]),
+        s(hap[:120]),             # long read
+        s(hap[-40:]),             # touches the PRG end
+        s(hap[:40]),              # touches the PRG start
+        "A" * 30, "acgtacgtacgtacgt",
+    ]
+    bases, offs = encode_reads(reads)
+    ro, _ = _check(prg, k, bases, offs, what="edges")
+    assert ro.stats[0] == 2 * len(reads) and ro.stats[1] == 4
+    # ragged batch with zero reads
+    bases, offs = encode_reads([])
+    _check(prg, k, bases, offs, what="empty-batch")
+
+
+def test_reference_test_prgs():
+    """PRGs + reads of the reference's quasimap tests (test_quasimap.cpp), both strands."""
+    import ctypes as C
+    cases = [
+        ("gct5c6g6t6ag7t8c8cta", ["agccta", "agtcta", "ctgagtcta", "tagtcta", "tgtcta", "gctc", "tagt", "gagt", "cagc"]),
+        ("TAG5Tc6g6T6AG7T8c8cta", ["tagt"] * 8),
+        ("gtagtac5gtagtact6t6ta", ["gtagt"] * 8),
+        ("ac5gtagtact6t6gggtagt6ta", ["gtagt"] * 4),
+        ("tac5gta6gtt6ta", ["tacgt"]),
+        ("gcac5t6g6c6ta7t8c8cta", ["accta", "gcact"]),
+    ]
+    from common import oracle_lib
+    for numbered, reads in cases:
+        # numbered -> ints
+        prg, num = [], ""
+        for ch in numbered:
+            if ch.isdigit():
+                num += ch
+            else:
+                if num:
+                    prg.append(int(num)); num = ""
+                prg.append("acgt".index(ch.lower()) + 1)
+        if num:
+            prg.append(int(num))
+        bases, offs = encode_reads(reads)
+        for seed in (42, 150, 29, 200):
+            _check(np.asarray(prg, dtype=np.uint32), 2, bases, offs, seed=seed, what=numbered)
+    nested = ["a[c,g[ct,t]a]c", "t[a[c,g][c,g],]t", "A[[A[CCC,c],t],g]TA", "a[t[tt,t]t,a[at,]a]g[c,g]",
+              "[AC,[C,G]]T", "[C,G][C,G]", "A[C,,G]T", "AT[GC[GCC,CCGC],T]TTTT", "AAT[ATAT,AA,]AGG"]
+    nreads = ["agtac", "tt", "tacct", "AACCCTA", "CTA", "ATTTTGC", "TT", "AAAGG", "ACT", "CT", "GT", "AT",
+              "CGCCTT", "ATTTT", "GCC", "CTTT", "ATAT", "ATAAA", "AATAGG"]
+    for br in nested:
+        stack, nid, prg = [], 3, []
+        for ch in br:
+            if ch == "[":
+                nid += 2; stack.append(nid); prg.append(nid)
+            elif ch == "]":
+                prg.append(stack.pop() + 1)
+            elif ch == ",":
+                prg.append(stack[-1] + 1)
+            else:
+                prg.append("acgt".index(ch.lower()) + 1)
+        bases, offs = encode_reads(nreads)
+        for k in (1, 2):
+            _check(np.asarray(prg, dtype=np.uint32), k, bases, offs, what=br)
+
+
+def test_integration_fixtures_through_product_code():
+    with open(os.path.join(ROOT, "tests", "golden", "it_fixtures.json")) as f:
+        fx = json.load(f)
+    for name, case in fx.items():
+        bases, offs = encode_reads(case["reads"])
+        _check(np.asarray(case["prg"], dtype=np.uint32), case["kmer_size"], bases, offs, what=name)
+
+
+def test_suffix_array_matches_oracle_order():
+    prg = synth.make_nested_prg(4, 300, 5)
+    e = Emu(prg, 3)
+    sa = e.sa()
+    text = np.concatenate([prg, [0]]).astype(np.int64)
+    assert sorted(sa.tolist()) == list(range(text.size))
+    # adjacent suffixes strictly increasing
+    for a, b in zip(sa[:-1], sa[1:]):
+        ta, tb = text[a:], text[b:]
+        m = min(ta.size, tb.size)
+        d = np.nonzero(ta[:m] != tb[:m])[0]
+        assert d.size and ta[d[0]] < tb[d[0]]
+
+
+def test_malformed_prgs_rejected():
+    for bad in ([5, 1, 6, 2, 6, 5, 3, 6, 4, 6], [1, 5, 2, 6, 4], [1, 5, 6, 2], [1, 6, 2, 6], [1, 5, 2, 6, 3]):
+        with pytest.raises(RuntimeError):
+            Emu(np.asarray(bad, dtype=np.uint32), 2)
