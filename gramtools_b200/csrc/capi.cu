@@ -72,12 +72,13 @@ struct gq_index {
   DevBuf<uint32_t> overflow_list, cov_overflow_list;
   DevBuf<uint32_t> arena, big_arena;
   // options
-  uint32_t arena_words = 256;
+  uint32_t arena_words = 512;
   uint32_t n_threads = 148 * 1024;
   uint32_t big_arena_words = 1u << 16;
   uint32_t big_threads = 2048;
   uint32_t pool_words_per_read = 48;
   bool super_in_smem = true;
+  uint32_t rf_thresh = 8, ev_thresh = 8;
   // run info
   double info[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
@@ -220,7 +221,7 @@ static void do_map(gq_index* ix) {
   size_t pool_need = std::max<size_t>((size_t)n * ix->pool_words_per_read, 1 << 16);
   pool_need = std::min<size_t>(pool_need, 0xFFFFFFF0ull);
   ix->pool.reserve(pool_need);
-  uint32_t threads = std::min<uint32_t>(ix->n_threads, ((n + 255) / 256) * 256);
+  uint32_t threads = std::min<uint32_t>(ix->n_threads, ((2 * n + 255) / 256) * 256);
   // the coverage kernel walks strands: give it the same arena (2n strands over `threads2` threads)
   uint32_t threads2 = std::min<uint32_t>(ix->n_threads, ((2 * n + 255) / 256) * 256);
   ix->arena.reserve((size_t)std::max(threads, threads2) * ix->arena_words);
@@ -232,7 +233,7 @@ static void do_map(gq_index* ix) {
   gq::CoverageView c = cov_view(ix);
   int launches = 0;
   CUDA_OK(cudaEventRecord(ix->ev[0], st));
-  gq::launch_search(ix->dv, b, o, ix->arena.p, ix->arena_words, threads, nullptr, 0, ix->super_in_smem, st);
+  gq::launch_search(ix->dv, b, o, ix->arena.p, ix->arena_words, threads, nullptr, 0, ix->super_in_smem, ix->rf_thresh, ix->ev_thresh, st);
   ++launches;
   CUDA_OK(cudaEventRecord(ix->ev[1], st));
   gq::launch_coverage(ix->dv, b, o, c, ix->arena.p, ix->arena_words, threads2, nullptr, 0, ix->cov_overflow_list.p,
@@ -278,7 +279,7 @@ static void do_map(gq_index* ix) {
     list.reserve(n_list);
     CUDA_OK(cudaMemcpyAsync(list.p, ix->overflow_list.p, (size_t)n_list * 4, cudaMemcpyDeviceToDevice, st));
     CUDA_OK(cudaMemsetAsync(ix->small.p + 1, 0, 4, st));
-    gq::launch_search(ix->dv, b, o, ix->big_arena.p, big_words, bt, list.p, n_list, ix->super_in_smem, st);
+    gq::launch_search(ix->dv, b, o, ix->big_arena.p, big_words, bt, list.p, n_list, ix->super_in_smem, ix->rf_thresh, ix->ev_thresh, st);
     gq::launch_coverage(ix->dv, b, o, c, ix->big_arena.p, big_words, bt, list.p, n_list, ix->cov_overflow_list.p,
                         ix->small.p + 2, st);
     launches += 2;
@@ -707,6 +708,10 @@ int gq_set_option(gq_index* ix, const char* name, int64_t value) {
   } else if (n == "pool_words_per_read") {
     ix->pool_words_per_read = (uint32_t)std::max<int64_t>(value, 1);
     ix->pool.release();
+  } else if (n == "rf_thresh") {
+    ix->rf_thresh = (uint32_t)value;
+  } else if (n == "ev_thresh") {
+    ix->ev_thresh = (uint32_t)value;
   } else if (n == "super_in_smem") {
     ix->super_in_smem = value != 0;
   } else

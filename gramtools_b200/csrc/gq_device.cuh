@@ -150,24 +150,205 @@ struct EmitStage {
   }
 };
 
-GQ_DEV void map_strand(const IndexView& v, const uint32_t* super_cnt, const BatchView& b, const SearchOut& o,
-                           uint32_t strand, uint32_t* arena, uint32_t arena_words) {
+// ------------------------------------------------------------------------------------------------
+// Lane state machine of the search kernel. One lane maps one strand at a time; the warp runs ONE flat
+// loop in which every lane executes the same unit operation per iteration, so lanes re-converge every
+// iteration instead of drifting apart inside nested per-read loops:
+//   lane_refill : idle lane takes the next strand, seeds its stack from the k-mer index
+//   lane_step   : the hot path — one read base: marker test + backward extension, registers only
+//   lane_event  : everything rare — marker scan / jumps, emitting finished states, pops, strand end
+// Order of work differs from quasimap_read (quasimap.cpp:159-194) without changing results: the search
+// runs first and the k-mer filter (all_read_kmers_occur_in_index, :212-225) is evaluated afterwards only
+// for strands that produced no state (classify_strand) — a strand that maps end to end necessarily has
+// all of its k-mers in the index, which holds every k-mer with >= 1 search state.
+// ------------------------------------------------------------------------------------------------
+enum LaneState : uint32_t { LS_IDLE = 0, LS_RUN = 1, LS_EV_SCAN = 2, LS_EV_POP = 3, LS_EV_TOP = 4, LS_EV_WIDE = 5 };
+constexpr uint8_t ST_UNCLASSIFIED = 4;  // search produced no state: classify_strand decides 1 vs 2
+
+struct Lane {
+  uint32_t state;
+  uint32_t strand;
+  ReadCursor rd;
+  Stack s;
+  uint32_t n_states;
+  uint32_t arena_words;
+  // top entry cached in registers while state == LS_RUN
+  uint32_t pos, lo, hi, kind;
+};
+
+GQ_DEV inline void lane_writeback(Lane& ln, uint32_t kind) {
+  uint32_t* t = ln.s.mem + ln.s.top;
+  t[0] = ln.pos | (kind << 28);
+  t[1] = ln.lo;
+  t[2] = ln.hi;
+}
+
+// decide what the (memory) top of the stack needs next
+GQ_DEV inline void lane_load_top(Lane& ln) {
+  const uint32_t* t = ln.s.mem + ln.s.top;
+  uint32_t w0 = t[0];
+  ln.kind = w0 >> 28;
+  ln.pos = w0 & 0x0FFFFFFFu;
+  ln.lo = t[1];
+  ln.hi = t[2];
+  ln.state = (ln.kind == K_JUMP || ln.pos == 0) ? LS_EV_TOP : LS_RUN;
+}
+
+GQ_DEV inline void lane_finish_strand(Lane& ln, const SearchOut& o) {
+  uint32_t words = ln.arena_words - ln.s.limit;
+  if (!ln.s.overflow && words) {
+    uint32_t off = gq_atomic_add(o.pool_used, words);
+    if (off + words > o.pool_cap) ln.s.overflow = true;
+    else {
+      for (uint32_t w = 0; w < words; ++w) o.pool[off + w] = ln.s.mem[ln.s.limit + w];
+      o.st_off[ln.strand] = off;
+      o.st_words[ln.strand] = words;
+      o.st_count[ln.strand] = ln.n_states;
+    }
+  }
+  if (ln.s.overflow) {
+    o.status[ln.strand] = ST_OVERFLOW;
+    o.overflow_list[gq_atomic_add(o.n_overflow, 1u)] = ln.strand;
+  } else
+    o.status[ln.strand] = ln.n_states ? ST_MAPPED : ST_UNCLASSIFIED;
+  ln.state = LS_IDLE;
+}
+
+// Start `strand` on this lane: seed with the index entry of its last k-mer (quasimap.cpp:178,235-241).
+GQ_DEV inline void lane_refill(Lane& ln, const IndexView& v, const BatchView& b, const SearchOut& o, uint32_t strand,
+                               uint32_t* arena, uint32_t arena_words) {
   const uint32_t r = strand >> 1;
   const uint32_t L = b.len[r];
   const uint32_t k = v.k;
-  if (L == 0) {  // non-ACGT read, emptied by the encoder: skipped (quasimap.cpp:108-113)
-    o.status[strand] = ST_SKIPPED;
-    o.st_count[strand] = 0;
-    return;
-  }
-  ReadCursor rd{b.packed + b.word_off[r], L, (strand & 1u) != 0, 0xFFFFFFFFu, 0};
+  ln.strand = strand;
+  ln.state = LS_IDLE;
   o.st_count[strand] = 0;
   o.st_words[strand] = 0;
-  // all_read_kmers_occur_in_index (quasimap.cpp:212-225); reads shorter than k cannot be seeded
-  if (L < k) {
+  if (L == 0) {  // non-ACGT read, emptied by the encoder: skipped (quasimap.cpp:108-113)
+    o.status[strand] = ST_SKIPPED;
+    return;
+  }
+  if (L < k) {  // cannot be seeded (UB in the reference, quasimap.cpp:206-210): counted as missing k-mer
     o.status[strand] = ST_MISSING_KMER;
     return;
   }
+  ln.rd = ReadCursor{b.packed + b.word_off[r], L, (strand & 1u) != 0, 0xFFFFFFFFu, 0};
+  uint32_t code = 0;
+  for (uint32_t i = L - k; i < L; ++i) code = (code << 2) | ln.rd(i);
+  uint32_t sb = GQ_LDG(v.kmer_off + code), se = GQ_LDG(v.kmer_off + code + 1);
+  if (sb == se) {  // the seeding k-mer itself is not indexed: the k-mer filter fails
+    o.status[strand] = ST_MISSING_KMER;
+    return;
+  }
+  ln.s.mem = arena;
+  ln.s.limit = arena_words;
+  ln.s.overflow = false;
+  ln.s.top = kNoAllele;
+  ln.n_states = 0;
+  ln.arena_words = arena_words;
+  uint32_t sp = 0;
+  for (uint32_t j = sb; j < se; ++j) {
+    KmerState ks = v.kmer_states[j];
+    uint32_t words = entry_words(ks.counts);
+    if (sp + words + 3 > ln.s.limit) {
+      ln.s.overflow = true;
+      break;
+    }
+    uint32_t* t = ln.s.mem + sp;
+    t[0] = (L - k) | (K_SCAN << 28);
+    t[1] = ks.lo;
+    t[2] = ks.hi;
+    t[3] = ks.counts;
+    t[4] = ln.s.top;
+    for (uint32_t w = kHdr; w < words; ++w) t[w] = GQ_LDG(v.kmer_paths + ks.path_off + (w - kHdr));
+    ln.s.top = sp;
+    sp += words;
+  }
+  if (ln.s.overflow) {
+    lane_finish_strand(ln, o);
+    return;
+  }
+  lane_load_top(ln);
+}
+
+// The hot path: one base for a lane in LS_RUN. Everything lives in registers; memory traffic is one
+// (or two) 32 B rank-block sectors. Any non-trivial outcome parks the lane in an event state.
+GQ_DEV inline void lane_step(Lane& ln, const IndexView& v, const uint32_t* super_cnt) {
+  const uint32_t lo = ln.lo, hi = ln.hi;
+  const uint32_t b0 = lo >> kBlkShift, bh = hi >> kBlkShift, b1 = (hi + 1) >> kBlkShift;
+  RankBlk B0 = load_blk(v.rank_blk + b0);
+  RankBlk B1 = (b1 == b0) ? B0 : load_blk(v.rank_blk + b1);
+  if (ln.kind == K_SCAN) {
+    uint64_t mk;
+    if (bh == b0) mk = marker_bits_in(B0, b0 << kBlkShift, lo, hi);
+    else if (bh == b1 && b1 == b0 + 1)
+      mk = marker_bits_in(B0, b0 << kBlkShift, lo, hi) | marker_bits_in(B1, b1 << kBlkShift, lo, hi);
+    else {  // interval wider than the two fetched blocks: rare, resolved in the event path
+      ln.state = LS_EV_WIDE;
+      return;
+    }
+    if (mk) {
+      ln.state = LS_EV_SCAN;
+      return;
+    }
+  }
+  const uint32_t c = ln.rd(ln.pos - 1);
+  const uint32_t r0 = rank_in_blk(B0, super_cnt + 4 * (b0 >> (kSuperShift - kBlkShift)), c, lo);
+  const uint32_t r1 = rank_in_blk(B1, super_cnt + 4 * (b1 >> (kSuperShift - kBlkShift)), c, hi + 1);
+  if (r1 <= r0) {
+    ln.state = LS_EV_POP;
+    return;
+  }
+  ln.lo = v.c_base[c] + r0;
+  ln.hi = v.c_base[c] + r1 - 1;
+  ln.kind = K_SCAN;
+  if (--ln.pos == 0) {
+    lane_writeback(ln, K_SCAN);
+    ln.state = LS_EV_TOP;
+  }
+}
+
+// One transition of the rare path. Ends in LS_RUN, LS_IDLE (strand finished) or another event state.
+GQ_DEV inline void lane_event(Lane& ln, const IndexView& v, const SearchOut& o) {
+  switch (ln.state) {
+    case LS_EV_WIDE:
+      if (!interval_has_marker(v, ln.lo, ln.hi)) {
+        ln.kind = K_READY;  // scanned, nothing found: extend without re-scanning
+        ln.state = LS_RUN;
+        return;
+      }
+      // fallthrough
+    case LS_EV_SCAN:
+      lane_writeback(ln, K_READY);
+      scan_markers(ln.s, v, ln.pos, ln.lo, ln.hi);
+      break;
+    case LS_EV_POP:
+      pop(ln.s);
+      break;
+    default: {  // LS_EV_TOP: a pending locus, or a finished state
+      uint32_t* t = ln.s.mem + ln.s.top;
+      if ((t[0] >> 28) == K_JUMP) process_jump(ln.s, v);
+      else {
+        EmitStage emit{&ln.s, &v, ln.n_states};
+        emit(t);
+        ln.n_states = emit.n_states;
+        pop(ln.s);
+      }
+    }
+  }
+  if (ln.s.overflow || stack_empty(ln.s)) {
+    lane_finish_strand(ln, o);
+    return;
+  }
+  lane_load_top(ln);
+}
+
+// all_read_kmers_occur_in_index (quasimap.cpp:212-225) for a strand whose search found nothing:
+// any k-mer absent from the index -> missing_kmer, else no_extension (quasimap.cpp:170-186).
+GQ_DEV inline void classify_strand(const IndexView& v, const BatchView& b, const SearchOut& o, uint32_t strand) {
+  const uint32_t r = strand >> 1;
+  const uint32_t L = b.len[r], k = v.k;
+  ReadCursor rd{b.packed + b.word_off[r], L, (strand & 1u) != 0, 0xFFFFFFFFu, 0};
   const uint32_t mask = (k == 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
   uint32_t code = 0;
   bool missing = false;
@@ -178,54 +359,19 @@ GQ_DEV void map_strand(const IndexView& v, const uint32_t* super_cnt, const Batc
       break;
     }
   }
-  if (missing) {
-    o.status[strand] = ST_MISSING_KMER;
-    return;
+  o.status[strand] = missing ? ST_MISSING_KMER : ST_NO_EXTENSION;
+}
+
+// Single-lane driver (host emulation and a reference for the warp loop in kernels.cu).
+GQ_DEV inline void map_strand(const IndexView& v, const uint32_t* super_cnt, const BatchView& b, const SearchOut& o,
+                              uint32_t strand, uint32_t* arena, uint32_t arena_words) {
+  Lane ln;
+  lane_refill(ln, v, b, o, strand, arena, arena_words);
+  while (ln.state != LS_IDLE) {
+    if (ln.state == LS_RUN) lane_step(ln, v, super_cnt);
+    else lane_event(ln, v, o);
   }
-  // seed with the index entry of the last k-mer (quasimap.cpp:178,235-241)
-  Stack s;
-  s.mem = arena;
-  s.limit = arena_words;
-  s.overflow = false;
-  s.top = kNoAllele;
-  uint32_t sb = GQ_LDG(v.kmer_off + code), se = GQ_LDG(v.kmer_off + code + 1);
-  uint32_t sp = 0;
-  for (uint32_t j = sb; j < se; ++j) {
-    KmerState ks = v.kmer_states[j];
-    uint32_t words = entry_words(ks.counts);
-    if (sp + words + 3 > s.limit) {
-      s.overflow = true;
-      break;
-    }
-    uint32_t* t = s.mem + sp;
-    t[0] = (L - k) | (K_SCAN << 28);
-    t[1] = ks.lo;
-    t[2] = ks.hi;
-    t[3] = ks.counts;
-    t[4] = s.top;
-    for (uint32_t w = kHdr; w < words; ++w) t[w] = GQ_LDG(v.kmer_paths + ks.path_off + (w - kHdr));
-    s.top = sp;
-    sp += words;
-  }
-  EmitStage emit{&s, &v, 0};
-  if (!s.overflow) run_stack(s, v, super_cnt, rd, emit);
-  uint32_t words = arena_words - s.limit;
-  if (!s.overflow && words) {
-    uint32_t off = gq_atomic_add(o.pool_used, words);
-    if (off + words > o.pool_cap) s.overflow = true;
-    else {
-      for (uint32_t w = 0; w < words; ++w) o.pool[off + w] = s.mem[s.limit + w];
-      o.st_off[strand] = off;
-      o.st_words[strand] = words;
-      o.st_count[strand] = emit.n_states;
-    }
-  }
-  if (s.overflow) {
-    o.status[strand] = ST_OVERFLOW;
-    o.overflow_list[gq_atomic_add(o.n_overflow, 1u)] = strand;
-    return;
-  }
-  o.status[strand] = emit.n_states ? ST_MAPPED : ST_NO_EXTENSION;
+  if (o.status[strand] == ST_UNCLASSIFIED) classify_strand(v, b, o, strand);
 }
 
 struct Scratch {

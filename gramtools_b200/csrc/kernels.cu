@@ -79,9 +79,16 @@ __device__ __forceinline__ void tma_stage_super(uint32_t* s_super, const uint32_
 constexpr int kSearchThreads = 256;
 constexpr int kMaxSuperSmem = 2048;  // superblocks (x16 B = 32 KB) staged in shared memory
 
+// Warp-synchronous driver of the lane state machine (gq_device.cuh). Each warp owns a contiguous chunk
+// of strands; ballots decide, warp-uniformly, which unit operation the whole warp executes next:
+//   * refill idle lanes        when >= rf_thresh lanes are idle (or nothing else can run)
+//   * rare-path transitions    when >= ev_thresh lanes wait on an event (or nothing else can run)
+//   * otherwise the hot step   for every lane in LS_RUN
+// Batching the rare paths keeps the hot step near full lane occupancy (v1 ran 3.5 lanes/instruction).
 __global__ void __launch_bounds__(kSearchThreads)
     search_kernel(IndexView v, BatchView b, SearchOut o, uint32_t* arena, uint32_t arena_words,
-                  const uint32_t* list, uint32_t n_list, uint32_t n_super_smem) {
+                  const uint32_t* list, uint32_t n_list, uint32_t n_super_smem, uint32_t rf_thresh,
+                  uint32_t ev_thresh) {
   __shared__ alignas(128) uint32_t s_super[kMaxSuperSmem * 4];
   __shared__ alignas(8) uint64_t s_bar;
   const uint32_t* super_cnt = v.super_cnt;
@@ -89,16 +96,43 @@ __global__ void __launch_bounds__(kSearchThreads)
     tma_stage_super(s_super, v.super_cnt, n_super_smem * 16u, &s_bar);
     super_cnt = s_super;
   }
-  uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t nthreads = gridDim.x * blockDim.x;
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warp = tid >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t work = list ? n_list : 2 * b.n_reads;
+  const uint32_t chunk = (work + n_warps - 1) / n_warps;
+  const uint32_t begin = min(work, warp * chunk), end = min(work, begin + chunk);
+  uint32_t cursor = begin;  // warp-uniform
   uint32_t* my_arena = arena + (size_t)tid * arena_words;
-  if (list) {
-    for (uint32_t i = tid; i < n_list; i += nthreads) map_strand(v, super_cnt, b, o, list[i], my_arena, arena_words);
-  } else {
-    for (uint32_t r = tid; r < b.n_reads; r += nthreads) {
-      map_strand(v, super_cnt, b, o, 2 * r, my_arena, arena_words);
-      map_strand(v, super_cnt, b, o, 2 * r + 1, my_arena, arena_words);
+  Lane ln;
+  ln.state = LS_IDLE;
+  ln.strand = kNoAllele;
+  const uint32_t full = 0xFFFFFFFFu;
+  while (true) {
+    const uint32_t idle = __ballot_sync(full, ln.state == LS_IDLE);
+    const uint32_t run = __ballot_sync(full, ln.state == LS_RUN);
+    const uint32_t ev = ~(idle | run);
+    const bool work_left = cursor < end;
+    if (idle == full && !work_left) break;
+    if (work_left && idle && ((uint32_t)__popc(idle) >= rf_thresh || run == 0)) {
+      if (ln.state == LS_IDLE) {
+        uint32_t i = cursor + __popc(idle & ((1u << lane) - 1u));
+        if (i < end) lane_refill(ln, v, b, o, list ? list[i] : i, my_arena, arena_words);
+      }
+      cursor = min(end, cursor + (uint32_t)__popc(idle));
+      continue;
     }
+    if (ev && ((uint32_t)__popc(ev) >= ev_thresh || run == 0)) {
+      if (ln.state >= LS_EV_SCAN) lane_event(ln, v, o);
+      continue;
+    }
+    if (ln.state == LS_RUN) lane_step(ln, v, super_cnt);
+  }
+  // k-mer filter, only for the strands of this warp whose search found nothing
+  __syncwarp();
+  for (uint32_t i = begin + lane; i < end; i += 32) {
+    uint32_t strand = list ? list[i] : i;
+    if (o.status[strand] == ST_UNCLASSIFIED) classify_strand(v, b, o, strand);
   }
 }
 
@@ -106,13 +140,14 @@ int search_kernel_smem_limit_superblocks() { return kMaxSuperSmem; }
 
 void launch_search(const IndexView& v, const BatchView& b, const SearchOut& o, uint32_t* arena,
                    uint32_t arena_words, uint32_t n_threads, const uint32_t* list, uint32_t n_list,
-                   bool super_in_smem, cudaStream_t st) {
-  uint32_t work = list ? n_list : b.n_reads;
+                   bool super_in_smem, uint32_t rf_thresh, uint32_t ev_thresh, cudaStream_t st) {
+  uint32_t work = list ? n_list : 2 * b.n_reads;
   if (work == 0) return;
   uint32_t blocks = (min(work, n_threads) + kSearchThreads - 1) / kSearchThreads;
   uint32_t n_super = (v.n >> kSuperShift) + 1;
   uint32_t n_super_smem = (super_in_smem && n_super <= (uint32_t)kMaxSuperSmem) ? n_super : 0;
-  search_kernel<<<blocks, kSearchThreads, 0, st>>>(v, b, o, arena, arena_words, list, n_list, n_super_smem);
+  search_kernel<<<blocks, kSearchThreads, 0, st>>>(v, b, o, arena, arena_words, list, n_list, n_super_smem,
+                                                   max(1u, min(32u, rf_thresh)), max(1u, min(32u, ev_thresh)));
 }
 
 // ------------------------------------------------------------------------------------------------
