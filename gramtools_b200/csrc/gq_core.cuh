@@ -53,7 +53,7 @@ struct KmerState {   // one seed SearchState (reference: kmer_index_types.hpp:24
 struct IndexView {
   uint32_t n;  // SA size = |prg| + 1
   const RankBlk* rank_blk;
-  const uint32_t* super_cnt;   // 4 per superblock: A,C,G,T occurrences before the superblock
+  const uint32_t* super_cnt;   // 4 per superblock: C[c] + occurrences of A,C,G,T before the superblock
   const uint32_t* mrank_blk;   // markers in BWT[0, block start)
   const uint32_t* marker_hit;  // 2 per BWT marker occurrence: (marker', allele); see index_build.cpp
   uint32_t c_base[4];          // first SA index of suffixes starting with A,C,G,T
@@ -362,8 +362,8 @@ GQ_HD void run_stack(Stack& s, const IndexView& v, const uint32_t* super_cnt, Re
         alive = false;
         break;
       }
-      lo = v.c_base[c] + r0;
-      hi = v.c_base[c] + r1 - 1;
+      lo = r0;  // C[c] is folded into the superblock counters
+      hi = r1 - 1;
       --pos;
       kind = K_SCAN;
       if (pos == 0) {

@@ -273,34 +273,65 @@ GQ_DEV inline void lane_refill(Lane& ln, const IndexView& v, const BatchView& b,
 
 // The hot path: one base for a lane in LS_RUN. Everything lives in registers; memory traffic is one
 // (or two) 32 B rank-block sectors. Any non-trivial outcome parks the lane in an event state.
-GQ_DEV inline void lane_step(Lane& ln, const IndexView& v, const uint32_t* super_cnt) {
+// `super_c` = per-superblock counts with C[c] folded in (IndexView::super_cnt_c), so
+// lo' = super_c[c] + blk.cnt[c] + popc(...) directly.
+template <class SuperPtr>
+GQ_DEV inline void lane_step(Lane& ln, const IndexView& v, SuperPtr super_c) {
   const uint32_t lo = ln.lo, hi = ln.hi;
-  const uint32_t b0 = lo >> kBlkShift, bh = hi >> kBlkShift, b1 = (hi + 1) >> kBlkShift;
-  RankBlk B0 = load_blk(v.rank_blk + b0);
-  RankBlk B1 = (b1 == b0) ? B0 : load_blk(v.rank_blk + b1);
-  if (ln.kind == K_SCAN) {
-    uint64_t mk;
-    if (bh == b0) mk = marker_bits_in(B0, b0 << kBlkShift, lo, hi);
-    else if (bh == b1 && b1 == b0 + 1)
-      mk = marker_bits_in(B0, b0 << kBlkShift, lo, hi) | marker_bits_in(B1, b1 << kBlkShift, lo, hi);
-    else {  // interval wider than the two fetched blocks: rare, resolved in the event path
-      ln.state = LS_EV_WIDE;
-      return;
-    }
-    if (mk) {
-      ln.state = LS_EV_SCAN;
-      return;
-    }
-  }
+  const uint32_t b0 = lo >> kBlkShift;
+  const RankBlk B0 = load_blk(v.rank_blk + b0);
   const uint32_t c = ln.rd(ln.pos - 1);
-  const uint32_t r0 = rank_in_blk(B0, super_cnt + 4 * (b0 >> (kSuperShift - kBlkShift)), c, lo);
-  const uint32_t r1 = rank_in_blk(B1, super_cnt + 4 * (b1 >> (kSuperShift - kBlkShift)), c, hi + 1);
-  if (r1 <= r0) {
-    ln.state = LS_EV_POP;
-    return;
+  const uint64_t x0 = (c & 1u) ? 0ull : ~0ull, x1 = (c & 2u) ? 0ull : ~0ull;
+  uint32_t nlo, nhi;
+  if (lo == hi) {
+    // width-1 interval (the steady state after seeding): the step only needs BWT[lo]
+    const uint32_t r = lo & 63u;
+    const uint64_t bit = 1ull << r;
+    if (B0.p2 & bit) {  // not a nucleotide: marker -> jump (unless already scanned), sentinel -> dead
+      ln.state = ((B0.p0 & bit) && ln.kind == K_SCAN) ? LS_EV_SCAN : LS_EV_POP;
+      return;
+    }
+    const uint64_t m = ~B0.p2 & (B0.p0 ^ x0) & (B0.p1 ^ x1);
+    if (!(m & bit)) {
+      ln.state = LS_EV_POP;
+      return;
+    }
+    nlo = super_c[4 * (b0 >> (kSuperShift - kBlkShift)) + c] + ((uint32_t)(B0.cnt >> (16 * c)) & 0xFFFFu) +
+          (uint32_t)popc64(m & (bit - 1));
+    nhi = nlo;
+  } else {
+    const uint32_t bh = hi >> kBlkShift, b1 = (hi + 1) >> kBlkShift;
+    const RankBlk B1 = (b1 == b0) ? B0 : load_blk(v.rank_blk + b1);
+    if (ln.kind == K_SCAN) {
+      uint64_t mk;
+      if (bh == b0) mk = marker_bits_in(B0, b0 << kBlkShift, lo, hi);
+      else if (bh == b1 && b1 == b0 + 1)
+        mk = marker_bits_in(B0, b0 << kBlkShift, lo, hi) | marker_bits_in(B1, b1 << kBlkShift, lo, hi);
+      else {  // interval wider than the two fetched blocks: rare, resolved in the event path
+        ln.state = LS_EV_WIDE;
+        return;
+      }
+      if (mk) {
+        ln.state = LS_EV_SCAN;
+        return;
+      }
+    }
+    const uint64_t m0 = ~B0.p2 & (B0.p0 ^ x0) & (B0.p1 ^ x1);
+    const uint64_t m1 = ~B1.p2 & (B1.p0 ^ x0) & (B1.p1 ^ x1);
+    const uint32_t ra = lo & 63u, rb = (hi + 1) & 63u;
+    const uint32_t r0 = super_c[4 * (b0 >> (kSuperShift - kBlkShift)) + c] + ((uint32_t)(B0.cnt >> (16 * c)) & 0xFFFFu) +
+                        (uint32_t)popc64(m0 & ((1ull << ra) - 1));
+    const uint32_t r1 = super_c[4 * (b1 >> (kSuperShift - kBlkShift)) + c] + ((uint32_t)(B1.cnt >> (16 * c)) & 0xFFFFu) +
+                        (uint32_t)popc64(m1 & ((1ull << rb) - 1));
+    if (r1 <= r0) {
+      ln.state = LS_EV_POP;
+      return;
+    }
+    nlo = r0;
+    nhi = r1 - 1;
   }
-  ln.lo = v.c_base[c] + r0;
-  ln.hi = v.c_base[c] + r1 - 1;
+  ln.lo = nlo;
+  ln.hi = nhi;
   ln.kind = K_SCAN;
   if (--ln.pos == 0) {
     lane_writeback(ln, K_SCAN);
@@ -308,39 +339,69 @@ GQ_DEV inline void lane_step(Lane& ln, const IndexView& v, const uint32_t* super
   }
 }
 
-// One transition of the rare path. Ends in LS_RUN, LS_IDLE (strand finished) or another event state.
-GQ_DEV inline void lane_event(Lane& ln, const IndexView& v, const SearchOut& o) {
-  switch (ln.state) {
-    case LS_EV_WIDE:
-      if (!interval_has_marker(v, ln.lo, ln.hi)) {
-        ln.kind = K_READY;  // scanned, nothing found: extend without re-scanning
-        ln.state = LS_RUN;
-        return;
-      }
-      // fallthrough
-    case LS_EV_SCAN:
-      lane_writeback(ln, K_READY);
-      scan_markers(ln.s, v, ln.pos, ln.lo, ln.hi);
-      break;
-    case LS_EV_POP:
-      pop(ln.s);
-      break;
-    default: {  // LS_EV_TOP: a pending locus, or a finished state
-      uint32_t* t = ln.s.mem + ln.s.top;
-      if ((t[0] >> 28) == K_JUMP) process_jump(ln.s, v);
-      else {
-        EmitStage emit{&ln.s, &v, ln.n_states};
-        emit(t);
-        ln.n_states = emit.n_states;
-        pop(ln.s);
-      }
-    }
-  }
+// after a transition of the rare path: finish the strand, or cache the new top
+GQ_DEV inline void lane_after_event(Lane& ln, const SearchOut& o) {
   if (ln.s.overflow || stack_empty(ln.s)) {
     lane_finish_strand(ln, o);
     return;
   }
   lane_load_top(ln);
+}
+
+// LS_EV_SCAN / LS_EV_WIDE: markers in the interval (left_markers_search, vBWT_jump.cpp:94-117)
+GQ_DEV inline void lane_event_scan(Lane& ln, const IndexView& v, const SearchOut& o) {
+  if (ln.state == LS_EV_WIDE && !interval_has_marker(v, ln.lo, ln.hi)) {
+    ln.kind = K_READY;  // scanned, nothing found: extend without re-scanning
+    ln.state = LS_RUN;
+    return;
+  }
+  if (ln.lo == ln.hi) {
+    // Single suffix preceded by a marker: the un-jumped state cannot be extended by any base (its only
+    // BWT symbol is the marker), so the jump replaces it in place instead of being pushed above it.
+    const uint32_t blk = ln.lo >> kBlkShift, bit = ln.lo & 63u;
+    const RankBlk B = load_blk(v.rank_blk + blk);
+    const uint64_t all = B.p2 & B.p0;
+    const uint32_t mr = GQ_LDG(v.mrank_blk + blk) + (uint32_t)popc64(all & ((1ull << bit) - 1));
+    const uint32_t marker = GQ_LDG(v.marker_hit + 2 * mr), allele = GQ_LDG(v.marker_hit + 2 * mr + 1);
+    if (marker == 0) {
+      ln.state = LS_EV_POP;
+      return;
+    }
+    uint32_t* t = ln.s.mem + ln.s.top;
+    t[0] = ln.pos | (K_JUMP << 28);
+    t[1] = marker;
+    t[2] = allele;
+    process_jump(ln.s, v);
+  } else {
+    lane_writeback(ln, K_READY);
+    scan_markers(ln.s, v, ln.pos, ln.lo, ln.hi);
+  }
+  lane_after_event(ln, o);
+}
+
+// LS_EV_POP: the top state died
+GQ_DEV inline void lane_event_pop(Lane& ln, const SearchOut& o) {
+  pop(ln.s);
+  lane_after_event(ln, o);
+}
+
+// LS_EV_TOP: a pending locus (K_JUMP) or a finished state (pos == 0) sits on top
+GQ_DEV inline void lane_event_top(Lane& ln, const IndexView& v, const SearchOut& o) {
+  uint32_t* t = ln.s.mem + ln.s.top;
+  if ((t[0] >> 28) == K_JUMP) process_jump(ln.s, v);
+  else {
+    EmitStage emit{&ln.s, &v, ln.n_states};
+    emit(t);
+    ln.n_states = emit.n_states;
+    pop(ln.s);
+  }
+  lane_after_event(ln, o);
+}
+
+GQ_DEV inline void lane_event(Lane& ln, const IndexView& v, const SearchOut& o) {
+  if (ln.state == LS_EV_SCAN || ln.state == LS_EV_WIDE) lane_event_scan(ln, v, o);
+  else if (ln.state == LS_EV_POP) lane_event_pop(ln, o);
+  else lane_event_top(ln, v, o);
 }
 
 // all_read_kmers_occur_in_index (quasimap.cpp:212-225) for a strand whose search found nothing:

@@ -298,7 +298,7 @@ void build_fm(HostIndex& ix, const std::vector<uint32_t>& hit_marker, const std:
   uint32_t tot[4] = {0, 0, 0, 0}, sup[4] = {0, 0, 0, 0}, nmark = 0;
   for (uint32_t i = 0; i <= n; ++i) {
     if ((i & ((1u << kSuperShift) - 1)) == 0) {
-      for (int c = 0; c < 4; ++c) sup[c] = tot[c], ix.super_cnt[4 * (size_t)(i >> kSuperShift) + c] = tot[c];
+      for (int c = 0; c < 4; ++c) sup[c] = tot[c], ix.super_cnt[4 * (size_t)(i >> kSuperShift) + c] = ix.c_base[c] + tot[c];
     }
     if ((i & 63u) == 0) {
       RankBlk& b = ix.rank_blk[i >> kBlkShift];

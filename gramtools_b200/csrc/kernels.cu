@@ -81,21 +81,22 @@ constexpr int kMaxSuperSmem = 2048;  // superblocks (x16 B = 32 KB) staged in sh
 
 // Warp-synchronous driver of the lane state machine (gq_device.cuh). Each warp owns a contiguous chunk
 // of strands; ballots decide, warp-uniformly, which unit operation the whole warp executes next:
-//   * refill idle lanes        when >= rf_thresh lanes are idle (or nothing else can run)
-//   * rare-path transitions    when >= ev_thresh lanes wait on an event (or nothing else can run)
-//   * otherwise the hot step   for every lane in LS_RUN
+//   * refill idle lanes                     when >= rf_thresh lanes are idle
+//   * one class of rare-path transitions    when >= ev_thresh lanes wait in that class
+//     (scan/jump, pop, top: lanes of one class run the same code together)
+//   * everything pending                    when no lane can take a hot step, or too many lanes wait
+//   * otherwise the hot step (x kHotUnroll) for every lane in LS_RUN
 // Batching the rare paths keeps the hot step near full lane occupancy (v1 ran 3.5 lanes/instruction).
+constexpr int kHotUnroll = 2;
+
+template <bool SUPER_SMEM>
 __global__ void __launch_bounds__(kSearchThreads)
     search_kernel(IndexView v, BatchView b, SearchOut o, uint32_t* arena, uint32_t arena_words,
                   const uint32_t* list, uint32_t n_list, uint32_t n_super_smem, uint32_t rf_thresh,
-                  uint32_t ev_thresh) {
-  __shared__ alignas(128) uint32_t s_super[kMaxSuperSmem * 4];
+                  uint32_t ev_thresh, uint32_t wait_max) {
+  __shared__ alignas(128) uint32_t s_super[SUPER_SMEM ? kMaxSuperSmem * 4 : 4];
   __shared__ alignas(8) uint64_t s_bar;
-  const uint32_t* super_cnt = v.super_cnt;
-  if (n_super_smem) {
-    tma_stage_super(s_super, v.super_cnt, n_super_smem * 16u, &s_bar);
-    super_cnt = s_super;
-  }
+  if (SUPER_SMEM) tma_stage_super(s_super, v.super_cnt, n_super_smem * 16u, &s_bar);
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t warp = tid >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -111,10 +112,29 @@ __global__ void __launch_bounds__(kSearchThreads)
   while (true) {
     const uint32_t idle = __ballot_sync(full, ln.state == LS_IDLE);
     const uint32_t run = __ballot_sync(full, ln.state == LS_RUN);
-    const uint32_t ev = ~(idle | run);
+    const uint32_t scan = __ballot_sync(full, ln.state == LS_EV_SCAN || ln.state == LS_EV_WIDE);
+    const uint32_t popm = __ballot_sync(full, ln.state == LS_EV_POP);
+    const uint32_t top = ~(idle | run | scan | popm);
     const bool work_left = cursor < end;
     if (idle == full && !work_left) break;
-    if (work_left && idle && ((uint32_t)__popc(idle) >= rf_thresh || run == 0)) {
+    const uint32_t n_idle = work_left ? __popc(idle) : 0, n_scan = __popc(scan), n_pop = __popc(popm),
+                   n_top = __popc(top);
+    const bool flush = run == 0 || n_idle + n_scan + n_pop + n_top >= wait_max;
+    bool did = false;
+    if (n_scan && (n_scan >= ev_thresh || flush)) {
+      if (ln.state == LS_EV_SCAN || ln.state == LS_EV_WIDE) lane_event_scan(ln, v, o);
+      did = true;
+    }
+    if (n_top && (n_top >= ev_thresh || flush)) {
+      if (ln.state == LS_EV_TOP) lane_event_top(ln, v, o);
+      did = true;
+    }
+    if (n_pop && (n_pop >= ev_thresh || flush)) {
+      if (ln.state == LS_EV_POP) lane_event_pop(ln, o);
+      did = true;
+    }
+    if (did) continue;  // states changed: re-vote (finished strands become idle lanes)
+    if (n_idle && (n_idle >= rf_thresh || flush)) {
       if (ln.state == LS_IDLE) {
         uint32_t i = cursor + __popc(idle & ((1u << lane) - 1u));
         if (i < end) lane_refill(ln, v, b, o, list ? list[i] : i, my_arena, arena_words);
@@ -122,11 +142,9 @@ __global__ void __launch_bounds__(kSearchThreads)
       cursor = min(end, cursor + (uint32_t)__popc(idle));
       continue;
     }
-    if (ev && ((uint32_t)__popc(ev) >= ev_thresh || run == 0)) {
-      if (ln.state >= LS_EV_SCAN) lane_event(ln, v, o);
-      continue;
-    }
-    if (ln.state == LS_RUN) lane_step(ln, v, super_cnt);
+#pragma unroll
+    for (int u = 0; u < kHotUnroll; ++u)
+      if (ln.state == LS_RUN) lane_step(ln, v, SUPER_SMEM ? (const uint32_t*)s_super : v.super_cnt);
   }
   // k-mer filter, only for the strands of this warp whose search found nothing
   __syncwarp();
@@ -146,8 +164,15 @@ void launch_search(const IndexView& v, const BatchView& b, const SearchOut& o, u
   uint32_t blocks = (min(work, n_threads) + kSearchThreads - 1) / kSearchThreads;
   uint32_t n_super = (v.n >> kSuperShift) + 1;
   uint32_t n_super_smem = (super_in_smem && n_super <= (uint32_t)kMaxSuperSmem) ? n_super : 0;
-  search_kernel<<<blocks, kSearchThreads, 0, st>>>(v, b, o, arena, arena_words, list, n_list, n_super_smem,
-                                                   max(1u, min(32u, rf_thresh)), max(1u, min(32u, ev_thresh)));
+  rf_thresh = max(1u, min(32u, rf_thresh));
+  ev_thresh = max(1u, min(32u, ev_thresh));
+  uint32_t wait_max = min(32u, rf_thresh + ev_thresh);
+  if (n_super_smem)
+    search_kernel<true><<<blocks, kSearchThreads, 0, st>>>(v, b, o, arena, arena_words, list, n_list, n_super_smem,
+                                                           rf_thresh, ev_thresh, wait_max);
+  else
+    search_kernel<false><<<blocks, kSearchThreads, 0, st>>>(v, b, o, arena, arena_words, list, n_list, 0, rf_thresh,
+                                                            ev_thresh, wait_max);
 }
 
 // ------------------------------------------------------------------------------------------------
