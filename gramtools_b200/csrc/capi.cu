@@ -69,7 +69,7 @@ struct gq_index {
   // search outputs
   DevBuf<uint8_t> status;
   DevBuf<uint32_t> st_off, st_words, st_count, pool, small;  // small: [pool_used, n_overflow, n_cov_overflow]
-  DevBuf<uint32_t> overflow_list, cov_overflow_list;
+  DevBuf<uint32_t> overflow_list, cov_overflow_list, mapped_list;
   DevBuf<uint32_t> arena, big_arena;
   // options
   uint32_t arena_words = 512;
@@ -104,6 +104,7 @@ static void upload_index(gq_index* ix) {
   v.marker_hit = upload(ix, h.marker_hit);
   for (int i = 0; i < 4; ++i) v.c_base[i] = h.c_base[i];
   v.n_slots = h.n_slots;
+  v.any_nested = h.is_nested ? 1u : 0u;
   v.site_sa = upload(ix, h.site_sa);
   v.allele_iv = upload(ix, h.allele_iv);
   v.par = upload(ix, h.par);
@@ -217,7 +218,8 @@ static void do_map(gq_index* ix) {
   ix->st_count.reserve(2 * (size_t)n);
   ix->overflow_list.reserve(2 * (size_t)n);
   ix->cov_overflow_list.reserve(2 * (size_t)n);
-  ix->small.reserve(4);
+  ix->mapped_list.reserve(2 * (size_t)n);
+  ix->small.reserve(8);
   size_t pool_need = std::max<size_t>((size_t)n * ix->pool_words_per_read, 1 << 16);
   pool_need = std::min<size_t>(pool_need, 0xFFFFFFF0ull);
   ix->pool.reserve(pool_need);
@@ -225,20 +227,22 @@ static void do_map(gq_index* ix) {
   // the coverage kernel walks strands: give it the same arena (2n strands over `threads2` threads)
   uint32_t threads2 = std::min<uint32_t>(ix->n_threads, ((2 * n + 255) / 256) * 256);
   ix->arena.reserve((size_t)std::max(threads, threads2) * ix->arena_words);
-  CUDA_OK(cudaMemsetAsync(ix->small.p, 0, 16, st));
+  CUDA_OK(cudaMemsetAsync(ix->small.p, 0, 32, st));  // [pool_used, n_overflow, n_cov_overflow, n_mapped, work_counter]
 
   gq::BatchView b{ix->packed.p, ix->word_off.p, ix->len.p, ix->seeds.p, n};
   gq::SearchOut o{ix->status.p, ix->st_off.p, ix->st_words.p, ix->st_count.p, ix->pool.p, (uint32_t)ix->pool.cap,
-                  ix->small.p,  ix->overflow_list.p, ix->small.p + 1};
+                  ix->small.p,  ix->overflow_list.p, ix->small.p + 1, ix->mapped_list.p, ix->small.p + 3,
+                  ix->small.p + 4};
   gq::CoverageView c = cov_view(ix);
   int launches = 0;
   CUDA_OK(cudaEventRecord(ix->ev[0], st));
   gq::launch_search(ix->dv, b, o, ix->arena.p, ix->arena_words, threads, nullptr, 0, ix->super_in_smem, ix->rf_thresh, ix->ev_thresh, st);
   ++launches;
   CUDA_OK(cudaEventRecord(ix->ev[1], st));
+  gq::launch_classify(ix->dv, b, o, nullptr, 0, st);
   gq::launch_coverage(ix->dv, b, o, c, ix->arena.p, ix->arena_words, threads2, nullptr, 0, ix->cov_overflow_list.p,
                       ix->small.p + 2, st);
-  ++launches;
+  launches += 2;
   CUDA_OK(cudaEventRecord(ix->ev[2], st));
   uint32_t small[4];
   CUDA_OK(cudaMemcpyAsync(small, ix->small.p, 16, cudaMemcpyDeviceToHost, st));
@@ -279,7 +283,10 @@ static void do_map(gq_index* ix) {
     list.reserve(n_list);
     CUDA_OK(cudaMemcpyAsync(list.p, ix->overflow_list.p, (size_t)n_list * 4, cudaMemcpyDeviceToDevice, st));
     CUDA_OK(cudaMemsetAsync(ix->small.p + 1, 0, 4, st));
+    CUDA_OK(cudaMemsetAsync(ix->small.p + 4, 0, 4, st));  // work counter of the list run
     gq::launch_search(ix->dv, b, o, ix->big_arena.p, big_words, bt, list.p, n_list, ix->super_in_smem, ix->rf_thresh, ix->ev_thresh, st);
+    gq::launch_classify(ix->dv, b, o, list.p, n_list, st);
+    ++launches;
     gq::launch_coverage(ix->dv, b, o, c, ix->big_arena.p, big_words, bt, list.p, n_list, ix->cov_overflow_list.p,
                         ix->small.p + 2, st);
     launches += 2;
@@ -395,6 +402,7 @@ int gq_index_destroy(gq_index* ix) {
   ix->small.release();
   ix->overflow_list.release();
   ix->cov_overflow_list.release();
+  ix->mapped_list.release();
   ix->arena.release();
   ix->big_arena.release();
   for (auto& e : ix->ev)

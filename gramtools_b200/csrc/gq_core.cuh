@@ -59,6 +59,7 @@ struct IndexView {
   uint32_t c_base[4];          // first SA index of suffixes starting with A,C,G,T
   // per site slot s = (site_id - 5) / 2
   uint32_t n_slots;
+  uint32_t any_nested;         // 1 if some site has a parent (coverage_graph.is_nested)
   const uint32_t* site_sa;     // SA index of the suffix starting with the odd (site entry) marker
   const uint32_t* allele_iv;   // 2 per slot: SA interval [lo,hi] of the even marker
   const uint32_t* par;         // 2 per slot: (parent site id or 0, parent allele)

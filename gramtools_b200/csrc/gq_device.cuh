@@ -45,6 +45,20 @@ GQ_DEV inline void gq_atomic_or(uint32_t* p, uint32_t v) {
   *p |= v;
 #endif
 }
+// append-style counter bump; on the device the lanes that arrive together issue ONE atomic
+GQ_DEV inline uint32_t gq_atomic_inc_aggregated(uint32_t* p) {
+#if defined(__CUDA_ARCH__)
+  const unsigned m = __activemask();
+  const int leader = __ffs(m) - 1;
+  const unsigned lane = threadIdx.x & 31u;
+  uint32_t base = 0;
+  if ((int)lane == leader) base = atomicAdd(p, (uint32_t)__popc(m));
+  base = __shfl_sync(m, base, leader);
+  return base + __popc(m & ((1u << lane) - 1u));
+#else
+  return (*p)++;
+#endif
+}
 GQ_DEV inline void gq_threadfence() {
 #if defined(__CUDA_ARCH__)
   __threadfence();
@@ -163,7 +177,6 @@ struct EmitStage {
 // all of its k-mers in the index, which holds every k-mer with >= 1 search state.
 // ------------------------------------------------------------------------------------------------
 enum LaneState : uint32_t { LS_IDLE = 0, LS_RUN = 1, LS_EV_SCAN = 2, LS_EV_POP = 3, LS_EV_TOP = 4, LS_EV_WIDE = 5 };
-constexpr uint8_t ST_UNCLASSIFIED = 4;  // search produced no state: classify_strand decides 1 vs 2
 
 struct Lane {
   uint32_t state;
@@ -209,8 +222,11 @@ GQ_DEV inline void lane_finish_strand(Lane& ln, const SearchOut& o) {
   if (ln.s.overflow) {
     o.status[ln.strand] = ST_OVERFLOW;
     o.overflow_list[gq_atomic_add(o.n_overflow, 1u)] = ln.strand;
+  } else if (ln.n_states) {
+    o.status[ln.strand] = ST_MAPPED;
+    o.mapped_list[gq_atomic_inc_aggregated(o.n_mapped)] = ln.strand;
   } else
-    o.status[ln.strand] = ln.n_states ? ST_MAPPED : ST_UNCLASSIFIED;
+    o.status[ln.strand] = ST_UNCLASSIFIED;
   ln.state = LS_IDLE;
 }
 
@@ -233,8 +249,8 @@ GQ_DEV inline void lane_refill(Lane& ln, const IndexView& v, const BatchView& b,
     return;
   }
   ln.rd = ReadCursor{b.packed + b.word_off[r], L, (strand & 1u) != 0, 0xFFFFFFFFu, 0};
-  uint32_t code = 0;
-  for (uint32_t i = L - k; i < L; ++i) code = (code << 2) | ln.rd(i);
+  uint32_t code = 0;  // k-mer code: base j of the k-mer at bits [2j, 2j+2)
+  for (uint32_t j = 0; j < k; ++j) code |= ln.rd(L - k + j) << (2 * j);
   uint32_t sb = GQ_LDG(v.kmer_off + code), se = GQ_LDG(v.kmer_off + code + 1);
   if (sb == se) {  // the seeding k-mer itself is not indexed: the k-mer filter fails
     o.status[strand] = ST_MISSING_KMER;
@@ -406,18 +422,45 @@ GQ_DEV inline void lane_event(Lane& ln, const IndexView& v, const SearchOut& o) 
 
 // all_read_kmers_occur_in_index (quasimap.cpp:212-225) for a strand whose search found nothing:
 // any k-mer absent from the index -> missing_kmer, else no_extension (quasimap.cpp:170-186).
+// The k-mer code convention (base j at bits [2j,2j+2)) makes the code of the window starting at base i
+// a plain bit-field of the 2-bit packed read, so the loop slides a 64-bit window by one base per
+// iteration. The reverse strand holds exactly the reverse complements of the forward windows
+// (complement = bitwise NOT of the 2-bit code, reversal = pair-reversal), and "any k-mer missing"
+// does not depend on the order in which windows are visited.
+GQ_DEV inline uint32_t pair_reverse32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  x = __brev(x);
+#else
+  x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+  x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+  x = ((x >> 4) & 0x0F0F0F0Fu) | ((x & 0x0F0F0F0Fu) << 4);
+  x = ((x >> 8) & 0x00FF00FFu) | ((x & 0x00FF00FFu) << 8);
+  x = (x >> 16) | (x << 16);
+#endif
+  return ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);  // bit reversal, then un-swap inside each pair
+}
+
 GQ_DEV inline void classify_strand(const IndexView& v, const BatchView& b, const SearchOut& o, uint32_t strand) {
   const uint32_t r = strand >> 1;
   const uint32_t L = b.len[r], k = v.k;
-  ReadCursor rd{b.packed + b.word_off[r], L, (strand & 1u) != 0, 0xFFFFFFFFu, 0};
+  const uint32_t* w = b.packed + b.word_off[r];
+  const bool rc = (strand & 1u) != 0;
   const uint32_t mask = (k == 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
-  uint32_t code = 0;
+  const uint32_t n_words = (L + 15) >> 4;
+  uint64_t win = GQ_LDG(w);
+  if (n_words > 1) win |= (uint64_t)GQ_LDG(w + 1) << 32;
   bool missing = false;
-  for (uint32_t i = 0; i < L; ++i) {
-    code = ((code << 2) | rd(i)) & mask;
-    if (i + 1 >= k && !((GQ_LDG(v.kmer_bits + (code >> 5)) >> (code & 31u)) & 1u)) {
+  for (uint32_t i = 0; i + k <= L; ++i) {
+    uint32_t code = (uint32_t)win & mask;
+    if (rc) code = pair_reverse32(~(uint32_t)win) >> (32 - 2 * k);
+    if (!((GQ_LDG(v.kmer_bits + (code >> 5)) >> (code & 31u)) & 1u)) {
       missing = true;
       break;
+    }
+    win >>= 2;
+    if ((i & 15u) == 15u) {  // 16 bases consumed: bring in the next packed word
+      uint32_t nw = (i >> 4) + 2;
+      if (nw < n_words) win |= (uint64_t)GQ_LDG(w + nw) << 32;
     }
   }
   o.status[strand] = missing ? ST_MISSING_KMER : ST_NO_EXTENSION;
@@ -729,7 +772,44 @@ GQ_DEV bool record_strand(const IndexView& v, const BatchView& b, const SearchOu
     }
   }
   if (npath == 0) return true;
-  // single pathful state and nothing else: one class, generate(1,1) == 1 -> skip the key machinery
+  // Fast path (nearly every strand of a non-nested PRG): exactly one state, one occurrence. One class and
+  // no non-variant mapping -> generate(1,1) == 1 selects it (coverage_common.cpp:97-107); every locus is
+  // its own level-0 site (no parents), each node is visited once, so no sets / hulls are needed.
+  if (ns == 1 && !v.any_nested) {
+    StateRec st = parse_rec(recs);
+    if (st.lo == st.hi && st.ng <= 1) {
+      const uint32_t pos0 = GQ_LDG(v.sa + st.lo);
+      const uint32_t nid0 = GQ_LDG(v.pos2node + pos0);
+      if (st.ng) {
+        const uint32_t site = st.G[0], slot = (site - 5) >> 1, al = (uint32_t)v.nodes[nid0].allele;
+        gq_atomic_add(c.allele_sum + c.allele_off[slot] + al, 1u);
+        gq_atomic_add(c.grouped_single + c.allele_off[slot] + al, 1u);
+      }
+      for (uint32_t j = 0; j < st.nt; ++j) {
+        const uint32_t slot = (st.T[2 * j] - 5) >> 1, al = st.T[2 * j + 1];
+        gq_atomic_add(c.allele_sum + c.allele_off[slot] + al, 1u);
+        gq_atomic_add(c.grouped_single + c.allele_off[slot] + al, 1u);
+      }
+      Trav t;
+      t.v = &v;
+      t.cur = nid0;
+      t.remaining = L;
+      t.T = st.T;
+      t.ti = st.nt;
+      t.first = true;
+      const Node& nd0 = v.nodes[nid0];
+      t.start_pos = nd0.len > 1 ? pos0 - nd0.start : 0;
+      t.end_pos = 0;
+      t.bad = false;
+      while (t.next()) {
+        const Node& nd = v.nodes[t.cur];
+        if (nd.len == 0 || nd.cov_off == kNoAllele) continue;
+        for (uint32_t x = t.start_pos; x <= t.end_pos; ++x) gq_atomic_add(c.per_base + nd.cov_off + x, 1u);
+      }
+      if (t.bad) gq_atomic_or(c.error_flags, 2u);
+      return true;
+    }
+  }
   uint32_t* key_off = sc.alloc(2 * ns);  // (offset, len) per state; len = 0xFFFFFFFF for path-less
   if (!key_off) return false;
   const uint32_t cap = (arena_words - sc.used) / 16;  // list capacities derive from the arena size

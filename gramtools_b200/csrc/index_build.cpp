@@ -20,6 +20,7 @@ IndexView HostIndex::view() const {
   v.marker_hit = marker_hit.data();
   for (int i = 0; i < 4; ++i) v.c_base[i] = c_base[i];
   v.n_slots = n_slots;
+  v.any_nested = is_nested ? 1u : 0u;
   v.site_sa = site_sa.data();
   v.allele_iv = allele_iv.data();
   v.par = par.data();
@@ -396,7 +397,7 @@ void kmer_recurse(const IndexView& v, uint32_t k, uint32_t depth, uint32_t code,
     std::vector<HState>& nxt = levels[depth];
     step_states(v, cur, c, depth == 0, arena, nxt);
     if (nxt.empty()) continue;
-    uint32_t ncode = code | (c << (2 * depth));
+    uint32_t ncode = code | (c << (2 * (k - 1 - depth)));  // base j of the k-mer sits at bits [2j, 2j+2)
     if (depth + 1 == k) {
       out.codes.push_back(ncode);
       out.n_states.push_back((uint32_t)nxt.size());
@@ -437,7 +438,7 @@ void build_kmers(HostIndex& ix) {
       for (uint32_t d = 0; d < pre; ++d) {
         uint32_t c = ((uint32_t)task >> (2 * d)) & 3u;
         step_states(v, cur, c, d == 0, arena, nxt);
-        code |= c << (2 * d);
+        code |= c << (2 * (k - 1 - d));
         cur.swap(nxt);
         if (cur.empty()) {
           dead = true;

@@ -93,17 +93,14 @@ template <bool SUPER_SMEM>
 __global__ void __launch_bounds__(kSearchThreads)
     search_kernel(IndexView v, BatchView b, SearchOut o, uint32_t* arena, uint32_t arena_words,
                   const uint32_t* list, uint32_t n_list, uint32_t n_super_smem, uint32_t rf_thresh,
-                  uint32_t ev_thresh, uint32_t wait_max) {
+                  uint32_t ev_thresh, uint32_t wait_max, uint32_t leave) {
   __shared__ alignas(128) uint32_t s_super[SUPER_SMEM ? kMaxSuperSmem * 4 : 4];
   __shared__ alignas(8) uint64_t s_bar;
   if (SUPER_SMEM) tma_stage_super(s_super, v.super_cnt, n_super_smem * 16u, &s_bar);
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t warp = tid >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
   const uint32_t work = list ? n_list : 2 * b.n_reads;
-  const uint32_t chunk = (work + n_warps - 1) / n_warps;
-  const uint32_t begin = min(work, warp * chunk), end = min(work, begin + chunk);
-  uint32_t cursor = begin;  // warp-uniform
+  bool work_left = true;  // warp-uniform: strands are handed out by one global counter
   uint32_t* my_arena = arena + (size_t)tid * arena_words;
   Lane ln;
   ln.state = LS_IDLE;
@@ -115,7 +112,6 @@ __global__ void __launch_bounds__(kSearchThreads)
     const uint32_t scan = __ballot_sync(full, ln.state == LS_EV_SCAN || ln.state == LS_EV_WIDE);
     const uint32_t popm = __ballot_sync(full, ln.state == LS_EV_POP);
     const uint32_t top = ~(idle | run | scan | popm);
-    const bool work_left = cursor < end;
     if (idle == full && !work_left) break;
     const uint32_t n_idle = work_left ? __popc(idle) : 0, n_scan = __popc(scan), n_pop = __popc(popm),
                    n_top = __popc(top);
@@ -135,23 +131,45 @@ __global__ void __launch_bounds__(kSearchThreads)
     }
     if (did) continue;  // states changed: re-vote (finished strands become idle lanes)
     if (n_idle && (n_idle >= rf_thresh || flush)) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(o.work_counter, (uint32_t)__popc(idle));
+      base = __shfl_sync(full, base, 0);
       if (ln.state == LS_IDLE) {
-        uint32_t i = cursor + __popc(idle & ((1u << lane) - 1u));
-        if (i < end) lane_refill(ln, v, b, o, list ? list[i] : i, my_arena, arena_words);
+        uint32_t i = base + __popc(idle & ((1u << lane) - 1u));
+        if (i < work) lane_refill(ln, v, b, o, list ? list[i] : i, my_arena, arena_words);
       }
-      cursor = min(end, cursor + (uint32_t)__popc(idle));
+      work_left = base + (uint32_t)__popc(idle) < work;
       continue;
     }
+    // hot loop: keep stepping until `leave` lanes have dropped out of LS_RUN (or none is left); the
+    // per-step control cost is one ballot + popc instead of the full vote above
+    const uint32_t n_run0 = __popc(run);
+    const uint32_t stay = n_run0 > leave ? n_run0 - leave : 0;
+    while (true) {
 #pragma unroll
-    for (int u = 0; u < kHotUnroll; ++u)
-      if (ln.state == LS_RUN) lane_step(ln, v, SUPER_SMEM ? (const uint32_t*)s_super : v.super_cnt);
+      for (int u = 0; u < kHotUnroll; ++u)
+        if (ln.state == LS_RUN) lane_step(ln, v, SUPER_SMEM ? (const uint32_t*)s_super : v.super_cnt);
+      const uint32_t n_run = __popc(__ballot_sync(full, ln.state == LS_RUN));
+      if (n_run <= stay) break;
+    }
   }
-  // k-mer filter, only for the strands of this warp whose search found nothing
-  __syncwarp();
-  for (uint32_t i = begin + lane; i < end; i += 32) {
+}
+
+__global__ void __launch_bounds__(256)
+    classify_kernel(IndexView v, BatchView b, SearchOut o, const uint32_t* list, uint32_t n_list) {
+  const uint32_t n = list ? n_list : 2 * b.n_reads;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     uint32_t strand = list ? list[i] : i;
     if (o.status[strand] == ST_UNCLASSIFIED) classify_strand(v, b, o, strand);
   }
+}
+
+void launch_classify(const IndexView& v, const BatchView& b, const SearchOut& o, const uint32_t* list, uint32_t n_list,
+                     cudaStream_t st) {
+  uint32_t work = list ? n_list : 2 * b.n_reads;
+  if (work == 0) return;
+  uint32_t blocks = min((work + 255) / 256, 148u * 8u);
+  classify_kernel<<<blocks, 256, 0, st>>>(v, b, o, list, n_list);
 }
 
 int search_kernel_smem_limit_superblocks() { return kMaxSuperSmem; }
@@ -167,12 +185,13 @@ void launch_search(const IndexView& v, const BatchView& b, const SearchOut& o, u
   rf_thresh = max(1u, min(32u, rf_thresh));
   ev_thresh = max(1u, min(32u, ev_thresh));
   uint32_t wait_max = min(32u, rf_thresh + ev_thresh);
+  uint32_t leave = max(1u, ev_thresh / 2);
   if (n_super_smem)
     search_kernel<true><<<blocks, kSearchThreads, 0, st>>>(v, b, o, arena, arena_words, list, n_list, n_super_smem,
-                                                           rf_thresh, ev_thresh, wait_max);
+                                                           rf_thresh, ev_thresh, wait_max, leave);
   else
     search_kernel<false><<<blocks, kSearchThreads, 0, st>>>(v, b, o, arena, arena_words, list, n_list, 0, rf_thresh,
-                                                            ev_thresh, wait_max);
+                                                            ev_thresh, wait_max, leave);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -184,9 +203,10 @@ __global__ void __launch_bounds__(256)
   uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t nthreads = gridDim.x * blockDim.x;
   uint32_t* my_arena = arena + (size_t)tid * arena_words;
-  uint32_t n = list ? n_list : 2 * b.n_reads;
+  const uint32_t* work_list = list ? list : o.mapped_list;
+  const uint32_t n = list ? n_list : *o.n_mapped;
   for (uint32_t i = tid; i < n; i += nthreads) {
-    uint32_t strand = list ? list[i] : i;
+    uint32_t strand = work_list[i];
     if (o.status[strand] != ST_MAPPED) continue;
     if (!record_strand(v, b, o, c, strand, my_arena, arena_words)) overflow_list[atomicAdd(n_overflow, 1u)] = strand;
   }

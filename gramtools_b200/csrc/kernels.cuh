@@ -8,7 +8,11 @@
 
 namespace gq {
 
-enum StrandStatus : uint8_t { ST_SKIPPED = 0, ST_MISSING_KMER = 1, ST_NO_EXTENSION = 2, ST_MAPPED = 3, ST_OVERFLOW = 255 };
+enum StrandStatus : uint8_t {
+  ST_SKIPPED = 0, ST_MISSING_KMER = 1, ST_NO_EXTENSION = 2, ST_MAPPED = 3,
+  ST_UNCLASSIFIED = 4,  // search produced no state: the classify kernel decides 1 vs 2
+  ST_OVERFLOW = 255
+};
 
 struct BatchView {               // one batch of reads, resident in HBM
   const uint32_t* packed;        // 2-bit base codes, 16 per word, every read starts on a word
@@ -28,6 +32,9 @@ struct SearchOut {
   uint32_t* pool_used;      // bump pointer
   uint32_t* overflow_list;  // strands that ran out of arena / pool
   uint32_t* n_overflow;
+  uint32_t* mapped_list;    // strands with >= 1 final state, in completion order (coverage work list)
+  uint32_t* n_mapped;
+  uint32_t* work_counter;   // dynamic work distribution of the search kernel
 };
 
 struct CoverageView {
@@ -56,9 +63,14 @@ void launch_search(const IndexView& v, const BatchView& b, const SearchOut& o, u
                    uint32_t arena_words, uint32_t n_threads, const uint32_t* list, uint32_t n_list,
                    bool super_in_smem, uint32_t rf_thresh, uint32_t ev_thresh, cudaStream_t st);
 
+// list == nullptr: the strands in o.mapped_list[0, *o.n_mapped); otherwise the listed strands.
 void launch_coverage(const IndexView& v, const BatchView& b, const SearchOut& o, const CoverageView& c,
                      uint32_t* arena, uint32_t arena_words, uint32_t n_threads, const uint32_t* list,
                      uint32_t n_list, uint32_t* overflow_list, uint32_t* n_overflow, cudaStream_t st);
+
+// k-mer filter for the strands whose search found nothing (status ST_UNCLASSIFIED -> 1 or 2)
+void launch_classify(const IndexView& v, const BatchView& b, const SearchOut& o, const uint32_t* list, uint32_t n_list,
+                     cudaStream_t st);
 
 void launch_stats(const uint8_t* status, const uint32_t* len, uint32_t n_reads, unsigned long long* stats,
                   cudaStream_t st);

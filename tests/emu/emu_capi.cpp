@@ -118,10 +118,10 @@ int emu_map(void* ev, const uint8_t* bases, const uint64_t* off, uint64_t n_read
     e->st_words.assign(2 * n_reads, 0);
     e->st_count.assign(2 * n_reads, 0);
     e->pool.assign(std::max<size_t>(1 << 16, n_reads * 256), 0);
-    std::vector<uint32_t> small(4, 0), ovf(2 * n_reads + 1), cov_ovf(2 * n_reads + 1);
+    std::vector<uint32_t> small(8, 0), ovf(2 * n_reads + 1), cov_ovf(2 * n_reads + 1), mapped(4 * n_reads + 1);
     BatchView b{packed.data(), word_off.data(), len.data(), seeds, (uint32_t)n_reads};
     SearchOut o{e->status.data(), e->st_off.data(), e->st_words.data(), e->st_count.data(), e->pool.data(),
-                (uint32_t)e->pool.size(), &small[0], ovf.data(), &small[1]};
+                (uint32_t)e->pool.size(), &small[0], ovf.data(), &small[1], mapped.data(), &small[3], &small[4]};
     CoverageView c{};
     uint64_t na = h.allele_off.back();
     c.allele_sum = e->counters.data();
@@ -142,6 +142,7 @@ int emu_map(void* ev, const uint8_t* bases, const uint64_t* off, uint64_t n_read
       uint32_t* a = arena.data();
       while (true) {  // same policy as the library: re-run the strand with a 4x larger arena
         small[1] = 0;
+        small[3] = 0;
         map_strand(v, v.super_cnt, b, o, s, a, aw);
         if (e->status[s] != ST_OVERFLOW) break;
         e->reruns++;
