@@ -176,7 +176,10 @@ struct EmitStage {
 // for strands that produced no state (classify_strand) — a strand that maps end to end necessarily has
 // all of its k-mers in the index, which holds every k-mer with >= 1 search state.
 // ------------------------------------------------------------------------------------------------
-enum LaneState : uint32_t { LS_IDLE = 0, LS_RUN = 1, LS_EV_SCAN = 2, LS_EV_POP = 3, LS_EV_TOP = 4, LS_EV_WIDE = 5 };
+enum LaneState : uint32_t {
+  LS_IDLE = 0, LS_RUN = 1 /* width-1 interval */, LS_EV_SCAN = 2, LS_EV_POP = 3, LS_EV_TOP = 4, LS_EV_WIDE = 5,
+  LS_RUNW = 6 /* wider interval */
+};
 
 struct Lane {
   uint32_t state;
@@ -204,7 +207,7 @@ GQ_DEV inline void lane_load_top(Lane& ln) {
   ln.pos = w0 & 0x0FFFFFFFu;
   ln.lo = t[1];
   ln.hi = t[2];
-  ln.state = (ln.kind == K_JUMP || ln.pos == 0) ? LS_EV_TOP : LS_RUN;
+  ln.state = (ln.kind == K_JUMP || ln.pos == 0) ? LS_EV_TOP : (ln.lo == ln.hi ? LS_RUN : LS_RUNW);
 }
 
 GQ_DEV inline void lane_finish_strand(Lane& ln, const SearchOut& o) {
@@ -287,68 +290,76 @@ GQ_DEV inline void lane_refill(Lane& ln, const IndexView& v, const BatchView& b,
   lane_load_top(ln);
 }
 
-// The hot path: one base for a lane in LS_RUN. Everything lives in registers; memory traffic is one
-// (or two) 32 B rank-block sectors. Any non-trivial outcome parks the lane in an event state.
-// `super_c` = per-superblock counts with C[c] folded in (IndexView::super_cnt_c), so
-// lo' = super_c[c] + blk.cnt[c] + popc(...) directly.
+// The hot path: one base for a lane in LS_RUN, i.e. a width-1 SA interval (the steady state after
+// seeding). Everything lives in registers; memory traffic is ONE 32 B rank-block sector; the step only
+// needs BWT[lo]. Any non-trivial outcome parks the lane in an event state.
+// `super_c` = per-superblock counts with C[c] folded in, so lo' = super_c[c] + blk.cnt[c] + popc(...).
 template <class SuperPtr>
 GQ_DEV inline void lane_step(Lane& ln, const IndexView& v, SuperPtr super_c) {
-  const uint32_t lo = ln.lo, hi = ln.hi;
+  const uint32_t lo = ln.lo;
   const uint32_t b0 = lo >> kBlkShift;
   const RankBlk B0 = load_blk(v.rank_blk + b0);
   const uint32_t c = ln.rd(ln.pos - 1);
   const uint64_t x0 = (c & 1u) ? 0ull : ~0ull, x1 = (c & 2u) ? 0ull : ~0ull;
-  uint32_t nlo, nhi;
-  if (lo == hi) {
-    // width-1 interval (the steady state after seeding): the step only needs BWT[lo]
-    const uint32_t r = lo & 63u;
-    const uint64_t bit = 1ull << r;
-    if (B0.p2 & bit) {  // not a nucleotide: marker -> jump (unless already scanned), sentinel -> dead
-      ln.state = ((B0.p0 & bit) && ln.kind == K_SCAN) ? LS_EV_SCAN : LS_EV_POP;
-      return;
-    }
-    const uint64_t m = ~B0.p2 & (B0.p0 ^ x0) & (B0.p1 ^ x1);
-    if (!(m & bit)) {
-      ln.state = LS_EV_POP;
-      return;
-    }
-    nlo = super_c[4 * (b0 >> (kSuperShift - kBlkShift)) + c] + ((uint32_t)(B0.cnt >> (16 * c)) & 0xFFFFu) +
-          (uint32_t)popc64(m & (bit - 1));
-    nhi = nlo;
-  } else {
-    const uint32_t bh = hi >> kBlkShift, b1 = (hi + 1) >> kBlkShift;
-    const RankBlk B1 = (b1 == b0) ? B0 : load_blk(v.rank_blk + b1);
-    if (ln.kind == K_SCAN) {
-      uint64_t mk;
-      if (bh == b0) mk = marker_bits_in(B0, b0 << kBlkShift, lo, hi);
-      else if (bh == b1 && b1 == b0 + 1)
-        mk = marker_bits_in(B0, b0 << kBlkShift, lo, hi) | marker_bits_in(B1, b1 << kBlkShift, lo, hi);
-      else {  // interval wider than the two fetched blocks: rare, resolved in the event path
-        ln.state = LS_EV_WIDE;
-        return;
-      }
-      if (mk) {
-        ln.state = LS_EV_SCAN;
-        return;
-      }
-    }
-    const uint64_t m0 = ~B0.p2 & (B0.p0 ^ x0) & (B0.p1 ^ x1);
-    const uint64_t m1 = ~B1.p2 & (B1.p0 ^ x0) & (B1.p1 ^ x1);
-    const uint32_t ra = lo & 63u, rb = (hi + 1) & 63u;
-    const uint32_t r0 = super_c[4 * (b0 >> (kSuperShift - kBlkShift)) + c] + ((uint32_t)(B0.cnt >> (16 * c)) & 0xFFFFu) +
-                        (uint32_t)popc64(m0 & ((1ull << ra) - 1));
-    const uint32_t r1 = super_c[4 * (b1 >> (kSuperShift - kBlkShift)) + c] + ((uint32_t)(B1.cnt >> (16 * c)) & 0xFFFFu) +
-                        (uint32_t)popc64(m1 & ((1ull << rb) - 1));
-    if (r1 <= r0) {
-      ln.state = LS_EV_POP;
-      return;
-    }
-    nlo = r0;
-    nhi = r1 - 1;
+  const uint64_t bit = 1ull << (lo & 63u);
+  if (B0.p2 & bit) {  // not a nucleotide: marker -> jump (unless already scanned), sentinel -> dead
+    ln.state = ((B0.p0 & bit) && ln.kind == K_SCAN) ? LS_EV_SCAN : LS_EV_POP;
+    return;
   }
-  ln.lo = nlo;
-  ln.hi = nhi;
+  const uint64_t m = ~B0.p2 & (B0.p0 ^ x0) & (B0.p1 ^ x1);
+  if (!(m & bit)) {
+    ln.state = LS_EV_POP;
+    return;
+  }
+  ln.lo = ln.hi = super_c[4 * (b0 >> (kSuperShift - kBlkShift)) + c] + ((uint32_t)(B0.cnt >> (16 * c)) & 0xFFFFu) +
+                  (uint32_t)popc64(m & (bit - 1));
   ln.kind = K_SCAN;
+  if (--ln.pos == 0) {
+    lane_writeback(ln, K_SCAN);
+    ln.state = LS_EV_TOP;
+  }
+}
+
+// One base for a lane in LS_RUNW: SA interval wider than one suffix (the first bases after seeding, and
+// states that just entered a site). Two rank queries (BWT_search.cpp:45-76) + the marker test of the
+// interval (vBWT_jump.cpp:100-101).
+template <class SuperPtr>
+GQ_DEV inline void lane_step_wide(Lane& ln, const IndexView& v, SuperPtr super_c) {
+  const uint32_t lo = ln.lo, hi = ln.hi;
+  const uint32_t b0 = lo >> kBlkShift, bh = hi >> kBlkShift, b1 = (hi + 1) >> kBlkShift;
+  const RankBlk B0 = load_blk(v.rank_blk + b0);
+  const RankBlk B1 = (b1 == b0) ? B0 : load_blk(v.rank_blk + b1);
+  if (ln.kind == K_SCAN) {
+    uint64_t mk;
+    if (bh == b0) mk = marker_bits_in(B0, b0 << kBlkShift, lo, hi);
+    else if (bh == b1 && b1 == b0 + 1)
+      mk = marker_bits_in(B0, b0 << kBlkShift, lo, hi) | marker_bits_in(B1, b1 << kBlkShift, lo, hi);
+    else {  // interval wider than the two fetched blocks: rare, resolved in the event path
+      ln.state = LS_EV_WIDE;
+      return;
+    }
+    if (mk) {
+      ln.state = LS_EV_SCAN;
+      return;
+    }
+  }
+  const uint32_t c = ln.rd(ln.pos - 1);
+  const uint64_t x0 = (c & 1u) ? 0ull : ~0ull, x1 = (c & 2u) ? 0ull : ~0ull;
+  const uint64_t m0 = ~B0.p2 & (B0.p0 ^ x0) & (B0.p1 ^ x1);
+  const uint64_t m1 = ~B1.p2 & (B1.p0 ^ x0) & (B1.p1 ^ x1);
+  const uint32_t ra = lo & 63u, rb = (hi + 1) & 63u;
+  const uint32_t r0 = super_c[4 * (b0 >> (kSuperShift - kBlkShift)) + c] + ((uint32_t)(B0.cnt >> (16 * c)) & 0xFFFFu) +
+                      (uint32_t)popc64(m0 & ((1ull << ra) - 1));
+  const uint32_t r1 = super_c[4 * (b1 >> (kSuperShift - kBlkShift)) + c] + ((uint32_t)(B1.cnt >> (16 * c)) & 0xFFFFu) +
+                      (uint32_t)popc64(m1 & ((1ull << rb) - 1));
+  if (r1 <= r0) {
+    ln.state = LS_EV_POP;
+    return;
+  }
+  ln.lo = r0;
+  ln.hi = r1 - 1;
+  ln.kind = K_SCAN;
+  ln.state = (ln.lo == ln.hi) ? LS_RUN : LS_RUNW;
   if (--ln.pos == 0) {
     lane_writeback(ln, K_SCAN);
     ln.state = LS_EV_TOP;
@@ -368,7 +379,7 @@ GQ_DEV inline void lane_after_event(Lane& ln, const SearchOut& o) {
 GQ_DEV inline void lane_event_scan(Lane& ln, const IndexView& v, const SearchOut& o) {
   if (ln.state == LS_EV_WIDE && !interval_has_marker(v, ln.lo, ln.hi)) {
     ln.kind = K_READY;  // scanned, nothing found: extend without re-scanning
-    ln.state = LS_RUN;
+    ln.state = LS_RUNW;
     return;
   }
   if (ln.lo == ln.hi) {
@@ -473,6 +484,7 @@ GQ_DEV inline void map_strand(const IndexView& v, const uint32_t* super_cnt, con
   lane_refill(ln, v, b, o, strand, arena, arena_words);
   while (ln.state != LS_IDLE) {
     if (ln.state == LS_RUN) lane_step(ln, v, super_cnt);
+    else if (ln.state == LS_RUNW) lane_step_wide(ln, v, super_cnt);
     else lane_event(ln, v, o);
   }
   if (o.status[strand] == ST_UNCLASSIFIED) classify_strand(v, b, o, strand);

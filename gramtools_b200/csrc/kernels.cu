@@ -109,28 +109,35 @@ __global__ void __launch_bounds__(kSearchThreads)
   while (true) {
     const uint32_t idle = __ballot_sync(full, ln.state == LS_IDLE);
     const uint32_t run = __ballot_sync(full, ln.state == LS_RUN);
+    const uint32_t wide = __ballot_sync(full, ln.state == LS_RUNW);
     const uint32_t scan = __ballot_sync(full, ln.state == LS_EV_SCAN || ln.state == LS_EV_WIDE);
     const uint32_t popm = __ballot_sync(full, ln.state == LS_EV_POP);
-    const uint32_t top = ~(idle | run | scan | popm);
+    const uint32_t top = ~(idle | run | wide | scan | popm);
     if (idle == full && !work_left) break;
-    const uint32_t n_idle = work_left ? __popc(idle) : 0, n_scan = __popc(scan), n_pop = __popc(popm),
-                   n_top = __popc(top);
-    const bool flush = run == 0 || n_idle + n_scan + n_pop + n_top >= wait_max;
-    bool did = false;
-    if (n_scan && (n_scan >= ev_thresh || flush)) {
+    const uint32_t n_idle = work_left ? __popc(idle) : 0, n_wide = __popc(wide), n_scan = __popc(scan),
+                   n_pop = __popc(popm), n_top = __popc(top);
+    // service a class when enough lanes wait in it; when nothing can step, or too many lanes wait in
+    // total, service the most populated class
+    const uint32_t waiting = n_idle + n_wide + n_scan + n_pop + n_top;
+    const bool force = run == 0 || waiting >= wait_max;
+    const uint32_t big = max(max(max(n_idle, n_wide), max(n_scan, n_pop)), n_top);
+    if (n_wide && (n_wide >= ev_thresh || (force && n_wide == big))) {
+      if (ln.state == LS_RUNW) lane_step_wide(ln, v, SUPER_SMEM ? (const uint32_t*)s_super : v.super_cnt);
+      continue;
+    }
+    if (n_scan && (n_scan >= ev_thresh || (force && n_scan == big))) {
       if (ln.state == LS_EV_SCAN || ln.state == LS_EV_WIDE) lane_event_scan(ln, v, o);
-      did = true;
+      continue;
     }
-    if (n_top && (n_top >= ev_thresh || flush)) {
+    if (n_top && (n_top >= ev_thresh || (force && n_top == big))) {
       if (ln.state == LS_EV_TOP) lane_event_top(ln, v, o);
-      did = true;
+      continue;
     }
-    if (n_pop && (n_pop >= ev_thresh || flush)) {
+    if (n_pop && (n_pop >= ev_thresh || (force && n_pop == big))) {
       if (ln.state == LS_EV_POP) lane_event_pop(ln, o);
-      did = true;
+      continue;
     }
-    if (did) continue;  // states changed: re-vote (finished strands become idle lanes)
-    if (n_idle && (n_idle >= rf_thresh || flush)) {
+    if (n_idle && (n_idle >= rf_thresh || (force && n_idle == big))) {
       uint32_t base = 0;
       if (lane == 0) base = atomicAdd(o.work_counter, (uint32_t)__popc(idle));
       base = __shfl_sync(full, base, 0);
