@@ -278,6 +278,7 @@ def main():
             q_rank = evc["q_rank"] / evc["reads"]
             alg_bytes_per_read = 32.0 * q_rank + 2 * ((READ_LEN + 3) // 4) + 2 * ((READ_LEN - KMER + 1 + 7) // 8) + 16
         roof = None
+        kernels = {"search_ms": search_ms / args.steps, "classify_coverage_ms": cov_ms / args.steps}
         if alg_bytes_per_read is not None:
             per_launch_s = (search_ms / args.steps) / 1e3
             achieved = alg_bytes_per_read * N_READS / per_launch_s / 1e9
@@ -293,7 +294,7 @@ def main():
             "e2e": {"value": reads_total / (e2e_ms / 1e3), "unit": "reads/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
-            "roofline": roof, "cpu_baseline": cpu,
+            "roofline": roof, "cpu_baseline": cpu, "kernels": kernels,
             "stats": {"all_reads": stats.all_reads_count, "skipped": stats.skipped_reads_count,
                       "missing_kmer": stats.missing_kmer_reads_count, "no_extension": stats.no_extension_reads_count,
                       "exact_mapped": stats.exact_mapped_reads_count, "rerun_strands": int(reruns),

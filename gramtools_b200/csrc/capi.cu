@@ -71,6 +71,9 @@ struct gq_index {
   DevBuf<uint32_t> st_off, st_words, st_count, pool, small;  // small: [pool_used, n_overflow, n_cov_overflow]
   DevBuf<uint32_t> overflow_list, cov_overflow_list, mapped_list;
   DevBuf<uint32_t> arena, big_arena;
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> chunk_events;
+  uint32_t chunk_reads = 1u << 18;  // slice size of the H2D / compute pipeline in gq_map_batch
   // options
   uint32_t arena_words = 512;
   uint32_t n_threads = 148 * 1024;
@@ -170,46 +173,62 @@ static gq::CoverageView cov_view(gq_index* ix) {
   return c;
 }
 
-static void do_upload(gq_index* ix, const uint8_t* bases, const uint64_t* off, uint64_t n_reads,
-                      const uint32_t* seeds) {
+static void reserve_batch(gq_index* ix, uint64_t n_reads, uint64_t nb) {
   if (n_reads >= (1ull << 30)) throw std::runtime_error("batch too large (max 2^30 reads per batch)");
-  CUDA_OK(cudaSetDevice(ix->device));
-  ix->n_reads = (uint32_t)n_reads;
-  if (n_reads == 0) return;
-  uint64_t nb = off[n_reads] - off[0];
-  if (off[0] != 0) throw std::runtime_error("read_offsets[0] must be 0");
-  std::vector<uint32_t> word_off(n_reads + 1);
-  uint64_t w = 0;
-  for (uint64_t r = 0; r < n_reads; ++r) {
-    word_off[r] = (uint32_t)w;
-    w += (off[r + 1] - off[r] + 15) >> 4;
-    if (w >= (1ull << 32)) throw std::runtime_error("batch too large (packed words exceed 2^32)");
-  }
-  word_off[n_reads] = (uint32_t)w;
-  ix->total_words = (uint32_t)w;
-  cudaStream_t st = ix->stream;
+  uint64_t max_words = (nb >> 4) + n_reads + 2;  // read r starts at word (offset >> 4) + r
+  if (max_words >= (1ull << 32)) throw std::runtime_error("batch too large (packed words exceed 2^32)");
   ix->bases.reserve(nb + 16);
   ix->offsets.reserve(n_reads + 1);
   ix->word_off.reserve(n_reads + 1);
-  ix->packed.reserve(w + 1);
+  ix->packed.reserve(max_words);
   ix->len.reserve(n_reads);
   ix->seeds.reserve(n_reads);
-  CUDA_OK(cudaMemcpyAsync(ix->bases.p, bases, nb, cudaMemcpyHostToDevice, st));
-  CUDA_OK(cudaMemcpyAsync(ix->offsets.p, off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
-  CUDA_OK(cudaMemcpyAsync(ix->word_off.p, word_off.data(), (n_reads + 1) * 4, cudaMemcpyHostToDevice, st));
-  CUDA_OK(cudaMemcpyAsync(ix->seeds.p, seeds, n_reads * 4, cudaMemcpyHostToDevice, st));
-  gq::launch_pack(ix->bases.p, ix->offsets.p, ix->word_off.p, ix->n_reads, ix->total_words, ix->packed.p, ix->len.p,
-                  st);
-  CUDA_OK(cudaGetLastError());
-  // word_off is a stack-local pageable buffer: wait for the copies before it goes away
-  CUDA_OK(cudaStreamSynchronize(st));
-  ix->info[5] = (double)(nb + (n_reads + 1) * 12 + n_reads * 4);  // H2D bytes of this upload
 }
 
-static void do_map(gq_index* ix) {
+struct Chunk {
+  uint32_t r0, r1;
+};
+
+static std::vector<Chunk> make_chunks(gq_index* ix, uint32_t n, bool pipelined) {
+  std::vector<Chunk> ch;
+  uint32_t per = pipelined ? std::max<uint32_t>(ix->chunk_reads, (n + 31) / 32) : n;
+  for (uint32_t r = 0; r < n; r += per) ch.push_back({r, std::min<uint32_t>(n, r + per)});
+  return ch;
+}
+
+// H2D of one slice of the caller's buffers + 2-bit packing, on stream `st`
+static void upload_chunk(gq_index* ix, const uint8_t* bases, const uint64_t* off, const uint32_t* seeds, Chunk c,
+                         cudaStream_t st) {
+  uint64_t b0 = off[c.r0], b1 = off[c.r1];
+  if (b1 > b0) CUDA_OK(cudaMemcpyAsync(ix->bases.p + b0, bases + b0, b1 - b0, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(ix->offsets.p + c.r0, off + c.r0, (size_t)(c.r1 - c.r0 + 1) * 8, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(ix->seeds.p + c.r0, seeds + c.r0, (size_t)(c.r1 - c.r0) * 4, cudaMemcpyHostToDevice, st));
+  gq::launch_pack(ix->bases.p, ix->offsets.p, c.r0, c.r1, ix->word_off.p, ix->packed.p, ix->len.p, st);
+}
+
+static void do_upload(gq_index* ix, const uint8_t* bases, const uint64_t* off, uint64_t n_reads,
+                      const uint32_t* seeds) {
   CUDA_OK(cudaSetDevice(ix->device));
+  if (n_reads && off[0] != 0) throw std::runtime_error("read_offsets[0] must be 0");
+  uint64_t nb = n_reads ? off[n_reads] : 0;
+  reserve_batch(ix, n_reads, nb);
+  ix->n_reads = (uint32_t)n_reads;
+  if (n_reads == 0) return;
+  upload_chunk(ix, bases, off, seeds, Chunk{0, (uint32_t)n_reads}, ix->stream);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaStreamSynchronize(ix->stream));  // the caller's buffers may go away after this call
+  ix->info[5] = (double)(nb + (n_reads + 1) * 8 + n_reads * 4);  // H2D bytes of this upload
+}
+
+// Map the batch. host pointers != nullptr: the reads come from the caller's HOST buffers and the H2D
+// copy of slice i+1 (copy stream) overlaps the kernels of slice i (compute stream).
+static void do_map(gq_index* ix, const uint8_t* h_bases = nullptr, const uint64_t* h_off = nullptr,
+                   const uint32_t* h_seeds = nullptr) {
+  CUDA_OK(cudaSetDevice(ix->device));
+  const bool pipelined = h_bases != nullptr || h_off != nullptr;
   const uint32_t n = ix->n_reads;
-  for (double& x : ix->info) x = (&x == &ix->info[5]) ? x : 0;
+  for (int i = 0; i < 8; ++i)
+    if (i != 5) ix->info[i] = 0;
   if (n == 0) return;
   cudaStream_t st = ix->stream;
   ix->status.reserve(2 * (size_t)n);
@@ -219,40 +238,74 @@ static void do_map(gq_index* ix) {
   ix->overflow_list.reserve(2 * (size_t)n);
   ix->cov_overflow_list.reserve(2 * (size_t)n);
   ix->mapped_list.reserve(2 * (size_t)n);
-  ix->small.reserve(8);
+  ix->small.reserve(8 + 2 * 64);
   size_t pool_need = std::max<size_t>((size_t)n * ix->pool_words_per_read, 1 << 16);
   pool_need = std::min<size_t>(pool_need, 0xFFFFFFF0ull);
   ix->pool.reserve(pool_need);
-  uint32_t threads = std::min<uint32_t>(ix->n_threads, ((2 * n + 255) / 256) * 256);
-  // the coverage kernel walks strands: give it the same arena (2n strands over `threads2` threads)
-  uint32_t threads2 = std::min<uint32_t>(ix->n_threads, ((2 * n + 255) / 256) * 256);
+  std::vector<Chunk> chunks = make_chunks(ix, n, pipelined);
+  uint32_t max_chunk = 0;
+  for (auto& c : chunks) max_chunk = std::max(max_chunk, c.r1 - c.r0);
+  // persistent lanes: never more than one lane per 4 strands, so the refill/batching steady state exists
+  uint32_t threads = std::min<uint32_t>(ix->n_threads, std::max<uint32_t>(256, ((2 * max_chunk / 4 + 255) / 256) * 256));
+  uint32_t threads2 = std::min<uint32_t>(ix->n_threads, ((2 * max_chunk + 255) / 256) * 256);
   ix->arena.reserve((size_t)std::max(threads, threads2) * ix->arena_words);
-  CUDA_OK(cudaMemsetAsync(ix->small.p, 0, 32, st));  // [pool_used, n_overflow, n_cov_overflow, n_mapped, work_counter]
+  // small: [0] pool_used [1] n_overflow [2] n_cov_overflow; per chunk c: [8+2c] n_mapped [9+2c] work counter
+  CUDA_OK(cudaMemsetAsync(ix->small.p, 0, (8 + 2 * 64) * 4, st));
 
-  gq::BatchView b{ix->packed.p, ix->word_off.p, ix->len.p, ix->seeds.p, n};
+  gq::BatchView b{ix->packed.p, ix->word_off.p, ix->len.p, ix->seeds.p, n, 0, n};
   gq::SearchOut o{ix->status.p, ix->st_off.p, ix->st_words.p, ix->st_count.p, ix->pool.p, (uint32_t)ix->pool.cap,
-                  ix->small.p,  ix->overflow_list.p, ix->small.p + 1, ix->mapped_list.p, ix->small.p + 3,
-                  ix->small.p + 4};
+                  ix->small.p,  ix->overflow_list.p, ix->small.p + 1, ix->mapped_list.p, ix->small.p + 8,
+                  ix->small.p + 9};
   gq::CoverageView c = cov_view(ix);
   int launches = 0;
+  if (pipelined) {
+    if (!ix->copy_stream) CUDA_OK(cudaStreamCreateWithFlags(&ix->copy_stream, cudaStreamNonBlocking));
+    while (ix->chunk_events.size() < chunks.size()) {
+      cudaEvent_t e;
+      CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      ix->chunk_events.push_back(e);
+    }
+    // the copy stream must not start overwriting buffers the compute stream may still be reading
+    CUDA_OK(cudaEventRecord(ix->ev[3], st));
+    CUDA_OK(cudaStreamWaitEvent(ix->copy_stream, ix->ev[3], 0));
+    for (size_t i = 0; i < chunks.size(); ++i) {
+      upload_chunk(ix, h_bases, h_off, h_seeds, chunks[i], ix->copy_stream);
+      CUDA_OK(cudaEventRecord(ix->chunk_events[i], ix->copy_stream));
+      launches += 1;
+    }
+  }
   CUDA_OK(cudaEventRecord(ix->ev[0], st));
-  gq::launch_search(ix->dv, b, o, ix->arena.p, ix->arena_words, threads, nullptr, 0, ix->super_in_smem, ix->rf_thresh, ix->ev_thresh, st);
-  ++launches;
-  CUDA_OK(cudaEventRecord(ix->ev[1], st));
-  gq::launch_classify(ix->dv, b, o, nullptr, 0, st);
-  gq::launch_coverage(ix->dv, b, o, c, ix->arena.p, ix->arena_words, threads2, nullptr, 0, ix->cov_overflow_list.p,
-                      ix->small.p + 2, st);
-  launches += 2;
+  for (size_t i = 0; i < chunks.size(); ++i) {
+    if (pipelined) CUDA_OK(cudaStreamWaitEvent(st, ix->chunk_events[i], 0));
+    gq::BatchView bc = b;
+    bc.read_begin = chunks[i].r0;
+    bc.read_end = chunks[i].r1;
+    gq::SearchOut oc = o;
+    oc.mapped_list = ix->mapped_list.p + 2 * (size_t)chunks[i].r0;
+    oc.n_mapped = ix->small.p + 8 + 2 * i;
+    oc.work_counter = ix->small.p + 9 + 2 * i;
+    gq::launch_search(ix->dv, bc, oc, ix->arena.p, ix->arena_words, threads, nullptr, 0, ix->super_in_smem,
+                      ix->rf_thresh, ix->ev_thresh, st);
+    if (chunks.size() == 1) CUDA_OK(cudaEventRecord(ix->ev[1], st));
+    gq::launch_classify(ix->dv, bc, oc, nullptr, 0, st);
+    gq::launch_coverage(ix->dv, bc, oc, c, ix->arena.p, ix->arena_words, threads2, nullptr, 0,
+                        ix->cov_overflow_list.p, ix->small.p + 2, st);
+    launches += 3;
+  }
   CUDA_OK(cudaEventRecord(ix->ev[2], st));
   uint32_t small[4];
   CUDA_OK(cudaMemcpyAsync(small, ix->small.p, 16, cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaStreamSynchronize(st));
   CUDA_OK(cudaGetLastError());
-  float ms_s = 0, ms_c = 0;
-  cudaEventElapsedTime(&ms_s, ix->ev[0], ix->ev[1]);
-  cudaEventElapsedTime(&ms_c, ix->ev[1], ix->ev[2]);
-  ix->info[2] = ms_s;
-  ix->info[3] = ms_c;
+  if (chunks.size() == 1) {
+    float ms_s = 0, ms_c = 0;
+    cudaEventElapsedTime(&ms_s, ix->ev[0], ix->ev[1]);
+    cudaEventElapsedTime(&ms_c, ix->ev[1], ix->ev[2]);
+    ix->info[2] = ms_s;
+    ix->info[3] = ms_c;
+  }
+  // list-mode re-runs below hand out work from counter slot [9] and append to the (already consumed)
+  // mapped list of slice 0
   uint64_t rerun = 0;
   // ---- overflow re-runs: same kernels, fewer threads, much larger per-thread arenas -------------
   uint32_t big_words = ix->big_arena_words;
@@ -283,7 +336,7 @@ static void do_map(gq_index* ix) {
     list.reserve(n_list);
     CUDA_OK(cudaMemcpyAsync(list.p, ix->overflow_list.p, (size_t)n_list * 4, cudaMemcpyDeviceToDevice, st));
     CUDA_OK(cudaMemsetAsync(ix->small.p + 1, 0, 4, st));
-    CUDA_OK(cudaMemsetAsync(ix->small.p + 4, 0, 4, st));  // work counter of the list run
+    CUDA_OK(cudaMemsetAsync(ix->small.p + 9, 0, 4, st));  // work counter of the list run
     gq::launch_search(ix->dv, b, o, ix->big_arena.p, big_words, bt, list.p, n_list, ix->super_in_smem, ix->rf_thresh, ix->ev_thresh, st);
     gq::launch_classify(ix->dv, b, o, list.p, n_list, st);
     ++launches;
@@ -407,6 +460,8 @@ int gq_index_destroy(gq_index* ix) {
   ix->big_arena.release();
   for (auto& e : ix->ev)
     if (e) cudaEventDestroy(e);
+  for (auto& e : ix->chunk_events) cudaEventDestroy(e);
+  if (ix->copy_stream) cudaStreamDestroy(ix->copy_stream);
   if (ix->own_stream) cudaStreamDestroy(ix->own_stream);
   delete ix;
   return 0;
@@ -470,8 +525,13 @@ int gq_map_resident(gq_index* ix) {
 int gq_map_batch(gq_index* ix, const uint8_t* bases, const uint64_t* off, uint64_t n_reads, const uint32_t* seeds) {
   GQ_TRY
   if (!ix || (n_reads && (!bases || !off || !seeds))) throw std::runtime_error("null argument");
-  do_upload(ix, bases, off, n_reads, seeds);
-  do_map(ix);
+  CUDA_OK(cudaSetDevice(ix->device));
+  if (n_reads && off[0] != 0) throw std::runtime_error("read_offsets[0] must be 0");
+  uint64_t nb = n_reads ? off[n_reads] : 0;
+  reserve_batch(ix, n_reads, nb);
+  ix->n_reads = (uint32_t)n_reads;
+  ix->info[5] = (double)(nb + (n_reads + 1) * 8 + n_reads * 4);
+  do_map(ix, bases, off, seeds);
   GQ_CATCH
 }
 
@@ -716,6 +776,8 @@ int gq_set_option(gq_index* ix, const char* name, int64_t value) {
   } else if (n == "pool_words_per_read") {
     ix->pool_words_per_read = (uint32_t)std::max<int64_t>(value, 1);
     ix->pool.release();
+  } else if (n == "chunk_reads") {
+    ix->chunk_reads = (uint32_t)std::max<int64_t>(value, 1024);
   } else if (n == "rf_thresh") {
     ix->rf_thresh = (uint32_t)value;
   } else if (n == "ev_thresh") {

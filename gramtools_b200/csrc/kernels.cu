@@ -20,17 +20,20 @@
 namespace gq {
 
 // ------------------------------------------------------------------------------------------------
-__global__ void pack_kernel(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offsets,
-                            const uint32_t* __restrict__ word_off, uint32_t n_reads, uint32_t* __restrict__ packed,
+__global__ void pack_kernel(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offsets, uint32_t r0,
+                            uint32_t r1, uint32_t* __restrict__ word_off, uint32_t* __restrict__ packed,
                             uint32_t* __restrict__ len) {
   // one warp per read; lanes write consecutive words
   uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t r = warp; r < n_reads; r += nwarps) {
+  for (uint32_t r = r0 + warp; r < r1; r += nwarps) {
     uint64_t b0 = offsets[r];
     uint32_t L = (uint32_t)(offsets[r + 1] - b0);
-    if (lane == 0) len[r] = L;
-    uint32_t w0 = word_off[r], nw = (L + 15) >> 4;
+    uint32_t w0 = (uint32_t)(b0 >> 4) + r, nw = (L + 15) >> 4;
+    if (lane == 0) {
+      len[r] = L;
+      word_off[r] = w0;
+    }
     for (uint32_t w = lane; w < nw; w += 32) {
       uint32_t x = 0;
       uint32_t base = w << 4;
@@ -41,12 +44,11 @@ __global__ void pack_kernel(const uint8_t* __restrict__ bases, const uint64_t* _
   }
 }
 
-void launch_pack(const uint8_t* bases, const uint64_t* offsets, const uint32_t* word_off, uint32_t n_reads,
-                 uint32_t total_words, uint32_t* packed, uint32_t* len, cudaStream_t st) {
-  (void)total_words;
-  if (n_reads == 0) return;
-  uint32_t blocks = min((n_reads + 7) / 8, 148u * 16u);
-  pack_kernel<<<blocks, 256, 0, st>>>(bases, offsets, word_off, n_reads, packed, len);
+void launch_pack(const uint8_t* bases, const uint64_t* offsets, uint32_t r0, uint32_t r1, uint32_t* word_off,
+                 uint32_t* packed, uint32_t* len, cudaStream_t st) {
+  if (r1 <= r0) return;
+  uint32_t blocks = min((r1 - r0 + 7) / 8, 148u * 16u);
+  pack_kernel<<<blocks, 256, 0, st>>>(bases, offsets, r0, r1, word_off, packed, len);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -99,7 +101,8 @@ __global__ void __launch_bounds__(kSearchThreads)
   if (SUPER_SMEM) tma_stage_super(s_super, v.super_cnt, n_super_smem * 16u, &s_bar);
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t work = list ? n_list : 2 * b.n_reads;
+  const uint32_t work = list ? n_list : 2 * (b.read_end - b.read_begin);
+  const uint32_t strand0 = 2 * b.read_begin;
   bool work_left = true;  // warp-uniform: strands are handed out by one global counter
   uint32_t* my_arena = arena + (size_t)tid * arena_words;
   Lane ln;
@@ -143,7 +146,7 @@ __global__ void __launch_bounds__(kSearchThreads)
       base = __shfl_sync(full, base, 0);
       if (ln.state == LS_IDLE) {
         uint32_t i = base + __popc(idle & ((1u << lane) - 1u));
-        if (i < work) lane_refill(ln, v, b, o, list ? list[i] : i, my_arena, arena_words);
+        if (i < work) lane_refill(ln, v, b, o, list ? list[i] : strand0 + i, my_arena, arena_words);
       }
       work_left = base + (uint32_t)__popc(idle) < work;
       continue;
@@ -164,16 +167,16 @@ __global__ void __launch_bounds__(kSearchThreads)
 
 __global__ void __launch_bounds__(256)
     classify_kernel(IndexView v, BatchView b, SearchOut o, const uint32_t* list, uint32_t n_list) {
-  const uint32_t n = list ? n_list : 2 * b.n_reads;
+  const uint32_t n = list ? n_list : 2 * (b.read_end - b.read_begin);
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    uint32_t strand = list ? list[i] : i;
+    uint32_t strand = list ? list[i] : 2 * b.read_begin + i;
     if (o.status[strand] == ST_UNCLASSIFIED) classify_strand(v, b, o, strand);
   }
 }
 
 void launch_classify(const IndexView& v, const BatchView& b, const SearchOut& o, const uint32_t* list, uint32_t n_list,
                      cudaStream_t st) {
-  uint32_t work = list ? n_list : 2 * b.n_reads;
+  uint32_t work = list ? n_list : 2 * (b.read_end - b.read_begin);
   if (work == 0) return;
   uint32_t blocks = min((work + 255) / 256, 148u * 8u);
   classify_kernel<<<blocks, 256, 0, st>>>(v, b, o, list, n_list);
@@ -184,7 +187,7 @@ int search_kernel_smem_limit_superblocks() { return kMaxSuperSmem; }
 void launch_search(const IndexView& v, const BatchView& b, const SearchOut& o, uint32_t* arena,
                    uint32_t arena_words, uint32_t n_threads, const uint32_t* list, uint32_t n_list,
                    bool super_in_smem, uint32_t rf_thresh, uint32_t ev_thresh, cudaStream_t st) {
-  uint32_t work = list ? n_list : 2 * b.n_reads;
+  uint32_t work = list ? n_list : 2 * (b.read_end - b.read_begin);
   if (work == 0) return;
   uint32_t blocks = (min(work, n_threads) + kSearchThreads - 1) / kSearchThreads;
   uint32_t n_super = (v.n >> kSuperShift) + 1;
@@ -222,7 +225,7 @@ __global__ void __launch_bounds__(256)
 void launch_coverage(const IndexView& v, const BatchView& b, const SearchOut& o, const CoverageView& c,
                      uint32_t* arena, uint32_t arena_words, uint32_t n_threads, const uint32_t* list,
                      uint32_t n_list, uint32_t* overflow_list, uint32_t* n_overflow, cudaStream_t st) {
-  uint32_t work = list ? n_list : 2 * b.n_reads;
+  uint32_t work = list ? n_list : 2 * (b.read_end - b.read_begin);
   if (work == 0) return;
   uint32_t blocks = (min(work, n_threads) + 255) / 256;
   coverage_kernel<<<blocks, 256, 0, st>>>(v, b, o, c, arena, arena_words, list, n_list, overflow_list, n_overflow);

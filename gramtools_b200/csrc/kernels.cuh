@@ -19,7 +19,8 @@ struct BatchView {               // one batch of reads, resident in HBM
   const uint32_t* word_off;      // n_reads + 1
   const uint32_t* len;           // n_reads (0 = skipped read)
   const uint32_t* seeds;         // n_reads (selection seed, shared by both strands)
-  uint32_t n_reads;
+  uint32_t n_reads;              // reads in the whole batch (arrays above are indexed by read id)
+  uint32_t read_begin, read_end; // the slice of the batch this launch works on (H2D/compute pipelining)
 };
 
 struct SearchOut {
@@ -53,9 +54,10 @@ struct CoverageView {
   uint32_t* error_flags;     // bit0: grouped table/pool full, bit1: inconsistent traversal
 };
 
-// bases (uint8 1..4, concatenated, device) -> packed 2-bit words
-void launch_pack(const uint8_t* bases, const uint64_t* offsets, const uint32_t* word_off, uint32_t n_reads,
-                 uint32_t total_words, uint32_t* packed, uint32_t* len, cudaStream_t st);
+// bases (uint8 1..4, concatenated, device) -> packed 2-bit words for reads [r0, r1). Read r starts at word
+// (offsets[r] >> 4) + r: word-aligned and non-overlapping without a prefix sum (<= 1 word wasted per read).
+void launch_pack(const uint8_t* bases, const uint64_t* offsets, uint32_t r0, uint32_t r1, uint32_t* word_off,
+                 uint32_t* packed, uint32_t* len, cudaStream_t st);
 
 // list == nullptr: all reads of the batch (one thread per read, both strands);
 // otherwise only the listed strands (overflow re-runs with a larger arena).

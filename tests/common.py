@@ -82,6 +82,9 @@ def emu_lib():
         lib.emu_grouped.argtypes = [C.c_void_p, u32p]
         lib.emu_grouped.restype = C.c_uint64
         lib.emu_stats.argtypes = [C.c_void_p, u64p]
+        lib.emu_counters_raw.argtypes = [C.c_void_p, u32p]
+        lib.emu_groups_raw.argtypes = [C.c_void_p, u32p]
+        lib.emu_groups_raw.restype = C.c_uint64
         _emu = lib
     return _emu
 
@@ -200,6 +203,22 @@ class Emu:
         if rc != 0:
             raise RuntimeError(self.lib.emu_last_error().decode())
         self.n_reads = n
+
+    def counters_raw(self):
+        out = np.zeros(max(2 * self.n_alleles + self.n_per_base, 1), dtype=np.uint32)
+        self.lib.emu_counters_raw(self.h, _ptr(out, C.c_uint32))
+        return out[:2 * self.n_alleles + self.n_per_base]
+
+    def groups_raw(self):
+        n = self.lib.emu_groups_raw(self.h, None)
+        w = np.zeros(max(n, 1), dtype=np.uint32)
+        self.lib.emu_groups_raw(self.h, _ptr(w, C.c_uint32))
+        return w[:n]
+
+    def stats(self):
+        st = np.zeros(5, dtype=np.uint64)
+        self.lib.emu_stats(self.h, _ptr(st, C.c_uint64))
+        return st
 
     def result(self):
         n = self.n_reads

@@ -119,7 +119,7 @@ int emu_map(void* ev, const uint8_t* bases, const uint64_t* off, uint64_t n_read
     e->st_count.assign(2 * n_reads, 0);
     e->pool.assign(std::max<size_t>(1 << 16, n_reads * 256), 0);
     std::vector<uint32_t> small(8, 0), ovf(2 * n_reads + 1), cov_ovf(2 * n_reads + 1), mapped(4 * n_reads + 1);
-    BatchView b{packed.data(), word_off.data(), len.data(), seeds, (uint32_t)n_reads};
+    BatchView b{packed.data(), word_off.data(), len.data(), seeds, (uint32_t)n_reads, 0, (uint32_t)n_reads};
     SearchOut o{e->status.data(), e->st_off.data(), e->st_words.data(), e->st_count.data(), e->pool.data(),
                 (uint32_t)e->pool.size(), &small[0], ovf.data(), &small[1], mapped.data(), &small[3], &small[4]};
     CoverageView c{};
@@ -237,6 +237,29 @@ uint64_t emu_grouped(void* ev, uint32_t* words) {
       for (size_t i = 1; i < kv.first.size(); ++i) words[t + 2 + i] = kv.first[i];
     }
     t += 2 + kv.first.size();
+  }
+  return t;
+}
+// raw u32 accumulators [allele_sum | grouped_single | per_base] (what gq_coverage_device_ptrs exposes)
+void emu_counters_raw(void* ev, uint32_t* out) {
+  auto* e = (Emu*)ev;
+  uint64_t na = e->h.allele_off.back();
+  std::memcpy(out, e->counters.data(), (2 * na + e->h.n_per_base) * 4);
+}
+// multi-allele groups only, raw counts: [slot, count, n, alleles...] (gq_coverage_groups_export)
+uint64_t emu_groups_raw(void* ev, uint32_t* words) {
+  auto* e = (Emu*)ev;
+  uint64_t t = 0;
+  for (size_t i = 0; i < e->gtab.size(); ++i) {
+    if (!e->gtab[i] || !e->gcount[i]) continue;
+    const uint32_t* rec = e->gpool.data() + (e->gtab[i] - 1);
+    if (words) {
+      words[t] = rec[0];
+      words[t + 1] = e->gcount[i];
+      words[t + 2] = rec[1];
+      for (uint32_t j = 0; j < rec[1]; ++j) words[t + 3 + j] = rec[2 + j];
+    }
+    t += 3 + rec[1];
   }
   return t;
 }

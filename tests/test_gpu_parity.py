@@ -124,3 +124,35 @@ def test_medium_snp_properties(built_lib):
     o.map(bases, offs, seeds, threads=8, want_states=False)
     ref_r = o.result(want_states=False)
     assert_parity(got, ref_r, "medium", check_states=False)
+
+
+def test_multi_gpu_plumbing_single_device(built_lib):
+    """The pieces bench.py uses for N>1: device pointers of the dense accumulators (aliased by a torch
+    tensor for the NCCL all-reduce) and export/import of sparse multi-allele groups."""
+    import torch
+    from gramtools_b200.distributed import finalize_counters, shard_bounds
+    prg = synth.make_nested_prg(3, 250, 31)
+    bases, offs = _reads_for(prg, 2000, 30, 31)
+    seeds = master_seeds(42, 2000)
+    parts = []
+    for r in range(2):  # two "ranks" on one device
+        lo, hi = shard_bounds(2000, r, 2)
+        idx = QuasimapIndex(prg, 4)
+        idx.map_batch(bases[int(offs[lo]):int(offs[hi])], offs[lo:hi + 1] - offs[lo], seeds[lo:hi])
+        ptr, n_cnt, _ = idx.device_counters()
+
+        class _Shim:
+            __cuda_array_interface__ = {"shape": (n_cnt,), "typestr": "<i4", "data": (ptr, False), "version": 2}
+        t = torch.as_tensor(_Shim(), device="cuda:0").clone()
+        parts.append((t, idx.groups_export(), idx))
+    total = (parts[0][0] + parts[1][0]).cpu().numpy().astype(np.uint32)
+    merged = QuasimapIndex(prg, 4)
+    merged.groups_import(parts[0][1], replace=True)
+    merged.groups_import(parts[1][1], replace=False)
+    groups = merged.groups_export()
+    o = Oracle(prg, 4)
+    o.map(bases, offs, seeds)
+    ref = o.result()
+    a, p, g = finalize_counters(total, o.n_alleles, o.n_per_base, groups, parts[0][2].allele_offsets())
+    assert np.array_equal(a, ref.allele_sum) and np.array_equal(p, ref.per_base)
+    assert np.array_equal(g, ref.grouped)
