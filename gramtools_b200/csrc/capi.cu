@@ -76,7 +76,8 @@ struct gq_index {
   uint32_t chunk_reads = 1u << 18;  // slice size of the H2D / compute pipeline in gq_map_batch
   // options
   uint32_t arena_words = 512;
-  uint32_t n_threads = 148 * 1024;
+  uint32_t n_threads = 148 * 1280;      // search kernel lanes (5 CTAs of 256 per SM)
+  uint32_t cov_threads = 148 * 1024;    // coverage kernel threads
   uint32_t big_arena_words = 1u << 16;
   uint32_t big_threads = 2048;
   uint32_t pool_words_per_read = 48;
@@ -247,7 +248,7 @@ static void do_map(gq_index* ix, const uint8_t* h_bases = nullptr, const uint64_
   for (auto& c : chunks) max_chunk = std::max(max_chunk, c.r1 - c.r0);
   // persistent lanes: never more than one lane per 4 strands, so the refill/batching steady state exists
   uint32_t threads = std::min<uint32_t>(ix->n_threads, std::max<uint32_t>(256, ((2 * max_chunk / 4 + 255) / 256) * 256));
-  uint32_t threads2 = std::min<uint32_t>(ix->n_threads, ((2 * max_chunk + 255) / 256) * 256);
+  uint32_t threads2 = std::min<uint32_t>(ix->cov_threads, ((2 * max_chunk + 255) / 256) * 256);
   ix->arena.reserve((size_t)std::max(threads, threads2) * ix->arena_words);
   // small: [0] pool_used [1] n_overflow [2] n_cov_overflow; per chunk c: [8+2c] n_mapped [9+2c] work counter
   CUDA_OK(cudaMemsetAsync(ix->small.p, 0, (8 + 2 * 64) * 4, st));

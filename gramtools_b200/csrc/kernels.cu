@@ -91,8 +91,11 @@ constexpr int kMaxSuperSmem = 2048;  // superblocks (x16 B = 32 KB) staged in sh
 // Batching the rare paths keeps the hot step near full lane occupancy (v1 ran 3.5 lanes/instruction).
 constexpr int kHotUnroll = 2;
 
+#ifndef GQ_SEARCH_MIN_BLOCKS
+#define GQ_SEARCH_MIN_BLOCKS 5  // 48 registers, 1280 resident lanes per SM
+#endif
 template <bool SUPER_SMEM>
-__global__ void __launch_bounds__(kSearchThreads)
+__global__ void __launch_bounds__(kSearchThreads, GQ_SEARCH_MIN_BLOCKS)
     search_kernel(IndexView v, BatchView b, SearchOut o, uint32_t* arena, uint32_t arena_words,
                   const uint32_t* list, uint32_t n_list, uint32_t n_super_smem, uint32_t rf_thresh,
                   uint32_t ev_thresh, uint32_t wait_max, uint32_t leave) {

@@ -17,7 +17,8 @@ class GqError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libgq.so")
+    # GQ_LIB: developer override to A/B-test another build of the same library (tools/)
+    return os.environ.get("GQ_LIB") or os.path.join(_HERE, "libgq.so")
 
 
 _lib = None
