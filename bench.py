@@ -285,8 +285,12 @@ def main():
         if alg_bytes_per_read is not None:
             per_launch_s = (search_ms / args.steps) / 1e3
             achieved = alg_bytes_per_read * N_READS / per_launch_s / 1e9
+            # dram__bytes_read.sum + dram__bytes_write.sum of one search_kernel launch on this workload, from
+            # the committed `ncu --set full` capture (profiles/r01_v5_kernels_summary.txt); it is far below
+            # the algorithmic bytes because the 2.4 MB of rank blocks are L2-resident at this index size
+            traffic = 683380992 + 272083968 if N_READS == 1_000_000 else None
             roof = {"bound": "hbm", "kernel": "search_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_read": alg_bytes_per_read,
                     "kernel_ms_per_launch": search_ms / args.steps, "coverage_kernel_ms": cov_ms / args.steps}
         line = {
