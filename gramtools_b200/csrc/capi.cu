@@ -732,6 +732,82 @@ int gq_coverage_groups_import(gq_index* ix, const uint32_t* words, uint64_t n_wo
   GQ_CATCH
 }
 
+int gq_read_depth_stats(gq_index* ix, double out[2], uint64_t counts[2]) {
+  GQ_TRY
+  if (!ix || !out || !counts) throw std::runtime_error("null argument");
+  const gq::HostIndex& h = ix->h;
+  std::map<std::vector<uint32_t>, uint64_t> g;
+  collect_groups(ix, g, false);
+  std::vector<uint32_t> pb32(ix->n_per_base);
+  if (ix->n_per_base)
+    CUDA_OK(cudaMemcpy(pb32.data(), ix->counters.p + 2 * ix->n_alleles, ix->n_per_base * 4, cudaMemcpyDeviceToHost));
+  // get_max_cov_haplogroup (read_stats.cpp:72-93): per site, allele with the largest summed group count
+  // (uint16 counters in the reference: wrap each group count first); ties -> smallest allele id
+  std::vector<std::map<uint32_t, uint32_t>> per_site(h.n_slots);
+  for (auto& e : g) {
+    uint16_t cnt = (uint16_t)(e.second & 0xFFFFu);
+    for (size_t i = 1; i < e.first.size(); ++i) {
+      auto& c = per_site[e.first[0]][e.first[i]];
+      c = (uint16_t)(c + cnt);
+    }
+  }
+  auto max_hap = [&](uint32_t slot) {
+    std::pair<uint32_t, uint32_t> best{0, 0};
+    bool first = true;
+    for (auto& kv : per_site[slot])
+      if (first || kv.second > best.second) best = kv, first = false;
+    return best;
+  };
+  std::vector<double> covs;
+  uint64_t nocov = 0;
+  double total = 0;
+  for (uint32_t s = 0; s < h.n_slots; ++s) {
+    if (h.n_alleles[s] == 0 || h.par[2 * s] != 0) continue;  // nested sites are skipped (:131-132)
+    // extract_max_coverage_allele (:95-117): walk from the bubble start to its end
+    uint32_t cur = h.site_start_node[s];
+    // the bubble end of site s is the node every allele path converges to: follow allele 0 greedily
+    auto top = max_hap(s);
+    uint64_t allele_cov = top.second;
+    double sum = 0;
+    uint64_t nb = 0;
+    uint32_t depth = 0;  // open bubbles below the level-0 one
+    while (true) {
+      const gq::Node& nd = h.nodes[cur];
+      bool is_start = nd.n_edges > 1 && nd.len == 0;
+      if (is_start) {
+        uint32_t slot = (nd.site - 5) / 2;
+        auto m = max_hap(slot);
+        if (m.first >= nd.n_edges) throw std::runtime_error("inconsistent grouped allele counts");
+        ++depth;
+        cur = h.edges[nd.edge_off + m.first];
+        continue;
+      }
+      if (nd.len == 0 && nd.allele == -1 && nd.site != 0) {  // a bubble end
+        if (--depth == 0) break;
+      }
+      if (nd.len > 0 && nd.cov_off != gq::kNoAllele) {
+        for (uint32_t i = 0; i < nd.len; ++i) sum += std::min<uint32_t>(pb32[nd.cov_off + i], 65535u);
+        nb += nd.len;
+      }
+      if (nd.n_edges == 0) break;
+      cur = h.edges[nd.edge_off];
+    }
+    double site_cov = nb ? sum / (double)nb : (double)allele_cov;
+    total += site_cov;
+    covs.push_back(site_cov);
+    if (allele_cov == 0) ++nocov;
+  }
+  double mean = covs.empty() ? 0.0 / 0.0 : total / covs.size();
+  double var = 0;
+  for (double c : covs) var += (c - mean) * (c - mean);
+  var = covs.empty() ? 0.0 / 0.0 : var / covs.size();
+  out[0] = mean;
+  out[1] = var;
+  counts[0] = nocov;
+  counts[1] = covs.size();
+  GQ_CATCH
+}
+
 int gq_coverage_reset(gq_index* ix) {
   GQ_TRY
   if (!ix) throw std::runtime_error("null argument");

@@ -1,0 +1,395 @@
+// gram_main.cpp — `gram genotype …`: the process seam of the reference, served by libgq.so.
+//
+// The Python front-end runs (gramtools/commands/genotype/genotype.py:71-93)
+//   gram genotype --gram_dir D --reads F… --sample_id S --ploidy {haploid|diploid} --kmer_size K
+//                 --genotype_dir G --max_threads T [--seed N] [--debug]
+// parsed in the reference by libgramtools/src/main.cpp:51-100 + src/genotype/parameters.cpp:45-116.
+// This executable keeps that argv contract and the geno_dir layout for the QUASIMAP part of
+// commands::genotype::run (genotype.cpp:24-66): it reads gram_dir/prg (raw LE uint32), maps every reads
+// file on the GPU and writes
+//   G/coverage/allele_sum_coverage                 (allele_sum.cpp:45-57)
+//   G/coverage/allele_base_coverage.json           (allele_base.cpp:91-107)
+//   G/coverage/grouped_allele_counts_coverage.json (grouped_allele_counts.cpp:93-111)
+//   G/read_stats.json                              (read_stats.cpp:162-209)
+// and prints the five counters as genotype.cpp:55-66 does. The genotyping step that follows in the
+// reference (LevelGenotyper, genotype.cpp:68-118) is out of scope of this back-end.
+// Only gram_dir/prg is consumed: the SDSL / Boost files next to it are third-party formats and the
+// index is rebuilt from the PRG.
+#include <sys/stat.h>
+#include <zlib.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <random>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../include/gq.h"
+
+namespace {
+
+struct Params {
+  std::string gram_dir, sample_id, ploidy, genotype_dir;
+  std::vector<std::string> reads;
+  uint32_t kmer_size = 0, max_threads = 1;
+  bool has_seed = false, debug = false;
+  uint32_t seed = 0;
+};
+
+[[noreturn]] void usage_fail(const std::string& msg) {
+  std::cout << msg << std::endl;
+  std::cout << "genotype options:\n  --gram_dir arg\n  --reads arg [arg…]\n  --sample_id arg\n"
+               "  --ploidy arg {haploid, diploid}\n  --kmer_size arg\n  --genotype_dir arg\n"
+               "  --max_threads arg (=1)\n  --seed arg\n";
+  std::exit(1);
+}
+
+Params parse_genotype(int argc, const char* const* argv, int first) {
+  Params p;
+  bool got_k = false;
+  for (int i = first; i < argc; ++i) {
+    std::string a = argv[i];
+    auto value = [&](const std::string& name) -> std::string {
+      if (i + 1 >= argc) usage_fail("the required argument for option '--" + name + "' is missing");
+      return argv[++i];
+    };
+    if (a == "--gram_dir") p.gram_dir = value("gram_dir");
+    else if (a == "--reads") {
+      while (i + 1 < argc && std::strncmp(argv[i + 1], "--", 2) != 0) p.reads.push_back(argv[++i]);
+    } else if (a == "--sample_id") p.sample_id = value("sample_id");
+    else if (a == "--ploidy") p.ploidy = value("ploidy");
+    else if (a == "--kmer_size") {
+      p.kmer_size = (uint32_t)std::stoul(value("kmer_size"));
+      got_k = true;
+    } else if (a == "--genotype_dir") p.genotype_dir = value("genotype_dir");
+    else if (a == "--max_threads") p.max_threads = (uint32_t)std::stoul(value("max_threads"));
+    else if (a == "--seed") {
+      p.seed = (uint32_t)std::stoul(value("seed"));
+      p.has_seed = true;
+    } else if (a == "--debug") p.debug = true;
+    else usage_fail("unrecognised option '" + a + "'");
+  }
+  if (p.gram_dir.empty()) usage_fail("the option '--gram_dir' is required but missing");
+  if (p.reads.empty()) usage_fail("the option '--reads' is required but missing");
+  if (p.sample_id.empty()) usage_fail("the option '--sample_id' is required but missing");
+  if (p.ploidy != "haploid" && p.ploidy != "diploid") usage_fail("the option '--ploidy' must be haploid or diploid");
+  if (!got_k) usage_fail("the option '--kmer_size' is required but missing");
+  if (p.genotype_dir.empty()) usage_fail("the option '--genotype_dir' is required but missing");
+  return p;
+}
+
+void make_dir(const std::string& d) {
+  if (mkdir(d.c_str(), 0775) != 0 && errno != EEXIST) {
+    std::cout << "Cannot create directory " << d << std::endl;
+    std::exit(1);
+  }
+}
+
+// PRG_String(file) (linearised_prg.cpp:8-45): little-endian uint32 stream
+std::vector<uint32_t> read_prg(const std::string& path) {
+  std::ifstream in(path, std::ios::binary);
+  if (!in) {
+    std::cout << "PRG String file not found: " << path << std::endl;
+    std::exit(1);
+  }
+  std::vector<uint32_t> prg;
+  unsigned char b[4];
+  while (in.read((char*)b, 4)) prg.push_back((uint32_t)b[0] | (uint32_t)b[1] << 8 | (uint32_t)b[2] << 16 | (uint32_t)b[3] << 24);
+  return prg;
+}
+
+// Minimal sequence reader with the behaviour of SeqRead / seq_file.h that matters here
+// (include/sequence_read/seqread.hpp:94-180, seq_file.h:247-335): format sniffed from the first byte
+// ('@' FASTQ, '>' FASTA, else one read per line), multi-line records joined, gz transparently
+// inflated, a malformed record ends the file.
+class ReadFile {
+ public:
+  explicit ReadFile(const std::string& path) {
+    gz_ = gzopen(path.c_str(), "rb");
+    if (!gz_) {
+      std::cout << "Cannot open reads file " << path << std::endl;
+      std::exit(1);
+    }
+    gzbuffer(gz_, 1 << 20);
+    have_line_ = next_line(line_);
+    if (have_line_) fmt_ = line_.empty() ? 'p' : (line_[0] == '@' ? 'q' : (line_[0] == '>' ? 'a' : 'p'));
+  }
+  ~ReadFile() {
+    if (gz_) gzclose(gz_);
+  }
+  bool next(std::string& seq, std::string& qual) {
+    seq.clear();
+    qual.clear();
+    if (!have_line_) return false;
+    if (fmt_ == 'p') {
+      seq = line_;
+      have_line_ = next_line(line_);
+      return true;
+    }
+    if (fmt_ == 'a') {
+      if (line_.empty() || line_[0] != '>') return false;
+      while ((have_line_ = next_line(line_)) && (line_.empty() || line_[0] != '>')) seq += line_;
+      return true;
+    }
+    if (line_.empty() || line_[0] != '@') return false;
+    while ((have_line_ = next_line(line_)) && (line_.empty() || line_[0] != '+')) seq += line_;
+    if (!have_line_) return false;  // no '+' line: malformed
+    while (qual.size() < seq.size() && (have_line_ = next_line(line_))) qual += line_;
+    if (qual.size() != seq.size()) return false;
+    have_line_ = next_line(line_);
+    return true;
+  }
+
+ private:
+  bool next_line(std::string& out) {
+    out.clear();
+    char buf[1 << 16];
+    while (gzgets(gz_, buf, sizeof buf)) {
+      size_t n = std::strlen(buf);
+      bool eol = n && buf[n - 1] == '\n';
+      if (eol) --n;
+      if (n && buf[n - 1] == '\r') --n;
+      out.append(buf, n);
+      if (eol) return true;
+    }
+    return !out.empty();
+  }
+  gzFile gz_ = nullptr;
+  std::string line_;
+  bool have_line_ = false;
+  char fmt_ = 'p';
+};
+
+inline uint8_t encode_base(char c) {  // encode_char, utils.cpp:13-47
+  switch (c) {
+    case 'A': case 'a': return 1;
+    case 'C': case 'c': return 2;
+    case 'G': case 'g': return 3;
+    case 'T': case 't': return 4;
+    default: return 0;
+  }
+}
+
+void check(int rc) {
+  if (rc != 0) {
+    std::cout << "libgq error: " << gq_last_error() << std::endl;
+    std::exit(1);
+  }
+}
+
+std::string join_path(const std::string& a, const std::string& b) { return a + (a.empty() || a.back() == '/' ? "" : "/") + b; }
+
+}  // namespace
+
+int main(int argc, const char* const* argv) {
+  // main.cpp:51-100: `gram` alone prints the global help and exits 0 (gramtools_main.py:80-90 relies on it)
+  std::string cmd;
+  int first = 1;
+  bool debug_flag = false;
+  for (int i = 1; i < argc; ++i) {
+    std::string a = argv[i];
+    if (a == "--help") break;
+    if (a == "--debug") {
+      debug_flag = true;
+      continue;
+    }
+    cmd = a;
+    first = i + 1;
+    break;
+  }
+  if (cmd.empty()) {
+    std::cout << "Gramtools! Global options:\n  --command arg   command to execute: {build, genotype, simulate}\n"
+                 "  --help          Produce this help message\n  --debug         Turn on debug output\n"
+                 "(B200 quasimap back-end: only `genotype` is served)\n";
+    return 0;
+  }
+  if (cmd != "genotype") {
+    std::cout << (cmd == "build" || cmd == "simulate" ? "Command not served by the B200 quasimap back-end: "
+                                                      : "Unrecognised command: ")
+              << cmd << std::endl;
+    return 1;
+  }
+  Params p = parse_genotype(argc, argv, first);
+  p.debug = p.debug || debug_flag;
+
+  std::cout << "Executing genotype command" << std::endl;
+  const std::string cov_dir = join_path(p.genotype_dir, "coverage");
+  make_dir(p.genotype_dir);
+  make_dir(cov_dir);
+  make_dir(join_path(p.genotype_dir, "genotype"));
+
+  // ReadStats::compute_base_error_rate on the first reads file (genotype.cpp:32-34, read_stats.cpp:21-70)
+  uint64_t max_read_length = 0, num_bases = 0, no_qual_reads = 0, informative = 0;
+  double running_qual = 0;
+  {
+    ReadFile rf(p.reads[0]);
+    std::string seq, qual;
+    while (informative < 10000 && rf.next(seq, qual)) {
+      if (seq.size() > max_read_length) max_read_length = seq.size();
+      if (qual.empty()) {
+        ++no_qual_reads;
+        continue;
+      }
+      for (char q : qual) running_qual += (float)(q - 33);
+      num_bases += qual.size();
+      ++informative;
+    }
+  }
+  double mean_pb_error = num_bases ? std::pow(10.0, -(running_qual / (double)num_bases) / 10.0) : 0.0;
+
+  std::cout << "Loading PRG data" << std::endl;
+  std::vector<uint32_t> prg = read_prg(join_path(p.gram_dir, "prg"));
+  gq_index* idx = nullptr;
+  check(gq_index_build(prg.data(), prg.size(), p.kmer_size, 0, &idx));
+  gq_layout lay;
+  check(gq_index_describe(idx, &lay));
+
+  std::cout << "Running quasimap" << std::endl;
+  uint32_t master_seed = p.has_seed ? p.seed : std::random_device{}();
+  std::cout << "Master random seed for read selection: " << master_seed << std::endl;
+  std::cout << "Maximum thread count: " << p.max_threads << " (ignored: reads are mapped on the GPU)" << std::endl;
+  std::cout << "Processing reads:" << std::endl;
+  std::mt19937 master;
+  master.seed(master_seed);
+  const uint64_t kRefBatch = 5000;       // quasimap.cpp:126-128: seeds are drawn 5000 at a time
+  const uint64_t kGpuBatch = 1u << 20;   // reads per gq_map_batch call
+  uint64_t total_reads = 0;
+  for (const auto& path : p.reads) {
+    ReadFile rf(path);
+    std::vector<uint8_t> bases;
+    std::vector<uint64_t> offs{0};
+    std::vector<uint32_t> seeds;
+    std::string seq, qual;
+    uint64_t in_ref_batch = 0;
+    auto flush = [&]() {
+      if (seeds.empty()) return;
+      check(gq_map_batch(idx, bases.data(), offs.data(), seeds.size(), seeds.data()));
+      total_reads += seeds.size();
+      std::cout << 2 * total_reads << std::endl;
+      bases.clear();
+      offs.assign(1, 0);
+      seeds.clear();
+    };
+    while (rf.next(seq, qual)) {
+      // read j of a 5000-read buffer gets the j-th of the 5000 draws made for that buffer
+      // (quasimap.cpp:132-139): unused draws of the last, partly filled buffer are discarded
+      if (in_ref_batch == kRefBatch) in_ref_batch = 0;
+      seeds.push_back((uint32_t)master());
+      ++in_ref_batch;
+      size_t start = bases.size();
+      bool ok = true;
+      for (char ch : seq) {
+        uint8_t e = encode_base(ch);
+        if (!e) {
+          ok = false;
+          break;
+        }
+        bases.push_back(e);
+      }
+      if (!ok) bases.resize(start);  // non-ACGT: the encoder returns an empty read (utils.cpp:72-81)
+      offs.push_back(bases.size());
+      if (seeds.size() == kGpuBatch) flush();
+    }
+    flush();
+    if (in_ref_batch) master.discard(kRefBatch - in_ref_batch);
+  }
+
+  // ---- outputs -----------------------------------------------------------------------------
+  std::vector<uint16_t> allele_sum(lay.n_alleles ? lay.n_alleles : 1), per_base(lay.n_per_base ? lay.n_per_base : 1);
+  uint64_t st[5];
+  check(gq_coverage_fetch(idx, allele_sum.data(), per_base.data(), st));
+  std::vector<uint64_t> allele_off(lay.n_site_slots + 1);
+  check(gq_index_allele_offsets(idx, allele_off.data()));
+  {  // allele_sum.cpp:45-57
+    std::ofstream f(join_path(cov_dir, "allele_sum_coverage"));
+    for (uint32_t s = 0; s < lay.n_site_slots; ++s) {
+      for (uint64_t a = allele_off[s]; a < allele_off[s + 1]; ++a) f << allele_sum[a] << (a + 1 < allele_off[s + 1] ? " " : "");
+      f << std::endl;
+    }
+  }
+  {  // allele_base.cpp:91-107; empty by convention for nested PRGs (:10-14)
+    std::ofstream f(join_path(cov_dir, "allele_base_coverage.json"));
+    f << "{\"allele_base_counts\":[";
+    if (!lay.is_nested) {
+      std::vector<uint64_t> ol(2 * (lay.n_alleles ? lay.n_alleles : 1));
+      check(gq_index_per_base_layout(idx, ol.data()));
+      for (uint32_t s = 0; s < lay.n_site_slots; ++s) {
+        f << "[";
+        for (uint64_t a = allele_off[s]; a < allele_off[s + 1]; ++a) {
+          f << "[";
+          for (uint64_t i = 0; i < ol[2 * a + 1]; ++i) f << (int)per_base[ol[2 * a] + i] << (i + 1 < ol[2 * a + 1] ? "," : "");
+          f << "]" << (a + 1 < allele_off[s + 1] ? "," : "");
+        }
+        f << "]" << (s + 1 < lay.n_site_slots ? "," : "");
+      }
+    }
+    f << "]}" << std::endl;
+  }
+  {  // grouped_allele_counts.cpp:51-111 (group ids numbered by first appearance, sites in order)
+    uint64_t nw = 0;
+    check(gq_coverage_grouped(idx, nullptr, &nw));
+    std::vector<uint32_t> w(nw ? nw : 1);
+    check(gq_coverage_grouped(idx, w.data(), &nw));
+    std::map<std::vector<uint32_t>, uint64_t> group_id;
+    std::vector<std::map<std::string, uint32_t>> site_counts(lay.n_site_slots);
+    for (uint64_t t = 0; t < nw;) {
+      uint32_t n = w[t + 2];
+      std::vector<uint32_t> ids(w.begin() + t + 3, w.begin() + t + 3 + n);
+      auto it = group_id.find(ids);
+      if (it == group_id.end()) it = group_id.insert({ids, group_id.size()}).first;
+      site_counts[w[t]][std::to_string(it->second)] = w[t + 1];
+      t += 3 + n;
+    }
+    std::map<std::string, std::vector<uint32_t>> groups_by_name;
+    for (auto& e : group_id) groups_by_name[std::to_string(e.second)] = e.first;
+    std::ofstream f(join_path(cov_dir, "grouped_allele_counts_coverage.json"));
+    f << "{\"grouped_allele_counts\":{\"allele_groups\":{";
+    bool first_g = true;
+    for (auto& e : groups_by_name) {
+      f << (first_g ? "" : ",") << "\"" << e.first << "\":[";
+      for (size_t i = 0; i < e.second.size(); ++i) f << e.second[i] << (i + 1 < e.second.size() ? "," : "");
+      f << "]";
+      first_g = false;
+    }
+    f << "},\"site_counts\":[";
+    for (uint32_t s = 0; s < lay.n_site_slots; ++s) {
+      f << "{";
+      bool first_c = true;
+      for (auto& e : site_counts[s]) {
+        f << (first_c ? "" : ",") << "\"" << e.first << "\":" << e.second;
+        first_c = false;
+      }
+      f << "}" << (s + 1 < lay.n_site_slots ? "," : "");
+    }
+    f << "]}}" << std::endl;
+  }
+  {  // read_stats.cpp:162-209
+    double depth[2];
+    uint64_t cnt[2];
+    check(gq_read_depth_stats(idx, depth, cnt));
+    const std::string path = join_path(p.genotype_dir, "read_stats.json");
+    std::cout << "Writing read stats to " << path << std::endl;
+    std::ofstream f(path);
+    f << "\n{\n\"Read_depth\":\n    {\"Mean\": " << depth[0] << ",\n    \"Variance\": " << depth[1]
+      << ",\n    \"num_sites_noCov\": " << cnt[0] << ",\n    \"num_sites_total\": " << cnt[1] << "\n    },\n"
+      << "\"Max_read_length\": " << max_read_length << ",\n\"Quality\":\n    {\"Error_rate_mean\": " << mean_pb_error
+      << ",\n    \"Num_bases\": " << num_bases << ",\n    \"No_qual_reads\": " << no_qual_reads << "\n    }}\n";
+  }
+  std::cout << std::endl << "The following counts include generated reverse complement reads." << std::endl;
+  std::cout << "Count all reads: " << st[0] << std::endl;
+  std::cout << "Count skipped reads with no sequence: " << st[1] << std::endl;
+  std::cout << "Count reads with >0 kmers not in kmer index: " << st[2] << std::endl;
+  std::cout << "Count reads with no exact mapping: " << st[3] << std::endl;
+  std::cout << "Count exact mapped reads: " << st[4] << std::endl;
+  std::cout << "====================" << std::endl
+            << "Genotyping (LevelGenotyper) is not part of the B200 quasimap back-end; coverage files are complete."
+            << std::endl;
+  gq_index_destroy(idx);
+  return 0;
+}

@@ -51,6 +51,7 @@ def load_library():
         "gq_coverage_fetch": [vp, u16p, u16p, u64p],
         "gq_coverage_grouped": [vp, u32p, u64p],
         "gq_coverage_reset": [vp],
+        "gq_read_depth_stats": [vp, C.POINTER(C.c_double), u64p],
         "gq_coverage_device_ptrs": [vp, C.POINTER(vp), u64p, C.POINTER(vp)],
         "gq_coverage_groups_export": [vp, u32p, u64p],
         "gq_coverage_groups_import": [vp, u32p, C.c_uint64, C.c_int],
@@ -220,6 +221,13 @@ class QuasimapIndex:
         o = np.zeros(max(2 * self.layout.n_alleles, 1), dtype=np.uint64)
         self._check(self._lib.gq_index_per_base_layout(self._h, _ptr(o, C.c_uint64)))
         return o[:2 * self.layout.n_alleles].reshape(-1, 2)
+
+    def read_depth_stats(self):
+        """ReadStats::compute_coverage_depth -> dict(mean, variance, num_sites_noCov, num_sites_total)"""
+        d = (C.c_double * 2)()
+        c = np.zeros(2, dtype=np.uint64)
+        self._check(self._lib.gq_read_depth_stats(self._h, d, _ptr(c, C.c_uint64)))
+        return dict(mean=d[0], variance=d[1], num_sites_noCov=int(c[0]), num_sites_total=int(c[1]))
 
     def reset_coverage(self):
         self._check(self._lib.gq_coverage_reset(self._h))

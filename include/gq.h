@@ -82,6 +82,11 @@ int gq_coverage_fetch(gq_index* idx, uint16_t* allele_sum, uint16_t* per_base, u
  * sorted by (site_slot, allele ids). Call with words == NULL to get the size. */
 int gq_coverage_grouped(gq_index* idx, uint32_t* words, uint64_t* n_words);
 int gq_coverage_reset(gq_index* idx);
+/* ReadStats::compute_coverage_depth (read_stats.cpp:119-160) on the coverage accumulated so far:
+ * per level-0 site the mean per-base coverage of the allele path with the highest grouped count (or
+ * that count for a direct deletion); out = {mean, variance} and counts = {num_sites_noCov,
+ * num_sites_total}. Host arithmetic in double, like the reference (not part of the GPU hot path). */
+int gq_read_depth_stats(gq_index* idx, double out[2], uint64_t counts[2]);
 
 /* Multi-GPU: raw device pointers of the additive uint32 accumulators so the host layer can run one
  * NCCL all-reduce(sum) over them (reads are sharded across GPUs, index replicated).
