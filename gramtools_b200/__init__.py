@@ -9,9 +9,9 @@ There is no CPU fallback: importing works anywhere, but every compute call needs
 library and a CUDA device and raises otherwise.
 """
 from .engine import (GqError, QuasimapIndex, QuasimapReadsStats, encode_reads, lib_path, load_library)  # noqa: F401
-from .synth import (make_snp_prg, make_nested_prg, sample_reads, master_seeds)  # noqa: F401
+from .synth import (make_snp_prg, make_indel_prg, make_nested_prg, sample_reads, master_seeds)  # noqa: F401
 
 __all__ = [
     "GqError", "QuasimapIndex", "QuasimapReadsStats", "encode_reads", "lib_path", "load_library",
-    "make_snp_prg", "make_nested_prg", "sample_reads", "master_seeds",
+    "make_snp_prg", "make_indel_prg", "make_nested_prg", "sample_reads", "master_seeds",
 ]

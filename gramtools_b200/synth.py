@@ -56,6 +56,35 @@ def make_snp_prg(ref_len, n_sites, seed, min_spacing=2):
     return out, ref, pos, alt
 
 
+def make_indel_prg(ref_len, n_sites, seed, snp_frac=0.8):
+    """SNP + indel sites as config 4/5 describe them: 80 % SNPs, 10 % deletions (REF of
+    2-10 bases, ALT = its first base), 10 % insertions (ALT = REF base + 1-9 random bases), emitted as
+    `odd REF even ALT even` (vcf_to_prg_string.py:81-101). Plain loop: meant for test-sized PRGs."""
+    rng = np.random.default_rng(seed)
+    ref = rng.integers(1, 5, size=ref_len)
+    starts = np.sort(rng.choice(np.arange(1, ref_len - 12, 14), size=min(n_sites, (ref_len - 13) // 14), replace=False))
+    out, prev, sid = [], 0, 5
+    for p in starts:
+        p = int(p)
+        out += [int(x) for x in ref[prev:p]]
+        r = rng.random()
+        if r < snp_frac:
+            refa = [int(ref[p])]
+            alta = [int((ref[p] - 1 + rng.integers(1, 4)) % 4 + 1)]
+        elif r < snp_frac + (1 - snp_frac) / 2:
+            n = int(rng.integers(2, 11))
+            refa = [int(x) for x in ref[p:p + n]]
+            alta = [int(ref[p])]
+        else:
+            refa = [int(ref[p])]
+            alta = [int(ref[p])] + [int(x) for x in rng.integers(1, 5, size=int(rng.integers(1, 10)))]
+        out += [sid] + refa + [sid + 1] + alta + [sid + 1]
+        sid += 2
+        prev = p + len(refa)
+    out += [int(x) for x in ref[prev:]]
+    return np.asarray(out, dtype=np.uint32)
+
+
 def snp_haplotypes(ref, pos, alt, n_hap, seed):
     rng = np.random.default_rng(seed)
     haps = []

@@ -50,6 +50,21 @@ def test_nested_prg(built_lib, seed):
     assert ref.grouped.size > 0
 
 
+@pytest.mark.parametrize("seed", range(2))
+def test_indel_prg(built_lib, seed):
+    prg = synth.make_indel_prg(6000, 300, seed)
+    bases, offs = _reads_for(prg, 4000, 70, seed)
+    _check(prg, 6, bases, offs, what=f"indel{seed}", threads=4)
+
+
+def test_nested_prg_larger(built_lib):
+    """config 3 shape, scaled to what the oracle checks in seconds: nested loci, many multi-state reads."""
+    prg = synth.make_nested_prg(40, 400, 77)
+    bases, offs = _reads_for(prg, 30000, 60, 77, garbage=0.02, n_frac=0.0)
+    got, ref = _check(prg, 7, bases, offs, what="nested-large", threads=8)
+    assert ref.stats[4] > 10000
+
+
 def test_config1_toy(built_lib):
     """BASELINE config 1: 1 kb ref + 50 biallelic SNPs, 10k x 100 bp reads, k=5."""
     prg, ref, pos, alt = synth.make_snp_prg(1000, 50, 0x6772616D)

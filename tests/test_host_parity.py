@@ -45,6 +45,15 @@ def test_nested_prg_parity(seed):
     assert ro.stats[4] > 100 and ro.grouped.size > 0
 
 
+@pytest.mark.parametrize("seed", range(3))
+def test_indel_prg_parity(seed):
+    """config 4/5 site mix: SNPs + deletions + insertions (ambiguous placements -> multi-allele groups)."""
+    prg = synth.make_indel_prg(1500, 80, seed)
+    bases, offs = _reads_for(prg, 500, 45, seed)
+    ro, _ = _check(prg, 5, bases, offs, what=f"indel{seed}")
+    assert ro.stats[4] > 100
+
+
 def test_tiny_arena_forces_overflow_reruns():
     """Arena overflow must re-run the strand with a larger arena, never truncate."""
     prg = synth.make_nested_prg(2, 200, 11)
