@@ -29,6 +29,14 @@ GQ_DEV inline uint32_t gq_atomic_add(uint32_t* p, uint32_t v) {
   return o;
 #endif
 }
+// fire-and-forget add (RED.ADD: no return value travels back from L2)
+GQ_DEV inline void gq_red_add(uint32_t* p, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#else
+  *p += v;
+#endif
+}
 GQ_DEV inline uint32_t gq_atomic_cas(uint32_t* p, uint32_t cmp, uint32_t v) {
 #if defined(__CUDA_ARCH__)
   return atomicCAS(p, cmp, v);
@@ -749,7 +757,7 @@ GQ_DEV void grouped_insert(const CoverageView& c, uint32_t slot, const uint32_t*
       }
       cur = gq_atomic_cas(c.gtab + h, 0u, mine);
       if (cur == 0) {
-        gq_atomic_add(c.gcount + h, 1u);
+        gq_red_add(c.gcount + h, 1u);
         return;
       }
     }
@@ -758,7 +766,7 @@ GQ_DEV void grouped_insert(const CoverageView& c, uint32_t slot, const uint32_t*
     bool same = rec[0] == slot && rec[1] == n;
     for (uint32_t i = 0; same && i < n; ++i) same = rec[2 + i] == loci[2 * i + 1];
     if (same) {
-      gq_atomic_add(c.gcount + h, 1u);
+      gq_red_add(c.gcount + h, 1u);
       return;
     }
   }
@@ -794,13 +802,13 @@ GQ_DEV bool record_strand(const IndexView& v, const BatchView& b, const SearchOu
       const uint32_t nid0 = GQ_LDG(v.pos2node + pos0);
       if (st.ng) {
         const uint32_t site = st.G[0], slot = (site - 5) >> 1, al = (uint32_t)v.nodes[nid0].allele;
-        gq_atomic_add(c.allele_sum + c.allele_off[slot] + al, 1u);
-        gq_atomic_add(c.grouped_single + c.allele_off[slot] + al, 1u);
+        gq_red_add(c.allele_sum + c.allele_off[slot] + al, 1u);
+        gq_red_add(c.grouped_single + c.allele_off[slot] + al, 1u);
       }
       for (uint32_t j = 0; j < st.nt; ++j) {
         const uint32_t slot = (st.T[2 * j] - 5) >> 1, al = st.T[2 * j + 1];
-        gq_atomic_add(c.allele_sum + c.allele_off[slot] + al, 1u);
-        gq_atomic_add(c.grouped_single + c.allele_off[slot] + al, 1u);
+        gq_red_add(c.allele_sum + c.allele_off[slot] + al, 1u);
+        gq_red_add(c.grouped_single + c.allele_off[slot] + al, 1u);
       }
       Trav t;
       t.v = &v;
@@ -816,7 +824,7 @@ GQ_DEV bool record_strand(const IndexView& v, const BatchView& b, const SearchOu
       while (t.next()) {
         const Node& nd = v.nodes[t.cur];
         if (nd.len == 0 || nd.cov_off == kNoAllele) continue;
-        for (uint32_t x = t.start_pos; x <= t.end_pos; ++x) gq_atomic_add(c.per_base + nd.cov_off + x, 1u);
+        for (uint32_t x = t.start_pos; x <= t.end_pos; ++x) gq_red_add(c.per_base + nd.cov_off + x, 1u);
       }
       if (t.bad) gq_atomic_or(c.error_flags, 2u);
       return true;
@@ -953,17 +961,17 @@ GQ_DEV bool record_strand(const IndexView& v, const BatchView& b, const SearchOu
     uint32_t site = ll.loci[2 * i], slot = (site - 5) >> 1;
     uint32_t e = i;
     while (e < ll.n_loci && ll.loci[2 * e] == site) {
-      gq_atomic_add(c.allele_sum + c.allele_off[slot] + ll.loci[2 * e + 1], 1u);  // allele_sum.cpp:31-43
+      gq_red_add(c.allele_sum + c.allele_off[slot] + ll.loci[2 * e + 1], 1u);  // allele_sum.cpp:31-43
       ++e;
     }
-    if (e - i == 1) gq_atomic_add(c.grouped_single + c.allele_off[slot] + ll.loci[2 * i + 1], 1u);
+    if (e - i == 1) gq_red_add(c.grouped_single + c.allele_off[slot] + ll.loci[2 * i + 1], 1u);
     else grouped_insert(c, slot, ll.loci + 2 * i, e - i);  // grouped_allele_counts.cpp:17-49
     i = e;
   }
   for (uint32_t i = 0; i < hull.n; ++i) {
     const Node& nd = v.nodes[hull.e[3 * i]];
     if (nd.cov_off == kNoAllele) continue;
-    for (uint32_t x = hull.e[3 * i + 1]; x <= hull.e[3 * i + 2]; ++x) gq_atomic_add(c.per_base + nd.cov_off + x, 1u);
+    for (uint32_t x = hull.e[3 * i + 1]; x <= hull.e[3 * i + 2]; ++x) gq_red_add(c.per_base + nd.cov_off + x, 1u);
   }
   return true;
 }

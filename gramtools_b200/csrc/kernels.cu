@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(kSearchThreads, GQ_SEARCH_MIN_BLOCKS)
     search_kernel(IndexView v, BatchView b, SearchOut o, uint32_t* arena, uint32_t arena_words,
                   const uint32_t* list, uint32_t n_list, uint32_t n_super_smem, uint32_t rf_thresh,
                   uint32_t ev_thresh, uint32_t wait_max, uint32_t leave) {
-  __shared__ alignas(128) uint32_t s_super[SUPER_SMEM ? kMaxSuperSmem * 4 : 4];
+  extern __shared__ __align__(128) uint32_t s_super[];  // n_super_smem x 16 B (dynamic: keeps 5 CTAs/SM)
   __shared__ alignas(8) uint64_t s_bar;
   if (SUPER_SMEM) tma_stage_super(s_super, v.super_cnt, n_super_smem * 16u, &s_bar);
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -113,19 +113,23 @@ __global__ void __launch_bounds__(kSearchThreads, GQ_SEARCH_MIN_BLOCKS)
   ln.strand = kNoAllele;
   const uint32_t full = 0xFFFFFFFFu;
   while (true) {
-    const uint32_t idle = __ballot_sync(full, ln.state == LS_IDLE);
-    const uint32_t run = __ballot_sync(full, ln.state == LS_RUN);
-    const uint32_t wide = __ballot_sync(full, ln.state == LS_RUNW);
-    const uint32_t scan = __ballot_sync(full, ln.state == LS_EV_SCAN || ln.state == LS_EV_WIDE);
-    const uint32_t popm = __ballot_sync(full, ln.state == LS_EV_POP);
-    const uint32_t top = ~(idle | run | wide | scan | popm);
-    if (idle == full && !work_left) break;
-    const uint32_t n_idle = work_left ? __popc(idle) : 0, n_wide = __popc(wide), n_scan = __popc(scan),
-                   n_pop = __popc(popm), n_top = __popc(top);
+    // one REDUX.ADD gives all class populations: 6-bit fields idle | wide | scan | pop | top
+    const uint32_t st = ln.state;
+    const uint32_t field = st == LS_IDLE ? 1u
+                           : st == LS_RUNW ? (1u << 6)
+                           : (st == LS_EV_SCAN || st == LS_EV_WIDE) ? (1u << 12)
+                           : st == LS_EV_POP ? (1u << 18)
+                           : st == LS_EV_TOP ? (1u << 24) : 0u;
+    const uint32_t votes = __reduce_add_sync(full, field);
+    const uint32_t c_idle = votes & 63u, n_wide = (votes >> 6) & 63u, n_scan = (votes >> 12) & 63u,
+                   n_pop = (votes >> 18) & 63u, n_top = (votes >> 24) & 63u;
+    if (c_idle == 32 && !work_left) break;
+    const uint32_t n_idle = work_left ? c_idle : 0;
+    const uint32_t n_run = 32u - (c_idle + n_wide + n_scan + n_pop + n_top);
     // service a class when enough lanes wait in it; when nothing can step, or too many lanes wait in
     // total, service the most populated class
     const uint32_t waiting = n_idle + n_wide + n_scan + n_pop + n_top;
-    const bool force = run == 0 || waiting >= wait_max;
+    const bool force = n_run == 0 || waiting >= wait_max;
     const uint32_t big = max(max(max(n_idle, n_wide), max(n_scan, n_pop)), n_top);
     if (n_wide && (n_wide >= ev_thresh || (force && n_wide == big))) {
       if (ln.state == LS_RUNW) lane_step_wide(ln, v, SUPER_SMEM ? (const uint32_t*)s_super : v.super_cnt);
@@ -144,19 +148,20 @@ __global__ void __launch_bounds__(kSearchThreads, GQ_SEARCH_MIN_BLOCKS)
       continue;
     }
     if (n_idle && (n_idle >= rf_thresh || (force && n_idle == big))) {
+      const uint32_t idle = __ballot_sync(full, ln.state == LS_IDLE);
       uint32_t base = 0;
-      if (lane == 0) base = atomicAdd(o.work_counter, (uint32_t)__popc(idle));
+      if (lane == 0) base = atomicAdd(o.work_counter, c_idle);
       base = __shfl_sync(full, base, 0);
       if (ln.state == LS_IDLE) {
         uint32_t i = base + __popc(idle & ((1u << lane) - 1u));
         if (i < work) lane_refill(ln, v, b, o, list ? list[i] : strand0 + i, my_arena, arena_words);
       }
-      work_left = base + (uint32_t)__popc(idle) < work;
+      work_left = base + c_idle < work;
       continue;
     }
     // hot loop: keep stepping until `leave` lanes have dropped out of LS_RUN (or none is left); the
     // per-step control cost is one ballot + popc instead of the full vote above
-    const uint32_t n_run0 = __popc(run);
+    const uint32_t n_run0 = n_run;
     const uint32_t stay = n_run0 > leave ? n_run0 - leave : 0;
     while (true) {
 #pragma unroll
@@ -168,12 +173,45 @@ __global__ void __launch_bounds__(kSearchThreads, GQ_SEARCH_MIN_BLOCKS)
   }
 }
 
+// k-mer filter for failed strands, one WARP per strand: lane j tests the k-mers starting at bases
+// j, j+32, ... of the strand (a k-mer code is a bit-field of the packed read, see classify_strand), a
+// ballot ends the strand at the first round that finds a missing k-mer. Lanes first vote on 32 statuses
+// at once to find the unclassified strands of the warp's slice.
 __global__ void __launch_bounds__(256)
     classify_kernel(IndexView v, BatchView b, SearchOut o, const uint32_t* list, uint32_t n_list) {
   const uint32_t n = list ? n_list : 2 * (b.read_end - b.read_begin);
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    uint32_t strand = list ? list[i] : 2 * b.read_begin + i;
-    if (o.status[strand] == ST_UNCLASSIFIED) classify_strand(v, b, o, strand);
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t k = v.k;
+  const uint32_t mask = (k == 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
+  for (uint32_t base = warp * 32; base < n; base += n_warps * 32) {
+    const uint32_t i = base + lane;
+    const uint32_t my_strand = i < n ? (list ? list[i] : 2 * b.read_begin + i) : 0;
+    uint32_t todo = __ballot_sync(0xFFFFFFFFu, i < n && o.status[my_strand] == ST_UNCLASSIFIED);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint32_t strand = __shfl_sync(0xFFFFFFFFu, my_strand, src);
+      const uint32_t r = strand >> 1;
+      const uint32_t L = b.len[r];
+      const uint32_t* w = b.packed + b.word_off[r];
+      const bool rc = (strand & 1u) != 0;
+      const uint32_t n_words = (L + 15) >> 4, n_kmers = L - k + 1;
+      bool missing = false;
+      for (uint32_t j0 = 0; j0 < n_kmers && !missing; j0 += 32) {
+        const uint32_t j = j0 + lane;
+        bool absent = false;
+        if (j < n_kmers) {
+          const uint32_t wi = j >> 4, sh = 2 * (j & 15u);
+          const uint32_t lo = __ldg(w + wi), hi = (wi + 1 < n_words) ? __ldg(w + wi + 1) : 0u;
+          const uint32_t win = __funnelshift_r(lo, hi, sh);
+          const uint32_t code = rc ? (pair_reverse32(~win) >> (32 - 2 * k)) : (win & mask);
+          absent = !((__ldg(v.kmer_bits + (code >> 5)) >> (code & 31u)) & 1u);
+        }
+        missing = __any_sync(0xFFFFFFFFu, absent);
+      }
+      if (lane == 0) o.status[strand] = missing ? ST_MISSING_KMER : ST_NO_EXTENSION;
+    }
   }
 }
 
@@ -181,7 +219,7 @@ void launch_classify(const IndexView& v, const BatchView& b, const SearchOut& o,
                      cudaStream_t st) {
   uint32_t work = list ? n_list : 2 * (b.read_end - b.read_begin);
   if (work == 0) return;
-  uint32_t blocks = min((work + 255) / 256, 148u * 8u);
+  uint32_t blocks = min((work + 255) / 256, 148u * 8u);  // 8 warps per CTA, 32 strands per warp round
   classify_kernel<<<blocks, 256, 0, st>>>(v, b, o, list, n_list);
 }
 
@@ -200,7 +238,7 @@ void launch_search(const IndexView& v, const BatchView& b, const SearchOut& o, u
   uint32_t wait_max = min(32u, rf_thresh + ev_thresh);
   uint32_t leave = max(1u, ev_thresh / 2);
   if (n_super_smem)
-    search_kernel<true><<<blocks, kSearchThreads, 0, st>>>(v, b, o, arena, arena_words, list, n_list, n_super_smem,
+    search_kernel<true><<<blocks, kSearchThreads, n_super_smem * 16, st>>>(v, b, o, arena, arena_words, list, n_list, n_super_smem,
                                                            rf_thresh, ev_thresh, wait_max, leave);
   else
     search_kernel<false><<<blocks, kSearchThreads, 0, st>>>(v, b, o, arena, arena_words, list, n_list, 0, rf_thresh,
