@@ -82,7 +82,7 @@ struct gq_index {
   uint32_t big_threads = 2048;
   uint32_t pool_words_per_read = 48;
   bool super_in_smem = true;
-  uint32_t rf_thresh = 8, ev_thresh = 8;
+  uint32_t rf_thresh = 8, ev_thresh = 8, leave_opt = 0, wait_opt = 0;
   // run info
   double info[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
@@ -286,7 +286,7 @@ static void do_map(gq_index* ix, const uint8_t* h_bases = nullptr, const uint64_
     oc.n_mapped = ix->small.p + 8 + 2 * i;
     oc.work_counter = ix->small.p + 9 + 2 * i;
     gq::launch_search(ix->dv, bc, oc, ix->arena.p, ix->arena_words, threads, nullptr, 0, ix->super_in_smem,
-                      ix->rf_thresh, ix->ev_thresh, st);
+                      ix->rf_thresh, ix->ev_thresh, st, ix->leave_opt, ix->wait_opt);
     if (chunks.size() == 1) CUDA_OK(cudaEventRecord(ix->ev[1], st));
     gq::launch_classify(ix->dv, bc, oc, nullptr, 0, st);
     gq::launch_coverage(ix->dv, bc, oc, c, ix->arena.p, ix->arena_words, threads2, nullptr, 0,
@@ -338,7 +338,7 @@ static void do_map(gq_index* ix, const uint8_t* h_bases = nullptr, const uint64_
     CUDA_OK(cudaMemcpyAsync(list.p, ix->overflow_list.p, (size_t)n_list * 4, cudaMemcpyDeviceToDevice, st));
     CUDA_OK(cudaMemsetAsync(ix->small.p + 1, 0, 4, st));
     CUDA_OK(cudaMemsetAsync(ix->small.p + 9, 0, 4, st));  // work counter of the list run
-    gq::launch_search(ix->dv, b, o, ix->big_arena.p, big_words, bt, list.p, n_list, ix->super_in_smem, ix->rf_thresh, ix->ev_thresh, st);
+    gq::launch_search(ix->dv, b, o, ix->big_arena.p, big_words, bt, list.p, n_list, ix->super_in_smem, ix->rf_thresh, ix->ev_thresh, st, ix->leave_opt, ix->wait_opt);
     gq::launch_classify(ix->dv, b, o, list.p, n_list, st);
     ++launches;
     gq::launch_coverage(ix->dv, b, o, c, ix->big_arena.p, big_words, bt, list.p, n_list, ix->cov_overflow_list.p,
@@ -855,6 +855,10 @@ int gq_set_option(gq_index* ix, const char* name, int64_t value) {
     ix->pool.release();
   } else if (n == "chunk_reads") {
     ix->chunk_reads = (uint32_t)std::max<int64_t>(value, 1024);
+  } else if (n == "leave") {
+    ix->leave_opt = (uint32_t)value;
+  } else if (n == "wait_max") {
+    ix->wait_opt = (uint32_t)value;
   } else if (n == "rf_thresh") {
     ix->rf_thresh = (uint32_t)value;
   } else if (n == "ev_thresh") {

@@ -55,7 +55,8 @@ struct IndexView {
   const RankBlk* rank_blk;
   const uint32_t* super_cnt;   // 4 per superblock: C[c] + occurrences of A,C,G,T before the superblock
   const uint32_t* mrank_blk;   // markers in BWT[0, block start)
-  const uint32_t* marker_hit;  // 2 per BWT marker occurrence: (marker', allele); see index_build.cpp
+  const uint32_t* marker_hit;  // 4 per BWT marker occurrence: (marker', allele, lo, hi): the jump target and, when
+                               // no marker is adjacent on the far side, the SA interval after the jump (else lo = ~0)
   uint32_t c_base[4];          // first SA index of suffixes starting with A,C,G,T
   // per site slot s = (site_id - 5) / 2
   uint32_t n_slots;
@@ -267,7 +268,7 @@ GQ_HD void scan_markers(Stack& s, const IndexView& v, uint32_t pos, uint32_t lo,
 #endif
       m &= m - 1;
       uint32_t mr = mr0 + (bit ? (uint32_t)popc64(all & (~0ull >> (64 - bit))) : 0u);
-      uint32_t marker = v.marker_hit[2 * mr], allele = v.marker_hit[2 * mr + 1];
+      uint32_t marker = v.marker_hit[4 * mr], allele = v.marker_hit[4 * mr + 1];
       if (marker == 0) continue;
       // copy of the scanned state (always at base_top) with the locus in the header
       uint32_t* src = s.mem + base_top;

@@ -67,6 +67,13 @@ GQ_DEV inline uint32_t gq_atomic_inc_aggregated(uint32_t* p) {
   return (*p)++;
 #endif
 }
+GQ_DEV inline uint32_t gq_funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) {  // bits [sh, sh+32) of hi:lo
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_r(lo, hi, sh);
+#else
+  return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+#endif
+}
 GQ_DEV inline void gq_threadfence() {
 #if defined(__CUDA_ARCH__)
   __threadfence();
@@ -241,6 +248,19 @@ GQ_DEV inline void lane_finish_strand(Lane& ln, const SearchOut& o) {
   ln.state = LS_IDLE;
 }
 
+GQ_DEV inline uint32_t pair_reverse32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  x = __brev(x);
+#else
+  x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+  x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+  x = ((x >> 4) & 0x0F0F0F0Fu) | ((x & 0x0F0F0F0Fu) << 4);
+  x = ((x >> 8) & 0x00FF00FFu) | ((x & 0x00FF00FFu) << 8);
+  x = (x >> 16) | (x << 16);
+#endif
+  return ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);  // bit reversal, then un-swap inside each pair
+}
+
 // Start `strand` on this lane: seed with the index entry of its last k-mer (quasimap.cpp:178,235-241).
 GQ_DEV inline void lane_refill(Lane& ln, const IndexView& v, const BatchView& b, const SearchOut& o, uint32_t strand,
                                uint32_t* arena, uint32_t arena_words) {
@@ -249,8 +269,6 @@ GQ_DEV inline void lane_refill(Lane& ln, const IndexView& v, const BatchView& b,
   const uint32_t k = v.k;
   ln.strand = strand;
   ln.state = LS_IDLE;
-  o.st_count[strand] = 0;
-  o.st_words[strand] = 0;
   if (L == 0) {  // non-ACGT read, emptied by the encoder: skipped (quasimap.cpp:108-113)
     o.status[strand] = ST_SKIPPED;
     return;
@@ -260,8 +278,17 @@ GQ_DEV inline void lane_refill(Lane& ln, const IndexView& v, const BatchView& b,
     return;
   }
   ln.rd = ReadCursor{b.packed + b.word_off[r], L, (strand & 1u) != 0, 0xFFFFFFFFu, 0};
-  uint32_t code = 0;  // k-mer code: base j of the k-mer at bits [2j, 2j+2)
-  for (uint32_t j = 0; j < k; ++j) code |= ln.rd(L - k + j) << (2 * j);
+  // seeding k-mer = last k bases of the strand; its code (base j at bits [2j,2j+2)) is a bit-field of the
+  // packed read: the last k pairs for the forward strand, the pair-reversed complement of the first k
+  // pairs for the reverse strand
+  uint32_t code;
+  if (ln.rd.rc) {
+    code = pair_reverse32(~GQ_LDG(ln.rd.w)) >> (32 - 2 * k);
+  } else {
+    const uint32_t j0 = L - k, wi = j0 >> 4, n_words = (L + 15) >> 4;
+    const uint32_t wlo = GQ_LDG(ln.rd.w + wi), whi = (wi + 1 < n_words) ? GQ_LDG(ln.rd.w + wi + 1) : 0u;
+    code = gq_funnelshift_r(wlo, whi, 2 * (j0 & 15u)) & ((k == 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u));
+  }
   uint32_t sb = GQ_LDG(v.kmer_off + code), se = GQ_LDG(v.kmer_off + code + 1);
   if (sb == se) {  // the seeding k-mer itself is not indexed: the k-mer filter fails
     o.status[strand] = ST_MISSING_KMER;
@@ -397,12 +424,43 @@ GQ_DEV inline void lane_event_scan(Lane& ln, const IndexView& v, const SearchOut
     const RankBlk B = load_blk(v.rank_blk + blk);
     const uint64_t all = B.p2 & B.p0;
     const uint32_t mr = GQ_LDG(v.mrank_blk + blk) + (uint32_t)popc64(all & ((1ull << bit) - 1));
-    const uint32_t marker = GQ_LDG(v.marker_hit + 2 * mr), allele = GQ_LDG(v.marker_hit + 2 * mr + 1);
+    const uint32_t marker = GQ_LDG(v.marker_hit + 4 * mr), allele = GQ_LDG(v.marker_hit + 4 * mr + 1);
+    const uint32_t jlo = GQ_LDG(v.marker_hit + 4 * mr + 2), jhi = GQ_LDG(v.marker_hit + 4 * mr + 3);
     if (marker == 0) {
       ln.state = LS_EV_POP;
       return;
     }
     uint32_t* t = ln.s.mem + ln.s.top;
+    if (jlo != kNoAllele) {
+      // pre-resolved jump (no adjacent marker on the other side): the whole vBWT jump is a path update
+      // + the SA interval stored with the marker occurrence; registers stay authoritative for lo/hi/pos
+      uint32_t nt = t[3] & 0xFFFFu, ng = t[3] >> 16;
+      if (ln.s.top + kHdr + 2 * nt + ng + 2 > ln.s.limit) {
+        ln.s.overflow = true;
+        lane_finish_strand(ln, o);
+        return;
+      }
+      uint32_t* T = t + kHdr;
+      if (marker & 1u) {  // exit through `allele` (exit_site_in_place)
+        uint32_t* G = T + 2 * nt;
+        if (ng > 0) {
+          --ng;
+          for (uint32_t j = ng; j-- > 0;) G[j + 2] = G[j];
+        }
+        T[2 * nt] = marker;
+        T[2 * nt + 1] = allele;
+        ++nt;
+      } else {  // enter the site whose end marker this is
+        T[2 * nt + ng] = marker - 1;
+        ++ng;
+      }
+      t[3] = nt | (ng << 16);
+      ln.lo = jlo;
+      ln.hi = jhi;
+      ln.kind = K_READY;
+      ln.state = (jlo == jhi) ? LS_RUN : LS_RUNW;
+      return;
+    }
     t[0] = ln.pos | (K_JUMP << 28);
     t[1] = marker;
     t[2] = allele;
@@ -424,7 +482,34 @@ GQ_DEV inline void lane_event_pop(Lane& ln, const SearchOut& o) {
 GQ_DEV inline void lane_event_top(Lane& ln, const IndexView& v, const SearchOut& o) {
   uint32_t* t = ln.s.mem + ln.s.top;
   if ((t[0] >> 28) == K_JUMP) process_jump(ln.s, v);
-  else {
+  else if (t[4] == kNoAllele && ln.n_states == 0 && t[3] != 0 && ln.s.limit == ln.arena_words) {
+    // the strand's only state, with a path: write its record straight into the pool
+    const uint32_t nt = t[3] & 0xFFFFu, ng = t[3] >> 16, words = 4 + 2 * nt + 2 * ng;
+    const uint32_t off = gq_atomic_add(o.pool_used, words);
+    if (off + words > o.pool_cap) {
+      ln.s.overflow = true;
+      lane_finish_strand(ln, o);
+      return;
+    }
+    uint32_t* d = o.pool + off;
+    d[0] = t[1];
+    d[1] = t[2];
+    d[2] = nt;
+    d[3] = ng;
+    const uint32_t* T = t + kHdr;
+    for (uint32_t j = 0; j < 2 * nt; ++j) d[4 + j] = T[j];
+    for (uint32_t j = 0; j < ng; ++j) {
+      d[4 + 2 * nt + 2 * j] = T[2 * nt + j];
+      d[4 + 2 * nt + 2 * j + 1] = kNoAllele;
+    }
+    o.st_off[ln.strand] = off;
+    o.st_words[ln.strand] = words;
+    o.st_count[ln.strand] = 1;
+    o.status[ln.strand] = ST_MAPPED;
+    o.mapped_list[gq_atomic_inc_aggregated(o.n_mapped)] = ln.strand;
+    ln.state = LS_IDLE;
+    return;
+  } else {
     EmitStage emit{&ln.s, &v, ln.n_states};
     emit(t);
     ln.n_states = emit.n_states;
@@ -446,19 +531,6 @@ GQ_DEV inline void lane_event(Lane& ln, const IndexView& v, const SearchOut& o) 
 // iteration. The reverse strand holds exactly the reverse complements of the forward windows
 // (complement = bitwise NOT of the 2-bit code, reversal = pair-reversal), and "any k-mer missing"
 // does not depend on the order in which windows are visited.
-GQ_DEV inline uint32_t pair_reverse32(uint32_t x) {
-#if defined(__CUDA_ARCH__)
-  x = __brev(x);
-#else
-  x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
-  x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
-  x = ((x >> 4) & 0x0F0F0F0Fu) | ((x & 0x0F0F0F0Fu) << 4);
-  x = ((x >> 8) & 0x00FF00FFu) | ((x & 0x00FF00FFu) << 8);
-  x = (x >> 16) | (x << 16);
-#endif
-  return ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);  // bit reversal, then un-swap inside each pair
-}
-
 GQ_DEV inline void classify_strand(const IndexView& v, const BatchView& b, const SearchOut& o, uint32_t strand) {
   const uint32_t r = strand >> 1;
   const uint32_t L = b.len[r], k = v.k;

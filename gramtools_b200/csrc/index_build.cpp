@@ -323,12 +323,28 @@ void build_fm(HostIndex& ix, const std::vector<uint32_t>& hit_marker, const std:
         b.p0 |= bit;
         ++nmark;
         bool at_base = p < prg.size() && prg[p] <= 4;
-        ix.marker_hit.push_back(at_base ? hit_marker[p] : 0);
-        ix.marker_hit.push_back(at_base ? hit_allele[p] : 0);
+        uint32_t hm = at_base ? hit_marker[p] : 0, ha = at_base ? hit_allele[p] : 0;
+        uint32_t jlo = kNoAllele, jhi = kNoAllele;
+        if (hm > 4) {
+          if (hm & 1u) {  // exit: simple when nothing is adjacent to the left of the site (tm_odd empty)
+            uint32_t slot = (hm - 5) / 2;
+            if (ix.tm_odd[slot] == 0) jlo = jhi = ix.site_sa[slot];
+          } else {  // entry: simple when the site has no empty allele / nested site at an allele end
+            uint32_t slot = (hm - 6) / 2;
+            if (ix.tm_even_off[slot + 1] == ix.tm_even_off[slot]) {
+              jlo = ix.allele_iv[2 * slot];
+              jhi = ix.allele_iv[2 * slot + 1];
+            }
+          }
+        }
+        ix.marker_hit.push_back(hm);
+        ix.marker_hit.push_back(ha);
+        ix.marker_hit.push_back(jlo);
+        ix.marker_hit.push_back(jhi);
       }
     }
   }
-  if (ix.marker_hit.empty()) ix.marker_hit.assign(2, 0);
+  if (ix.marker_hit.empty()) ix.marker_hit.assign(4, 0);
 }
 
 // ---- all-k-mers index (reference: src/build/kmer_index/build.cpp:18-148) ---------------------

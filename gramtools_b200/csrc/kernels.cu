@@ -89,7 +89,10 @@ constexpr int kMaxSuperSmem = 2048;  // superblocks (x16 B = 32 KB) staged in sh
 //   * everything pending                    when no lane can take a hot step, or too many lanes wait
 //   * otherwise the hot step (x kHotUnroll) for every lane in LS_RUN
 // Batching the rare paths keeps the hot step near full lane occupancy (v1 ran 3.5 lanes/instruction).
-constexpr int kHotUnroll = 2;
+#ifndef GQ_HOT_UNROLL
+#define GQ_HOT_UNROLL 2
+#endif
+constexpr int kHotUnroll = GQ_HOT_UNROLL;
 
 #ifndef GQ_SEARCH_MIN_BLOCKS
 #define GQ_SEARCH_MIN_BLOCKS 5  // 48 registers, 1280 resident lanes per SM
@@ -227,7 +230,8 @@ int search_kernel_smem_limit_superblocks() { return kMaxSuperSmem; }
 
 void launch_search(const IndexView& v, const BatchView& b, const SearchOut& o, uint32_t* arena,
                    uint32_t arena_words, uint32_t n_threads, const uint32_t* list, uint32_t n_list,
-                   bool super_in_smem, uint32_t rf_thresh, uint32_t ev_thresh, cudaStream_t st) {
+                   bool super_in_smem, uint32_t rf_thresh, uint32_t ev_thresh, cudaStream_t st, uint32_t leave_opt,
+                   uint32_t wait_opt) {
   uint32_t work = list ? n_list : 2 * (b.read_end - b.read_begin);
   if (work == 0) return;
   uint32_t blocks = (min(work, n_threads) + kSearchThreads - 1) / kSearchThreads;
@@ -235,8 +239,8 @@ void launch_search(const IndexView& v, const BatchView& b, const SearchOut& o, u
   uint32_t n_super_smem = (super_in_smem && n_super <= (uint32_t)kMaxSuperSmem) ? n_super : 0;
   rf_thresh = max(1u, min(32u, rf_thresh));
   ev_thresh = max(1u, min(32u, ev_thresh));
-  uint32_t wait_max = min(32u, rf_thresh + ev_thresh);
-  uint32_t leave = max(1u, ev_thresh / 2);
+  uint32_t wait_max = wait_opt ? wait_opt : min(32u, rf_thresh + ev_thresh);
+  uint32_t leave = leave_opt ? leave_opt : max(1u, ev_thresh / 2);
   if (n_super_smem)
     search_kernel<true><<<blocks, kSearchThreads, n_super_smem * 16, st>>>(v, b, o, arena, arena_words, list, n_list, n_super_smem,
                                                            rf_thresh, ev_thresh, wait_max, leave);

@@ -63,7 +63,8 @@ void launch_pack(const uint8_t* bases, const uint64_t* offsets, uint32_t r0, uin
 // otherwise only the listed strands (overflow re-runs with a larger arena).
 void launch_search(const IndexView& v, const BatchView& b, const SearchOut& o, uint32_t* arena,
                    uint32_t arena_words, uint32_t n_threads, const uint32_t* list, uint32_t n_list,
-                   bool super_in_smem, uint32_t rf_thresh, uint32_t ev_thresh, cudaStream_t st);
+                   bool super_in_smem, uint32_t rf_thresh, uint32_t ev_thresh, cudaStream_t st,
+                   uint32_t leave_opt = 0, uint32_t wait_opt = 0);
 
 // list == nullptr: the strands in o.mapped_list[0, *o.n_mapped); otherwise the listed strands.
 void launch_coverage(const IndexView& v, const BatchView& b, const SearchOut& o, const CoverageView& c,
