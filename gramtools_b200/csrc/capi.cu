@@ -13,6 +13,7 @@
 #include "kernels.cuh"
 
 namespace gq {
+void debug_counters(unsigned long long* out32);
 void launch_stats(const uint8_t* status, const uint32_t* len, uint32_t n_reads, unsigned long long* stats,
                   cudaStream_t st);
 }
@@ -70,6 +71,9 @@ struct gq_index {
   DevBuf<uint8_t> status;
   DevBuf<uint32_t> st_off, st_words, st_count, pool, small;  // small: [pool_used, n_overflow, n_cov_overflow]
   DevBuf<uint32_t> overflow_list, cov_overflow_list, mapped_list;
+  DevBuf<uint32_t> seed_rec, pre_off, pre_cnt, live_list;  // seed pass (SeedOut)
+  uint32_t seed_recs_per_read = 8;
+  bool use_seed_pass = true;
   DevBuf<uint32_t> arena, big_arena;
   cudaStream_t copy_stream = nullptr;
   std::vector<cudaEvent_t> chunk_events;
@@ -239,7 +243,11 @@ static void do_map(gq_index* ix, const uint8_t* h_bases = nullptr, const uint64_
   ix->overflow_list.reserve(2 * (size_t)n);
   ix->cov_overflow_list.reserve(2 * (size_t)n);
   ix->mapped_list.reserve(2 * (size_t)n);
-  ix->small.reserve(8 + 2 * 64);
+  ix->small.reserve(8 + 4 * 64);
+  ix->pre_off.reserve(2 * (size_t)n);
+  ix->pre_cnt.reserve(2 * (size_t)n);
+  ix->live_list.reserve(2 * (size_t)n);
+  ix->seed_rec.reserve(4 * std::max<size_t>((size_t)n * ix->seed_recs_per_read, 1 << 16));
   size_t pool_need = std::max<size_t>((size_t)n * ix->pool_words_per_read, 1 << 16);
   pool_need = std::min<size_t>(pool_need, 0xFFFFFFF0ull);
   ix->pool.reserve(pool_need);
@@ -250,8 +258,9 @@ static void do_map(gq_index* ix, const uint8_t* h_bases = nullptr, const uint64_
   uint32_t threads = std::min<uint32_t>(ix->n_threads, std::max<uint32_t>(256, ((2 * max_chunk / 4 + 255) / 256) * 256));
   uint32_t threads2 = std::min<uint32_t>(ix->cov_threads, ((2 * max_chunk + 255) / 256) * 256);
   ix->arena.reserve((size_t)std::max(threads, threads2) * ix->arena_words);
-  // small: [0] pool_used [1] n_overflow [2] n_cov_overflow; per chunk c: [8+2c] n_mapped [9+2c] work counter
-  CUDA_OK(cudaMemsetAsync(ix->small.p, 0, (8 + 2 * 64) * 4, st));
+  // small: [0] pool_used [1] n_overflow [2] n_cov_overflow [3] seed records used;
+  // per chunk c: [8+4c] n_mapped [9+4c] work counter [10+4c] n_live
+  CUDA_OK(cudaMemsetAsync(ix->small.p, 0, (8 + 4 * 64) * 4, st));
 
   gq::BatchView b{ix->packed.p, ix->word_off.p, ix->len.p, ix->seeds.p, n, 0, n};
   gq::SearchOut o{ix->status.p, ix->st_off.p, ix->st_words.p, ix->st_count.p, ix->pool.p, (uint32_t)ix->pool.cap,
@@ -283,10 +292,17 @@ static void do_map(gq_index* ix, const uint8_t* h_bases = nullptr, const uint64_
     bc.read_end = chunks[i].r1;
     gq::SearchOut oc = o;
     oc.mapped_list = ix->mapped_list.p + 2 * (size_t)chunks[i].r0;
-    oc.n_mapped = ix->small.p + 8 + 2 * i;
-    oc.work_counter = ix->small.p + 9 + 2 * i;
+    oc.n_mapped = ix->small.p + 8 + 4 * i;
+    oc.work_counter = ix->small.p + 9 + 4 * i;
+    gq::SeedOut pre{ix->seed_rec.p, (uint32_t)(ix->seed_rec.cap / 4), ix->small.p + 3, ix->pre_off.p, ix->pre_cnt.p,
+                    ix->live_list.p + 2 * (size_t)chunks[i].r0, ix->small.p + 10 + 4 * i};
+    if (ix->use_seed_pass) {
+      gq::launch_seed(ix->dv, bc, oc, pre, st);
+      ++launches;
+    }
     gq::launch_search(ix->dv, bc, oc, ix->arena.p, ix->arena_words, threads, nullptr, 0, ix->super_in_smem,
-                      ix->rf_thresh, ix->ev_thresh, st, ix->leave_opt, ix->wait_opt);
+                      ix->rf_thresh, ix->ev_thresh, st, ix->leave_opt, ix->wait_opt,
+                      ix->use_seed_pass ? &pre : nullptr);
     if (chunks.size() == 1) CUDA_OK(cudaEventRecord(ix->ev[1], st));
     gq::launch_classify(ix->dv, bc, oc, nullptr, 0, st);
     gq::launch_coverage(ix->dv, bc, oc, c, ix->arena.p, ix->arena_words, threads2, nullptr, 0,
@@ -403,6 +419,9 @@ extern "C" {
 
 const char* gq_last_error(void) { return g_err.c_str(); }
 
+// developer hook (not in gq.h): warp-loop statistics when built with -DGQ_DEBUG_COUNTERS
+void gq_debug_counters(unsigned long long* out32) { gq::debug_counters(out32); }
+
 int gq_index_build(const uint32_t* prg, uint64_t n_symbols, uint32_t kmer_size, int device, gq_index** out) {
   gq_index* ix = nullptr;
   GQ_TRY
@@ -457,6 +476,10 @@ int gq_index_destroy(gq_index* ix) {
   ix->overflow_list.release();
   ix->cov_overflow_list.release();
   ix->mapped_list.release();
+  ix->seed_rec.release();
+  ix->pre_off.release();
+  ix->pre_cnt.release();
+  ix->live_list.release();
   ix->arena.release();
   ix->big_arena.release();
   for (auto& e : ix->ev)
@@ -855,6 +878,11 @@ int gq_set_option(gq_index* ix, const char* name, int64_t value) {
     ix->pool.release();
   } else if (n == "chunk_reads") {
     ix->chunk_reads = (uint32_t)std::max<int64_t>(value, 1024);
+  } else if (n == "seed_pass") {
+    ix->use_seed_pass = value != 0;
+  } else if (n == "seed_recs_per_read") {
+    ix->seed_recs_per_read = (uint32_t)std::max<int64_t>(value, 1);
+    ix->seed_rec.release();
   } else if (n == "leave") {
     ix->leave_opt = (uint32_t)value;
   } else if (n == "wait_max") {

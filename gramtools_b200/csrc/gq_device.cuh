@@ -524,6 +524,136 @@ GQ_DEV inline void lane_event(Lane& ln, const IndexView& v, const SearchOut& o) 
   else lane_event_top(ln, v, o);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Seed pass. For one strand: look up the seeding k-mer (quasimap.cpp:178,235-241) and pre-extend each of
+// its seed states by up to kPreSteps marker-free bases with the very same step functions the search
+// kernel uses. Seeds of strands that cannot map die here (a random 16-mer does not occur in the PRG), so
+// they never occupy a lane of the warp-synchronous kernel; survivors are handed over with their current
+// (pos, lo, hi) and resume exactly where they stopped.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kPreSteps = 6;
+
+// part 1: k-mer lookup. Returns the number of seed states (0: the strand is already classified).
+GQ_DEV inline uint32_t preseed_lookup(const IndexView& v, const BatchView& b, const SearchOut& o, const SeedOut& pre,
+                                      uint32_t strand, uint32_t& sb) {
+  const uint32_t r = strand >> 1;
+  const uint32_t L = b.len[r];
+  const uint32_t k = v.k;
+  pre.pre_cnt[strand] = 0;
+  if (L == 0) {  // non-ACGT read, emptied by the encoder: skipped (quasimap.cpp:108-113)
+    o.status[strand] = ST_SKIPPED;
+    return 0;
+  }
+  if (L < k) {  // cannot be seeded (UB in the reference, quasimap.cpp:206-210): counted as missing k-mer
+    o.status[strand] = ST_MISSING_KMER;
+    return 0;
+  }
+  const uint32_t* w = b.packed + b.word_off[r];
+  uint32_t code;
+  if (strand & 1u) {
+    code = pair_reverse32(~GQ_LDG(w)) >> (32 - 2 * k);
+  } else {
+    const uint32_t j0 = L - k, wi = j0 >> 4, n_words = (L + 15) >> 4;
+    const uint32_t wlo = GQ_LDG(w + wi), whi = (wi + 1 < n_words) ? GQ_LDG(w + wi + 1) : 0u;
+    code = gq_funnelshift_r(wlo, whi, 2 * (j0 & 15u)) & ((k == 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u));
+  }
+  sb = GQ_LDG(v.kmer_off + code);
+  const uint32_t se = GQ_LDG(v.kmer_off + code + 1);
+  if (sb == se) {  // the seeding k-mer itself is not indexed: the k-mer filter fails
+    o.status[strand] = ST_MISSING_KMER;
+    return 0;
+  }
+  return se - sb;
+}
+
+// part 2: pre-extension of the n seed states [sb, sb+n) into the record slots starting at `base`
+template <class SuperPtr>
+GQ_DEV inline void preseed_extend(const IndexView& v, SuperPtr super_c, const BatchView& b, const SearchOut& o,
+                                  const SeedOut& pre, uint32_t strand, uint32_t sb, uint32_t n, uint32_t base) {
+  if (base + n > pre.cap) {  // record pool full: re-run later, seeded inside the search kernel
+    o.status[strand] = ST_OVERFLOW;
+    o.overflow_list[gq_atomic_add(o.n_overflow, 1u)] = strand;
+    return;
+  }
+  const uint32_t r = strand >> 1;
+  const uint32_t L = b.len[r], k = v.k;
+  Lane ln;
+  ln.rd = ReadCursor{b.packed + b.word_off[r], L, (strand & 1u) != 0, 0xFFFFFFFFu, 0};
+  uint32_t cnt = 0;
+  for (uint32_t j = sb; j < sb + n; ++j) {
+    const KmerState ks = v.kmer_states[j];
+    ln.pos = L - k;
+    ln.lo = ks.lo;
+    ln.hi = ks.hi;
+    ln.kind = K_SCAN;
+    ln.state = ln.pos == 0 ? LS_EV_TOP : (ln.lo == ln.hi ? LS_RUN : LS_RUNW);
+    // never consume the last base here: the finished state is emitted by the search kernel
+    const uint32_t max_steps = ln.pos > 1 ? (ln.pos - 1 < kPreSteps ? ln.pos - 1 : kPreSteps) : 0;
+    for (uint32_t s = 0; s < max_steps && (ln.state == LS_RUN || ln.state == LS_RUNW); ++s) {
+      if (ln.state == LS_RUN) lane_step(ln, v, super_c);
+      else lane_step_wide(ln, v, super_c);
+    }
+    if (ln.state == LS_EV_POP) continue;
+    uint32_t* d = pre.rec + 4 * (size_t)(base + cnt);
+    d[0] = j;
+    d[1] = ln.pos | (ln.kind << 28);
+    d[2] = ln.lo;
+    d[3] = ln.hi;
+    ++cnt;
+  }
+  pre.pre_off[strand] = base;
+  pre.pre_cnt[strand] = cnt;
+  if (cnt == 0) o.status[strand] = ST_UNCLASSIFIED;
+  else pre.live_list[gq_atomic_inc_aggregated(pre.n_live)] = strand;
+}
+
+template <class SuperPtr>
+GQ_DEV inline void preseed_strand(const IndexView& v, SuperPtr super_c, const BatchView& b, const SearchOut& o,
+                                  const SeedOut& pre, uint32_t strand) {
+  uint32_t sb = 0;
+  const uint32_t n = preseed_lookup(v, b, o, pre, strand, sb);
+  if (n) preseed_extend(v, super_c, b, o, pre, strand, sb, n, gq_atomic_add(pre.used, n));
+}
+
+// Start a pre-seeded strand on this lane: its surviving seed states become the initial stack.
+GQ_DEV inline void lane_refill_pre(Lane& ln, const IndexView& v, const BatchView& b, const SearchOut& o,
+                                   const SeedOut& pre, uint32_t strand, uint32_t* arena, uint32_t arena_words) {
+  const uint32_t r = strand >> 1;
+  ln.strand = strand;
+  ln.rd = ReadCursor{b.packed + b.word_off[r], b.len[r], (strand & 1u) != 0, 0xFFFFFFFFu, 0};
+  ln.s.mem = arena;
+  ln.s.limit = arena_words;
+  ln.s.overflow = false;
+  ln.s.top = kNoAllele;
+  ln.n_states = 0;
+  ln.arena_words = arena_words;
+  const uint32_t p0 = pre.pre_off[strand], n = pre.pre_cnt[strand];
+  uint32_t sp = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    const uint32_t* rec = pre.rec + 4 * (size_t)(p0 + i);
+    const KmerState ks = v.kmer_states[rec[0]];
+    const uint32_t words = entry_words(ks.counts);
+    if (sp + words + 3 > ln.s.limit) {
+      ln.s.overflow = true;
+      break;
+    }
+    uint32_t* t = ln.s.mem + sp;
+    t[0] = rec[1];
+    t[1] = rec[2];
+    t[2] = rec[3];
+    t[3] = ks.counts;
+    t[4] = ln.s.top;
+    for (uint32_t w = kHdr; w < words; ++w) t[w] = GQ_LDG(v.kmer_paths + ks.path_off + (w - kHdr));
+    ln.s.top = sp;
+    sp += words;
+  }
+  if (ln.s.overflow || n == 0) {
+    lane_finish_strand(ln, o);
+    return;
+  }
+  lane_load_top(ln);
+}
+
 // all_read_kmers_occur_in_index (quasimap.cpp:212-225) for a strand whose search found nothing:
 // any k-mer absent from the index -> missing_kmer, else no_extension (quasimap.cpp:170-186).
 // The k-mer code convention (base j at bits [2j,2j+2)) makes the code of the window starting at base i
@@ -557,11 +687,20 @@ GQ_DEV inline void classify_strand(const IndexView& v, const BatchView& b, const
   o.status[strand] = missing ? ST_MISSING_KMER : ST_NO_EXTENSION;
 }
 
-// Single-lane driver (host emulation and a reference for the warp loop in kernels.cu).
+// Single-lane driver (host emulation and a reference for the kernels): seed pass, then the lane state
+// machine on the survivors, then the k-mer filter if nothing mapped. A strand the seed pass could not
+// place (record pool full) is seeded directly from the k-mer index, as the overflow re-runs do.
 GQ_DEV inline void map_strand(const IndexView& v, const uint32_t* super_cnt, const BatchView& b, const SearchOut& o,
-                              uint32_t strand, uint32_t* arena, uint32_t arena_words) {
+                              const SeedOut& pre, uint32_t strand, uint32_t* arena, uint32_t arena_words) {
   Lane ln;
-  lane_refill(ln, v, b, o, strand, arena, arena_words);
+  ln.state = LS_IDLE;
+  if (o.status[strand] == ST_OVERFLOW) {
+    lane_refill(ln, v, b, o, strand, arena, arena_words);
+  } else {
+    preseed_strand(v, super_cnt, b, o, pre, strand);
+    if (o.status[strand] == ST_OVERFLOW) return;
+    if (pre.pre_cnt[strand]) lane_refill_pre(ln, v, b, o, pre, strand, arena, arena_words);
+  }
   while (ln.state != LS_IDLE) {
     if (ln.state == LS_RUN) lane_step(ln, v, super_cnt);
     else if (ln.state == LS_RUNW) lane_step_wide(ln, v, super_cnt);

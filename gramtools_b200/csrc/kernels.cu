@@ -97,19 +97,69 @@ constexpr int kHotUnroll = GQ_HOT_UNROLL;
 #ifndef GQ_SEARCH_MIN_BLOCKS
 #define GQ_SEARCH_MIN_BLOCKS 5  // 48 registers, 1280 resident lanes per SM
 #endif
+// Seed pass: thread per strand (see preseed_strand). Superblock counters come from shared memory when
+// they fit, like in the search kernel.
+template <bool SUPER_SMEM>
+__global__ void __launch_bounds__(256)
+    seed_kernel(IndexView v, BatchView b, SearchOut o, SeedOut pre, uint32_t n_super_smem) {
+  extern __shared__ __align__(128) uint32_t s_super[];
+  __shared__ alignas(8) uint64_t s_bar;
+  if (SUPER_SMEM) tma_stage_super(s_super, v.super_cnt, n_super_smem * 16u, &s_bar);
+  const uint32_t n = 2 * (b.read_end - b.read_begin);
+  const uint32_t lane = threadIdx.x & 31u;
+  // warp-convergent rounds: the record slots of the 32 strands of a round come from ONE atomic
+  for (uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; i0 < n; i0 += gridDim.x * blockDim.x) {
+    const uint32_t i = i0 + lane;
+    const uint32_t strand = 2 * b.read_begin + i;
+    uint32_t sb = 0;
+    const uint32_t ns = i < n ? preseed_lookup(v, b, o, pre, strand, sb) : 0;
+    uint32_t incl = ns;  // inclusive warp scan
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+      if (lane >= (uint32_t)d) incl += t;
+    }
+    uint32_t base = 0;
+    if (lane == 31 && incl) base = atomicAdd(pre.used, incl);
+    base = __shfl_sync(0xFFFFFFFFu, base, 31) + incl - ns;
+    if (ns) preseed_extend(v, SUPER_SMEM ? (const uint32_t*)s_super : v.super_cnt, b, o, pre, strand, sb, ns, base);
+  }
+}
+
+void launch_seed(const IndexView& v, const BatchView& b, const SearchOut& o, const SeedOut& pre, cudaStream_t st) {
+  uint32_t work = 2 * (b.read_end - b.read_begin);
+  if (work == 0) return;
+  uint32_t blocks = min((work + 255) / 256, 148u * 8u);
+  uint32_t n_super = (v.n >> kSuperShift) + 1;
+  if (n_super <= (uint32_t)kMaxSuperSmem)
+    seed_kernel<true><<<blocks, 256, n_super * 16, st>>>(v, b, o, pre, n_super);
+  else
+    seed_kernel<false><<<blocks, 256, 0, st>>>(v, b, o, pre, 0);
+}
+
+#ifdef GQ_DEBUG_COUNTERS
+__device__ unsigned long long g_dbg[32];
+#define DBG(i, v) do { if (lane == 0) atomicAdd(&g_dbg[i], (unsigned long long)(v)); } while (0)
+#else
+#define DBG(i, v) do { } while (0)
+#endif
+
 template <bool SUPER_SMEM>
 __global__ void __launch_bounds__(kSearchThreads, GQ_SEARCH_MIN_BLOCKS)
     search_kernel(IndexView v, BatchView b, SearchOut o, uint32_t* arena, uint32_t arena_words,
                   const uint32_t* list, uint32_t n_list, uint32_t n_super_smem, uint32_t rf_thresh,
-                  uint32_t ev_thresh, uint32_t wait_max, uint32_t leave) {
+                  uint32_t ev_thresh, uint32_t wait_max, uint32_t leave, SeedOut pre) {
   extern __shared__ __align__(128) uint32_t s_super[];  // n_super_smem x 16 B (dynamic: keeps 5 CTAs/SM)
   __shared__ alignas(8) uint64_t s_bar;
   if (SUPER_SMEM) tma_stage_super(s_super, v.super_cnt, n_super_smem * 16u, &s_bar);
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t work = list ? n_list : 2 * (b.read_end - b.read_begin);
+  // work items: a list of strands (overflow re-runs), the live list of the seed pass, or the whole slice
+  const bool pre_seeded = !list && pre.rec != nullptr;
+  const uint32_t* work_list = list ? list : (pre_seeded ? pre.live_list : nullptr);
+  const uint32_t work = list ? n_list : (pre_seeded ? *pre.n_live : 2 * (b.read_end - b.read_begin));
   const uint32_t strand0 = 2 * b.read_begin;
-  bool work_left = true;  // warp-uniform: strands are handed out by one global counter
+  bool work_left = work > 0;  // warp-uniform: strands are handed out by one global counter
   uint32_t* my_arena = arena + (size_t)tid * arena_words;
   Lane ln;
   ln.state = LS_IDLE;
@@ -134,30 +184,40 @@ __global__ void __launch_bounds__(kSearchThreads, GQ_SEARCH_MIN_BLOCKS)
     const uint32_t waiting = n_idle + n_wide + n_scan + n_pop + n_top;
     const bool force = n_run == 0 || waiting >= wait_max;
     const uint32_t big = max(max(max(n_idle, n_wide), max(n_scan, n_pop)), n_top);
+    DBG(0, 1); DBG(1, n_run); DBG(2, waiting);
     if (n_wide && (n_wide >= ev_thresh || (force && n_wide == big))) {
+      DBG(3, 1); DBG(4, n_wide);
       if (ln.state == LS_RUNW) lane_step_wide(ln, v, SUPER_SMEM ? (const uint32_t*)s_super : v.super_cnt);
       continue;
     }
     if (n_scan && (n_scan >= ev_thresh || (force && n_scan == big))) {
+      DBG(5, 1); DBG(6, n_scan);
       if (ln.state == LS_EV_SCAN || ln.state == LS_EV_WIDE) lane_event_scan(ln, v, o);
       continue;
     }
     if (n_top && (n_top >= ev_thresh || (force && n_top == big))) {
+      DBG(7, 1); DBG(8, n_top);
       if (ln.state == LS_EV_TOP) lane_event_top(ln, v, o);
       continue;
     }
     if (n_pop && (n_pop >= ev_thresh || (force && n_pop == big))) {
+      DBG(9, 1); DBG(10, n_pop);
       if (ln.state == LS_EV_POP) lane_event_pop(ln, o);
       continue;
     }
     if (n_idle && (n_idle >= rf_thresh || (force && n_idle == big))) {
+      DBG(11, 1); DBG(12, n_idle);
       const uint32_t idle = __ballot_sync(full, ln.state == LS_IDLE);
       uint32_t base = 0;
       if (lane == 0) base = atomicAdd(o.work_counter, c_idle);
       base = __shfl_sync(full, base, 0);
       if (ln.state == LS_IDLE) {
         uint32_t i = base + __popc(idle & ((1u << lane) - 1u));
-        if (i < work) lane_refill(ln, v, b, o, list ? list[i] : strand0 + i, my_arena, arena_words);
+        if (i < work) {
+          const uint32_t strand = work_list ? work_list[i] : strand0 + i;
+          if (pre_seeded) lane_refill_pre(ln, v, b, o, pre, strand, my_arena, arena_words);
+          else lane_refill(ln, v, b, o, strand, my_arena, arena_words);
+        }
       }
       work_left = base + c_idle < work;
       continue;
@@ -171,6 +231,7 @@ __global__ void __launch_bounds__(kSearchThreads, GQ_SEARCH_MIN_BLOCKS)
       for (int u = 0; u < kHotUnroll; ++u)
         if (ln.state == LS_RUN) lane_step(ln, v, SUPER_SMEM ? (const uint32_t*)s_super : v.super_cnt);
       const uint32_t n_run = __popc(__ballot_sync(full, ln.state == LS_RUN));
+      DBG(13, 1); DBG(14, n_run);
       if (n_run <= stay) break;
     }
   }
@@ -228,10 +289,22 @@ void launch_classify(const IndexView& v, const BatchView& b, const SearchOut& o,
 
 int search_kernel_smem_limit_superblocks() { return kMaxSuperSmem; }
 
+void debug_counters(unsigned long long* out32) {
+#ifdef GQ_DEBUG_COUNTERS
+  cudaMemcpyFromSymbol(out32, g_dbg, sizeof(unsigned long long) * 32);
+  unsigned long long z[32] = {0};
+  cudaMemcpyToSymbol(g_dbg, z, sizeof z);
+#else
+  for (int i = 0; i < 32; ++i) out32[i] = 0;
+#endif
+}
+
 void launch_search(const IndexView& v, const BatchView& b, const SearchOut& o, uint32_t* arena,
                    uint32_t arena_words, uint32_t n_threads, const uint32_t* list, uint32_t n_list,
                    bool super_in_smem, uint32_t rf_thresh, uint32_t ev_thresh, cudaStream_t st, uint32_t leave_opt,
-                   uint32_t wait_opt) {
+                   uint32_t wait_opt, const SeedOut* pre) {
+  SeedOut pz{};
+  if (pre && !list) pz = *pre;
   uint32_t work = list ? n_list : 2 * (b.read_end - b.read_begin);
   if (work == 0) return;
   uint32_t blocks = (min(work, n_threads) + kSearchThreads - 1) / kSearchThreads;
@@ -243,10 +316,10 @@ void launch_search(const IndexView& v, const BatchView& b, const SearchOut& o, u
   uint32_t leave = leave_opt ? leave_opt : max(1u, ev_thresh / 2);
   if (n_super_smem)
     search_kernel<true><<<blocks, kSearchThreads, n_super_smem * 16, st>>>(v, b, o, arena, arena_words, list, n_list, n_super_smem,
-                                                           rf_thresh, ev_thresh, wait_max, leave);
+                                                           rf_thresh, ev_thresh, wait_max, leave, pz);
   else
     search_kernel<false><<<blocks, kSearchThreads, 0, st>>>(v, b, o, arena, arena_words, list, n_list, 0, rf_thresh,
-                                                            ev_thresh, wait_max, leave);
+                                                            ev_thresh, wait_max, leave, pz);
 }
 
 // ------------------------------------------------------------------------------------------------

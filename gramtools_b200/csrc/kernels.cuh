@@ -38,6 +38,19 @@ struct SearchOut {
   uint32_t* work_counter;   // dynamic work distribution of the search kernel
 };
 
+// Output of the seed pass (seed_kernel): per strand, the seed states of its last k-mer that are still
+// alive after a few marker-free extension steps. Most seeds of a strand that cannot map die there, so the
+// warp-synchronous search kernel only sees strands with real work.
+struct SeedOut {
+  uint32_t* rec;        // 4 words per survivor: {k-mer state index, pos | kind << 28, lo, hi}
+  uint32_t cap;         // survivor records available
+  uint32_t* used;       // bump pointer
+  uint32_t* pre_off;    // per strand: first survivor record
+  uint32_t* pre_cnt;    // per strand: number of survivors
+  uint32_t* live_list;  // strands with >= 1 survivor (work list of the search kernel)
+  uint32_t* n_live;
+};
+
 struct CoverageView {
   uint32_t* allele_sum;      // per (slot, allele): allele_off[slot] + allele
   uint32_t* per_base;        // flat in-bubble bases, PRG order
@@ -61,10 +74,13 @@ void launch_pack(const uint8_t* bases, const uint64_t* offsets, uint32_t r0, uin
 
 // list == nullptr: all reads of the batch (one thread per read, both strands);
 // otherwise only the listed strands (overflow re-runs with a larger arena).
+void launch_seed(const IndexView& v, const BatchView& b, const SearchOut& o, const SeedOut& pre, cudaStream_t st);
+
+// pre == nullptr (or list != nullptr): strands are seeded from the k-mer index inside the kernel.
 void launch_search(const IndexView& v, const BatchView& b, const SearchOut& o, uint32_t* arena,
                    uint32_t arena_words, uint32_t n_threads, const uint32_t* list, uint32_t n_list,
                    bool super_in_smem, uint32_t rf_thresh, uint32_t ev_thresh, cudaStream_t st,
-                   uint32_t leave_opt = 0, uint32_t wait_opt = 0);
+                   uint32_t leave_opt = 0, uint32_t wait_opt = 0, const SeedOut* pre = nullptr);
 
 // list == nullptr: the strands in o.mapped_list[0, *o.n_mapped); otherwise the listed strands.
 void launch_coverage(const IndexView& v, const BatchView& b, const SearchOut& o, const CoverageView& c,
