@@ -566,7 +566,35 @@ GQ_DEV inline uint32_t preseed_lookup(const IndexView& v, const BatchView& b, co
   return se - sb;
 }
 
-// part 2: pre-extension of the n seed states [sb, sb+n) into the record slots starting at `base`
+// part 2: pre-extension of ONE seed state j of a strand into record slot `d` (4 words); a seed that
+// dies is marked by d[1] = 0xFFFFFFFF. Returns whether the seed survived.
+constexpr uint32_t kDeadSeed = 0xFFFFFFFFu;
+template <class SuperPtr>
+GQ_DEV inline bool preseed_one(const IndexView& v, SuperPtr super_c, const uint32_t* w, uint32_t L, bool rc, uint32_t j,
+                               uint32_t* d) {
+  Lane ln;
+  ln.rd = ReadCursor{w, L, rc, 0xFFFFFFFFu, 0};
+  const KmerState ks = v.kmer_states[j];
+  ln.pos = L - v.k;
+  ln.lo = ks.lo;
+  ln.hi = ks.hi;
+  ln.kind = K_SCAN;
+  ln.state = ln.pos == 0 ? LS_EV_TOP : (ln.lo == ln.hi ? LS_RUN : LS_RUNW);
+  // never consume the last base here: the finished state is emitted by the search kernel
+  const uint32_t max_steps = ln.pos > 1 ? (ln.pos - 1 < kPreSteps ? ln.pos - 1 : kPreSteps) : 0;
+  for (uint32_t s = 0; s < max_steps && (ln.state == LS_RUN || ln.state == LS_RUNW); ++s) {
+    if (ln.state == LS_RUN) lane_step(ln, v, super_c);
+    else lane_step_wide(ln, v, super_c);
+  }
+  const bool alive = ln.state != LS_EV_POP;
+  d[0] = j;
+  d[1] = alive ? (ln.pos | (ln.kind << 28)) : kDeadSeed;
+  d[2] = ln.lo;
+  d[3] = ln.hi;
+  return alive;
+}
+
+// per-strand form (host emulation; the kernel spreads the seeds of 32 strands over the lanes of a warp)
 template <class SuperPtr>
 GQ_DEV inline void preseed_extend(const IndexView& v, SuperPtr super_c, const BatchView& b, const SearchOut& o,
                                   const SeedOut& pre, uint32_t strand, uint32_t sb, uint32_t n, uint32_t base) {
@@ -576,34 +604,13 @@ GQ_DEV inline void preseed_extend(const IndexView& v, SuperPtr super_c, const Ba
     return;
   }
   const uint32_t r = strand >> 1;
-  const uint32_t L = b.len[r], k = v.k;
-  Lane ln;
-  ln.rd = ReadCursor{b.packed + b.word_off[r], L, (strand & 1u) != 0, 0xFFFFFFFFu, 0};
-  uint32_t cnt = 0;
-  for (uint32_t j = sb; j < sb + n; ++j) {
-    const KmerState ks = v.kmer_states[j];
-    ln.pos = L - k;
-    ln.lo = ks.lo;
-    ln.hi = ks.hi;
-    ln.kind = K_SCAN;
-    ln.state = ln.pos == 0 ? LS_EV_TOP : (ln.lo == ln.hi ? LS_RUN : LS_RUNW);
-    // never consume the last base here: the finished state is emitted by the search kernel
-    const uint32_t max_steps = ln.pos > 1 ? (ln.pos - 1 < kPreSteps ? ln.pos - 1 : kPreSteps) : 0;
-    for (uint32_t s = 0; s < max_steps && (ln.state == LS_RUN || ln.state == LS_RUNW); ++s) {
-      if (ln.state == LS_RUN) lane_step(ln, v, super_c);
-      else lane_step_wide(ln, v, super_c);
-    }
-    if (ln.state == LS_EV_POP) continue;
-    uint32_t* d = pre.rec + 4 * (size_t)(base + cnt);
-    d[0] = j;
-    d[1] = ln.pos | (ln.kind << 28);
-    d[2] = ln.lo;
-    d[3] = ln.hi;
-    ++cnt;
-  }
+  bool any = false;
+  for (uint32_t t = 0; t < n; ++t)
+    any |= preseed_one(v, super_c, b.packed + b.word_off[r], b.len[r], (strand & 1u) != 0, sb + t,
+                       pre.rec + 4 * (size_t)(base + t));
   pre.pre_off[strand] = base;
-  pre.pre_cnt[strand] = cnt;
-  if (cnt == 0) o.status[strand] = ST_UNCLASSIFIED;
+  pre.pre_cnt[strand] = n;
+  if (!any) o.status[strand] = ST_UNCLASSIFIED;
   else pre.live_list[gq_atomic_inc_aggregated(pre.n_live)] = strand;
 }
 
@@ -631,6 +638,7 @@ GQ_DEV inline void lane_refill_pre(Lane& ln, const IndexView& v, const BatchView
   uint32_t sp = 0;
   for (uint32_t i = 0; i < n; ++i) {
     const uint32_t* rec = pre.rec + 4 * (size_t)(p0 + i);
+    if (rec[1] == kDeadSeed) continue;
     const KmerState ks = v.kmer_states[rec[0]];
     const uint32_t words = entry_words(ks.counts);
     if (sp + words + 3 > ln.s.limit) {
@@ -647,7 +655,7 @@ GQ_DEV inline void lane_refill_pre(Lane& ln, const IndexView& v, const BatchView
     ln.s.top = sp;
     sp += words;
   }
-  if (ln.s.overflow || n == 0) {
+  if (ln.s.overflow || ln.s.top == kNoAllele) {
     lane_finish_strand(ln, o);
     return;
   }

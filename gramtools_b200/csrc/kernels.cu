@@ -107,7 +107,11 @@ __global__ void __launch_bounds__(256)
   if (SUPER_SMEM) tma_stage_super(s_super, v.super_cnt, n_super_smem * 16u, &s_bar);
   const uint32_t n = 2 * (b.read_end - b.read_begin);
   const uint32_t lane = threadIdx.x & 31u;
-  // warp-convergent rounds: the record slots of the 32 strands of a round come from ONE atomic
+  const uint32_t full = 0xFFFFFFFFu;
+  // Warp-convergent rounds of 32 strands. Phase A: every lane looks up the seeds of its strand and one
+  // atomic allocates the record slots of the whole round. Phase B: the seeds of the round (about 3 per
+  // strand) are spread evenly over the lanes, so lanes run the same short pre-extension loop instead of
+  // per-strand loops of very different lengths.
   for (uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; i0 < n; i0 += gridDim.x * blockDim.x) {
     const uint32_t i = i0 + lane;
     const uint32_t strand = 2 * b.read_begin + i;
@@ -116,13 +120,54 @@ __global__ void __launch_bounds__(256)
     uint32_t incl = ns;  // inclusive warp scan
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+      uint32_t t = __shfl_up_sync(full, incl, d);
       if (lane >= (uint32_t)d) incl += t;
     }
+    const uint32_t total = __shfl_sync(full, incl, 31);
+    if (total == 0) continue;
     uint32_t base = 0;
-    if (lane == 31 && incl) base = atomicAdd(pre.used, incl);
-    base = __shfl_sync(0xFFFFFFFFu, base, 31) + incl - ns;
-    if (ns) preseed_extend(v, SUPER_SMEM ? (const uint32_t*)s_super : v.super_cnt, b, o, pre, strand, sb, ns, base);
+    if (lane == 31) base = atomicAdd(pre.used, total);
+    base = __shfl_sync(full, base, 31);
+    if (base + total > pre.cap) {  // record pool full: these strands are re-run, seeded inside the search kernel
+      if (ns) {
+        o.status[strand] = ST_OVERFLOW;
+        o.overflow_list[atomicAdd(o.n_overflow, 1u)] = strand;
+      }
+      continue;
+    }
+    const uint32_t r = strand >> 1;
+    const uint32_t my_L = ns ? b.len[r] : 0;
+    const uint64_t my_w = ns ? (uint64_t)(b.packed + b.word_off[r]) : 0ull;
+    if (ns) {
+      pre.pre_off[strand] = base + incl - ns;
+      pre.pre_cnt[strand] = ns;
+    }
+    uint32_t alive = 0;
+    for (uint32_t t0 = 0; t0 < total; t0 += 32) {
+      const uint32_t t = t0 + lane;
+      // owner of task t = first lane whose inclusive count exceeds t
+      uint32_t lo_l = 0, hi_l = 31;
+#pragma unroll
+      for (int it = 0; it < 5; ++it) {
+        const uint32_t mid = (lo_l + hi_l) >> 1;
+        const uint32_t val = __shfl_sync(full, incl, mid);
+        if (val > t) hi_l = mid;
+        else lo_l = mid + 1;
+      }
+      const uint32_t owner = hi_l;
+      const uint32_t o_incl = __shfl_sync(full, incl, owner), o_ns = __shfl_sync(full, ns, owner),
+                     o_sb = __shfl_sync(full, sb, owner), o_L = __shfl_sync(full, my_L, owner);
+      const uint64_t o_w = __shfl_sync(full, my_w, owner);
+      bool survived = false;
+      if (t < total)
+        survived = preseed_one(v, SUPER_SMEM ? (const uint32_t*)s_super : v.super_cnt, (const uint32_t*)o_w, o_L,
+                               ((i0 + owner) & 1u) != 0, o_sb + (t - (o_incl - o_ns)), pre.rec + 4 * (size_t)(base + t));
+      alive |= __reduce_or_sync(full, survived ? (1u << owner) : 0u);
+    }
+    if (ns) {
+      if ((alive >> lane) & 1u) pre.live_list[gq_atomic_inc_aggregated(pre.n_live)] = strand;
+      else o.status[strand] = ST_UNCLASSIFIED;
+    }
   }
 }
 
