@@ -289,7 +289,7 @@ def main():
             # the committed `ncu --set full` capture (profiles/r01_v5_kernels_summary.txt); it is far below
             # the algorithmic bytes because the 2.4 MB of rank blocks are L2-resident at this index size
             traffic = 683380992 + 272083968 if N_READS == 1_000_000 else None
-            roof = {"bound": "hbm", "kernel": "search_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            roof = {"bound": "hbm", "kernel": "seed_kernel+search_kernel (search phase)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_read": alg_bytes_per_read,
                     "kernel_ms_per_launch": search_ms / args.steps, "coverage_kernel_ms": cov_ms / args.steps}

@@ -1,0 +1,33 @@
+"""Developer probe: end-to-end gq_map_batch time (pinned host buffers) vs pipeline slice size."""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from gramtools_b200 import QuasimapIndex  # noqa: E402
+
+prg, bases, offs, seeds = bench.make_workload(0, 1_000_000)
+idx = QuasimapIndex(prg, bench.KMER)
+pb = torch.from_numpy(bases).pin_memory().numpy()
+po = torch.from_numpy(offs.view(np.int64)).pin_memory().numpy().view(np.uint64)
+ps = torch.from_numpy(seeds.view(np.int32)).pin_memory().numpy().view(np.uint32)
+for chunk in [int(x) for x in os.environ.get("GQ_CHUNKS", "65536,131072,262144,524288,1048576").split(",")]:
+    idx.set_option("chunk_reads", chunk)
+    for _ in range(3):
+        idx.map_batch(pb, po, ps)
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    for _ in range(10):
+        idx.map_batch(pb, po, ps)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t) / 10
+    t = time.perf_counter()
+    for _ in range(10):
+        idx.coverage()
+    dc = (time.perf_counter() - t) / 10
+    print(f"chunk_reads={chunk}: map_batch {dt*1e3:.2f} ms ({1e6/dt/1e6:.0f} M reads/s); coverage fetch {dc*1e3:.2f} ms")
