@@ -72,7 +72,7 @@ struct gq_index {
   DevBuf<uint32_t> st_off, st_words, st_count, pool, small;  // small: [pool_used, n_overflow, n_cov_overflow]
   DevBuf<uint32_t> overflow_list, cov_overflow_list, mapped_list;
   DevBuf<uint32_t> seed_rec, pre_off, pre_cnt, live_list;  // seed pass (SeedOut)
-  uint32_t seed_recs_per_read = 8;
+  uint32_t seed_recs_per_read = 8;  // set from the index in gq_index_build: ~1.5 x mean states per indexed k-mer
   bool use_seed_pass = true;
   DevBuf<uint32_t> arena, big_arena;
   cudaStream_t copy_stream = nullptr;
@@ -324,13 +324,19 @@ static void do_map(gq_index* ix, const uint8_t* h_bases = nullptr, const uint64_
   // list-mode re-runs below hand out work from counter slot [9] and append to the (already consumed)
   // mapped list of slice 0
   uint64_t rerun = 0;
-  // ---- overflow re-runs: same kernels, fewer threads, much larger per-thread arenas -------------
-  uint32_t big_words = ix->big_arena_words;
+  // ---- overflow re-runs: same kernels in list mode (strands seeded inside the search kernel) ----
+  // A full seed-record pool is a capacity miss, not a deep search: those strands are re-run with the
+  // normal arenas and lane count (and the pool is enlarged for the next batch). Arena / state-pool
+  // overflows are re-run with fewer lanes and much larger per-lane arenas (x4 per further retry).
+  uint32_t big_words = ix->big_arena_words, big_threads = ix->big_threads;
+  bool seed_pool_miss = small[3] > ix->seed_rec.cap / 4;
+  if (seed_pool_miss) ix->seed_recs_per_read = (uint32_t)((double)small[3] / n * 1.25) + 4;
   int guard = 0;
   while (small[1] > 0) {
     uint32_t n_list = small[1];
     rerun += n_list;
     if (++guard > 12) throw std::runtime_error("search state arena overflow persists at the largest arena size");
+    const bool normal_cfg = seed_pool_miss && guard == 1;
     if (small[0] > ix->pool.cap) {  // the pool ran out: grow it, keeping what was written
       size_t ncap = std::min<size_t>(std::max<size_t>((size_t)small[0] * 2, ix->pool.cap * 2), 0xFFFFFFF0ull);
       if (ncap <= ix->pool.cap) throw std::runtime_error("final-state pool exceeds 2^32 words; use smaller batches");
@@ -346,27 +352,39 @@ static void do_map(gq_index* ix, const uint8_t* h_bases = nullptr, const uint64_
       o.pool = np;
       o.pool_cap = (uint32_t)ncap;
     }
-    uint32_t bt = std::min<uint32_t>(ix->big_threads, ((n_list + 255) / 256) * 256);
-    ix->big_arena.reserve((size_t)bt * big_words);
+    uint32_t bt, aw;
+    uint32_t* ar;
+    if (normal_cfg) {
+      bt = std::min<uint32_t>(ix->n_threads, std::max<uint32_t>(256, ((n_list / 4 + 255) / 256) * 256));
+      aw = ix->arena_words;
+      ix->arena.reserve((size_t)std::max(bt, threads2) * aw);
+      ar = ix->arena.p;
+    } else {
+      bt = std::min<uint32_t>(big_threads, ((n_list + 255) / 256) * 256);
+      aw = big_words;
+      ix->big_arena.reserve((size_t)bt * big_words);
+      ar = ix->big_arena.p;
+    }
     // the kernel appends to the same list while reading it: read from a copy
     DevBuf<uint32_t> list;
     list.reserve(n_list);
     CUDA_OK(cudaMemcpyAsync(list.p, ix->overflow_list.p, (size_t)n_list * 4, cudaMemcpyDeviceToDevice, st));
     CUDA_OK(cudaMemsetAsync(ix->small.p + 1, 0, 4, st));
     CUDA_OK(cudaMemsetAsync(ix->small.p + 9, 0, 4, st));  // work counter of the list run
-    gq::launch_search(ix->dv, b, o, ix->big_arena.p, big_words, bt, list.p, n_list, ix->super_in_smem, ix->rf_thresh, ix->ev_thresh, st, ix->leave_opt, ix->wait_opt);
+    gq::launch_search(ix->dv, b, o, ar, aw, bt, list.p, n_list, ix->super_in_smem, ix->rf_thresh, ix->ev_thresh, st,
+                      ix->leave_opt, ix->wait_opt);
     gq::launch_classify(ix->dv, b, o, list.p, n_list, st);
     ++launches;
-    gq::launch_coverage(ix->dv, b, o, c, ix->big_arena.p, big_words, bt, list.p, n_list, ix->cov_overflow_list.p,
-                        ix->small.p + 2, st);
+    gq::launch_coverage(ix->dv, b, o, c, ar, aw, std::min<uint32_t>(bt, threads2), list.p, n_list,
+                        ix->cov_overflow_list.p, ix->small.p + 2, st);
     launches += 2;
     CUDA_OK(cudaMemcpyAsync(small, ix->small.p, 16, cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
     CUDA_OK(cudaGetLastError());
     list.release();
-    if (small[1] > 0) {
+    if (small[1] > 0 && !normal_cfg) {
       big_words *= 4;
-      ix->big_threads = std::max<uint32_t>(256, ix->big_threads / 4);
+      big_threads = std::max<uint32_t>(256, big_threads / 4);
     }
   }
   guard = 0;
@@ -374,7 +392,7 @@ static void do_map(gq_index* ix, const uint8_t* h_bases = nullptr, const uint64_
     uint32_t n_list = small[2];
     rerun += n_list;
     if (++guard > 12) throw std::runtime_error("coverage scratch overflow persists at the largest arena size");
-    uint32_t bt = std::min<uint32_t>(ix->big_threads, ((n_list + 255) / 256) * 256);
+    uint32_t bt = std::min<uint32_t>(big_threads, ((n_list + 255) / 256) * 256);
     ix->big_arena.reserve((size_t)bt * big_words);
     DevBuf<uint32_t> list;
     list.reserve(n_list);
@@ -389,7 +407,7 @@ static void do_map(gq_index* ix, const uint8_t* h_bases = nullptr, const uint64_
     list.release();
     if (small[2] > 0) {
       big_words *= 4;
-      ix->big_threads = std::max<uint32_t>(256, ix->big_threads / 4);
+      big_threads = std::max<uint32_t>(256, big_threads / 4);
     }
   }
   gq::launch_stats(ix->status.p, ix->len.p, n, ix->stats.p, st);
@@ -438,6 +456,12 @@ int gq_index_build(const uint32_t* prg, uint64_t n_symbols, uint32_t kmer_size, 
   ix->stream = ix->own_stream;
   for (auto& e : ix->ev) CUDA_OK(cudaEventCreate(&e));
   upload_index(ix);
+  {  // seed records per read: ~1.5 x the mean number of states of an indexed k-mer, both strands
+    uint64_t present = 0;
+    for (uint32_t w : ix->h.kmer_bits) present += __builtin_popcount(w);
+    double mean = present ? (double)ix->h.kmer_off.back() / (double)present : 1.0;
+    ix->seed_recs_per_read = (uint32_t)(2.0 * (1.5 * mean + 2.0)) + 1;
+  }
   alloc_coverage(ix);
   reset_coverage(ix);
   *out = ix;
