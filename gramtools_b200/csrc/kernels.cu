@@ -97,6 +97,30 @@ constexpr int kHotUnroll = GQ_HOT_UNROLL;
 #ifndef GQ_SEARCH_MIN_BLOCKS
 #define GQ_SEARCH_MIN_BLOCKS 5  // 48 registers, 1280 resident lanes per SM
 #endif
+// k-mer filter of one strand by a whole warp: lane j tests the k-mers starting at bases j, j+32, ... (a
+// k-mer code is a bit-field of the packed read, see classify_strand); a ballot ends the strand at the
+// first round that finds a missing k-mer. Must be called by all 32 lanes with uniform arguments.
+__device__ __forceinline__ bool warp_any_kmer_missing(const IndexView& v, const uint32_t* w, uint32_t L, bool rc,
+                                                      uint32_t lane) {
+  const uint32_t k = v.k;
+  const uint32_t mask = (k == 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
+  const uint32_t n_words = (L + 15) >> 4, n_kmers = L - k + 1;
+  bool missing = false;
+  for (uint32_t j0 = 0; j0 < n_kmers && !missing; j0 += 32) {
+    const uint32_t j = j0 + lane;
+    bool absent = false;
+    if (j < n_kmers) {
+      const uint32_t wi = j >> 4, sh = 2 * (j & 15u);
+      const uint32_t lo = __ldg(w + wi), hi = (wi + 1 < n_words) ? __ldg(w + wi + 1) : 0u;
+      const uint32_t win = __funnelshift_r(lo, hi, sh);
+      const uint32_t code = rc ? (pair_reverse32(~win) >> (32 - 2 * k)) : (win & mask);
+      absent = !((__ldg(v.kmer_bits + (code >> 5)) >> (code & 31u)) & 1u);
+    }
+    missing = __any_sync(0xFFFFFFFFu, absent);
+  }
+  return missing;
+}
+
 // Seed pass: thread per strand (see preseed_strand). Superblock counters come from shared memory when
 // they fit, like in the search kernel.
 template <bool SUPER_SMEM>
@@ -165,6 +189,8 @@ __global__ void __launch_bounds__(256)
       alive |= __reduce_or_sync(full, survived ? (1u << owner) : 0u);
     }
     if (ns) {
+      // (classifying the dead strands right here was measured: slower than the separate warp-per-strand
+      // classify_kernel, which hides the dependent loads behind many more resident warps)
       if ((alive >> lane) & 1u) pre.live_list[gq_atomic_inc_aggregated(pre.n_live)] = strand;
       else o.status[strand] = ST_UNCLASSIFIED;
     }
@@ -291,8 +317,6 @@ __global__ void __launch_bounds__(256)
   const uint32_t n = list ? n_list : 2 * (b.read_end - b.read_begin);
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-  const uint32_t k = v.k;
-  const uint32_t mask = (k == 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
   for (uint32_t base = warp * 32; base < n; base += n_warps * 32) {
     const uint32_t i = base + lane;
     const uint32_t my_strand = i < n ? (list ? list[i] : 2 * b.read_begin + i) : 0;
@@ -305,20 +329,7 @@ __global__ void __launch_bounds__(256)
       const uint32_t L = b.len[r];
       const uint32_t* w = b.packed + b.word_off[r];
       const bool rc = (strand & 1u) != 0;
-      const uint32_t n_words = (L + 15) >> 4, n_kmers = L - k + 1;
-      bool missing = false;
-      for (uint32_t j0 = 0; j0 < n_kmers && !missing; j0 += 32) {
-        const uint32_t j = j0 + lane;
-        bool absent = false;
-        if (j < n_kmers) {
-          const uint32_t wi = j >> 4, sh = 2 * (j & 15u);
-          const uint32_t lo = __ldg(w + wi), hi = (wi + 1 < n_words) ? __ldg(w + wi + 1) : 0u;
-          const uint32_t win = __funnelshift_r(lo, hi, sh);
-          const uint32_t code = rc ? (pair_reverse32(~win) >> (32 - 2 * k)) : (win & mask);
-          absent = !((__ldg(v.kmer_bits + (code >> 5)) >> (code & 31u)) & 1u);
-        }
-        missing = __any_sync(0xFFFFFFFFu, absent);
-      }
+      const bool missing = warp_any_kmer_missing(v, w, L, rc, lane);
       if (lane == 0) o.status[strand] = missing ? ST_MISSING_KMER : ST_NO_EXTENSION;
     }
   }
