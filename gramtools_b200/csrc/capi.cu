@@ -119,6 +119,8 @@ static void upload_index(gq_index* ix) {
   v.tm_odd = upload(ix, h.tm_odd);
   v.tm_even_off = upload(ix, h.tm_even_off);
   v.tm_even = upload(ix, h.tm_even);
+  v.entry_next = upload(ix, h.entry_next);
+  v.site_snp = upload(ix, h.site_snp);
   v.sa = upload(ix, h.sa);
   v.pos2node = upload(ix, h.pos2node);
   v.nodes = upload(ix, h.nodes);

@@ -24,6 +24,7 @@ namespace gq {
 constexpr uint32_t kBlkShift = 6;     // 64 BWT positions per rank block
 constexpr uint32_t kSuperShift = 15;  // 32768 positions per superblock (block counts fit u16)
 constexpr uint32_t kNoAllele = 0xFFFFFFFFu;
+constexpr uint32_t kNotSnp = 0xFFFFFFFEu;
 
 // 32-byte rank block = one DRAM/L2 sector, fetched with a single 256-bit load.
 // Symbol at position j of the block: code = p0 | p1<<1 for A,C,G,T (p2 = 0); p2 = 1 marks a
@@ -67,6 +68,10 @@ struct IndexView {
   const uint32_t* tm_odd;      // target_map[odd marker]: id of the marker just left of the site, or 0
   const uint32_t* tm_even_off; // CSR over target_map[even marker]
   const uint32_t* tm_even;     // 2 per entry: (marker id, direct deletion allele)
+  const uint32_t* entry_next;  // 8 per slot: SA interval (lo,hi) after entering the site AND consuming base c
+                               // (c = 0..3; lo > hi = no allele ends in c); valid for 'simple' entries only
+  const uint32_t* site_snp;    // per slot: kNotSnp, or one byte per base c: the allele (0xFF none) whose single
+                               // base is c — a site of distinct 1-base alleles with nothing adjacent
   // end-of-read lookups
   const uint32_t* sa;
   const uint32_t* pos2node;

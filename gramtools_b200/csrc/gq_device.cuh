@@ -450,9 +450,47 @@ GQ_DEV inline void lane_event_scan(Lane& ln, const IndexView& v, const SearchOut
         T[2 * nt] = marker;
         T[2 * nt + 1] = allele;
         ++nt;
-      } else {  // enter the site whose end marker this is
+      } else {
+        // Enter the site whose end marker this is, and consume the next base right away: the entered
+        // state is a committed jump state (extended without another scan), so entry + extension is a
+        // table lookup. For a site of distinct single-base alleles the exit that follows is folded in
+        // as well (entry, allele base, exit = one event) unless the read ends inside the site.
+        const uint32_t slot = (marker - 6) >> 1;
+        const uint32_t c = ln.rd(ln.pos - 1);
+        const uint32_t snp = GQ_LDG(v.site_snp + slot);
+        if (snp != kNotSnp && ln.pos >= 2) {
+          const uint32_t a = (snp >> (8 * c)) & 0xFFu;
+          if (a == 0xFFu) {
+            ln.state = LS_EV_POP;
+            return;
+          }
+          for (uint32_t j = ng; j-- > 0;) T[2 * nt + 2 + j] = T[2 * nt + j];  // open sites stay behind T (room checked above)
+          T[2 * nt] = marker - 1;
+          T[2 * nt + 1] = a;
+          t[3] = (nt + 1) | (ng << 16);
+          ln.lo = ln.hi = GQ_LDG(v.site_sa + slot);
+          ln.pos -= 1;
+          ln.kind = K_READY;
+          ln.state = LS_RUN;
+          return;
+        }
         T[2 * nt + ng] = marker - 1;
         ++ng;
+        t[3] = nt | (ng << 16);
+        const uint32_t nlo = GQ_LDG(v.entry_next + 8 * slot + 2 * c), nhi = GQ_LDG(v.entry_next + 8 * slot + 2 * c + 1);
+        if (nhi + 1 <= nlo) {  // no allele ends in c
+          ln.state = LS_EV_POP;
+          return;
+        }
+        ln.lo = nlo;
+        ln.hi = nhi;
+        ln.kind = K_SCAN;
+        ln.state = (nlo == nhi) ? LS_RUN : LS_RUNW;
+        if (--ln.pos == 0) {
+          lane_writeback(ln, K_SCAN);
+          ln.state = LS_EV_TOP;
+        }
+        return;
       }
       t[3] = nt | (ng << 16);
       ln.lo = jlo;

@@ -27,6 +27,8 @@ IndexView HostIndex::view() const {
   v.tm_odd = tm_odd.data();
   v.tm_even_off = tm_even_off.data();
   v.tm_even = tm_even.data();
+  v.entry_next = entry_next.data();
+  v.site_snp = site_snp.data();
   v.sa = sa.data();
   v.pos2node = pos2node.data();
   v.nodes = nodes.data();
@@ -89,6 +91,7 @@ void build_graph(HostIndex& ix, std::vector<uint32_t>& hit_marker, std::vector<u
   ix.tm_odd.assign(S, 0);
   ix.n_alleles.assign(S, 0);
   ix.site_start_node.assign(S, 0);
+  ix.site_start_pos.assign(S, 0);
   std::vector<std::vector<uint32_t>> tm_even(S);
   ix.pos2node.assign(L, 0);
   hit_marker.assign(L, 0);
@@ -158,6 +161,7 @@ void build_graph(HostIndex& ix, std::vector<uint32_t>& hit_marker, std::vector<u
         uint32_t s = (m - 5) / 2;
         uint32_t sn = new_node(m, -1, p), en = new_node(m, -1, p);
         ix.site_start_node[s] = sn;
+        ix.site_start_pos[s] = p;
         site_end_node[s] = en;
         wire(sn);
         back = sn;
@@ -345,6 +349,39 @@ void build_fm(HostIndex& ix, const std::vector<uint32_t>& hit_marker, const std:
     }
   }
   if (ix.marker_hit.empty()) ix.marker_hit.assign(4, 0);
+
+  // ---- pre-resolved site crossings (used by lane_event_scan) ----
+  // entry_next[s][c]: interval after entering site s from its right end and consuming base c
+  // (entering_site_search_state + base_next_sa_interval); site_snp[s]: the whole crossing of a site
+  // made of distinct single-base alleles with no marker adjacent on either side.
+  auto rank_c = [&](uint32_t c, uint32_t i) {
+    const RankBlk& b = ix.rank_blk[i >> kBlkShift];
+    return rank_in_blk(b, ix.super_cnt.data() + 4 * (size_t)((i >> kBlkShift) >> (kSuperShift - kBlkShift)), c, i);
+  };
+  ix.entry_next.assign(8 * (size_t)S + 8, 0);
+  ix.site_snp.assign((size_t)S + 1, kNotSnp);
+  for (uint32_t s = 0; s < S; ++s) {
+    if (ix.n_alleles[s] == 0) continue;
+    for (uint32_t c = 0; c < 4; ++c) {
+      uint32_t r0 = rank_c(c, ix.allele_iv[2 * s]), r1 = rank_c(c, ix.allele_iv[2 * s + 1] + 1);
+      ix.entry_next[8 * (size_t)s + 2 * c] = r0;
+      ix.entry_next[8 * (size_t)s + 2 * c + 1] = r1 - 1;  // r1 == r0 -> hi = lo - 1: empty
+    }
+    if (ix.tm_odd[s] != 0 || ix.tm_even_off[s + 1] != ix.tm_even_off[s]) continue;
+    const uint32_t p0 = ix.site_start_pos[s], na = ix.n_alleles[s];
+    if ((size_t)p0 + 2 * na >= prg.size() + 1) continue;
+    uint32_t tab = 0xFFFFFFFFu;
+    bool ok = true;
+    for (uint32_t a = 0; a < na && ok; ++a) {
+      uint32_t base = prg[p0 + 1 + 2 * a], sep = prg[p0 + 2 + 2 * a];
+      ok = base >= 1 && base <= 4 && sep == 6 + 2 * s && a < 0xFF;
+      if (!ok) break;
+      uint32_t c = base - 1;
+      if (((tab >> (8 * c)) & 0xFFu) != 0xFFu) ok = false;  // two alleles with the same base
+      else tab = (tab & ~(0xFFu << (8 * c))) | (a << (8 * c));
+    }
+    if (ok) ix.site_snp[s] = tab;
+  }
 }
 
 // ---- all-k-mers index (reference: src/build/kmer_index/build.cpp:18-148) ---------------------

@@ -27,7 +27,8 @@ struct HostIndex {
   // sites
   uint32_t n_slots = 0;   // (max site id - 5)/2 + 1
   uint32_t n_sites = 0;   // sites actually present
-  std::vector<uint32_t> site_sa, allele_iv, par, tm_odd, tm_even_off, tm_even;
+  std::vector<uint32_t> site_sa, allele_iv, par, tm_odd, tm_even_off, tm_even, entry_next, site_snp;
+  std::vector<uint32_t> site_start_pos;  // PRG position of the site-entry marker
   std::vector<uint32_t> n_alleles;   // per slot (0 if the slot is unused)
   std::vector<uint32_t> allele_off;  // n_slots + 1: prefix sum of n_alleles (allele_sum layout)
   bool is_nested = false;
