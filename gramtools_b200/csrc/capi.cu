@@ -71,7 +71,7 @@ struct gq_index {
   DevBuf<uint8_t> status;
   DevBuf<uint32_t> st_off, st_words, st_count, pool, small;  // small: [pool_used, n_overflow, n_cov_overflow]
   DevBuf<uint32_t> overflow_list, cov_overflow_list, mapped_list;
-  DevBuf<uint32_t> seed_rec, pre_off, pre_cnt, live_list;  // seed pass (SeedOut)
+  DevBuf<uint32_t> seed_rec, pre_hdr, live_list;  // seed pass (SeedOut)
   uint32_t seed_recs_per_read = 8;  // set from the index in gq_index_build: ~1.5 x mean states per indexed k-mer
   bool use_seed_pass = true;
   DevBuf<uint32_t> arena, big_arena;
@@ -246,10 +246,9 @@ static void do_map(gq_index* ix, const uint8_t* h_bases = nullptr, const uint64_
   ix->cov_overflow_list.reserve(2 * (size_t)n);
   ix->mapped_list.reserve(2 * (size_t)n);
   ix->small.reserve(8 + 4 * 64);
-  ix->pre_off.reserve(2 * (size_t)n);
-  ix->pre_cnt.reserve(2 * (size_t)n);
+  ix->pre_hdr.reserve(8 * (size_t)n);
   ix->live_list.reserve(2 * (size_t)n);
-  ix->seed_rec.reserve(4 * std::max<size_t>((size_t)n * ix->seed_recs_per_read, 1 << 16));
+  ix->seed_rec.reserve(8 * std::max<size_t>((size_t)n * ix->seed_recs_per_read, 1 << 16));
   size_t pool_need = std::max<size_t>((size_t)n * ix->pool_words_per_read, 1 << 16);
   pool_need = std::min<size_t>(pool_need, 0xFFFFFFF0ull);
   ix->pool.reserve(pool_need);
@@ -296,7 +295,7 @@ static void do_map(gq_index* ix, const uint8_t* h_bases = nullptr, const uint64_
     oc.mapped_list = ix->mapped_list.p + 2 * (size_t)chunks[i].r0;
     oc.n_mapped = ix->small.p + 8 + 4 * i;
     oc.work_counter = ix->small.p + 9 + 4 * i;
-    gq::SeedOut pre{ix->seed_rec.p, (uint32_t)(ix->seed_rec.cap / 4), ix->small.p + 3, ix->pre_off.p, ix->pre_cnt.p,
+    gq::SeedOut pre{ix->seed_rec.p, (uint32_t)(ix->seed_rec.cap / 8), ix->small.p + 3, ix->pre_hdr.p,
                     ix->live_list.p + 2 * (size_t)chunks[i].r0, ix->small.p + 10 + 4 * i};
     if (ix->use_seed_pass) {
       gq::launch_seed(ix->dv, bc, oc, pre, st);
@@ -331,7 +330,7 @@ static void do_map(gq_index* ix, const uint8_t* h_bases = nullptr, const uint64_
   // normal arenas and lane count (and the pool is enlarged for the next batch). Arena / state-pool
   // overflows are re-run with fewer lanes and much larger per-lane arenas (x4 per further retry).
   uint32_t big_words = ix->big_arena_words, big_threads = ix->big_threads;
-  bool seed_pool_miss = small[3] > ix->seed_rec.cap / 4;
+  bool seed_pool_miss = small[3] > ix->seed_rec.cap / 8;
   if (seed_pool_miss) ix->seed_recs_per_read = (uint32_t)((double)small[3] / n * 1.25) + 4;
   int guard = 0;
   while (small[1] > 0) {
@@ -503,8 +502,7 @@ int gq_index_destroy(gq_index* ix) {
   ix->cov_overflow_list.release();
   ix->mapped_list.release();
   ix->seed_rec.release();
-  ix->pre_off.release();
-  ix->pre_cnt.release();
+  ix->pre_hdr.release();
   ix->live_list.release();
   ix->arena.release();
   ix->big_arena.release();

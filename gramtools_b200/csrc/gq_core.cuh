@@ -56,8 +56,9 @@ struct IndexView {
   const RankBlk* rank_blk;
   const uint32_t* super_cnt;   // 4 per superblock: C[c] + occurrences of A,C,G,T before the superblock
   const uint32_t* mrank_blk;   // markers in BWT[0, block start)
-  const uint32_t* marker_hit;  // 4 per BWT marker occurrence: (marker', allele, lo, hi): the jump target and, when
-                               // no marker is adjacent on the far side, the SA interval after the jump (else lo = ~0)
+  const uint32_t* marker_hit;  // 8 per BWT marker occurrence (one 32 B sector): (marker', allele, lo, hi, snp, site_sa):
+                               // the jump target; when no marker is adjacent on the far side the SA interval after
+                               // the jump (else lo = ~0); for such entries the site's SNP table and C[site]
   uint32_t c_base[4];          // first SA index of suffixes starting with A,C,G,T
   // per site slot s = (site_id - 5) / 2
   uint32_t n_slots;
@@ -273,7 +274,7 @@ GQ_HD void scan_markers(Stack& s, const IndexView& v, uint32_t pos, uint32_t lo,
 #endif
       m &= m - 1;
       uint32_t mr = mr0 + (bit ? (uint32_t)popc64(all & (~0ull >> (64 - bit))) : 0u);
-      uint32_t marker = v.marker_hit[4 * mr], allele = v.marker_hit[4 * mr + 1];
+      uint32_t marker = v.marker_hit[8 * mr], allele = v.marker_hit[8 * mr + 1];
       if (marker == 0) continue;
       // copy of the scanned state (always at base_top) with the locus in the header
       uint32_t* src = s.mem + base_top;

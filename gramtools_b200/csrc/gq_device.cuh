@@ -205,6 +205,7 @@ struct Lane {
   uint32_t arena_words;
   // top entry cached in registers while state == LS_RUN
   uint32_t pos, lo, hi, kind;
+  uint32_t mr;  // LS_EV_SCAN of a width-1 interval: rank of the marker at BWT[lo] among all BWT markers
 };
 
 GQ_DEV inline void lane_writeback(Lane& ln, uint32_t kind) {
@@ -338,7 +339,12 @@ GQ_DEV inline void lane_step(Lane& ln, const IndexView& v, SuperPtr super_c) {
   const uint64_t x0 = (c & 1u) ? 0ull : ~0ull, x1 = (c & 2u) ? 0ull : ~0ull;
   const uint64_t bit = 1ull << (lo & 63u);
   if (B0.p2 & bit) {  // not a nucleotide: marker -> jump (unless already scanned), sentinel -> dead
-    ln.state = ((B0.p0 & bit) && ln.kind == K_SCAN) ? LS_EV_SCAN : LS_EV_POP;
+    if ((B0.p0 & bit) && ln.kind == K_SCAN) {
+      // start the marker-rank load now: it completes while the lane waits for its event batch
+      ln.mr = GQ_LDG(v.mrank_blk + b0) + (uint32_t)popc64(B0.p2 & B0.p0 & (bit - 1));
+      ln.state = LS_EV_SCAN;
+    } else
+      ln.state = LS_EV_POP;
     return;
   }
   const uint64_t m = ~B0.p2 & (B0.p0 ^ x0) & (B0.p1 ^ x1);
@@ -374,6 +380,7 @@ GQ_DEV inline void lane_step_wide(Lane& ln, const IndexView& v, SuperPtr super_c
       return;
     }
     if (mk) {
+      ln.mr = kNoAllele;  // interval state: the event path computes marker ranks itself
       ln.state = LS_EV_SCAN;
       return;
     }
@@ -420,12 +427,16 @@ GQ_DEV inline void lane_event_scan(Lane& ln, const IndexView& v, const SearchOut
   if (ln.lo == ln.hi) {
     // Single suffix preceded by a marker: the un-jumped state cannot be extended by any base (its only
     // BWT symbol is the marker), so the jump replaces it in place instead of being pushed above it.
-    const uint32_t blk = ln.lo >> kBlkShift, bit = ln.lo & 63u;
-    const RankBlk B = load_blk(v.rank_blk + blk);
-    const uint64_t all = B.p2 & B.p0;
-    const uint32_t mr = GQ_LDG(v.mrank_blk + blk) + (uint32_t)popc64(all & ((1ull << bit) - 1));
-    const uint32_t marker = GQ_LDG(v.marker_hit + 4 * mr), allele = GQ_LDG(v.marker_hit + 4 * mr + 1);
-    const uint32_t jlo = GQ_LDG(v.marker_hit + 4 * mr + 2), jhi = GQ_LDG(v.marker_hit + 4 * mr + 3);
+    uint32_t mr = ln.mr;
+    if (mr == kNoAllele) {  // width-1 interval reached through the wide step
+      const uint32_t blk = ln.lo >> kBlkShift, bit = ln.lo & 63u;
+      const RankBlk B = load_blk(v.rank_blk + blk);
+      mr = GQ_LDG(v.mrank_blk + blk) + (uint32_t)popc64(B.p2 & B.p0 & ((1ull << bit) - 1));
+    }
+    // one 32 B sector: jump target, post-jump interval, SNP table + C[site] of a simple entry
+    const uint32_t* jr = v.marker_hit + 8 * (size_t)mr;
+    const uint32_t marker = GQ_LDG(jr), allele = GQ_LDG(jr + 1), jlo = GQ_LDG(jr + 2), jhi = GQ_LDG(jr + 3);
+    const uint32_t snp = GQ_LDG(jr + 4), entered_site_sa = GQ_LDG(jr + 5);
     if (marker == 0) {
       ln.state = LS_EV_POP;
       return;
@@ -457,7 +468,6 @@ GQ_DEV inline void lane_event_scan(Lane& ln, const IndexView& v, const SearchOut
         // as well (entry, allele base, exit = one event) unless the read ends inside the site.
         const uint32_t slot = (marker - 6) >> 1;
         const uint32_t c = ln.rd(ln.pos - 1);
-        const uint32_t snp = GQ_LDG(v.site_snp + slot);
         if (snp != kNotSnp && ln.pos >= 2) {
           const uint32_t a = (snp >> (8 * c)) & 0xFFu;
           if (a == 0xFFu) {
@@ -468,7 +478,7 @@ GQ_DEV inline void lane_event_scan(Lane& ln, const IndexView& v, const SearchOut
           T[2 * nt] = marker - 1;
           T[2 * nt + 1] = a;
           t[3] = (nt + 1) | (ng << 16);
-          ln.lo = ln.hi = GQ_LDG(v.site_sa + slot);
+          ln.lo = ln.hi = entered_site_sa;
           ln.pos -= 1;
           ln.kind = K_READY;
           ln.state = LS_RUN;
@@ -577,7 +587,7 @@ GQ_DEV inline uint32_t preseed_lookup(const IndexView& v, const BatchView& b, co
   const uint32_t r = strand >> 1;
   const uint32_t L = b.len[r];
   const uint32_t k = v.k;
-  pre.pre_cnt[strand] = 0;
+  pre.pre_hdr[4 * (size_t)strand + 1] = 0;
   if (L == 0) {  // non-ACGT read, emptied by the encoder: skipped (quasimap.cpp:108-113)
     o.status[strand] = ST_SKIPPED;
     return 0;
@@ -625,10 +635,17 @@ GQ_DEV inline bool preseed_one(const IndexView& v, SuperPtr super_c, const uint3
     else lane_step_wide(ln, v, super_c);
   }
   const bool alive = ln.state != LS_EV_POP;
-  d[0] = j;
-  d[1] = alive ? (ln.pos | (ln.kind << 28)) : kDeadSeed;
-  d[2] = ln.lo;
-  d[3] = ln.hi;
+  d[0] = alive ? (ln.pos | (ln.kind << 28)) : kDeadSeed;
+  if (alive) {
+    d[1] = ln.lo;
+    d[2] = ln.hi;
+    d[3] = ks.counts;
+    d[4] = ks.path_off;
+    const uint32_t pw = 2 * (ks.counts & 0xFFFFu) + (ks.counts >> 16);
+    d[5] = pw > 0 ? GQ_LDG(v.kmer_paths + ks.path_off) : 0;
+    d[6] = pw > 1 ? GQ_LDG(v.kmer_paths + ks.path_off + 1) : 0;
+    d[7] = j;
+  }
   return alive;
 }
 
@@ -645,9 +662,12 @@ GQ_DEV inline void preseed_extend(const IndexView& v, SuperPtr super_c, const Ba
   bool any = false;
   for (uint32_t t = 0; t < n; ++t)
     any |= preseed_one(v, super_c, b.packed + b.word_off[r], b.len[r], (strand & 1u) != 0, sb + t,
-                       pre.rec + 4 * (size_t)(base + t));
-  pre.pre_off[strand] = base;
-  pre.pre_cnt[strand] = n;
+                       pre.rec + 8 * (size_t)(base + t));
+  uint32_t* h = pre.pre_hdr + 4 * (size_t)strand;
+  h[0] = base;
+  h[1] = n;
+  h[2] = b.len[r];
+  h[3] = b.word_off[r];
   if (!any) o.status[strand] = ST_UNCLASSIFIED;
   else pre.live_list[gq_atomic_inc_aggregated(pre.n_live)] = strand;
 }
@@ -660,36 +680,44 @@ GQ_DEV inline void preseed_strand(const IndexView& v, SuperPtr super_c, const Ba
   if (n) preseed_extend(v, super_c, b, o, pre, strand, sb, n, gq_atomic_add(pre.used, n));
 }
 
-// Start a pre-seeded strand on this lane: its surviving seed states become the initial stack.
+// Start a pre-seeded strand on this lane: its surviving seed states become the initial stack. Everything
+// comes from the strand header + its seed records (two dependent loads); the k-mer index is only
+// touched for seeds whose path is longer than the two words kept inline.
 GQ_DEV inline void lane_refill_pre(Lane& ln, const IndexView& v, const BatchView& b, const SearchOut& o,
                                    const SeedOut& pre, uint32_t strand, uint32_t* arena, uint32_t arena_words) {
-  const uint32_t r = strand >> 1;
+  const uint32_t* h = pre.pre_hdr + 4 * (size_t)strand;
+  const uint32_t p0 = GQ_LDG(h), n = GQ_LDG(h + 1), L = GQ_LDG(h + 2), woff = GQ_LDG(h + 3);
   ln.strand = strand;
-  ln.rd = ReadCursor{b.packed + b.word_off[r], b.len[r], (strand & 1u) != 0, 0xFFFFFFFFu, 0};
+  ln.rd = ReadCursor{b.packed + woff, L, (strand & 1u) != 0, 0xFFFFFFFFu, 0};
   ln.s.mem = arena;
   ln.s.limit = arena_words;
   ln.s.overflow = false;
   ln.s.top = kNoAllele;
   ln.n_states = 0;
   ln.arena_words = arena_words;
-  const uint32_t p0 = pre.pre_off[strand], n = pre.pre_cnt[strand];
   uint32_t sp = 0;
   for (uint32_t i = 0; i < n; ++i) {
-    const uint32_t* rec = pre.rec + 4 * (size_t)(p0 + i);
-    if (rec[1] == kDeadSeed) continue;
-    const KmerState ks = v.kmer_states[rec[0]];
-    const uint32_t words = entry_words(ks.counts);
+    const uint32_t* rec = pre.rec + 8 * (size_t)(p0 + i);
+    const uint32_t w0 = GQ_LDG(rec);
+    if (w0 == kDeadSeed) continue;
+    const uint32_t counts = GQ_LDG(rec + 3);
+    const uint32_t words = entry_words(counts);
     if (sp + words + 3 > ln.s.limit) {
       ln.s.overflow = true;
       break;
     }
     uint32_t* t = ln.s.mem + sp;
-    t[0] = rec[1];
-    t[1] = rec[2];
-    t[2] = rec[3];
-    t[3] = ks.counts;
+    t[0] = w0;
+    t[1] = GQ_LDG(rec + 1);
+    t[2] = GQ_LDG(rec + 2);
+    t[3] = counts;
     t[4] = ln.s.top;
-    for (uint32_t w = kHdr; w < words; ++w) t[w] = GQ_LDG(v.kmer_paths + ks.path_off + (w - kHdr));
+    if (words > kHdr) t[kHdr] = GQ_LDG(rec + 5);
+    if (words > kHdr + 1) t[kHdr + 1] = GQ_LDG(rec + 6);
+    if (words > kHdr + 2) {
+      const uint32_t path_off = GQ_LDG(rec + 4);
+      for (uint32_t w = kHdr + 2; w < words; ++w) t[w] = GQ_LDG(v.kmer_paths + path_off + (w - kHdr));
+    }
     ln.s.top = sp;
     sp += words;
   }
@@ -745,7 +773,7 @@ GQ_DEV inline void map_strand(const IndexView& v, const uint32_t* super_cnt, con
   } else {
     preseed_strand(v, super_cnt, b, o, pre, strand);
     if (o.status[strand] == ST_OVERFLOW) return;
-    if (pre.pre_cnt[strand]) lane_refill_pre(ln, v, b, o, pre, strand, arena, arena_words);
+    if (pre.pre_hdr[4 * (size_t)strand + 1]) lane_refill_pre(ln, v, b, o, pre, strand, arena, arena_words);
   }
   while (ln.state != LS_IDLE) {
     if (ln.state == LS_RUN) lane_step(ln, v, super_cnt);

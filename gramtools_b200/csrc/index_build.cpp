@@ -345,10 +345,16 @@ void build_fm(HostIndex& ix, const std::vector<uint32_t>& hit_marker, const std:
         ix.marker_hit.push_back(ha);
         ix.marker_hit.push_back(jlo);
         ix.marker_hit.push_back(jhi);
+        // words 4,5 (SNP crossing table, site_sa of the entered site) are filled once the per-site
+        // tables exist; 6,7 pad the record to one 32 B sector
+        ix.marker_hit.push_back(kNotSnp);
+        ix.marker_hit.push_back(0);
+        ix.marker_hit.push_back(0);
+        ix.marker_hit.push_back(0);
       }
     }
   }
-  if (ix.marker_hit.empty()) ix.marker_hit.assign(4, 0);
+  if (ix.marker_hit.empty()) ix.marker_hit.assign(8, 0);
 
   // ---- pre-resolved site crossings (used by lane_event_scan) ----
   // entry_next[s][c]: interval after entering site s from its right end and consuming base c
@@ -381,6 +387,14 @@ void build_fm(HostIndex& ix, const std::vector<uint32_t>& hit_marker, const std:
       else tab = (tab & ~(0xFFu << (8 * c))) | (a << (8 * c));
     }
     if (ok) ix.site_snp[s] = tab;
+  }
+  for (size_t m = 0; m + 7 < ix.marker_hit.size(); m += 8) {
+    uint32_t hm = ix.marker_hit[m];
+    if (hm > 4 && (hm & 1u) == 0 && ix.marker_hit[m + 2] != kNoAllele) {  // simple entry
+      uint32_t slot = (hm - 6) / 2;
+      ix.marker_hit[m + 4] = ix.site_snp[slot];
+      ix.marker_hit[m + 5] = ix.site_sa[slot];
+    }
   }
 }
 

@@ -163,8 +163,11 @@ __global__ void __launch_bounds__(256)
     const uint32_t my_L = ns ? b.len[r] : 0;
     const uint64_t my_w = ns ? (uint64_t)(b.packed + b.word_off[r]) : 0ull;
     if (ns) {
-      pre.pre_off[strand] = base + incl - ns;
-      pre.pre_cnt[strand] = ns;
+      uint32_t* h = pre.pre_hdr + 4 * (size_t)strand;
+      h[0] = base + incl - ns;
+      h[1] = ns;
+      h[2] = my_L;
+      h[3] = b.word_off[r];
     }
     uint32_t alive = 0;
     for (uint32_t t0 = 0; t0 < total; t0 += 32) {
@@ -185,7 +188,7 @@ __global__ void __launch_bounds__(256)
       bool survived = false;
       if (t < total)
         survived = preseed_one(v, SUPER_SMEM ? (const uint32_t*)s_super : v.super_cnt, (const uint32_t*)o_w, o_L,
-                               ((i0 + owner) & 1u) != 0, o_sb + (t - (o_incl - o_ns)), pre.rec + 4 * (size_t)(base + t));
+                               ((i0 + owner) & 1u) != 0, o_sb + (t - (o_incl - o_ns)), pre.rec + 8 * (size_t)(base + t));
       alive |= __reduce_or_sync(full, survived ? (1u << owner) : 0u);
     }
     if (ns) {

@@ -42,11 +42,11 @@ struct SearchOut {
 // alive after a few marker-free extension steps. Most seeds of a strand that cannot map die there, so the
 // warp-synchronous search kernel only sees strands with real work.
 struct SeedOut {
-  uint32_t* rec;        // 4 words per survivor: {k-mer state index, pos | kind << 28, lo, hi}
-  uint32_t cap;         // survivor records available
+  uint32_t* rec;        // 8 words (one sector) per seed: {pos | kind << 28 (or dead), lo, hi, nt | ng << 16,
+                        //  path_off, first two path words, k-mer state index}: all the search kernel needs
+  uint32_t cap;         // seed records available
   uint32_t* used;       // bump pointer
-  uint32_t* pre_off;    // per strand: first survivor record
-  uint32_t* pre_cnt;    // per strand: number of survivors
+  uint32_t* pre_hdr;    // 4 words per strand: {first record, number of records, read length, packed word offset}
   uint32_t* live_list;  // strands with >= 1 survivor (work list of the search kernel)
   uint32_t* n_live;
 };

@@ -136,10 +136,10 @@ int emu_map(void* ev, const uint8_t* bases, const uint64_t* off, uint64_t n_read
     c.error_flags = &e->gsmall[1];
     c.stats = e->stats;
     c.allele_off = h.allele_off.data();
-    std::vector<uint32_t> seed_rec(4 * std::max<size_t>(1024, 64 * n_reads)), pre_off(2 * n_reads + 1), pre_cnt(2 * n_reads + 1),
+    std::vector<uint32_t> seed_rec(8 * std::max<size_t>(1024, 64 * n_reads)), pre_hdr(8 * n_reads + 4),
         live(2 * n_reads + 1), pre_small(2, 0);
-    SeedOut pre{seed_rec.data(), (uint32_t)(seed_rec.size() / 4), &pre_small[0], pre_off.data(), pre_cnt.data(),
-                live.data(), &pre_small[1]};
+    SeedOut pre{seed_rec.data(), (uint32_t)(seed_rec.size() / 8), &pre_small[0], pre_hdr.data(), live.data(),
+                &pre_small[1]};
     std::vector<uint32_t> arena(arena_words), big;
     for (uint32_t s = 0; s < 2 * n_reads; ++s) {
       uint32_t aw = arena_words;
