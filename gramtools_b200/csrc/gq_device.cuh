@@ -80,22 +80,60 @@ GQ_DEV inline void gq_threadfence() {
 #endif
 }
 
-// Strand cursor: base code i of the strand (forward, or reverse complement of the stored read;
-// reverse_complement_read, quasimap.cpp:273-298) with the current packed word cached in a register.
+GQ_DEV inline uint32_t pair_reverse32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  x = __brev(x);
+#else
+  x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+  x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+  x = ((x >> 4) & 0x0F0F0F0Fu) | ((x & 0x0F0F0F0Fu) << 4);
+  x = ((x >> 8) & 0x00FF00FFu) | ((x & 0x00FF00FFu) << 8);
+  x = (x >> 16) | (x << 16);
+#endif
+  return ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);  // bit reversal, then un-swap inside each pair
+}
+
+// Strand cursor over the 2-bit packed read: the bases of the strand (forward, or reverse complement of
+// the stored read; reverse_complement_read, quasimap.cpp:273-298) are consumed right to left, one per
+// search step. `cw` holds the current packed word shifted so that the next base sits in its top two
+// bits — for the reverse strand the word is complemented and pair-reversed once per 16 bases, so
+// peek/advance are identical for both strands (2 instructions per base in the hot step).
 struct ReadCursor {
   const uint32_t* w;
   uint32_t L;
-  bool rc;
-  uint32_t cw_idx, cw;
-  GQ_DEV inline uint32_t operator()(uint32_t i) {
-    uint32_t phys = rc ? (L - 1 - i) : i;
-    uint32_t wi = phys >> 4;
-    if (wi != cw_idx) {
-      cw = GQ_LDG(w + wi);
-      cw_idx = wi;
+  uint32_t rc;
+  uint32_t cw, left, wi;
+  GQ_DEV inline void load_word() {
+    const uint32_t word = GQ_LDG(w + wi);
+    cw = rc ? pair_reverse32(~word) : word;
+  }
+  // position the cursor so that peek() returns the base at logical index pos-1 (pos >= 1)
+  GQ_DEV inline void seek(uint32_t pos) {
+    const uint32_t i = pos - 1;
+    const uint32_t p = rc ? (L - 1 - i) : i;
+    wi = p >> 4;
+    const uint32_t q = p & 15u;
+    load_word();
+    if (rc) {
+      cw <<= 2 * q;
+      left = 16 - q;
+    } else {
+      cw <<= 2 * (15 - q);
+      left = q + 1;
     }
-    uint32_t c = (cw >> ((phys & 15u) * 2)) & 3u;
-    return rc ? 3u - c : c;
+  }
+  GQ_DEV inline uint32_t peek() const { return cw >> 30; }
+  GQ_DEV inline void advance() {
+    cw <<= 2;
+    if (--left == 0) {
+      left = 16;
+      if (rc) {
+        if (++wi < ((L + 15) >> 4)) load_word();
+      } else if (wi > 0) {
+        --wi;
+        load_word();
+      }
+    }
   }
 };
 
@@ -224,6 +262,7 @@ GQ_DEV inline void lane_load_top(Lane& ln) {
   ln.lo = t[1];
   ln.hi = t[2];
   ln.state = (ln.kind == K_JUMP || ln.pos == 0) ? LS_EV_TOP : (ln.lo == ln.hi ? LS_RUN : LS_RUNW);
+  if (ln.state != LS_EV_TOP) ln.rd.seek(ln.pos);  // stack entries resume at their own read position
 }
 
 GQ_DEV inline void lane_finish_strand(Lane& ln, const SearchOut& o) {
@@ -249,19 +288,6 @@ GQ_DEV inline void lane_finish_strand(Lane& ln, const SearchOut& o) {
   ln.state = LS_IDLE;
 }
 
-GQ_DEV inline uint32_t pair_reverse32(uint32_t x) {
-#if defined(__CUDA_ARCH__)
-  x = __brev(x);
-#else
-  x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
-  x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
-  x = ((x >> 4) & 0x0F0F0F0Fu) | ((x & 0x0F0F0F0Fu) << 4);
-  x = ((x >> 8) & 0x00FF00FFu) | ((x & 0x00FF00FFu) << 8);
-  x = (x >> 16) | (x << 16);
-#endif
-  return ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);  // bit reversal, then un-swap inside each pair
-}
-
 // Start `strand` on this lane: seed with the index entry of its last k-mer (quasimap.cpp:178,235-241).
 GQ_DEV inline void lane_refill(Lane& ln, const IndexView& v, const BatchView& b, const SearchOut& o, uint32_t strand,
                                uint32_t* arena, uint32_t arena_words) {
@@ -278,7 +304,7 @@ GQ_DEV inline void lane_refill(Lane& ln, const IndexView& v, const BatchView& b,
     o.status[strand] = ST_MISSING_KMER;
     return;
   }
-  ln.rd = ReadCursor{b.packed + b.word_off[r], L, (strand & 1u) != 0, 0xFFFFFFFFu, 0};
+  ln.rd = ReadCursor{b.packed + b.word_off[r], L, strand & 1u, 0, 0, 0};
   // seeding k-mer = last k bases of the strand; its code (base j at bits [2j,2j+2)) is a bit-field of the
   // packed read: the last k pairs for the forward strand, the pair-reversed complement of the first k
   // pairs for the reverse strand
@@ -335,7 +361,7 @@ GQ_DEV inline void lane_step(Lane& ln, const IndexView& v, SuperPtr super_c) {
   const uint32_t lo = ln.lo;
   const uint32_t b0 = lo >> kBlkShift;
   const RankBlk B0 = load_blk(v.rank_blk + b0);
-  const uint32_t c = ln.rd(ln.pos - 1);
+  const uint32_t c = ln.rd.peek();
   const uint64_t x0 = (c & 1u) ? 0ull : ~0ull, x1 = (c & 2u) ? 0ull : ~0ull;
   const uint64_t bit = 1ull << (lo & 63u);
   if (B0.p2 & bit) {  // not a nucleotide: marker -> jump (unless already scanned), sentinel -> dead
@@ -355,10 +381,8 @@ GQ_DEV inline void lane_step(Lane& ln, const IndexView& v, SuperPtr super_c) {
   ln.lo = ln.hi = super_c[4 * (b0 >> (kSuperShift - kBlkShift)) + c] + ((uint32_t)(B0.cnt >> (16 * c)) & 0xFFFFu) +
                   (uint32_t)popc64(m & (bit - 1));
   ln.kind = K_SCAN;
-  if (--ln.pos == 0) {
-    lane_writeback(ln, K_SCAN);
-    ln.state = LS_EV_TOP;
-  }
+  ln.rd.advance();
+  if (--ln.pos == 0) ln.state = LS_EV_TOP;  // registers hold the finished state; lane_event_top stores it
 }
 
 // One base for a lane in LS_RUNW: SA interval wider than one suffix (the first bases after seeding, and
@@ -385,7 +409,7 @@ GQ_DEV inline void lane_step_wide(Lane& ln, const IndexView& v, SuperPtr super_c
       return;
     }
   }
-  const uint32_t c = ln.rd(ln.pos - 1);
+  const uint32_t c = ln.rd.peek();
   const uint64_t x0 = (c & 1u) ? 0ull : ~0ull, x1 = (c & 2u) ? 0ull : ~0ull;
   const uint64_t m0 = ~B0.p2 & (B0.p0 ^ x0) & (B0.p1 ^ x1);
   const uint64_t m1 = ~B1.p2 & (B1.p0 ^ x0) & (B1.p1 ^ x1);
@@ -402,10 +426,8 @@ GQ_DEV inline void lane_step_wide(Lane& ln, const IndexView& v, SuperPtr super_c
   ln.hi = r1 - 1;
   ln.kind = K_SCAN;
   ln.state = (ln.lo == ln.hi) ? LS_RUN : LS_RUNW;
-  if (--ln.pos == 0) {
-    lane_writeback(ln, K_SCAN);
-    ln.state = LS_EV_TOP;
-  }
+  ln.rd.advance();
+  if (--ln.pos == 0) ln.state = LS_EV_TOP;
 }
 
 // after a transition of the rare path: finish the strand, or cache the new top
@@ -467,7 +489,7 @@ GQ_DEV inline void lane_event_scan(Lane& ln, const IndexView& v, const SearchOut
         // table lookup. For a site of distinct single-base alleles the exit that follows is folded in
         // as well (entry, allele base, exit = one event) unless the read ends inside the site.
         const uint32_t slot = (marker - 6) >> 1;
-        const uint32_t c = ln.rd(ln.pos - 1);
+        const uint32_t c = ln.rd.peek();
         if (snp != kNotSnp && ln.pos >= 2) {
           const uint32_t a = (snp >> (8 * c)) & 0xFFu;
           if (a == 0xFFu) {
@@ -480,6 +502,7 @@ GQ_DEV inline void lane_event_scan(Lane& ln, const IndexView& v, const SearchOut
           t[3] = (nt + 1) | (ng << 16);
           ln.lo = ln.hi = entered_site_sa;
           ln.pos -= 1;
+          ln.rd.advance();
           ln.kind = K_READY;
           ln.state = LS_RUN;
           return;
@@ -496,10 +519,8 @@ GQ_DEV inline void lane_event_scan(Lane& ln, const IndexView& v, const SearchOut
         ln.hi = nhi;
         ln.kind = K_SCAN;
         ln.state = (nlo == nhi) ? LS_RUN : LS_RUNW;
-        if (--ln.pos == 0) {
-          lane_writeback(ln, K_SCAN);
-          ln.state = LS_EV_TOP;
-        }
+        ln.rd.advance();
+        if (--ln.pos == 0) ln.state = LS_EV_TOP;
         return;
       }
       t[3] = nt | (ng << 16);
@@ -529,6 +550,8 @@ GQ_DEV inline void lane_event_pop(Lane& ln, const SearchOut& o) {
 // LS_EV_TOP: a pending locus (K_JUMP) or a finished state (pos == 0) sits on top
 GQ_DEV inline void lane_event_top(Lane& ln, const IndexView& v, const SearchOut& o) {
   uint32_t* t = ln.s.mem + ln.s.top;
+  // a state that finished in a step is still only in registers (equal to memory if it was loaded)
+  if (ln.pos == 0 && ln.kind != K_JUMP) lane_writeback(ln, K_SCAN);
   if ((t[0] >> 28) == K_JUMP) process_jump(ln.s, v);
   else if (t[4] == kNoAllele && ln.n_states == 0 && t[3] != 0 && ln.s.limit == ln.arena_words) {
     // the strand's only state, with a path: write its record straight into the pool
@@ -621,13 +644,14 @@ template <class SuperPtr>
 GQ_DEV inline bool preseed_one(const IndexView& v, SuperPtr super_c, const uint32_t* w, uint32_t L, bool rc, uint32_t j,
                                uint32_t* d) {
   Lane ln;
-  ln.rd = ReadCursor{w, L, rc, 0xFFFFFFFFu, 0};
+  ln.rd = ReadCursor{w, L, rc ? 1u : 0u, 0, 0, 0};
   const KmerState ks = v.kmer_states[j];
   ln.pos = L - v.k;
   ln.lo = ks.lo;
   ln.hi = ks.hi;
   ln.kind = K_SCAN;
   ln.state = ln.pos == 0 ? LS_EV_TOP : (ln.lo == ln.hi ? LS_RUN : LS_RUNW);
+  if (ln.pos) ln.rd.seek(ln.pos);
   // never consume the last base here: the finished state is emitted by the search kernel
   const uint32_t max_steps = ln.pos > 1 ? (ln.pos - 1 < kPreSteps ? ln.pos - 1 : kPreSteps) : 0;
   for (uint32_t s = 0; s < max_steps && (ln.state == LS_RUN || ln.state == LS_RUNW); ++s) {
@@ -688,7 +712,7 @@ GQ_DEV inline void lane_refill_pre(Lane& ln, const IndexView& v, const BatchView
   const uint32_t* h = pre.pre_hdr + 4 * (size_t)strand;
   const uint32_t p0 = GQ_LDG(h), n = GQ_LDG(h + 1), L = GQ_LDG(h + 2), woff = GQ_LDG(h + 3);
   ln.strand = strand;
-  ln.rd = ReadCursor{b.packed + woff, L, (strand & 1u) != 0, 0xFFFFFFFFu, 0};
+  ln.rd = ReadCursor{b.packed + woff, L, strand & 1u, 0, 0, 0};
   ln.s.mem = arena;
   ln.s.limit = arena_words;
   ln.s.overflow = false;
