@@ -110,6 +110,10 @@ static void upload_index(gq_index* ix) {
   v.super_cnt = upload(ix, h.super_cnt);
   v.mrank_blk = upload(ix, h.mrank_blk);
   v.marker_hit = upload(ix, h.marker_hit);
+  v.text_grp = upload(ix, h.text_grp);
+  v.text_super = upload(ix, h.text_super);
+  v.tmarker_hit = upload(ix, h.tmarker_hit);
+  v.isa = upload(ix, h.isa);
   for (int i = 0; i < 4; ++i) v.c_base[i] = h.c_base[i];
   v.n_slots = h.n_slots;
   v.any_nested = h.is_nested ? 1u : 0u;

@@ -23,6 +23,7 @@ namespace gq {
 
 constexpr uint32_t kBlkShift = 6;     // 64 BWT positions per rank block
 constexpr uint32_t kSuperShift = 15;  // 32768 positions per superblock (block counts fit u16)
+constexpr uint32_t kTextSuperShift = 15;  // 32768 text positions per marker-rank superblock (relative ranks fit u16)
 constexpr uint32_t kNoAllele = 0xFFFFFFFFu;
 constexpr uint32_t kNotSnp = 0xFFFFFFFEu;
 
@@ -32,6 +33,15 @@ constexpr uint32_t kNotSnp = 0xFFFFFFFEu;
 struct alignas(32) RankBlk {
   uint64_t cnt;  // 4 x u16: A,C,G,T occurrences in [superblock start, block start)
   uint64_t p0, p1, p2;
+};
+
+// 8 bytes per 16 PRG text positions: what a width-1 search state needs to walk the text itself instead of
+// the BWT (text mode, gq_device.cuh lane_text_step). `codes`: 2-bit base code of position 16g+i at bits
+// [2i,2i+2) — the layout of a packed read word — 0 at markers; `info`: bit i (i < 16) = position 16g+i
+// holds a variant marker; bits 16..31 = markers in [superblock start, 16g).
+struct TextGrp {
+  uint32_t codes;
+  uint32_t info;
 };
 
 struct Node {        // flat coverage-graph node (reference: include/prg/coverage_graph.hpp:40-124)
@@ -56,9 +66,17 @@ struct IndexView {
   const RankBlk* rank_blk;
   const uint32_t* super_cnt;   // 4 per superblock: C[c] + occurrences of A,C,G,T before the superblock
   const uint32_t* mrank_blk;   // markers in BWT[0, block start)
-  const uint32_t* marker_hit;  // 8 per BWT marker occurrence (one 32 B sector): (marker', allele, lo, hi, snp, site_sa):
-                               // the jump target; when no marker is adjacent on the far side the SA interval after
-                               // the jump (else lo = ~0); for such entries the site's SNP table and C[site]
+  const uint32_t* marker_hit;  // 8 per BWT marker occurrence (one 32 B sector): (marker', allele, lo, hi, snp, site_sa,
+                               // p_jump, p_site): the jump target; when no marker is adjacent on the far side the SA
+                               // interval after the jump (else lo = ~0); for such entries the site's SNP table and
+                               // C[site]; p_jump = SA[lo] when lo == hi, p_site = SA[C[site]] (text positions, so a
+                               // width-1 state lands in text mode without an SA lookup)
+  // text mode (width-1 states): the PRG itself, 2 bits per base + marker flags, and the same jump records
+  // in TEXT order (index = rank of the marker among the markers of the text)
+  const TextGrp* text_grp;     // one per 16 text positions
+  const uint32_t* text_super;  // markers before each superblock of 2^kTextSuperShift positions
+  const uint32_t* tmarker_hit; // marker_hit records, text order
+  const uint32_t* isa;         // inverse suffix array (final SA index of a text-mode state)
   uint32_t c_base[4];          // first SA index of suffixes starting with A,C,G,T
   // per site slot s = (site_id - 5) / 2
   uint32_t n_slots;

@@ -74,6 +74,20 @@ GQ_DEV inline uint32_t gq_funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) {
   return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
 #endif
 }
+GQ_DEV inline uint32_t gq_clz(uint32_t x) {  // 32 for x == 0
+#if defined(__CUDA_ARCH__)
+  return (uint32_t)__clz((int)x);
+#else
+  return x ? (uint32_t)__builtin_clz(x) : 32u;
+#endif
+}
+GQ_DEV inline uint32_t gq_popc(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return (uint32_t)__popc(x);
+#else
+  return (uint32_t)__builtin_popcount(x);
+#endif
+}
 GQ_DEV inline void gq_threadfence() {
 #if defined(__CUDA_ARCH__)
   __threadfence();
@@ -123,17 +137,24 @@ struct ReadCursor {
     }
   }
   GQ_DEV inline uint32_t peek() const { return cw >> 30; }
+  GQ_DEV inline void next_word() {
+    left = 16;
+    if (rc) {
+      if (++wi < ((L + 15) >> 4)) load_word();
+    } else if (wi > 0) {
+      --wi;
+      load_word();
+    }
+  }
   GQ_DEV inline void advance() {
     cw <<= 2;
-    if (--left == 0) {
-      left = 16;
-      if (rc) {
-        if (++wi < ((L + 15) >> 4)) load_word();
-      } else if (wi > 0) {
-        --wi;
-        load_word();
-      }
-    }
+    if (--left == 0) next_word();
+  }
+  // consume r <= left bases at once (text mode compares up to a whole word per step)
+  GQ_DEV inline void advance_n(uint32_t r) {
+    left -= r;
+    if (left == 0) next_word();
+    else cw <<= 2 * r;
   }
 };
 
@@ -231,7 +252,9 @@ struct EmitStage {
 // ------------------------------------------------------------------------------------------------
 enum LaneState : uint32_t {
   LS_IDLE = 0, LS_RUN = 1 /* width-1 interval */, LS_EV_SCAN = 2, LS_EV_POP = 3, LS_EV_TOP = 4, LS_EV_WIDE = 5,
-  LS_RUNW = 6 /* wider interval */
+  LS_RUNW = 6 /* wider interval */,
+  LS_TEXT = 7 /* width-1 interval followed in the PRG text (lane_text_step): `p` is authoritative, lo/hi are not */,
+  LS_EV_TSCAN = 8 /* text mode reached a marker: `mr` is its rank among the markers of the text */
 };
 
 struct Lane {
@@ -244,6 +267,7 @@ struct Lane {
   // top entry cached in registers while state == LS_RUN
   uint32_t pos, lo, hi, kind;
   uint32_t mr;  // LS_EV_SCAN of a width-1 interval: rank of the marker at BWT[lo] among all BWT markers
+  uint32_t p;   // LS_TEXT: text position SA[lo] of the state's single suffix
 };
 
 GQ_DEV inline void lane_writeback(Lane& ln, uint32_t kind) {
@@ -430,6 +454,69 @@ GQ_DEV inline void lane_step_wide(Lane& ln, const IndexView& v, SuperPtr super_c
   if (--ln.pos == 0) ln.state = LS_EV_TOP;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Text mode. A width-1 SA interval [lo,lo] is ONE suffix of the PRG, at text position p = SA[lo]. Extending
+// it backwards by base c (BWT_search.cpp:45-76) succeeds iff BWT[lo] = prg[p-1] = c, and the new interval
+// is the single suffix at p-1 (LF(lo) = ISA[p-1]); a marker at prg[p-1] is the marker the reference finds
+// in BWT[lo] (vBWT_jump.cpp:100-114), and p = 0 puts the sentinel there. So while the interval stays one
+// suffix wide the whole backward search is a comparison of the packed read with the packed PRG, up to 16
+// bases per step instead of one rank query per base — same states, same jumps, same final SA index
+// (ISA[p], read once when the read is exhausted).
+// ------------------------------------------------------------------------------------------------
+GQ_DEV inline void lane_to_text(Lane& ln, const IndexView& v) {  // LS_RUN -> LS_TEXT
+  ln.p = GQ_LDG(v.sa + ln.lo);
+  ln.state = LS_TEXT;
+}
+
+GQ_DEV inline void lane_text_step(Lane& ln, const IndexView& v) {
+  const uint32_t p = ln.p;
+  if (p == 0) {  // BWT[lo] is the sentinel
+    ln.state = LS_EV_POP;
+    return;
+  }
+  // the positions [16g, p-1] of the group holding p-1, aligned so that p-1 sits where the cursor keeps
+  // the next read base (top bit pair / top flag bit)
+  const uint32_t q = p - 1, g = q >> 4, j = (q & 15u) + 1, sh = 16 - j;
+#if defined(__CUDA_ARCH__)
+  const uint2 raw = __ldg(reinterpret_cast<const uint2*>(v.text_grp) + g);
+  const uint32_t codes = raw.x, info = raw.y;
+#else
+  const uint32_t codes = v.text_grp[g].codes, info = v.text_grp[g].info;
+#endif
+  const uint32_t run_mis = gq_clz(ln.rd.cw ^ (codes << (2 * sh))) >> 1;  // equal bases from the top (<= 16)
+  const uint32_t run_mark = gq_clz(info << (16 + sh));                   // marker-free positions from the top
+  uint32_t limit = j < ln.rd.left ? j : ln.rd.left;
+  limit = limit < ln.pos ? limit : ln.pos;
+  if (run_mark < limit && run_mark <= run_mis) {
+    // a marker after run_mark further bases: committed jump states do not scan again (K_READY), any
+    // other state jumps (lane_event_scan, text flavour)
+    if (run_mark == 0 && ln.kind != K_SCAN) {
+      ln.state = LS_EV_POP;
+      return;
+    }
+    ln.p = p - run_mark;
+    ln.pos -= run_mark;
+    ln.rd.advance_n(run_mark);
+    ln.kind = K_SCAN;
+    const uint32_t below = (1u << ((q - run_mark) & 15u)) - 1u;
+    ln.mr = GQ_LDG(v.text_super + (g >> (kTextSuperShift - 4))) + (info >> 16) + gq_popc(info & below);
+    ln.state = LS_EV_TSCAN;
+    return;
+  }
+  if (run_mis < limit) {  // the PRG continues with another base
+    ln.state = LS_EV_POP;
+    return;
+  }
+  ln.p = p - limit;
+  ln.pos -= limit;
+  ln.rd.advance_n(limit);
+  ln.kind = K_SCAN;
+  if (ln.pos == 0) {  // finished: the state's SA index, for the record lane_event_top writes
+    ln.lo = ln.hi = GQ_LDG(v.isa + ln.p);
+    ln.state = LS_EV_TOP;
+  }
+}
+
 // after a transition of the rare path: finish the strand, or cache the new top
 GQ_DEV inline void lane_after_event(Lane& ln, const SearchOut& o) {
   if (ln.s.overflow || stack_empty(ln.s)) {
@@ -446,19 +533,22 @@ GQ_DEV inline void lane_event_scan(Lane& ln, const IndexView& v, const SearchOut
     ln.state = LS_RUNW;
     return;
   }
-  if (ln.lo == ln.hi) {
+  const bool text = ln.state == LS_EV_TSCAN;
+  if (text || ln.lo == ln.hi) {
     // Single suffix preceded by a marker: the un-jumped state cannot be extended by any base (its only
     // BWT symbol is the marker), so the jump replaces it in place instead of being pushed above it.
     uint32_t mr = ln.mr;
-    if (mr == kNoAllele) {  // width-1 interval reached through the wide step
+    if (!text && mr == kNoAllele) {  // width-1 interval reached through the wide step
       const uint32_t blk = ln.lo >> kBlkShift, bit = ln.lo & 63u;
       const RankBlk B = load_blk(v.rank_blk + blk);
       mr = GQ_LDG(v.mrank_blk + blk) + (uint32_t)popc64(B.p2 & B.p0 & ((1ull << bit) - 1));
     }
-    // one 32 B sector: jump target, post-jump interval, SNP table + C[site] of a simple entry
-    const uint32_t* jr = v.marker_hit + 8 * (size_t)mr;
+    // one 32 B sector: jump target, post-jump interval, SNP table + C[site] of a simple entry, and the text
+    // positions behind the post-jump SA indices (the state continues in text mode without an SA lookup)
+    const uint32_t* jr = (text ? v.tmarker_hit : v.marker_hit) + 8 * (size_t)mr;
     const uint32_t marker = GQ_LDG(jr), allele = GQ_LDG(jr + 1), jlo = GQ_LDG(jr + 2), jhi = GQ_LDG(jr + 3);
     const uint32_t snp = GQ_LDG(jr + 4), entered_site_sa = GQ_LDG(jr + 5);
+    const uint32_t p_jump = GQ_LDG(jr + 6), p_site = GQ_LDG(jr + 7);
     if (marker == 0) {
       ln.state = LS_EV_POP;
       return;
@@ -501,10 +591,11 @@ GQ_DEV inline void lane_event_scan(Lane& ln, const IndexView& v, const SearchOut
           T[2 * nt + 1] = a;
           t[3] = (nt + 1) | (ng << 16);
           ln.lo = ln.hi = entered_site_sa;
+          ln.p = p_site;
           ln.pos -= 1;
           ln.rd.advance();
           ln.kind = K_READY;
-          ln.state = LS_RUN;
+          ln.state = LS_TEXT;
           return;
         }
         T[2 * nt + ng] = marker - 1;
@@ -526,8 +617,9 @@ GQ_DEV inline void lane_event_scan(Lane& ln, const IndexView& v, const SearchOut
       t[3] = nt | (ng << 16);
       ln.lo = jlo;
       ln.hi = jhi;
+      ln.p = p_jump;
       ln.kind = K_READY;
-      ln.state = (jlo == jhi) ? LS_RUN : LS_RUNW;
+      ln.state = (jlo == jhi) ? LS_TEXT : LS_RUNW;
       return;
     }
     t[0] = ln.pos | (K_JUMP << 28);
@@ -590,7 +682,7 @@ GQ_DEV inline void lane_event_top(Lane& ln, const IndexView& v, const SearchOut&
 }
 
 GQ_DEV inline void lane_event(Lane& ln, const IndexView& v, const SearchOut& o) {
-  if (ln.state == LS_EV_SCAN || ln.state == LS_EV_WIDE) lane_event_scan(ln, v, o);
+  if (ln.state == LS_EV_SCAN || ln.state == LS_EV_WIDE || ln.state == LS_EV_TSCAN) lane_event_scan(ln, v, o);
   else if (ln.state == LS_EV_POP) lane_event_pop(ln, o);
   else lane_event_top(ln, v, o);
 }
@@ -800,7 +892,8 @@ GQ_DEV inline void map_strand(const IndexView& v, const uint32_t* super_cnt, con
     if (pre.pre_hdr[4 * (size_t)strand + 1]) lane_refill_pre(ln, v, b, o, pre, strand, arena, arena_words);
   }
   while (ln.state != LS_IDLE) {
-    if (ln.state == LS_RUN) lane_step(ln, v, super_cnt);
+    if (ln.state == LS_RUN) lane_to_text(ln, v);
+    else if (ln.state == LS_TEXT) lane_text_step(ln, v);
     else if (ln.state == LS_RUNW) lane_step_wide(ln, v, super_cnt);
     else lane_event(ln, v, o);
   }

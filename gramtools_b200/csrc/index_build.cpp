@@ -18,6 +18,10 @@ IndexView HostIndex::view() const {
   v.super_cnt = super_cnt.data();
   v.mrank_blk = mrank_blk.data();
   v.marker_hit = marker_hit.data();
+  v.text_grp = text_grp.data();
+  v.text_super = text_super.data();
+  v.tmarker_hit = tmarker_hit.data();
+  v.isa = isa.data();
   for (int i = 0; i < 4; ++i) v.c_base[i] = c_base[i];
   v.n_slots = n_slots;
   v.any_nested = is_nested ? 1u : 0u;
@@ -301,6 +305,7 @@ void build_fm(HostIndex& ix, const std::vector<uint32_t>& hit_marker, const std:
   ix.mrank_blk.assign(nblk, 0);
   ix.marker_hit.clear();
   uint32_t tot[4] = {0, 0, 0, 0}, sup[4] = {0, 0, 0, 0}, nmark = 0;
+  std::vector<uint32_t> bwt_marker_pos;  // text position of the marker behind each BWT marker occurrence
   for (uint32_t i = 0; i <= n; ++i) {
     if ((i & ((1u << kSuperShift) - 1)) == 0) {
       for (int c = 0; c < 4; ++c) sup[c] = tot[c], ix.super_cnt[4 * (size_t)(i >> kSuperShift) + c] = ix.c_base[c] + tot[c];
@@ -326,6 +331,7 @@ void build_fm(HostIndex& ix, const std::vector<uint32_t>& hit_marker, const std:
       if (sym > 4) {
         b.p0 |= bit;
         ++nmark;
+        bwt_marker_pos.push_back(p - 1);
         bool at_base = p < prg.size() && prg[p] <= 4;
         uint32_t hm = at_base ? hit_marker[p] : 0, ha = at_base ? hit_allele[p] : 0;
         uint32_t jlo = kNoAllele, jhi = kNoAllele;
@@ -394,8 +400,35 @@ void build_fm(HostIndex& ix, const std::vector<uint32_t>& hit_marker, const std:
       uint32_t slot = (hm - 6) / 2;
       ix.marker_hit[m + 4] = ix.site_snp[slot];
       ix.marker_hit[m + 5] = ix.site_sa[slot];
+      ix.marker_hit[m + 7] = ix.sa[ix.site_sa[slot]];
     }
+    const uint32_t jlo = ix.marker_hit[m + 2], jhi = ix.marker_hit[m + 3];
+    ix.marker_hit[m + 6] = (jlo != kNoAllele && jlo == jhi) ? ix.sa[jlo] : kNoAllele;
   }
+
+  // ---- text mode: the PRG as 2-bit codes + marker flags, jump records in text order, inverse SA ----
+  const uint32_t L = (uint32_t)prg.size();
+  ix.isa.assign(n, 0);
+  for (uint32_t i = 0; i < n; ++i) ix.isa[ix.sa[i]] = i;
+  const uint32_t ngrp = (L >> 4) + 1;
+  ix.text_grp.assign(ngrp, TextGrp{0, 0});
+  ix.text_super.assign((L >> kTextSuperShift) + 1, 0);
+  std::vector<uint32_t> text_rank(L, 0);  // rank of a marker position among the markers of the text
+  uint32_t tm = 0, tsup = 0;
+  for (uint32_t q = 0; q < L; ++q) {
+    if ((q & ((1u << kTextSuperShift) - 1)) == 0) ix.text_super[q >> kTextSuperShift] = tsup = tm;
+    if ((q & 15u) == 0) ix.text_grp[q >> 4].info = (tm - tsup) << 16;
+    const uint32_t sym = prg[q];
+    if (sym > 4) {
+      ix.text_grp[q >> 4].info |= 1u << (q & 15u);
+      text_rank[q] = tm++;
+    } else
+      ix.text_grp[q >> 4].codes |= (sym - 1) << (2 * (q & 15u));
+  }
+  ix.tmarker_hit.assign(std::max<size_t>(8, 8 * (size_t)tm), 0);
+  for (size_t mr = 0; mr < bwt_marker_pos.size(); ++mr)
+    std::copy(ix.marker_hit.begin() + 8 * mr, ix.marker_hit.begin() + 8 * mr + 8,
+              ix.tmarker_hit.begin() + 8 * (size_t)text_rank[bwt_marker_pos[mr]]);
 }
 
 // ---- all-k-mers index (reference: src/build/kmer_index/build.cpp:18-148) ---------------------

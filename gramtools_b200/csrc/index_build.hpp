@@ -23,6 +23,9 @@ struct HostIndex {
   std::vector<uint32_t> super_cnt;
   std::vector<uint32_t> mrank_blk;
   std::vector<uint32_t> marker_hit;
+  // text mode
+  std::vector<TextGrp> text_grp;
+  std::vector<uint32_t> text_super, tmarker_hit, isa;
   uint32_t c_base[4] = {0, 0, 0, 0};
   // sites
   uint32_t n_slots = 0;   // (max site id - 5)/2 + 1

@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(kSearchThreads, GQ_SEARCH_MIN_BLOCKS)
     const uint32_t st = ln.state;
     const uint32_t field = st == LS_IDLE ? 1u
                            : st == LS_RUNW ? (1u << 6)
-                           : (st == LS_EV_SCAN || st == LS_EV_WIDE) ? (1u << 12)
+                           : (st == LS_EV_SCAN || st == LS_EV_WIDE || st == LS_EV_TSCAN) ? (1u << 12)
                            : st == LS_EV_POP ? (1u << 18)
                            : st == LS_EV_TOP ? (1u << 24) : 0u;
     const uint32_t votes = __reduce_add_sync(full, field);
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(kSearchThreads, GQ_SEARCH_MIN_BLOCKS)
     }
     if (n_scan && (n_scan >= ev_thresh || (force && n_scan == big))) {
       DBG(5, 1); DBG(6, n_scan);
-      if (ln.state == LS_EV_SCAN || ln.state == LS_EV_WIDE) lane_event_scan(ln, v, o);
+      if (ln.state == LS_EV_SCAN || ln.state == LS_EV_WIDE || ln.state == LS_EV_TSCAN) lane_event_scan(ln, v, o);
       continue;
     }
     if (n_top && (n_top >= ev_thresh || (force && n_top == big))) {
@@ -302,9 +302,13 @@ __global__ void __launch_bounds__(kSearchThreads, GQ_SEARCH_MIN_BLOCKS)
     const uint32_t stay = n_run0 > leave ? n_run0 - leave : 0;
     while (true) {
 #pragma unroll
-      for (int u = 0; u < kHotUnroll; ++u)
-        if (ln.state == LS_RUN) lane_step(ln, v, SUPER_SMEM ? (const uint32_t*)s_super : v.super_cnt);
-      const uint32_t n_run = __popc(__ballot_sync(full, ln.state == LS_RUN));
+      for (int u = 0; u < kHotUnroll; ++u) {
+        // width-1 states walk the PRG text (up to 16 bases per step); a state that just became one suffix
+        // wide first fetches its text position
+        if (ln.state == LS_TEXT) lane_text_step(ln, v);
+        else if (ln.state == LS_RUN) lane_to_text(ln, v);
+      }
+      const uint32_t n_run = __popc(__ballot_sync(full, ln.state == LS_RUN || ln.state == LS_TEXT));
       DBG(13, 1); DBG(14, n_run);
       if (n_run <= stay) break;
     }
