@@ -71,8 +71,8 @@ struct gq_index {
   DevBuf<uint8_t> status;
   DevBuf<uint32_t> st_off, st_words, st_count, pool, small;  // small: [pool_used, n_overflow, n_cov_overflow]
   DevBuf<uint32_t> overflow_list, cov_overflow_list, mapped_list;
-  DevBuf<uint32_t> seed_rec, pre_hdr, live_list;  // seed pass (SeedOut)
-  uint32_t seed_recs_per_read = 8;  // set from the index in gq_index_build: ~1.5 x mean states per indexed k-mer
+  DevBuf<uint32_t> seed_rec, surv_cnt, gen_list;  // seed pass (SeedOut): survivor records, per-strand counts, general list
+  uint32_t seed_recs_per_read = 4;  // survivor records per read (both strands); a full pool sends strands to the general kernel
   bool use_seed_pass = true;
   DevBuf<uint32_t> arena, big_arena;
   cudaStream_t copy_stream = nullptr;
@@ -250,8 +250,8 @@ static void do_map(gq_index* ix, const uint8_t* h_bases = nullptr, const uint64_
   ix->cov_overflow_list.reserve(2 * (size_t)n);
   ix->mapped_list.reserve(2 * (size_t)n);
   ix->small.reserve(8 + 4 * 64);
-  ix->pre_hdr.reserve(8 * (size_t)n);
-  ix->live_list.reserve(2 * (size_t)n);
+  ix->surv_cnt.reserve(2 * (size_t)n);
+  ix->gen_list.reserve(2 * (size_t)n);
   ix->seed_rec.reserve(8 * std::max<size_t>((size_t)n * ix->seed_recs_per_read, 1 << 16));
   size_t pool_need = std::max<size_t>((size_t)n * ix->pool_words_per_read, 1 << 16);
   pool_need = std::min<size_t>(pool_need, 0xFFFFFFF0ull);
@@ -263,8 +263,8 @@ static void do_map(gq_index* ix, const uint8_t* h_bases = nullptr, const uint64_
   uint32_t threads = std::min<uint32_t>(ix->n_threads, std::max<uint32_t>(256, ((2 * max_chunk / 4 + 255) / 256) * 256));
   uint32_t threads2 = std::min<uint32_t>(ix->cov_threads, ((2 * max_chunk + 255) / 256) * 256);
   ix->arena.reserve((size_t)std::max(threads, threads2) * ix->arena_words);
-  // small: [0] pool_used [1] n_overflow [2] n_cov_overflow [3] seed records used;
-  // per chunk c: [8+4c] n_mapped [9+4c] work counter [10+4c] n_live
+  // small: [0] pool_used [1] n_overflow [2] n_cov_overflow;
+  // per chunk c: [8+4c] n_mapped [9+4c] work counter [10+4c] survivor records [11+4c] n_gen (general-kernel work list)
   CUDA_OK(cudaMemsetAsync(ix->small.p, 0, (8 + 4 * 64) * 4, st));
 
   gq::BatchView b{ix->packed.p, ix->word_off.p, ix->len.p, ix->seeds.p, n, 0, n};
@@ -299,15 +299,22 @@ static void do_map(gq_index* ix, const uint8_t* h_bases = nullptr, const uint64_
     oc.mapped_list = ix->mapped_list.p + 2 * (size_t)chunks[i].r0;
     oc.n_mapped = ix->small.p + 8 + 4 * i;
     oc.work_counter = ix->small.p + 9 + 4 * i;
-    gq::SeedOut pre{ix->seed_rec.p, (uint32_t)(ix->seed_rec.cap / 8), ix->small.p + 3, ix->pre_hdr.p,
-                    ix->live_list.p + 2 * (size_t)chunks[i].r0, ix->small.p + 10 + 4 * i};
     if (ix->use_seed_pass) {
+      // seed pass -> text kernel (strands with one surviving width-1 seed) -> general kernel (the rest)
+      uint32_t* gen_list = ix->gen_list.p + 2 * (size_t)chunks[i].r0;
+      uint32_t* n_gen = ix->small.p + 11 + 4 * i;
+      gq::SeedOut pre{ix->seed_rec.p + 8 * (size_t)ix->seed_recs_per_read * chunks[i].r0,
+                      (uint32_t)(ix->seed_recs_per_read * (chunks[i].r1 - chunks[i].r0)),
+                      ix->small.p + 10 + 4 * i, ix->surv_cnt.p, gen_list, n_gen};
       gq::launch_seed(ix->dv, bc, oc, pre, st);
-      ++launches;
-    }
-    gq::launch_search(ix->dv, bc, oc, ix->arena.p, ix->arena_words, threads, nullptr, 0, ix->super_in_smem,
-                      ix->rf_thresh, ix->ev_thresh, st, ix->leave_opt, ix->wait_opt,
-                      ix->use_seed_pass ? &pre : nullptr);
+      gq::launch_text(ix->dv, bc, oc, pre, st);
+      gq::launch_search(ix->dv, bc, oc, ix->arena.p, ix->arena_words, threads, gen_list,
+                        2 * (chunks[i].r1 - chunks[i].r0), ix->super_in_smem, ix->rf_thresh, ix->ev_thresh, st,
+                        ix->leave_opt, ix->wait_opt, n_gen);
+      launches += 2;
+    } else
+      gq::launch_search(ix->dv, bc, oc, ix->arena.p, ix->arena_words, threads, nullptr, 0, ix->super_in_smem,
+                        ix->rf_thresh, ix->ev_thresh, st, ix->leave_opt, ix->wait_opt);
     if (chunks.size() == 1) CUDA_OK(cudaEventRecord(ix->ev[1], st));
     gq::launch_classify(ix->dv, bc, oc, nullptr, 0, st);
     gq::launch_coverage(ix->dv, bc, oc, c, ix->arena.p, ix->arena_words, threads2, nullptr, 0,
@@ -330,12 +337,11 @@ static void do_map(gq_index* ix, const uint8_t* h_bases = nullptr, const uint64_
   // mapped list of slice 0
   uint64_t rerun = 0;
   // ---- overflow re-runs: same kernels in list mode (strands seeded inside the search kernel) ----
-  // A full seed-record pool is a capacity miss, not a deep search: those strands are re-run with the
-  // normal arenas and lane count (and the pool is enlarged for the next batch). Arena / state-pool
-  // overflows are re-run with fewer lanes and much larger per-lane arenas (x4 per further retry).
+  // Arena / state-pool overflows are re-run with fewer lanes and much larger per-lane arenas (x4 per
+  // further retry). (A full survivor pool of the seed pass is not an overflow: those strands simply take
+  // the general kernel.)
   uint32_t big_words = ix->big_arena_words, big_threads = ix->big_threads;
-  bool seed_pool_miss = small[3] > ix->seed_rec.cap / 8;
-  if (seed_pool_miss) ix->seed_recs_per_read = (uint32_t)((double)small[3] / n * 1.25) + 4;
+  const bool seed_pool_miss = false;
   int guard = 0;
   while (small[1] > 0) {
     uint32_t n_list = small[1];
@@ -461,12 +467,6 @@ int gq_index_build(const uint32_t* prg, uint64_t n_symbols, uint32_t kmer_size, 
   ix->stream = ix->own_stream;
   for (auto& e : ix->ev) CUDA_OK(cudaEventCreate(&e));
   upload_index(ix);
-  {  // seed records per read: ~1.5 x the mean number of states of an indexed k-mer, both strands
-    uint64_t present = 0;
-    for (uint32_t w : ix->h.kmer_bits) present += __builtin_popcount(w);
-    double mean = present ? (double)ix->h.kmer_off.back() / (double)present : 1.0;
-    ix->seed_recs_per_read = (uint32_t)(2.0 * (1.5 * mean + 2.0)) + 1;
-  }
   alloc_coverage(ix);
   reset_coverage(ix);
   *out = ix;
@@ -506,8 +506,8 @@ int gq_index_destroy(gq_index* ix) {
   ix->cov_overflow_list.release();
   ix->mapped_list.release();
   ix->seed_rec.release();
-  ix->pre_hdr.release();
-  ix->live_list.release();
+  ix->surv_cnt.release();
+  ix->gen_list.release();
   ix->arena.release();
   ix->big_arena.release();
   for (auto& e : ix->ev)
@@ -908,6 +908,7 @@ int gq_set_option(gq_index* ix, const char* name, int64_t value) {
     ix->chunk_reads = (uint32_t)std::max<int64_t>(value, 1024);
   } else if (n == "seed_pass") {
     ix->use_seed_pass = value != 0;
+
   } else if (n == "seed_recs_per_read") {
     ix->seed_recs_per_read = (uint32_t)std::max<int64_t>(value, 1);
     ix->seed_rec.release();

@@ -20,6 +20,14 @@
 
 namespace gq {
 
+// path statistics of the host emulation (tests/emu): which route strands take. No-op on the device.
+#if !defined(__CUDA_ARCH__) && defined(GQ_EMU_COUNTERS)
+extern unsigned long long gq_emu_counters[32];
+#define GQ_COUNT(i) (++gq_emu_counters[i])
+#else
+#define GQ_COUNT(i) ((void)0)
+#endif
+
 GQ_DEV inline uint32_t gq_atomic_add(uint32_t* p, uint32_t v) {
 #if defined(__CUDA_ARCH__)
   return atomicAdd(p, v);
@@ -688,21 +696,30 @@ GQ_DEV inline void lane_event(Lane& ln, const IndexView& v, const SearchOut& o) 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Seed pass. For one strand: look up the seeding k-mer (quasimap.cpp:178,235-241) and pre-extend each of
-// its seed states by up to kPreSteps marker-free bases with the very same step functions the search
-// kernel uses. Seeds of strands that cannot map die here (a random 16-mer does not occur in the PRG), so
-// they never occupy a lane of the warp-synchronous kernel; survivors are handed over with their current
-// (pos, lo, hi) and resume exactly where they stopped.
+// Seed pass. For one strand: look up the seeding k-mer (quasimap.cpp:178,235-241); each of its seed states
+// is narrowed by rank steps while it is wider than kSplitWidth suffixes, then SPLIT into its suffixes: every
+// occurrence becomes a width-1 state of its own, checked against the PRG text (up to kPreTextSteps x 16
+// bases). Splitting is exact: a SearchState's interval is a set of suffixes that the reference advances in
+// lock-step (one LF step per suffix, one jump per marker-preceded suffix, vBWT_jump.cpp:94-117); walking
+// them one by one visits the same (suffix, path) pairs. Only the grouping of the final states can differ —
+// two suffixes of one state that both survive to the end of the read stay ONE state in the reference — so
+// a strand with more than one survivor is not finished here but handed to the general search kernel, which
+// redoes it with interval states. False seeds (a 10-mer has several occurrences, one of them real) die in
+// the text check, so the text kernel sees about one survivor per mappable strand.
 // ------------------------------------------------------------------------------------------------
-constexpr uint32_t kPreSteps = 6;
+constexpr uint32_t kPreSteps = 6;       // rank steps at most, while the interval is wide
+constexpr uint32_t kSplitWidth = 4;     // stop narrowing at this many suffixes
+constexpr uint32_t kMaxSplit = 32;      // wider than this after narrowing: general kernel
+constexpr uint32_t kVerifyBases = 12;   // a survivor agrees with the PRG on this many bases beyond the k-mer
+constexpr uint32_t kVerifyIters = 8;    //  ... or has made this many steps / jumps
+constexpr uint32_t kSurvGeneral = 0x10000u;  // surv_cnt flag: the strand is on the general kernel's list
 
 // part 1: k-mer lookup. Returns the number of seed states (0: the strand is already classified).
-GQ_DEV inline uint32_t preseed_lookup(const IndexView& v, const BatchView& b, const SearchOut& o, const SeedOut& pre,
-                                      uint32_t strand, uint32_t& sb) {
+GQ_DEV inline uint32_t preseed_lookup(const IndexView& v, const BatchView& b, const SearchOut& o, uint32_t strand,
+                                      uint32_t& sb) {
   const uint32_t r = strand >> 1;
   const uint32_t L = b.len[r];
   const uint32_t k = v.k;
-  pre.pre_hdr[4 * (size_t)strand + 1] = 0;
   if (L == 0) {  // non-ACGT read, emptied by the encoder: skipped (quasimap.cpp:108-113)
     o.status[strand] = ST_SKIPPED;
     return 0;
@@ -729,119 +746,277 @@ GQ_DEV inline uint32_t preseed_lookup(const IndexView& v, const BatchView& b, co
   return se - sb;
 }
 
-// part 2: pre-extension of ONE seed state j of a strand into record slot `d` (4 words); a seed that
-// dies is marked by d[1] = 0xFFFFFFFF. Returns whether the seed survived.
-constexpr uint32_t kDeadSeed = 0xFFFFFFFFu;
-template <class SuperPtr>
-GQ_DEV inline bool preseed_one(const IndexView& v, SuperPtr super_c, const uint32_t* w, uint32_t L, bool rc, uint32_t j,
-                               uint32_t* d) {
+// the strand goes to the general search kernel (once: whoever sets the flag appends it)
+GQ_DEV inline void send_to_general(const SeedOut& pre, uint32_t strand) {
+#if defined(__CUDA_ARCH__)
+  const uint32_t old = atomicOr(pre.surv_cnt + strand, kSurvGeneral);
+#else
+  const uint32_t old = pre.surv_cnt[strand];
+  pre.surv_cnt[strand] |= kSurvGeneral;
+#endif
+  if (!(old & kSurvGeneral)) pre.gen_list[gq_atomic_add(pre.n_gen, 1u)] = strand;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fast path (text kernel): a strand whose seed pass left exactly ONE survivor is followed to the end of the
+// read by one thread, entirely in text mode: registers + a short local path, no stack, no arena. Jumps are
+// taken from the pre-resolved text-order records (exit of a site, whole-SNP crossing, plain entry);
+// anything else — a jump that needs the general machinery, an interval that widens, a path longer than the
+// local buffers — sends the strand to the general search kernel, which redoes it from the k-mer index (same
+// results: both follow quasimap.cpp:227-268 / vBWT_jump.cpp state by state).
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kFastT = 24;  // (site, allele) pairs
+constexpr uint32_t kFastG = 4;   // open sites
+enum FastResult : uint32_t { FAST_NONE = 0, FAST_DEAD = 1, FAST_MAPPED = 2, FAST_BAIL = 3, FAST_POOL_FULL = 4 };
+
+struct FastLane {
   Lane ln;
-  ln.rd = ReadCursor{w, L, rc ? 1u : 0u, 0, 0, 0};
+  uint32_t nt, ng;
+  uint32_t T[2 * kFastT], G[kFastG];
+  uint32_t result;  // FAST_NONE while running
+  bool p_valid;     // ln.p is the text position of the current suffix
+};
+
+GQ_DEV inline bool fast_running(const FastLane& f) {
+  return f.result == FAST_NONE && (f.ln.state == LS_TEXT || f.ln.state == LS_EV_TSCAN);
+}
+
+// survivor record -> lane. A strand with several survivors is not followed (see above).
+GQ_DEV inline void fast_begin(FastLane& f, const IndexView& v, const BatchView& b, const SeedOut& pre, uint32_t idx) {
+  const uint32_t* rec = pre.rec + 8 * (size_t)idx;
+  const uint32_t w0 = GQ_LDG(rec), counts = GQ_LDG(rec + 2), path_off = GQ_LDG(rec + 3), strand = GQ_LDG(rec + 4);
+  f.ln.strand = strand;
+  f.result = FAST_NONE;
+  f.p_valid = true;
+  f.nt = counts & 0xFFFFu;
+  f.ng = counts >> 16;
+  f.ln.state = LS_IDLE;
+  if (pre.surv_cnt[strand] != 1u || f.nt > kFastT || f.ng > kFastG) {
+    GQ_COUNT(4);  // several survivors / long seed path
+#if defined(GQ_EMU_TRACE)
+    if (gq_emu_counters[4] < 6) {
+      printf("strand %u survivors %u:", strand, pre.surv_cnt[strand]);
+      for (uint32_t q = 0; q < pre.surv_cnt[strand]; ++q) {
+        const uint32_t* r2 = pre.rec + 8 * (size_t)(idx + q);
+        printf(" [pos %u kind %u p %u nt %u ng %u j %u]", r2[0] & 0xFFFFFFF, r2[0] >> 28, r2[1], r2[2] & 0xFFFF, r2[2] >> 16, r2[7]);
+      }
+      printf("\n");
+    }
+#endif
+    f.result = FAST_BAIL;
+    return;
+  }
+  const uint32_t pw = 2 * f.nt + f.ng;
+  for (uint32_t i = 0; i < pw; ++i) {
+    const uint32_t x = GQ_LDG(v.kmer_paths + path_off + i);
+    if (i < 2 * f.nt) f.T[i] = x;
+    else f.G[i - 2 * f.nt] = x;
+  }
+  f.ln.rd = ReadCursor{b.packed + GQ_LDG(rec + 6), GQ_LDG(rec + 5), strand & 1u, 0, 0, 0};
+  f.ln.pos = w0 & 0x0FFFFFFFu;
+  f.ln.kind = w0 >> 28;
+  f.ln.p = GQ_LDG(rec + 1);
+  f.ln.lo = f.ln.hi = 0;
+  f.ln.mr = 0;
+  if (f.ln.pos) {
+    f.ln.rd.seek(f.ln.pos);
+    f.ln.state = LS_TEXT;
+  } else {  // already finished by the seed pass (short read)
+    f.ln.lo = f.ln.hi = GQ_LDG(v.isa + f.ln.p);
+    f.ln.state = LS_EV_TOP;
+  }
+}
+
+// LS_EV_TSCAN: the marker left of the suffix (lane_event_scan's pre-resolved cases, on the local path)
+GQ_DEV inline void fast_event(FastLane& f, const IndexView& v) {
+  Lane& ln = f.ln;
+  const uint32_t* jr = v.tmarker_hit + 8 * (size_t)ln.mr;
+  const uint32_t marker = GQ_LDG(jr), allele = GQ_LDG(jr + 1), jlo = GQ_LDG(jr + 2), jhi = GQ_LDG(jr + 3);
+  const uint32_t snp = GQ_LDG(jr + 4), p_jump = GQ_LDG(jr + 6), p_site = GQ_LDG(jr + 7);
+  if (marker == 0) {
+    f.result = FAST_DEAD;
+    return;
+  }
+  if (jlo == kNoAllele) {  // adjacent markers: general jump machinery
+    GQ_COUNT(5);
+    f.result = FAST_BAIL;
+    return;
+  }
+  if (marker & 1u) {  // leave the site through `allele` (exit_site_in_place)
+    if (jlo != jhi || f.nt == kFastT) {
+      f.result = FAST_BAIL;
+      return;
+    }
+    if (f.ng > 0) --f.ng;
+    f.T[2 * f.nt] = marker;
+    f.T[2 * f.nt + 1] = allele;
+    ++f.nt;
+    ln.p = p_jump;
+    ln.kind = K_READY;
+    ln.state = LS_TEXT;
+    return;
+  }
+  // enter the site from its right end and consume the next base
+  const uint32_t c = ln.rd.peek();
+  if (snp != kNotSnp && ln.pos >= 2) {  // site of distinct single-base alleles: entry, base, exit
+    const uint32_t a = (snp >> (8 * c)) & 0xFFu;
+    if (a == 0xFFu) {
+      f.result = FAST_DEAD;
+      return;
+    }
+    if (f.nt == kFastT) {
+      f.result = FAST_BAIL;
+      return;
+    }
+    f.T[2 * f.nt] = marker - 1;
+    f.T[2 * f.nt + 1] = a;
+    ++f.nt;
+    ln.p = p_site;
+    ln.pos -= 1;
+    ln.rd.advance();
+    ln.kind = K_READY;
+    ln.state = LS_TEXT;
+    return;
+  }
+  if (f.ng == kFastG) {
+    f.result = FAST_BAIL;
+    return;
+  }
+  f.G[f.ng++] = marker - 1;
+  const uint32_t slot = (marker - 6) >> 1;
+  const uint32_t nlo = GQ_LDG(v.entry_next + 8 * slot + 2 * c), nhi = GQ_LDG(v.entry_next + 8 * slot + 2 * c + 1);
+  if (nhi + 1 <= nlo) {  // no allele ends in c
+    f.result = FAST_DEAD;
+    return;
+  }
+  if (nlo != nhi) {  // several alleles end in c
+    GQ_COUNT(6);
+    f.result = FAST_BAIL;
+    return;
+  }
+  ln.rd.advance();
+  ln.kind = K_SCAN;
+  if (--ln.pos == 0) {
+    ln.lo = ln.hi = nlo;
+    f.p_valid = false;
+    ln.state = LS_EV_TOP;
+  } else {
+    ln.p = GQ_LDG(v.sa + nlo);
+    ln.state = LS_TEXT;
+  }
+}
+
+// Seed pass, part 2: ONE seed state j of a strand. Returns bit 0: some suffix survived (survivor records
+// written), bit 1: the strand needs the general kernel. A suffix survives if kVerifyBases further bases of
+// the read agree with the PRG along its walk (text steps and pre-resolved jumps, path not recorded); the
+// survivor record holds the state as it was seeded and the text kernel walks it again, with its path.
+template <class SuperPtr>
+GQ_DEV inline uint32_t seed_state_split(const IndexView& v, SuperPtr super_c, const SeedOut& pre, const uint32_t* w,
+                                        uint32_t L, uint32_t woff, uint32_t strand, uint32_t j) {
+  Lane ln;
+  ln.rd = ReadCursor{w, L, strand & 1u, 0, 0, 0};
   const KmerState ks = v.kmer_states[j];
   ln.pos = L - v.k;
   ln.lo = ks.lo;
   ln.hi = ks.hi;
+  ln.p = 0;
+  ln.mr = 0;
   ln.kind = K_SCAN;
-  ln.state = ln.pos == 0 ? LS_EV_TOP : (ln.lo == ln.hi ? LS_RUN : LS_RUNW);
-  if (ln.pos) ln.rd.seek(ln.pos);
-  // never consume the last base here: the finished state is emitted by the search kernel
-  const uint32_t max_steps = ln.pos > 1 ? (ln.pos - 1 < kPreSteps ? ln.pos - 1 : kPreSteps) : 0;
-  for (uint32_t s = 0; s < max_steps && (ln.state == LS_RUN || ln.state == LS_RUNW); ++s) {
-    if (ln.state == LS_RUN) lane_step(ln, v, super_c);
-    else lane_step_wide(ln, v, super_c);
+  if (ln.pos == 0) {  // the seed states are the final states
+    GQ_COUNT(0);
+    return 2u;
   }
-  const bool alive = ln.state != LS_EV_POP;
-  d[0] = alive ? (ln.pos | (ln.kind << 28)) : kDeadSeed;
-  if (alive) {
-    d[1] = ln.lo;
-    d[2] = ln.hi;
-    d[3] = ks.counts;
-    d[4] = ks.path_off;
-    const uint32_t pw = 2 * (ks.counts & 0xFFFFu) + (ks.counts >> 16);
-    d[5] = pw > 0 ? GQ_LDG(v.kmer_paths + ks.path_off) : 0;
-    d[6] = pw > 1 ? GQ_LDG(v.kmer_paths + ks.path_off + 1) : 0;
+  ln.rd.seek(ln.pos);
+  ln.state = ln.lo == ln.hi ? LS_RUN : LS_RUNW;
+  for (uint32_t s = 0; s < kPreSteps && ln.state == LS_RUNW && ln.hi - ln.lo >= kSplitWidth && ln.pos > 1; ++s)
+    lane_step_wide(ln, v, super_c);
+  if (ln.state == LS_EV_POP) return 0u;
+  // LS_RUN / LS_RUNW / LS_EV_SCAN (a marker inside the interval: every suffix checks its own symbol)
+  if (ln.state == LS_EV_WIDE || ln.hi - ln.lo >= kMaxSplit) {
+    GQ_COUNT(1);
+    return 2u;
+  }
+  GQ_COUNT(2);                                               // seed states split
+  GQ_COUNT(16 + (ln.hi - ln.lo < 15 ? ln.hi - ln.lo : 15));  // histogram of split widths
+  uint32_t out = 0;
+  const ReadCursor rd0 = ln.rd;
+  const uint32_t pos0 = ln.pos, kind0 = ln.kind, lo = ln.lo, hi = ln.hi;
+  for (uint32_t i = lo; i <= hi; ++i) {
+    FastLane f;
+    f.nt = f.ng = 0;
+    f.result = FAST_NONE;
+    f.p_valid = true;
+    f.ln.rd = rd0;
+    f.ln.pos = pos0;
+    f.ln.kind = kind0;
+    f.ln.lo = f.ln.hi = f.ln.mr = 0;
+    const uint32_t p_seed = GQ_LDG(v.sa + i);
+    f.ln.p = p_seed;
+    f.ln.state = LS_TEXT;
+    for (uint32_t it = 0; it < kVerifyIters && fast_running(f) && pos0 - f.ln.pos < kVerifyBases; ++it) {
+      if (f.ln.state == LS_TEXT) lane_text_step(f.ln, v);
+      if (f.ln.state == LS_EV_TSCAN) fast_event(f, v);
+    }
+    if (f.result == FAST_DEAD || f.ln.state == LS_EV_POP) continue;
+    GQ_COUNT(3);  // survivors
+    const uint32_t idx = gq_atomic_inc_aggregated(pre.n_surv);
+    if (idx >= pre.cap) {  // survivor pool full
+      out |= 2u;
+      continue;
+    }
+    uint32_t* d = pre.rec + 8 * (size_t)idx;
+    d[0] = pos0 | (kind0 << 28);
+    d[1] = p_seed;
+    d[2] = ks.counts;
+    d[3] = ks.path_off;
+    d[4] = strand;
+    d[5] = L;
+    d[6] = woff;
     d[7] = j;
+    gq_atomic_add(pre.surv_cnt + strand, 1u);
+    out |= 1u;
   }
-  return alive;
+  return out;
 }
 
-// per-strand form (host emulation; the kernel spreads the seeds of 32 strands over the lanes of a warp)
-template <class SuperPtr>
-GQ_DEV inline void preseed_extend(const IndexView& v, SuperPtr super_c, const BatchView& b, const SearchOut& o,
-                                  const SeedOut& pre, uint32_t strand, uint32_t sb, uint32_t n, uint32_t base) {
-  if (base + n > pre.cap) {  // record pool full: re-run later, seeded inside the search kernel
-    o.status[strand] = ST_OVERFLOW;
-    o.overflow_list[gq_atomic_add(o.n_overflow, 1u)] = strand;
-    return;
+// after the walk: classify the outcome; for a finished state, settle its record (encapsulated_search.cpp:30-88
+// for a path-less one) and return the pool words it needs (0 otherwise)
+GQ_DEV inline uint32_t fast_outcome(FastLane& f, const IndexView& v) {
+  if (f.result != FAST_NONE) return 0;
+  if (f.ln.state != LS_EV_TOP) {
+    f.result = FAST_DEAD;
+    return 0;
   }
-  const uint32_t r = strand >> 1;
-  bool any = false;
-  for (uint32_t t = 0; t < n; ++t)
-    any |= preseed_one(v, super_c, b.packed + b.word_off[r], b.len[r], (strand & 1u) != 0, sb + t,
-                       pre.rec + 8 * (size_t)(base + t));
-  uint32_t* h = pre.pre_hdr + 4 * (size_t)strand;
-  h[0] = base;
-  h[1] = n;
-  h[2] = b.len[r];
-  h[3] = b.word_off[r];
-  if (!any) o.status[strand] = ST_UNCLASSIFIED;
-  else pre.live_list[gq_atomic_inc_aggregated(pre.n_live)] = strand;
-}
-
-template <class SuperPtr>
-GQ_DEV inline void preseed_strand(const IndexView& v, SuperPtr super_c, const BatchView& b, const SearchOut& o,
-                                  const SeedOut& pre, uint32_t strand) {
-  uint32_t sb = 0;
-  const uint32_t n = preseed_lookup(v, b, o, pre, strand, sb);
-  if (n) preseed_extend(v, super_c, b, o, pre, strand, sb, n, gq_atomic_add(pre.used, n));
-}
-
-// Start a pre-seeded strand on this lane: its surviving seed states become the initial stack. Everything
-// comes from the strand header + its seed records (two dependent loads); the k-mer index is only
-// touched for seeds whose path is longer than the two words kept inline.
-GQ_DEV inline void lane_refill_pre(Lane& ln, const IndexView& v, const BatchView& b, const SearchOut& o,
-                                   const SeedOut& pre, uint32_t strand, uint32_t* arena, uint32_t arena_words) {
-  const uint32_t* h = pre.pre_hdr + 4 * (size_t)strand;
-  const uint32_t p0 = GQ_LDG(h), n = GQ_LDG(h + 1), L = GQ_LDG(h + 2), woff = GQ_LDG(h + 3);
-  ln.strand = strand;
-  ln.rd = ReadCursor{b.packed + woff, L, strand & 1u, 0, 0, 0};
-  ln.s.mem = arena;
-  ln.s.limit = arena_words;
-  ln.s.overflow = false;
-  ln.s.top = kNoAllele;
-  ln.n_states = 0;
-  ln.arena_words = arena_words;
-  uint32_t sp = 0;
-  for (uint32_t i = 0; i < n; ++i) {
-    const uint32_t* rec = pre.rec + 8 * (size_t)(p0 + i);
-    const uint32_t w0 = GQ_LDG(rec);
-    if (w0 == kDeadSeed) continue;
-    const uint32_t counts = GQ_LDG(rec + 3);
-    const uint32_t words = entry_words(counts);
-    if (sp + words + 3 > ln.s.limit) {
-      ln.s.overflow = true;
-      break;
+  f.result = FAST_MAPPED;
+  GQ_COUNT(7);  // strands finished by the fast path
+  if (!(f.nt | f.ng)) {
+    const uint32_t pf = f.p_valid ? f.ln.p : GQ_LDG(v.sa + f.ln.lo);
+    const Node& nd = v.nodes[GQ_LDG(v.pos2node + pf)];
+    if (nd.site != 0) {
+      f.T[0] = nd.site;
+      f.T[1] = (uint32_t)nd.allele;
+      f.nt = 1;
     }
-    uint32_t* t = ln.s.mem + sp;
-    t[0] = w0;
-    t[1] = GQ_LDG(rec + 1);
-    t[2] = GQ_LDG(rec + 2);
-    t[3] = counts;
-    t[4] = ln.s.top;
-    if (words > kHdr) t[kHdr] = GQ_LDG(rec + 5);
-    if (words > kHdr + 1) t[kHdr + 1] = GQ_LDG(rec + 6);
-    if (words > kHdr + 2) {
-      const uint32_t path_off = GQ_LDG(rec + 4);
-      for (uint32_t w = kHdr + 2; w < words; ++w) t[w] = GQ_LDG(v.kmer_paths + path_off + (w - kHdr));
-    }
-    ln.s.top = sp;
-    sp += words;
   }
-  if (ln.s.overflow || ln.s.top == kNoAllele) {
-    lane_finish_strand(ln, o);
-    return;
+  return 4 + 2 * f.nt + 2 * f.ng;
+}
+
+// write the single final state of the strand at pool offset `off`
+GQ_DEV inline void fast_emit(const FastLane& f, const SearchOut& o, uint32_t off) {
+  uint32_t* d = o.pool + off;
+  d[0] = f.ln.lo;
+  d[1] = f.ln.hi;
+  d[2] = f.nt;
+  d[3] = f.ng;
+  for (uint32_t j = 0; j < 2 * f.nt; ++j) d[4 + j] = f.T[j];
+  for (uint32_t j = 0; j < f.ng; ++j) {
+    d[4 + 2 * f.nt + 2 * j] = f.G[j];
+    d[4 + 2 * f.nt + 2 * j + 1] = kNoAllele;
   }
-  lane_load_top(ln);
+  const uint32_t strand = f.ln.strand;
+  o.st_off[strand] = off;
+  o.st_words[strand] = 4 + 2 * f.nt + 2 * f.ng;
+  o.st_count[strand] = 1;
 }
 
 // all_read_kmers_occur_in_index (quasimap.cpp:212-225) for a strand whose search found nothing:
@@ -877,25 +1052,60 @@ GQ_DEV inline void classify_strand(const IndexView& v, const BatchView& b, const
   o.status[strand] = missing ? ST_MISSING_KMER : ST_NO_EXTENSION;
 }
 
-// Single-lane driver (host emulation and a reference for the kernels): seed pass, then the lane state
-// machine on the survivors, then the k-mer filter if nothing mapped. A strand the seed pass could not
-// place (record pool full) is seeded directly from the k-mer index, as the overflow re-runs do.
+// Single-lane driver (host emulation and a reference for the kernels): seed pass, text fast path for a
+// single survivor, else the general lane state machine seeded from the k-mer index; then the k-mer filter
+// if nothing mapped.
 GQ_DEV inline void map_strand(const IndexView& v, const uint32_t* super_cnt, const BatchView& b, const SearchOut& o,
                               const SeedOut& pre, uint32_t strand, uint32_t* arena, uint32_t arena_words) {
   Lane ln;
   ln.state = LS_IDLE;
-  if (o.status[strand] == ST_OVERFLOW) {
-    lane_refill(ln, v, b, o, strand, arena, arena_words);
-  } else {
-    preseed_strand(v, super_cnt, b, o, pre, strand);
-    if (o.status[strand] == ST_OVERFLOW) return;
-    if (pre.pre_hdr[4 * (size_t)strand + 1]) lane_refill_pre(ln, v, b, o, pre, strand, arena, arena_words);
+  bool general = o.status[strand] == ST_OVERFLOW;  // overflow re-runs always use the general machinery
+  if (!general) {
+    uint32_t sb = 0;
+    const uint32_t ns = preseed_lookup(v, b, o, strand, sb);
+    if (ns == 0) return;
+    const uint32_t r = strand >> 1;
+    const uint32_t first = *pre.n_surv;
+    pre.surv_cnt[strand] = 0;
+    uint32_t flags = 0;
+    for (uint32_t t = 0; t < ns; ++t)
+      flags |= seed_state_split(v, super_cnt, pre, b.packed + b.word_off[r], b.len[r], b.word_off[r], strand, sb + t);
+    if (flags & 2u) general = true;
+    else if (!(flags & 1u)) o.status[strand] = ST_UNCLASSIFIED;
+    else {
+      FastLane f;
+      fast_begin(f, v, b, pre, first);
+      while (fast_running(f)) {
+        if (f.ln.state == LS_TEXT) lane_text_step(f.ln, v);
+        if (f.ln.state == LS_EV_TSCAN) fast_event(f, v);
+      }
+      const uint32_t words = fast_outcome(f, v);
+      if (f.result == FAST_MAPPED) {
+        const uint32_t off = gq_atomic_add(o.pool_used, words);
+        if (off + words > o.pool_cap) {
+          o.status[strand] = ST_OVERFLOW;
+          o.overflow_list[gq_atomic_add(o.n_overflow, 1u)] = strand;
+          return;
+        }
+        fast_emit(f, o, off);
+        o.status[strand] = ST_MAPPED;
+        o.mapped_list[gq_atomic_inc_aggregated(o.n_mapped)] = strand;
+      } else if (f.result == FAST_DEAD)
+        o.status[strand] = ST_UNCLASSIFIED;
+      else
+        general = true;
+    }
+    *pre.n_surv = first;  // the emulation reuses the survivor pool strand by strand
   }
-  while (ln.state != LS_IDLE) {
-    if (ln.state == LS_RUN) lane_to_text(ln, v);
-    else if (ln.state == LS_TEXT) lane_text_step(ln, v);
-    else if (ln.state == LS_RUNW) lane_step_wide(ln, v, super_cnt);
-    else lane_event(ln, v, o);
+  if (general) {
+    GQ_COUNT(8);  // strands through the general machinery
+    lane_refill(ln, v, b, o, strand, arena, arena_words);
+    while (ln.state != LS_IDLE) {
+      if (ln.state == LS_RUN) lane_to_text(ln, v);
+      else if (ln.state == LS_TEXT) lane_text_step(ln, v);
+      else if (ln.state == LS_RUNW) lane_step_wide(ln, v, super_cnt);
+      else lane_event(ln, v, o);
+    }
   }
   if (o.status[strand] == ST_UNCLASSIFIED) classify_strand(v, b, o, strand);
 }

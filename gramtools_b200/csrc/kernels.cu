@@ -121,8 +121,8 @@ __device__ __forceinline__ bool warp_any_kmer_missing(const IndexView& v, const 
   return missing;
 }
 
-// Seed pass: thread per strand (see preseed_strand). Superblock counters come from shared memory when
-// they fit, like in the search kernel.
+// Seed pass (seed_state_split). Superblock counters come from shared memory when they fit, like in the
+// search kernel.
 template <bool SUPER_SMEM>
 __global__ void __launch_bounds__(256)
     seed_kernel(IndexView v, BatchView b, SearchOut o, SeedOut pre, uint32_t n_super_smem) {
@@ -132,15 +132,14 @@ __global__ void __launch_bounds__(256)
   const uint32_t n = 2 * (b.read_end - b.read_begin);
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t full = 0xFFFFFFFFu;
-  // Warp-convergent rounds of 32 strands. Phase A: every lane looks up the seeds of its strand and one
-  // atomic allocates the record slots of the whole round. Phase B: the seeds of the round (about 3 per
-  // strand) are spread evenly over the lanes, so lanes run the same short pre-extension loop instead of
-  // per-strand loops of very different lengths.
+  // Warp-convergent rounds of 32 strands. Phase A: every lane looks up the seed states of its strand.
+  // Phase B: the seed states of the round (about 1.5 per strand) are spread evenly over the lanes, so lanes
+  // run the same short narrowing / splitting code instead of per-strand loops of very different lengths.
   for (uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; i0 < n; i0 += gridDim.x * blockDim.x) {
     const uint32_t i = i0 + lane;
     const uint32_t strand = 2 * b.read_begin + i;
     uint32_t sb = 0;
-    const uint32_t ns = i < n ? preseed_lookup(v, b, o, pre, strand, sb) : 0;
+    const uint32_t ns = i < n ? preseed_lookup(v, b, o, strand, sb) : 0;
     uint32_t incl = ns;  // inclusive warp scan
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -149,27 +148,11 @@ __global__ void __launch_bounds__(256)
     }
     const uint32_t total = __shfl_sync(full, incl, 31);
     if (total == 0) continue;
-    uint32_t base = 0;
-    if (lane == 31) base = atomicAdd(pre.used, total);
-    base = __shfl_sync(full, base, 31);
-    if (base + total > pre.cap) {  // record pool full: these strands are re-run, seeded inside the search kernel
-      if (ns) {
-        o.status[strand] = ST_OVERFLOW;
-        o.overflow_list[atomicAdd(o.n_overflow, 1u)] = strand;
-      }
-      continue;
-    }
     const uint32_t r = strand >> 1;
-    const uint32_t my_L = ns ? b.len[r] : 0;
-    const uint64_t my_w = ns ? (uint64_t)(b.packed + b.word_off[r]) : 0ull;
-    if (ns) {
-      uint32_t* h = pre.pre_hdr + 4 * (size_t)strand;
-      h[0] = base + incl - ns;
-      h[1] = ns;
-      h[2] = my_L;
-      h[3] = b.word_off[r];
-    }
-    uint32_t alive = 0;
+    const uint32_t my_L = ns ? b.len[r] : 0, my_woff = ns ? b.word_off[r] : 0;
+    if (ns) pre.surv_cnt[strand] = 0;
+    __syncwarp();
+    uint32_t alive = 0, general = 0;
     for (uint32_t t0 = 0; t0 < total; t0 += 32) {
       const uint32_t t = t0 + lane;
       // owner of task t = first lane whose inclusive count exceeds t
@@ -183,19 +166,18 @@ __global__ void __launch_bounds__(256)
       }
       const uint32_t owner = hi_l;
       const uint32_t o_incl = __shfl_sync(full, incl, owner), o_ns = __shfl_sync(full, ns, owner),
-                     o_sb = __shfl_sync(full, sb, owner), o_L = __shfl_sync(full, my_L, owner);
-      const uint64_t o_w = __shfl_sync(full, my_w, owner);
-      bool survived = false;
+                     o_sb = __shfl_sync(full, sb, owner), o_L = __shfl_sync(full, my_L, owner),
+                     o_woff = __shfl_sync(full, my_woff, owner);
+      uint32_t flags = 0;
       if (t < total)
-        survived = preseed_one(v, SUPER_SMEM ? (const uint32_t*)s_super : v.super_cnt, (const uint32_t*)o_w, o_L,
-                               ((i0 + owner) & 1u) != 0, o_sb + (t - (o_incl - o_ns)), pre.rec + 8 * (size_t)(base + t));
-      alive |= __reduce_or_sync(full, survived ? (1u << owner) : 0u);
+        flags = seed_state_split(v, SUPER_SMEM ? (const uint32_t*)s_super : v.super_cnt, pre, b.packed + o_woff, o_L,
+                                 o_woff, 2 * b.read_begin + i0 + owner, o_sb + (t - (o_incl - o_ns)));
+      alive |= __reduce_or_sync(full, (flags & 1u) ? (1u << owner) : 0u);
+      general |= __reduce_or_sync(full, (flags & 2u) ? (1u << owner) : 0u);
     }
     if (ns) {
-      // (classifying the dead strands right here was measured: slower than the separate warp-per-strand
-      // classify_kernel, which hides the dependent loads behind many more resident warps)
-      if ((alive >> lane) & 1u) pre.live_list[gq_atomic_inc_aggregated(pre.n_live)] = strand;
-      else o.status[strand] = ST_UNCLASSIFIED;
+      if ((general >> lane) & 1u) send_to_general(pre, strand);
+      else if (!((alive >> lane) & 1u)) o.status[strand] = ST_UNCLASSIFIED;
     }
   }
 }
@@ -211,6 +193,73 @@ void launch_seed(const IndexView& v, const BatchView& b, const SearchOut& o, con
     seed_kernel<false><<<blocks, 256, 0, st>>>(v, b, o, pre, 0);
 }
 
+// Fast path: one thread per survivor record of the seed pass, 32 records per warp round. The walk is ONE
+// warp-convergent loop — text step for the lanes in text mode, then the jump for the lanes that reached a
+// marker — so lanes meet again every iteration; the round ends with a convergent emission phase (one pool
+// allocation and one mapped-list allocation per warp).
+__global__ void __launch_bounds__(256) text_kernel(IndexView v, BatchView b, SearchOut o, SeedOut pre) {
+  const uint32_t n = min(*pre.n_surv, pre.cap);
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t full = 0xFFFFFFFFu;
+  for (uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; i0 < n; i0 += gridDim.x * blockDim.x) {
+    const uint32_t i = i0 + lane;
+    FastLane f;
+    f.result = FAST_DEAD;
+    f.ln.state = LS_IDLE;
+    f.ln.strand = 0;
+    if (i < n) fast_begin(f, v, b, pre, i);
+    while (__any_sync(full, fast_running(f))) {
+      if (fast_running(f) && f.ln.state == LS_TEXT) lane_text_step(f.ln, v);
+      if (fast_running(f) && f.ln.state == LS_EV_TSCAN) fast_event(f, v);
+    }
+    const uint32_t words = i < n ? fast_outcome(f, v) : 0;
+    // pool space for the finished states of the round: warp scan + one atomic
+    uint32_t incl = words;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t t = __shfl_up_sync(full, incl, d);
+      if (lane >= (uint32_t)d) incl += t;
+    }
+    const uint32_t total = __shfl_sync(full, incl, 31);
+    uint32_t base = 0;
+    if (total && lane == 31) base = atomicAdd(o.pool_used, total);
+    base = __shfl_sync(full, base, 31);
+    const uint32_t strand = f.ln.strand;
+    bool mapped = false;
+    if (i < n) {
+      if (f.result == FAST_MAPPED) {
+        const uint32_t off = base + incl - words;
+        if (off + words > o.pool_cap) {  // final-state pool full: re-run after the host has grown it
+          o.status[strand] = ST_OVERFLOW;
+          o.overflow_list[atomicAdd(o.n_overflow, 1u)] = strand;
+        } else {
+          fast_emit(f, o, off);
+          o.status[strand] = ST_MAPPED;
+          mapped = true;
+        }
+      } else if (f.result == FAST_DEAD) {
+        o.status[strand] = ST_UNCLASSIFIED;
+      } else {
+        send_to_general(pre, strand);
+      }
+    }
+    const uint32_t mm = __ballot_sync(full, mapped);
+    if (mm) {
+      uint32_t mbase = 0;
+      if (lane == 0) mbase = atomicAdd(o.n_mapped, (uint32_t)__popc(mm));
+      mbase = __shfl_sync(full, mbase, 0);
+      if (mapped) o.mapped_list[mbase + __popc(mm & ((1u << lane) - 1u))] = strand;
+    }
+  }
+}
+
+void launch_text(const IndexView& v, const BatchView& b, const SearchOut& o, const SeedOut& pre, cudaStream_t st) {
+  uint32_t work = 2 * (b.read_end - b.read_begin);
+  if (work == 0) return;
+  uint32_t blocks = min((work / 2 + 255) / 256, 148u * 8u);
+  text_kernel<<<blocks, 256, 0, st>>>(v, b, o, pre);
+}
+
 #ifdef GQ_DEBUG_COUNTERS
 __device__ unsigned long long g_dbg[32];
 #define DBG(i, v) do { if (lane == 0) atomicAdd(&g_dbg[i], (unsigned long long)(v)); } while (0)
@@ -222,16 +271,16 @@ template <bool SUPER_SMEM>
 __global__ void __launch_bounds__(kSearchThreads, GQ_SEARCH_MIN_BLOCKS)
     search_kernel(IndexView v, BatchView b, SearchOut o, uint32_t* arena, uint32_t arena_words,
                   const uint32_t* list, uint32_t n_list, uint32_t n_super_smem, uint32_t rf_thresh,
-                  uint32_t ev_thresh, uint32_t wait_max, uint32_t leave, SeedOut pre) {
+                  uint32_t ev_thresh, uint32_t wait_max, uint32_t leave, const uint32_t* n_list_dev) {
   extern __shared__ __align__(128) uint32_t s_super[];  // n_super_smem x 16 B (dynamic: keeps 5 CTAs/SM)
   __shared__ alignas(8) uint64_t s_bar;
+  // work items: a list of strands (the seed pass's general list, overflow re-runs) or the whole slice
+  const uint32_t* work_list = list;
+  const uint32_t work = list ? (n_list_dev ? *n_list_dev : n_list) : 2 * (b.read_end - b.read_begin);
+  if (work == 0) return;
   if (SUPER_SMEM) tma_stage_super(s_super, v.super_cnt, n_super_smem * 16u, &s_bar);
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t lane = threadIdx.x & 31u;
-  // work items: a list of strands (overflow re-runs), the live list of the seed pass, or the whole slice
-  const bool pre_seeded = !list && pre.rec != nullptr;
-  const uint32_t* work_list = list ? list : (pre_seeded ? pre.live_list : nullptr);
-  const uint32_t work = list ? n_list : (pre_seeded ? *pre.n_live : 2 * (b.read_end - b.read_begin));
   const uint32_t strand0 = 2 * b.read_begin;
   bool work_left = work > 0;  // warp-uniform: strands are handed out by one global counter
   uint32_t* my_arena = arena + (size_t)tid * arena_words;
@@ -289,8 +338,7 @@ __global__ void __launch_bounds__(kSearchThreads, GQ_SEARCH_MIN_BLOCKS)
         uint32_t i = base + __popc(idle & ((1u << lane) - 1u));
         if (i < work) {
           const uint32_t strand = work_list ? work_list[i] : strand0 + i;
-          if (pre_seeded) lane_refill_pre(ln, v, b, o, pre, strand, my_arena, arena_words);
-          else lane_refill(ln, v, b, o, strand, my_arena, arena_words);
+          lane_refill(ln, v, b, o, strand, my_arena, arena_words);
         }
       }
       work_left = base + c_idle < work;
@@ -365,9 +413,7 @@ void debug_counters(unsigned long long* out32) {
 void launch_search(const IndexView& v, const BatchView& b, const SearchOut& o, uint32_t* arena,
                    uint32_t arena_words, uint32_t n_threads, const uint32_t* list, uint32_t n_list,
                    bool super_in_smem, uint32_t rf_thresh, uint32_t ev_thresh, cudaStream_t st, uint32_t leave_opt,
-                   uint32_t wait_opt, const SeedOut* pre) {
-  SeedOut pz{};
-  if (pre && !list) pz = *pre;
+                   uint32_t wait_opt, const uint32_t* n_list_dev) {
   uint32_t work = list ? n_list : 2 * (b.read_end - b.read_begin);
   if (work == 0) return;
   uint32_t blocks = (min(work, n_threads) + kSearchThreads - 1) / kSearchThreads;
@@ -379,10 +425,10 @@ void launch_search(const IndexView& v, const BatchView& b, const SearchOut& o, u
   uint32_t leave = leave_opt ? leave_opt : max(1u, ev_thresh / 2);
   if (n_super_smem)
     search_kernel<true><<<blocks, kSearchThreads, n_super_smem * 16, st>>>(v, b, o, arena, arena_words, list, n_list, n_super_smem,
-                                                           rf_thresh, ev_thresh, wait_max, leave, pz);
+                                                           rf_thresh, ev_thresh, wait_max, leave, n_list_dev);
   else
     search_kernel<false><<<blocks, kSearchThreads, 0, st>>>(v, b, o, arena, arena_words, list, n_list, 0, rf_thresh,
-                                                            ev_thresh, wait_max, leave, pz);
+                                                            ev_thresh, wait_max, leave, n_list_dev);
 }
 
 // ------------------------------------------------------------------------------------------------

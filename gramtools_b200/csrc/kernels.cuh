@@ -38,17 +38,16 @@ struct SearchOut {
   uint32_t* work_counter;   // dynamic work distribution of the search kernel
 };
 
-// Output of the seed pass (seed_kernel): per strand, the seed states of its last k-mer that are still
-// alive after a few marker-free extension steps. Most seeds of a strand that cannot map die there, so the
-// warp-synchronous search kernel only sees strands with real work.
+// Output of the seed pass (seed_kernel): the width-1 states (one suffix each, in text mode) that survived the
+// text check, as records for the text kernel, plus the strands that need the general search kernel.
 struct SeedOut {
-  uint32_t* rec;        // 8 words (one sector) per seed: {pos | kind << 28 (or dead), lo, hi, nt | ng << 16,
-                        //  path_off, first two path words, k-mer state index}: all the search kernel needs
-  uint32_t cap;         // seed records available
-  uint32_t* used;       // bump pointer
-  uint32_t* pre_hdr;    // 4 words per strand: {first record, number of records, read length, packed word offset}
-  uint32_t* live_list;  // strands with >= 1 survivor (work list of the search kernel)
-  uint32_t* n_live;
+  uint32_t* rec;        // 8 words (one sector) per survivor: {pos | kind << 28, text position, nt | ng << 16,
+                        //  path_off (k-mer index), strand, read length, packed word offset, k-mer state index}
+  uint32_t cap;         // survivor records available
+  uint32_t* n_surv;     // bump pointer
+  uint32_t* surv_cnt;   // per strand: survivors | kSurvGeneral once the strand is on gen_list
+  uint32_t* gen_list;   // strands for the general search kernel (several survivors, wide or finished seed
+  uint32_t* n_gen;      //  states, jumps the text kernel does not take)
 };
 
 struct CoverageView {
@@ -72,15 +71,19 @@ struct CoverageView {
 void launch_pack(const uint8_t* bases, const uint64_t* offsets, uint32_t r0, uint32_t r1, uint32_t* word_off,
                  uint32_t* packed, uint32_t* len, cudaStream_t st);
 
-// list == nullptr: all reads of the batch (one thread per read, both strands);
-// otherwise only the listed strands (overflow re-runs with a larger arena).
+// Seed pass over the strands of the slice b.read_begin..b.read_end.
 void launch_seed(const IndexView& v, const BatchView& b, const SearchOut& o, const SeedOut& pre, cudaStream_t st);
 
-// pre == nullptr (or list != nullptr): strands are seeded from the k-mer index inside the kernel.
+// Fast path over the survivor records: strands with one survivor are finished in text mode; the rest is
+// appended to pre.gen_list.
+void launch_text(const IndexView& v, const BatchView& b, const SearchOut& o, const SeedOut& pre, cudaStream_t st);
+
+// General search kernel. list == nullptr: every strand of the slice; otherwise the listed strands (n_list of
+// them, or *n_list_dev when that pointer is given). Strands are seeded from the k-mer index in the kernel.
 void launch_search(const IndexView& v, const BatchView& b, const SearchOut& o, uint32_t* arena,
                    uint32_t arena_words, uint32_t n_threads, const uint32_t* list, uint32_t n_list,
                    bool super_in_smem, uint32_t rf_thresh, uint32_t ev_thresh, cudaStream_t st,
-                   uint32_t leave_opt = 0, uint32_t wait_opt = 0, const SeedOut* pre = nullptr);
+                   uint32_t leave_opt = 0, uint32_t wait_opt = 0, const uint32_t* n_list_dev = nullptr);
 
 // list == nullptr: the strands in o.mapped_list[0, *o.n_mapped); otherwise the listed strands.
 void launch_coverage(const IndexView& v, const BatchView& b, const SearchOut& o, const CoverageView& c,

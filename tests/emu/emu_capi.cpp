@@ -10,10 +10,14 @@
 #include <string>
 #include <vector>
 
+#define GQ_EMU_COUNTERS 1
 #include "../../gramtools_b200/csrc/gq_device.cuh"
 #include "../../gramtools_b200/csrc/index_build.hpp"
 
 using namespace gq;
+namespace gq {
+unsigned long long gq_emu_counters[32];
+}
 
 struct Emu {
   HostIndex h;
@@ -136,9 +140,8 @@ int emu_map(void* ev, const uint8_t* bases, const uint64_t* off, uint64_t n_read
     c.error_flags = &e->gsmall[1];
     c.stats = e->stats;
     c.allele_off = h.allele_off.data();
-    std::vector<uint32_t> seed_rec(8 * std::max<size_t>(1024, 64 * n_reads)), pre_hdr(8 * n_reads + 4),
-        live(2 * n_reads + 1), pre_small(2, 0);
-    SeedOut pre{seed_rec.data(), (uint32_t)(seed_rec.size() / 8), &pre_small[0], pre_hdr.data(), live.data(),
+    std::vector<uint32_t> seed_rec(8 * 4096), surv_cnt(2 * n_reads + 1, 0), gen(2 * n_reads + 1), pre_small(2, 0);
+    SeedOut pre{seed_rec.data(), (uint32_t)(seed_rec.size() / 8), &pre_small[0], surv_cnt.data(), gen.data(),
                 &pre_small[1]};
     std::vector<uint32_t> arena(arena_words), big;
     for (uint32_t s = 0; s < 2 * n_reads; ++s) {
@@ -179,6 +182,12 @@ int emu_map(void* ev, const uint8_t* bases, const uint64_t* off, uint64_t n_read
   } catch (const std::exception& ex) {
     g_err = ex.what();
     return -1;
+  }
+}
+void emu_path_counters(uint64_t* out32, int reset) {
+  for (int i = 0; i < 32; ++i) {
+    out32[i] = gq_emu_counters[i];
+    if (reset) gq_emu_counters[i] = 0;
   }
 }
 uint64_t emu_reruns(void* ev) { return ((Emu*)ev)->reruns; }
