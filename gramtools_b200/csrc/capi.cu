@@ -71,8 +71,8 @@ struct gq_index {
   DevBuf<uint8_t> status;
   DevBuf<uint32_t> st_off, st_words, st_count, pool, small;  // small: [pool_used, n_overflow, n_cov_overflow]
   DevBuf<uint32_t> overflow_list, cov_overflow_list, mapped_list;
-  DevBuf<uint32_t> seed_rec, surv_cnt, gen_list;  // seed pass (SeedOut): survivor records, per-strand counts, general list
-  uint32_t seed_recs_per_read = 4;  // survivor records per read (both strands); a full pool sends strands to the general kernel
+  DevBuf<uint32_t> seed_rec, surv_rec, surv_cnt, gen_list;  // seed pass (SeedOut): survivor records, per-strand counts, general list
+  uint32_t seed_recs_per_read = 16;  // candidate records per read (set from the index: ~2.5 x mean suffixes per indexed k-mer, both strands); a full pool sends strands to the general kernel
   bool use_seed_pass = true;
   DevBuf<uint32_t> arena, big_arena;
   cudaStream_t copy_stream = nullptr;
@@ -249,10 +249,11 @@ static void do_map(gq_index* ix, const uint8_t* h_bases = nullptr, const uint64_
   ix->overflow_list.reserve(2 * (size_t)n);
   ix->cov_overflow_list.reserve(2 * (size_t)n);
   ix->mapped_list.reserve(2 * (size_t)n);
-  ix->small.reserve(8 + 4 * 64);
+  ix->small.reserve(8 + 5 * 64);
   ix->surv_cnt.reserve(2 * (size_t)n);
   ix->gen_list.reserve(2 * (size_t)n);
-  ix->seed_rec.reserve(8 * std::max<size_t>((size_t)n * ix->seed_recs_per_read, 1 << 16));
+  ix->seed_rec.reserve(4 * std::max<size_t>((size_t)n * ix->seed_recs_per_read, 1 << 16));
+  ix->surv_rec.reserve(4 * std::max<size_t>((size_t)n * ix->seed_recs_per_read, 1 << 16));
   size_t pool_need = std::max<size_t>((size_t)n * ix->pool_words_per_read, 1 << 16);
   pool_need = std::min<size_t>(pool_need, 0xFFFFFFF0ull);
   ix->pool.reserve(pool_need);
@@ -265,12 +266,12 @@ static void do_map(gq_index* ix, const uint8_t* h_bases = nullptr, const uint64_
   ix->arena.reserve((size_t)std::max(threads, threads2) * ix->arena_words);
   // small: [0] pool_used [1] n_overflow [2] n_cov_overflow;
   // per chunk c: [8+4c] n_mapped [9+4c] work counter [10+4c] survivor records [11+4c] n_gen (general-kernel work list)
-  CUDA_OK(cudaMemsetAsync(ix->small.p, 0, (8 + 4 * 64) * 4, st));
+  CUDA_OK(cudaMemsetAsync(ix->small.p, 0, (8 + 5 * 64) * 4, st));
 
   gq::BatchView b{ix->packed.p, ix->word_off.p, ix->len.p, ix->seeds.p, n, 0, n};
   gq::SearchOut o{ix->status.p, ix->st_off.p, ix->st_words.p, ix->st_count.p, ix->pool.p, (uint32_t)ix->pool.cap,
                   ix->small.p,  ix->overflow_list.p, ix->small.p + 1, ix->mapped_list.p, ix->small.p + 8,
-                  ix->small.p + 9};
+                  ix->small.p + 9, ix->use_seed_pass ? ix->surv_cnt.p : nullptr};
   gq::CoverageView c = cov_view(ix);
   int launches = 0;
   if (pipelined) {
@@ -303,11 +304,13 @@ static void do_map(gq_index* ix, const uint8_t* h_bases = nullptr, const uint64_
       // seed pass -> text kernel (strands with one surviving width-1 seed) -> general kernel (the rest)
       uint32_t* gen_list = ix->gen_list.p + 2 * (size_t)chunks[i].r0;
       uint32_t* n_gen = ix->small.p + 11 + 4 * i;
-      gq::SeedOut pre{ix->seed_rec.p + 8 * (size_t)ix->seed_recs_per_read * chunks[i].r0,
+      gq::SeedOut pre{ix->seed_rec.p + 4 * (size_t)ix->seed_recs_per_read * chunks[i].r0,
                       (uint32_t)(ix->seed_recs_per_read * (chunks[i].r1 - chunks[i].r0)),
                       ix->small.p + 10 + 4 * i, ix->surv_cnt.p, gen_list, n_gen};
       gq::launch_seed(ix->dv, bc, oc, pre, st);
-      gq::launch_text(ix->dv, bc, oc, pre, st);
+      gq::launch_text(ix->dv, bc, oc, pre, ix->surv_rec.p + 4 * (size_t)ix->seed_recs_per_read * chunks[i].r0,
+                      ix->small.p + 8 + 4 * 64 + i, st);
+      ++launches;
       gq::launch_search(ix->dv, bc, oc, ix->arena.p, ix->arena_words, threads, gen_list,
                         2 * (chunks[i].r1 - chunks[i].r0), ix->super_in_smem, ix->rf_thresh, ix->ev_thresh, st,
                         ix->leave_opt, ix->wait_opt, n_gen);
@@ -467,6 +470,20 @@ int gq_index_build(const uint32_t* prg, uint64_t n_symbols, uint32_t kmer_size, 
   ix->stream = ix->own_stream;
   for (auto& e : ix->ev) CUDA_OK(cudaEventCreate(&e));
   upload_index(ix);
+  {  // candidate records per read: a forward strand's seeding k-mer is drawn by occurrence (size-biased
+     // mean of the suffix counts), a reverse strand's is any k-mer (plain mean over all 4^k)
+    double sum = 0, sum2 = 0;
+    const auto& h = ix->h;
+    const uint64_t nk = 1ull << (2 * h.k);
+    for (uint64_t c = 0; c < nk; ++c) {
+      double w = 0;
+      for (uint32_t j = h.kmer_off[c]; j < h.kmer_off[c + 1]; ++j) w += (double)(h.kmer_states[j].hi - h.kmer_states[j].lo + 1);
+      sum += w;
+      sum2 += w * w;
+    }
+    const double per_read = (sum > 0 ? sum2 / sum : 1.0) + sum / (double)nk;
+    ix->seed_recs_per_read = (uint32_t)std::min(4096.0, 1.3 * per_read + 8.0);
+  }
   alloc_coverage(ix);
   reset_coverage(ix);
   *out = ix;
@@ -506,6 +523,7 @@ int gq_index_destroy(gq_index* ix) {
   ix->cov_overflow_list.release();
   ix->mapped_list.release();
   ix->seed_rec.release();
+  ix->surv_rec.release();
   ix->surv_cnt.release();
   ix->gen_list.release();
   ix->arena.release();
@@ -912,6 +930,7 @@ int gq_set_option(gq_index* ix, const char* name, int64_t value) {
   } else if (n == "seed_recs_per_read") {
     ix->seed_recs_per_read = (uint32_t)std::max<int64_t>(value, 1);
     ix->seed_rec.release();
+  ix->surv_rec.release();
   } else if (n == "leave") {
     ix->leave_opt = (uint32_t)value;
   } else if (n == "wait_max") {

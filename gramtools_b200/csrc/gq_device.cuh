@@ -297,6 +297,23 @@ GQ_DEV inline void lane_load_top(Lane& ln) {
   if (ln.state != LS_EV_TOP) ln.rd.seek(ln.pos);  // stack entries resume at their own read position
 }
 
+constexpr uint32_t kSurvGeneral = 0x10000u;  // SeedOut::surv_cnt flag: the strand is on the general kernel's list
+constexpr uint32_t kSurvListed = 0x20000u;   //  ... the strand is on mapped_list (the coverage work list)
+
+// append a mapped strand to the coverage work list, once (the text kernel may have listed it already)
+GQ_DEV inline void list_mapped(const SearchOut& o, uint32_t strand) {
+  if (o.listed) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t old = atomicOr(o.listed + strand, kSurvListed);
+#else
+    const uint32_t old = o.listed[strand];
+    o.listed[strand] |= kSurvListed;
+#endif
+    if (old & kSurvListed) return;
+  }
+  o.mapped_list[gq_atomic_inc_aggregated(o.n_mapped)] = strand;
+}
+
 GQ_DEV inline void lane_finish_strand(Lane& ln, const SearchOut& o) {
   uint32_t words = ln.arena_words - ln.s.limit;
   if (!ln.s.overflow && words) {
@@ -314,7 +331,7 @@ GQ_DEV inline void lane_finish_strand(Lane& ln, const SearchOut& o) {
     o.overflow_list[gq_atomic_add(o.n_overflow, 1u)] = ln.strand;
   } else if (ln.n_states) {
     o.status[ln.strand] = ST_MAPPED;
-    o.mapped_list[gq_atomic_inc_aggregated(o.n_mapped)] = ln.strand;
+    list_mapped(o, ln.strand);
   } else
     o.status[ln.strand] = ST_UNCLASSIFIED;
   ln.state = LS_IDLE;
@@ -677,7 +694,7 @@ GQ_DEV inline void lane_event_top(Lane& ln, const IndexView& v, const SearchOut&
     o.st_words[ln.strand] = words;
     o.st_count[ln.strand] = 1;
     o.status[ln.strand] = ST_MAPPED;
-    o.mapped_list[gq_atomic_inc_aggregated(o.n_mapped)] = ln.strand;
+    list_mapped(o, ln.strand);
     ln.state = LS_IDLE;
     return;
   } else {
@@ -698,21 +715,19 @@ GQ_DEV inline void lane_event(Lane& ln, const IndexView& v, const SearchOut& o) 
 // ------------------------------------------------------------------------------------------------
 // Seed pass. For one strand: look up the seeding k-mer (quasimap.cpp:178,235-241); each of its seed states
 // is narrowed by rank steps while it is wider than kSplitWidth suffixes, then SPLIT into its suffixes: every
-// occurrence becomes a width-1 state of its own, checked against the PRG text (up to kPreTextSteps x 16
-// bases). Splitting is exact: a SearchState's interval is a set of suffixes that the reference advances in
+// occurrence becomes a width-1 state of its own — a candidate — that the text kernel walks through the PRG
+// text. Splitting is exact: a SearchState's interval is a set of suffixes that the reference advances in
 // lock-step (one LF step per suffix, one jump per marker-preceded suffix, vBWT_jump.cpp:94-117); walking
 // them one by one visits the same (suffix, path) pairs. Only the grouping of the final states can differ —
 // two suffixes of one state that both survive to the end of the read stay ONE state in the reference — so
-// a strand with more than one survivor is not finished here but handed to the general search kernel, which
-// redoes it with interval states. False seeds (a 10-mer has several occurrences, one of them real) die in
-// the text check, so the text kernel sees about one survivor per mappable strand.
+// a strand with more than one finished candidate is handed to the general search kernel, which redoes it
+// with interval states. False candidates (a 10-mer has several occurrences, one of them real) die within
+// a step or two of the text walk.
 // ------------------------------------------------------------------------------------------------
-constexpr uint32_t kPreSteps = 6;       // rank steps at most, while the interval is wide
-constexpr uint32_t kSplitWidth = 4;     // stop narrowing at this many suffixes
-constexpr uint32_t kMaxSplit = 32;      // wider than this after narrowing: general kernel
-constexpr uint32_t kVerifyBases = 12;   // a survivor agrees with the PRG on this many bases beyond the k-mer
-constexpr uint32_t kVerifyIters = 8;    //  ... or has made this many steps / jumps
-constexpr uint32_t kSurvGeneral = 0x10000u;  // surv_cnt flag: the strand is on the general kernel's list
+constexpr uint32_t kPreSteps = 6;    // rank steps at most, while the interval is wide
+constexpr uint32_t kSplitWidth = 4;  // stop narrowing at this many suffixes
+constexpr uint32_t kMaxSplit = 32;   // wider than this after narrowing: general kernel
+constexpr uint32_t kMaxSeedStates = 16;
 
 // part 1: k-mer lookup. Returns the number of seed states (0: the strand is already classified).
 GQ_DEV inline uint32_t preseed_lookup(const IndexView& v, const BatchView& b, const SearchOut& o, uint32_t strand,
@@ -757,21 +772,94 @@ GQ_DEV inline void send_to_general(const SeedOut& pre, uint32_t strand) {
   if (!(old & kSurvGeneral)) pre.gen_list[gq_atomic_add(pre.n_gen, 1u)] = strand;
 }
 
+// part 2: the candidates of one strand. `lo/w/w0[t]`: first SA index, number of suffixes and pos | kind << 28
+// of seed state t after narrowing (w = 0: dead). Returns the number of candidates, or kNoAllele when the
+// strand needs the general kernel.
+struct SeedPlan {
+  uint32_t sb, ns;
+  uint32_t lo[kMaxSeedStates], w[kMaxSeedStates], w0[kMaxSeedStates];
+};
+
+template <class SuperPtr>
+GQ_DEV inline uint32_t seed_plan(const IndexView& v, SuperPtr super_c, const BatchView& b, uint32_t strand, uint32_t sb,
+                                 uint32_t ns, SeedPlan& plan) {
+  plan.sb = sb;
+  plan.ns = ns;
+  if (ns > kMaxSeedStates) {
+    GQ_COUNT(9);
+    return kNoAllele;
+  }
+  const uint32_t r = strand >> 1;
+  const uint32_t L = b.len[r];
+  const uint32_t pos0 = L - v.k;
+  if (pos0 == 0) {  // the seed states are the final states
+    GQ_COUNT(0);
+    return kNoAllele;
+  }
+  uint32_t total = 0;
+  for (uint32_t t = 0; t < ns; ++t) {
+    const KmerState ks = v.kmer_states[sb + t];
+    uint32_t lo = ks.lo, hi = ks.hi, w0 = pos0 | (K_SCAN << 28);
+    if (hi - lo >= kSplitWidth) {  // narrow it with rank steps first (BWT_search.cpp:45-76)
+      Lane ln;
+      ln.rd = ReadCursor{b.packed + b.word_off[r], L, strand & 1u, 0, 0, 0};
+      ln.pos = pos0;
+      ln.lo = lo;
+      ln.hi = hi;
+      ln.p = ln.mr = 0;
+      ln.kind = K_SCAN;
+      ln.rd.seek(ln.pos);
+      ln.state = LS_RUNW;
+      for (uint32_t s = 0; s < kPreSteps && ln.state == LS_RUNW && ln.hi - ln.lo >= kSplitWidth && ln.pos > 1; ++s)
+        lane_step_wide(ln, v, super_c);
+      // LS_RUN / LS_RUNW / LS_EV_SCAN (a marker inside the interval: every suffix checks its own symbol)
+      if (ln.state == LS_EV_WIDE || (ln.state != LS_EV_POP && ln.hi - ln.lo >= kMaxSplit)) {
+        GQ_COUNT(1);
+        return kNoAllele;
+      }
+      lo = ln.lo;
+      hi = ln.state == LS_EV_POP ? lo - 1 : ln.hi;
+      w0 = ln.pos | (ln.kind << 28);
+    }
+    plan.lo[t] = lo;
+    plan.w[t] = hi + 1 - lo;
+    plan.w0[t] = w0;
+    total += hi + 1 - lo;
+    GQ_COUNT(2);
+  }
+  return total;
+}
+
+// candidate record: 4 words {strand, k-mer state index, text position SA[i], pos | kind << 28}
+GQ_DEV inline void seed_write(const IndexView& v, const SeedPlan& plan, const SeedOut& pre, uint32_t strand,
+                              uint32_t base) {
+  uint32_t* d = pre.rec + 4 * (size_t)base;
+  for (uint32_t t = 0; t < plan.ns; ++t)
+    for (uint32_t i = 0; i < plan.w[t]; ++i, d += 4) {
+      d[0] = strand;
+      d[1] = plan.sb + t;
+      d[2] = GQ_LDG(v.sa + plan.lo[t] + i);
+      d[3] = plan.w0[t];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
-// Fast path (text kernel): a strand whose seed pass left exactly ONE survivor is followed to the end of the
-// read by one thread, entirely in text mode: registers + a short local path, no stack, no arena. Jumps are
-// taken from the pre-resolved text-order records (exit of a site, whole-SNP crossing, plain entry);
-// anything else — a jump that needs the general machinery, an interval that widens, a path longer than the
-// local buffers — sends the strand to the general search kernel, which redoes it from the k-mer index (same
-// results: both follow quasimap.cpp:227-268 / vBWT_jump.cpp state by state).
+// Text kernel: every candidate is followed by one thread, entirely in text mode: registers + a short local
+// path, no stack, no arena. Jumps are taken from the pre-resolved text-order records (exit of a site,
+// whole-SNP crossing, plain entry); anything else — a jump that needs the general machinery, an interval
+// that widens, a path longer than the local buffers — sends the strand to the general search kernel, which
+// redoes it from the k-mer index (same results: both follow quasimap.cpp:227-268 / vBWT_jump.cpp state by
+// state). The path of the seed state itself (k-mer index) is only fetched when the candidate finishes.
 // ------------------------------------------------------------------------------------------------
-constexpr uint32_t kFastT = 24;  // (site, allele) pairs
-constexpr uint32_t kFastG = 4;   // open sites
-enum FastResult : uint32_t { FAST_NONE = 0, FAST_DEAD = 1, FAST_MAPPED = 2, FAST_BAIL = 3, FAST_POOL_FULL = 4 };
+constexpr uint32_t kFastT = 24;  // (site, allele) pairs added during the walk
+constexpr uint32_t kFastG = 4;   // sites opened during the walk
+enum FastResult : uint32_t { FAST_NONE = 0, FAST_DEAD = 1, FAST_MAPPED = 2, FAST_BAIL = 3 };
 
 struct FastLane {
   Lane ln;
-  uint32_t nt, ng;
+  uint32_t nt, ng;       // local path: pairs in T, open sites in G
+  uint32_t nt0, ng0;     // what is left of the seed state's own path (its open sites can be closed by exits)
+  uint32_t path_off;     // ... in kmer_paths
   uint32_t T[2 * kFastT], G[kFastG];
   uint32_t result;  // FAST_NONE while running
   bool p_valid;     // ln.p is the text position of the current suffix
@@ -781,58 +869,51 @@ GQ_DEV inline bool fast_running(const FastLane& f) {
   return f.result == FAST_NONE && (f.ln.state == LS_TEXT || f.ln.state == LS_EV_TSCAN);
 }
 
-// survivor record -> lane. A strand with several survivors is not followed (see above).
+// candidate record -> lane (TRACK: the seed state's path counts are needed, from the k-mer index)
+template <bool TRACK>
 GQ_DEV inline void fast_begin(FastLane& f, const IndexView& v, const BatchView& b, const SeedOut& pre, uint32_t idx) {
-  const uint32_t* rec = pre.rec + 8 * (size_t)idx;
-  const uint32_t w0 = GQ_LDG(rec), counts = GQ_LDG(rec + 2), path_off = GQ_LDG(rec + 3), strand = GQ_LDG(rec + 4);
+#if defined(__CUDA_ARCH__)
+  const uint4 c = __ldg(reinterpret_cast<const uint4*>(pre.rec) + idx);
+  const uint32_t strand = c.x, j = c.y, p = c.z, w0 = c.w;
+#else
+  const uint32_t* c = pre.rec + 4 * (size_t)idx;
+  const uint32_t strand = c[0], j = c[1], p = c[2], w0 = c[3];
+#endif
+  const uint32_t r = strand >> 1;
+  const uint32_t L = b.len[r], woff = b.word_off[r];
   f.ln.strand = strand;
   f.result = FAST_NONE;
   f.p_valid = true;
-  f.nt = counts & 0xFFFFu;
-  f.ng = counts >> 16;
-  f.ln.state = LS_IDLE;
-  if (pre.surv_cnt[strand] != 1u || f.nt > kFastT || f.ng > kFastG) {
-    GQ_COUNT(4);  // several survivors / long seed path
-#if defined(GQ_EMU_TRACE)
-    if (gq_emu_counters[4] < 6) {
-      printf("strand %u survivors %u:", strand, pre.surv_cnt[strand]);
-      for (uint32_t q = 0; q < pre.surv_cnt[strand]; ++q) {
-        const uint32_t* r2 = pre.rec + 8 * (size_t)(idx + q);
-        printf(" [pos %u kind %u p %u nt %u ng %u j %u]", r2[0] & 0xFFFFFFF, r2[0] >> 28, r2[1], r2[2] & 0xFFFF, r2[2] >> 16, r2[7]);
-      }
-      printf("\n");
-    }
-#endif
-    f.result = FAST_BAIL;
-    return;
+  f.nt = f.ng = 0;
+  f.nt0 = f.ng0 = f.path_off = 0;
+  if (TRACK) {
+    const KmerState ks = v.kmer_states[j];
+    f.nt0 = ks.counts & 0xFFFFu;
+    f.ng0 = ks.counts >> 16;
+    f.path_off = ks.path_off;
   }
-  const uint32_t pw = 2 * f.nt + f.ng;
-  for (uint32_t i = 0; i < pw; ++i) {
-    const uint32_t x = GQ_LDG(v.kmer_paths + path_off + i);
-    if (i < 2 * f.nt) f.T[i] = x;
-    else f.G[i - 2 * f.nt] = x;
-  }
-  f.ln.rd = ReadCursor{b.packed + GQ_LDG(rec + 6), GQ_LDG(rec + 5), strand & 1u, 0, 0, 0};
+  f.ln.rd = ReadCursor{b.packed + woff, L, strand & 1u, 0, 0, 0};
   f.ln.pos = w0 & 0x0FFFFFFFu;
   f.ln.kind = w0 >> 28;
-  f.ln.p = GQ_LDG(rec + 1);
+  f.ln.p = p;
   f.ln.lo = f.ln.hi = 0;
   f.ln.mr = 0;
-  if (f.ln.pos) {
-    f.ln.rd.seek(f.ln.pos);
-    f.ln.state = LS_TEXT;
-  } else {  // already finished by the seed pass (short read)
-    f.ln.lo = f.ln.hi = GQ_LDG(v.isa + f.ln.p);
-    f.ln.state = LS_EV_TOP;
-  }
+  f.ln.rd.seek(f.ln.pos);  // pos >= 1: seed states of reads with L == k never become candidates
+  f.ln.state = LS_TEXT;
 }
 
-// LS_EV_TSCAN: the marker left of the suffix (lane_event_scan's pre-resolved cases, on the local path)
+// LS_EV_TSCAN: the marker left of the suffix (lane_event_scan's pre-resolved cases, on the local path).
+// TRACK = false (verify pass): same walk, path not recorded.
+template <bool TRACK>
 GQ_DEV inline void fast_event(FastLane& f, const IndexView& v) {
   Lane& ln = f.ln;
   const uint32_t* jr = v.tmarker_hit + 8 * (size_t)ln.mr;
-  const uint32_t marker = GQ_LDG(jr), allele = GQ_LDG(jr + 1), jlo = GQ_LDG(jr + 2), jhi = GQ_LDG(jr + 3);
-  const uint32_t snp = GQ_LDG(jr + 4), p_jump = GQ_LDG(jr + 6), p_site = GQ_LDG(jr + 7);
+#if defined(__CUDA_ARCH__)
+  const uint4 ja = __ldg(reinterpret_cast<const uint4*>(jr)), jb = __ldg(reinterpret_cast<const uint4*>(jr) + 1);
+  const uint32_t marker = ja.x, allele = ja.y, jlo = ja.z, jhi = ja.w, snp = jb.x, p_jump = jb.z, p_site = jb.w;
+#else
+  const uint32_t marker = jr[0], allele = jr[1], jlo = jr[2], jhi = jr[3], snp = jr[4], p_jump = jr[6], p_site = jr[7];
+#endif
   if (marker == 0) {
     f.result = FAST_DEAD;
     return;
@@ -843,14 +924,17 @@ GQ_DEV inline void fast_event(FastLane& f, const IndexView& v) {
     return;
   }
   if (marker & 1u) {  // leave the site through `allele` (exit_site_in_place)
-    if (jlo != jhi || f.nt == kFastT) {
+    if (jlo != jhi || (TRACK && f.nt == kFastT)) {
       f.result = FAST_BAIL;
       return;
     }
-    if (f.ng > 0) --f.ng;
-    f.T[2 * f.nt] = marker;
-    f.T[2 * f.nt + 1] = allele;
-    ++f.nt;
+    if (TRACK) {
+      if (f.ng > 0) --f.ng;  // the site being left is the innermost open one
+      else if (f.ng0 > 0) --f.ng0;
+      f.T[2 * f.nt] = marker;
+      f.T[2 * f.nt + 1] = allele;
+      ++f.nt;
+    }
     ln.p = p_jump;
     ln.kind = K_READY;
     ln.state = LS_TEXT;
@@ -864,13 +948,15 @@ GQ_DEV inline void fast_event(FastLane& f, const IndexView& v) {
       f.result = FAST_DEAD;
       return;
     }
-    if (f.nt == kFastT) {
-      f.result = FAST_BAIL;
-      return;
+    if (TRACK) {
+      if (f.nt == kFastT) {
+        f.result = FAST_BAIL;
+        return;
+      }
+      f.T[2 * f.nt] = marker - 1;
+      f.T[2 * f.nt + 1] = a;
+      ++f.nt;
     }
-    f.T[2 * f.nt] = marker - 1;
-    f.T[2 * f.nt + 1] = a;
-    ++f.nt;
     ln.p = p_site;
     ln.pos -= 1;
     ln.rd.advance();
@@ -878,11 +964,13 @@ GQ_DEV inline void fast_event(FastLane& f, const IndexView& v) {
     ln.state = LS_TEXT;
     return;
   }
-  if (f.ng == kFastG) {
-    f.result = FAST_BAIL;
-    return;
+  if (TRACK) {
+    if (f.ng == kFastG) {
+      f.result = FAST_BAIL;
+      return;
+    }
+    f.G[f.ng++] = marker - 1;
   }
-  f.G[f.ng++] = marker - 1;
   const uint32_t slot = (marker - 6) >> 1;
   const uint32_t nlo = GQ_LDG(v.entry_next + 8 * slot + 2 * c), nhi = GQ_LDG(v.entry_next + 8 * slot + 2 * c + 1);
   if (nhi + 1 <= nlo) {  // no allele ends in c
@@ -906,77 +994,16 @@ GQ_DEV inline void fast_event(FastLane& f, const IndexView& v) {
   }
 }
 
-// Seed pass, part 2: ONE seed state j of a strand. Returns bit 0: some suffix survived (survivor records
-// written), bit 1: the strand needs the general kernel. A suffix survives if kVerifyBases further bases of
-// the read agree with the PRG along its walk (text steps and pre-resolved jumps, path not recorded); the
-// survivor record holds the state as it was seeded and the text kernel walks it again, with its path.
-template <class SuperPtr>
-GQ_DEV inline uint32_t seed_state_split(const IndexView& v, SuperPtr super_c, const SeedOut& pre, const uint32_t* w,
-                                        uint32_t L, uint32_t woff, uint32_t strand, uint32_t j) {
-  Lane ln;
-  ln.rd = ReadCursor{w, L, strand & 1u, 0, 0, 0};
-  const KmerState ks = v.kmer_states[j];
-  ln.pos = L - v.k;
-  ln.lo = ks.lo;
-  ln.hi = ks.hi;
-  ln.p = 0;
-  ln.mr = 0;
-  ln.kind = K_SCAN;
-  if (ln.pos == 0) {  // the seed states are the final states
-    GQ_COUNT(0);
-    return 2u;
-  }
-  ln.rd.seek(ln.pos);
-  ln.state = ln.lo == ln.hi ? LS_RUN : LS_RUNW;
-  for (uint32_t s = 0; s < kPreSteps && ln.state == LS_RUNW && ln.hi - ln.lo >= kSplitWidth && ln.pos > 1; ++s)
-    lane_step_wide(ln, v, super_c);
-  if (ln.state == LS_EV_POP) return 0u;
-  // LS_RUN / LS_RUNW / LS_EV_SCAN (a marker inside the interval: every suffix checks its own symbol)
-  if (ln.state == LS_EV_WIDE || ln.hi - ln.lo >= kMaxSplit) {
-    GQ_COUNT(1);
-    return 2u;
-  }
-  GQ_COUNT(2);                                               // seed states split
-  GQ_COUNT(16 + (ln.hi - ln.lo < 15 ? ln.hi - ln.lo : 15));  // histogram of split widths
-  uint32_t out = 0;
-  const ReadCursor rd0 = ln.rd;
-  const uint32_t pos0 = ln.pos, kind0 = ln.kind, lo = ln.lo, hi = ln.hi;
-  for (uint32_t i = lo; i <= hi; ++i) {
-    FastLane f;
-    f.nt = f.ng = 0;
-    f.result = FAST_NONE;
-    f.p_valid = true;
-    f.ln.rd = rd0;
-    f.ln.pos = pos0;
-    f.ln.kind = kind0;
-    f.ln.lo = f.ln.hi = f.ln.mr = 0;
-    const uint32_t p_seed = GQ_LDG(v.sa + i);
-    f.ln.p = p_seed;
-    f.ln.state = LS_TEXT;
-    for (uint32_t it = 0; it < kVerifyIters && fast_running(f) && pos0 - f.ln.pos < kVerifyBases; ++it) {
-      if (f.ln.state == LS_TEXT) lane_text_step(f.ln, v);
-      if (f.ln.state == LS_EV_TSCAN) fast_event(f, v);
-    }
-    if (f.result == FAST_DEAD || f.ln.state == LS_EV_POP) continue;
-    GQ_COUNT(3);  // survivors
-    const uint32_t idx = gq_atomic_inc_aggregated(pre.n_surv);
-    if (idx >= pre.cap) {  // survivor pool full
-      out |= 2u;
-      continue;
-    }
-    uint32_t* d = pre.rec + 8 * (size_t)idx;
-    d[0] = pos0 | (kind0 << 28);
-    d[1] = p_seed;
-    d[2] = ks.counts;
-    d[3] = ks.path_off;
-    d[4] = strand;
-    d[5] = L;
-    d[6] = woff;
-    d[7] = j;
-    gq_atomic_add(pre.surv_cnt + strand, 1u);
-    out |= 1u;
-  }
-  return out;
+// Verify pass: does the candidate agree with the PRG on kVerifyBases further bases (or to the end of the read,
+// or up to something only the full walk can decide)? False candidates — the other occurrences of the
+// seeding k-mer — end here, so the full walk only sees about one candidate per mappable strand.
+constexpr uint32_t kVerifyBases = 12;
+constexpr uint32_t kVerifyIters = 6;
+GQ_DEV inline bool fast_verified(const FastLane& f, uint32_t pos0) {
+  return !fast_running(f) || pos0 - f.ln.pos >= kVerifyBases;
+}
+GQ_DEV inline bool fast_alive(const FastLane& f) {
+  return !(f.result == FAST_DEAD || (f.result == FAST_NONE && f.ln.state == LS_EV_POP));
 }
 
 // after the walk: classify the outcome; for a finished state, settle its record (encapsulated_search.cpp:30-88
@@ -988,8 +1015,8 @@ GQ_DEV inline uint32_t fast_outcome(FastLane& f, const IndexView& v) {
     return 0;
   }
   f.result = FAST_MAPPED;
-  GQ_COUNT(7);  // strands finished by the fast path
-  if (!(f.nt | f.ng)) {
+  GQ_COUNT(7);  // candidates finished by the fast path
+  if (!(f.nt | f.ng | f.nt0 | f.ng0)) {
     const uint32_t pf = f.p_valid ? f.ln.p : GQ_LDG(v.sa + f.ln.lo);
     const Node& nd = v.nodes[GQ_LDG(v.pos2node + pf)];
     if (nd.site != 0) {
@@ -998,25 +1025,45 @@ GQ_DEV inline uint32_t fast_outcome(FastLane& f, const IndexView& v) {
       f.nt = 1;
     }
   }
-  return 4 + 2 * f.nt + 2 * f.ng;
+  return 4 + 2 * (f.nt0 + f.nt) + 2 * (f.ng0 + f.ng);
 }
 
-// write the single final state of the strand at pool offset `off`
-GQ_DEV inline void fast_emit(const FastLane& f, const SearchOut& o, uint32_t off) {
+// write the single final state of the strand at pool offset `off`: the seed state's path, then the local one
+GQ_DEV inline void fast_emit(const FastLane& f, const IndexView& v, const SearchOut& o, uint32_t off) {
   uint32_t* d = o.pool + off;
+  const uint32_t nt = f.nt0 + f.nt, ng = f.ng0 + f.ng;
   d[0] = f.ln.lo;
   d[1] = f.ln.hi;
-  d[2] = f.nt;
-  d[3] = f.ng;
-  for (uint32_t j = 0; j < 2 * f.nt; ++j) d[4 + j] = f.T[j];
+  d[2] = nt;
+  d[3] = ng;
+  d += 4;
+  for (uint32_t j = 0; j < 2 * f.nt0; ++j) *d++ = GQ_LDG(v.kmer_paths + f.path_off + j);
+  for (uint32_t j = 0; j < 2 * f.nt; ++j) *d++ = f.T[j];
+  for (uint32_t j = 0; j < f.ng0; ++j) {
+    *d++ = GQ_LDG(v.kmer_paths + f.path_off + 2 * f.nt0 + j);
+    *d++ = kNoAllele;
+  }
   for (uint32_t j = 0; j < f.ng; ++j) {
-    d[4 + 2 * f.nt + 2 * j] = f.G[j];
-    d[4 + 2 * f.nt + 2 * j + 1] = kNoAllele;
+    *d++ = f.G[j];
+    *d++ = kNoAllele;
   }
   const uint32_t strand = f.ln.strand;
   o.st_off[strand] = off;
-  o.st_words[strand] = 4 + 2 * f.nt + 2 * f.ng;
+  o.st_words[strand] = 4 + 2 * nt + 2 * ng;
   o.st_count[strand] = 1;
+}
+
+// a finished candidate claims its strand: 0 = first one (emit), otherwise the strand is (or becomes) the
+// general kernel's
+GQ_DEV inline bool fast_claim(const SeedOut& pre, uint32_t strand) {
+  const uint32_t old = gq_atomic_add(pre.surv_cnt + strand, 1u);
+  if (old & kSurvGeneral) return false;
+  if (old & 0xFFFFu) {
+    GQ_COUNT(4);  // several finished candidates
+    send_to_general(pre, strand);
+    return false;
+  }
+  return true;
 }
 
 // all_read_kmers_occur_in_index (quasimap.cpp:212-225) for a strand whose search found nothing:
@@ -1052,53 +1099,61 @@ GQ_DEV inline void classify_strand(const IndexView& v, const BatchView& b, const
   o.status[strand] = missing ? ST_MISSING_KMER : ST_NO_EXTENSION;
 }
 
-// Single-lane driver (host emulation and a reference for the kernels): seed pass, text fast path for a
-// single survivor, else the general lane state machine seeded from the k-mer index; then the k-mer filter
-// if nothing mapped.
+// Single-lane driver (host emulation and a reference for the kernels): seed pass, text walk of every
+// candidate, the general lane state machine (seeded from the k-mer index) where the fast path does not
+// apply; then the k-mer filter if nothing mapped.
 GQ_DEV inline void map_strand(const IndexView& v, const uint32_t* super_cnt, const BatchView& b, const SearchOut& o,
                               const SeedOut& pre, uint32_t strand, uint32_t* arena, uint32_t arena_words) {
-  Lane ln;
-  ln.state = LS_IDLE;
   bool general = o.status[strand] == ST_OVERFLOW;  // overflow re-runs always use the general machinery
   if (!general) {
     uint32_t sb = 0;
     const uint32_t ns = preseed_lookup(v, b, o, strand, sb);
     if (ns == 0) return;
-    const uint32_t r = strand >> 1;
-    const uint32_t first = *pre.n_surv;
+    o.status[strand] = ST_UNCLASSIFIED;
     pre.surv_cnt[strand] = 0;
-    uint32_t flags = 0;
-    for (uint32_t t = 0; t < ns; ++t)
-      flags |= seed_state_split(v, super_cnt, pre, b.packed + b.word_off[r], b.len[r], b.word_off[r], strand, sb + t);
-    if (flags & 2u) general = true;
-    else if (!(flags & 1u)) o.status[strand] = ST_UNCLASSIFIED;
+    SeedPlan plan;
+    const uint32_t total = seed_plan(v, super_cnt, b, strand, sb, ns, plan);
+    if (total == kNoAllele || total > pre.cap) general = true;
     else {
-      FastLane f;
-      fast_begin(f, v, b, pre, first);
-      while (fast_running(f)) {
-        if (f.ln.state == LS_TEXT) lane_text_step(f.ln, v);
-        if (f.ln.state == LS_EV_TSCAN) fast_event(f, v);
-      }
-      const uint32_t words = fast_outcome(f, v);
-      if (f.result == FAST_MAPPED) {
-        const uint32_t off = gq_atomic_add(o.pool_used, words);
-        if (off + words > o.pool_cap) {
-          o.status[strand] = ST_OVERFLOW;
-          o.overflow_list[gq_atomic_add(o.n_overflow, 1u)] = strand;
-          return;
+      seed_write(v, plan, pre, strand, 0);  // the emulation reuses the candidate pool strand by strand
+      for (uint32_t i = 0; i < total; ++i) {
+        FastLane f;
+        fast_begin<false>(f, v, b, pre, i);
+        {  // verify pass (verify_kernel), then the full walk from the start (text_kernel)
+          const uint32_t pos0 = f.ln.pos;
+          for (uint32_t it = 0; it < kVerifyIters && !fast_verified(f, pos0); ++it) {
+            if (f.ln.state == LS_TEXT) lane_text_step(f.ln, v);
+            if (fast_running(f) && f.ln.state == LS_EV_TSCAN) fast_event<false>(f, v);
+          }
+          if (!fast_alive(f)) continue;
+          fast_begin<true>(f, v, b, pre, i);
         }
-        fast_emit(f, o, off);
-        o.status[strand] = ST_MAPPED;
-        o.mapped_list[gq_atomic_inc_aggregated(o.n_mapped)] = strand;
-      } else if (f.result == FAST_DEAD)
-        o.status[strand] = ST_UNCLASSIFIED;
-      else
-        general = true;
+        while (fast_running(f)) {
+          if (f.ln.state == LS_TEXT) lane_text_step(f.ln, v);
+          if (f.ln.state == LS_EV_TSCAN) fast_event<true>(f, v);
+        }
+        const uint32_t words = fast_outcome(f, v);
+        if (f.result == FAST_MAPPED) {
+          if (!fast_claim(pre, strand)) continue;
+          const uint32_t off = gq_atomic_add(o.pool_used, words);
+          if (off + words > o.pool_cap) {
+            o.status[strand] = ST_OVERFLOW;
+            o.overflow_list[gq_atomic_add(o.n_overflow, 1u)] = strand;
+            return;
+          }
+          fast_emit(f, v, o, off);
+          o.status[strand] = ST_MAPPED;
+          list_mapped(o, strand);
+        } else if (f.result == FAST_BAIL)
+          send_to_general(pre, strand);
+      }
+      general = (pre.surv_cnt[strand] & kSurvGeneral) != 0;
     }
-    *pre.n_surv = first;  // the emulation reuses the survivor pool strand by strand
   }
   if (general) {
     GQ_COUNT(8);  // strands through the general machinery
+    Lane ln;
+    ln.state = LS_IDLE;
     lane_refill(ln, v, b, o, strand, arena, arena_words);
     while (ln.state != LS_IDLE) {
       if (ln.state == LS_RUN) lane_to_text(ln, v);

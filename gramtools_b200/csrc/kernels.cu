@@ -121,8 +121,9 @@ __device__ __forceinline__ bool warp_any_kmer_missing(const IndexView& v, const 
   return missing;
 }
 
-// Seed pass (seed_state_split). Superblock counters come from shared memory when they fit, like in the
-// search kernel.
+// Seed pass: thread per strand (preseed_lookup + seed_plan), candidates written through one warp-aggregated
+// allocation per 32 strands. Superblock counters (only needed to narrow wide seed states) come from shared
+// memory when they fit, like in the search kernel.
 template <bool SUPER_SMEM>
 __global__ void __launch_bounds__(256)
     seed_kernel(IndexView v, BatchView b, SearchOut o, SeedOut pre, uint32_t n_super_smem) {
@@ -132,53 +133,32 @@ __global__ void __launch_bounds__(256)
   const uint32_t n = 2 * (b.read_end - b.read_begin);
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t full = 0xFFFFFFFFu;
-  // Warp-convergent rounds of 32 strands. Phase A: every lane looks up the seed states of its strand.
-  // Phase B: the seed states of the round (about 1.5 per strand) are spread evenly over the lanes, so lanes
-  // run the same short narrowing / splitting code instead of per-strand loops of very different lengths.
   for (uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; i0 < n; i0 += gridDim.x * blockDim.x) {
     const uint32_t i = i0 + lane;
     const uint32_t strand = 2 * b.read_begin + i;
     uint32_t sb = 0;
     const uint32_t ns = i < n ? preseed_lookup(v, b, o, strand, sb) : 0;
-    uint32_t incl = ns;  // inclusive warp scan
+    SeedPlan plan;
+    uint32_t total = 0;
+    if (ns) {
+      o.status[strand] = ST_UNCLASSIFIED;  // until a candidate finishes or the general kernel decides
+      pre.surv_cnt[strand] = 0;
+      total = seed_plan(v, SUPER_SMEM ? (const uint32_t*)s_super : v.super_cnt, b, strand, sb, ns, plan);
+    }
+    const bool general = total == kNoAllele;
+    const uint32_t mine = general ? 0u : total;
+    uint32_t incl = mine;  // inclusive warp scan
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       uint32_t t = __shfl_up_sync(full, incl, d);
       if (lane >= (uint32_t)d) incl += t;
     }
-    const uint32_t total = __shfl_sync(full, incl, 31);
-    if (total == 0) continue;
-    const uint32_t r = strand >> 1;
-    const uint32_t my_L = ns ? b.len[r] : 0, my_woff = ns ? b.word_off[r] : 0;
-    if (ns) pre.surv_cnt[strand] = 0;
-    __syncwarp();
-    uint32_t alive = 0, general = 0;
-    for (uint32_t t0 = 0; t0 < total; t0 += 32) {
-      const uint32_t t = t0 + lane;
-      // owner of task t = first lane whose inclusive count exceeds t
-      uint32_t lo_l = 0, hi_l = 31;
-#pragma unroll
-      for (int it = 0; it < 5; ++it) {
-        const uint32_t mid = (lo_l + hi_l) >> 1;
-        const uint32_t val = __shfl_sync(full, incl, mid);
-        if (val > t) hi_l = mid;
-        else lo_l = mid + 1;
-      }
-      const uint32_t owner = hi_l;
-      const uint32_t o_incl = __shfl_sync(full, incl, owner), o_ns = __shfl_sync(full, ns, owner),
-                     o_sb = __shfl_sync(full, sb, owner), o_L = __shfl_sync(full, my_L, owner),
-                     o_woff = __shfl_sync(full, my_woff, owner);
-      uint32_t flags = 0;
-      if (t < total)
-        flags = seed_state_split(v, SUPER_SMEM ? (const uint32_t*)s_super : v.super_cnt, pre, b.packed + o_woff, o_L,
-                                 o_woff, 2 * b.read_begin + i0 + owner, o_sb + (t - (o_incl - o_ns)));
-      alive |= __reduce_or_sync(full, (flags & 1u) ? (1u << owner) : 0u);
-      general |= __reduce_or_sync(full, (flags & 2u) ? (1u << owner) : 0u);
-    }
-    if (ns) {
-      if ((general >> lane) & 1u) send_to_general(pre, strand);
-      else if (!((alive >> lane) & 1u)) o.status[strand] = ST_UNCLASSIFIED;
-    }
+    const uint32_t sum = __shfl_sync(full, incl, 31);
+    uint32_t base = 0;
+    if (sum && lane == 31) base = atomicAdd(pre.n_surv, sum);
+    base = __shfl_sync(full, base, 31);
+    if (general || (mine && base + sum > pre.cap)) send_to_general(pre, strand);  // cannot split / pool full
+    else if (mine) seed_write(v, plan, pre, strand, base + incl - mine);
   }
 }
 
@@ -193,10 +173,44 @@ void launch_seed(const IndexView& v, const BatchView& b, const SearchOut& o, con
     seed_kernel<false><<<blocks, 256, 0, st>>>(v, b, o, pre, 0);
 }
 
-// Fast path: one thread per survivor record of the seed pass, 32 records per warp round. The walk is ONE
-// warp-convergent loop — text step for the lanes in text mode, then the jump for the lanes that reached a
-// marker — so lanes meet again every iteration; the round ends with a convergent emission phase (one pool
-// allocation and one mapped-list allocation per warp).
+// Verify pass: one thread per candidate; a few warp-convergent walk iterations decide whether the candidate
+// is real (see fast_verified). Survivors are copied, densely, behind the candidate records (second half of
+// the pool) for the text kernel.
+__global__ void __launch_bounds__(256) verify_kernel(IndexView v, BatchView b, SeedOut pre, uint32_t* surv_rec,
+                                                     uint32_t* n_verified) {
+  const uint32_t n = min(*pre.n_surv, pre.cap);
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t full = 0xFFFFFFFFu;
+  for (uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; i0 < n; i0 += gridDim.x * blockDim.x) {
+    const uint32_t i = i0 + lane;
+    FastLane f;
+    f.result = FAST_DEAD;
+    f.ln.state = LS_IDLE;
+    f.ln.pos = 0;
+    if (i < n) fast_begin<false>(f, v, b, pre, i);
+    const uint32_t pos0 = f.ln.pos;
+    for (uint32_t it = 0; it < kVerifyIters && __any_sync(full, !fast_verified(f, pos0)); ++it) {
+      if (!fast_verified(f, pos0) && f.ln.state == LS_TEXT) lane_text_step(f.ln, v);
+      if (!fast_verified(f, pos0) && f.ln.state == LS_EV_TSCAN) fast_event<false>(f, v);
+    }
+    const bool alive = i < n && fast_alive(f);
+    const uint32_t mm = __ballot_sync(full, alive);
+    if (mm) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(n_verified, (uint32_t)__popc(mm));
+      base = __shfl_sync(full, base, 0);
+      if (alive) {
+        const uint32_t dst = base + __popc(mm & ((1u << lane) - 1u));
+        reinterpret_cast<uint4*>(surv_rec)[dst] = __ldg(reinterpret_cast<const uint4*>(pre.rec) + i);
+      }
+    }
+  }
+}
+
+// Text kernel: one thread per verified candidate, 32 per warp round. The walk is ONE warp-convergent loop
+// — text step for the lanes in text mode, then the jump for the lanes that reached a marker — so lanes meet
+// again every iteration; the round ends with a convergent emission phase (one pool allocation and one
+// mapped-list allocation per warp).
 __global__ void __launch_bounds__(256) text_kernel(IndexView v, BatchView b, SearchOut o, SeedOut pre) {
   const uint32_t n = min(*pre.n_surv, pre.cap);
   const uint32_t lane = threadIdx.x & 31u;
@@ -207,12 +221,17 @@ __global__ void __launch_bounds__(256) text_kernel(IndexView v, BatchView b, Sea
     f.result = FAST_DEAD;
     f.ln.state = LS_IDLE;
     f.ln.strand = 0;
-    if (i < n) fast_begin(f, v, b, pre, i);
+    if (i < n) fast_begin<true>(f, v, b, pre, i);
     while (__any_sync(full, fast_running(f))) {
       if (fast_running(f) && f.ln.state == LS_TEXT) lane_text_step(f.ln, v);
-      if (fast_running(f) && f.ln.state == LS_EV_TSCAN) fast_event(f, v);
+      if (fast_running(f) && f.ln.state == LS_EV_TSCAN) fast_event<true>(f, v);
     }
-    const uint32_t words = i < n ? fast_outcome(f, v) : 0;
+    uint32_t words = i < n ? fast_outcome(f, v) : 0;
+    const uint32_t strand = f.ln.strand;
+    if (f.result == FAST_BAIL) send_to_general(pre, strand);
+    // a finished candidate claims its strand; a second one makes the strand the general kernel's
+    bool emit = f.result == FAST_MAPPED && fast_claim(pre, strand);
+    if (!emit) words = 0;
     // pool space for the finished states of the round: warp scan + one atomic
     uint32_t incl = words;
 #pragma unroll
@@ -224,40 +243,38 @@ __global__ void __launch_bounds__(256) text_kernel(IndexView v, BatchView b, Sea
     uint32_t base = 0;
     if (total && lane == 31) base = atomicAdd(o.pool_used, total);
     base = __shfl_sync(full, base, 31);
-    const uint32_t strand = f.ln.strand;
-    bool mapped = false;
-    if (i < n) {
-      if (f.result == FAST_MAPPED) {
-        const uint32_t off = base + incl - words;
-        if (off + words > o.pool_cap) {  // final-state pool full: re-run after the host has grown it
-          o.status[strand] = ST_OVERFLOW;
-          o.overflow_list[atomicAdd(o.n_overflow, 1u)] = strand;
-        } else {
-          fast_emit(f, o, off);
-          o.status[strand] = ST_MAPPED;
-          mapped = true;
-        }
-      } else if (f.result == FAST_DEAD) {
-        o.status[strand] = ST_UNCLASSIFIED;
+    if (emit) {
+      const uint32_t off = base + incl - words;
+      if (off + words > o.pool_cap) {  // final-state pool full: re-run after the host has grown it
+        o.status[strand] = ST_OVERFLOW;
+        o.overflow_list[atomicAdd(o.n_overflow, 1u)] = strand;
+        emit = false;
       } else {
-        send_to_general(pre, strand);
+        fast_emit(f, v, o, off);
+        o.status[strand] = ST_MAPPED;
+        atomicOr(pre.surv_cnt + strand, kSurvListed);
       }
     }
-    const uint32_t mm = __ballot_sync(full, mapped);
+    const uint32_t mm = __ballot_sync(full, emit);
     if (mm) {
       uint32_t mbase = 0;
       if (lane == 0) mbase = atomicAdd(o.n_mapped, (uint32_t)__popc(mm));
       mbase = __shfl_sync(full, mbase, 0);
-      if (mapped) o.mapped_list[mbase + __popc(mm & ((1u << lane) - 1u))] = strand;
+      if (emit) o.mapped_list[mbase + __popc(mm & ((1u << lane) - 1u))] = strand;
     }
   }
 }
 
-void launch_text(const IndexView& v, const BatchView& b, const SearchOut& o, const SeedOut& pre, cudaStream_t st) {
+void launch_text(const IndexView& v, const BatchView& b, const SearchOut& o, const SeedOut& pre, uint32_t* surv_rec,
+                 uint32_t* n_verified, cudaStream_t st) {
   uint32_t work = 2 * (b.read_end - b.read_begin);
   if (work == 0) return;
-  uint32_t blocks = min((work / 2 + 255) / 256, 148u * 8u);
-  text_kernel<<<blocks, 256, 0, st>>>(v, b, o, pre);
+  uint32_t blocks = min((work + 255) / 256, 148u * 8u);
+  verify_kernel<<<blocks, 256, 0, st>>>(v, b, pre, surv_rec, n_verified);
+  SeedOut ver = pre;  // the text kernel's candidates are the verified ones
+  ver.rec = surv_rec;
+  ver.n_surv = n_verified;
+  text_kernel<<<blocks, 256, 0, st>>>(v, b, o, ver);
 }
 
 #ifdef GQ_DEBUG_COUNTERS
@@ -282,6 +299,7 @@ __global__ void __launch_bounds__(kSearchThreads, GQ_SEARCH_MIN_BLOCKS)
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t strand0 = 2 * b.read_begin;
+  const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
   bool work_left = work > 0;  // warp-uniform: strands are handed out by one global counter
   uint32_t* my_arena = arena + (size_t)tid * arena_words;
   Lane ln;
@@ -331,17 +349,21 @@ __global__ void __launch_bounds__(kSearchThreads, GQ_SEARCH_MIN_BLOCKS)
     if (n_idle && (n_idle >= rf_thresh || (force && n_idle == big))) {
       DBG(11, 1); DBG(12, n_idle);
       const uint32_t idle = __ballot_sync(full, ln.state == LS_IDLE);
+      // scarce work (the seed pass's general list is usually short) is spread over the warps: the kernel is
+      // a chain of dependent loads per strand, so one strand per warp finishes sooner than 32
+      const uint32_t take = min(c_idle, max(1u, work / n_warps));
       uint32_t base = 0;
-      if (lane == 0) base = atomicAdd(o.work_counter, c_idle);
+      if (lane == 0) base = atomicAdd(o.work_counter, take);
       base = __shfl_sync(full, base, 0);
       if (ln.state == LS_IDLE) {
-        uint32_t i = base + __popc(idle & ((1u << lane) - 1u));
-        if (i < work) {
+        const uint32_t rank = __popc(idle & ((1u << lane) - 1u));
+        uint32_t i = base + rank;
+        if (rank < take && i < work) {
           const uint32_t strand = work_list ? work_list[i] : strand0 + i;
           lane_refill(ln, v, b, o, strand, my_arena, arena_words);
         }
       }
-      work_left = base + c_idle < work;
+      work_left = base + take < work;
       continue;
     }
     // hot loop: keep stepping until `leave` lanes have dropped out of LS_RUN (or none is left); the

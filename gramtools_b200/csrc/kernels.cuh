@@ -36,18 +36,18 @@ struct SearchOut {
   uint32_t* mapped_list;    // strands with >= 1 final state, in completion order (coverage work list)
   uint32_t* n_mapped;
   uint32_t* work_counter;   // dynamic work distribution of the search kernel
+  uint32_t* listed;         // per strand flags (SeedOut::surv_cnt) or nullptr: kSurvListed = already on mapped_list
 };
 
-// Output of the seed pass (seed_kernel): the width-1 states (one suffix each, in text mode) that survived the
-// text check, as records for the text kernel, plus the strands that need the general search kernel.
+// Output of the seed pass (seed_kernel): one candidate per suffix of every (narrowed) seed state — a width-1
+// search state the text kernel walks through the PRG text — plus the strands that need the general kernel.
 struct SeedOut {
-  uint32_t* rec;        // 8 words (one sector) per survivor: {pos | kind << 28, text position, nt | ng << 16,
-                        //  path_off (k-mer index), strand, read length, packed word offset, k-mer state index}
-  uint32_t cap;         // survivor records available
+  uint32_t* rec;        // 4 words per candidate: {strand, k-mer state index, SA index, pos | kind << 28}
+  uint32_t cap;         // candidate records available
   uint32_t* n_surv;     // bump pointer
-  uint32_t* surv_cnt;   // per strand: survivors | kSurvGeneral once the strand is on gen_list
-  uint32_t* gen_list;   // strands for the general search kernel (several survivors, wide or finished seed
-  uint32_t* n_gen;      //  states, jumps the text kernel does not take)
+  uint32_t* surv_cnt;   // per strand: finished candidates (low 16 bits) | kSurvGeneral | kSurvListed
+  uint32_t* gen_list;   // strands for the general search kernel (several finished candidates, seed states
+  uint32_t* n_gen;      //  that cannot be split, jumps the text kernel does not take)
 };
 
 struct CoverageView {
@@ -74,9 +74,11 @@ void launch_pack(const uint8_t* bases, const uint64_t* offsets, uint32_t r0, uin
 // Seed pass over the strands of the slice b.read_begin..b.read_end.
 void launch_seed(const IndexView& v, const BatchView& b, const SearchOut& o, const SeedOut& pre, cudaStream_t st);
 
-// Fast path over the survivor records: strands with one survivor are finished in text mode; the rest is
-// appended to pre.gen_list.
-void launch_text(const IndexView& v, const BatchView& b, const SearchOut& o, const SeedOut& pre, cudaStream_t st);
+// Fast path: verify pass over the candidates (survivors copied to surv_rec, same capacity as pre.rec, counted
+// in *n_verified), then the text kernel over the survivors: strands with one finished candidate get their
+// final state here; the rest is appended to pre.gen_list.
+void launch_text(const IndexView& v, const BatchView& b, const SearchOut& o, const SeedOut& pre, uint32_t* surv_rec,
+                 uint32_t* n_verified, cudaStream_t st);
 
 // General search kernel. list == nullptr: every strand of the slice; otherwise the listed strands (n_list of
 // them, or *n_list_dev when that pointer is given). Strands are seeded from the k-mer index in the kernel.

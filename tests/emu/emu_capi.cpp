@@ -124,8 +124,10 @@ int emu_map(void* ev, const uint8_t* bases, const uint64_t* off, uint64_t n_read
     e->pool.assign(std::max<size_t>(1 << 16, n_reads * 256), 0);
     std::vector<uint32_t> small(8, 0), ovf(2 * n_reads + 1), cov_ovf(2 * n_reads + 1), mapped(4 * n_reads + 1);
     BatchView b{packed.data(), word_off.data(), len.data(), seeds, (uint32_t)n_reads, 0, (uint32_t)n_reads};
+    std::vector<uint32_t> seed_rec(4 * 4096), surv_cnt(2 * n_reads + 1, 0), gen(2 * n_reads + 1), pre_small(2, 0);
     SearchOut o{e->status.data(), e->st_off.data(), e->st_words.data(), e->st_count.data(), e->pool.data(),
-                (uint32_t)e->pool.size(), &small[0], ovf.data(), &small[1], mapped.data(), &small[3], &small[4]};
+                (uint32_t)e->pool.size(), &small[0], ovf.data(), &small[1], mapped.data(), &small[3], &small[4],
+                surv_cnt.data()};
     CoverageView c{};
     uint64_t na = h.allele_off.back();
     c.allele_sum = e->counters.data();
@@ -140,8 +142,7 @@ int emu_map(void* ev, const uint8_t* bases, const uint64_t* off, uint64_t n_read
     c.error_flags = &e->gsmall[1];
     c.stats = e->stats;
     c.allele_off = h.allele_off.data();
-    std::vector<uint32_t> seed_rec(8 * 4096), surv_cnt(2 * n_reads + 1, 0), gen(2 * n_reads + 1), pre_small(2, 0);
-    SeedOut pre{seed_rec.data(), (uint32_t)(seed_rec.size() / 8), &pre_small[0], surv_cnt.data(), gen.data(),
+    SeedOut pre{seed_rec.data(), (uint32_t)(seed_rec.size() / 4), &pre_small[0], surv_cnt.data(), gen.data(),
                 &pre_small[1]};
     std::vector<uint32_t> arena(arena_words), big;
     for (uint32_t s = 0; s < 2 * n_reads; ++s) {
