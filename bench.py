@@ -26,6 +26,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 REF_LEN, N_SITES, N_READS, READ_LEN, KMER = 4_400_000, 100_000, 1_000_000, 150, 10
 GEN_SEED = 0x6772616D + 2
 MAP_SEED = 42
+# ncu --set full, config 2, 1M reads, dram__bytes_read.sum + dram__bytes_write.sum summed over seed_kernel,
+# verify_kernel, text_kernel and search_kernel (profiles/r01_v9_kernels_summary.txt)
+SEARCH_PHASE_DRAM_BYTES = None
 
 
 def env_int(name, default):
@@ -285,14 +288,17 @@ def main():
         if alg_bytes_per_read is not None:
             per_launch_s = (search_ms / args.steps) / 1e3
             achieved = alg_bytes_per_read * N_READS / per_launch_s / 1e9
-            # dram__bytes_read.sum + dram__bytes_write.sum of one search_kernel launch on this workload, from
-            # the committed `ncu --set full` capture (profiles/r01_v5_kernels_summary.txt); it is far below
-            # the algorithmic bytes because the 2.4 MB of rank blocks are L2-resident at this index size
-            traffic = 683380992 + 272083968 if N_READS == 1_000_000 else None
-            roof = {"bound": "hbm", "kernel": "seed_kernel+search_kernel (search phase)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            # dram__bytes_read.sum + dram__bytes_write.sum of the search-phase kernels (seed + verify + text +
+            # general) for one 1M-read batch, from the committed `ncu --set full` capture (profiles/)
+            traffic = SEARCH_PHASE_DRAM_BYTES if N_READS == 1_000_000 else None
+            roof = {"bound": "hbm", "kernel": "search phase: seed_kernel + verify_kernel + text_kernel + search_kernel",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_read": alg_bytes_per_read,
-                    "kernel_ms_per_launch": search_ms / args.steps, "coverage_kernel_ms": cov_ms / args.steps}
+                    "kernel_ms_per_launch": search_ms / args.steps, "coverage_kernel_ms": cov_ms / args.steps,
+                    "note": "algorithmic bytes are the REFERENCE algorithm's (SURVEY 8d: 32 B per rank query, 2 per state "
+                            "per base); width-1 states are walked in the packed PRG text instead (16 bases per 8 B), so "
+                            "frac can exceed 1 and measured DRAM traffic is far below the algorithmic bytes"}
         line = {
             "metric": "quasimap reads/sec", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",

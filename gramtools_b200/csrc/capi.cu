@@ -75,9 +75,16 @@ struct gq_index {
   uint32_t seed_recs_per_read = 16;  // candidate records per read (set from the index: ~2.5 x mean suffixes per indexed k-mer, both strands); a full pool sends strands to the general kernel
   bool use_seed_pass = true;
   DevBuf<uint32_t> arena, big_arena;
-  cudaStream_t copy_stream = nullptr;
+  cudaStream_t copy_stream = nullptr, copy_stream2 = nullptr;
+  cudaStream_t aux_stream = nullptr;  // second compute stream of the pipelined path
+  cudaEvent_t aux_event = nullptr;
+  DevBuf<uint32_t> arena2;
+  void* fetch_host = nullptr;  // pinned staging of gq_coverage_fetch
+  size_t fetch_host_bytes = 0;
+  DevBuf<uint16_t> fetch_dev;
   std::vector<cudaEvent_t> chunk_events;
-  uint32_t chunk_reads = 1u << 18;  // slice size of the H2D / compute pipeline in gq_map_batch
+  uint32_t chunk_reads = 1u << 17, tail_chunk_reads = 1u << 15;
+  uint32_t resident_slices = 1;  // gq_map_resident: slices run on two streams  // slice size of the H2D / compute pipeline in gq_map_batch
   // options
   uint32_t arena_words = 512;
   uint32_t n_threads = 148 * 1280;      // search kernel lanes (5 CTAs of 256 per SM)
@@ -202,18 +209,38 @@ struct Chunk {
 
 static std::vector<Chunk> make_chunks(gq_index* ix, uint32_t n, bool pipelined) {
   std::vector<Chunk> ch;
-  uint32_t per = pipelined ? std::max<uint32_t>(ix->chunk_reads, (n + 31) / 32) : n;
-  for (uint32_t r = 0; r < n; r += per) ch.push_back({r, std::min<uint32_t>(n, r + per)});
+  if (!pipelined) {  // resident batch: equal slices (alternating between the two compute streams)
+    const uint32_t k = std::max<uint32_t>(1, std::min<uint32_t>(ix->resident_slices, (n + 65535) / 65536));
+    const uint32_t per = (n + k - 1) / k;
+    for (uint32_t r = 0; r < n; r += per) ch.push_back({r, std::min(n, r + per)});
+    return ch;
+  }
+  // Slices of chunk_reads reads, then halving towards the end: the copy engine is the bottleneck of the
+  // pipelined path, so what matters is how little compute is left when the last byte has arrived.
+  const uint32_t big = std::max<uint32_t>(ix->chunk_reads, (n + 23) / 24), small = std::max<uint32_t>(ix->tail_chunk_reads, 1024);
+  for (uint32_t r = 0; r < n;) {
+    uint32_t left = n - r;
+    uint32_t per = left <= small ? left : std::max(small, std::min(big, left / 2));
+    ch.push_back({r, r + per});
+    r += per;
+  }
   return ch;
 }
 
-// H2D of one slice of the caller's buffers + 2-bit packing, on stream `st`
-static void upload_chunk(gq_index* ix, const uint8_t* bases, const uint64_t* off, const uint32_t* seeds, Chunk c,
-                         cudaStream_t st) {
+// H2D of one slice of the caller's buffers: bases on `st`, the small per-read arrays on `st_small` (their
+// set-up latency then overlaps the big copy instead of sitting between two of them)
+static void copy_chunk(gq_index* ix, const uint8_t* bases, const uint64_t* off, const uint32_t* seeds, Chunk c,
+                       cudaStream_t st, cudaStream_t st_small) {
   uint64_t b0 = off[c.r0], b1 = off[c.r1];
   if (b1 > b0) CUDA_OK(cudaMemcpyAsync(ix->bases.p + b0, bases + b0, b1 - b0, cudaMemcpyHostToDevice, st));
-  CUDA_OK(cudaMemcpyAsync(ix->offsets.p + c.r0, off + c.r0, (size_t)(c.r1 - c.r0 + 1) * 8, cudaMemcpyHostToDevice, st));
-  CUDA_OK(cudaMemcpyAsync(ix->seeds.p + c.r0, seeds + c.r0, (size_t)(c.r1 - c.r0) * 4, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(ix->offsets.p + c.r0, off + c.r0, (size_t)(c.r1 - c.r0 + 1) * 8, cudaMemcpyHostToDevice, st_small));
+  CUDA_OK(cudaMemcpyAsync(ix->seeds.p + c.r0, seeds + c.r0, (size_t)(c.r1 - c.r0) * 4, cudaMemcpyHostToDevice, st_small));
+}
+
+// H2D + 2-bit packing of one slice on one stream
+static void upload_chunk(gq_index* ix, const uint8_t* bases, const uint64_t* off, const uint32_t* seeds, Chunk c,
+                         cudaStream_t st) {
+  copy_chunk(ix, bases, off, seeds, c, st, st);
   gq::launch_pack(ix->bases.p, ix->offsets.p, c.r0, c.r1, ix->word_off.p, ix->packed.p, ix->len.p, st);
 }
 
@@ -276,23 +303,45 @@ static void do_map(gq_index* ix, const uint8_t* h_bases = nullptr, const uint64_
   int launches = 0;
   if (pipelined) {
     if (!ix->copy_stream) CUDA_OK(cudaStreamCreateWithFlags(&ix->copy_stream, cudaStreamNonBlocking));
-    while (ix->chunk_events.size() < chunks.size()) {
+    if (!ix->copy_stream2) CUDA_OK(cudaStreamCreateWithFlags(&ix->copy_stream2, cudaStreamNonBlocking));
+    while (ix->chunk_events.size() < 2 * chunks.size()) {
       cudaEvent_t e;
       CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
       ix->chunk_events.push_back(e);
     }
-    // the copy stream must not start overwriting buffers the compute stream may still be reading
+    // the copy streams must not start overwriting buffers the compute stream may still be reading
     CUDA_OK(cudaEventRecord(ix->ev[3], st));
     CUDA_OK(cudaStreamWaitEvent(ix->copy_stream, ix->ev[3], 0));
+    CUDA_OK(cudaStreamWaitEvent(ix->copy_stream2, ix->ev[3], 0));
+    // copies only on the copy streams, back to back; packing runs on the compute stream
     for (size_t i = 0; i < chunks.size(); ++i) {
-      upload_chunk(ix, h_bases, h_off, h_seeds, chunks[i], ix->copy_stream);
-      CUDA_OK(cudaEventRecord(ix->chunk_events[i], ix->copy_stream));
-      launches += 1;
+      copy_chunk(ix, h_bases, h_off, h_seeds, chunks[i], ix->copy_stream, ix->copy_stream2);
+      CUDA_OK(cudaEventRecord(ix->chunk_events[2 * i], ix->copy_stream));
+      CUDA_OK(cudaEventRecord(ix->chunk_events[2 * i + 1], ix->copy_stream2));
     }
   }
   CUDA_OK(cudaEventRecord(ix->ev[0], st));
+  // Slices alternate between two compute streams (each with its own arena), so the kernels of slice i+1
+  // fill the GPU while slice i's are in their latency-bound tails; the caller's stream joins at the end.
+  const bool two_streams = chunks.size() > 1;
+  if (two_streams) {
+    if (!ix->aux_stream) {
+      CUDA_OK(cudaStreamCreateWithFlags(&ix->aux_stream, cudaStreamNonBlocking));
+      CUDA_OK(cudaEventCreateWithFlags(&ix->aux_event, cudaEventDisableTiming));
+    }
+    ix->arena2.reserve((size_t)std::max(threads, threads2) * ix->arena_words);
+    if (!pipelined) CUDA_OK(cudaEventRecord(ix->ev[3], st));
+    CUDA_OK(cudaStreamWaitEvent(ix->aux_stream, ix->ev[3], 0));  // after the counters' memset
+  }
   for (size_t i = 0; i < chunks.size(); ++i) {
-    if (pipelined) CUDA_OK(cudaStreamWaitEvent(st, ix->chunk_events[i], 0));
+    cudaStream_t cs = (two_streams && (i & 1)) ? ix->aux_stream : st;
+    uint32_t* arena = (two_streams && (i & 1)) ? ix->arena2.p : ix->arena.p;
+    if (pipelined) {
+      CUDA_OK(cudaStreamWaitEvent(cs, ix->chunk_events[2 * i], 0));
+      CUDA_OK(cudaStreamWaitEvent(cs, ix->chunk_events[2 * i + 1], 0));
+      gq::launch_pack(ix->bases.p, ix->offsets.p, chunks[i].r0, chunks[i].r1, ix->word_off.p, ix->packed.p, ix->len.p, cs);
+      ++launches;
+    }
     gq::BatchView bc = b;
     bc.read_begin = chunks[i].r0;
     bc.read_end = chunks[i].r1;
@@ -301,34 +350,43 @@ static void do_map(gq_index* ix, const uint8_t* h_bases = nullptr, const uint64_
     oc.n_mapped = ix->small.p + 8 + 4 * i;
     oc.work_counter = ix->small.p + 9 + 4 * i;
     if (ix->use_seed_pass) {
-      // seed pass -> text kernel (strands with one surviving width-1 seed) -> general kernel (the rest)
+      // seed pass -> verify + text kernels (candidates walked through the PRG text) -> general kernel (the rest)
       uint32_t* gen_list = ix->gen_list.p + 2 * (size_t)chunks[i].r0;
       uint32_t* n_gen = ix->small.p + 11 + 4 * i;
       gq::SeedOut pre{ix->seed_rec.p + 4 * (size_t)ix->seed_recs_per_read * chunks[i].r0,
                       (uint32_t)(ix->seed_recs_per_read * (chunks[i].r1 - chunks[i].r0)),
                       ix->small.p + 10 + 4 * i, ix->surv_cnt.p, gen_list, n_gen};
-      gq::launch_seed(ix->dv, bc, oc, pre, st);
+      gq::launch_seed(ix->dv, bc, oc, pre, cs);
       gq::launch_text(ix->dv, bc, oc, pre, ix->surv_rec.p + 4 * (size_t)ix->seed_recs_per_read * chunks[i].r0,
-                      ix->small.p + 8 + 4 * 64 + i, st);
+                      ix->small.p + 8 + 4 * 64 + i, cs);
       ++launches;
-      gq::launch_search(ix->dv, bc, oc, ix->arena.p, ix->arena_words, threads, gen_list,
-                        2 * (chunks[i].r1 - chunks[i].r0), ix->super_in_smem, ix->rf_thresh, ix->ev_thresh, st,
+      gq::launch_search(ix->dv, bc, oc, arena, ix->arena_words, threads, gen_list,
+                        2 * (chunks[i].r1 - chunks[i].r0), ix->super_in_smem, ix->rf_thresh, ix->ev_thresh, cs,
                         ix->leave_opt, ix->wait_opt, n_gen);
       launches += 2;
     } else
-      gq::launch_search(ix->dv, bc, oc, ix->arena.p, ix->arena_words, threads, nullptr, 0, ix->super_in_smem,
-                        ix->rf_thresh, ix->ev_thresh, st, ix->leave_opt, ix->wait_opt);
+      gq::launch_search(ix->dv, bc, oc, arena, ix->arena_words, threads, nullptr, 0, ix->super_in_smem,
+                        ix->rf_thresh, ix->ev_thresh, cs, ix->leave_opt, ix->wait_opt);
     if (chunks.size() == 1) CUDA_OK(cudaEventRecord(ix->ev[1], st));
-    gq::launch_classify(ix->dv, bc, oc, nullptr, 0, st);
-    gq::launch_coverage(ix->dv, bc, oc, c, ix->arena.p, ix->arena_words, threads2, nullptr, 0,
-                        ix->cov_overflow_list.p, ix->small.p + 2, st);
+    gq::launch_classify(ix->dv, bc, oc, nullptr, 0, cs);
+    gq::launch_coverage(ix->dv, bc, oc, c, arena, ix->arena_words, threads2, nullptr, 0,
+                        ix->cov_overflow_list.p, ix->small.p + 2, cs);
     launches += 3;
+  }
+  if (two_streams) {
+    CUDA_OK(cudaEventRecord(ix->aux_event, ix->aux_stream));
+    CUDA_OK(cudaStreamWaitEvent(st, ix->aux_event, 0));
   }
   CUDA_OK(cudaEventRecord(ix->ev[2], st));
   uint32_t small[4];
   CUDA_OK(cudaMemcpyAsync(small, ix->small.p, 16, cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaStreamSynchronize(st));
   CUDA_OK(cudaGetLastError());
+  {
+    float ms_t = 0;
+    cudaEventElapsedTime(&ms_t, ix->ev[0], ix->ev[2]);
+    ix->info[6] = ms_t;  // all kernels of the call (CUDA events on the caller's stream)
+  }
   if (chunks.size() == 1) {
     float ms_s = 0, ms_c = 0;
     cudaEventElapsedTime(&ms_s, ix->ev[0], ix->ev[1]);
@@ -532,6 +590,12 @@ int gq_index_destroy(gq_index* ix) {
     if (e) cudaEventDestroy(e);
   for (auto& e : ix->chunk_events) cudaEventDestroy(e);
   if (ix->copy_stream) cudaStreamDestroy(ix->copy_stream);
+  if (ix->copy_stream2) cudaStreamDestroy(ix->copy_stream2);
+  if (ix->aux_stream) cudaStreamDestroy(ix->aux_stream);
+  if (ix->aux_event) cudaEventDestroy(ix->aux_event);
+  ix->arena2.release();
+  if (ix->fetch_host) cudaFreeHost(ix->fetch_host);
+  ix->fetch_dev.release();
   if (ix->own_stream) cudaStreamDestroy(ix->own_stream);
   delete ix;
   return 0;
@@ -672,21 +736,29 @@ int gq_coverage_fetch(gq_index* ix, uint16_t* allele_sum, uint16_t* per_base, ui
   if (!ix) throw std::runtime_error("null argument");
   CUDA_OK(cudaSetDevice(ix->device));
   CUDA_OK(cudaStreamSynchronize(ix->stream));
-  if (allele_sum && ix->n_alleles) {
-    std::vector<uint32_t> t(ix->n_alleles);
-    CUDA_OK(cudaMemcpy(t.data(), ix->counters.p, ix->n_alleles * 4, cudaMemcpyDeviceToHost));
-    for (size_t i = 0; i < t.size(); ++i) allele_sum[i] = (uint16_t)(t[i] & 0xFFFFu);  // uint16 wrap
+  // uint16 semantics applied on the device; one D2H of the uint16 vectors + counters into pinned memory
+  const size_t n16 = ix->n_alleles + ix->n_per_base;
+  const size_t bytes = n16 * 2 + 64;
+  if (ix->fetch_host_bytes < bytes) {
+    if (ix->fetch_host) cudaFreeHost(ix->fetch_host);
+    ix->fetch_host = nullptr;
+    CUDA_OK(cudaMallocHost(&ix->fetch_host, bytes));
+    ix->fetch_host_bytes = bytes;
   }
-  if (per_base && ix->n_per_base) {
-    std::vector<uint32_t> t(ix->n_per_base);
-    CUDA_OK(cudaMemcpy(t.data(), ix->counters.p + 2 * ix->n_alleles, ix->n_per_base * 4, cudaMemcpyDeviceToHost));
-    for (size_t i = 0; i < t.size(); ++i) per_base[i] = (uint16_t)std::min<uint32_t>(t[i], 65535u);  // saturate
+  ix->fetch_dev.reserve(n16 + 1);
+  unsigned long long* hs = (unsigned long long*)ix->fetch_host;
+  uint16_t* h16 = (uint16_t*)((char*)ix->fetch_host + 64);
+  if ((allele_sum || per_base) && n16) {
+    gq::launch_fetch(ix->counters.p, (uint32_t)ix->n_alleles, ix->counters.p + 2 * ix->n_alleles, (uint32_t)ix->n_per_base,
+                     ix->fetch_dev.p, ix->stream);
+    CUDA_OK(cudaMemcpyAsync(h16, ix->fetch_dev.p, n16 * 2, cudaMemcpyDeviceToHost, ix->stream));
   }
-  if (stats) {
-    unsigned long long s[5];
-    CUDA_OK(cudaMemcpy(s, ix->stats.p, sizeof(s), cudaMemcpyDeviceToHost));
-    for (int i = 0; i < 5; ++i) stats[i] = s[i];
-  }
+  if (stats) CUDA_OK(cudaMemcpyAsync(hs, ix->stats.p, 40, cudaMemcpyDeviceToHost, ix->stream));
+  CUDA_OK(cudaStreamSynchronize(ix->stream));
+  if (allele_sum && ix->n_alleles) std::memcpy(allele_sum, h16, ix->n_alleles * 2);
+  if (per_base && ix->n_per_base) std::memcpy(per_base, h16 + ix->n_alleles, ix->n_per_base * 2);
+  if (stats)
+    for (int i = 0; i < 5; ++i) stats[i] = hs[i];
   GQ_CATCH
 }
 
@@ -922,6 +994,10 @@ int gq_set_option(gq_index* ix, const char* name, int64_t value) {
   } else if (n == "pool_words_per_read") {
     ix->pool_words_per_read = (uint32_t)std::max<int64_t>(value, 1);
     ix->pool.release();
+  } else if (n == "resident_slices") {
+    ix->resident_slices = (uint32_t)std::max<int64_t>(value, 1);
+  } else if (n == "tail_chunk_reads") {
+    ix->tail_chunk_reads = (uint32_t)std::max<int64_t>(value, 1024);
   } else if (n == "chunk_reads") {
     ix->chunk_reads = (uint32_t)std::max<int64_t>(value, 1024);
   } else if (n == "seed_pass") {

@@ -420,6 +420,22 @@ void launch_classify(const IndexView& v, const BatchView& b, const SearchOut& o,
   classify_kernel<<<blocks, 256, 0, st>>>(v, b, o, list, n_list);
 }
 
+// uint16 view of the accumulators for gq_coverage_fetch: allele_sum wraps mod 65536 (allele_sum.cpp:41),
+// per-base coverage saturates at 65535 (allele_base.cpp:239)
+__global__ void fetch_kernel(const uint32_t* __restrict__ allele_sum, uint32_t n_alleles,
+                             const uint32_t* __restrict__ per_base, uint32_t n_per_base, uint16_t* __restrict__ out) {
+  const uint32_t n = n_alleles + n_per_base;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    out[i] = i < n_alleles ? (uint16_t)(allele_sum[i] & 0xFFFFu) : (uint16_t)min(per_base[i - n_alleles], 65535u);
+}
+
+void launch_fetch(const uint32_t* allele_sum, uint32_t n_alleles, const uint32_t* per_base, uint32_t n_per_base,
+                  uint16_t* out, cudaStream_t st) {
+  const uint32_t n = n_alleles + n_per_base;
+  if (n == 0) return;
+  fetch_kernel<<<min((n + 255) / 256, 148u * 8u), 256, 0, st>>>(allele_sum, n_alleles, per_base, n_per_base, out);
+}
+
 int search_kernel_smem_limit_superblocks() { return kMaxSuperSmem; }
 
 void debug_counters(unsigned long long* out32) {

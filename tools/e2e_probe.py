@@ -1,4 +1,5 @@
-"""Developer probe: end-to-end gq_map_batch time (pinned host buffers) vs pipeline slice size."""
+"""Developer probe: end-to-end gq_map_batch time (pinned host buffers) vs pipeline slice sizes.
+GQ_CHUNKS = comma list of chunk_reads[:tail_chunk_reads]."""
 import os
 import sys
 import time
@@ -16,8 +17,10 @@ idx = QuasimapIndex(prg, bench.KMER)
 pb = torch.from_numpy(bases).pin_memory().numpy()
 po = torch.from_numpy(offs.view(np.int64)).pin_memory().numpy().view(np.uint64)
 ps = torch.from_numpy(seeds.view(np.int32)).pin_memory().numpy().view(np.uint32)
-for chunk in [int(x) for x in os.environ.get("GQ_CHUNKS", "65536,131072,262144,524288,1048576").split(",")]:
+for spec in os.environ.get("GQ_CHUNKS", "131072:131072,262144:32768,262144:65536,524288:32768").split(","):
+    chunk, tail = (int(x) for x in (spec.split(":") + [spec])[:2])
     idx.set_option("chunk_reads", chunk)
+    idx.set_option("tail_chunk_reads", tail)
     for _ in range(3):
         idx.map_batch(pb, po, ps)
     torch.cuda.synchronize()
@@ -30,4 +33,4 @@ for chunk in [int(x) for x in os.environ.get("GQ_CHUNKS", "65536,131072,262144,5
     for _ in range(10):
         idx.coverage()
     dc = (time.perf_counter() - t) / 10
-    print(f"chunk_reads={chunk}: map_batch {dt*1e3:.2f} ms ({1e6/dt/1e6:.0f} M reads/s); coverage fetch {dc*1e3:.2f} ms")
+    print(f"chunk_reads={chunk} tail={tail}: map_batch {dt*1e3:.2f} ms ({1e6/dt/1e6:.0f} M reads/s); coverage fetch {dc*1e3:.2f} ms")

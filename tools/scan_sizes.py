@@ -20,7 +20,7 @@ for n in sizes:
     for _ in range(5):
         idx.map_resident()
         i = idx.run_info()
-        t = (i["search_ms"], i["coverage_ms"])
-        best = t if best is None or sum(t) < sum(best) else best
-    print(f"n_reads={n}: search {best[0]:.3f} ms, classify+coverage {best[1]:.3f} ms -> "
-          f"{n / (sum(best) / 1e3) / 1e6:.0f} M reads/s (kernels)", flush=True)
+        t = (i["search_ms"], i["coverage_ms"], i["kernels_ms"])
+        best = t if best is None or t[2] < best[2] else best
+    print(f"n_reads={n}: search {best[0]:.3f} ms, classify+coverage {best[1]:.3f} ms, all kernels {best[2]:.3f} ms -> "
+          f"{n / (best[2] / 1e3) / 1e6:.0f} M reads/s (kernels)", flush=True)
