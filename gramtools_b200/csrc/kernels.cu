@@ -157,8 +157,12 @@ __global__ void __launch_bounds__(256)
     uint32_t base = 0;
     if (sum && lane == 31) base = atomicAdd(pre.n_surv, sum);
     base = __shfl_sync(full, base, 31);
-    if (general || (mine && base + sum > pre.cap)) send_to_general(pre, strand);  // cannot split / pool full
-    else if (mine) seed_write(v, plan, pre, strand, base + incl - mine);
+    if (general) send_to_general(pre, strand);  // cannot be split
+    else if (mine && base + sum > pre.cap) {    // candidate pool full: general kernel; the slots stay dead
+      send_to_general(pre, strand);
+      for (uint32_t q = base + incl - mine; q < base + incl && q < pre.cap; ++q) pre.rec[4 * (size_t)q] = kNoAllele;
+    } else if (mine)
+      seed_write(v, plan, pre, strand, base + incl - mine);
   }
 }
 
@@ -187,7 +191,7 @@ __global__ void __launch_bounds__(256) verify_kernel(IndexView v, BatchView b, S
     f.result = FAST_DEAD;
     f.ln.state = LS_IDLE;
     f.ln.pos = 0;
-    if (i < n) fast_begin<false>(f, v, b, pre, i);
+    if (i < n && __ldg(pre.rec + 4 * (size_t)i) != kNoAllele) fast_begin<false>(f, v, b, pre, i);
     const uint32_t pos0 = f.ln.pos;
     for (uint32_t it = 0; it < kVerifyIters && __any_sync(full, !fast_verified(f, pos0)); ++it) {
       if (!fast_verified(f, pos0) && f.ln.state == LS_TEXT) lane_text_step(f.ln, v);

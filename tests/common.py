@@ -82,6 +82,8 @@ def emu_lib():
         lib.emu_grouped.argtypes = [C.c_void_p, u32p]
         lib.emu_grouped.restype = C.c_uint64
         lib.emu_stats.argtypes = [C.c_void_p, u64p]
+        lib.emu_path_counters.argtypes = [u64p, C.c_int]
+        lib.emu_force_general.argtypes = [C.c_int]
         lib.emu_counters_raw.argtypes = [C.c_void_p, u32p]
         lib.emu_groups_raw.argtypes = [C.c_void_p, u32p]
         lib.emu_groups_raw.restype = C.c_uint64
@@ -203,6 +205,18 @@ class Emu:
         if rc != 0:
             raise RuntimeError(self.lib.emu_last_error().decode())
         self.n_reads = n
+
+    ROUTES = ["seed_finished", "too_wide", "seed_states", "-", "multi_finisher", "unresolved_jump", "wide_entry",
+              "fast_finished", "general", "many_seed_states"]
+
+    def routes(self, reset=True):
+        """Which route strands took since the last reset (process-wide counters of the emulation)."""
+        c = np.zeros(32, dtype=np.uint64)
+        self.lib.emu_path_counters(_ptr(c, C.c_uint64), int(reset))
+        return {k: int(v) for k, v in zip(self.ROUTES, c) if k != "-"}
+
+    def force_general(self, on):
+        self.lib.emu_force_general(int(on))
 
     def counters_raw(self):
         out = np.zeros(max(2 * self.n_alleles + self.n_per_base, 1), dtype=np.uint32)

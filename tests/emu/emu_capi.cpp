@@ -30,6 +30,7 @@ struct Emu {
   uint64_t reruns = 0;
 };
 static thread_local std::string g_err;
+static int g_force_general = 0;
 
 extern "C" {
 const char* emu_last_error() { return g_err.c_str(); }
@@ -151,6 +152,7 @@ int emu_map(void* ev, const uint8_t* bases, const uint64_t* off, uint64_t n_read
       while (true) {  // same policy as the library: re-run the strand with a 4x larger arena
         small[1] = 0;
         small[3] = 0;
+        if (g_force_general) e->status[s] = ST_OVERFLOW;  // map_strand's re-run route = general machinery
         map_strand(v, v.super_cnt, b, o, pre, s, a, aw);
         if (e->status[s] != ST_OVERFLOW) break;
         e->reruns++;
@@ -185,6 +187,9 @@ int emu_map(void* ev, const uint8_t* bases, const uint64_t* off, uint64_t n_read
     return -1;
   }
 }
+// 1: every strand through the general lane machine (as libgq does with the seed_pass option off)
+void emu_force_general(int on) { g_force_general = on; }
+
 void emu_path_counters(uint64_t* out32, int reset) {
   for (int i = 0; i < 32; ++i) {
     out32[i] = gq_emu_counters[i];

@@ -171,3 +171,22 @@ def test_multi_gpu_plumbing_single_device(built_lib):
     a, p, g = finalize_counters(total, o.n_alleles, o.n_per_base, groups, parts[0][2].allele_offsets())
     assert np.array_equal(a, ref.allele_sum) and np.array_equal(p, ref.per_base)
     assert np.array_equal(g, ref.grouped)
+
+
+@pytest.mark.parametrize("options", [{"seed_pass": 0}, {"seed_recs_per_read": 1}, {"resident_slices": 3}])
+def test_route_options(built_lib, options):
+    """General kernel only / candidate pool too small (strands fall back to the general kernel) / slices on two
+    streams: same results."""
+    for prg, k, L in ((synth.make_snp_prg(3000, 200, 5)[0], 6, 70), (synth.make_nested_prg(6, 300, 5), 5, 40)):
+        bases, offs = _reads_for(prg, 4000, L, 9, garbage=0.02, n_frac=0.0)
+        _check(prg, k, bases, offs, what=str(options), options=options, threads=4)
+
+
+def test_repeats(built_lib):
+    rng = np.random.default_rng(3)
+    unit = rng.integers(1, 5, 120)
+    prg = np.concatenate([rng.integers(1, 5, 200), unit, rng.integers(1, 5, 150), unit, rng.integers(1, 5, 200)]).astype(np.uint32)
+    s = lambda a: "".join("?ACGT"[x] for x in a)
+    reads = [s(unit[10:70]), s(unit[30:110]), s(prg[150:230]), s(prg[5:90])] * 50
+    bases, offs = encode_reads(reads)
+    _check(prg, 6, bases, offs, what="repeats")

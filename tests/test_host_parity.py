@@ -160,3 +160,53 @@ def test_malformed_prgs_rejected():
     for bad in ([5, 1, 6, 2, 6, 5, 3, 6, 4, 6], [1, 5, 2, 6, 4], [1, 5, 6, 2], [1, 6, 2, 6], [1, 5, 2, 6, 3]):
         with pytest.raises(RuntimeError):
             Emu(np.asarray(bad, dtype=np.uint32), 2)
+
+
+def test_text_and_general_routes_agree():
+    """The text-mode fast path (seed candidates -> verify -> text walk) and the general lane machine must
+    give the same states and coverage; both are exercised, and both match the oracle."""
+    for name, prg, k, L in (("snp", synth.make_snp_prg(3000, 200, 5)[0], 6, 70),
+                            ("nested", synth.make_nested_prg(6, 300, 5), 5, 40),
+                            ("indel", synth.make_indel_prg(3000, 150, 5), 6, 60)):
+        bases, offs = _reads_for(prg, 1500, L, 9, garbage=0.02, n_frac=0.0)
+        seeds = master_seeds(42, offs.size - 1)
+        o, e = Oracle(prg, k), Emu(prg, k)
+        o.map(bases, offs, seeds)
+        ro = o.result()
+        e.routes(reset=True)
+        e.map(bases, offs, seeds)
+        r = e.routes()
+        assert_parity(e.result(), ro, name + "/default")
+        assert r["fast_finished"] > 0, r
+        if name == "snp":
+            assert r["fast_finished"] > 20 * r["general"], r  # isolated SNPs: nearly everything on the fast path
+        if name == "nested":
+            assert r["general"] > 0, r  # adjacent / nested markers need the general jump machinery
+        g = Emu(prg, k)
+        g.force_general(True)
+        try:
+            g.map(bases, offs, seeds)
+            r2 = g.routes()
+        finally:
+            g.force_general(False)
+        assert r2["fast_finished"] == 0 and r2["general"] > 0, r2
+        assert_parity(g.result(), ro, name + "/general-only")
+
+
+def test_repeats_take_the_general_route():
+    """A read that maps to two copies of a repeat is ONE SearchState with a 2-wide interval in the reference;
+    the split candidates both finish, so the strand must be redone by the general machinery."""
+    rng = np.random.default_rng(3)
+    unit = rng.integers(1, 5, 120)
+    prg = np.concatenate([rng.integers(1, 5, 200), unit, rng.integers(1, 5, 150), unit, rng.integers(1, 5, 200)]).astype(np.uint32)
+    s = lambda a: "".join("?ACGT"[x] for x in a)
+    reads = [s(unit[10:70]), s(unit[30:110]), s(prg[150:230]), s(prg[5:90])]
+    bases, offs = encode_reads(reads)
+    seeds = master_seeds(1, len(reads))
+    o, e = Oracle(prg, 6), Emu(prg, 6)
+    o.map(bases, offs, seeds)
+    e.routes(reset=True)
+    e.map(bases, offs, seeds)
+    r = e.routes()
+    assert_parity(e.result(), o.result(), "repeats")
+    assert r["multi_finisher"] >= 2 and r["general"] >= 2, r
