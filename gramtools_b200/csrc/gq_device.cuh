@@ -116,18 +116,32 @@ GQ_DEV inline uint32_t pair_reverse32(uint32_t x) {
 }
 
 // Strand cursor over the 2-bit packed read: the bases of the strand (forward, or reverse complement of
-// the stored read; reverse_complement_read, quasimap.cpp:273-298) are consumed right to left, one per
-// search step. `cw` holds the current packed word shifted so that the next base sits in its top two
-// bits — for the reverse strand the word is complemented and pair-reversed once per 16 bases, so
-// peek/advance are identical for both strands (2 instructions per base in the hot step).
+// the stored read; reverse_complement_read, quasimap.cpp:273-298) are consumed right to left. `cw` is a
+// 64-bit shift register holding the next `left` bases, the next one in its top two bits — for the reverse
+// strand each packed word is complemented and pair-reversed as it is loaded, so peek/advance are identical
+// for both strands. The register is topped up with the following word whenever it holds 16 bases or fewer,
+// so (while the strand has that many left) at least 16 bases are always available to a text step.
 struct ReadCursor {
   const uint32_t* w;
   uint32_t L;
   uint32_t rc;
-  uint32_t cw, left, wi;
-  GQ_DEV inline void load_word() {
-    const uint32_t word = GQ_LDG(w + wi);
-    cw = rc ? pair_reverse32(~word) : word;
+  uint64_t cw;
+  uint32_t left, wi;
+  GQ_DEV inline uint32_t word_at(uint32_t i) const {
+    const uint32_t word = GQ_LDG(w + i);
+    return rc ? pair_reverse32(~word) : word;
+  }
+  GQ_DEV inline void refill() {
+    if (left > 16) return;
+    if (rc) {
+      if (wi + 1 >= ((L + 15) >> 4)) return;
+      ++wi;
+    } else {
+      if (wi == 0) return;
+      --wi;
+    }
+    cw |= (uint64_t)word_at(wi) << (32 - 2 * left);  // left <= 16: the new 16 bases follow the valid ones
+    left += 16;
   }
   // position the cursor so that peek() returns the base at logical index pos-1 (pos >= 1)
   GQ_DEV inline void seek(uint32_t pos) {
@@ -135,34 +149,28 @@ struct ReadCursor {
     const uint32_t p = rc ? (L - 1 - i) : i;
     wi = p >> 4;
     const uint32_t q = p & 15u;
-    load_word();
+    const uint32_t word = word_at(wi);
     if (rc) {
-      cw <<= 2 * q;
+      cw = (uint64_t)(word << (2 * q)) << 32;
       left = 16 - q;
     } else {
-      cw <<= 2 * (15 - q);
+      cw = (uint64_t)(word << (2 * (15 - q))) << 32;
       left = q + 1;
     }
+    refill();
   }
-  GQ_DEV inline uint32_t peek() const { return cw >> 30; }
-  GQ_DEV inline void next_word() {
-    left = 16;
-    if (rc) {
-      if (++wi < ((L + 15) >> 4)) load_word();
-    } else if (wi > 0) {
-      --wi;
-      load_word();
-    }
-  }
+  GQ_DEV inline uint32_t peek() const { return (uint32_t)(cw >> 62); }
+  GQ_DEV inline uint32_t top32() const { return (uint32_t)(cw >> 32); }
   GQ_DEV inline void advance() {
     cw <<= 2;
-    if (--left == 0) next_word();
+    --left;
+    refill();
   }
-  // consume r <= left bases at once (text mode compares up to a whole word per step)
+  // consume r <= min(left, 16) bases at once (a text step compares up to a whole word)
   GQ_DEV inline void advance_n(uint32_t r) {
+    cw <<= 2 * r;
     left -= r;
-    if (left == 0) next_word();
-    else cw <<= 2 * r;
+    refill();
   }
 };
 
@@ -508,7 +516,7 @@ GQ_DEV inline void lane_text_step(Lane& ln, const IndexView& v) {
 #else
   const uint32_t codes = v.text_grp[g].codes, info = v.text_grp[g].info;
 #endif
-  const uint32_t run_mis = gq_clz(ln.rd.cw ^ (codes << (2 * sh))) >> 1;  // equal bases from the top (<= 16)
+  const uint32_t run_mis = gq_clz(ln.rd.top32() ^ (codes << (2 * sh))) >> 1;  // equal bases from the top (<= 16)
   const uint32_t run_mark = gq_clz(info << (16 + sh));                   // marker-free positions from the top
   uint32_t limit = j < ln.rd.left ? j : ln.rd.left;
   limit = limit < ln.pos ? limit : ln.pos;
@@ -997,7 +1005,7 @@ GQ_DEV inline void fast_event(FastLane& f, const IndexView& v) {
 // Verify pass: does the candidate agree with the PRG on kVerifyBases further bases (or to the end of the read,
 // or up to something only the full walk can decide)? False candidates — the other occurrences of the
 // seeding k-mer — end here, so the full walk only sees about one candidate per mappable strand.
-constexpr uint32_t kVerifyBases = 12;
+constexpr uint32_t kVerifyBases = 8;
 constexpr uint32_t kVerifyIters = 6;
 GQ_DEV inline bool fast_verified(const FastLane& f, uint32_t pos0) {
   return !fast_running(f) || pos0 - f.ln.pos >= kVerifyBases;
