@@ -127,21 +127,18 @@ struct ReadCursor {
   uint32_t rc;
   uint64_t cw;
   uint32_t left, wi;
-  GQ_DEV inline uint32_t word_at(uint32_t i) const {
-    const uint32_t word = GQ_LDG(w + i);
-    return rc ? pair_reverse32(~word) : word;
+  GQ_DEV inline uint32_t word_at(uint32_t i) const {  // branch-free: both strands run the same instructions
+    const uint32_t x = GQ_LDG(w + i) ^ (0u - rc);
+    const uint32_t y = pair_reverse32(x);
+    return rc ? y : x;
   }
   GQ_DEV inline void refill() {
-    if (left > 16) return;
-    if (rc) {
-      if (wi + 1 >= ((L + 15) >> 4)) return;
-      ++wi;
-    } else {
-      if (wi == 0) return;
-      --wi;
+    const uint32_t last = rc ? ((L + 15) >> 4) - 1u : 0u;
+    if (left <= 16 && wi != last) {
+      wi += rc ? 1u : 0xFFFFFFFFu;
+      cw |= (uint64_t)word_at(wi) << (32 - 2 * left);  // left <= 16: the new 16 bases follow the valid ones
+      left += 16;
     }
-    cw |= (uint64_t)word_at(wi) << (32 - 2 * left);  // left <= 16: the new 16 bases follow the valid ones
-    left += 16;
   }
   // position the cursor so that peek() returns the base at logical index pos-1 (pos >= 1)
   GQ_DEV inline void seek(uint32_t pos) {

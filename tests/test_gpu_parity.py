@@ -190,3 +190,38 @@ def test_repeats(built_lib):
     reads = [s(unit[10:70]), s(unit[30:110]), s(prg[150:230]), s(prg[5:90])] * 50
     bases, offs = encode_reads(reads)
     _check(prg, 6, bases, offs, what="repeats")
+
+
+def test_config2_full_size_properties(built_lib):
+    """BASELINE config 2 at full size (4.4 Mb + 100k SNPs, 1M x 150 bp, k=10): too big for the oracle, so
+    size-independent properties: every error-free read maps exactly one strand (random 4.4 Mb reference: no
+    150-mer repeats), each mapped strand adds one allele_sum count per site it crosses and one per-base count per
+    allele base it covers (SNP alleles are single bases, so the two totals agree), a second pass doubles every
+    counter (idempotent accumulation), the pipelined host path equals the resident path, and a 20k-read prefix
+    is bit-identical to the oracle."""
+    import bench
+    n = bench.N_READS
+    prg, bases, offs, seeds = bench.make_workload(0, n)
+    idx = QuasimapIndex(prg, bench.KMER, device=0)
+    idx.upload(bases, offs, seeds)
+    idx.map_resident()
+    status = idx.batch_status().reshape(-1, 2)
+    assert ((status == 3).sum(axis=1) == 1).all()
+    a1, p1, st1 = idx.coverage()
+    assert st1.all_reads_count == 2 * n and st1.exact_mapped_reads_count == n and st1.skipped_reads_count == 0
+    assert st1.missing_kmer_reads_count + st1.no_extension_reads_count == n
+    tot = int(a1.astype(np.int64).sum())
+    assert tot == int(p1.astype(np.int64).sum()) and tot > 3 * n
+    g1 = idx.grouped()
+    idx.map_resident()
+    a2, p2, st2 = idx.coverage()
+    assert np.array_equal(a2.astype(np.int64), 2 * a1.astype(np.int64)) and np.array_equal(p2.astype(np.int64), 2 * p1.astype(np.int64))
+    assert st2.exact_mapped_reads_count == 2 * n
+    idx.reset_coverage()
+    idx.map_batch(bases, offs, seeds)  # host buffers, sliced + pipelined over two streams
+    a3, p3, st3 = idx.coverage()
+    assert np.array_equal(a3, a1) and np.array_equal(p3, p1) and st3 == st1
+    assert np.array_equal(idx.grouped(), g1)
+    idx.close()
+    m = 20000
+    _check(prg, bench.KMER, bases[:int(offs[m])], offs[:m + 1], what="config2-prefix", threads=os.cpu_count())
