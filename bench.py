@@ -28,7 +28,7 @@ GEN_SEED = 0x6772616D + 2
 MAP_SEED = 42
 # ncu --set full, config 2, 1M reads, dram__bytes_read.sum + dram__bytes_write.sum summed over seed_kernel,
 # verify_kernel, text_kernel and search_kernel (profiles/r01_v9_kernels_summary.txt)
-SEARCH_PHASE_DRAM_BYTES = None
+SEARCH_PHASE_DRAM_BYTES = 306805760 + 159697152 + 214277120 + 17659648 + 341317888 + 98457088 + 66048
 
 
 def env_int(name, default):

@@ -84,7 +84,8 @@ struct gq_index {
   DevBuf<uint16_t> fetch_dev;
   std::vector<cudaEvent_t> chunk_events;
   uint32_t chunk_reads = 1u << 17, tail_chunk_reads = 1u << 15;
-  uint32_t resident_slices = 1;  // gq_map_resident: slices run on two streams  // slice size of the H2D / compute pipeline in gq_map_batch
+  uint32_t resident_slices = 1;  // gq_map_resident: slices run on two streams
+  bool overlap_classify = true;  // single-slice runs: classify_kernel beside coverage_kernel on a second stream  // slice size of the H2D / compute pipeline in gq_map_batch
   // options
   uint32_t arena_words = 512;
   uint32_t n_threads = 148 * 1280;      // search kernel lanes (5 CTAs of 256 per SM)
@@ -368,9 +369,24 @@ static void do_map(gq_index* ix, const uint8_t* h_bases = nullptr, const uint64_
       gq::launch_search(ix->dv, bc, oc, arena, ix->arena_words, threads, nullptr, 0, ix->super_in_smem,
                         ix->rf_thresh, ix->ev_thresh, cs, ix->leave_opt, ix->wait_opt);
     if (chunks.size() == 1) CUDA_OK(cudaEventRecord(ix->ev[1], st));
-    gq::launch_classify(ix->dv, bc, oc, nullptr, 0, cs);
-    gq::launch_coverage(ix->dv, bc, oc, c, arena, ix->arena_words, threads2, nullptr, 0,
-                        ix->cov_overflow_list.p, ix->small.p + 2, cs);
+    if (!two_streams && ix->overlap_classify) {
+      // classify (issue-bound) and coverage (latency-bound) are independent: run them side by side
+      if (!ix->aux_stream) {
+        CUDA_OK(cudaStreamCreateWithFlags(&ix->aux_stream, cudaStreamNonBlocking));
+        CUDA_OK(cudaEventCreateWithFlags(&ix->aux_event, cudaEventDisableTiming));
+      }
+      CUDA_OK(cudaEventRecord(ix->aux_event, cs));
+      CUDA_OK(cudaStreamWaitEvent(ix->aux_stream, ix->aux_event, 0));
+      gq::launch_classify(ix->dv, bc, oc, nullptr, 0, ix->aux_stream);
+      gq::launch_coverage(ix->dv, bc, oc, c, arena, ix->arena_words, threads2, nullptr, 0,
+                          ix->cov_overflow_list.p, ix->small.p + 2, cs);
+      CUDA_OK(cudaEventRecord(ix->aux_event, ix->aux_stream));
+      CUDA_OK(cudaStreamWaitEvent(cs, ix->aux_event, 0));
+    } else {
+      gq::launch_classify(ix->dv, bc, oc, nullptr, 0, cs);
+      gq::launch_coverage(ix->dv, bc, oc, c, arena, ix->arena_words, threads2, nullptr, 0,
+                          ix->cov_overflow_list.p, ix->small.p + 2, cs);
+    }
     launches += 3;
   }
   if (two_streams) {
@@ -994,6 +1010,8 @@ int gq_set_option(gq_index* ix, const char* name, int64_t value) {
   } else if (n == "pool_words_per_read") {
     ix->pool_words_per_read = (uint32_t)std::max<int64_t>(value, 1);
     ix->pool.release();
+  } else if (n == "overlap_classify") {
+    ix->overlap_classify = value != 0;
   } else if (n == "resident_slices") {
     ix->resident_slices = (uint32_t)std::max<int64_t>(value, 1);
   } else if (n == "tail_chunk_reads") {
