@@ -185,29 +185,38 @@ __global__ void __launch_bounds__(256) verify_kernel(IndexView v, BatchView b, S
   const uint32_t n = min(*pre.n_surv, pre.cap);
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t full = 0xFFFFFFFFu;
+  // survivors of a round are written one round later, so the list allocation (one atomic per warp) is in
+  // flight during the next round instead of stalling this one
+  uint4 pend_rec = make_uint4(0, 0, 0, 0);
+  uint32_t pend_base = 0, pend_rank = 0, pend_mask = 0;
   for (uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; i0 < n; i0 += gridDim.x * blockDim.x) {
     const uint32_t i = i0 + lane;
     FastLane f;
     f.result = FAST_DEAD;
     f.ln.state = LS_IDLE;
     f.ln.pos = 0;
-    if (i < n && __ldg(pre.rec + 4 * (size_t)i) != kNoAllele) fast_begin<false>(f, v, b, pre, i);
+    uint4 rec = make_uint4(kNoAllele, 0, 0, 0);
+    if (i < n) rec = __ldg(reinterpret_cast<const uint4*>(pre.rec) + i);
+    if (rec.x != kNoAllele) fast_begin<false>(f, v, b, pre, i);
     const uint32_t pos0 = f.ln.pos;
     for (uint32_t it = 0; it < kVerifyIters && __any_sync(full, !fast_verified(f, pos0)); ++it) {
       if (!fast_verified(f, pos0) && f.ln.state == LS_TEXT) lane_text_step(f.ln, v);
       if (!fast_verified(f, pos0) && f.ln.state == LS_EV_TSCAN) fast_event<false>(f, v);
     }
-    const bool alive = i < n && fast_alive(f);
+    const bool alive = rec.x != kNoAllele && fast_alive(f);
     const uint32_t mm = __ballot_sync(full, alive);
-    if (mm) {
-      uint32_t base = 0;
-      if (lane == 0) base = atomicAdd(n_verified, (uint32_t)__popc(mm));
-      base = __shfl_sync(full, base, 0);
-      if (alive) {
-        const uint32_t dst = base + __popc(mm & ((1u << lane) - 1u));
-        reinterpret_cast<uint4*>(surv_rec)[dst] = __ldg(reinterpret_cast<const uint4*>(pre.rec) + i);
-      }
+    if (pend_mask) {  // flush the previous round
+      const uint32_t base = __shfl_sync(full, pend_base, 0);
+      if ((pend_mask >> lane) & 1u) reinterpret_cast<uint4*>(surv_rec)[base + pend_rank] = pend_rec;
     }
+    if (mm && lane == 0) pend_base = atomicAdd(n_verified, (uint32_t)__popc(mm));
+    pend_mask = mm;
+    pend_rank = __popc(mm & ((1u << lane) - 1u));
+    pend_rec = rec;
+  }
+  if (pend_mask) {
+    const uint32_t base = __shfl_sync(full, pend_base, 0);
+    if ((pend_mask >> lane) & 1u) reinterpret_cast<uint4*>(surv_rec)[base + pend_rank] = pend_rec;
   }
 }
 
@@ -230,13 +239,13 @@ __global__ void __launch_bounds__(256) text_kernel(IndexView v, BatchView b, Sea
       if (fast_running(f) && f.ln.state == LS_TEXT) lane_text_step(f.ln, v);
       if (fast_running(f) && f.ln.state == LS_EV_TSCAN) fast_event<true>(f, v);
     }
-    uint32_t words = i < n ? fast_outcome(f, v) : 0;
+    const uint32_t words = i < n ? fast_outcome(f, v) : 0;
     const uint32_t strand = f.ln.strand;
-    if (f.result == FAST_BAIL) send_to_general(pre, strand);
-    // a finished candidate claims its strand; a second one makes the strand the general kernel's
-    bool emit = f.result == FAST_MAPPED && fast_claim(pre, strand);
-    if (!emit) words = 0;
-    // pool space for the finished states of the round: warp scan + one atomic
+    const bool finished = f.result == FAST_MAPPED;
+    // The three allocations of the round are issued together, for every finished candidate: its strand claim
+    // (a second finished candidate makes the strand the general kernel's), pool space (warp scan + one
+    // atomic) and mapped-list slots (one atomic). A candidate that loses its claim leaves its pool words
+    // unused and kNoAllele in its list slot (coverage_kernel skips it).
     uint32_t incl = words;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -244,27 +253,31 @@ __global__ void __launch_bounds__(256) text_kernel(IndexView v, BatchView b, Sea
       if (lane >= (uint32_t)d) incl += t;
     }
     const uint32_t total = __shfl_sync(full, incl, 31);
-    uint32_t base = 0;
+    const uint32_t mm = __ballot_sync(full, finished);
+    uint32_t base = 0, mbase = 0, claim = 0;
     if (total && lane == 31) base = atomicAdd(o.pool_used, total);
+    if (mm && lane == 0) mbase = atomicAdd(o.n_mapped, (uint32_t)__popc(mm));
+    if (finished) claim = atomicAdd(pre.surv_cnt + strand, 1u);
+    if (f.result == FAST_BAIL) send_to_general(pre, strand);
     base = __shfl_sync(full, base, 31);
-    if (emit) {
+    mbase = __shfl_sync(full, mbase, 0);
+    if (finished) {
+      uint32_t listed = kNoAllele;
       const uint32_t off = base + incl - words;
-      if (off + words > o.pool_cap) {  // final-state pool full: re-run after the host has grown it
+      if (claim & kSurvGeneral) {
+        // already the general kernel's
+      } else if (claim & 0xFFFFu) {
+        send_to_general(pre, strand);  // several finished candidates (a repeat)
+      } else if (off + words > o.pool_cap) {  // final-state pool full: re-run after the host has grown it
         o.status[strand] = ST_OVERFLOW;
         o.overflow_list[atomicAdd(o.n_overflow, 1u)] = strand;
-        emit = false;
       } else {
         fast_emit(f, v, o, off);
         o.status[strand] = ST_MAPPED;
         atomicOr(pre.surv_cnt + strand, kSurvListed);
+        listed = strand;
       }
-    }
-    const uint32_t mm = __ballot_sync(full, emit);
-    if (mm) {
-      uint32_t mbase = 0;
-      if (lane == 0) mbase = atomicAdd(o.n_mapped, (uint32_t)__popc(mm));
-      mbase = __shfl_sync(full, mbase, 0);
-      if (emit) o.mapped_list[mbase + __popc(mm & ((1u << lane) - 1u))] = strand;
+      o.mapped_list[mbase + __popc(mm & ((1u << lane) - 1u))] = listed;
     }
   }
 }
@@ -486,7 +499,7 @@ __global__ void __launch_bounds__(256)
   const uint32_t n = list ? n_list : *o.n_mapped;
   for (uint32_t i = tid; i < n; i += nthreads) {
     uint32_t strand = work_list[i];
-    if (o.status[strand] != ST_MAPPED) continue;
+    if (strand == kNoAllele || o.status[strand] != ST_MAPPED) continue;  // kNoAllele: slot of a lost claim
     if (!record_strand(v, b, o, c, strand, my_arena, arena_words)) overflow_list[atomicAdd(n_overflow, 1u)] = strand;
   }
 }
