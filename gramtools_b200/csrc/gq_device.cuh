@@ -732,7 +732,7 @@ GQ_DEV inline void lane_event(Lane& ln, const IndexView& v, const SearchOut& o) 
 constexpr uint32_t kPreSteps = 6;    // rank steps at most, while the interval is wide
 constexpr uint32_t kSplitWidth = 4;  // stop narrowing at this many suffixes
 constexpr uint32_t kMaxSplit = 32;   // wider than this after narrowing: general kernel
-constexpr uint32_t kMaxSeedStates = 16;
+constexpr uint32_t kMaxSeedStates = 32;  // = kMaxPlan
 
 // part 1: k-mer lookup. Returns the number of seed states (0: the strand is already classified).
 GQ_DEV inline uint32_t preseed_lookup(const IndexView& v, const BatchView& b, const SearchOut& o, uint32_t strand,
@@ -777,19 +777,24 @@ GQ_DEV inline void send_to_general(const SeedOut& pre, uint32_t strand) {
   if (!(old & kSurvGeneral)) pre.gen_list[gq_atomic_add(pre.n_gen, 1u)] = strand;
 }
 
-// part 2: the candidates of one strand. `lo/w/w0[t]`: first SA index, number of suffixes and pos | kind << 28
-// of seed state t after narrowing (w = 0: dead). Returns the number of candidates, or kNoAllele when the
-// strand needs the general kernel.
+// part 2: the candidates of one strand, as a plan of entries {first SA index, number of suffixes,
+// pos | kind << 28, seed state}. A seed state narrower than kSplitWidth suffixes is one entry as it stands. A
+// wider one is narrowed first, the way the reference advances it (quasimap.cpp:258-268): every marker-preceded
+// suffix of the interval becomes an entry of its own (its walk starts with that jump — the state
+// left_markers_search would spawn, vBWT_jump.cpp:94-117), then the interval consumes the next read base with
+// two rank queries (BWT_search.cpp:45-76), until fewer than kSplitWidth suffixes are left. Returns the number
+// of candidates, or kNoAllele when the strand needs the general kernel.
+constexpr uint32_t kMaxPlan = 32;
 struct SeedPlan {
-  uint32_t sb, ns;
-  uint32_t lo[kMaxSeedStates], w[kMaxSeedStates], w0[kMaxSeedStates];
+  uint32_t sb, n;
+  uint32_t lo[kMaxPlan], w[kMaxPlan], w0[kMaxPlan], t[kMaxPlan];
 };
 
 template <class SuperPtr>
 GQ_DEV inline uint32_t seed_plan(const IndexView& v, SuperPtr super_c, const BatchView& b, uint32_t strand, uint32_t sb,
                                  uint32_t ns, SeedPlan& plan) {
   plan.sb = sb;
-  plan.ns = ns;
+  plan.n = 0;
   if (ns > kMaxSeedStates) {
     GQ_COUNT(9);
     return kNoAllele;
@@ -805,7 +810,7 @@ GQ_DEV inline uint32_t seed_plan(const IndexView& v, SuperPtr super_c, const Bat
   for (uint32_t t = 0; t < ns; ++t) {
     const KmerState ks = v.kmer_states[sb + t];
     uint32_t lo = ks.lo, hi = ks.hi, w0 = pos0 | (K_SCAN << 28);
-    if (hi - lo >= kSplitWidth) {  // narrow it with rank steps first (BWT_search.cpp:45-76)
+    if (hi - lo >= kSplitWidth) {
       Lane ln;
       ln.rd = ReadCursor{b.packed + b.word_off[r], L, strand & 1u, 0, 0, 0};
       ln.pos = pos0;
@@ -815,21 +820,54 @@ GQ_DEV inline uint32_t seed_plan(const IndexView& v, SuperPtr super_c, const Bat
       ln.kind = K_SCAN;
       ln.rd.seek(ln.pos);
       ln.state = LS_RUNW;
-      for (uint32_t s = 0; s < kPreSteps && ln.state == LS_RUNW && ln.hi - ln.lo >= kSplitWidth && ln.pos > 1; ++s)
+      for (uint32_t s = 0; s < kPreSteps && ln.state == LS_RUNW && ln.hi - ln.lo >= kSplitWidth && ln.pos > 1; ++s) {
+        if (ln.kind == K_SCAN) {  // marker-preceded suffixes leave the interval as candidates of their own
+          for (uint32_t blk = ln.lo >> kBlkShift; blk <= (ln.hi >> kBlkShift); ++blk) {
+            uint64_t m = marker_bits_in(load_blk(v.rank_blk + blk), blk << kBlkShift, ln.lo, ln.hi);
+            while (m) {
+#if defined(__CUDA_ARCH__)
+              const uint32_t bit = __ffsll((long long)m) - 1;
+#else
+              const uint32_t bit = (uint32_t)__builtin_ctzll(m);
+#endif
+              m &= m - 1;
+              if (plan.n == kMaxPlan) {
+                GQ_COUNT(1);
+                return kNoAllele;
+              }
+              plan.lo[plan.n] = (blk << kBlkShift) + bit;
+              plan.w[plan.n] = 1;
+              plan.w0[plan.n] = ln.pos | (K_SCAN << 28);
+              plan.t[plan.n] = t;
+              ++plan.n;
+              ++total;
+            }
+          }
+          ln.kind = K_READY;  // scanned
+        }
         lane_step_wide(ln, v, super_c);
-      // LS_RUN / LS_RUNW / LS_EV_SCAN (a marker inside the interval: every suffix checks its own symbol)
-      if (ln.state == LS_EV_WIDE || (ln.state != LS_EV_POP && ln.hi - ln.lo >= kMaxSplit)) {
+      }
+      if (ln.state != LS_EV_POP && (ln.state == LS_EV_WIDE || ln.hi - ln.lo >= kMaxSplit)) {
         GQ_COUNT(1);
         return kNoAllele;
       }
+      // LS_RUN / LS_RUNW / LS_EV_SCAN (a marker inside the narrow interval: every suffix checks its own symbol)
       lo = ln.lo;
       hi = ln.state == LS_EV_POP ? lo - 1 : ln.hi;
       w0 = ln.pos | (ln.kind << 28);
     }
-    plan.lo[t] = lo;
-    plan.w[t] = hi + 1 - lo;
-    plan.w0[t] = w0;
-    total += hi + 1 - lo;
+    if (hi + 1 != lo) {
+      if (plan.n == kMaxPlan) {
+        GQ_COUNT(1);
+        return kNoAllele;
+      }
+      plan.lo[plan.n] = lo;
+      plan.w[plan.n] = hi + 1 - lo;
+      plan.w0[plan.n] = w0;
+      plan.t[plan.n] = t;
+      ++plan.n;
+      total += hi + 1 - lo;
+    }
     GQ_COUNT(2);
   }
   return total;
@@ -839,12 +877,12 @@ GQ_DEV inline uint32_t seed_plan(const IndexView& v, SuperPtr super_c, const Bat
 GQ_DEV inline void seed_write(const IndexView& v, const SeedPlan& plan, const SeedOut& pre, uint32_t strand,
                               uint32_t base) {
   uint32_t* d = pre.rec + 4 * (size_t)base;
-  for (uint32_t t = 0; t < plan.ns; ++t)
-    for (uint32_t i = 0; i < plan.w[t]; ++i, d += 4) {
+  for (uint32_t e = 0; e < plan.n; ++e)
+    for (uint32_t i = 0; i < plan.w[e]; ++i, d += 4) {
       d[0] = strand;
-      d[1] = plan.sb + t;
-      d[2] = GQ_LDG(v.sa + plan.lo[t] + i);
-      d[3] = plan.w0[t];
+      d[1] = plan.sb + plan.t[e];
+      d[2] = GQ_LDG(v.sa + plan.lo[e] + i);
+      d[3] = plan.w0[e];
     }
 }
 

@@ -225,3 +225,10 @@ def test_config2_full_size_properties(built_lib):
     idx.close()
     m = 20000
     _check(prg, bench.KMER, bases[:int(offs[m])], offs[:m + 1], what="config2-prefix", threads=os.cpu_count())
+
+
+def test_frequent_kmers_wide_seed_intervals(built_lib):
+    """config 4/5 regime in miniature: ~200 occurrences per k-mer, wide seed intervals narrowed in the seed pass."""
+    prg = synth.make_snp_prg(200000, 400, 7)[0]
+    bases, offs = _reads_for(prg, 6000, 60, 5, garbage=0.02, n_frac=0.0)
+    _check(prg, 5, bases, offs, what="wide-seeds", threads=os.cpu_count())

@@ -210,3 +210,21 @@ def test_repeats_take_the_general_route():
     r = e.routes()
     assert_parity(e.result(), o.result(), "repeats")
     assert r["multi_finisher"] >= 2 and r["general"] >= 2, r
+
+
+@pytest.mark.parametrize("shape", [(200000, 400, 5, 60), (400000, 4000, 6, 70)])
+def test_frequent_kmers_wide_seed_intervals(shape):
+    """Large-genome regime in miniature (config 4/5: tens of occurrences per k-mer): the seeding k-mer's main state
+    is an interval of ~100-200 suffixes that the seed pass narrows with rank steps, peeling off marker-preceded
+    suffixes as candidates of their own."""
+    n, n_sites, k, L = shape
+    prg = synth.make_snp_prg(n, n_sites, 7)[0]
+    bases, offs = _reads_for(prg, 1500, L, 5, garbage=0.02, n_frac=0.0)
+    seeds = master_seeds(42, offs.size - 1)
+    o, e = Oracle(prg, k), Emu(prg, k)
+    o.map(bases, offs, seeds, threads=os.cpu_count())
+    e.routes(reset=True)
+    e.map(bases, offs, seeds)
+    r = e.routes()
+    assert_parity(e.result(), o.result(), f"wide{shape}")
+    assert r["fast_finished"] > 2 * r["general"] and r["too_wide"] == 0, r
