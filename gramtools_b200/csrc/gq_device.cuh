@@ -732,7 +732,7 @@ GQ_DEV inline void lane_event(Lane& ln, const IndexView& v, const SearchOut& o) 
 constexpr uint32_t kPreSteps = 6;    // rank steps at most, while the interval is wide
 constexpr uint32_t kSplitWidth = 4;  // stop narrowing at this many suffixes
 constexpr uint32_t kMaxSplit = 32;   // wider than this after narrowing: general kernel
-constexpr uint32_t kMaxSeedStates = 32;  // = kMaxPlan
+constexpr uint32_t kMaxSeedStates = 32;
 
 // part 1: k-mer lookup. Returns the number of seed states (0: the strand is already classified).
 GQ_DEV inline uint32_t preseed_lookup(const IndexView& v, const BatchView& b, const SearchOut& o, uint32_t strand,
@@ -784,7 +784,7 @@ GQ_DEV inline void send_to_general(const SeedOut& pre, uint32_t strand) {
 // left_markers_search would spawn, vBWT_jump.cpp:94-117), then the interval consumes the next read base with
 // two rank queries (BWT_search.cpp:45-76), until fewer than kSplitWidth suffixes are left. Returns the number
 // of candidates, or kNoAllele when the strand needs the general kernel.
-constexpr uint32_t kMaxPlan = 32;
+constexpr uint32_t kMaxPlan = 64;
 struct SeedPlan {
   uint32_t sb, n;
   uint32_t lo[kMaxPlan], w[kMaxPlan], w0[kMaxPlan], t[kMaxPlan];
