@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 #include <map>
 #include <stdexcept>
@@ -83,7 +84,7 @@ struct gq_index {
   size_t fetch_host_bytes = 0;
   DevBuf<uint16_t> fetch_dev;
   std::vector<cudaEvent_t> chunk_events;
-  uint32_t chunk_reads = 1u << 17, tail_chunk_reads = 1u << 15;
+  uint32_t chunk_reads = 1u << 18, tail_chunk_reads = 1u << 15;
   uint32_t resident_slices = 1;  // gq_map_resident: slices run on two streams
   bool overlap_classify = true;  // single-slice runs: classify_kernel beside coverage_kernel on a second stream  // slice size of the H2D / compute pipeline in gq_map_batch
   // options
@@ -265,6 +266,7 @@ static void do_map(gq_index* ix, const uint8_t* h_bases = nullptr, const uint64_
                    const uint32_t* h_seeds = nullptr) {
   CUDA_OK(cudaSetDevice(ix->device));
   const bool pipelined = h_bases != nullptr || h_off != nullptr;
+  const auto t_host0 = std::chrono::steady_clock::now();  // info[7]: host time spent enqueueing the call
   const uint32_t n = ix->n_reads;
   for (int i = 0; i < 8; ++i)
     if (i != 5) ix->info[i] = 0;
@@ -394,6 +396,7 @@ static void do_map(gq_index* ix, const uint8_t* h_bases = nullptr, const uint64_
     CUDA_OK(cudaStreamWaitEvent(st, ix->aux_event, 0));
   }
   CUDA_OK(cudaEventRecord(ix->ev[2], st));
+  ix->info[7] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
   uint32_t small[4];
   CUDA_OK(cudaMemcpyAsync(small, ix->small.p, 16, cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaStreamSynchronize(st));

@@ -175,7 +175,7 @@ class QuasimapIndex:
         a = (C.c_double * 8)()
         self._check(self._lib.gq_last_run_info(self._h, a))
         return dict(launches=int(a[0]), rerun_strands=int(a[1]), search_ms=a[2], coverage_ms=a[3],
-                    pool_words=int(a[4]), h2d_bytes=int(a[5]), kernels_ms=a[6])
+                    pool_words=int(a[4]), h2d_bytes=int(a[5]), kernels_ms=a[6], enqueue_ms=a[7])
 
     # -- results -------------------------------------------------------------------------------
     def batch_status(self):

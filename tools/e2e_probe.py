@@ -33,4 +33,6 @@ for spec in os.environ.get("GQ_CHUNKS", "131072:131072,262144:32768,262144:65536
     for _ in range(10):
         idx.coverage()
     dc = (time.perf_counter() - t) / 10
-    print(f"chunk_reads={chunk} tail={tail}: map_batch {dt*1e3:.2f} ms ({1e6/dt/1e6:.0f} M reads/s); coverage fetch {dc*1e3:.2f} ms")
+    info = idx.run_info()
+    print(f"chunk_reads={chunk} tail={tail}: map_batch {dt*1e3:.2f} ms ({1e6/dt/1e6:.0f} M reads/s); coverage fetch {dc*1e3:.2f} ms; "
+          f"host enqueue {info['enqueue_ms']:.2f} ms, {info['launches']} launches")
