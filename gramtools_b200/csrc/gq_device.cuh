@@ -255,9 +255,11 @@ struct EmitStage {
 // Lane state machine of the search kernel. One lane maps one strand at a time; the warp runs ONE flat
 // loop in which every lane executes the same unit operation per iteration, so lanes re-converge every
 // iteration instead of drifting apart inside nested per-read loops:
-//   lane_refill : idle lane takes the next strand, seeds its stack from the k-mer index
-//   lane_step   : the hot path — one read base: marker test + backward extension, registers only
-//   lane_event  : everything rare — marker scan / jumps, emitting finished states, pops, strand end
+//   lane_refill    : idle lane takes the next strand, seeds its stack from the k-mer index
+//   lane_to_text / lane_text_step : width-1 interval — its text position, then up to 16 bases per step in the
+//                    packed PRG text (see "Text mode" below)
+//   lane_step_wide : wider interval — one read base: marker test + two rank queries
+//   lane_event     : everything else — marker scan / jumps, emitting finished states, pops, strand end
 // Order of work differs from quasimap_read (quasimap.cpp:159-194) without changing results: the search
 // runs first and the k-mer filter (all_read_kmers_occur_in_index, :212-225) is evaluated afterwards only
 // for strands that produced no state (classify_strand) — a strand that maps end to end necessarily has
@@ -404,39 +406,6 @@ GQ_DEV inline void lane_refill(Lane& ln, const IndexView& v, const BatchView& b,
     return;
   }
   lane_load_top(ln);
-}
-
-// The hot path: one base for a lane in LS_RUN, i.e. a width-1 SA interval (the steady state after
-// seeding). Everything lives in registers; memory traffic is ONE 32 B rank-block sector; the step only
-// needs BWT[lo]. Any non-trivial outcome parks the lane in an event state.
-// `super_c` = per-superblock counts with C[c] folded in, so lo' = super_c[c] + blk.cnt[c] + popc(...).
-template <class SuperPtr>
-GQ_DEV inline void lane_step(Lane& ln, const IndexView& v, SuperPtr super_c) {
-  const uint32_t lo = ln.lo;
-  const uint32_t b0 = lo >> kBlkShift;
-  const RankBlk B0 = load_blk(v.rank_blk + b0);
-  const uint32_t c = ln.rd.peek();
-  const uint64_t x0 = (c & 1u) ? 0ull : ~0ull, x1 = (c & 2u) ? 0ull : ~0ull;
-  const uint64_t bit = 1ull << (lo & 63u);
-  if (B0.p2 & bit) {  // not a nucleotide: marker -> jump (unless already scanned), sentinel -> dead
-    if ((B0.p0 & bit) && ln.kind == K_SCAN) {
-      // start the marker-rank load now: it completes while the lane waits for its event batch
-      ln.mr = GQ_LDG(v.mrank_blk + b0) + (uint32_t)popc64(B0.p2 & B0.p0 & (bit - 1));
-      ln.state = LS_EV_SCAN;
-    } else
-      ln.state = LS_EV_POP;
-    return;
-  }
-  const uint64_t m = ~B0.p2 & (B0.p0 ^ x0) & (B0.p1 ^ x1);
-  if (!(m & bit)) {
-    ln.state = LS_EV_POP;
-    return;
-  }
-  ln.lo = ln.hi = super_c[4 * (b0 >> (kSuperShift - kBlkShift)) + c] + ((uint32_t)(B0.cnt >> (16 * c)) & 0xFFFFu) +
-                  (uint32_t)popc64(m & (bit - 1));
-  ln.kind = K_SCAN;
-  ln.rd.advance();
-  if (--ln.pos == 0) ln.state = LS_EV_TOP;  // registers hold the finished state; lane_event_top stores it
 }
 
 // One base for a lane in LS_RUNW: SA interval wider than one suffix (the first bases after seeding, and

@@ -1,16 +1,23 @@
-// kernels.cu — hand-written sm_100a kernels for the quasimap hot path.
+// kernels.cu — hand-written sm_100a kernels for the quasimap hot path (per-strand logic in gq_device.cuh).
 //
 //   pack_kernel      uint8 bases -> 2-bit packed words (16 bases / word)
-//   search_kernel    k-mer filter + k-mer seeding + vBWT backward search with marker jumps
-//                    (reference: libgramtools/src/genotype/quasimap/quasimap.cpp:159-256,
-//                     search/BWT_search.cpp, search/vBWT_jump.cpp, search/encapsulated_search.cpp)
+//   seed_kernel      seeding k-mer -> seed SearchStates -> candidates: one width-1 state per suffix
+//                    (reference: quasimap.cpp:159-194,235-241; BWT_search.cpp for narrowing wide seeds)
+//   verify_kernel    drops the candidates that disagree with the PRG within a few bases
+//   text_kernel      walks the surviving candidates through the packed PRG text, pre-resolved jumps at
+//                    variant markers, writes the strand's final SearchState
+//                    (reference: quasimap.cpp:227-268, vBWT_jump.cpp, encapsulated_search.cpp)
+//   search_kernel    general lane state machine for everything the text route does not take
+//                    (interval states, marker scans, LIFO jump worklist; same reference functions)
+//   classify_kernel  k-mer filter for strands that found nothing (quasimap.cpp:212-225)
 //   coverage_kernel  equivalence classes, seeded selection, allele-sum / grouped / per-base recording
 //                    (reference: coverage/coverage_common.cpp, allele_sum.cpp,
 //                     grouped_allele_counts.cpp, allele_base.cpp)
 //   stats_kernel     the five QuasimapReadsStats counters (quasimap.hpp:17-24)
+//   fetch_kernel     uint16 wrap / saturate view of the accumulators
 //
-// Integer / bit arithmetic only; the bound is random 32 B sector traffic to the rank blocks (HBM, or
-// L2 when the index fits), so there is no tensor-core work here. Rank superblock counters are staged
+// Integer / bit arithmetic only; the kernels are bound by the latency of dependent 32 B sector loads (L2 when
+// the index fits, HBM beyond), so there is no tensor-core work here. Rank superblock counters are staged
 // into shared memory with one TMA bulk copy per CTA.
 #include "kernels.cuh"
 #include "gq_device.cuh"
@@ -87,7 +94,7 @@ constexpr int kMaxSuperSmem = 2048;  // superblocks (x16 B = 32 KB) staged in sh
 //   * one class of rare-path transitions    when >= ev_thresh lanes wait in that class
 //     (scan/jump, pop, top: lanes of one class run the same code together)
 //   * everything pending                    when no lane can take a hot step, or too many lanes wait
-//   * otherwise the hot step (x kHotUnroll) for every lane in LS_RUN
+//   * otherwise the text step (x kHotUnroll) for every lane holding a width-1 state
 // Batching the rare paths keeps the hot step near full lane occupancy (v1 ran 3.5 lanes/instruction).
 #ifndef GQ_HOT_UNROLL
 #define GQ_HOT_UNROLL 2
