@@ -701,7 +701,6 @@ GQ_DEV inline void lane_event(Lane& ln, const IndexView& v, const SearchOut& o) 
 constexpr uint32_t kPreSteps = 6;    // rank steps at most, while the interval is wide
 constexpr uint32_t kSplitWidth = 4;  // stop narrowing at this many suffixes
 constexpr uint32_t kMaxSplit = 32;   // wider than this after narrowing: general kernel
-constexpr uint32_t kMaxSeedStates = 32;
 
 // part 1: k-mer lookup. Returns the number of seed states (0: the strand is already classified).
 GQ_DEV inline uint32_t preseed_lookup(const IndexView& v, const BatchView& b, const SearchOut& o, uint32_t strand,
@@ -746,110 +745,94 @@ GQ_DEV inline void send_to_general(const SeedOut& pre, uint32_t strand) {
   if (!(old & kSurvGeneral)) pre.gen_list[gq_atomic_add(pre.n_gen, 1u)] = strand;
 }
 
-// part 2: the candidates of one strand, as a plan of entries {first SA index, number of suffixes,
-// pos | kind << 28, seed state}. A seed state narrower than kSplitWidth suffixes is one entry as it stands. A
-// wider one is narrowed first, the way the reference advances it (quasimap.cpp:258-268): every marker-preceded
-// suffix of the interval becomes an entry of its own (its walk starts with that jump — the state
-// left_markers_search would spawn, vBWT_jump.cpp:94-117), then the interval consumes the next read base with
-// two rank queries (BWT_search.cpp:45-76), until fewer than kSplitWidth suffixes are left. Returns the number
-// of candidates, or kNoAllele when the strand needs the general kernel.
-constexpr uint32_t kMaxPlan = 64;
+// part 2: the candidates of ONE seed state, as a plan of entries {first SA index, number of suffixes,
+// pos | kind << 28}. A seed state narrower than kSplitWidth suffixes is one entry as it stands. A wider one is
+// narrowed first, the way the reference advances it (quasimap.cpp:258-268): every marker-preceded suffix of
+// the interval becomes an entry of its own (its walk starts with that jump — the state left_markers_search
+// would spawn, vBWT_jump.cpp:94-117), then the interval consumes the next read base with two rank queries
+// (BWT_search.cpp:45-76), until fewer than kSplitWidth suffixes are left. Returns the number of candidates,
+// or kNoAllele when the strand needs the general kernel.
+constexpr uint32_t kMaxPlan = 24;
 struct SeedPlan {
-  uint32_t sb, n;
-  uint32_t lo[kMaxPlan], w[kMaxPlan], w0[kMaxPlan], t[kMaxPlan];
+  uint32_t n;
+  uint32_t lo[kMaxPlan], w[kMaxPlan], w0[kMaxPlan];
 };
 
 template <class SuperPtr>
-GQ_DEV inline uint32_t seed_plan(const IndexView& v, SuperPtr super_c, const BatchView& b, uint32_t strand, uint32_t sb,
-                                 uint32_t ns, SeedPlan& plan) {
-  plan.sb = sb;
+GQ_DEV inline uint32_t seed_state_plan(const IndexView& v, SuperPtr super_c, const uint32_t* w, uint32_t L, uint32_t rc,
+                                       uint32_t j, SeedPlan& plan) {
   plan.n = 0;
-  if (ns > kMaxSeedStates) {
-    GQ_COUNT(9);
-    return kNoAllele;
-  }
-  const uint32_t r = strand >> 1;
-  const uint32_t L = b.len[r];
   const uint32_t pos0 = L - v.k;
   if (pos0 == 0) {  // the seed states are the final states
     GQ_COUNT(0);
     return kNoAllele;
   }
-  uint32_t total = 0;
-  for (uint32_t t = 0; t < ns; ++t) {
-    const KmerState ks = v.kmer_states[sb + t];
-    uint32_t lo = ks.lo, hi = ks.hi, w0 = pos0 | (K_SCAN << 28);
-    if (hi - lo >= kSplitWidth) {
-      Lane ln;
-      ln.rd = ReadCursor{b.packed + b.word_off[r], L, strand & 1u, 0, 0, 0};
-      ln.pos = pos0;
-      ln.lo = lo;
-      ln.hi = hi;
-      ln.p = ln.mr = 0;
-      ln.kind = K_SCAN;
-      ln.rd.seek(ln.pos);
-      ln.state = LS_RUNW;
-      for (uint32_t s = 0; s < kPreSteps && ln.state == LS_RUNW && ln.hi - ln.lo >= kSplitWidth && ln.pos > 1; ++s) {
-        if (ln.kind == K_SCAN) {  // marker-preceded suffixes leave the interval as candidates of their own
-          for (uint32_t blk = ln.lo >> kBlkShift; blk <= (ln.hi >> kBlkShift); ++blk) {
-            uint64_t m = marker_bits_in(load_blk(v.rank_blk + blk), blk << kBlkShift, ln.lo, ln.hi);
-            while (m) {
+  const KmerState ks = v.kmer_states[j];
+  uint32_t lo = ks.lo, hi = ks.hi, w0 = pos0 | (K_SCAN << 28), total = 0;
+  if (hi - lo >= kSplitWidth) {
+    Lane ln;
+    ln.rd = ReadCursor{w, L, rc, 0, 0, 0};
+    ln.pos = pos0;
+    ln.lo = lo;
+    ln.hi = hi;
+    ln.p = ln.mr = 0;
+    ln.kind = K_SCAN;
+    ln.rd.seek(ln.pos);
+    ln.state = LS_RUNW;
+    for (uint32_t s = 0; s < kPreSteps && ln.state == LS_RUNW && ln.hi - ln.lo >= kSplitWidth && ln.pos > 1; ++s) {
+      if (ln.kind == K_SCAN) {  // marker-preceded suffixes leave the interval as candidates of their own
+        for (uint32_t blk = ln.lo >> kBlkShift; blk <= (ln.hi >> kBlkShift); ++blk) {
+          uint64_t m = marker_bits_in(load_blk(v.rank_blk + blk), blk << kBlkShift, ln.lo, ln.hi);
+          while (m) {
 #if defined(__CUDA_ARCH__)
-              const uint32_t bit = __ffsll((long long)m) - 1;
+            const uint32_t bit = __ffsll((long long)m) - 1;
 #else
-              const uint32_t bit = (uint32_t)__builtin_ctzll(m);
+            const uint32_t bit = (uint32_t)__builtin_ctzll(m);
 #endif
-              m &= m - 1;
-              if (plan.n == kMaxPlan) {
-                GQ_COUNT(1);
-                return kNoAllele;
-              }
-              plan.lo[plan.n] = (blk << kBlkShift) + bit;
-              plan.w[plan.n] = 1;
-              plan.w0[plan.n] = ln.pos | (K_SCAN << 28);
-              plan.t[plan.n] = t;
-              ++plan.n;
-              ++total;
+            m &= m - 1;
+            if (plan.n + 1 >= kMaxPlan) {  // keep one entry for the interval itself
+              GQ_COUNT(1);
+              return kNoAllele;
             }
+            plan.lo[plan.n] = (blk << kBlkShift) + bit;
+            plan.w[plan.n] = 1;
+            plan.w0[plan.n] = ln.pos | (K_SCAN << 28);
+            ++plan.n;
+            ++total;
           }
-          ln.kind = K_READY;  // scanned
         }
-        lane_step_wide(ln, v, super_c);
+        ln.kind = K_READY;  // scanned
       }
-      if (ln.state != LS_EV_POP && (ln.state == LS_EV_WIDE || ln.hi - ln.lo >= kMaxSplit)) {
-        GQ_COUNT(1);
-        return kNoAllele;
-      }
-      // LS_RUN / LS_RUNW / LS_EV_SCAN (a marker inside the narrow interval: every suffix checks its own symbol)
-      lo = ln.lo;
-      hi = ln.state == LS_EV_POP ? lo - 1 : ln.hi;
-      w0 = ln.pos | (ln.kind << 28);
+      lane_step_wide(ln, v, super_c);
     }
-    if (hi + 1 != lo) {
-      if (plan.n == kMaxPlan) {
-        GQ_COUNT(1);
-        return kNoAllele;
-      }
-      plan.lo[plan.n] = lo;
-      plan.w[plan.n] = hi + 1 - lo;
-      plan.w0[plan.n] = w0;
-      plan.t[plan.n] = t;
-      ++plan.n;
-      total += hi + 1 - lo;
+    if (ln.state != LS_EV_POP && (ln.state == LS_EV_WIDE || ln.hi - ln.lo >= kMaxSplit)) {
+      GQ_COUNT(1);
+      return kNoAllele;
     }
-    GQ_COUNT(2);
+    // LS_RUN / LS_RUNW / LS_EV_SCAN (a marker inside the narrow interval: every suffix checks its own symbol)
+    lo = ln.lo;
+    hi = ln.state == LS_EV_POP ? lo - 1 : ln.hi;
+    w0 = ln.pos | (ln.kind << 28);
   }
+  if (hi + 1 != lo) {
+    plan.lo[plan.n] = lo;
+    plan.w[plan.n] = hi + 1 - lo;
+    plan.w0[plan.n] = w0;
+    ++plan.n;
+    total += hi + 1 - lo;
+  }
+  GQ_COUNT(2);
   return total;
 }
 
 // candidate record: 4 words {strand, k-mer state index, text position SA[i], pos | kind << 28}
-GQ_DEV inline void seed_write(const IndexView& v, const SeedPlan& plan, const SeedOut& pre, uint32_t strand,
+GQ_DEV inline void seed_write(const IndexView& v, const SeedPlan& plan, const SeedOut& pre, uint32_t strand, uint32_t j,
                               uint32_t base) {
   uint32_t* d = pre.rec + 4 * (size_t)base;
   for (uint32_t e = 0; e < plan.n; ++e)
     for (uint32_t i = 0; i < plan.w[e]; ++i, d += 4) {
       d[0] = strand;
-      d[1] = plan.sb + plan.t[e];
+      d[1] = j;
       d[2] = GQ_LDG(v.sa + plan.lo[e] + i);
       d[3] = plan.w0[e];
     }
@@ -1123,11 +1106,19 @@ GQ_DEV inline void map_strand(const IndexView& v, const uint32_t* super_cnt, con
     if (ns == 0) return;
     o.status[strand] = ST_UNCLASSIFIED;
     pre.surv_cnt[strand] = 0;
-    SeedPlan plan;
-    const uint32_t total = seed_plan(v, super_cnt, b, strand, sb, ns, plan);
-    if (total == kNoAllele || total > pre.cap) general = true;
-    else {
-      seed_write(v, plan, pre, strand, 0);  // the emulation reuses the candidate pool strand by strand
+    // the emulation reuses the candidate pool strand by strand
+    uint32_t total = 0;
+    const uint32_t r = strand >> 1;
+    for (uint32_t t = 0; t < ns && !general; ++t) {
+      SeedPlan plan;
+      const uint32_t cnt = seed_state_plan(v, super_cnt, b.packed + b.word_off[r], b.len[r], strand & 1u, sb + t, plan);
+      if (cnt == kNoAllele || total + cnt > pre.cap) general = true;
+      else {
+        seed_write(v, plan, pre, strand, sb + t, total);
+        total += cnt;
+      }
+    }
+    if (!general) {
       for (uint32_t i = 0; i < total; ++i) {
         FastLane f;
         fast_begin<false>(f, v, b, pre, i);

@@ -128,8 +128,11 @@ __device__ __forceinline__ bool warp_any_kmer_missing(const IndexView& v, const 
   return missing;
 }
 
-// Seed pass: thread per strand (preseed_lookup + seed_plan), candidates written through one warp-aggregated
-// allocation per 32 strands. Superblock counters (only needed to narrow wide seed states) come from shared
+// Seed pass. Warp-convergent rounds of 32 strands. Phase A: every lane looks up the seed states of its strand
+// (preseed_lookup). Phase B: the seed states of the round (3 per strand at config 2, tens for large genomes)
+// are spread evenly over the lanes, so lanes run the same narrowing / candidate code (seed_state_plan) instead
+// of per-strand loops of very different lengths; the candidates of 32 seed states are written through one
+// warp-aggregated allocation. Superblock counters (only needed to narrow wide seed states) come from shared
 // memory when they fit, like in the search kernel.
 template <bool SUPER_SMEM>
 __global__ void __launch_bounds__(256)
@@ -145,31 +148,66 @@ __global__ void __launch_bounds__(256)
     const uint32_t strand = 2 * b.read_begin + i;
     uint32_t sb = 0;
     const uint32_t ns = i < n ? preseed_lookup(v, b, o, strand, sb) : 0;
-    SeedPlan plan;
-    uint32_t total = 0;
+    uint32_t my_L = 0, my_woff = 0;
     if (ns) {
       o.status[strand] = ST_UNCLASSIFIED;  // until a candidate finishes or the general kernel decides
       pre.surv_cnt[strand] = 0;
-      total = seed_plan(v, SUPER_SMEM ? (const uint32_t*)s_super : v.super_cnt, b, strand, sb, ns, plan);
+      my_L = b.len[strand >> 1];
+      my_woff = b.word_off[strand >> 1];
     }
-    const bool general = total == kNoAllele;
-    const uint32_t mine = general ? 0u : total;
-    uint32_t incl = mine;  // inclusive warp scan
+    uint32_t incl = ns;  // inclusive warp scan of the seed-state counts
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       uint32_t t = __shfl_up_sync(full, incl, d);
       if (lane >= (uint32_t)d) incl += t;
     }
-    const uint32_t sum = __shfl_sync(full, incl, 31);
-    uint32_t base = 0;
-    if (sum && lane == 31) base = atomicAdd(pre.n_surv, sum);
-    base = __shfl_sync(full, base, 31);
-    if (general) send_to_general(pre, strand);  // cannot be split
-    else if (mine && base + sum > pre.cap) {    // candidate pool full: general kernel; the slots stay dead
-      send_to_general(pre, strand);
-      for (uint32_t q = base + incl - mine; q < base + incl && q < pre.cap; ++q) pre.rec[4 * (size_t)q] = kNoAllele;
-    } else if (mine)
-      seed_write(v, plan, pre, strand, base + incl - mine);
+    const uint32_t total = __shfl_sync(full, incl, 31);
+    uint32_t general = 0;  // bit per strand of the round: needs the general kernel
+    for (uint32_t t0 = 0; t0 < total; t0 += 32) {
+      const uint32_t t = t0 + lane;
+      // owner of task t = first lane whose inclusive count exceeds t
+      uint32_t lo_l = 0, hi_l = 31;
+#pragma unroll
+      for (int it = 0; it < 5; ++it) {
+        const uint32_t mid = (lo_l + hi_l) >> 1;
+        const uint32_t val = __shfl_sync(full, incl, mid);
+        if (val > t) hi_l = mid;
+        else lo_l = mid + 1;
+      }
+      const uint32_t owner = hi_l;
+      const uint32_t o_incl = __shfl_sync(full, incl, owner), o_ns = __shfl_sync(full, ns, owner),
+                     o_sb = __shfl_sync(full, sb, owner), o_L = __shfl_sync(full, my_L, owner),
+                     o_woff = __shfl_sync(full, my_woff, owner);
+      const uint32_t o_strand = 2 * b.read_begin + i0 + owner;
+      const uint32_t j = o_sb + (t - (o_incl - o_ns));
+      SeedPlan plan;
+      plan.n = 0;
+      uint32_t cnt = 0;
+      if (t < total)
+        cnt = seed_state_plan(v, SUPER_SMEM ? (const uint32_t*)s_super : v.super_cnt, b.packed + o_woff, o_L,
+                              o_strand & 1u, j, plan);
+      const bool bad = cnt == kNoAllele;
+      const uint32_t mine = bad ? 0u : cnt;
+      uint32_t cincl = mine;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        uint32_t x = __shfl_up_sync(full, cincl, d);
+        if (lane >= (uint32_t)d) cincl += x;
+      }
+      const uint32_t sum = __shfl_sync(full, cincl, 31);
+      uint32_t base = 0;
+      if (sum && lane == 31) base = atomicAdd(pre.n_surv, sum);
+      base = __shfl_sync(full, base, 31);
+      const bool pool_full = base + sum > pre.cap;
+      if (mine) {
+        if (pool_full) {  // candidate pool full: general kernel; the slots stay dead
+          for (uint32_t q = base + cincl - mine; q < base + cincl && q < pre.cap; ++q) pre.rec[4 * (size_t)q] = kNoAllele;
+        } else
+          seed_write(v, plan, pre, o_strand, j, base + cincl - mine);
+      }
+      general |= __reduce_or_sync(full, (bad || (mine && pool_full)) ? (1u << owner) : 0u);
+    }
+    if ((general >> lane) & 1u) send_to_general(pre, strand);
   }
 }
 
