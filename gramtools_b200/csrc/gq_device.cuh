@@ -825,17 +825,54 @@ GQ_DEV inline uint32_t seed_state_plan(const IndexView& v, SuperPtr super_c, con
   return total;
 }
 
-// candidate record: 4 words {strand, k-mer state index, text position SA[i], pos | kind << 28}
-GQ_DEV inline void seed_write(const IndexView& v, const SeedPlan& plan, const SeedOut& pre, uint32_t strand, uint32_t j,
+// part 3: the suffixes of the plan become candidates {text position, pos | kind << 28} — unless their very first
+// text step already fails (wrong base left of the suffix: most of the other occurrences of the seeding k-mer
+// end here, before they cost a record). Returns the number kept, or kNoAllele when they do not fit.
+constexpr uint32_t kMaxCand = 24;
+struct SeedCands {
+  uint32_t p[kMaxCand], w0[kMaxCand];
+};
+
+GQ_DEV inline uint32_t seed_filter(const IndexView& v, const SeedPlan& plan, const uint32_t* w, uint32_t L, uint32_t rc,
+                                   SeedCands& out) {
+  uint32_t n = 0, cur_pos = 0;
+  ReadCursor rd{w, L, rc, 0, 0, 0};
+  for (uint32_t e = 0; e < plan.n; ++e) {
+    const uint32_t w0 = plan.w0[e], pos = w0 & 0x0FFFFFFFu;
+    if (pos != cur_pos) {  // entries of one seed state share a few read positions
+      rd.seek(pos);
+      cur_pos = pos;
+    }
+    for (uint32_t i = 0; i < plan.w[e]; ++i) {
+      const uint32_t p = GQ_LDG(v.sa + plan.lo[e] + i);
+      Lane ln;
+      ln.rd = rd;
+      ln.pos = pos;
+      ln.kind = w0 >> 28;
+      ln.p = p;
+      ln.lo = ln.hi = ln.mr = 0;
+      ln.state = LS_TEXT;
+      lane_text_step(ln, v);
+      if (ln.state == LS_EV_POP) continue;
+      if (n == kMaxCand) return kNoAllele;
+      out.p[n] = p;
+      out.w0[n] = w0;
+      ++n;
+    }
+  }
+  return n;
+}
+
+// candidate record: 4 words {strand, k-mer state index, text position, pos | kind << 28}
+GQ_DEV inline void seed_write(const SeedCands& c, uint32_t n, const SeedOut& pre, uint32_t strand, uint32_t j,
                               uint32_t base) {
   uint32_t* d = pre.rec + 4 * (size_t)base;
-  for (uint32_t e = 0; e < plan.n; ++e)
-    for (uint32_t i = 0; i < plan.w[e]; ++i, d += 4) {
-      d[0] = strand;
-      d[1] = j;
-      d[2] = GQ_LDG(v.sa + plan.lo[e] + i);
-      d[3] = plan.w0[e];
-    }
+  for (uint32_t i = 0; i < n; ++i, d += 4) {
+    d[0] = strand;
+    d[1] = j;
+    d[2] = c.p[i];
+    d[3] = c.w0[i];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1111,10 +1148,12 @@ GQ_DEV inline void map_strand(const IndexView& v, const uint32_t* super_cnt, con
     const uint32_t r = strand >> 1;
     for (uint32_t t = 0; t < ns && !general; ++t) {
       SeedPlan plan;
-      const uint32_t cnt = seed_state_plan(v, super_cnt, b.packed + b.word_off[r], b.len[r], strand & 1u, sb + t, plan);
+      SeedCands cands;
+      uint32_t cnt = seed_state_plan(v, super_cnt, b.packed + b.word_off[r], b.len[r], strand & 1u, sb + t, plan);
+      if (cnt != kNoAllele) cnt = seed_filter(v, plan, b.packed + b.word_off[r], b.len[r], strand & 1u, cands);
       if (cnt == kNoAllele || total + cnt > pre.cap) general = true;
       else {
-        seed_write(v, plan, pre, strand, sb + t, total);
+        seed_write(cands, cnt, pre, strand, sb + t, total);
         total += cnt;
       }
     }

@@ -101,10 +101,14 @@ int gq_coverage_groups_import(gq_index* idx, const uint32_t* words, uint64_t n_w
 /* Run the kernels on a caller-owned CUDA stream (e.g. torch's current stream) so that the caller's
  * CUDA events bracket them. NULL = the library's own stream. */
 int gq_set_stream(gq_index* idx, void* cuda_stream);
-/* Tunables: arena words per thread, resident threads, stage rank superblocks in shared memory. */
+/* Tunables (name, value): arena_words, n_threads, cov_threads, super_in_smem, rf_thresh, ev_thresh (general
+ * kernel); seed_pass (0: every strand through the general kernel), seed_recs_per_read (candidate pool);
+ * chunk_reads, tail_chunk_reads (slices of the pipelined host path), resident_slices, overlap_classify.
+ * Results never depend on them. */
 int gq_set_option(gq_index* idx, const char* name, int64_t value);
-/* Counters of the last gq_map_* call: [kernel launches, overflow re-run strands, search ms (CUDA
- * events), coverage ms, pool words used] */
+/* Counters of the last gq_map_* call: [0] kernel launches, [1] overflow re-run strands, [2] search-phase ms
+ * and [3] classify + coverage ms (CUDA events; single-slice runs only), [4] pool words used, [5] H2D bytes,
+ * [6] all kernels ms (CUDA events on the caller's stream), [7] host ms spent enqueueing the call */
 int gq_last_run_info(gq_index* idx, double info[8]);
 
 const char* gq_last_error(void);
