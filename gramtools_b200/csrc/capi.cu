@@ -142,6 +142,9 @@ static void upload_index(gq_index* ix) {
   v.kmer_bits = upload(ix, h.kmer_bits);
   v.kmer_off = upload(ix, h.kmer_off);
   v.kmer_states = upload(ix, h.kmer_states);
+  v.seed_off = upload(ix, h.seed_off);
+  v.seed_ent = upload(ix, h.seed_ent);
+  v.seed_state = upload(ix, h.seed_state);
   v.kmer_paths = upload(ix, h.kmer_paths);
 }
 

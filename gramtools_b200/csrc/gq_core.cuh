@@ -61,6 +61,19 @@ struct KmerState {   // one seed SearchState (reference: kmer_index_types.hpp:24
   uint32_t counts;   // nt | ng << 16
 };
 
+// Seed-pass view of the k-mer index: per k-mer (seed_off, 4^k + 1) a run of 8-byte entries, one per SUFFIX of
+// every seed state of at most kSplitWidth suffixes, one per wider state. A suffix entry carries its text position
+// and its LEFT CONTEXT — the up to 12 PRG bases left of the occurrence, up to the first marker or the text start —
+// so the other occurrences of the seeding k-mer are rejected against the read without touching SA or text:
+//   key = text position SA[i];  aux = 1<<31 | n_ctx << 24 | ctx, base at p-1 in bits 23:22, p-2 in 21:20, ...
+// A wide state: key = lo, aux = hi (bit 31 clear: SA indices are below 2^31). seed_state[e] = index of the
+// entry's state in kmer_states (its path, needed only by candidates that finish).
+struct KmerSeed {
+  uint32_t key, aux;
+};
+constexpr uint32_t kSplitWidth = 256;  // states of up to this many suffixes are enumerated in the index
+constexpr uint32_t kSeedCtxBases = 12;
+
 struct IndexView {
   uint32_t n;  // SA size = |prg| + 1
   const RankBlk* rank_blk;
@@ -101,6 +114,9 @@ struct IndexView {
   const uint32_t* kmer_bits;   // 4^k bits: k-mer has >= 1 state
   const uint32_t* kmer_off;    // 4^k + 1
   const KmerState* kmer_states;
+  const uint32_t* seed_off;    // 4^k + 1
+  const KmerSeed* seed_ent;
+  const uint32_t* seed_state;
   const uint32_t* kmer_paths;
 };
 

@@ -688,7 +688,8 @@ GQ_DEV inline void lane_event(Lane& ln, const IndexView& v, const SearchOut& o) 
 
 // ------------------------------------------------------------------------------------------------
 // Seed pass. For one strand: look up the seeding k-mer (quasimap.cpp:178,235-241); each of its seed states
-// is narrowed by rank steps while it is wider than kSplitWidth suffixes, then SPLIT into its suffixes: every
+// is SPLIT into its suffixes (in the index itself for states of up to kSplitWidth suffixes; wider ones are
+// first narrowed by rank steps): every
 // occurrence becomes a width-1 state of its own — a candidate — that the text kernel walks through the PRG
 // text. Splitting is exact: a SearchState's interval is a set of suffixes that the reference advances in
 // lock-step (one LF step per suffix, one jump per marker-preceded suffix, vBWT_jump.cpp:94-117); walking
@@ -698,11 +699,11 @@ GQ_DEV inline void lane_event(Lane& ln, const IndexView& v, const SearchOut& o) 
 // with interval states. False candidates (a 10-mer has several occurrences, one of them real) die within
 // a step or two of the text walk.
 // ------------------------------------------------------------------------------------------------
-constexpr uint32_t kPreSteps = 6;    // rank steps at most, while the interval is wide
-constexpr uint32_t kSplitWidth = 4;  // stop narrowing at this many suffixes
+constexpr uint32_t kPreSteps = 8;     // rank steps at most, while the interval is wide
+constexpr uint32_t kNarrowWidth = 4;  // stop narrowing at this many suffixes
 constexpr uint32_t kMaxSplit = 32;   // wider than this after narrowing: general kernel
 
-// part 1: k-mer lookup. Returns the number of seed states (0: the strand is already classified).
+// part 1: k-mer lookup. Returns the number of seed entries (0: the strand is already classified).
 GQ_DEV inline uint32_t preseed_lookup(const IndexView& v, const BatchView& b, const SearchOut& o, uint32_t strand,
                                       uint32_t& sb) {
   const uint32_t r = strand >> 1;
@@ -725,8 +726,8 @@ GQ_DEV inline uint32_t preseed_lookup(const IndexView& v, const BatchView& b, co
     const uint32_t wlo = GQ_LDG(w + wi), whi = (wi + 1 < n_words) ? GQ_LDG(w + wi + 1) : 0u;
     code = gq_funnelshift_r(wlo, whi, 2 * (j0 & 15u)) & ((k == 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u));
   }
-  sb = GQ_LDG(v.kmer_off + code);
-  const uint32_t se = GQ_LDG(v.kmer_off + code + 1);
+  sb = GQ_LDG(v.seed_off + code);  // seed-pass view of the k-mer index: entries per suffix / wide state
+  const uint32_t se = GQ_LDG(v.seed_off + code + 1);
   if (sb == se) {  // the seeding k-mer itself is not indexed: the k-mer filter fails
     o.status[strand] = ST_MISSING_KMER;
     return 0;
@@ -746,11 +747,12 @@ GQ_DEV inline void send_to_general(const SeedOut& pre, uint32_t strand) {
 }
 
 // part 2: the candidates of ONE seed state, as a plan of entries {first SA index, number of suffixes,
-// pos | kind << 28}. A seed state narrower than kSplitWidth suffixes is one entry as it stands. A wider one is
+// pos | kind << 28}. (Only states wider than kSplitWidth get here: the suffixes of the others are entries of
+// the index.) A seed state narrower than kNarrowWidth suffixes is one entry as it stands. A wider one is
 // narrowed first, the way the reference advances it (quasimap.cpp:258-268): every marker-preceded suffix of
 // the interval becomes an entry of its own (its walk starts with that jump — the state left_markers_search
 // would spawn, vBWT_jump.cpp:94-117), then the interval consumes the next read base with two rank queries
-// (BWT_search.cpp:45-76), until fewer than kSplitWidth suffixes are left. Returns the number of candidates,
+// (BWT_search.cpp:45-76), until fewer than kNarrowWidth suffixes are left. Returns the number of candidates,
 // or kNoAllele when the strand needs the general kernel.
 constexpr uint32_t kMaxPlan = 24;
 struct SeedPlan {
@@ -760,16 +762,11 @@ struct SeedPlan {
 
 template <class SuperPtr>
 GQ_DEV inline uint32_t seed_state_plan(const IndexView& v, SuperPtr super_c, const uint32_t* w, uint32_t L, uint32_t rc,
-                                       uint32_t j, SeedPlan& plan) {
+                                       uint32_t lo, uint32_t hi, SeedPlan& plan) {
   plan.n = 0;
   const uint32_t pos0 = L - v.k;
-  if (pos0 == 0) {  // the seed states are the final states
-    GQ_COUNT(0);
-    return kNoAllele;
-  }
-  const KmerState ks = v.kmer_states[j];
-  uint32_t lo = ks.lo, hi = ks.hi, w0 = pos0 | (K_SCAN << 28), total = 0;
-  if (hi - lo >= kSplitWidth) {
+  uint32_t w0 = pos0 | (K_SCAN << 28), total = 0;
+  if (hi - lo >= kNarrowWidth) {
     Lane ln;
     ln.rd = ReadCursor{w, L, rc, 0, 0, 0};
     ln.pos = pos0;
@@ -779,7 +776,7 @@ GQ_DEV inline uint32_t seed_state_plan(const IndexView& v, SuperPtr super_c, con
     ln.kind = K_SCAN;
     ln.rd.seek(ln.pos);
     ln.state = LS_RUNW;
-    for (uint32_t s = 0; s < kPreSteps && ln.state == LS_RUNW && ln.hi - ln.lo >= kSplitWidth && ln.pos > 1; ++s) {
+    for (uint32_t s = 0; s < kPreSteps && ln.state == LS_RUNW && ln.hi - ln.lo >= kNarrowWidth && ln.pos > 1; ++s) {
       if (ln.kind == K_SCAN) {  // marker-preceded suffixes leave the interval as candidates of their own
         for (uint32_t blk = ln.lo >> kBlkShift; blk <= (ln.hi >> kBlkShift); ++blk) {
           uint64_t m = marker_bits_in(load_blk(v.rank_blk + blk), blk << kBlkShift, ln.lo, ln.hi);
@@ -861,6 +858,41 @@ GQ_DEV inline uint32_t seed_filter(const IndexView& v, const SeedPlan& plan, con
     }
   }
   return n;
+}
+
+// parts 2 + 3 for seed entry j. The common case — a suffix of a narrow state — is decided from its 8-byte
+// entry alone: text position + left context (KmerSeed), compared with the next read bases in registers.
+template <class SuperPtr>
+GQ_DEV inline uint32_t seed_state_cands(const IndexView& v, SuperPtr super_c, const uint32_t* w, uint32_t L, uint32_t rc,
+                                        uint32_t j, SeedCands& out) {
+  const uint32_t pos0 = L - v.k;
+  if (pos0 == 0) {  // the seed states are the final states
+    GQ_COUNT(0);
+    return kNoAllele;
+  }
+#if defined(__CUDA_ARCH__)
+  const uint2 raw = __ldg(reinterpret_cast<const uint2*>(v.seed_ent) + j);
+  const uint32_t key = raw.x, aux = raw.y;
+#else
+  const uint32_t key = v.seed_ent[j].key, aux = v.seed_ent[j].aux;
+#endif
+  if (aux & 0x80000000u) {
+    uint32_t m = (aux >> 24) & 0x7Fu;  // context bases, up to the first marker / the text start
+    m = m < pos0 ? m : pos0;
+    if (m) {
+      ReadCursor rd{w, L, rc, 0, 0, 0};
+      rd.seek(pos0);
+      const uint32_t x = ((rd.top32() >> 8) ^ aux) & ((0xFFFFFFFFu << (24 - 2 * m)) & 0xFFFFFFu);
+      if (x) return 0;  // another occurrence of the k-mer: the read continues differently
+    }
+    GQ_COUNT(2);
+    out.p[0] = key;
+    out.w0[0] = pos0 | (K_SCAN << 28);
+    return 1;
+  }
+  SeedPlan plan;
+  const uint32_t cnt = seed_state_plan(v, super_c, w, L, rc, key, aux, plan);
+  return cnt == kNoAllele ? cnt : seed_filter(v, plan, w, L, rc, out);
 }
 
 // candidate record: 4 words {strand, k-mer state index, text position, pos | kind << 28}
@@ -1147,13 +1179,11 @@ GQ_DEV inline void map_strand(const IndexView& v, const uint32_t* super_cnt, con
     uint32_t total = 0;
     const uint32_t r = strand >> 1;
     for (uint32_t t = 0; t < ns && !general; ++t) {
-      SeedPlan plan;
       SeedCands cands;
-      uint32_t cnt = seed_state_plan(v, super_cnt, b.packed + b.word_off[r], b.len[r], strand & 1u, sb + t, plan);
-      if (cnt != kNoAllele) cnt = seed_filter(v, plan, b.packed + b.word_off[r], b.len[r], strand & 1u, cands);
+      const uint32_t cnt = seed_state_cands(v, super_cnt, b.packed + b.word_off[r], b.len[r], strand & 1u, sb + t, cands);
       if (cnt == kNoAllele || total + cnt > pre.cap) general = true;
       else {
-        seed_write(cands, cnt, pre, strand, sb + t, total);
+        seed_write(cands, cnt, pre, strand, v.seed_state[sb + t], total);
         total += cnt;
       }
     }

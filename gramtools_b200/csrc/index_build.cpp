@@ -41,6 +41,9 @@ IndexView HostIndex::view() const {
   v.kmer_bits = kmer_bits.data();
   v.kmer_off = kmer_off.data();
   v.kmer_states = kmer_states.data();
+  v.seed_off = seed_off.data();
+  v.seed_ent = seed_ent.data();
+  v.seed_state = seed_state.data();
   v.kmer_paths = kmer_paths.data();
   return v;
 }
@@ -590,6 +593,44 @@ void build_kmers(HostIndex& ix) {
   }
   if (ix.kmer_paths.empty()) ix.kmer_paths.push_back(0);
   if (ix.kmer_states.empty()) ix.kmer_states.push_back(KmerState{});
+  // seed-pass view: per k-mer one entry per suffix of its narrow states (text position + left context), one
+  // entry per wide state
+  ix.seed_off.assign(nk + 1, 0);
+  for (uint64_t c = 0; c < nk; ++c) {
+    uint32_t cnt = 0;
+    for (uint32_t j = ix.kmer_off[c]; j < ix.kmer_off[c + 1]; ++j) {
+      const uint32_t wdt = ix.kmer_states[j].hi - ix.kmer_states[j].lo + 1;
+      cnt += wdt <= kSplitWidth ? wdt : 1;
+    }
+    ix.seed_off[c + 1] = ix.seed_off[c] + cnt;
+  }
+  ix.seed_ent.assign(std::max<size_t>(ix.seed_off[nk], 1), KmerSeed{0, 0});
+  ix.seed_state.assign(std::max<size_t>(ix.seed_off[nk], 1), 0);
+  const int64_t n_codes = (int64_t)nk;
+#pragma omp parallel for schedule(dynamic, 4096)
+  for (int64_t c = 0; c < n_codes; ++c) {
+    uint32_t e = ix.seed_off[c];
+    for (uint32_t j = ix.kmer_off[c]; j < ix.kmer_off[c + 1]; ++j) {
+      const KmerState& ks = ix.kmer_states[j];
+      if (ks.hi - ks.lo + 1 > kSplitWidth) {
+        ix.seed_ent[e] = KmerSeed{ks.lo, ks.hi};
+        ix.seed_state[e++] = j;
+        continue;
+      }
+      for (uint32_t i = ks.lo; i <= ks.hi; ++i) {
+        const uint32_t p = ix.sa[i];
+        uint32_t ctx = 0, nctx = 0;
+        while (nctx < kSeedCtxBases && nctx < p) {
+          const uint32_t sym = ix.prg[p - 1 - nctx];
+          if (sym > 4) break;
+          ctx |= (sym - 1) << (22 - 2 * nctx);
+          ++nctx;
+        }
+        ix.seed_ent[e] = KmerSeed{p, 0x80000000u | (nctx << 24) | ctx};
+        ix.seed_state[e++] = j;
+      }
+    }
+  }
 }
 
 }  // namespace

@@ -44,6 +44,8 @@ struct HostIndex {
   // k-mer index
   std::vector<uint32_t> kmer_bits, kmer_off, kmer_paths;
   std::vector<KmerState> kmer_states;
+  std::vector<uint32_t> seed_off, seed_state;  // seed-pass view (KmerSeed)
+  std::vector<KmerSeed> seed_ent;
 
   IndexView view() const;
 };

@@ -180,15 +180,11 @@ __global__ void __launch_bounds__(256)
                      o_woff = __shfl_sync(full, my_woff, owner);
       const uint32_t o_strand = 2 * b.read_begin + i0 + owner;
       const uint32_t j = o_sb + (t - (o_incl - o_ns));
-      SeedPlan plan;
       SeedCands cands;
-      plan.n = 0;
       uint32_t cnt = 0;
-      if (t < total) {
-        cnt = seed_state_plan(v, SUPER_SMEM ? (const uint32_t*)s_super : v.super_cnt, b.packed + o_woff, o_L,
-                              o_strand & 1u, j, plan);
-        if (cnt != kNoAllele) cnt = seed_filter(v, plan, b.packed + o_woff, o_L, o_strand & 1u, cands);
-      }
+      if (t < total)
+        cnt = seed_state_cands(v, SUPER_SMEM ? (const uint32_t*)s_super : v.super_cnt, b.packed + o_woff, o_L,
+                               o_strand & 1u, j, cands);
       const bool bad = cnt == kNoAllele;
       const uint32_t mine = bad ? 0u : cnt;
       uint32_t cincl = mine;
@@ -206,7 +202,7 @@ __global__ void __launch_bounds__(256)
         if (pool_full) {  // candidate pool full: general kernel; the slots stay dead
           for (uint32_t q = base + cincl - mine; q < base + cincl && q < pre.cap; ++q) pre.rec[4 * (size_t)q] = kNoAllele;
         } else
-          seed_write(cands, mine, pre, o_strand, j, base + cincl - mine);
+          seed_write(cands, mine, pre, o_strand, __ldg(v.seed_state + j), base + cincl - mine);
       }
       general |= __reduce_or_sync(full, (bad || (mine && pool_full)) ? (1u << owner) : 0u);
     }

@@ -232,3 +232,6 @@ def test_frequent_kmers_wide_seed_intervals(built_lib):
     prg = synth.make_snp_prg(200000, 400, 7)[0]
     bases, offs = _reads_for(prg, 6000, 60, 5, garbage=0.02, n_frac=0.0)
     _check(prg, 5, bases, offs, what="wide-seeds", threads=os.cpu_count())
+    prg = synth.make_snp_prg(300000, 300, 7)[0]  # ~1200 occurrences per 4-mer: narrowed with rank steps
+    bases, offs = _reads_for(prg, 3000, 50, 5, garbage=0.02, n_frac=0.0)
+    _check(prg, 4, bases, offs, what="very-wide-seeds", threads=os.cpu_count())

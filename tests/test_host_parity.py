@@ -212,11 +212,12 @@ def test_repeats_take_the_general_route():
     assert r["multi_finisher"] >= 2 and r["general"] >= 2, r
 
 
-@pytest.mark.parametrize("shape", [(200000, 400, 5, 60), (400000, 4000, 6, 70)])
+@pytest.mark.parametrize("shape", [(200000, 400, 5, 60), (400000, 4000, 6, 70), (300000, 300, 4, 50)])
 def test_frequent_kmers_wide_seed_intervals(shape):
     """Large-genome regime in miniature (config 4/5: tens of occurrences per k-mer): the seeding k-mer's main state
-    is an interval of ~100-200 suffixes that the seed pass narrows with rank steps, peeling off marker-preceded
-    suffixes as candidates of their own."""
+    is an interval of ~100-200 suffixes, enumerated in the seed view of the index; in the last shape (~1200
+    occurrences per k-mer, beyond kSplitWidth) the seed pass narrows it with rank steps, peeling off
+    marker-preceded suffixes as candidates of their own."""
     n, n_sites, k, L = shape
     prg = synth.make_snp_prg(n, n_sites, 7)[0]
     bases, offs = _reads_for(prg, 1500, L, 5, garbage=0.02, n_frac=0.0)
