@@ -128,21 +128,78 @@ __device__ __forceinline__ bool warp_any_kmer_missing(const IndexView& v, const 
   return missing;
 }
 
-// Seed pass. Warp-convergent rounds of 32 strands. Phase A: every lane looks up the seed states of its strand
-// (preseed_lookup). Phase B: the seed states of the round (3 per strand at config 2, tens for large genomes)
-// are spread evenly over the lanes, so lanes run the same narrowing / candidate code (seed_state_plan) instead
-// of per-strand loops of very different lengths; the candidates of 32 seed states are written through one
-// warp-aggregated allocation. Superblock counters (only needed to narrow wide seed states) come from shared
-// memory when they fit, like in the search kernel.
+// Seed pass. Warp-convergent rounds of 32 strands. Phase A: every lane looks up the seed entries of its strand
+// (preseed_lookup). Phase B: the entries of the round are examined (seed_state_cands) by all lanes —
+//   * few entries per strand (config 2: ~4): the round's entries are spread evenly over the lanes, so lanes
+//     run the same code instead of per-strand loops of very different lengths;
+//   * many entries per strand (large genomes: tens to hundreds): strand by strand, 32 consecutive entries per
+//     step — coalesced 8-byte loads, no search for the owner.
+// Survivors are staged in shared memory and written through one warp-aggregated allocation when the stage
+// fills. Superblock counters (only needed to narrow very wide seed states) come from shared memory when they
+// fit, like in the search kernel.
+constexpr uint32_t kSeedStage = 96;        // candidates staged per warp
+constexpr uint32_t kSeedStrandMode = 384;  // entries per round of 32 strands from which mode 2 is used
+
+struct SeedStage {
+  uint32_t* rec;  // this warp's kSeedStage x 4 words in shared memory
+  uint32_t n;     // staged candidates (warp-uniform)
+};
+
+// write the staged candidates to the pool; a full pool sends their strands to the general kernel
+__device__ __forceinline__ void seed_flush(SeedStage& st, const SeedOut& pre, uint32_t lane) {
+  const uint32_t full = 0xFFFFFFFFu;
+  if (st.n == 0) return;
+  uint32_t base = 0;
+  if (lane == 0) base = atomicAdd(pre.n_surv, st.n);
+  base = __shfl_sync(full, base, 0);
+  __syncwarp();
+  const bool fits = base + st.n <= pre.cap;
+  for (uint32_t q = lane; q < st.n; q += 32) {
+    const uint4 c = reinterpret_cast<const uint4*>(st.rec)[q];
+    if (fits) reinterpret_cast<uint4*>(pre.rec)[base + q] = c;
+    else {
+      send_to_general(pre, c.x);
+      if (base + q < pre.cap) pre.rec[4 * (size_t)(base + q)] = kNoAllele;  // the slot stays dead
+    }
+  }
+  __syncwarp();
+  st.n = 0;
+}
+
+// stage up to `cnt` candidates per lane (cnt is 0 or 1 except for very wide seed states)
+__device__ __forceinline__ void seed_push(SeedStage& st, const SeedOut& pre, const IndexView& v, const SeedCands& c,
+                                          uint32_t cnt, uint32_t strand, uint32_t entry, uint32_t lane) {
+  const uint32_t full = 0xFFFFFFFFu;
+  uint32_t most = cnt;
+#pragma unroll
+  for (int d = 16; d; d >>= 1) most = max(most, __shfl_xor_sync(full, most, d));
+  for (uint32_t r = 0; r < most; ++r) {
+    const uint32_t mm = __ballot_sync(full, r < cnt);
+    const uint32_t k = __popc(mm);
+    if (st.n + k > kSeedStage) seed_flush(st, pre, lane);
+    if (r < cnt) {
+      uint32_t* d = st.rec + 4 * (st.n + __popc(mm & ((1u << lane) - 1u)));
+      d[0] = strand;
+      d[1] = __ldg(v.seed_state + entry);
+      d[2] = c.p[r];
+      d[3] = c.w0[r];
+    }
+    st.n += k;
+  }
+}
+
 template <bool SUPER_SMEM>
 __global__ void __launch_bounds__(256)
     seed_kernel(IndexView v, BatchView b, SearchOut o, SeedOut pre, uint32_t n_super_smem) {
   extern __shared__ __align__(128) uint32_t s_super[];
   __shared__ alignas(8) uint64_t s_bar;
+  __shared__ alignas(16) uint32_t s_stage[8][kSeedStage * 4];
   if (SUPER_SMEM) tma_stage_super(s_super, v.super_cnt, n_super_smem * 16u, &s_bar);
+  const uint32_t* super_c = SUPER_SMEM ? (const uint32_t*)s_super : v.super_cnt;
   const uint32_t n = 2 * (b.read_end - b.read_begin);
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t full = 0xFFFFFFFFu;
+  SeedStage stage{s_stage[threadIdx.x >> 5], 0};
   for (uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; i0 < n; i0 += gridDim.x * blockDim.x) {
     const uint32_t i = i0 + lane;
     const uint32_t strand = 2 * b.read_begin + i;
@@ -155,7 +212,7 @@ __global__ void __launch_bounds__(256)
       my_L = b.len[strand >> 1];
       my_woff = b.word_off[strand >> 1];
     }
-    uint32_t incl = ns;  // inclusive warp scan of the seed-state counts
+    uint32_t incl = ns;  // inclusive warp scan of the entry counts
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       uint32_t t = __shfl_up_sync(full, incl, d);
@@ -163,51 +220,52 @@ __global__ void __launch_bounds__(256)
     }
     const uint32_t total = __shfl_sync(full, incl, 31);
     uint32_t general = 0;  // bit per strand of the round: needs the general kernel
-    for (uint32_t t0 = 0; t0 < total; t0 += 32) {
-      const uint32_t t = t0 + lane;
-      // owner of task t = first lane whose inclusive count exceeds t
-      uint32_t lo_l = 0, hi_l = 31;
+    if (total < kSeedStrandMode) {
+      for (uint32_t t0 = 0; t0 < total; t0 += 32) {
+        const uint32_t t = t0 + lane;
+        // owner of task t = first lane whose inclusive count exceeds t
+        uint32_t lo_l = 0, hi_l = 31;
 #pragma unroll
-      for (int it = 0; it < 5; ++it) {
-        const uint32_t mid = (lo_l + hi_l) >> 1;
-        const uint32_t val = __shfl_sync(full, incl, mid);
-        if (val > t) hi_l = mid;
-        else lo_l = mid + 1;
+        for (int it = 0; it < 5; ++it) {
+          const uint32_t mid = (lo_l + hi_l) >> 1;
+          const uint32_t val = __shfl_sync(full, incl, mid);
+          if (val > t) hi_l = mid;
+          else lo_l = mid + 1;
+        }
+        const uint32_t owner = hi_l;
+        const uint32_t o_incl = __shfl_sync(full, incl, owner), o_ns = __shfl_sync(full, ns, owner),
+                       o_sb = __shfl_sync(full, sb, owner), o_L = __shfl_sync(full, my_L, owner),
+                       o_woff = __shfl_sync(full, my_woff, owner);
+        const uint32_t o_strand = 2 * b.read_begin + i0 + owner;
+        const uint32_t e = o_sb + (t - (o_incl - o_ns));
+        SeedCands cands;
+        uint32_t cnt = 0;
+        if (t < total) cnt = seed_state_cands(v, super_c, b.packed + o_woff, o_L, o_strand & 1u, e, cands);
+        const bool bad = cnt == kNoAllele;
+        general |= __reduce_or_sync(full, bad ? (1u << owner) : 0u);
+        seed_push(stage, pre, v, cands, bad ? 0u : cnt, o_strand, e, lane);
       }
-      const uint32_t owner = hi_l;
-      const uint32_t o_incl = __shfl_sync(full, incl, owner), o_ns = __shfl_sync(full, ns, owner),
-                     o_sb = __shfl_sync(full, sb, owner), o_L = __shfl_sync(full, my_L, owner),
-                     o_woff = __shfl_sync(full, my_woff, owner);
-      const uint32_t o_strand = 2 * b.read_begin + i0 + owner;
-      const uint32_t j = o_sb + (t - (o_incl - o_ns));
-      SeedCands cands;
-      uint32_t cnt = 0;
-      if (t < total)
-        cnt = seed_state_cands(v, SUPER_SMEM ? (const uint32_t*)s_super : v.super_cnt, b.packed + o_woff, o_L,
-                               o_strand & 1u, j, cands);
-      const bool bad = cnt == kNoAllele;
-      const uint32_t mine = bad ? 0u : cnt;
-      uint32_t cincl = mine;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        uint32_t x = __shfl_up_sync(full, cincl, d);
-        if (lane >= (uint32_t)d) cincl += x;
+    } else {
+      for (uint32_t owner = 0; owner < 32; ++owner) {
+        const uint32_t o_ns = __shfl_sync(full, ns, owner);
+        if (o_ns == 0) continue;
+        const uint32_t o_sb = __shfl_sync(full, sb, owner), o_L = __shfl_sync(full, my_L, owner),
+                       o_woff = __shfl_sync(full, my_woff, owner);
+        const uint32_t o_strand = 2 * b.read_begin + i0 + owner;
+        for (uint32_t c0 = 0; c0 < o_ns; c0 += 32) {
+          const uint32_t e = o_sb + c0 + lane;
+          SeedCands cands;
+          uint32_t cnt = 0;
+          if (c0 + lane < o_ns) cnt = seed_state_cands(v, super_c, b.packed + o_woff, o_L, o_strand & 1u, e, cands);
+          const bool bad = cnt == kNoAllele;
+          if (__any_sync(full, bad)) general |= 1u << owner;
+          seed_push(stage, pre, v, cands, bad ? 0u : cnt, o_strand, e, lane);
+        }
       }
-      const uint32_t sum = __shfl_sync(full, cincl, 31);
-      uint32_t base = 0;
-      if (sum && lane == 31) base = atomicAdd(pre.n_surv, sum);
-      base = __shfl_sync(full, base, 31);
-      const bool pool_full = base + sum > pre.cap;
-      if (mine) {
-        if (pool_full) {  // candidate pool full: general kernel; the slots stay dead
-          for (uint32_t q = base + cincl - mine; q < base + cincl && q < pre.cap; ++q) pre.rec[4 * (size_t)q] = kNoAllele;
-        } else
-          seed_write(cands, mine, pre, o_strand, __ldg(v.seed_state + j), base + cincl - mine);
-      }
-      general |= __reduce_or_sync(full, (bad || (mine && pool_full)) ? (1u << owner) : 0u);
     }
     if ((general >> lane) & 1u) send_to_general(pre, strand);
   }
+  seed_flush(stage, pre, lane);
 }
 
 void launch_seed(const IndexView& v, const BatchView& b, const SearchOut& o, const SeedOut& pre, cudaStream_t st) {
