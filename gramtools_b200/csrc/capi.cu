@@ -140,6 +140,7 @@ static void upload_index(gq_index* ix) {
   v.edges = upload(ix, h.edges);
   v.k = h.k;
   v.kmer_bits = upload(ix, h.kmer_bits);
+  v.kmer_bits_rc = upload(ix, h.kmer_bits_rc);
   v.kmer_off = upload(ix, h.kmer_off);
   v.kmer_states = upload(ix, h.kmer_states);
   v.seed_off = upload(ix, h.seed_off);

@@ -39,6 +39,7 @@ IndexView HostIndex::view() const {
   v.edges = edges.data();
   v.k = k;
   v.kmer_bits = kmer_bits.data();
+  v.kmer_bits_rc = kmer_bits_rc.data();
   v.kmer_off = kmer_off.data();
   v.kmer_states = kmer_states.data();
   v.seed_off = seed_off.data();
@@ -593,6 +594,14 @@ void build_kmers(HostIndex& ix) {
   }
   if (ix.kmer_paths.empty()) ix.kmer_paths.push_back(0);
   if (ix.kmer_states.empty()) ix.kmer_states.push_back(KmerState{});
+  // presence set indexed by the reverse complement's code: bits_rc[c] = bits[revcomp_k(c)]
+  ix.kmer_bits_rc.assign(ix.kmer_bits.size(), 0);
+  for (uint64_t c = 0; c < nk; ++c) {
+    if (!((ix.kmer_bits[c >> 5] >> (c & 31)) & 1u)) continue;
+    uint64_t r = 0, x = ~c;
+    for (uint32_t i = 0; i < k; ++i) r |= ((x >> (2 * i)) & 3ull) << (2 * (k - 1 - i));
+    ix.kmer_bits_rc[r >> 5] |= 1u << (r & 31);
+  }
   // seed-pass view: per k-mer one entry per suffix of its narrow states (text position + left context), one
   // entry per wide state
   ix.seed_off.assign(nk + 1, 0);

@@ -42,7 +42,7 @@ struct HostIndex {
   std::vector<uint32_t> site_start_node;  // per slot: bubble start node id
   uint32_t n_per_base = 0;                // number of in-bubble bases (flat per-base layout)
   // k-mer index
-  std::vector<uint32_t> kmer_bits, kmer_off, kmer_paths;
+  std::vector<uint32_t> kmer_bits, kmer_bits_rc, kmer_off, kmer_paths;
   std::vector<KmerState> kmer_states;
   std::vector<uint32_t> seed_off, seed_state;  // seed-pass view (KmerSeed)
   std::vector<KmerSeed> seed_ent;

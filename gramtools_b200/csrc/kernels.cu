@@ -104,24 +104,46 @@ constexpr int kHotUnroll = GQ_HOT_UNROLL;
 #ifndef GQ_SEARCH_MIN_BLOCKS
 #define GQ_SEARCH_MIN_BLOCKS 5  // 48 registers, 1280 resident lanes per SM
 #endif
-// k-mer filter of one strand by a whole warp: lane j tests the k-mers starting at bases j, j+32, ... (a
-// k-mer code is a bit-field of the packed read, see classify_strand); a ballot ends the strand at the
-// first round that finds a missing k-mer. Must be called by all 32 lanes with uniform arguments.
-__device__ __forceinline__ bool warp_any_kmer_missing(const IndexView& v, const uint32_t* w, uint32_t L, bool rc,
-                                                      uint32_t lane) {
-  const uint32_t k = v.k;
+// k-mer filter of one strand by a whole warp. A k-mer code is a bit-field of the packed read (see
+// classify_strand), so each lane takes a RUN of consecutive k-mers: one 64-bit window of the read, then one
+// shift + mask + bit test per k-mer; the reverse strand tests the same windows against the presence set
+// indexed by the reverse complement's code (kmer_bits_rc), so no per-k-mer transform is needed. A ballot ends
+// the strand at the first round that finds a missing k-mer (a 150 bp read is one round). Must be called by all
+// 32 lanes with uniform arguments.
+// `bits`: the presence set to probe (global or a shared-memory copy); `transform`: reverse strand probing the
+// forward-indexed set, so each code is reverse-complemented first.
+// The packed words come from memory (`w`) or, when w == nullptr, from the lanes' registers (`word` = packed word
+// `lane` of the strand, reads of up to 512 bases).
+__device__ __forceinline__ bool warp_any_kmer_missing(uint32_t k, const uint32_t* bits, bool transform, const uint32_t* w,
+                                                      uint32_t word, uint32_t L, uint32_t lane) {
   const uint32_t mask = (k == 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
   const uint32_t n_words = (L + 15) >> 4, n_kmers = L - k + 1;
+  // k-mers per lane and round: the run's bases (k + per - 1) must fit the 64-bit window at any 2-bit offset
+  uint32_t per = (n_kmers + 31) >> 5;
+  const uint32_t fit = k < 17 ? 18 - k : 1;
+  per = per < fit ? per : fit;
   bool missing = false;
-  for (uint32_t j0 = 0; j0 < n_kmers && !missing; j0 += 32) {
-    const uint32_t j = j0 + lane;
+  for (uint32_t j0 = 0; j0 < n_kmers && !missing; j0 += 32 * per) {
+    const uint32_t j = j0 + lane * per;
     bool absent = false;
+    const uint32_t wi = j >> 4, sh = 2 * (j & 15u);
+    uint32_t lo, hi;
+    if (w) {
+      lo = (j < n_kmers) ? __ldg(w + wi) : 0u;
+      hi = (j < n_kmers && wi + 1 < n_words) ? __ldg(w + wi + 1) : 0u;
+    } else {  // all lanes take part in the shuffles
+      lo = __shfl_sync(0xFFFFFFFFu, word, wi & 31u);
+      hi = __shfl_sync(0xFFFFFFFFu, word, (wi + 1) & 31u);
+      if (wi + 1 >= n_words) hi = 0u;
+    }
     if (j < n_kmers) {
-      const uint32_t wi = j >> 4, sh = 2 * (j & 15u);
-      const uint32_t lo = __ldg(w + wi), hi = (wi + 1 < n_words) ? __ldg(w + wi + 1) : 0u;
-      const uint32_t win = __funnelshift_r(lo, hi, sh);
-      const uint32_t code = rc ? (pair_reverse32(~win) >> (32 - 2 * k)) : (win & mask);
-      absent = !((__ldg(v.kmer_bits + (code >> 5)) >> (code & 31u)) & 1u);
+      uint64_t win = (((uint64_t)hi << 32) | lo) >> sh;
+      const uint32_t cnt = min(per, n_kmers - j);
+      for (uint32_t t = 0; t < cnt; ++t, win >>= 2) {
+        uint32_t code = (uint32_t)win & mask;
+        if (transform) code = pair_reverse32(~(uint32_t)win) >> (32 - 2 * k);
+        absent |= !((bits[code >> 5] >> (code & 31u)) & 1u);
+      }
     }
     missing = __any_sync(0xFFFFFFFFu, absent);
   }
@@ -504,28 +526,63 @@ __global__ void __launch_bounds__(kSearchThreads, GQ_SEARCH_MIN_BLOCKS)
   }
 }
 
-// k-mer filter for failed strands, one WARP per strand: lane j tests the k-mers starting at bases
-// j, j+32, ... of the strand (a k-mer code is a bit-field of the packed read, see classify_strand), a
-// ballot ends the strand at the first round that finds a missing k-mer. Lanes first vote on 32 statuses
-// at once to find the unclassified strands of the warp's slice.
-__global__ void __launch_bounds__(256)
-    classify_kernel(IndexView v, BatchView b, SearchOut o, const uint32_t* list, uint32_t n_list) {
+// k-mer filter for failed strands, one WARP per strand (warp_any_kmer_missing). Lanes first vote on 32 statuses
+// at once to find the unclassified strands of the warp's slice. The probes are random 4-byte reads — 32
+// different L1 lines per warp load — so when the 4^k-bit set fits (k <= 10: 128 KB) each CTA keeps a copy in
+// shared memory (one persistent 1024-thread CTA per SM) and the probes become bank-conflict-bound instead.
+constexpr uint32_t kClassifySmemBytes = 160 * 1024;
+
+template <bool SMEM>
+__global__ void __launch_bounds__(SMEM ? 1024 : 256)
+    classify_kernel(IndexView v, BatchView b, SearchOut o, const uint32_t* list, uint32_t n_list, uint32_t bits_words) {
+  extern __shared__ __align__(16) uint32_t s_bits[];
+  if (SMEM) {
+    const uint4* src = reinterpret_cast<const uint4*>(v.kmer_bits);
+    uint4* dst = reinterpret_cast<uint4*>(s_bits);
+    for (uint32_t q = threadIdx.x; q < (bits_words + 3) / 4; q += blockDim.x) dst[q] = __ldg(src + q);
+    __syncthreads();
+  }
   const uint32_t n = list ? n_list : 2 * (b.read_end - b.read_begin);
   const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t full = 0xFFFFFFFFu;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t* bits_f = SMEM ? (const uint32_t*)s_bits : v.kmer_bits;
   for (uint32_t base = warp * 32; base < n; base += n_warps * 32) {
     const uint32_t i = base + lane;
     const uint32_t my_strand = i < n ? (list ? list[i] : 2 * b.read_begin + i) : 0;
-    uint32_t todo = __ballot_sync(0xFFFFFFFFu, i < n && o.status[my_strand] == ST_UNCLASSIFIED);
+    const bool need = i < n && o.status[my_strand] == ST_UNCLASSIFIED;
+    // every lane fetches the metadata of its own strand once; the strands are then classified one after the
+    // other by the whole warp, the packed words of the NEXT strand in flight (one word per lane) while the
+    // current one is probed from registers — no dependent global load left in the per-strand chain
+    const uint32_t my_L = need ? b.len[my_strand >> 1] : 0, my_woff = need ? b.word_off[my_strand >> 1] : 0;
+    uint32_t todo = __ballot_sync(full, need);
+    auto fetch = [&](int src, uint32_t& L) -> uint32_t {
+      L = __shfl_sync(full, my_L, src);
+      const uint32_t woff = __shfl_sync(full, my_woff, src);
+      return lane < ((L + 15) >> 4) ? __ldg(b.packed + woff + lane) : 0u;
+    };
+    int src = todo ? __ffs(todo) - 1 : 0;
+    uint32_t nxt_L = 0, nxt_w = todo ? fetch(src, nxt_L) : 0u;
     while (todo) {
-      const int src = __ffs(todo) - 1;
+      const uint32_t strand = __shfl_sync(full, my_strand, src);
+      const uint32_t L = nxt_L, word = nxt_w;
       todo &= todo - 1;
-      const uint32_t strand = __shfl_sync(0xFFFFFFFFu, my_strand, src);
-      const uint32_t r = strand >> 1;
-      const uint32_t L = b.len[r];
-      const uint32_t* w = b.packed + b.word_off[r];
+      if (todo) {
+        src = __ffs(todo) - 1;
+        nxt_w = fetch(src, nxt_L);
+      }
       const bool rc = (strand & 1u) != 0;
-      const bool missing = warp_any_kmer_missing(v, w, L, rc, lane);
+      bool missing;
+      if (L <= 512) {
+        // global: the reverse strand probes the set indexed by reverse-complement codes; shared: one copy of the
+        // forward set, reverse-strand codes transformed
+        missing = SMEM ? warp_any_kmer_missing(v.k, bits_f, rc, nullptr, word, L, lane)
+                       : warp_any_kmer_missing(v.k, rc ? v.kmer_bits_rc : v.kmer_bits, false, nullptr, word, L, lane);
+      } else {  // more than 32 packed words: windows from memory
+        const uint32_t* w = b.packed + b.word_off[strand >> 1];
+        missing = SMEM ? warp_any_kmer_missing(v.k, bits_f, rc, w, 0u, L, lane)
+                       : warp_any_kmer_missing(v.k, rc ? v.kmer_bits_rc : v.kmer_bits, false, w, 0u, L, lane);
+      }
       if (lane == 0) o.status[strand] = missing ? ST_MISSING_KMER : ST_NO_EXTENSION;
     }
   }
@@ -535,8 +592,15 @@ void launch_classify(const IndexView& v, const BatchView& b, const SearchOut& o,
                      cudaStream_t st) {
   uint32_t work = list ? n_list : 2 * (b.read_end - b.read_begin);
   if (work == 0) return;
-  uint32_t blocks = min((work + 255) / 256, 148u * 8u);  // 8 warps per CTA, 32 strands per warp round
-  classify_kernel<<<blocks, 256, 0, st>>>(v, b, o, list, n_list);
+  const uint64_t bits_words = ((1ull << (2 * v.k)) + 31) / 32;
+  const uint64_t bytes = ((bits_words + 3) / 4) * 16;
+  if (bytes <= kClassifySmemBytes && work >= 148u * 32u * 4u) {
+    cudaFuncSetAttribute(classify_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClassifySmemBytes);
+    classify_kernel<true><<<148, 1024, bytes, st>>>(v, b, o, list, n_list, (uint32_t)bits_words);
+  } else {
+    uint32_t blocks = min((work + 255) / 256, 148u * 8u);  // 8 warps per CTA, 32 strands per warp round
+    classify_kernel<false><<<blocks, 256, 0, st>>>(v, b, o, list, n_list, (uint32_t)bits_words);
+  }
 }
 
 // uint16 view of the accumulators for gq_coverage_fetch: allele_sum wraps mod 65536 (allele_sum.cpp:41),
