@@ -210,9 +210,6 @@ def main():
             reduce_counters()
 
     # ---------------- device-resident arm (`value`) ----------------
-    # the resident batch runs as two slices on two streams (kernels of one slice fill the latency-bound tails of
-    # the other's); per-kernel durations for the roofline come from a single-stream pass below
-    idx.set_option("resident_slices", 2)
     idx.upload(hb, ho, hs)
     for _ in range(args.warmup):
         step_resident()
@@ -230,6 +227,8 @@ def main():
         step_resident()
         ev[s][1].record(stream)
         info = idx.run_info()
+        search_ms += info["search_ms"]   # CUDA events inside the library, on the launching stream:
+        cov_ms += info["coverage_ms"]    # search phase / classify + coverage phase of this step
         launches += info["launches"] + (1 if counters is not None else 0)
         reruns += info["rerun_strands"]
     barrier()
@@ -240,23 +239,6 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
     a_sum, p_base, stats = idx.coverage()
-
-    # ---- kernel durations (roofline): the same batch, one slice on one stream, so that the search phase
-    # (seed + verify + text + general kernels) and the classify/coverage phase are bracketed by CUDA events
-    # inside the library (gq_last_run_info); L2 flushed before every pass ----
-    idx.set_option("resident_slices", 1)
-    k_steps = max(3, min(args.steps, 10))
-    single_ms = 0.0
-    for s in range(k_steps + 1):
-        flush.fill_(s & 0xFF)
-        torch.cuda.synchronize()
-        idx.map_resident()
-        info = idx.run_info()
-        if s:  # first pass warms the new configuration up
-            search_ms += info["search_ms"]
-            cov_ms += info["coverage_ms"]
-            single_ms += info["kernels_ms"]
-    search_ms, cov_ms, single_ms = (x * args.steps / k_steps for x in (search_ms, cov_ms, single_ms))
 
     # ---------------- end-to-end arm (`e2e`): host buffers in, counters out, every step -------------
     idx.reset_coverage()
@@ -302,10 +284,7 @@ def main():
             q_rank = evc["q_rank"] / evc["reads"]
             alg_bytes_per_read = 32.0 * q_rank + 2 * ((READ_LEN + 3) // 4) + 2 * ((READ_LEN - KMER + 1 + 7) // 8) + 16
         roof = None
-        kernels = {"search_ms": search_ms / args.steps, "classify_coverage_ms": cov_ms / args.steps,
-                   "single_stream_step_ms": single_ms / args.steps,
-                   "timing": "one slice on one stream (CUDA events in the library); the timed `value` region runs two "
-                             "slices on two streams"}
+        kernels = {"search_ms": search_ms / args.steps, "classify_coverage_ms": cov_ms / args.steps}
         if alg_bytes_per_read is not None:
             per_launch_s = (search_ms / args.steps) / 1e3
             achieved = alg_bytes_per_read * N_READS / per_launch_s / 1e9

@@ -139,11 +139,26 @@ __device__ __forceinline__ bool warp_any_kmer_missing(uint32_t k, const uint32_t
     if (j < n_kmers) {
       uint64_t win = (((uint64_t)hi << 32) | lo) >> sh;
       const uint32_t cnt = min(per, n_kmers - j);
-      for (uint32_t t = 0; t < cnt; ++t, win >>= 2) {
-        uint32_t code = (uint32_t)win & mask;
-        if (transform) code = pair_reverse32(~(uint32_t)win) >> (32 - 2 * k);
-        absent |= !((bits[code >> 5] >> (code & 31u)) & 1u);
+      uint32_t present = 1u;
+      if (transform) {
+        // reverse complement of the whole run (m = k + cnt - 1 bases) once: the reverse-complement code of the
+        // run's k-mer t is then the bit-field of R starting at pair cnt-1-t, so the run's codes are again
+        // consecutive windows (visited in the opposite order, which does not matter)
+        const uint64_t x = ~win;
+        uint64_t r = ((uint64_t)__brev((uint32_t)x) << 32) | __brev((uint32_t)(x >> 32));
+        r = ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);
+        r >>= 64 - 2 * (k + cnt - 1);
+        for (uint32_t t = 0; t < cnt; ++t, r >>= 2) {
+          const uint32_t code = (uint32_t)r & mask;
+          present &= bits[code >> 5] >> (code & 31u);
+        }
+      } else {
+        for (uint32_t t = 0; t < cnt; ++t, win >>= 2) {
+          const uint32_t code = (uint32_t)win & mask;
+          present &= bits[code >> 5] >> (code & 31u);
+        }
       }
+      absent = !(present & 1u);
     }
     missing = __any_sync(0xFFFFFFFFu, absent);
   }
