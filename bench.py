@@ -159,6 +159,11 @@ def main():
     from gramtools_b200 import QuasimapIndex
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    # stdout carries exactly one JSON line: anything libraries write to fd 1 (NCCL prints its version banner
+    # there) is sent to stderr, and the line goes to the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
@@ -313,7 +318,7 @@ def main():
                       "exact_mapped": stats.exact_mapped_reads_count, "rerun_strands": int(reruns),
                       "index_build_s": build_s},
         }
-        print(json.dumps(line))
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
