@@ -52,7 +52,8 @@ struct Node {        // flat coverage-graph node (reference: include/prg/coverag
   uint32_t edge_off; // into edges[]
   uint32_t n_edges;
   uint32_t cov_off;  // offset into the flat per-base counters; kNoAllele if the node holds none
-  uint32_t pad;
+  uint32_t next0;    // edges[edge_off] (target of the first edge), inline: most nodes have exactly one edge, and
+                     // the per-base traversal then needs one load per hop instead of two
 };
 
 struct KmerState {   // one seed SearchState (reference: kmer_index_types.hpp:24-27)

@@ -1404,7 +1404,7 @@ struct Trav {
         cur = kNoAllele;
         return;
       }
-      cur = v->edges[node().edge_off];
+      cur = node().next0;
       update_coordinates();
       const Node& nd = node();
       if (nd.allele != -1 && nd.site != 0) return;

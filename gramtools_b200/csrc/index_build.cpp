@@ -248,6 +248,7 @@ void build_graph(HostIndex& ix, std::vector<uint32_t>& hit_marker, std::vector<u
   for (size_t i = 0; i < ix.nodes.size(); ++i) {
     ix.nodes[i].edge_off = deg[i];
     ix.nodes[i].n_edges = deg[i + 1] - deg[i];
+    ix.nodes[i].next0 = deg[i + 1] > deg[i] ? ix.edges[deg[i]] : 0;
   }
   // target_map[even] CSR, allele_sum layout
   ix.tm_even_off.assign(S + 1, 0);
