@@ -82,6 +82,7 @@ def emu_lib():
         lib.emu_grouped.argtypes = [C.c_void_p, u32p]
         lib.emu_grouped.restype = C.c_uint64
         lib.emu_stats.argtypes = [C.c_void_p, u64p]
+        lib.emu_index_check.argtypes = [C.c_void_p]
         lib.emu_path_counters.argtypes = [u64p, C.c_int]
         lib.emu_force_general.argtypes = [C.c_int]
         lib.emu_counters_raw.argtypes = [C.c_void_p, u32p]
@@ -214,6 +215,10 @@ class Emu:
         c = np.zeros(32, dtype=np.uint64)
         self.lib.emu_path_counters(_ptr(c, C.c_uint64), int(reset))
         return {k: int(v) for k, v in zip(self.ROUTES, c) if k != "-"}
+
+    def index_check(self):
+        if self.lib.emu_index_check(self.h) != 0:
+            raise AssertionError(self.lib.emu_last_error().decode())
 
     def force_general(self, on):
         self.lib.emu_force_general(int(on))

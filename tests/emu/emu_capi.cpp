@@ -196,6 +196,84 @@ void emu_path_counters(uint64_t* out32, int reset) {
     if (reset) gq_emu_counters[i] = 0;
   }
 }
+// Structural invariants of the flat index (what the kernels assume about text mode, the seed view, ...),
+// checked directly on the host copy. Returns 0, or -1 with the first violation in emu_last_error().
+int emu_index_check(void* ev) {
+  auto* e = (Emu*)ev;
+  const HostIndex& h = e->h;
+  try {
+    auto fail = [](const std::string& m) { throw std::runtime_error("index invariant: " + m); };
+    const uint32_t L = (uint32_t)h.prg.size(), n = h.n;
+    if (n != L + 1 || h.sa.size() != n || h.isa.size() != n) fail("sizes");
+    for (uint32_t i = 0; i < n; ++i)
+      if (h.isa[h.sa[i]] != i) fail("isa[sa[i]] != i");
+    // text groups: codes, marker flags, relative marker ranks
+    uint32_t tm = 0, tsup = 0;
+    std::vector<uint32_t> text_rank(L, 0);
+    for (uint32_t q = 0; q < L; ++q) {
+      if ((q & ((1u << kTextSuperShift) - 1)) == 0) {
+        tsup = tm;
+        if (h.text_super[q >> kTextSuperShift] != tm) fail("text_super");
+      }
+      const TextGrp& g = h.text_grp[q >> 4];
+      if ((q & 15u) == 0 && (g.info >> 16) != tm - tsup) fail("relative marker rank");
+      const bool mk = h.prg[q] > 4;
+      if (((g.info >> (q & 15u)) & 1u) != (mk ? 1u : 0u)) fail("marker flag");
+      if (!mk && ((g.codes >> (2 * (q & 15u))) & 3u) != h.prg[q] - 1) fail("base code");
+      if (mk) text_rank[q] = tm++;
+    }
+    // jump records: BWT order and text order hold the same record for the same marker
+    uint32_t mr = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+      const uint32_t p = h.sa[i];
+      if (p == 0 || h.prg[p - 1] <= 4) continue;
+      for (int w = 0; w < 8; ++w)
+        if (h.marker_hit[8 * (size_t)mr + w] != h.tmarker_hit[8 * (size_t)text_rank[p - 1] + w]) fail("tmarker_hit");
+      const uint32_t jlo = h.marker_hit[8 * (size_t)mr + 2], jhi = h.marker_hit[8 * (size_t)mr + 3];
+      const uint32_t pj = h.marker_hit[8 * (size_t)mr + 6];
+      if (jlo != kNoAllele && jlo == jhi ? pj != h.sa[jlo] : pj != kNoAllele) fail("p_jump");
+      ++mr;
+    }
+    if (mr != tm) fail("marker count");
+    // seed view of the k-mer index
+    const uint64_t nk = 1ull << (2 * h.k);
+    if (h.seed_off.size() != nk + 1) fail("seed_off size");
+    for (uint64_t c = 0; c < nk; ++c) {
+      uint32_t ent = h.seed_off[c];
+      for (uint32_t j = h.kmer_off[c]; j < h.kmer_off[c + 1]; ++j) {
+        const KmerState& ks = h.kmer_states[j];
+        if (ks.hi - ks.lo + 1 > kSplitWidth) {
+          if (h.seed_ent[ent].key != ks.lo || h.seed_ent[ent].aux != ks.hi || h.seed_state[ent] != j) fail("wide seed entry");
+          ++ent;
+          continue;
+        }
+        for (uint32_t i = ks.lo; i <= ks.hi; ++i, ++ent) {
+          const KmerSeed& sd = h.seed_ent[ent];
+          if (!(sd.aux >> 31) || sd.key != h.sa[i] || h.seed_state[ent] != j) fail("suffix seed entry");
+          const uint32_t nctx = (sd.aux >> 24) & 0x7Fu, p = sd.key;
+          if (nctx > kSeedCtxBases || nctx > p) fail("context length");
+          for (uint32_t d = 0; d < nctx; ++d)
+            if (h.prg[p - 1 - d] > 4 || ((sd.aux >> (22 - 2 * d)) & 3u) != h.prg[p - 1 - d] - 1) fail("context base");
+          if (nctx < kSeedCtxBases && nctx < p && h.prg[p - 1 - nctx] <= 4) fail("context ends early");
+        }
+      }
+      if (ent != h.seed_off[c + 1]) fail("seed_off run length");
+      // presence sets
+      const bool present = h.kmer_off[c + 1] > h.kmer_off[c];
+      if ((((h.kmer_bits[c >> 5] >> (c & 31)) & 1u) != 0) != present) fail("kmer_bits");
+      uint64_t r = 0, x = ~c;
+      for (uint32_t i = 0; i < h.k; ++i) r |= ((x >> (2 * i)) & 3ull) << (2 * (h.k - 1 - i));
+      if ((((h.kmer_bits_rc[r >> 5] >> (r & 31)) & 1u) != 0) != present) fail("kmer_bits_rc");
+    }
+    for (const Node& nd : h.nodes)
+      if (nd.n_edges && nd.next0 != h.edges[nd.edge_off]) fail("next0");
+    return 0;
+  } catch (const std::exception& ex) {
+    g_err = ex.what();
+    return -1;
+  }
+}
+
 uint64_t emu_reruns(void* ev) { return ((Emu*)ev)->reruns; }
 void emu_status(void* ev, uint8_t* out) {
   auto* e = (Emu*)ev;

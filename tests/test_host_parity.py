@@ -229,3 +229,13 @@ def test_frequent_kmers_wide_seed_intervals(shape):
     r = e.routes()
     assert_parity(e.result(), o.result(), f"wide{shape}")
     assert r["fast_finished"] > 2 * r["general"] and r["too_wide"] == 0, r
+
+
+def test_flat_index_invariants():
+    """Text groups, inverse SA, text-order jump records, the seed view (per-suffix entries with left context),
+    the reverse-complement presence set and the inline first edge: checked structurally on SNP, nested, indel and
+    frequent-k-mer PRGs (k-mers with more than kSplitWidth occurrences keep an interval entry)."""
+    for prg, k in ((synth.make_snp_prg(3000, 200, 5)[0], 6), (synth.make_nested_prg(6, 300, 5), 5),
+                   (synth.make_indel_prg(3000, 150, 5), 6), (synth.make_snp_prg(60000, 100, 2)[0], 3),
+                   (np.asarray([1, 2, 3, 4, 5, 1, 6, 2, 6, 3, 3, 7, 4, 8, 8, 1], dtype=np.uint32), 2)):
+        Emu(prg, k).index_check()
