@@ -687,21 +687,21 @@ GQ_DEV inline void lane_event(Lane& ln, const IndexView& v, const SearchOut& o) 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Seed pass. For one strand: look up the seeding k-mer (quasimap.cpp:178,235-241); each of its seed states
-// is SPLIT into its suffixes (in the index itself for states of up to kSplitWidth suffixes; wider ones are
-// first narrowed by rank steps): every
-// occurrence becomes a width-1 state of its own — a candidate — that the text kernel walks through the PRG
-// text. Splitting is exact: a SearchState's interval is a set of suffixes that the reference advances in
-// lock-step (one LF step per suffix, one jump per marker-preceded suffix, vBWT_jump.cpp:94-117); walking
-// them one by one visits the same (suffix, path) pairs. Only the grouping of the final states can differ —
-// two suffixes of one state that both survive to the end of the read stay ONE state in the reference — so
-// a strand with more than one finished candidate is handed to the general search kernel, which redoes it
-// with interval states. False candidates (a 10-mer has several occurrences, one of them real) die within
-// a step or two of the text walk.
+// Seed pass. For one strand: look up the seeding k-mer (quasimap.cpp:178,235-241); each of its seed states is
+// SPLIT into its suffixes — in the index itself (seed view, KmerSeed) for states of up to kSplitWidth suffixes,
+// after narrowing by rank steps for wider ones: every occurrence becomes a width-1 state of its own — a
+// candidate — that the text kernel walks through the PRG text. Splitting is exact: a SearchState's interval is
+// a set of suffixes that the reference advances in lock-step (one LF step per suffix, one jump per
+// marker-preceded suffix, vBWT_jump.cpp:94-117); walking them one by one visits the same (suffix, path) pairs.
+// Only the grouping of the final states can differ — two suffixes of one state that both survive to the end
+// of the read stay ONE state in the reference — so a strand with more than one finished candidate is handed
+// to the general search kernel, which redoes it with interval states. False candidates (a 10-mer has several
+// occurrences, one of them real) are rejected against their left context here, or within a step or two of
+// the text walk (verify pass).
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t kPreSteps = 8;     // rank steps at most, while the interval is wide
 constexpr uint32_t kNarrowWidth = 4;  // stop narrowing at this many suffixes
-constexpr uint32_t kMaxSplit = 32;   // wider than this after narrowing: general kernel
+constexpr uint32_t kMaxSplit = 32;    // wider than this after narrowing: general kernel
 
 // part 1: k-mer lookup. Returns the number of seed entries (0: the strand is already classified).
 GQ_DEV inline uint32_t preseed_lookup(const IndexView& v, const BatchView& b, const SearchOut& o, uint32_t strand,

@@ -39,10 +39,11 @@ struct SearchOut {
   uint32_t* listed;         // per strand flags (SeedOut::surv_cnt) or nullptr: kSurvListed = already on mapped_list
 };
 
-// Output of the seed pass (seed_kernel): one candidate per suffix of every (narrowed) seed state — a width-1
-// search state the text kernel walks through the PRG text — plus the strands that need the general kernel.
+// Output of the seed pass (seed_kernel): one candidate per suffix of a seed state that agrees with the read on
+// its left context — a width-1 search state the text kernel walks through the PRG text — plus the strands that
+// need the general kernel.
 struct SeedOut {
-  uint32_t* rec;        // 4 words per candidate: {strand, k-mer state index, SA index, pos | kind << 28}
+  uint32_t* rec;        // 4 words per candidate: {strand, k-mer state index, text position, pos | kind << 28}
   uint32_t cap;         // candidate records available
   uint32_t* n_surv;     // bump pointer
   uint32_t* surv_cnt;   // per strand: finished candidates (low 16 bits) | kSurvGeneral | kSurvListed
