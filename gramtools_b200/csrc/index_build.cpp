@@ -523,7 +523,7 @@ void build_kmers(HostIndex& ix) {
   const uint32_t k = ix.k;
   if (k < 1 || k > 14) throw std::runtime_error("kmer_size must be in [1,14]");  // command_setup.py:97-99
   const uint64_t nk = 1ull << (2 * k);
-  ix.kmer_bits.assign((nk + 31) / 32, 0);
+  ix.kmer_bits.assign((((nk + 31) / 32) + 3) & ~3ull, 0);  // whole 16-byte groups: copied to shared memory as uint4
   ix.kmer_off.assign(nk + 1, 0);
   IndexView v = ix.view();
   // independent subtrees: the first min(k,2) bases (rightmost of the k-mer)

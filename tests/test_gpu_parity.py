@@ -235,3 +235,14 @@ def test_frequent_kmers_wide_seed_intervals(built_lib):
     prg = synth.make_snp_prg(300000, 300, 7)[0]  # ~1200 occurrences per 4-mer: narrowed with rank steps
     bases, offs = _reads_for(prg, 3000, 50, 5, garbage=0.02, n_frac=0.0)
     _check(prg, 4, bases, offs, what="very-wide-seeds", threads=os.cpu_count())
+
+
+def test_long_reads(built_lib):
+    """Reads of more than 512 bases (more than 32 packed words): the classify kernel then takes its k-mer windows
+    from memory instead of the lanes' registers; long walks, many sites per read."""
+    prg = synth.make_snp_prg(30000, 1200, 21)[0]
+    bases, offs = _reads_for(prg, 1500, 700, 21, garbage=0.3, n_frac=0.0)
+    got, ref = _check(prg, 8, bases, offs, what="long-reads-k8", threads=os.cpu_count())
+    assert ref.stats[2] > 0 and ref.stats[4] > 500  # unmappable strands miss a k-mer (8-mers are sparse here)
+    got, ref = _check(prg, 6, bases, offs, what="long-reads-k6", threads=os.cpu_count())
+    assert ref.stats[3] > 0 and ref.stats[4] > 500  # every 6-mer occurs: the whole strand is probed, no extension

@@ -239,3 +239,10 @@ def test_flat_index_invariants():
                    (synth.make_indel_prg(3000, 150, 5), 6), (synth.make_snp_prg(60000, 100, 2)[0], 3),
                    (np.asarray([1, 2, 3, 4, 5, 1, 6, 2, 6, 3, 3, 7, 4, 8, 8, 1], dtype=np.uint32), 2)):
         Emu(prg, k).index_check()
+
+
+def test_long_reads_host():
+    prg = synth.make_snp_prg(30000, 1200, 21)[0]
+    bases, offs = _reads_for(prg, 300, 700, 21, garbage=0.3, n_frac=0.0)
+    ro, _ = _check(prg, 8, bases, offs, what="long-reads")
+    assert ro.stats[4] > 100
