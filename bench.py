@@ -27,8 +27,8 @@ REF_LEN, N_SITES, N_READS, READ_LEN, KMER = 4_400_000, 100_000, 1_000_000, 150, 
 GEN_SEED = 0x6772616D + 2
 MAP_SEED = 42
 # ncu --set full, config 2, 1M reads, dram__bytes_read.sum + dram__bytes_write.sum summed over seed_kernel,
-# verify_kernel, text_kernel and search_kernel (profiles/r01_v12_kernels_summary.txt)
-SEARCH_PHASE_DRAM_BYTES = 187654656 + 29486336 + 90777856 + 5580032 + 336938496 + 96582656 + 66048
+# verify_kernel, text_kernel and search_kernel (profiles/r01_v13_kernels_summary.txt)
+SEARCH_PHASE_DRAM_BYTES = 187977728 + 30433280 + 90977280 + 6275584 + 335387136 + 97702912 + 66304
 
 
 def env_int(name, default):
