@@ -156,6 +156,14 @@ int emu_map(void* ev, const uint8_t* bases, const uint64_t* off, uint64_t n_read
         map_strand(v, v.super_cnt, b, o, pre, s, a, aw);
         if (e->status[s] != ST_OVERFLOW) break;
         e->reruns++;
+        if (small[0] > e->pool.size()) {  // the final-state pool ran out (libgq grows it the same way): redo the strand
+          const size_t used = std::min<size_t>(e->pool.size(), small[0]);
+          e->pool.resize(std::max<size_t>(2 * e->pool.size(), 2 * (size_t)small[0]), 0);
+          small[0] = (uint32_t)used;
+          o.pool = e->pool.data();
+          o.pool_cap = (uint32_t)e->pool.size();
+          continue;
+        }
         aw *= 4;
         if (aw > (1u << 28)) throw std::runtime_error("emu: arena overflow persists");
         big.assign(aw, 0);

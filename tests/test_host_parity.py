@@ -246,3 +246,37 @@ def test_long_reads_host():
     bases, offs = _reads_for(prg, 300, 700, 21, garbage=0.3, n_frac=0.0)
     ro, _ = _check(prg, 8, bases, offs, what="long-reads")
     assert ro.stats[4] > 100
+
+
+def test_random_shapes():
+    """Seeded sweep over random PRG shapes (isolated SNPs, nested bracket grammar, indels, duplicated segments),
+    k in 2..7, read lengths from k to 90 (so reads with L == k and reads shorter than the walk buffers both occur),
+    1 % substitution errors in a third of the cases, arenas down to 64 words: emulation == oracle, and the flat
+    index passes its structural checks. (3000 cases of this sweep were run when the text-mode route was written;
+    60 are kept here.)"""
+    for case in range(60):
+        rng = np.random.default_rng(1000 + case)
+        kind = case % 4
+        if kind == 0:
+            prg = synth.make_snp_prg(int(rng.integers(300, 4000)), int(rng.integers(10, 300)), case)[0]
+        elif kind == 1:
+            prg = synth.make_nested_prg(int(rng.integers(1, 6)), int(rng.integers(100, 400)), case)
+        elif kind == 2:
+            prg = synth.make_indel_prg(int(rng.integers(500, 4000)), int(rng.integers(10, 200)), case)
+        else:
+            base = rng.integers(1, 5, int(rng.integers(200, 1500))).astype(np.uint32)
+            u = base[10:10 + int(rng.integers(30, 150))]
+            prg = np.concatenate([base, u, rng.integers(1, 5, 100).astype(np.uint32), u, base[:50]]).astype(np.uint32)
+        k = int(rng.integers(2, 8))
+        L = int(rng.integers(k, 90))
+        bases, offs = _reads_for(prg, 300, L, case, garbage=0.05, n_frac=0.01)
+        if float(rng.choice([0.0, 0.0, 0.01])) > 0:
+            bases = bases.copy()
+            hit = rng.random(bases.size) < 0.01
+            bases[hit] = rng.integers(1, 5, int(hit.sum()))
+        seeds = master_seeds(int(rng.integers(0, 1000)), offs.size - 1)
+        o, e = Oracle(prg, k), Emu(prg, k)
+        e.index_check()
+        o.map(bases, offs, seeds)
+        e.map(bases, offs, seeds, arena_words=int(rng.choice([64, 256, 1024])))
+        assert_parity(e.result(), o.result(), f"random-shape-{case}")
