@@ -280,7 +280,7 @@ static void do_map(gq_index* ix, const uint8_t* h_bases = nullptr, const uint64_
   ix->st_off.reserve(2 * (size_t)n);
   ix->st_words.reserve(2 * (size_t)n);
   ix->st_count.reserve(2 * (size_t)n);
-  ix->overflow_list.reserve(2 * (size_t)n);
+  ix->overflow_list.reserve(4 * (size_t)n + 16);  // a strand can be flagged by the text kernel and again by the general one
   ix->cov_overflow_list.reserve(2 * (size_t)n);
   ix->mapped_list.reserve(2 * (size_t)n);
   ix->small.reserve(8 + 5 * 64);

@@ -378,45 +378,42 @@ __global__ void __launch_bounds__(256) text_kernel(IndexView v, BatchView b, Sea
       if (fast_running(f) && f.ln.state == LS_TEXT) lane_text_step(f.ln, v);
       if (fast_running(f) && f.ln.state == LS_EV_TSCAN) fast_event<true>(f, v);
     }
-    const uint32_t words = i < n ? fast_outcome(f, v) : 0;
+    uint32_t words = i < n ? fast_outcome(f, v) : 0;
     const uint32_t strand = f.ln.strand;
-    const bool finished = f.result == FAST_MAPPED;
-    // The three allocations of the round are issued together, for every finished candidate: its strand claim
-    // (a second finished candidate makes the strand the general kernel's), pool space (warp scan + one
-    // atomic) and mapped-list slots (one atomic). A candidate that loses its claim leaves its pool words
-    // unused and kNoAllele in its list slot (coverage_kernel skips it).
-    uint32_t incl = words;
+    if (f.result == FAST_BAIL) send_to_general(pre, strand);
+    // A finished candidate claims its strand; a second one (reads in repeats) makes the strand the general
+    // kernel's. Only claim winners take pool space and a mapped-list slot: a strand can have many finished
+    // candidates, the list holds one entry per strand.
+    bool emit = f.result == FAST_MAPPED && fast_claim(pre, strand);
+    if (!emit) words = 0;
+    uint32_t incl = words;  // pool space for the round: warp scan + one atomic
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       uint32_t t = __shfl_up_sync(full, incl, d);
       if (lane >= (uint32_t)d) incl += t;
     }
     const uint32_t total = __shfl_sync(full, incl, 31);
-    const uint32_t mm = __ballot_sync(full, finished);
-    uint32_t base = 0, mbase = 0, claim = 0;
+    uint32_t base = 0;
     if (total && lane == 31) base = atomicAdd(o.pool_used, total);
-    if (mm && lane == 0) mbase = atomicAdd(o.n_mapped, (uint32_t)__popc(mm));
-    if (finished) claim = atomicAdd(pre.surv_cnt + strand, 1u);
-    if (f.result == FAST_BAIL) send_to_general(pre, strand);
     base = __shfl_sync(full, base, 31);
-    mbase = __shfl_sync(full, mbase, 0);
-    if (finished) {
-      uint32_t listed = kNoAllele;
+    if (emit) {
       const uint32_t off = base + incl - words;
-      if (claim & kSurvGeneral) {
-        // already the general kernel's
-      } else if (claim & 0xFFFFu) {
-        send_to_general(pre, strand);  // several finished candidates (a repeat)
-      } else if (off + words > o.pool_cap) {  // final-state pool full: re-run after the host has grown it
+      if (off + words > o.pool_cap) {  // final-state pool full: re-run after the host has grown it
         o.status[strand] = ST_OVERFLOW;
         o.overflow_list[atomicAdd(o.n_overflow, 1u)] = strand;
+        emit = false;
       } else {
         fast_emit(f, v, o, off);
         o.status[strand] = ST_MAPPED;
         atomicOr(pre.surv_cnt + strand, kSurvListed);
-        listed = strand;
       }
-      o.mapped_list[mbase + __popc(mm & ((1u << lane) - 1u))] = listed;
+    }
+    const uint32_t mm = __ballot_sync(full, emit);
+    if (mm) {
+      uint32_t mbase = 0;
+      if (lane == 0) mbase = atomicAdd(o.n_mapped, (uint32_t)__popc(mm));
+      mbase = __shfl_sync(full, mbase, 0);
+      if (emit) o.mapped_list[mbase + __popc(mm & ((1u << lane) - 1u))] = strand;
     }
   }
 }

@@ -246,3 +246,31 @@ def test_long_reads(built_lib):
     assert ref.stats[2] > 0 and ref.stats[4] > 500  # unmappable strands miss a k-mer (8-mers are sparse here)
     got, ref = _check(prg, 6, bases, offs, what="long-reads-k6", threads=os.cpu_count())
     assert ref.stats[3] > 0 and ref.stats[4] > 500  # every 6-mer occurs: the whole strand is probed, no extension
+
+
+def test_random_shapes_gpu(built_lib):
+    """The seeded sweep of tests/test_host_parity.py::test_random_shapes through libgq (first 24 cases; case 7 —
+    3-base reads, k = 2, a PRG with duplicated segments — has dozens of finished candidates per strand and once
+    overran the per-strand coverage work list). tools/gpu_fuzz.py runs more cases."""
+    for case in range(24):
+        rng = np.random.default_rng(1000 + case)
+        kind = case % 4
+        if kind == 0:
+            prg = synth.make_snp_prg(int(rng.integers(300, 4000)), int(rng.integers(10, 300)), case)[0]
+        elif kind == 1:
+            prg = synth.make_nested_prg(int(rng.integers(1, 6)), int(rng.integers(100, 400)), case)
+        elif kind == 2:
+            prg = synth.make_indel_prg(int(rng.integers(500, 4000)), int(rng.integers(10, 200)), case)
+        else:
+            base = rng.integers(1, 5, int(rng.integers(200, 1500))).astype(np.uint32)
+            u = base[10:10 + int(rng.integers(30, 150))]
+            prg = np.concatenate([base, u, rng.integers(1, 5, 100).astype(np.uint32), u, base[:50]]).astype(np.uint32)
+        k = int(rng.integers(2, 8))
+        L = int(rng.integers(k, 90))
+        bases, offs = _reads_for(prg, 300, L, case, garbage=0.05, n_frac=0.01)
+        if float(rng.choice([0.0, 0.0, 0.01])) > 0:
+            bases = bases.copy()
+            hit = rng.random(bases.size) < 0.01
+            bases[hit] = rng.integers(1, 5, int(hit.sum()))
+        _check(prg, k, bases, offs, seed=int(rng.integers(0, 1000)), what=f"random-shape-{case}",
+               options={"arena_words": int(rng.choice([64, 256, 1024]))})
