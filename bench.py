@@ -237,7 +237,6 @@ def main():
         launches += info["launches"] + (1 if counters is not None else 0)
         reruns += info["rerun_strands"]
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
     if world > 1:
         t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
@@ -260,6 +259,7 @@ def main():
         d2h = (a_sum.size + p_base.size) * 2 + 40 + 24  # uint16 vectors + counters + the call's status words
     torch.cuda.synchronize()
     e2e_ms = 1e3 * (time.perf_counter() - t0)
+    clocks = sampler.stop() if rank == 0 else None  # sampled over both timed regions (resident + end to end)
     if world > 1:
         t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
