@@ -1570,7 +1570,8 @@ GQ_DEV bool record_strand(const IndexView& v, const BatchView& b, const SearchOu
     }
   }
   uint32_t* key_off = sc.alloc(2 * ns);  // (offset, len) per state; len = 0xFFFFFFFF for path-less
-  if (!key_off) return false;
+  uint32_t* rep = sc.alloc(ns);          // class representative per state
+  if (!key_off || !rep) return false;
   const uint32_t cap = (arena_words - sc.used) / 16;  // list capacities derive from the arena size
   LocusLists ll;
   ll.cap = cap;
@@ -1600,39 +1601,35 @@ GQ_DEV bool record_strand(const IndexView& v, const BatchView& b, const SearchOu
       key_off[2 * j + 1] = ll.n_base;
     }
   }
-  // number of distinct classes, and for the first state of each class its rank among classes
+  // class representative of every state with a path = the first state with the same key (compared with the
+  // representatives found so far only), and the number of distinct classes
   uint32_t ncls = 0;
   for (uint32_t j = 0; j < ns; ++j) {
+    rep[j] = 0xFFFFFFFFu;
     if (key_off[2 * j + 1] == 0xFFFFFFFFu) continue;
-    bool dup = false;
-    for (uint32_t i = 0; i < j && !dup; ++i)
-      dup = key_off[2 * i + 1] != 0xFFFFFFFFu && cmp_key(arena + key_off[2 * i], key_off[2 * i + 1],
-                                                          arena + key_off[2 * j], key_off[2 * j + 1]) == 0;
-    if (!dup) ++ncls;
+    rep[j] = j;
+    for (uint32_t i = 0; i < j; ++i)
+      if (rep[i] == i && cmp_key(arena + key_off[2 * i], key_off[2 * i + 1], arena + key_off[2 * j], key_off[2 * j + 1]) == 0) {
+        rep[j] = i;
+        break;
+      }
+    if (rep[j] == j) ++ncls;
   }
   // random_select_entry :97-107
   uint32_t total = nonvar + ncls;
   uint32_t pick = total == 1 ? 1u : uniform_1_to(b.seeds[strand >> 1], total);
   if (pick <= nonvar) return true;
+  // the (pick - nonvar - 1)-th class in std::map order: the representative with that many smaller ones
   uint32_t want = pick - nonvar - 1;
   int chosen = -1;
   for (uint32_t j = 0; j < ns && chosen < 0; ++j) {
-    if (key_off[2 * j + 1] == 0xFFFFFFFFu) continue;
-    bool dup = false;
+    if (rep[j] != j) continue;
     uint32_t less = 0;
-    for (uint32_t i = 0; i < ns; ++i) {
-      if (i == j || key_off[2 * i + 1] == 0xFFFFFFFFu) continue;
-      int cm = cmp_key(arena + key_off[2 * i], key_off[2 * i + 1], arena + key_off[2 * j], key_off[2 * j + 1]);
-      if (cm == 0 && i < j) dup = true;
-      if (cm < 0) {  // count distinct smaller keys: only the first occurrence of each
-        bool first_occ = true;
-        for (uint32_t h = 0; h < i && first_occ; ++h)
-          first_occ = !(key_off[2 * h + 1] != 0xFFFFFFFFu &&
-                        cmp_key(arena + key_off[2 * h], key_off[2 * h + 1], arena + key_off[2 * i], key_off[2 * i + 1]) == 0);
-        if (first_occ) ++less;
-      }
-    }
-    if (!dup && less == want) chosen = (int)j;
+    for (uint32_t i = 0; i < ns; ++i)
+      if (i != j && rep[i] == i &&
+          cmp_key(arena + key_off[2 * i], key_off[2 * i + 1], arena + key_off[2 * j], key_off[2 * j + 1]) < 0)
+        ++less;
+    if (less == want) chosen = (int)j;
   }
   if (chosen < 0) {
     gq_atomic_or(c.error_flags, 2u);
@@ -1645,15 +1642,12 @@ GQ_DEV bool record_strand(const IndexView& v, const BatchView& b, const SearchOu
   hull.e = arena + sc.used;
   hull.n = 0;
   hull.overflow = false;
-  const uint32_t* ck = arena + key_off[2 * chosen];
-  const uint32_t cn = key_off[2 * chosen + 1];
   {
     const uint32_t* p = recs;
     for (uint32_t j = 0; j < ns; ++j) {
       StateRec st = parse_rec(p);
       p += st.words();
-      if (key_off[2 * j + 1] == 0xFFFFFFFFu) continue;
-      if (cmp_key(arena + key_off[2 * j], key_off[2 * j + 1], ck, cn) != 0) continue;
+      if (rep[j] != (uint32_t)chosen) continue;  // not a state of the chosen class (or path-less)
       ll.n_base = 0;
       locus_finder(v, st, ll);  // loci accumulate across the class (set union)
       if (ll.overflow) return false;
