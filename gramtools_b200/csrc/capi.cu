@@ -212,11 +212,16 @@ static void reserve_batch(gq_index* ix, uint64_t n_reads, uint64_t nb) {
 struct Chunk {
   uint32_t r0, r1;
 };
+constexpr size_t kMaxChunks = 64;  // per-slice counters live in fixed slots of `small`
+
+extern "C" {
+static void grow_groups(gq_index* ix);
+}
 
 static std::vector<Chunk> make_chunks(gq_index* ix, uint32_t n, bool pipelined) {
   std::vector<Chunk> ch;
   if (!pipelined) {  // resident batch: equal slices (alternating between the two compute streams)
-    const uint32_t k = std::max<uint32_t>(1, std::min<uint32_t>(ix->resident_slices, (n + 65535) / 65536));
+    const uint32_t k = std::max<uint32_t>(1, std::min<uint32_t>(std::min<uint32_t>(ix->resident_slices, (uint32_t)kMaxChunks), (n + 65535) / 65536));
     const uint32_t per = (n + k - 1) / k;
     for (uint32_t r = 0; r < n; r += per) ch.push_back({r, std::min(n, r + per)});
     return ch;
@@ -227,6 +232,7 @@ static std::vector<Chunk> make_chunks(gq_index* ix, uint32_t n, bool pipelined) 
   for (uint32_t r = 0; r < n;) {
     uint32_t left = n - r;
     uint32_t per = left <= small ? left : std::max(small, std::min(big, left / 2));
+    if (ch.size() + 1 == kMaxChunks) per = left;  // (only with extreme chunk options) the last slot takes the rest
     ch.push_back({r, r + per});
     r += per;
   }
@@ -283,7 +289,7 @@ static void do_map(gq_index* ix, const uint8_t* h_bases = nullptr, const uint64_
   ix->overflow_list.reserve(4 * (size_t)n + 16);  // a strand can be flagged by the text kernel and again by the general one
   ix->cov_overflow_list.reserve(2 * (size_t)n);
   ix->mapped_list.reserve(2 * (size_t)n);
-  ix->small.reserve(8 + 5 * 64);
+  ix->small.reserve(8 + 5 * kMaxChunks);
   ix->surv_cnt.reserve(2 * (size_t)n);
   ix->gen_list.reserve(2 * (size_t)n);
   ix->seed_rec.reserve(4 * std::max<size_t>((size_t)n * ix->seed_recs_per_read, 1 << 16));
@@ -300,7 +306,7 @@ static void do_map(gq_index* ix, const uint8_t* h_bases = nullptr, const uint64_
   ix->arena.reserve((size_t)std::max(threads, threads2) * ix->arena_words);
   // small: [0] pool_used [1] n_overflow [2] n_cov_overflow;
   // per chunk c: [8+4c] n_mapped [9+4c] work counter [10+4c] survivor records [11+4c] n_gen (general-kernel work list)
-  CUDA_OK(cudaMemsetAsync(ix->small.p, 0, (8 + 5 * 64) * 4, st));
+  CUDA_OK(cudaMemsetAsync(ix->small.p, 0, (8 + 5 * kMaxChunks) * 4, st));
 
   gq::BatchView b{ix->packed.p, ix->word_off.p, ix->len.p, ix->seeds.p, n, 0, n};
   gq::SearchOut o{ix->status.p, ix->st_off.p, ix->st_words.p, ix->st_count.p, ix->pool.p, (uint32_t)ix->pool.cap,
@@ -361,11 +367,11 @@ static void do_map(gq_index* ix, const uint8_t* h_bases = nullptr, const uint64_
       uint32_t* gen_list = ix->gen_list.p + 2 * (size_t)chunks[i].r0;
       uint32_t* n_gen = ix->small.p + 11 + 4 * i;
       gq::SeedOut pre{ix->seed_rec.p + 4 * (size_t)ix->seed_recs_per_read * chunks[i].r0,
-                      (uint32_t)(ix->seed_recs_per_read * (chunks[i].r1 - chunks[i].r0)),
+                      (uint32_t)std::min<uint64_t>((uint64_t)ix->seed_recs_per_read * (chunks[i].r1 - chunks[i].r0), 0x3FFFFFFFull),
                       ix->small.p + 10 + 4 * i, ix->surv_cnt.p, gen_list, n_gen};
       gq::launch_seed(ix->dv, bc, oc, pre, cs);
       gq::launch_text(ix->dv, bc, oc, pre, ix->surv_rec.p + 4 * (size_t)ix->seed_recs_per_read * chunks[i].r0,
-                      ix->small.p + 8 + 4 * 64 + i, cs);
+                      ix->small.p + 8 + 4 * kMaxChunks + i, cs);
       ++launches;
       gq::launch_search(ix->dv, bc, oc, arena, ix->arena_words, threads, gen_list,
                         2 * (chunks[i].r1 - chunks[i].r0), ix->super_in_smem, ix->rf_thresh, ix->ev_thresh, cs,
@@ -460,10 +466,18 @@ static void do_map(gq_index* ix, const uint8_t* h_bases = nullptr, const uint64_
       ix->big_arena.reserve((size_t)bt * big_words);
       ar = ix->big_arena.p;
     }
-    // the kernel appends to the same list while reading it: read from a copy
+    // The kernel appends to the same list while reading it: read from a copy. A strand can be on the list twice
+    // (flagged by the text kernel when the pool filled up, and again by the general kernel that took it over):
+    // the copy holds every strand once, so no strand is mapped by two lanes or recorded twice.
+    std::vector<uint32_t> hl(n_list);
+    CUDA_OK(cudaMemcpyAsync(hl.data(), ix->overflow_list.p, (size_t)n_list * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    std::sort(hl.begin(), hl.end());
+    hl.erase(std::unique(hl.begin(), hl.end()), hl.end());
+    n_list = (uint32_t)hl.size();
     DevBuf<uint32_t> list;
     list.reserve(n_list);
-    CUDA_OK(cudaMemcpyAsync(list.p, ix->overflow_list.p, (size_t)n_list * 4, cudaMemcpyDeviceToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(list.p, hl.data(), (size_t)n_list * 4, cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaMemsetAsync(ix->small.p + 1, 0, 4, st));
     CUDA_OK(cudaMemsetAsync(ix->small.p + 9, 0, 4, st));  // work counter of the list run
     gq::launch_search(ix->dv, b, o, ar, aw, bt, list.p, n_list, ix->super_in_smem, ix->rf_thresh, ix->ev_thresh, st,
@@ -486,7 +500,16 @@ static void do_map(gq_index* ix, const uint8_t* h_bases = nullptr, const uint64_
   while (small[2] > 0) {
     uint32_t n_list = small[2];
     rerun += n_list;
-    if (++guard > 12) throw std::runtime_error("coverage scratch overflow persists at the largest arena size");
+    if (++guard > 16) throw std::runtime_error("coverage scratch overflow persists at the largest arena size");
+    // strands given back because the multi-allele group table (or its record pool) was full: grow it first
+    uint32_t gs0[2];
+    CUDA_OK(cudaMemcpyAsync(gs0, ix->gsmall.p, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    const bool grouped_full = (gs0[1] & 1u) != 0;
+    if (grouped_full) {
+      grow_groups(ix);  // clears the "full" flag, keeps the others
+      c = cov_view(ix);
+    }
     uint32_t bt = std::min<uint32_t>(big_threads, ((n_list + 255) / 256) * 256);
     ix->big_arena.reserve((size_t)bt * big_words);
     DevBuf<uint32_t> list;
@@ -500,7 +523,7 @@ static void do_map(gq_index* ix, const uint8_t* h_bases = nullptr, const uint64_
     CUDA_OK(cudaStreamSynchronize(st));
     CUDA_OK(cudaGetLastError());
     list.release();
-    if (small[2] > 0) {
+    if (small[2] > 0 && !grouped_full) {
       big_words *= 4;
       big_threads = std::max<uint32_t>(256, big_threads / 4);
     }
@@ -511,7 +534,7 @@ static void do_map(gq_index* ix, const uint8_t* h_bases = nullptr, const uint64_
   CUDA_OK(cudaMemcpyAsync(gs, ix->gsmall.p, 8, cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaStreamSynchronize(st));
   CUDA_OK(cudaGetLastError());
-  if (gs[1] & 1u) throw std::runtime_error("grouped allele count table is full");
+  if (gs[1] & 1u) throw std::runtime_error("grouped allele count table is full (internal error: flagged strands were not re-run)");
   if (gs[1] & 2u) throw std::runtime_error("inconsistent traversal while recording per-base coverage");
   ix->info[0] = launches;
   ix->info[1] = (double)rerun;
@@ -853,6 +876,59 @@ int gq_coverage_groups_export(gq_index* ix, uint32_t* words, uint64_t* n_words) 
   GQ_CATCH
 }
 
+// Rebuild the multi-allele group table + record pool from `g` on the host (with the device's hash) and upload
+// them, growing both so that the table is at most a quarter full. Drops leaked / never-counted records.
+static uint32_t hash_group_host(const std::vector<uint32_t>& key) {
+  uint32_t hsh = 2166136261u ^ key[0];
+  hsh *= 16777619u;
+  for (size_t i = 1; i < key.size(); ++i) {
+    hsh ^= key[i];
+    hsh *= 16777619u;
+  }
+  hsh ^= hsh >> 15;
+  return hsh;
+}
+
+static void rebuild_groups(gq_index* ix, const std::map<std::vector<uint32_t>, uint64_t>& g, size_t min_cap) {
+  size_t pool_words = 0;
+  for (auto& e : g) pool_words += e.first.size() + 1;
+  size_t cap = std::max<size_t>(ix->gtab.cap, min_cap);
+  while (cap < 4 * g.size()) cap <<= 1;
+  if (cap > (1u << 30)) throw std::runtime_error("grouped allele count table exceeds 2^30 slots");
+  const size_t pool_cap = std::max<size_t>(std::max<size_t>(ix->gpool.cap, cap * 4), 2 * pool_words);
+  if (pool_cap >= 0xFFFFFFF0ull) throw std::runtime_error("grouped allele count pool exceeds 2^32 words");
+  ix->gtab.reserve(cap);
+  ix->gcount.reserve(cap);
+  ix->gpool.reserve(pool_cap);
+  std::vector<uint32_t> tab(ix->gtab.cap, 0), cnt(ix->gtab.cap, 0), pool;
+  pool.reserve(pool_words);
+  const uint32_t maskc = (uint32_t)ix->gtab.cap - 1;
+  for (auto& e : g) {
+    uint32_t hsh = hash_group_host(e.first) & maskc;
+    while (tab[hsh]) hsh = (hsh + 1) & maskc;  // terminates: the table is at most a quarter full
+    tab[hsh] = (uint32_t)pool.size() + 1;
+    cnt[hsh] = (uint32_t)e.second;
+    pool.push_back(e.first[0]);
+    pool.push_back((uint32_t)e.first.size() - 1);
+    pool.insert(pool.end(), e.first.begin() + 1, e.first.end());
+  }
+  CUDA_OK(cudaMemcpy(ix->gtab.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(ix->gcount.p, cnt.data(), cnt.size() * 4, cudaMemcpyHostToDevice));
+  if (!pool.empty()) CUDA_OK(cudaMemcpy(ix->gpool.p, pool.data(), pool.size() * 4, cudaMemcpyHostToDevice));
+  uint32_t gs[2];
+  CUDA_OK(cudaMemcpy(gs, ix->gsmall.p, 8, cudaMemcpyDeviceToHost));
+  gs[0] = (uint32_t)pool.size();  // pool bump pointer
+  gs[1] &= ~1u;                   // "table / pool full" is settled; other error flags stay
+  CUDA_OK(cudaMemcpy(ix->gsmall.p, gs, 8, cudaMemcpyHostToDevice));
+}
+
+// the group table or its pool filled up during a batch (flagged strands were given back uncommitted): 4x larger
+static void grow_groups(gq_index* ix) {
+  std::map<std::vector<uint32_t>, uint64_t> g;
+  collect_groups(ix, g, true);
+  rebuild_groups(ix, g, ix->gtab.cap * 4);
+}
+
 int gq_coverage_groups_import(gq_index* ix, const uint32_t* words, uint64_t n_words, int replace) {
   GQ_TRY
   if (!ix || (n_words && !words)) throw std::runtime_error("null argument");
@@ -861,38 +937,14 @@ int gq_coverage_groups_import(gq_index* ix, const uint32_t* words, uint64_t n_wo
   std::map<std::vector<uint32_t>, uint64_t> g;
   if (!replace) collect_groups(ix, g, true);
   for (uint64_t t = 0; t < n_words;) {
+    if (t + 3 > n_words || t + 3 + words[t + 2] > n_words) throw std::runtime_error("truncated group record");
     uint32_t n = words[t + 2];
     std::vector<uint32_t> key{words[t]};
     key.insert(key.end(), words + t + 3, words + t + 3 + n);
     g[key] += words[t + 1];
     t += 3 + n;
   }
-  // rebuild table + pool on the host with the device's hash, then upload
-  std::vector<uint32_t> tab(ix->gtab.cap, 0), cnt(ix->gtab.cap, 0), pool;
-  uint32_t maskc = (uint32_t)ix->gtab.cap - 1;
-  for (auto& e : g) {
-    uint32_t slot = e.first[0], n = (uint32_t)e.first.size() - 1;
-    uint32_t hsh = 2166136261u ^ slot;
-    hsh *= 16777619u;
-    for (uint32_t i = 0; i < n; ++i) {
-      hsh ^= e.first[1 + i];
-      hsh *= 16777619u;
-    }
-    hsh ^= hsh >> 15;
-    hsh &= maskc;
-    while (tab[hsh]) hsh = (hsh + 1) & maskc;
-    tab[hsh] = (uint32_t)pool.size() + 1;
-    cnt[hsh] = (uint32_t)e.second;
-    pool.push_back(slot);
-    pool.push_back(n);
-    pool.insert(pool.end(), e.first.begin() + 1, e.first.end());
-  }
-  if (pool.size() > ix->gpool.cap) throw std::runtime_error("grouped allele count pool is full");
-  CUDA_OK(cudaMemcpy(ix->gtab.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMemcpy(ix->gcount.p, cnt.data(), cnt.size() * 4, cudaMemcpyHostToDevice));
-  if (!pool.empty()) CUDA_OK(cudaMemcpy(ix->gpool.p, pool.data(), pool.size() * 4, cudaMemcpyHostToDevice));
-  uint32_t used = (uint32_t)pool.size();
-  CUDA_OK(cudaMemcpy(ix->gsmall.p, &used, 4, cudaMemcpyHostToDevice));
+  rebuild_groups(ix, g, 0);
   GQ_CATCH
 }
 
@@ -1017,6 +1069,18 @@ int gq_set_option(gq_index* ix, const char* name, int64_t value) {
   } else if (n == "pool_words_per_read") {
     ix->pool_words_per_read = (uint32_t)std::max<int64_t>(value, 1);
     ix->pool.release();
+  } else if (n == "gtab_cap") {  // (tests) shrink the multi-allele group table so that its growth path runs
+    uint32_t cap = 4;
+    while (cap < (uint64_t)std::max<int64_t>(value, 4)) cap <<= 1;
+    CUDA_OK(cudaSetDevice(ix->device));
+    CUDA_OK(cudaStreamSynchronize(ix->stream));
+    ix->gtab.release();
+    ix->gcount.release();
+    ix->gpool.release();
+    ix->gtab.reserve(cap);
+    ix->gcount.reserve(cap);
+    ix->gpool.reserve((size_t)cap * 4);
+    reset_coverage(ix);
   } else if (n == "overlap_classify") {
     ix->overlap_classify = value != 0;
   } else if (n == "resident_slices") {

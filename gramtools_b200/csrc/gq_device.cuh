@@ -1474,19 +1474,24 @@ GQ_DEV uint32_t hash_group(uint32_t slot, const uint32_t* loci, uint32_t n) {
   return h;
 }
 
-// multi-allele group of one site: find-or-insert in the open-addressing table, then count
-GQ_DEV void grouped_insert(const CoverageView& c, uint32_t slot, const uint32_t* loci, uint32_t n) {
+// multi-allele group of one site: find-or-insert in the open-addressing table. Returns the table slot (whose
+// counter the caller bumps when it commits), or kNoAllele when the table or the record pool is full — the caller
+// then gives the strand back uncommitted and the host grows the table (capi.cu: grow_groups). An inserted key
+// that is never counted is harmless: readers skip zero counters.
+GQ_DEV uint32_t grouped_find_or_insert(const CoverageView& c, uint32_t slot, const uint32_t* loci, uint32_t n) {
   uint32_t maskc = c.gtab_cap - 1;
   uint32_t h = hash_group(slot, loci, n) & maskc;
   uint32_t mine = 0;  // offset + 1 of a record this thread allocated (lazily)
-  for (uint32_t probe = 0; probe < c.gtab_cap; ++probe, h = (h + 1) & maskc) {
+  uint32_t found = kNoAllele;
+  // at most half the table is probed: a table that full is grown rather than searched
+  for (uint32_t probe = 0; probe < (c.gtab_cap >> 1) + 1; ++probe, h = (h + 1) & maskc) {
     uint32_t cur = gq_atomic_add(c.gtab + h, 0u);
     if (cur == 0) {
       if (!mine) {
         uint32_t off = gq_atomic_add(c.gpool_used, n + 2);
         if (off + n + 2 > c.gpool_cap) {
           gq_atomic_or(c.error_flags, 1u);
-          return;
+          return kNoAllele;
         }
         c.gpool[off] = slot;
         c.gpool[off + 1] = n;
@@ -1495,21 +1500,23 @@ GQ_DEV void grouped_insert(const CoverageView& c, uint32_t slot, const uint32_t*
         mine = off + 1;
       }
       cur = gq_atomic_cas(c.gtab + h, 0u, mine);
-      if (cur == 0) {
-        gq_red_add(c.gcount + h, 1u);
-        return;
-      }
+      if (cur == 0) return h;
     }
     // occupied: same key?
     const volatile uint32_t* rec = c.gpool + (cur - 1);
     bool same = rec[0] == slot && rec[1] == n;
     for (uint32_t i = 0; same && i < n; ++i) same = rec[2 + i] == loci[2 * i + 1];
     if (same) {
-      gq_red_add(c.gcount + h, 1u);
-      return;
+      found = h;
+      break;
     }
   }
-  gq_atomic_or(c.error_flags, 1u);
+  // a record allocated for a slot somebody else won: hand it back if it is still the newest allocation (many
+  // threads meeting the same new group at kernel start would otherwise each leak one; what cannot be handed back
+  // is dropped when the table is next rebuilt)
+  if (mine) gq_atomic_cas(c.gpool_used, mine - 1 + n + 2, mine - 1);
+  if (found == kNoAllele) gq_atomic_or(c.error_flags, 1u);
+  return found;
 }
 
 GQ_DEV bool record_strand(const IndexView& v, const BatchView& b, const SearchOut& o, const CoverageView& c,
@@ -1677,7 +1684,6 @@ GQ_DEV bool record_strand(const IndexView& v, const BatchView& b, const SearchOu
       }
     }
   }
-  // ---- commit (nothing above touched the counters, so an overflow re-run cannot double count) ----
   // sort loci by (site, allele) — std::set<VariantLocus> order
   for (uint32_t i = 1; i < ll.n_loci; ++i) {
     uint32_t s0 = ll.loci[2 * i], a0 = ll.loci[2 * i + 1], j = i;
@@ -1690,7 +1696,24 @@ GQ_DEV bool record_strand(const IndexView& v, const BatchView& b, const SearchOu
     ll.loci[2 * j] = s0;
     ll.loci[2 * j + 1] = a0;
   }
-  for (uint32_t i = 0; i < ll.n_loci;) {
+  // multi-allele groups first find (or create) their table slots — kept in `used`, no longer needed by the locus
+  // finder; a full table gives the strand back before any counter is touched (grouped_allele_counts.cpp:17-49)
+  {
+    uint32_t ng = 0;
+    for (uint32_t i = 0; i < ll.n_loci;) {
+      uint32_t e = i;
+      while (e < ll.n_loci && ll.loci[2 * e] == ll.loci[2 * i]) ++e;
+      if (e - i > 1) {
+        if (ng >= ll.cap) return false;
+        const uint32_t h = grouped_find_or_insert(c, (ll.loci[2 * i] - 5) >> 1, ll.loci + 2 * i, e - i);
+        if (h == kNoAllele) return false;
+        ll.used[ng++] = h;
+      }
+      i = e;
+    }
+  }
+  // ---- commit (nothing above touched the counters, so an overflow re-run cannot double count) ----
+  for (uint32_t i = 0, ng = 0; i < ll.n_loci;) {
     uint32_t site = ll.loci[2 * i], slot = (site - 5) >> 1;
     uint32_t e = i;
     while (e < ll.n_loci && ll.loci[2 * e] == site) {
@@ -1698,7 +1721,7 @@ GQ_DEV bool record_strand(const IndexView& v, const BatchView& b, const SearchOu
       ++e;
     }
     if (e - i == 1) gq_red_add(c.grouped_single + c.allele_off[slot] + ll.loci[2 * i + 1], 1u);
-    else grouped_insert(c, slot, ll.loci + 2 * i, e - i);  // grouped_allele_counts.cpp:17-49
+    else gq_red_add(c.gcount + ll.used[ng++], 1u);
     i = e;
   }
   for (uint32_t i = 0; i < hull.n; ++i) {

@@ -85,6 +85,84 @@ def make_indel_prg(ref_len, n_sites, seed, snp_frac=0.8):
     return np.asarray(out, dtype=np.uint32)
 
 
+def make_indel_prg_np(ref_len, n_sites, seed, snp_frac=0.8):
+    """Vectorised make_indel_prg for config-4/5-sized PRGs: 80 % SNPs, 10 % deletions (REF of 2-10
+    bases, ALT = its first base), 10 % insertions (ALT = REF base + 1-9 random bases), emitted as
+    `odd REF even ALT even`. Returns (prg uint32, ref uint8 codes, sites) with sites = dict of arrays
+    start / ref_len / alt_off / alt_len / alt_bases for `indel_haplotypes`."""
+    rng = np.random.default_rng(seed)
+    ref = rng.integers(1, 5, size=ref_len, dtype=np.uint8)
+    stride = 13  # REF alleles are at most 10 bases: sites never touch
+    n_sites = min(n_sites, (ref_len - 14) // stride)
+    slots = np.sort(rng.choice((ref_len - 14) // stride, size=n_sites, replace=False))
+    start = (slots * stride + 1 + rng.integers(0, 2, size=n_sites)).astype(np.int64)
+    r = rng.random(n_sites)
+    is_del = (r >= snp_frac) & (r < snp_frac + (1 - snp_frac) / 2)
+    is_ins = r >= snp_frac + (1 - snp_frac) / 2
+    rlen = np.ones(n_sites, dtype=np.int64)
+    rlen[is_del] = rng.integers(2, 11, size=int(is_del.sum()))
+    alen = np.ones(n_sites, dtype=np.int64)
+    alen[is_ins] = 1 + rng.integers(1, 10, size=int(is_ins.sum()))
+    alt_off = np.zeros(n_sites + 1, dtype=np.int64)
+    np.cumsum(alen, out=alt_off[1:])
+    alt_bases = rng.integers(1, 5, size=int(alt_off[-1]), dtype=np.uint8)
+    first = alt_off[:-1]
+    # first ALT base: SNP = a different base; deletion / insertion = the REF allele's first base
+    snp = ~(is_del | is_ins)
+    alt_bases[first[snp]] = ((ref[start[snp]].astype(np.int64) - 1 + rng.integers(1, 4, size=int(snp.sum()))) % 4 + 1)
+    alt_bases[first[~snp]] = ref[start[~snp]]
+    # output index of every reference base: +1 at a site start (odd marker), +(2 + alen) after the REF allele
+    shift = np.zeros(ref_len + 1, dtype=np.int64)
+    np.add.at(shift, start, 1)
+    np.add.at(shift, start + rlen, 2 + alen)
+    shift = np.cumsum(shift)[:ref_len]
+    out = np.zeros(ref_len + int((3 + alen).sum()), dtype=np.uint32)
+    out[np.arange(ref_len) + shift] = ref
+    ids = 5 + 2 * np.arange(n_sites, dtype=np.uint32)
+    o_start = start + shift[start]                 # first REF-allele base in the PRG
+    out[o_start - 1] = ids
+    sep = o_start + rlen                           # even marker after the REF allele
+    out[sep] = ids + 1
+    within = np.arange(int(alt_off[-1])) - np.repeat(first, alen)
+    out[np.repeat(sep + 1, alen) + within] = alt_bases
+    out[sep + 1 + alen] = ids + 1
+    sites = dict(start=start, ref_len=rlen, alt_off=alt_off, alt_len=alen, alt_bases=alt_bases)
+    return out, ref, sites
+
+
+def indel_haplotypes(ref, sites, n_hap, seed):
+    """Random haplotypes of a make_indel_prg_np PRG: every site takes REF or ALT with equal probability."""
+    rng = np.random.default_rng(seed)
+    start, rlen, alen, alt_off, alt_bases = (sites[k] for k in ("start", "ref_len", "alt_len", "alt_off", "alt_bases"))
+    haps = []
+    for _ in range(n_hap):
+        pick = rng.integers(0, 2, size=start.size).astype(bool)
+        keep = np.ones(ref.size + 1, dtype=np.int64)
+        # drop the REF allele of ALT-carrying sites, then splice the ALT bases in front of what follows it
+        d = np.zeros(ref.size + 1, dtype=np.int64)
+        np.add.at(d, start[pick], 1)
+        np.add.at(d, start[pick] + rlen[pick], -1)
+        dropped = np.cumsum(d)[:ref.size] > 0
+        ins_at = start[pick] + rlen[pick]          # ALT bases go before reference position ins_at
+        ins_len = alen[pick]
+        add = np.zeros(ref.size + 1, dtype=np.int64)
+        np.add.at(add, ins_at, ins_len)
+        kept = ~dropped
+        new_pos = np.cumsum(kept.astype(np.int64) + add[:ref.size]) - kept  # index of base i if kept (after inserts at i)
+        total = int(kept.sum() + ins_len.sum())
+        h = np.zeros(total, dtype=np.uint8)
+        h[new_pos[kept]] = ref[kept]
+        # inserted runs end right before new_pos[ins_at] (or at the end of the haplotype)
+        end = np.where(ins_at < ref.size, new_pos[np.minimum(ins_at, ref.size - 1)] - 0, total)
+        # when the base at ins_at is itself dropped (cannot happen: sites never touch) new_pos would be off
+        within = np.arange(int(ins_len.sum())) - np.repeat(np.cumsum(ins_len) - ins_len, ins_len)
+        src = np.repeat(alt_off[:-1][pick], ins_len) + within
+        h[np.repeat(end - ins_len, ins_len) + within] = alt_bases[src]
+        del keep
+        haps.append(h)
+    return haps
+
+
 def snp_haplotypes(ref, pos, alt, n_hap, seed):
     rng = np.random.default_rng(seed)
     haps = []

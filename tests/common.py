@@ -85,6 +85,7 @@ def emu_lib():
         lib.emu_index_check.argtypes = [C.c_void_p]
         lib.emu_path_counters.argtypes = [u64p, C.c_int]
         lib.emu_force_general.argtypes = [C.c_int]
+        lib.emu_set_gtab_cap.argtypes = [C.c_void_p, C.c_uint32]
         lib.emu_counters_raw.argtypes = [C.c_void_p, u32p]
         lib.emu_groups_raw.argtypes = [C.c_void_p, u32p]
         lib.emu_groups_raw.restype = C.c_uint64
@@ -223,6 +224,10 @@ class Emu:
     def force_general(self, on):
         self.lib.emu_force_general(int(on))
 
+    def set_gtab_cap(self, cap):
+        """Shrink the multi-allele group table (power of two) so that its growth path runs."""
+        self.lib.emu_set_gtab_cap(self.h, int(cap))
+
     def counters_raw(self):
         out = np.zeros(max(2 * self.n_alleles + self.n_per_base, 1), dtype=np.uint32)
         self.lib.emu_counters_raw(self.h, _ptr(out, C.c_uint32))
@@ -292,3 +297,80 @@ def assert_parity(got: Result, ref: Result, what="", check_states=True):
     assert np.array_equal(got.per_base, ref.per_base), \
         f"{what}: per-base coverage differs at {np.nonzero(got.per_base != ref.per_base)[0][:10]}"
     assert np.array_equal(got.grouped, ref.grouped), f"{what}: grouped allele counts differ"
+
+
+# ---------------------------------------------------------------------------------------------------
+# Shared cases (used by the CPU suite through the emulation and by the GPU suite through libgq.so)
+# ---------------------------------------------------------------------------------------------------
+def numbered_prg(numbered):
+    """'gct5c6g6t6ag' -> ints (the notation of the reference's tests, prg_string_to_ints)."""
+    prg, num = [], ""
+    for ch in numbered:
+        if ch.isdigit():
+            num += ch
+        else:
+            if num:
+                prg.append(int(num))
+                num = ""
+            prg.append("acgt".index(ch.lower()) + 1)
+    if num:
+        prg.append(int(num))
+    return np.asarray(prg, dtype=np.uint32)
+
+
+def bracket_prg(br):
+    """'a[c,g[ct,t]a]c' -> ints (nested bracket notation of test_linearised_prg / test_covGraph)."""
+    stack, nid, prg = [], 3, []
+    for ch in br:
+        if ch == "[":
+            nid += 2
+            stack.append(nid)
+            prg.append(nid)
+        elif ch == "]":
+            prg.append(stack.pop() + 1)
+        elif ch == ",":
+            prg.append(stack[-1] + 1)
+        else:
+            prg.append("acgt".index(ch.lower()) + 1)
+    return np.asarray(prg, dtype=np.uint32)
+
+
+REFERENCE_SEEDS = (42, 150, 29, 200)  # test_quasimap.cpp:174-198,240-258,386-404
+
+
+def reference_test_cases():
+    """PRGs + reads of the reference's quasimap tests (test_quasimap.cpp), both strands, with the seeds its
+    seed-dependent selection tests use. Yields (name, prg, k, reads, seeds_to_try)."""
+    cases = [
+        ("gct5c6g6t6ag7t8c8cta", ["agccta", "agtcta", "ctgagtcta", "tagtcta", "tgtcta", "gctc", "tagt", "gagt", "cagc"]),
+        ("TAG5Tc6g6T6AG7T8c8cta", ["tagt"] * 8),
+        ("gtagtac5gtagtact6t6ta", ["gtagt"] * 8),
+        ("ac5gtagtact6t6gggtagt6ta", ["gtagt"] * 4),
+        ("tac5gta6gtt6ta", ["tacgt"]),
+        ("gcac5t6g6c6ta7t8c8cta", ["accta", "gcact"]),
+    ]
+    for numbered, reads in cases:
+        yield numbered, numbered_prg(numbered), 2, reads, REFERENCE_SEEDS
+    nested = ["a[c,g[ct,t]a]c", "t[a[c,g][c,g],]t", "A[[A[CCC,c],t],g]TA", "a[t[tt,t]t,a[at,]a]g[c,g]",
+              "[AC,[C,G]]T", "[C,G][C,G]", "A[C,,G]T", "AT[GC[GCC,CCGC],T]TTTT", "AAT[ATAT,AA,]AGG"]
+    nreads = ["agtac", "tt", "tacct", "AACCCTA", "CTA", "ATTTTGC", "TT", "AAAGG", "ACT", "CT", "GT", "AT",
+              "CGCCTT", "ATTTT", "GCC", "CTTT", "ATAT", "ATAAA", "AATAGG"]
+    for br in nested:
+        for k in (1, 2):
+            yield br, bracket_prg(br), k, nreads, (42,)
+
+
+def uint16_case():
+    """One batch that pushes every kind of counter past 65535: a SNP allele (allele_sum and its single-allele
+    group WRAP, allele_sum.cpp:40-41 / grouped_allele_counts.cpp:44-47), a multi-allele group (a read that
+    starts inside a site on a suffix shared by two alleles: wraps), and per-base cells (SATURATE at 65535,
+    allele_base.cpp:239-241). Returns (prg, k, reads)."""
+    rng = np.random.default_rng(12)
+    s = lambda a: "".join("?ACGT"[int(x)] for x in a)
+    left, mid, right = rng.integers(1, 5, 40), rng.integers(1, 5, 30), rng.integers(1, 5, 40)
+    # site 5: SNP A/C; site 7: alleles GGTA / CCTA / T (the first two share the suffix TA)
+    prg = np.concatenate([left, [5, 1, 6, 2, 6], mid, [7, 3, 3, 4, 1, 8, 2, 2, 4, 1, 8, 4, 8], right]).astype(np.uint32)
+    snp_read = s(left[-12:]) + "C" + s(mid[:12])          # crosses site 5 through allele 1
+    shared = "TA" + s(right[:20])                          # starts inside site 7: alleles 0 and 1 both fit
+    reads = [snp_read] * 70000 + [shared] * 66000 + [s(mid[-10:]) + "T" + s(right[:15])] * 300
+    return prg, 5, reads

@@ -54,6 +54,14 @@ void* emu_new(const uint32_t* prg, uint64_t n, uint32_t k) {
   }
 }
 void emu_free(void* e) { delete (Emu*)e; }
+// test hook: shrink the multi-allele group table (power of two) so that its growth path runs
+void emu_set_gtab_cap(void* ev, uint32_t cap) {
+  auto* e = (Emu*)ev;
+  e->gtab.assign(cap, 0);
+  e->gcount.assign(cap, 0);
+  e->gpool.assign((size_t)cap * 4, 0);
+  e->gsmall.assign(4, 0);
+}
 
 void emu_sizes(void* ev, uint64_t out[6]) {
   auto* e = (Emu*)ev;
@@ -172,6 +180,39 @@ int emu_map(void* ev, const uint8_t* bases, const uint64_t* off, uint64_t n_read
       if (e->status[s] != ST_MAPPED) continue;
       while (!record_strand(v, b, o, c, s, a, aw)) {
         e->reruns++;
+        if (e->gsmall[1] & 1u) {  // group table / pool full: rebuild 4x larger (libgq: grow_groups), strand again
+          std::vector<uint32_t> ot = e->gtab, oc = e->gcount, op = e->gpool;
+          const size_t cap = ot.size() * 4;
+          e->gtab.assign(cap, 0);
+          e->gcount.assign(cap, 0);
+          e->gpool.assign(std::max(op.size(), cap * 4), 0);
+          uint32_t used = 0;
+          for (size_t i = 0; i < ot.size(); ++i) {
+            if (!ot[i] || !oc[i]) continue;
+            const uint32_t* rec = op.data() + (ot[i] - 1);
+            uint32_t hsh = 2166136261u ^ rec[0];
+            hsh *= 16777619u;
+            for (uint32_t q = 0; q < rec[1]; ++q) {
+              hsh ^= rec[2 + q];
+              hsh *= 16777619u;
+            }
+            hsh ^= hsh >> 15;
+            hsh &= (uint32_t)cap - 1;
+            while (e->gtab[hsh]) hsh = (hsh + 1) & ((uint32_t)cap - 1);
+            e->gtab[hsh] = used + 1;
+            e->gcount[hsh] = oc[i];
+            std::memcpy(e->gpool.data() + used, rec, (2 + rec[1]) * 4);
+            used += 2 + rec[1];
+          }
+          e->gsmall[0] = used;
+          e->gsmall[1] &= ~1u;
+          c.gtab = e->gtab.data();
+          c.gcount = e->gcount.data();
+          c.gtab_cap = (uint32_t)cap;
+          c.gpool = e->gpool.data();
+          c.gpool_cap = (uint32_t)e->gpool.size();
+          continue;
+        }
         aw *= 4;
         if (aw > (1u << 28)) throw std::runtime_error("emu: coverage scratch overflow persists");
         big.assign(aw, 0);

@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from common import ROOT, Oracle, assert_parity, gpu_result
+from common import ROOT, Oracle, assert_parity, gpu_result, reference_test_cases, uint16_case
 from gramtools_b200 import QuasimapIndex, encode_reads, master_seeds, synth
 
 pytestmark = pytest.mark.gpu
@@ -118,6 +118,13 @@ def test_integration_fixtures(built_lib):
         if "allele_base_counts" in case:
             flat = [c for site in case["allele_base_counts"] for allele in site for c in allele]
             assert list(got.per_base) == flat
+        # grouped counts against the golden expectation itself (test_genotype_integration_tests.py:68-157)
+        w, i, groups = [int(x) for x in got.grouped], 0, {}
+        while i < len(w):
+            n = w[i + 2]
+            groups.setdefault(str(w[i]), {})[",".join(map(str, w[i + 3:i + 3 + n]))] = w[i + 1]
+            i += 3 + n
+        assert groups == case["grouped"], name
 
 
 def test_medium_snp_properties(built_lib):
@@ -274,3 +281,80 @@ def test_random_shapes_gpu(built_lib):
             bases[hit] = rng.integers(1, 5, int(hit.sum()))
         _check(prg, k, bases, offs, seed=int(rng.integers(0, 1000)), what=f"random-shape-{case}",
                options={"arena_words": int(rng.choice([64, 256, 1024]))})
+
+
+def test_reference_seeded_selection_gpu(built_lib):
+    """The reference's quasimap test PRGs through libgq.so, including the seed-dependent multi-class selections
+    with seeds 42 / 150 / 29 / 200 (test_quasimap.cpp:174-198,240-258,386-404) and the nested bracket PRGs."""
+    for name, prg, k, reads, seeds in reference_test_cases():
+        bases, offs = encode_reads(reads)
+        for seed in seeds:
+            _check(prg, k, bases, offs, seed=seed, what=f"{name}/seed{seed}")
+
+
+def test_uint16_wrap_and_saturation_gpu(built_lib):
+    """Counters past 65535: allele_sum and grouped counts (single- and multi-allele) wrap, per-base saturates
+    (allele_sum.cpp:40-41, grouped_allele_counts.cpp:44-47, allele_base.cpp:239-241); expected values from the
+    oracle, which counts in uint16_t like the reference."""
+    prg, k, reads = uint16_case()
+    bases, offs = encode_reads(reads)
+    got, ref = _check(prg, k, bases, offs, what="uint16", threads=os.cpu_count())
+    assert got.per_base.max() == 65535 and (got.per_base == 65535).sum() >= 3
+    assert got.allele_sum[1] == 70000 - 65536
+    # the same batch mapped in two halves on the same handle accumulates to the same wrapped totals
+    idx = QuasimapIndex(prg, k)
+    seeds = master_seeds(42, offs.size - 1)
+    h = (offs.size - 1) // 2
+    idx.map_batch(bases[:int(offs[h])], offs[:h + 1], seeds[:h])
+    idx.map_batch(bases[int(offs[h]):], offs[h:] - offs[h], seeds[h:])
+    a, p, _ = idx.coverage()
+    assert np.array_equal(a, ref.allele_sum) and np.array_equal(p, ref.per_base)
+    assert np.array_equal(idx.grouped(), ref.grouped)
+
+
+def test_group_table_growth_gpu(built_lib):
+    """Multi-allele group table of 4 slots on a nested PRG with dozens of distinct groups: the table grows
+    (strands flagged before anything is committed, re-run after the rebuild) and results stay exact."""
+    prg = synth.make_nested_prg(6, 300, 4)
+    bases, offs = _reads_for(prg, 6000, 30, 4, garbage=0.0, n_frac=0.0)
+    got, _ = _check(prg, 4, bases, offs, what="gtab-growth", options={"gtab_cap": 4}, threads=4)
+    assert got.extra["rerun_strands"] > 0
+
+
+def test_state_pool_overflow_multislice(built_lib):
+    """Final-state pool far too small on a repeat-rich nested PRG, mapped in several pipelined slices: text-kernel
+    winners and general-kernel strands both overflow, some strands are flagged twice; every strand must still be
+    mapped and recorded exactly once."""
+    rng = np.random.default_rng(8)
+    unit = synth.make_nested_prg(2, 200, 8)
+    # two copies of the same flanks around distinct loci: reads in the flanks have several finished candidates
+    flank = rng.integers(1, 5, 300).astype(np.uint32)
+    renum = unit.copy()
+    renum[renum > 4] += int(unit.max()) - 4  # site ids continue after the first copy's (max marker is even)
+    prg = np.concatenate([flank, unit, flank, renum, flank]).astype(np.uint32)
+    bases, offs = _reads_for(prg, 40000, 40, 8, garbage=0.01, n_frac=0.0)
+    got, _ = _check(prg, 5, bases, offs, what="pool-overflow",
+                    options={"pool_words_per_read": 1, "chunk_reads": 4096, "tail_chunk_reads": 1024}, threads=os.cpu_count())
+    assert got.extra["rerun_strands"] > 1000
+
+
+def test_config3_shape_prefix(built_lib):
+    """BASELINE config 3 at its stated shape (nested PRG, 200 loci x 5 kb, k = 10, 150 bp reads): a 20k-read
+    prefix bit-identical to the oracle — states, all three coverage structures, counters."""
+    prg = synth.make_nested_prg(200, 5000, 0x6772616D + 3)
+    rng = np.random.default_rng(3)
+    haps = [synth.random_haplotype(prg, rng) for _ in range(8)]
+    bases, offs = synth.sample_reads(haps, 20000, 150, 13)
+    got, ref = _check(prg, 10, bases, offs, what="config3-shape", threads=os.cpu_count())
+    assert ref.stats[4] >= 20000 and ref.grouped.size > 0
+
+
+def test_config4_shape_prefix(built_lib):
+    """BASELINE config 4's regime scaled so that the oracle builds its index in seconds: the same site mix (80 %
+    SNPs, 10 % deletions, 10 % insertions, one site per 50 bp) and the same ~60 occurrences per seeding k-mer
+    (config 4: 2.7e8 symbols / 4^11; here 4 Mb / 4^8), 150 bp reads: 20k-read prefix bit-identical to the oracle."""
+    prg, ref, sites = synth.make_indel_prg_np(4_000_000, 80_000, 0x6772616D + 4)
+    haps = synth.indel_haplotypes(ref, sites, 4, 11)
+    bases, offs = synth.sample_reads(haps, 20000, 150, 12)
+    got, ref_r = _check(prg, 8, bases, offs, what="config4-shape", threads=os.cpu_count())
+    assert ref_r.stats[4] >= 20000

@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from common import ROOT, Emu, Oracle, assert_parity
+from common import ROOT, Emu, Oracle, assert_parity, reference_test_cases, uint16_case
 from gramtools_b200 import encode_reads, master_seeds, synth
 
 
@@ -88,50 +88,47 @@ def test_edge_cases():
 
 
 def test_reference_test_prgs():
-    """PRGs + reads of the reference's quasimap tests (test_quasimap.cpp), both strands."""
-    import ctypes as C
-    cases = [
-        ("gct5c6g6t6ag7t8c8cta", ["agccta", "agtcta", "ctgagtcta", "tagtcta", "tgtcta", "gctc", "tagt", "gagt", "cagc"]),
-        ("TAG5Tc6g6T6AG7T8c8cta", ["tagt"] * 8),
-        ("gtagtac5gtagtact6t6ta", ["gtagt"] * 8),
-        ("ac5gtagtact6t6gggtagt6ta", ["gtagt"] * 4),
-        ("tac5gta6gtt6ta", ["tacgt"]),
-        ("gcac5t6g6c6ta7t8c8cta", ["accta", "gcact"]),
-    ]
-    from common import oracle_lib
-    for numbered, reads in cases:
-        # numbered -> ints
-        prg, num = [], ""
-        for ch in numbered:
-            if ch.isdigit():
-                num += ch
-            else:
-                if num:
-                    prg.append(int(num)); num = ""
-                prg.append("acgt".index(ch.lower()) + 1)
-        if num:
-            prg.append(int(num))
+    """PRGs + reads of the reference's quasimap tests (test_quasimap.cpp), both strands, incl. the seed-dependent
+    selections (seeds 42 / 150 / 29 / 200)."""
+    for name, prg, k, reads, seeds in reference_test_cases():
         bases, offs = encode_reads(reads)
-        for seed in (42, 150, 29, 200):
-            _check(np.asarray(prg, dtype=np.uint32), 2, bases, offs, seed=seed, what=numbered)
-    nested = ["a[c,g[ct,t]a]c", "t[a[c,g][c,g],]t", "A[[A[CCC,c],t],g]TA", "a[t[tt,t]t,a[at,]a]g[c,g]",
-              "[AC,[C,G]]T", "[C,G][C,G]", "A[C,,G]T", "AT[GC[GCC,CCGC],T]TTTT", "AAT[ATAT,AA,]AGG"]
-    nreads = ["agtac", "tt", "tacct", "AACCCTA", "CTA", "ATTTTGC", "TT", "AAAGG", "ACT", "CT", "GT", "AT",
-              "CGCCTT", "ATTTT", "GCC", "CTTT", "ATAT", "ATAAA", "AATAGG"]
-    for br in nested:
-        stack, nid, prg = [], 3, []
-        for ch in br:
-            if ch == "[":
-                nid += 2; stack.append(nid); prg.append(nid)
-            elif ch == "]":
-                prg.append(stack.pop() + 1)
-            elif ch == ",":
-                prg.append(stack[-1] + 1)
-            else:
-                prg.append("acgt".index(ch.lower()) + 1)
-        bases, offs = encode_reads(nreads)
-        for k in (1, 2):
-            _check(np.asarray(prg, dtype=np.uint32), k, bases, offs, what=br)
+        for seed in seeds:
+            _check(prg, k, bases, offs, seed=seed, what=name)
+
+
+def test_uint16_wrap_and_saturation():
+    """allele_sum and grouped counts wrap mod 65536, per-base counts saturate at 65535 — the oracle counts in
+    uint16_t like the reference; the product counts in uint32 and converts when fetching."""
+    prg, k, reads = uint16_case()
+    bases, offs = encode_reads(reads)
+    ro, re = _check(prg, k, bases, offs, what="uint16")
+    assert ro.per_base.max() == 65535 and (ro.per_base == 65535).sum() >= 3       # saturated cells
+    assert 0 < ro.allele_sum[1] < 10000 and ro.stats[4] >= 136000                  # 70000 wrapped to 4464
+    g = [int(x) for x in ro.grouped]
+    recs, i = {}, 0
+    while i < len(g):
+        recs[(g[i], tuple(g[i + 3:i + 3 + g[i + 2]]))] = g[i + 1]
+        i += 3 + g[i + 2]
+    assert recs[(1, (0, 1))] == 66000 - 65536 and recs[(0, (1,))] == 70000 - 65536
+
+
+def test_group_table_growth():
+    """A multi-allele group table that is far too small must grow (flagged strands are given back uncommitted
+    and recorded after the rebuild), never drop or double count."""
+    prg = synth.make_nested_prg(6, 300, 4)
+    bases, offs = _reads_for(prg, 1500, 30, 4, garbage=0.0, n_frac=0.0)
+    seeds = master_seeds(42, offs.size - 1)
+    o, e = Oracle(prg, 4), Emu(prg, 4)
+    e.set_gtab_cap(4)
+    o.map(bases, offs, seeds)
+    e.map(bases, offs, seeds)
+    ro, re = o.result(), e.result()
+    assert_parity(re, ro, "gtab-growth")
+    n_multi, g, i = 0, [int(x) for x in ro.grouped], 0
+    while i < len(g):
+        n_multi += g[i + 2] > 1
+        i += 3 + g[i + 2]
+    assert n_multi > 16 and re.extra["reruns"] > 0, (n_multi, re.extra)
 
 
 def test_integration_fixtures_through_product_code():
