@@ -8,10 +8,12 @@ driver; names follow the reference's quasimap interface
 There is no CPU fallback: importing works anywhere, but every compute call needs the built
 library and a CUDA device and raises otherwise.
 """
-from .engine import (GqError, QuasimapIndex, QuasimapReadsStats, encode_reads, lib_path, load_library)  # noqa: F401
+from .engine import (GqError, QuasimapIndex, QuasimapReadsStats, comm_unique_id, encode_reads, lib_path,  # noqa: F401
+                     load_library, pack_ascii, pack_reads)
 from .synth import (make_snp_prg, make_indel_prg, make_nested_prg, sample_reads, master_seeds)  # noqa: F401
 
 __all__ = [
-    "GqError", "QuasimapIndex", "QuasimapReadsStats", "encode_reads", "lib_path", "load_library",
+    "GqError", "QuasimapIndex", "QuasimapReadsStats", "comm_unique_id", "encode_reads", "lib_path", "load_library",
+    "pack_ascii", "pack_reads",
     "make_snp_prg", "make_indel_prg", "make_nested_prg", "sample_reads", "master_seeds",
 ]

@@ -20,85 +20,9 @@ void launch_stats(const uint8_t* status, const uint32_t* len, uint32_t n_reads, 
 }
 
 static thread_local std::string g_err;
+void set_last_error(const std::string& what) { g_err = what; }
 
-#define CUDA_OK(expr)                                                                              \
-  do {                                                                                             \
-    cudaError_t _e = (expr);                                                                       \
-    if (_e != cudaSuccess)                                                                         \
-      throw std::runtime_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                \
-  } while (0)
-
-template <class T>
-struct DevBuf {
-  T* p = nullptr;
-  size_t cap = 0;  // elements
-  void reserve(size_t n) {
-    if (n <= cap) return;
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-    CUDA_OK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
-    cap = n;
-  }
-  void release() {
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-  }
-  size_t bytes() const { return cap * sizeof(T); }
-};
-
-struct gq_index {
-  gq::HostIndex h;
-  int device = 0;
-  cudaStream_t own_stream = nullptr, stream = nullptr;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  std::vector<void*> index_allocs;
-  size_t index_bytes = 0;
-  gq::IndexView dv{};
-  // coverage accumulators
-  DevBuf<uint32_t> counters;  // allele_sum | grouped_single | per_base
-  DevBuf<uint32_t> allele_off;
-  DevBuf<uint32_t> gtab, gcount, gpool, gsmall;  // gsmall: [gpool_used, error_flags]
-  DevBuf<unsigned long long> stats;
-  uint64_t n_alleles = 0, n_per_base = 0;
-  // batch
-  DevBuf<uint8_t> bases;
-  DevBuf<uint64_t> offsets;
-  DevBuf<uint32_t> word_off, packed, len, seeds;
-  uint32_t n_reads = 0;
-  uint32_t total_words = 0;
-  // search outputs
-  DevBuf<uint8_t> status;
-  DevBuf<uint32_t> st_off, st_words, st_count, pool, small;  // small: [pool_used, n_overflow, n_cov_overflow]
-  DevBuf<uint32_t> overflow_list, cov_overflow_list, mapped_list;
-  DevBuf<uint32_t> seed_rec, surv_rec, surv_cnt, gen_list;  // seed pass (SeedOut): survivor records, per-strand counts, general list
-  uint32_t seed_recs_per_read = 16;  // candidate records per read (set from the index: ~2.5 x mean suffixes per indexed k-mer, both strands); a full pool sends strands to the general kernel
-  bool use_seed_pass = true;
-  DevBuf<uint32_t> arena, big_arena;
-  cudaStream_t copy_stream = nullptr, copy_stream2 = nullptr;
-  cudaStream_t aux_stream = nullptr;  // second compute stream of the pipelined path
-  cudaEvent_t aux_event = nullptr;
-  DevBuf<uint32_t> arena2;
-  void* fetch_host = nullptr;  // pinned staging of gq_coverage_fetch
-  size_t fetch_host_bytes = 0;
-  DevBuf<uint16_t> fetch_dev;
-  std::vector<cudaEvent_t> chunk_events;
-  uint32_t chunk_reads = 1u << 18, tail_chunk_reads = 1u << 15;
-  uint32_t resident_slices = 1;  // gq_map_resident: slices run on two streams
-  bool overlap_classify = true;  // single-slice runs: classify_kernel beside coverage_kernel on a second stream  // slice size of the H2D / compute pipeline in gq_map_batch
-  // options
-  uint32_t arena_words = 512;
-  uint32_t n_threads = 148 * 1280;      // search kernel lanes (5 CTAs of 256 per SM)
-  uint32_t cov_threads = 148 * 1024;    // coverage kernel threads
-  uint32_t big_arena_words = 1u << 16;
-  uint32_t big_threads = 2048;
-  uint32_t pool_words_per_read = 48;
-  bool super_in_smem = true;
-  uint32_t rf_thresh = 8, ev_thresh = 8, leave_opt = 0, wait_opt = 0;
-  // run info
-  double info[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-};
+#include "gq_handle.hpp"
 
 template <class T>
 static const T* upload(gq_index* ix, const std::vector<T>& v) {
@@ -180,7 +104,7 @@ static void reset_coverage(gq_index* ix) {
   CUDA_OK(cudaStreamSynchronize(ix->stream));
 }
 
-static gq::CoverageView cov_view(gq_index* ix) {
+gq::CoverageView cov_view(gq_index* ix) {
   gq::CoverageView c{};
   c.allele_sum = ix->counters.p;
   c.grouped_single = ix->counters.p + ix->n_alleles;
@@ -214,9 +138,7 @@ struct Chunk {
 };
 constexpr size_t kMaxChunks = 64;  // per-slice counters live in fixed slots of `small`
 
-extern "C" {
 static void grow_groups(gq_index* ix);
-}
 
 static std::vector<Chunk> make_chunks(gq_index* ix, uint32_t n, bool pipelined) {
   std::vector<Chunk> ch;
@@ -239,10 +161,33 @@ static std::vector<Chunk> make_chunks(gq_index* ix, uint32_t n, bool pipelined) 
   return ch;
 }
 
+// The caller's host buffers of one batch: unpacked (one byte per base, packed on the device after the copy) or
+// already 2-bit packed on the host (gq_pack_reads / gq_pack_ascii: a third of the PCIe bytes, no pack kernel).
+struct HostBatch {
+  const uint8_t* bases = nullptr;    // unpacked form
+  const uint64_t* off = nullptr;
+  const uint32_t* packed = nullptr;  // packed form
+  const uint32_t* word_off = nullptr;
+  const uint32_t* len = nullptr;
+  const uint32_t* seeds = nullptr;
+  bool is_packed() const { return packed != nullptr || word_off != nullptr; }
+};
+
 // H2D of one slice of the caller's buffers: bases on `st`, the small per-read arrays on `st_small` (their
 // set-up latency then overlaps the big copy instead of sitting between two of them)
-static void copy_chunk(gq_index* ix, const uint8_t* bases, const uint64_t* off, const uint32_t* seeds, Chunk c,
-                       cudaStream_t st, cudaStream_t st_small) {
+static void copy_chunk(gq_index* ix, const HostBatch& hb, Chunk c, cudaStream_t st, cudaStream_t st_small) {
+  const size_t nr = c.r1 - c.r0;
+  if (hb.is_packed()) {
+    const uint32_t w0 = hb.word_off[c.r0], w1 = hb.word_off[c.r1];
+    if (w1 > w0) CUDA_OK(cudaMemcpyAsync(ix->packed.p + w0, hb.packed + w0, (size_t)(w1 - w0) * 4, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(ix->word_off.p + c.r0, hb.word_off + c.r0, (nr + 1) * 4, cudaMemcpyHostToDevice, st_small));
+    CUDA_OK(cudaMemcpyAsync(ix->len.p + c.r0, hb.len + c.r0, nr * 4, cudaMemcpyHostToDevice, st_small));
+    CUDA_OK(cudaMemcpyAsync(ix->seeds.p + c.r0, hb.seeds + c.r0, nr * 4, cudaMemcpyHostToDevice, st_small));
+    return;
+  }
+  const uint8_t* bases = hb.bases;
+  const uint64_t* off = hb.off;
+  const uint32_t* seeds = hb.seeds;
   uint64_t b0 = off[c.r0], b1 = off[c.r1];
   if (b1 > b0) CUDA_OK(cudaMemcpyAsync(ix->bases.p + b0, bases + b0, b1 - b0, cudaMemcpyHostToDevice, st));
   CUDA_OK(cudaMemcpyAsync(ix->offsets.p + c.r0, off + c.r0, (size_t)(c.r1 - c.r0 + 1) * 8, cudaMemcpyHostToDevice, st_small));
@@ -252,7 +197,11 @@ static void copy_chunk(gq_index* ix, const uint8_t* bases, const uint64_t* off, 
 // H2D + 2-bit packing of one slice on one stream
 static void upload_chunk(gq_index* ix, const uint8_t* bases, const uint64_t* off, const uint32_t* seeds, Chunk c,
                          cudaStream_t st) {
-  copy_chunk(ix, bases, off, seeds, c, st, st);
+  HostBatch hb;
+  hb.bases = bases;
+  hb.off = off;
+  hb.seeds = seeds;
+  copy_chunk(ix, hb, c, st, st);
   gq::launch_pack(ix->bases.p, ix->offsets.p, c.r0, c.r1, ix->word_off.p, ix->packed.p, ix->len.p, st);
 }
 
@@ -272,10 +221,10 @@ static void do_upload(gq_index* ix, const uint8_t* bases, const uint64_t* off, u
 
 // Map the batch. host pointers != nullptr: the reads come from the caller's HOST buffers and the H2D
 // copy of slice i+1 (copy stream) overlaps the kernels of slice i (compute stream).
-static void do_map(gq_index* ix, const uint8_t* h_bases = nullptr, const uint64_t* h_off = nullptr,
-                   const uint32_t* h_seeds = nullptr) {
+static void do_map(gq_index* ix, const HostBatch* hb = nullptr) {
   CUDA_OK(cudaSetDevice(ix->device));
-  const bool pipelined = h_bases != nullptr || h_off != nullptr;
+  const bool pipelined = hb != nullptr;
+  const bool host_packed = hb && hb->is_packed();
   const auto t_host0 = std::chrono::steady_clock::now();  // info[7]: host time spent enqueueing the call
   const uint32_t n = ix->n_reads;
   for (int i = 0; i < 8; ++i)
@@ -328,7 +277,7 @@ static void do_map(gq_index* ix, const uint8_t* h_bases = nullptr, const uint64_
     CUDA_OK(cudaStreamWaitEvent(ix->copy_stream2, ix->ev[3], 0));
     // copies only on the copy streams, back to back; packing runs on the compute stream
     for (size_t i = 0; i < chunks.size(); ++i) {
-      copy_chunk(ix, h_bases, h_off, h_seeds, chunks[i], ix->copy_stream, ix->copy_stream2);
+      copy_chunk(ix, *hb, chunks[i], ix->copy_stream, ix->copy_stream2);
       CUDA_OK(cudaEventRecord(ix->chunk_events[2 * i], ix->copy_stream));
       CUDA_OK(cudaEventRecord(ix->chunk_events[2 * i + 1], ix->copy_stream2));
     }
@@ -352,8 +301,10 @@ static void do_map(gq_index* ix, const uint8_t* h_bases = nullptr, const uint64_
     if (pipelined) {
       CUDA_OK(cudaStreamWaitEvent(cs, ix->chunk_events[2 * i], 0));
       CUDA_OK(cudaStreamWaitEvent(cs, ix->chunk_events[2 * i + 1], 0));
-      gq::launch_pack(ix->bases.p, ix->offsets.p, chunks[i].r0, chunks[i].r1, ix->word_off.p, ix->packed.p, ix->len.p, cs);
-      ++launches;
+      if (!host_packed) {
+        gq::launch_pack(ix->bases.p, ix->offsets.p, chunks[i].r0, chunks[i].r1, ix->word_off.p, ix->packed.p, ix->len.p, cs);
+        ++launches;
+      }
     }
     gq::BatchView bc = b;
     bc.read_begin = chunks[i].r0;
@@ -369,9 +320,13 @@ static void do_map(gq_index* ix, const uint8_t* h_bases = nullptr, const uint64_
       gq::SeedOut pre{ix->seed_rec.p + 4 * (size_t)ix->seed_recs_per_read * chunks[i].r0,
                       (uint32_t)std::min<uint64_t>((uint64_t)ix->seed_recs_per_read * (chunks[i].r1 - chunks[i].r0), 0x3FFFFFFFull),
                       ix->small.p + 10 + 4 * i, ix->surv_cnt.p, gen_list, n_gen};
+      const bool timed = chunks.size() == 1;  // per-kernel events (single-slice runs)
+      if (timed) CUDA_OK(cudaEventRecord(ix->kev[0], cs));
       gq::launch_seed(ix->dv, bc, oc, pre, cs);
+      if (timed) CUDA_OK(cudaEventRecord(ix->kev[1], cs));
       gq::launch_text(ix->dv, bc, oc, pre, ix->surv_rec.p + 4 * (size_t)ix->seed_recs_per_read * chunks[i].r0,
-                      ix->small.p + 8 + 4 * kMaxChunks + i, cs);
+                      ix->small.p + 8 + 4 * kMaxChunks + i, cs, timed ? ix->kev[2] : nullptr);
+      if (timed) CUDA_OK(cudaEventRecord(ix->kev[3], cs));
       ++launches;
       gq::launch_search(ix->dv, bc, oc, arena, ix->arena_words, threads, gen_list,
                         2 * (chunks[i].r1 - chunks[i].r0), ix->super_in_smem, ix->rf_thresh, ix->ev_thresh, cs,
@@ -389,9 +344,12 @@ static void do_map(gq_index* ix, const uint8_t* h_bases = nullptr, const uint64_
       }
       CUDA_OK(cudaEventRecord(ix->aux_event, cs));
       CUDA_OK(cudaStreamWaitEvent(ix->aux_stream, ix->aux_event, 0));
+      CUDA_OK(cudaEventRecord(ix->kev[4], ix->aux_stream));
       gq::launch_classify(ix->dv, bc, oc, nullptr, 0, ix->aux_stream);
+      CUDA_OK(cudaEventRecord(ix->kev[5], ix->aux_stream));
       gq::launch_coverage(ix->dv, bc, oc, c, arena, ix->arena_words, threads2, nullptr, 0,
                           ix->cov_overflow_list.p, ix->small.p + 2, cs);
+      CUDA_OK(cudaEventRecord(ix->kev[6], cs));
       CUDA_OK(cudaEventRecord(ix->aux_event, ix->aux_stream));
       CUDA_OK(cudaStreamWaitEvent(cs, ix->aux_event, 0));
     } else {
@@ -422,6 +380,23 @@ static void do_map(gq_index* ix, const uint8_t* h_bases = nullptr, const uint64_
     cudaEventElapsedTime(&ms_c, ix->ev[1], ix->ev[2]);
     ix->info[2] = ms_s;
     ix->info[3] = ms_c;
+    for (auto& m : ix->kernel_ms) m = 0;
+    if (ix->use_seed_pass && !two_streams && ix->overlap_classify) {
+      auto el = [&](int a, int b) {
+        float ms = 0;
+        return cudaEventElapsedTime(&ms, ix->kev[a], ix->kev[b]) == cudaSuccess ? (double)ms : 0.0;
+      };
+      ix->kernel_ms[0] = el(0, 1);  // seed
+      ix->kernel_ms[1] = el(1, 2);  // verify
+      ix->kernel_ms[2] = el(2, 3);  // text
+      float ms_g = 0;               // general: from the end of the text kernel to the end of the search phase
+      cudaEventElapsedTime(&ms_g, ix->kev[3], ix->ev[1]);
+      ix->kernel_ms[3] = ms_g;
+      ix->kernel_ms[4] = el(4, 5);  // classify (second stream, beside coverage)
+      float ms_cov = 0;
+      cudaEventElapsedTime(&ms_cov, ix->ev[1], ix->kev[6]);
+      ix->kernel_ms[5] = ms_cov;    // coverage
+    }
   }
   // list-mode re-runs below hand out work from counter slot [9] and append to the (already consumed)
   // mapped list of slice 0
@@ -541,6 +516,33 @@ static void do_map(gq_index* ix, const uint8_t* h_bases = nullptr, const uint64_
   ix->info[4] = small[0];
 }
 
+// device side of a handle whose host index (ix->h) is ready: streams, upload, candidate pool sizing, accumulators
+static void finish_handle(gq_index* ix) {
+  const int device = ix->device;
+  CUDA_OK(cudaSetDevice(device));
+  CUDA_OK(cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking));
+  ix->stream = ix->own_stream;
+  for (auto& e : ix->ev) CUDA_OK(cudaEventCreate(&e));
+  for (auto& e : ix->kev) CUDA_OK(cudaEventCreate(&e));
+  upload_index(ix);
+  {  // candidate records per read: a forward strand's seeding k-mer is drawn by occurrence (size-biased
+     // mean of the suffix counts), a reverse strand's is any k-mer (plain mean over all 4^k)
+    double sum = 0, sum2 = 0;
+    const auto& h = ix->h;
+    const uint64_t nk = 1ull << (2 * h.k);
+    for (uint64_t c = 0; c < nk; ++c) {
+      double w = 0;
+      for (uint32_t j = h.kmer_off[c]; j < h.kmer_off[c + 1]; ++j) w += (double)(h.kmer_states[j].hi - h.kmer_states[j].lo + 1);
+      sum += w;
+      sum2 += w * w;
+    }
+    const double per_read = (sum > 0 ? sum2 / sum : 1.0) + sum / (double)nk;
+    ix->seed_recs_per_read = (uint32_t)std::min(4096.0, 1.3 * per_read + 8.0);
+  }
+  alloc_coverage(ix);
+  reset_coverage(ix);
+}
+
 // -------------------------------------------------------------------------------------------------
 #define GQ_TRY try {
 #define GQ_CATCH                    \
@@ -569,27 +571,27 @@ int gq_index_build(const uint32_t* prg, uint64_t n_symbols, uint32_t kmer_size, 
   ix = new gq_index();
   ix->device = device;
   gq::build_host_index(prg, n_symbols, kmer_size, ix->h);
-  CUDA_OK(cudaSetDevice(device));
-  CUDA_OK(cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking));
-  ix->stream = ix->own_stream;
-  for (auto& e : ix->ev) CUDA_OK(cudaEventCreate(&e));
-  upload_index(ix);
-  {  // candidate records per read: a forward strand's seeding k-mer is drawn by occurrence (size-biased
-     // mean of the suffix counts), a reverse strand's is any k-mer (plain mean over all 4^k)
-    double sum = 0, sum2 = 0;
-    const auto& h = ix->h;
-    const uint64_t nk = 1ull << (2 * h.k);
-    for (uint64_t c = 0; c < nk; ++c) {
-      double w = 0;
-      for (uint32_t j = h.kmer_off[c]; j < h.kmer_off[c + 1]; ++j) w += (double)(h.kmer_states[j].hi - h.kmer_states[j].lo + 1);
-      sum += w;
-      sum2 += w * w;
-    }
-    const double per_read = (sum > 0 ? sum2 / sum : 1.0) + sum / (double)nk;
-    ix->seed_recs_per_read = (uint32_t)std::min(4096.0, 1.3 * per_read + 8.0);
+  finish_handle(ix);
+  *out = ix;
   }
-  alloc_coverage(ix);
-  reset_coverage(ix);
+  catch (const std::exception& e) {
+    g_err = e.what();
+    if (ix) gq_index_destroy(ix);
+    return -1;
+  }
+  return 0;
+}
+
+int gq_index_clone(const gq_index* src, int device, gq_index** out) {
+  gq_index* ix = nullptr;
+  GQ_TRY
+  if (!src || !out) throw std::runtime_error("null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) throw std::runtime_error("invalid device ordinal");
+  ix = new gq_index();
+  ix->device = device;
+  ix->h = src->h;  // the host index is shared by value: built once, uploaded per GPU
+  finish_handle(ix);
   *out = ix;
   }
   catch (const std::exception& e) {
@@ -602,6 +604,7 @@ int gq_index_build(const uint32_t* prg, uint64_t n_symbols, uint32_t kmer_size, 
 
 int gq_index_destroy(gq_index* ix) {
   if (!ix) return 0;
+  gq_comm_destroy(ix);
   cudaSetDevice(ix->device);
   for (void* p : ix->index_allocs) cudaFree(p);
   ix->counters.release();
@@ -633,6 +636,8 @@ int gq_index_destroy(gq_index* ix) {
   ix->arena.release();
   ix->big_arena.release();
   for (auto& e : ix->ev)
+    if (e) cudaEventDestroy(e);
+  for (auto& e : ix->kev)
     if (e) cudaEventDestroy(e);
   for (auto& e : ix->chunk_events) cudaEventDestroy(e);
   if (ix->copy_stream) cudaStreamDestroy(ix->copy_stream);
@@ -711,7 +716,101 @@ int gq_map_batch(gq_index* ix, const uint8_t* bases, const uint64_t* off, uint64
   reserve_batch(ix, n_reads, nb);
   ix->n_reads = (uint32_t)n_reads;
   ix->info[5] = (double)(nb + (n_reads + 1) * 8 + n_reads * 4);
-  do_map(ix, bases, off, seeds);
+  HostBatch hb;
+  hb.bases = bases;
+  hb.off = off;
+  hb.seeds = seeds;
+  do_map(ix, &hb);
+  GQ_CATCH
+}
+
+int gq_packed_words(const uint64_t* off, uint64_t n_reads, uint64_t* n_words) {
+  GQ_TRY
+  if (!n_words || (n_reads && !off)) throw std::runtime_error("null argument");
+  *n_words = (n_reads ? (off[n_reads] >> 4) : 0) + n_reads + 1;
+  GQ_CATCH
+}
+
+// read r starts at word (off[r] >> 4) + r: word-aligned, non-overlapping, computable per read without a prefix
+// sum (at most one word wasted per read) — the layout pack_kernel produces on the device
+int gq_pack_reads(const uint8_t* bases, const uint64_t* off, uint64_t n_reads, uint32_t* packed, uint32_t* word_off,
+                  uint32_t* len, int n_threads) {
+  GQ_TRY
+  if (n_reads && (!bases || !off || !packed || !word_off || !len)) throw std::runtime_error("null argument");
+  if (n_reads && ((off[n_reads] >> 4) + n_reads + 1 >= (1ull << 32))) throw std::runtime_error("batch too large (packed words exceed 2^32)");
+  const int nt = n_threads > 0 ? n_threads : 1;
+  (void)nt;
+#pragma omp parallel for schedule(static) num_threads(nt)
+  for (int64_t r = 0; r < (int64_t)n_reads; ++r) {
+    const uint64_t b0 = off[r];
+    const uint32_t L = (uint32_t)(off[r + 1] - b0), w0 = (uint32_t)(b0 >> 4) + (uint32_t)r;
+    word_off[r] = w0;
+    len[r] = L;
+    const uint8_t* src = bases + b0;
+    for (uint32_t w = 0; w < (L + 15) / 16; ++w) {
+      const uint32_t cnt = std::min<uint32_t>(16, L - 16 * w);
+      uint32_t x = 0;
+      for (uint32_t j = 0; j < cnt; ++j) x |= ((uint32_t)(src[16 * w + j] - 1) & 3u) << (2 * j);
+      packed[w0 + w] = x;
+    }
+  }
+  if (word_off) word_off[n_reads] = (uint32_t)((n_reads ? (off[n_reads] >> 4) : 0) + n_reads);
+  GQ_CATCH
+}
+
+// the same from ASCII sequence text (FASTQ / FASTA sequence lines): upper or lower case ACGT; a read holding any
+// other character becomes EMPTY, as encode_dna_bases does (utils.cpp:13-47,72-92) — len 0, counted as skipped
+int gq_pack_ascii(const char* text, const uint64_t* off, uint64_t n_reads, uint32_t* packed, uint32_t* word_off,
+                  uint32_t* len, int n_threads) {
+  GQ_TRY
+  if (n_reads && (!text || !off || !packed || !word_off || !len)) throw std::runtime_error("null argument");
+  if (n_reads && ((off[n_reads] >> 4) + n_reads + 1 >= (1ull << 32))) throw std::runtime_error("batch too large (packed words exceed 2^32)");
+  const int nt = n_threads > 0 ? n_threads : 1;
+  (void)nt;
+#pragma omp parallel for schedule(static) num_threads(nt)
+  for (int64_t r = 0; r < (int64_t)n_reads; ++r) {
+    const uint64_t b0 = off[r];
+    const uint32_t L = (uint32_t)(off[r + 1] - b0), w0 = (uint32_t)(b0 >> 4) + (uint32_t)r;
+    word_off[r] = w0;
+    const char* src = text + b0;
+    bool ok = true;
+    for (uint32_t w = 0; w < (L + 15) / 16 && ok; ++w) {
+      const uint32_t cnt = std::min<uint32_t>(16, L - 16 * w);
+      uint32_t x = 0;
+      for (uint32_t j = 0; j < cnt; ++j) {
+        // A/a 0, C/c 1, G/g 2, T/t 3: bits 1-2 of the ASCII code give 0,1,3,2 for A,C,G,T
+        const unsigned char ch = (unsigned char)src[16 * w + j], up = ch & 0xDFu;
+        const uint32_t code = up == 'A' ? 0u : up == 'C' ? 1u : up == 'G' ? 2u : up == 'T' ? 3u : 4u;
+        ok &= code < 4u;
+        x |= (code & 3u) << (2 * j);
+      }
+      packed[w0 + w] = x;
+    }
+    len[r] = ok ? L : 0u;
+  }
+  if (word_off) word_off[n_reads] = (uint32_t)((n_reads ? (off[n_reads] >> 4) : 0) + n_reads);
+  GQ_CATCH
+}
+
+int gq_map_batch_packed(gq_index* ix, const uint32_t* packed, const uint32_t* word_off, const uint32_t* len,
+                        uint64_t n_reads, const uint32_t* seeds) {
+  GQ_TRY
+  if (!ix || (n_reads && (!packed || !word_off || !len || !seeds))) throw std::runtime_error("null argument");
+  CUDA_OK(cudaSetDevice(ix->device));
+  if (n_reads >= (1ull << 30)) throw std::runtime_error("batch too large (max 2^30 reads per batch)");
+  const uint64_t total_words = n_reads ? word_off[n_reads] : 0;
+  ix->word_off.reserve(n_reads + 1);
+  ix->packed.reserve(total_words + 2);
+  ix->len.reserve(n_reads);
+  ix->seeds.reserve(n_reads);
+  ix->n_reads = (uint32_t)n_reads;
+  ix->info[5] = (double)(total_words * 4 + (n_reads + 1) * 4 + n_reads * 8);
+  HostBatch hb;
+  hb.packed = packed;
+  hb.word_off = word_off;
+  hb.len = len;
+  hb.seeds = seeds;
+  do_map(ix, &hb);
   GQ_CATCH
 }
 
@@ -808,8 +907,10 @@ int gq_coverage_fetch(gq_index* ix, uint16_t* allele_sum, uint16_t* per_base, ui
   GQ_CATCH
 }
 
+}  // extern "C"
+
 // all groups of this handle as (slot, alleles) -> raw count; singles first from the dense array
-static void collect_groups(gq_index* ix, std::map<std::vector<uint32_t>, uint64_t>& out, bool multi_only) {
+void collect_groups(gq_index* ix, std::map<std::vector<uint32_t>, uint64_t>& out, bool multi_only) {
   CUDA_OK(cudaSetDevice(ix->device));
   CUDA_OK(cudaStreamSynchronize(ix->stream));
   const gq::HostIndex& h = ix->h;
@@ -858,6 +959,8 @@ static int write_groups(const std::map<std::vector<uint32_t>, uint64_t>& g, uint
   return 0;
 }
 
+extern "C" {
+
 int gq_coverage_grouped(gq_index* ix, uint32_t* words, uint64_t* n_words) {
   GQ_TRY
   if (!ix || !n_words) throw std::runtime_error("null argument");
@@ -876,6 +979,8 @@ int gq_coverage_groups_export(gq_index* ix, uint32_t* words, uint64_t* n_words) 
   GQ_CATCH
 }
 
+}  // extern "C"
+
 // Rebuild the multi-allele group table + record pool from `g` on the host (with the device's hash) and upload
 // them, growing both so that the table is at most a quarter full. Drops leaked / never-counted records.
 static uint32_t hash_group_host(const std::vector<uint32_t>& key) {
@@ -889,7 +994,7 @@ static uint32_t hash_group_host(const std::vector<uint32_t>& key) {
   return hsh;
 }
 
-static void rebuild_groups(gq_index* ix, const std::map<std::vector<uint32_t>, uint64_t>& g, size_t min_cap) {
+void rebuild_groups(gq_index* ix, const std::map<std::vector<uint32_t>, uint64_t>& g, size_t min_cap) {
   size_t pool_words = 0;
   for (auto& e : g) pool_words += e.first.size() + 1;
   size_t cap = std::max<size_t>(ix->gtab.cap, min_cap);
@@ -928,6 +1033,8 @@ static void grow_groups(gq_index* ix) {
   collect_groups(ix, g, true);
   rebuild_groups(ix, g, ix->gtab.cap * 4);
 }
+
+extern "C" {
 
 int gq_coverage_groups_import(gq_index* ix, const uint32_t* words, uint64_t n_words, int replace) {
   GQ_TRY
@@ -1108,6 +1215,13 @@ int gq_set_option(gq_index* ix, const char* name, int64_t value) {
     ix->super_in_smem = value != 0;
   } else
     throw std::runtime_error("unknown option: " + n);
+  GQ_CATCH
+}
+
+int gq_last_kernel_ms(gq_index* ix, double ms[8]) {
+  GQ_TRY
+  if (!ix || !ms) throw std::runtime_error("null argument");
+  for (int i = 0; i < 8; ++i) ms[i] = ix->kernel_ms[i];
   GQ_CATCH
 }
 

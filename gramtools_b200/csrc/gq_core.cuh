@@ -19,6 +19,30 @@
 #define GQ_HD inline
 #endif
 
+// Byte model of the algorithm (tools/byte_model.py): the TEST-ONLY host emulation (tests/emu, built with
+// -DGQ_EMU_COUNTERS) records which 32-byte sectors every strand touches in which structure. On the device, and in
+// any build without that define, these macros are the plain accesses.
+#if !defined(__CUDA_ARCH__) && defined(GQ_EMU_COUNTERS)
+namespace gq {
+void gq_emu_touch(const void* p, unsigned bytes);
+void gq_emu_phase(int kernel);  // which kernel's work the following touches belong to
+}
+#define GQ_PHASE(k) ::gq::gq_emu_phase(k)
+#define GQ_TOUCH(p, bytes) ::gq::gq_emu_touch((const void*)(p), (unsigned)(bytes))
+namespace gq {
+template <class T>
+inline T& gq_emu_at(T* arr, size_t i) {  // the index expression is evaluated once (it may have side effects)
+  gq_emu_touch(arr + i, sizeof(T));
+  return arr[i];
+}
+}
+#define GQ_AT(arr, i) ::gq::gq_emu_at((arr), (size_t)(i))
+#else
+#define GQ_PHASE(k) ((void)0)
+#define GQ_TOUCH(p, bytes) ((void)0)
+#define GQ_AT(arr, i) ((arr)[i])
+#endif
+
 namespace gq {
 
 constexpr uint32_t kBlkShift = 6;     // 64 BWT positions per rank block
@@ -138,6 +162,7 @@ GQ_HD RankBlk load_blk(const RankBlk* p) {
   asm("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(b.cnt), "=l"(b.p0), "=l"(b.p1), "=l"(b.p2) : "l"(p));
   return b;
 #else
+  GQ_TOUCH(p, 32);
   return *p;
 #endif
 }
@@ -147,7 +172,7 @@ GQ_HD uint32_t rank_in_blk(const RankBlk& b, const uint32_t* super4, uint32_t c,
   uint64_t m = ~b.p2 & ((c & 1) ? b.p0 : ~b.p0) & ((c & 2) ? b.p1 : ~b.p1);
   uint32_t r = i & 63u;
   uint64_t below = r ? (m & (~0ull >> (64 - r))) : 0ull;
-  return super4[c] + ((uint32_t)(b.cnt >> (16 * c)) & 0xFFFFu) + (uint32_t)popc64(below);
+  return GQ_AT(super4, c) + ((uint32_t)(b.cnt >> (16 * c)) & 0xFFFFu) + (uint32_t)popc64(below);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -215,7 +240,7 @@ GQ_HD bool exit_site_in_place(Stack& s, const IndexView& v, uint32_t site, uint3
   ++nt;
   t[3] = nt | (ng << 16);
   uint32_t slot = (site - 5) >> 1;
-  t[1] = t[2] = v.site_sa[slot];
+  t[1] = t[2] = GQ_AT(v.site_sa, slot);
   return true;
 }
 
@@ -230,7 +255,7 @@ GQ_HD void process_jump(Stack& s, const IndexView& v) {
     uint32_t site = marker;
     if (!exit_site_in_place(s, v, site, allele)) return;
     while (true) {
-      uint32_t nxt = v.tm_odd[(site - 5) >> 1];
+      uint32_t nxt = GQ_AT(v.tm_odd, (site - 5) >> 1);
       if (nxt == 0) {  // plain exit: commit, nothing adjacent
         t[0] = pos | (K_READY << 28);
         return;
@@ -243,7 +268,7 @@ GQ_HD void process_jump(Stack& s, const IndexView& v) {
       }
       // double exit: parent's allele from par_map
       uint32_t slot = (site - 5) >> 1;
-      uint32_t pal = v.par[2 * slot + 1];
+      uint32_t pal = GQ_AT(v.par, 2 * slot + 1);
       if (!exit_site_in_place(s, v, nxt, pal)) return;
       site = nxt;
     }
@@ -259,13 +284,13 @@ GQ_HD void process_jump(Stack& s, const IndexView& v) {
     ++ng;
     t[3] = nt | (ng << 16);
     t[0] = pos | (K_READY << 28);
-    t[1] = v.allele_iv[2 * slot];
-    t[2] = v.allele_iv[2 * slot + 1];
+    t[1] = GQ_AT(v.allele_iv, 2 * slot);
+    t[2] = GQ_AT(v.allele_iv, 2 * slot + 1);
     // direct deletions and double entries hang off the entered state
-    uint32_t b = v.tm_even_off[slot], e = v.tm_even_off[slot + 1];
+    uint32_t b = GQ_AT(v.tm_even_off, slot), e = GQ_AT(v.tm_even_off, slot + 1);
     uint32_t base_top = s.top;
     for (uint32_t j = b; j < e; ++j) {
-      uint32_t id = v.tm_even[2 * j], del = v.tm_even[2 * j + 1];
+      uint32_t id = GQ_AT(v.tm_even, 2 * j), del = GQ_AT(v.tm_even, 2 * j + 1);
       // copies must be taken from the entered state, which is no longer the top after the 1st push
       uint32_t save_top = s.top;
       uint32_t* src = s.mem + base_top;
@@ -302,7 +327,7 @@ GQ_HD void scan_markers(Stack& s, const IndexView& v, uint32_t pos, uint32_t lo,
     if (hi - first < 63u) m &= ~0ull >> (63u - (hi - first));
     if (!m) continue;
     uint64_t all = b.p2 & b.p0;
-    uint32_t mr0 = v.mrank_blk[blk];
+    uint32_t mr0 = GQ_AT(v.mrank_blk, blk);
     while (m) {
 #if defined(__CUDA_ARCH__)
       uint32_t bit = __ffsll((long long)m) - 1;
@@ -311,7 +336,7 @@ GQ_HD void scan_markers(Stack& s, const IndexView& v, uint32_t pos, uint32_t lo,
 #endif
       m &= m - 1;
       uint32_t mr = mr0 + (bit ? (uint32_t)popc64(all & (~0ull >> (64 - bit))) : 0u);
-      uint32_t marker = v.marker_hit[8 * mr], allele = v.marker_hit[8 * mr + 1];
+      uint32_t marker = GQ_AT(v.marker_hit, 8 * mr), allele = GQ_AT(v.marker_hit, 8 * mr + 1);
       if (marker == 0) continue;
       // copy of the scanned state (always at base_top) with the locus in the header
       uint32_t* src = s.mem + base_top;

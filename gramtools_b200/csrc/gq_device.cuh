@@ -10,7 +10,7 @@
 #if defined(__CUDA_ARCH__)
 #define GQ_LDG(p) __ldg(p)
 #else
-#define GQ_LDG(p) (*(p))
+#define GQ_LDG(p) (*(GQ_TOUCH((p), sizeof(*(p))), (p)))
 #endif
 #if defined(__CUDACC__)
 #define GQ_DEV __host__ __device__
@@ -32,6 +32,7 @@ GQ_DEV inline uint32_t gq_atomic_add(uint32_t* p, uint32_t v) {
 #if defined(__CUDA_ARCH__)
   return atomicAdd(p, v);
 #else
+  GQ_TOUCH(p, 4);
   uint32_t o = *p;
   *p += v;
   return o;
@@ -42,6 +43,7 @@ GQ_DEV inline void gq_red_add(uint32_t* p, uint32_t v) {
 #if defined(__CUDA_ARCH__)
   asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 #else
+  GQ_TOUCH(p, 4);
   *p += v;
 #endif
 }
@@ -72,6 +74,7 @@ GQ_DEV inline uint32_t gq_atomic_inc_aggregated(uint32_t* p) {
   base = __shfl_sync(m, base, leader);
   return base + __popc(m & ((1u << lane) - 1u));
 #else
+  GQ_TOUCH(p, 4);
   return (*p)++;
 #endif
 }
@@ -226,7 +229,7 @@ struct EmitStage {
     uint32_t c_lo = 0, c_hi = 0, c_site = 0, c_al = 0;
     for (uint32_t i = lo;; ++i) {
       uint32_t p = GQ_LDG(v->sa + i);
-      const Node& nd = v->nodes[GQ_LDG(v->pos2node + p)];
+      const Node& nd = GQ_AT(v->nodes, GQ_LDG(v->pos2node + p));
       uint32_t site = nd.site, al = (uint32_t)nd.allele;
       if (site == 0) {
         if (cached) put(c_lo, c_hi, c_site, c_al, true);
@@ -313,12 +316,12 @@ GQ_DEV inline void list_mapped(const SearchOut& o, uint32_t strand) {
 #if defined(__CUDA_ARCH__)
     const uint32_t old = atomicOr(o.listed + strand, kSurvListed);
 #else
-    const uint32_t old = o.listed[strand];
-    o.listed[strand] |= kSurvListed;
+    const uint32_t old = GQ_AT(o.listed, strand);
+    GQ_AT(o.listed, strand) |= kSurvListed;
 #endif
     if (old & kSurvListed) return;
   }
-  o.mapped_list[gq_atomic_inc_aggregated(o.n_mapped)] = strand;
+  GQ_AT(o.mapped_list, gq_atomic_inc_aggregated(o.n_mapped)) = strand;
 }
 
 GQ_DEV inline void lane_finish_strand(Lane& ln, const SearchOut& o) {
@@ -327,20 +330,20 @@ GQ_DEV inline void lane_finish_strand(Lane& ln, const SearchOut& o) {
     uint32_t off = gq_atomic_add(o.pool_used, words);
     if (off + words > o.pool_cap) ln.s.overflow = true;
     else {
-      for (uint32_t w = 0; w < words; ++w) o.pool[off + w] = ln.s.mem[ln.s.limit + w];
-      o.st_off[ln.strand] = off;
-      o.st_words[ln.strand] = words;
-      o.st_count[ln.strand] = ln.n_states;
+      for (uint32_t w = 0; w < words; ++w) GQ_AT(o.pool, off + w) = ln.s.mem[ln.s.limit + w];
+      GQ_AT(o.st_off, ln.strand) = off;
+      GQ_AT(o.st_words, ln.strand) = words;
+      GQ_AT(o.st_count, ln.strand) = ln.n_states;
     }
   }
   if (ln.s.overflow) {
-    o.status[ln.strand] = ST_OVERFLOW;
-    o.overflow_list[gq_atomic_add(o.n_overflow, 1u)] = ln.strand;
+    GQ_AT(o.status, ln.strand) = ST_OVERFLOW;
+    GQ_AT(o.overflow_list, gq_atomic_add(o.n_overflow, 1u)) = ln.strand;
   } else if (ln.n_states) {
-    o.status[ln.strand] = ST_MAPPED;
+    GQ_AT(o.status, ln.strand) = ST_MAPPED;
     list_mapped(o, ln.strand);
   } else
-    o.status[ln.strand] = ST_UNCLASSIFIED;
+    GQ_AT(o.status, ln.strand) = ST_UNCLASSIFIED;
   ln.state = LS_IDLE;
 }
 
@@ -348,19 +351,19 @@ GQ_DEV inline void lane_finish_strand(Lane& ln, const SearchOut& o) {
 GQ_DEV inline void lane_refill(Lane& ln, const IndexView& v, const BatchView& b, const SearchOut& o, uint32_t strand,
                                uint32_t* arena, uint32_t arena_words) {
   const uint32_t r = strand >> 1;
-  const uint32_t L = b.len[r];
+  const uint32_t L = GQ_AT(b.len, r);
   const uint32_t k = v.k;
   ln.strand = strand;
   ln.state = LS_IDLE;
   if (L == 0) {  // non-ACGT read, emptied by the encoder: skipped (quasimap.cpp:108-113)
-    o.status[strand] = ST_SKIPPED;
+    GQ_AT(o.status, strand) = ST_SKIPPED;
     return;
   }
   if (L < k) {  // cannot be seeded (UB in the reference, quasimap.cpp:206-210): counted as missing k-mer
-    o.status[strand] = ST_MISSING_KMER;
+    GQ_AT(o.status, strand) = ST_MISSING_KMER;
     return;
   }
-  ln.rd = ReadCursor{b.packed + b.word_off[r], L, strand & 1u, 0, 0, 0};
+  ln.rd = ReadCursor{b.packed + GQ_AT(b.word_off, r), L, strand & 1u, 0, 0, 0};
   // seeding k-mer = last k bases of the strand; its code (base j at bits [2j,2j+2)) is a bit-field of the
   // packed read: the last k pairs for the forward strand, the pair-reversed complement of the first k
   // pairs for the reverse strand
@@ -374,7 +377,7 @@ GQ_DEV inline void lane_refill(Lane& ln, const IndexView& v, const BatchView& b,
   }
   uint32_t sb = GQ_LDG(v.kmer_off + code), se = GQ_LDG(v.kmer_off + code + 1);
   if (sb == se) {  // the seeding k-mer itself is not indexed: the k-mer filter fails
-    o.status[strand] = ST_MISSING_KMER;
+    GQ_AT(o.status, strand) = ST_MISSING_KMER;
     return;
   }
   ln.s.mem = arena;
@@ -385,7 +388,7 @@ GQ_DEV inline void lane_refill(Lane& ln, const IndexView& v, const BatchView& b,
   ln.arena_words = arena_words;
   uint32_t sp = 0;
   for (uint32_t j = sb; j < se; ++j) {
-    KmerState ks = v.kmer_states[j];
+    KmerState ks = GQ_AT(v.kmer_states, j);
     uint32_t words = entry_words(ks.counts);
     if (sp + words + 3 > ln.s.limit) {
       ln.s.overflow = true;
@@ -437,9 +440,9 @@ GQ_DEV inline void lane_step_wide(Lane& ln, const IndexView& v, SuperPtr super_c
   const uint64_t m0 = ~B0.p2 & (B0.p0 ^ x0) & (B0.p1 ^ x1);
   const uint64_t m1 = ~B1.p2 & (B1.p0 ^ x0) & (B1.p1 ^ x1);
   const uint32_t ra = lo & 63u, rb = (hi + 1) & 63u;
-  const uint32_t r0 = super_c[4 * (b0 >> (kSuperShift - kBlkShift)) + c] + ((uint32_t)(B0.cnt >> (16 * c)) & 0xFFFFu) +
+  const uint32_t r0 = GQ_AT(super_c, 4 * (b0 >> (kSuperShift - kBlkShift)) + c) + ((uint32_t)(B0.cnt >> (16 * c)) & 0xFFFFu) +
                       (uint32_t)popc64(m0 & ((1ull << ra) - 1));
-  const uint32_t r1 = super_c[4 * (b1 >> (kSuperShift - kBlkShift)) + c] + ((uint32_t)(B1.cnt >> (16 * c)) & 0xFFFFu) +
+  const uint32_t r1 = GQ_AT(super_c, 4 * (b1 >> (kSuperShift - kBlkShift)) + c) + ((uint32_t)(B1.cnt >> (16 * c)) & 0xFFFFu) +
                       (uint32_t)popc64(m1 & ((1ull << rb) - 1));
   if (r1 <= r0) {
     ln.state = LS_EV_POP;
@@ -480,7 +483,7 @@ GQ_DEV inline void lane_text_step(Lane& ln, const IndexView& v) {
   const uint2 raw = __ldg(reinterpret_cast<const uint2*>(v.text_grp) + g);
   const uint32_t codes = raw.x, info = raw.y;
 #else
-  const uint32_t codes = v.text_grp[g].codes, info = v.text_grp[g].info;
+  const uint32_t codes = GQ_AT(v.text_grp, g).codes, info = GQ_AT(v.text_grp, g).info;
 #endif
   const uint32_t run_mis = gq_clz(ln.rd.top32() ^ (codes << (2 * sh))) >> 1;  // equal bases from the top (<= 16)
   const uint32_t run_mark = gq_clz(info << (16 + sh));                   // marker-free positions from the top
@@ -654,6 +657,7 @@ GQ_DEV inline void lane_event_top(Lane& ln, const IndexView& v, const SearchOut&
       return;
     }
     uint32_t* d = o.pool + off;
+    GQ_TOUCH(d, 4 * words);
     d[0] = t[1];
     d[1] = t[2];
     d[2] = nt;
@@ -664,10 +668,10 @@ GQ_DEV inline void lane_event_top(Lane& ln, const IndexView& v, const SearchOut&
       d[4 + 2 * nt + 2 * j] = T[2 * nt + j];
       d[4 + 2 * nt + 2 * j + 1] = kNoAllele;
     }
-    o.st_off[ln.strand] = off;
-    o.st_words[ln.strand] = words;
-    o.st_count[ln.strand] = 1;
-    o.status[ln.strand] = ST_MAPPED;
+    GQ_AT(o.st_off, ln.strand) = off;
+    GQ_AT(o.st_words, ln.strand) = words;
+    GQ_AT(o.st_count, ln.strand) = 1;
+    GQ_AT(o.status, ln.strand) = ST_MAPPED;
     list_mapped(o, ln.strand);
     ln.state = LS_IDLE;
     return;
@@ -707,17 +711,17 @@ constexpr uint32_t kMaxSplit = 32;    // wider than this after narrowing: genera
 GQ_DEV inline uint32_t preseed_lookup(const IndexView& v, const BatchView& b, const SearchOut& o, uint32_t strand,
                                       uint32_t& sb) {
   const uint32_t r = strand >> 1;
-  const uint32_t L = b.len[r];
+  const uint32_t L = GQ_AT(b.len, r);
   const uint32_t k = v.k;
   if (L == 0) {  // non-ACGT read, emptied by the encoder: skipped (quasimap.cpp:108-113)
-    o.status[strand] = ST_SKIPPED;
+    GQ_AT(o.status, strand) = ST_SKIPPED;
     return 0;
   }
   if (L < k) {  // cannot be seeded (UB in the reference, quasimap.cpp:206-210): counted as missing k-mer
-    o.status[strand] = ST_MISSING_KMER;
+    GQ_AT(o.status, strand) = ST_MISSING_KMER;
     return 0;
   }
-  const uint32_t* w = b.packed + b.word_off[r];
+  const uint32_t* w = b.packed + GQ_AT(b.word_off, r);
   uint32_t code;
   if (strand & 1u) {
     code = pair_reverse32(~GQ_LDG(w)) >> (32 - 2 * k);
@@ -729,7 +733,7 @@ GQ_DEV inline uint32_t preseed_lookup(const IndexView& v, const BatchView& b, co
   sb = GQ_LDG(v.seed_off + code);  // seed-pass view of the k-mer index: entries per suffix / wide state
   const uint32_t se = GQ_LDG(v.seed_off + code + 1);
   if (sb == se) {  // the seeding k-mer itself is not indexed: the k-mer filter fails
-    o.status[strand] = ST_MISSING_KMER;
+    GQ_AT(o.status, strand) = ST_MISSING_KMER;
     return 0;
   }
   return se - sb;
@@ -740,10 +744,10 @@ GQ_DEV inline void send_to_general(const SeedOut& pre, uint32_t strand) {
 #if defined(__CUDA_ARCH__)
   const uint32_t old = atomicOr(pre.surv_cnt + strand, kSurvGeneral);
 #else
-  const uint32_t old = pre.surv_cnt[strand];
-  pre.surv_cnt[strand] |= kSurvGeneral;
+  const uint32_t old = GQ_AT(pre.surv_cnt, strand);
+  GQ_AT(pre.surv_cnt, strand) |= kSurvGeneral;
 #endif
-  if (!(old & kSurvGeneral)) pre.gen_list[gq_atomic_add(pre.n_gen, 1u)] = strand;
+  if (!(old & kSurvGeneral)) GQ_AT(pre.gen_list, gq_atomic_add(pre.n_gen, 1u)) = strand;
 }
 
 // part 2: the candidates of ONE seed state, as a plan of entries {first SA index, number of suffixes,
@@ -874,7 +878,7 @@ GQ_DEV inline uint32_t seed_state_cands(const IndexView& v, SuperPtr super_c, co
   const uint2 raw = __ldg(reinterpret_cast<const uint2*>(v.seed_ent) + j);
   const uint32_t key = raw.x, aux = raw.y;
 #else
-  const uint32_t key = v.seed_ent[j].key, aux = v.seed_ent[j].aux;
+  const uint32_t key = GQ_AT(v.seed_ent, j).key, aux = GQ_AT(v.seed_ent, j).aux;
 #endif
   if (aux & 0x80000000u) {
     uint32_t m = (aux >> 24) & 0x7Fu;  // context bases, up to the first marker / the text start
@@ -899,6 +903,7 @@ GQ_DEV inline uint32_t seed_state_cands(const IndexView& v, SuperPtr super_c, co
 GQ_DEV inline void seed_write(const SeedCands& c, uint32_t n, const SeedOut& pre, uint32_t strand, uint32_t j,
                               uint32_t base) {
   uint32_t* d = pre.rec + 4 * (size_t)base;
+  GQ_TOUCH(d, 16 * n);
   for (uint32_t i = 0; i < n; ++i, d += 4) {
     d[0] = strand;
     d[1] = j;
@@ -941,17 +946,18 @@ GQ_DEV inline void fast_begin(FastLane& f, const IndexView& v, const BatchView& 
   const uint32_t strand = c.x, j = c.y, p = c.z, w0 = c.w;
 #else
   const uint32_t* c = pre.rec + 4 * (size_t)idx;
+  GQ_TOUCH(c, 16);
   const uint32_t strand = c[0], j = c[1], p = c[2], w0 = c[3];
 #endif
   const uint32_t r = strand >> 1;
-  const uint32_t L = b.len[r], woff = b.word_off[r];
+  const uint32_t L = GQ_AT(b.len, r), woff = GQ_AT(b.word_off, r);
   f.ln.strand = strand;
   f.result = FAST_NONE;
   f.p_valid = true;
   f.nt = f.ng = 0;
   f.nt0 = f.ng0 = f.path_off = 0;
   if (TRACK) {
-    const KmerState ks = v.kmer_states[j];
+    const KmerState ks = GQ_AT(v.kmer_states, j);
     f.nt0 = ks.counts & 0xFFFFu;
     f.ng0 = ks.counts >> 16;
     f.path_off = ks.path_off;
@@ -976,6 +982,7 @@ GQ_DEV inline void fast_event(FastLane& f, const IndexView& v) {
   const uint4 ja = __ldg(reinterpret_cast<const uint4*>(jr)), jb = __ldg(reinterpret_cast<const uint4*>(jr) + 1);
   const uint32_t marker = ja.x, allele = ja.y, jlo = ja.z, jhi = ja.w, snp = jb.x, p_jump = jb.z, p_site = jb.w;
 #else
+  GQ_TOUCH(jr, 32);
   const uint32_t marker = jr[0], allele = jr[1], jlo = jr[2], jhi = jr[3], snp = jr[4], p_jump = jr[6], p_site = jr[7];
 #endif
   if (marker == 0) {
@@ -1082,7 +1089,7 @@ GQ_DEV inline uint32_t fast_outcome(FastLane& f, const IndexView& v) {
   GQ_COUNT(7);  // candidates finished by the fast path
   if (!(f.nt | f.ng | f.nt0 | f.ng0)) {
     const uint32_t pf = f.p_valid ? f.ln.p : GQ_LDG(v.sa + f.ln.lo);
-    const Node& nd = v.nodes[GQ_LDG(v.pos2node + pf)];
+    const Node& nd = GQ_AT(v.nodes, GQ_LDG(v.pos2node + pf));
     if (nd.site != 0) {
       f.T[0] = nd.site;
       f.T[1] = (uint32_t)nd.allele;
@@ -1096,6 +1103,7 @@ GQ_DEV inline uint32_t fast_outcome(FastLane& f, const IndexView& v) {
 GQ_DEV inline void fast_emit(const FastLane& f, const IndexView& v, const SearchOut& o, uint32_t off) {
   uint32_t* d = o.pool + off;
   const uint32_t nt = f.nt0 + f.nt, ng = f.ng0 + f.ng;
+  GQ_TOUCH(d, 4 * (4 + 2 * nt + 2 * ng));
   d[0] = f.ln.lo;
   d[1] = f.ln.hi;
   d[2] = nt;
@@ -1112,9 +1120,9 @@ GQ_DEV inline void fast_emit(const FastLane& f, const IndexView& v, const Search
     *d++ = kNoAllele;
   }
   const uint32_t strand = f.ln.strand;
-  o.st_off[strand] = off;
-  o.st_words[strand] = 4 + 2 * nt + 2 * ng;
-  o.st_count[strand] = 1;
+  GQ_AT(o.st_off, strand) = off;
+  GQ_AT(o.st_words, strand) = 4 + 2 * nt + 2 * ng;
+  GQ_AT(o.st_count, strand) = 1;
 }
 
 // a finished candidate claims its strand: 0 = first one (emit), otherwise the strand is (or becomes) the
@@ -1139,8 +1147,8 @@ GQ_DEV inline bool fast_claim(const SeedOut& pre, uint32_t strand) {
 // does not depend on the order in which windows are visited.
 GQ_DEV inline void classify_strand(const IndexView& v, const BatchView& b, const SearchOut& o, uint32_t strand) {
   const uint32_t r = strand >> 1;
-  const uint32_t L = b.len[r], k = v.k;
-  const uint32_t* w = b.packed + b.word_off[r];
+  const uint32_t L = GQ_AT(b.len, r), k = v.k;
+  const uint32_t* w = b.packed + GQ_AT(b.word_off, r);
   const bool rc = (strand & 1u) != 0;
   const uint32_t mask = (k == 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
   const uint32_t n_words = (L + 15) >> 4;
@@ -1160,7 +1168,7 @@ GQ_DEV inline void classify_strand(const IndexView& v, const BatchView& b, const
       if (nw < n_words) win |= (uint64_t)GQ_LDG(w + nw) << 32;
     }
   }
-  o.status[strand] = missing ? ST_MISSING_KMER : ST_NO_EXTENSION;
+  GQ_AT(o.status, strand) = missing ? ST_MISSING_KMER : ST_NO_EXTENSION;
 }
 
 // Single-lane driver (host emulation and a reference for the kernels): seed pass, text walk of every
@@ -1168,28 +1176,30 @@ GQ_DEV inline void classify_strand(const IndexView& v, const BatchView& b, const
 // apply; then the k-mer filter if nothing mapped.
 GQ_DEV inline void map_strand(const IndexView& v, const uint32_t* super_cnt, const BatchView& b, const SearchOut& o,
                               const SeedOut& pre, uint32_t strand, uint32_t* arena, uint32_t arena_words) {
-  bool general = o.status[strand] == ST_OVERFLOW;  // overflow re-runs always use the general machinery
+  bool general = GQ_AT(o.status, strand) == ST_OVERFLOW;  // overflow re-runs always use the general machinery
   if (!general) {
+    GQ_PHASE(0);  // seed_kernel
     uint32_t sb = 0;
     const uint32_t ns = preseed_lookup(v, b, o, strand, sb);
     if (ns == 0) return;
-    o.status[strand] = ST_UNCLASSIFIED;
-    pre.surv_cnt[strand] = 0;
+    GQ_AT(o.status, strand) = ST_UNCLASSIFIED;
+    GQ_AT(pre.surv_cnt, strand) = 0;
     // the emulation reuses the candidate pool strand by strand
     uint32_t total = 0;
     const uint32_t r = strand >> 1;
     for (uint32_t t = 0; t < ns && !general; ++t) {
       SeedCands cands;
-      const uint32_t cnt = seed_state_cands(v, super_cnt, b.packed + b.word_off[r], b.len[r], strand & 1u, sb + t, cands);
+      const uint32_t cnt = seed_state_cands(v, super_cnt, b.packed + GQ_AT(b.word_off, r), GQ_AT(b.len, r), strand & 1u, sb + t, cands);
       if (cnt == kNoAllele || total + cnt > pre.cap) general = true;
       else {
-        seed_write(cands, cnt, pre, strand, v.seed_state[sb + t], total);
+        seed_write(cands, cnt, pre, strand, GQ_AT(v.seed_state, sb + t), total);
         total += cnt;
       }
     }
     if (!general) {
       for (uint32_t i = 0; i < total; ++i) {
         FastLane f;
+        GQ_PHASE(1);  // verify_kernel
         fast_begin<false>(f, v, b, pre, i);
         {  // verify pass (verify_kernel), then the full walk from the start (text_kernel)
           const uint32_t pos0 = f.ln.pos;
@@ -1198,6 +1208,8 @@ GQ_DEV inline void map_strand(const IndexView& v, const uint32_t* super_cnt, con
             if (fast_running(f) && f.ln.state == LS_EV_TSCAN) fast_event<false>(f, v);
           }
           if (!fast_alive(f)) continue;
+          GQ_TOUCH(pre.rec + 4 * (size_t)i, 16);  // the survivor is copied to the text kernel's list
+          GQ_PHASE(2);                            // text_kernel
           fast_begin<true>(f, v, b, pre, i);
         }
         while (fast_running(f)) {
@@ -1209,21 +1221,22 @@ GQ_DEV inline void map_strand(const IndexView& v, const uint32_t* super_cnt, con
           if (!fast_claim(pre, strand)) continue;
           const uint32_t off = gq_atomic_add(o.pool_used, words);
           if (off + words > o.pool_cap) {
-            o.status[strand] = ST_OVERFLOW;
-            o.overflow_list[gq_atomic_add(o.n_overflow, 1u)] = strand;
+            GQ_AT(o.status, strand) = ST_OVERFLOW;
+            GQ_AT(o.overflow_list, gq_atomic_add(o.n_overflow, 1u)) = strand;
             return;
           }
           fast_emit(f, v, o, off);
-          o.status[strand] = ST_MAPPED;
+          GQ_AT(o.status, strand) = ST_MAPPED;
           list_mapped(o, strand);
         } else if (f.result == FAST_BAIL)
           send_to_general(pre, strand);
       }
-      general = (pre.surv_cnt[strand] & kSurvGeneral) != 0;
+      general = (GQ_AT(pre.surv_cnt, strand) & kSurvGeneral) != 0;
     }
   }
   if (general) {
     GQ_COUNT(8);  // strands through the general machinery
+    GQ_PHASE(3);  // search_kernel
     Lane ln;
     ln.state = LS_IDLE;
     lane_refill(ln, v, b, o, strand, arena, arena_words);
@@ -1234,7 +1247,10 @@ GQ_DEV inline void map_strand(const IndexView& v, const uint32_t* super_cnt, con
       else lane_event(ln, v, o);
     }
   }
-  if (o.status[strand] == ST_UNCLASSIFIED) classify_strand(v, b, o, strand);
+  if (GQ_AT(o.status, strand) == ST_UNCLASSIFIED) {
+    GQ_PHASE(4);  // classify_kernel
+    classify_strand(v, b, o, strand);
+  }
 }
 
 struct Scratch {
@@ -1331,14 +1347,14 @@ GQ_DEV void assign_nested(const IndexView& v, LocusLists& l, uint32_t site, uint
     l.used[l.n_used++] = site;
     add_locus(l, site, allele);
     uint32_t slot = (site - 5) >> 1;
-    uint32_t ps = v.par[2 * slot];
+    uint32_t ps = GQ_AT(v.par, 2 * slot);
     if (ps == 0) {
       bool seen = false;
       for (uint32_t i = 0; i < l.n_base; ++i) seen |= l.base[i] == site;
       if (!seen) l.base[l.n_base++] = site;
       return;
     }
-    allele = v.par[2 * slot + 1];
+    allele = GQ_AT(v.par, 2 * slot + 1);
     site = ps;
   }
 }
@@ -1349,7 +1365,7 @@ GQ_DEV void locus_finder(const IndexView& v, const StateRec& st, LocusLists& l) 
     uint32_t last_al = 0;
     for (uint32_t i = st.lo;; ++i) {
       uint32_t p = GQ_LDG(v.sa + i);
-      last_al = (uint32_t)v.nodes[GQ_LDG(v.pos2node + p)].allele;
+      last_al = (uint32_t)GQ_AT(v.nodes, GQ_LDG(v.pos2node + p)).allele;
       add_locus(l, seed_site, last_al);
       if (i == st.hi) break;
     }
@@ -1387,7 +1403,7 @@ struct Trav {
   bool first;
   uint32_t start_pos, end_pos;
   bool bad;
-  GQ_DEV inline const Node& node() const { return v->nodes[cur]; }
+  GQ_DEV inline const Node& node() const { return GQ_AT(v->nodes, cur); }
   GQ_DEV void update_coordinates() {
     const Node& nd = node();
     end_pos = 0;
@@ -1421,7 +1437,7 @@ struct Trav {
       cur = kNoAllele;
       return;
     }
-    cur = v->edges[node().edge_off + allele];
+    cur = GQ_AT(v->edges, node().edge_off + allele);
     update_coordinates();
   }
   // returns false when the traversal is over
@@ -1445,7 +1461,7 @@ struct Hull {
   bool overflow;
 };
 GQ_DEV void hull_add(const IndexView& v, Hull& h, uint32_t node, uint32_t s, uint32_t e) {
-  if (v.nodes[node].len == 0) return;  // process_Node :282-287
+  if (GQ_AT(v.nodes, node).len == 0) return;  // process_Node :282-287
   for (uint32_t i = 0; i < h.n; ++i) {
     if (h.e[3 * i] == node) {
       if (s < h.e[3 * i + 1]) h.e[3 * i + 1] = s;
@@ -1463,11 +1479,12 @@ GQ_DEV void hull_add(const IndexView& v, Hull& h, uint32_t node, uint32_t s, uin
   ++h.n;
 }
 
-GQ_DEV uint32_t hash_group(uint32_t slot, const uint32_t* loci, uint32_t n) {
+// `alleles`: n allele ids, `stride` words apart (2 inside a sorted locus list, 1 in a group record)
+GQ_DEV uint32_t hash_group(uint32_t slot, const uint32_t* alleles, uint32_t n, uint32_t stride) {
   uint32_t h = 2166136261u ^ slot;
   h *= 16777619u;
   for (uint32_t i = 0; i < n; ++i) {
-    h ^= loci[2 * i + 1];
+    h ^= alleles[stride * i];
     h *= 16777619u;
   }
   h ^= h >> 15;
@@ -1478,9 +1495,10 @@ GQ_DEV uint32_t hash_group(uint32_t slot, const uint32_t* loci, uint32_t n) {
 // counter the caller bumps when it commits), or kNoAllele when the table or the record pool is full — the caller
 // then gives the strand back uncommitted and the host grows the table (capi.cu: grow_groups). An inserted key
 // that is never counted is harmless: readers skip zero counters.
-GQ_DEV uint32_t grouped_find_or_insert(const CoverageView& c, uint32_t slot, const uint32_t* loci, uint32_t n) {
+GQ_DEV uint32_t grouped_find_or_insert(const CoverageView& c, uint32_t slot, const uint32_t* alleles, uint32_t n,
+                                       uint32_t stride) {
   uint32_t maskc = c.gtab_cap - 1;
-  uint32_t h = hash_group(slot, loci, n) & maskc;
+  uint32_t h = hash_group(slot, alleles, n, stride) & maskc;
   uint32_t mine = 0;  // offset + 1 of a record this thread allocated (lazily)
   uint32_t found = kNoAllele;
   // at most half the table is probed: a table that full is grown rather than searched
@@ -1495,7 +1513,7 @@ GQ_DEV uint32_t grouped_find_or_insert(const CoverageView& c, uint32_t slot, con
         }
         c.gpool[off] = slot;
         c.gpool[off + 1] = n;
-        for (uint32_t i = 0; i < n; ++i) c.gpool[off + 2 + i] = loci[2 * i + 1];
+        for (uint32_t i = 0; i < n; ++i) c.gpool[off + 2 + i] = alleles[stride * i];
         gq_threadfence();
         mine = off + 1;
       }
@@ -1505,7 +1523,7 @@ GQ_DEV uint32_t grouped_find_or_insert(const CoverageView& c, uint32_t slot, con
     // occupied: same key?
     const volatile uint32_t* rec = c.gpool + (cur - 1);
     bool same = rec[0] == slot && rec[1] == n;
-    for (uint32_t i = 0; same && i < n; ++i) same = rec[2 + i] == loci[2 * i + 1];
+    for (uint32_t i = 0; same && i < n; ++i) same = rec[2 + i] == alleles[stride * i];
     if (same) {
       found = h;
       break;
@@ -1521,9 +1539,11 @@ GQ_DEV uint32_t grouped_find_or_insert(const CoverageView& c, uint32_t slot, con
 
 GQ_DEV bool record_strand(const IndexView& v, const BatchView& b, const SearchOut& o, const CoverageView& c,
                               uint32_t strand, uint32_t* arena, uint32_t arena_words) {
-  const uint32_t ns = o.st_count[strand];
-  const uint32_t* recs = o.pool + o.st_off[strand];
-  const uint32_t L = b.len[strand >> 1];
+  GQ_PHASE(5);  // coverage_kernel
+  const uint32_t ns = GQ_AT(o.st_count, strand);
+  const uint32_t* recs = o.pool + GQ_AT(o.st_off, strand);
+  GQ_TOUCH(recs, 4 * GQ_AT(o.st_words, strand));
+  const uint32_t L = GQ_AT(b.len, strand >> 1);
   Scratch sc{arena, 0, arena_words, false};
 
   // ---- pass 1: non-variant mapping count, per-state class keys (MappingInstanceSelector) ----
@@ -1547,14 +1567,14 @@ GQ_DEV bool record_strand(const IndexView& v, const BatchView& b, const SearchOu
       const uint32_t pos0 = GQ_LDG(v.sa + st.lo);
       const uint32_t nid0 = GQ_LDG(v.pos2node + pos0);
       if (st.ng) {
-        const uint32_t site = st.G[0], slot = (site - 5) >> 1, al = (uint32_t)v.nodes[nid0].allele;
-        gq_red_add(c.allele_sum + c.allele_off[slot] + al, 1u);
-        gq_red_add(c.grouped_single + c.allele_off[slot] + al, 1u);
+        const uint32_t site = st.G[0], slot = (site - 5) >> 1, al = (uint32_t)GQ_AT(v.nodes, nid0).allele;
+        gq_red_add(c.allele_sum + GQ_AT(c.allele_off, slot) + al, 1u);
+        gq_red_add(c.grouped_single + GQ_AT(c.allele_off, slot) + al, 1u);
       }
       for (uint32_t j = 0; j < st.nt; ++j) {
         const uint32_t slot = (st.T[2 * j] - 5) >> 1, al = st.T[2 * j + 1];
-        gq_red_add(c.allele_sum + c.allele_off[slot] + al, 1u);
-        gq_red_add(c.grouped_single + c.allele_off[slot] + al, 1u);
+        gq_red_add(c.allele_sum + GQ_AT(c.allele_off, slot) + al, 1u);
+        gq_red_add(c.grouped_single + GQ_AT(c.allele_off, slot) + al, 1u);
       }
       Trav t;
       t.v = &v;
@@ -1563,12 +1583,12 @@ GQ_DEV bool record_strand(const IndexView& v, const BatchView& b, const SearchOu
       t.T = st.T;
       t.ti = st.nt;
       t.first = true;
-      const Node& nd0 = v.nodes[nid0];
+      const Node& nd0 = GQ_AT(v.nodes, nid0);
       t.start_pos = nd0.len > 1 ? pos0 - nd0.start : 0;
       t.end_pos = 0;
       t.bad = false;
       while (t.next()) {
-        const Node& nd = v.nodes[t.cur];
+        const Node& nd = GQ_AT(v.nodes, t.cur);
         if (nd.len == 0 || nd.cov_off == kNoAllele) continue;
         for (uint32_t x = t.start_pos; x <= t.end_pos; ++x) gq_red_add(c.per_base + nd.cov_off + x, 1u);
       }
@@ -1624,7 +1644,7 @@ GQ_DEV bool record_strand(const IndexView& v, const BatchView& b, const SearchOu
   }
   // random_select_entry :97-107
   uint32_t total = nonvar + ncls;
-  uint32_t pick = total == 1 ? 1u : uniform_1_to(b.seeds[strand >> 1], total);
+  uint32_t pick = total == 1 ? 1u : uniform_1_to(GQ_AT(b.seeds, strand >> 1), total);
   if (pick <= nonvar) return true;
   // the (pick - nonvar - 1)-th class in std::map order: the representative with that many smaller ones
   uint32_t want = pick - nonvar - 1;
@@ -1669,7 +1689,7 @@ GQ_DEV bool record_strand(const IndexView& v, const BatchView& b, const SearchOu
         t.T = st.T;
         t.ti = st.nt;
         t.first = true;
-        const Node& nd = v.nodes[nid];
+        const Node& nd = GQ_AT(v.nodes, nid);
         t.start_pos = nd.len > 1 ? pos - nd.start : 0;  // setup_random_access, coverage_graph.cpp:131-144
         t.end_pos = 0;
         t.bad = false;
@@ -1705,7 +1725,7 @@ GQ_DEV bool record_strand(const IndexView& v, const BatchView& b, const SearchOu
       while (e < ll.n_loci && ll.loci[2 * e] == ll.loci[2 * i]) ++e;
       if (e - i > 1) {
         if (ng >= ll.cap) return false;
-        const uint32_t h = grouped_find_or_insert(c, (ll.loci[2 * i] - 5) >> 1, ll.loci + 2 * i, e - i);
+        const uint32_t h = grouped_find_or_insert(c, (ll.loci[2 * i] - 5) >> 1, ll.loci + 2 * i + 1, e - i, 2);
         if (h == kNoAllele) return false;
         ll.used[ng++] = h;
       }
@@ -1717,15 +1737,15 @@ GQ_DEV bool record_strand(const IndexView& v, const BatchView& b, const SearchOu
     uint32_t site = ll.loci[2 * i], slot = (site - 5) >> 1;
     uint32_t e = i;
     while (e < ll.n_loci && ll.loci[2 * e] == site) {
-      gq_red_add(c.allele_sum + c.allele_off[slot] + ll.loci[2 * e + 1], 1u);  // allele_sum.cpp:31-43
+      gq_red_add(c.allele_sum + GQ_AT(c.allele_off, slot) + ll.loci[2 * e + 1], 1u);  // allele_sum.cpp:31-43
       ++e;
     }
-    if (e - i == 1) gq_red_add(c.grouped_single + c.allele_off[slot] + ll.loci[2 * i + 1], 1u);
+    if (e - i == 1) gq_red_add(c.grouped_single + GQ_AT(c.allele_off, slot) + ll.loci[2 * i + 1], 1u);
     else gq_red_add(c.gcount + ll.used[ng++], 1u);
     i = e;
   }
   for (uint32_t i = 0; i < hull.n; ++i) {
-    const Node& nd = v.nodes[hull.e[3 * i]];
+    const Node& nd = GQ_AT(v.nodes, hull.e[3 * i]);
     if (nd.cov_off == kNoAllele) continue;
     for (uint32_t x = hull.e[3 * i + 1]; x <= hull.e[3 * i + 2]; ++x) gq_red_add(c.per_base + nd.cov_off + x, 1u);
   }

@@ -419,11 +419,12 @@ __global__ void __launch_bounds__(256) text_kernel(IndexView v, BatchView b, Sea
 }
 
 void launch_text(const IndexView& v, const BatchView& b, const SearchOut& o, const SeedOut& pre, uint32_t* surv_rec,
-                 uint32_t* n_verified, cudaStream_t st) {
+                 uint32_t* n_verified, cudaStream_t st, cudaEvent_t between) {
   uint32_t work = 2 * (b.read_end - b.read_begin);
   if (work == 0) return;
   uint32_t blocks = min((work + 255) / 256, 148u * 8u);
   verify_kernel<<<blocks, 256, 0, st>>>(v, b, pre, surv_rec, n_verified);
+  if (between) cudaEventRecord(between, st);
   SeedOut ver = pre;  // the text kernel's candidates are the verified ones
   ver.rec = surv_rec;
   ver.n_surv = n_verified;
@@ -629,6 +630,52 @@ void launch_fetch(const uint32_t* allele_sum, uint32_t n_alleles, const uint32_t
   const uint32_t n = n_alleles + n_per_base;
   if (n == 0) return;
   fetch_kernel<<<min((n + 255) / 256, 148u * 8u), 256, 0, st>>>(allele_sum, n_alleles, per_base, n_per_base, out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sparse multi-allele groups for the multi-GPU exchange (comm.cu): every occupied, counted table slot becomes a
+// record [slot, count, n, alleles...] in `words` (+ its start in `rec_off`); n_out = {records, words}.
+__global__ void groups_export_kernel(CoverageView c, uint32_t* __restrict__ words, uint32_t words_cap,
+                                     uint32_t* __restrict__ rec_off, uint32_t rec_cap, uint32_t* __restrict__ n_out) {
+  for (uint32_t h = blockIdx.x * blockDim.x + threadIdx.x; h < c.gtab_cap; h += gridDim.x * blockDim.x) {
+    const uint32_t cur = c.gtab[h], cnt = c.gcount[h];
+    if (!cur || !cnt) continue;
+    const uint32_t* rec = c.gpool + (cur - 1);
+    const uint32_t n = rec[1];
+    const uint32_t i = atomicAdd(n_out, 1u), w = atomicAdd(n_out + 1, 3u + n);
+    if (i >= rec_cap || w + 3 + n > words_cap) continue;  // sized from a first pass: cannot happen
+    rec_off[i] = w;
+    words[w] = rec[0];
+    words[w + 1] = cnt;
+    words[w + 2] = n;
+    for (uint32_t j = 0; j < n; ++j) words[w + 3 + j] = rec[2 + j];
+  }
+}
+
+// add the records of every OTHER rank (gathered, `stride_*` apart per rank) into this GPU's table
+__global__ void groups_import_kernel(CoverageView c, const uint32_t* __restrict__ words, uint32_t stride_words,
+                                     const uint32_t* __restrict__ rec_off, uint32_t stride_recs,
+                                     const uint32_t* __restrict__ counts /* 2 per rank */, uint32_t n_ranks,
+                                     uint32_t my_rank) {
+  for (uint32_t r = 0; r < n_ranks; ++r) {
+    if (r == my_rank) continue;
+    const uint32_t n_rec = counts[2 * r];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rec; i += gridDim.x * blockDim.x) {
+      const uint32_t* rec = words + (size_t)r * stride_words + rec_off[(size_t)r * stride_recs + i];
+      const uint32_t h = grouped_find_or_insert(c, rec[0], rec + 3, rec[2], 1);
+      if (h != kNoAllele) atomicAdd(c.gcount + h, rec[1]);  // table pre-sized by the host: h is always valid
+    }
+  }
+}
+
+void launch_groups_export(const CoverageView& c, uint32_t* words, uint32_t words_cap, uint32_t* rec_off, uint32_t rec_cap,
+                          uint32_t* n_out, cudaStream_t st) {
+  groups_export_kernel<<<min((c.gtab_cap + 255) / 256, 148u * 8u), 256, 0, st>>>(c, words, words_cap, rec_off, rec_cap, n_out);
+}
+
+void launch_groups_import(const CoverageView& c, const uint32_t* words, uint32_t stride_words, const uint32_t* rec_off,
+                          uint32_t stride_recs, const uint32_t* counts, uint32_t n_ranks, uint32_t my_rank, cudaStream_t st) {
+  groups_import_kernel<<<148 * 4, 256, 0, st>>>(c, words, stride_words, rec_off, stride_recs, counts, n_ranks, my_rank);
 }
 
 int search_kernel_smem_limit_superblocks() { return kMaxSuperSmem; }

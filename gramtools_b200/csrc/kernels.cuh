@@ -79,7 +79,7 @@ void launch_seed(const IndexView& v, const BatchView& b, const SearchOut& o, con
 // in *n_verified), then the text kernel over the survivors: strands with one finished candidate get their
 // final state here; the rest is appended to pre.gen_list.
 void launch_text(const IndexView& v, const BatchView& b, const SearchOut& o, const SeedOut& pre, uint32_t* surv_rec,
-                 uint32_t* n_verified, cudaStream_t st);
+                 uint32_t* n_verified, cudaStream_t st, cudaEvent_t between = nullptr);
 
 // General search kernel. list == nullptr: every strand of the slice; otherwise the listed strands (n_list of
 // them, or *n_list_dev when that pointer is given). Strands are seeded from the k-mer index in the kernel.
@@ -103,6 +103,12 @@ void launch_stats(const uint8_t* status, const uint32_t* len, uint32_t n_reads, 
 // out[0, n_alleles) = allele_sum mod 65536, out[n_alleles, n_alleles + n_per_base) = min(per_base, 65535)
 void launch_fetch(const uint32_t* allele_sum, uint32_t n_alleles, const uint32_t* per_base, uint32_t n_per_base,
                   uint16_t* out, cudaStream_t st);
+
+// multi-GPU exchange of the sparse multi-allele groups (comm.cu)
+void launch_groups_export(const CoverageView& c, uint32_t* words, uint32_t words_cap, uint32_t* rec_off, uint32_t rec_cap,
+                          uint32_t* n_out, cudaStream_t st);
+void launch_groups_import(const CoverageView& c, const uint32_t* words, uint32_t stride_words, const uint32_t* rec_off,
+                          uint32_t stride_recs, const uint32_t* counts, uint32_t n_ranks, uint32_t my_rank, cudaStream_t st);
 
 int search_kernel_smem_limit_superblocks();
 

@@ -43,6 +43,18 @@ def load_library():
         "gq_index_allele_offsets": [vp, u64p],
         "gq_index_per_base_layout": [vp, u64p],
         "gq_map_batch": [vp, u8p, u64p, C.c_uint64, u32p],
+        "gq_map_batch_packed": [vp, u32p, u32p, u32p, C.c_uint64, u32p],
+        "gq_packed_words": [u64p, C.c_uint64, u64p],
+        "gq_pack_reads": [u8p, u64p, C.c_uint64, u32p, u32p, u32p, C.c_int],
+        "gq_pack_ascii": [C.c_char_p, u64p, C.c_uint64, u32p, u32p, u32p, C.c_int],
+        "gq_comm_unique_id": [u8p],
+        "gq_comm_init": [vp, u8p, C.c_int, C.c_int],
+        "gq_comm_init_all": [C.POINTER(vp), C.c_int],
+        "gq_comm_destroy": [vp],
+        "gq_comm_version": [C.POINTER(C.c_int)],
+        "gq_coverage_allreduce": [vp],
+        "gq_coverage_allreduce_all": [C.POINTER(vp), C.c_int],
+        "gq_index_clone": [vp, C.c_int, C.POINTER(vp)],
         "gq_batch_upload": [vp, u8p, u64p, C.c_uint64, u32p],
         "gq_map_resident": [vp],
         "gq_batch_status": [vp, u8p],
@@ -58,6 +70,7 @@ def load_library():
         "gq_set_stream": [vp, vp],
         "gq_set_option": [vp, C.c_char_p, C.c_int64],
         "gq_last_run_info": [vp, C.POINTER(C.c_double)],
+        "gq_last_kernel_ms": [vp, C.POINTER(C.c_double)],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)
@@ -111,15 +124,64 @@ def encode_reads(reads):
     return np.ascontiguousarray(bases, dtype=np.uint8), np.asarray(offs, dtype=np.uint64)
 
 
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id():
+    """ncclGetUniqueId through libgq (rank 0 calls it and hands the 128 bytes to the other ranks)."""
+    lib = load_library()
+    a = np.zeros(COMM_ID_BYTES, dtype=np.uint8)
+    if lib.gq_comm_unique_id(_ptr(a, C.c_uint8)) != 0:
+        raise GqError(lib.gq_last_error().decode())
+    return a
+
+
+def pack_reads(bases, offsets, n_threads=None, out=None):
+    """gq_pack_reads: encoded bases (1..4) -> (packed uint32, word_off uint32[n+1], len uint32[n]), the host form
+    gq_map_batch_packed takes. `out` = optional preallocated (packed, word_off, len), e.g. pinned memory."""
+    lib = load_library()
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    n = offsets.size - 1
+    nw = C.c_uint64()
+    if lib.gq_packed_words(_ptr(offsets, C.c_uint64), n, C.byref(nw)) != 0:
+        raise GqError(lib.gq_last_error().decode())
+    if out is None:
+        out = (np.zeros(nw.value, np.uint32), np.zeros(n + 1, np.uint32), np.zeros(max(n, 1), np.uint32))
+    packed, word_off, ln = out
+    assert packed.size >= nw.value and word_off.size >= n + 1 and ln.size >= n
+    if lib.gq_pack_reads(_ptr(bases, C.c_uint8), _ptr(offsets, C.c_uint64), n, _ptr(packed, C.c_uint32),
+                         _ptr(word_off, C.c_uint32), _ptr(ln, C.c_uint32), int(n_threads or os.cpu_count() or 1)) != 0:
+        raise GqError(lib.gq_last_error().decode())
+    return packed, word_off, ln[:n]
+
+
+def pack_ascii(text, offsets, n_threads=None):
+    """gq_pack_ascii: sequence text (bytes) -> packed form; reads with a non-ACGT character become empty."""
+    lib = load_library()
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    n = offsets.size - 1
+    nw = C.c_uint64()
+    lib.gq_packed_words(_ptr(offsets, C.c_uint64), n, C.byref(nw))
+    packed, word_off, ln = np.zeros(nw.value, np.uint32), np.zeros(n + 1, np.uint32), np.zeros(max(n, 1), np.uint32)
+    if lib.gq_pack_ascii(bytes(text), _ptr(offsets, C.c_uint64), n, _ptr(packed, C.c_uint32), _ptr(word_off, C.c_uint32),
+                         _ptr(ln, C.c_uint32), int(n_threads or os.cpu_count() or 1)) != 0:
+        raise GqError(lib.gq_last_error().decode())
+    return packed, word_off, ln[:n]
+
+
 class QuasimapIndex:
     """One PRG index resident on one GPU + its coverage accumulators."""
 
-    def __init__(self, prg, kmer_size, device=0):
+    def __init__(self, prg, kmer_size, device=0, _clone_of=None):
         self._lib = load_library()
-        prg = np.ascontiguousarray(prg, dtype=np.uint32)
         h = C.c_void_p()
         self._h = None
-        self._check(self._lib.gq_index_build(_ptr(prg, C.c_uint32), prg.size, int(kmer_size), int(device), C.byref(h)))
+        if _clone_of is not None:
+            self._check(self._lib.gq_index_clone(_clone_of._h, int(device), C.byref(h)))
+        else:
+            prg = np.ascontiguousarray(prg, dtype=np.uint32)
+            self._check(self._lib.gq_index_build(_ptr(prg, C.c_uint32), prg.size, int(kmer_size), int(device), C.byref(h)))
         self._h = h
         lay = GqLayout()
         self._check(self._lib.gq_index_describe(self._h, C.byref(lay)))
@@ -165,6 +227,48 @@ class QuasimapIndex:
         """handle_reads_buffer (quasimap.cpp:82-118) for one batch held in HOST memory."""
         self._check(self._lib.gq_map_batch(self._h, *self._args(bases, offsets, seeds)))
 
+    def map_batch_packed(self, packed, word_off, length, seeds):
+        """The same batch from 2-bit packed HOST buffers (pack_reads / pack_ascii)."""
+        packed = np.ascontiguousarray(packed, dtype=np.uint32)
+        word_off = np.ascontiguousarray(word_off, dtype=np.uint32)
+        length = np.ascontiguousarray(length, dtype=np.uint32)
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+        n = word_off.size - 1
+        if seeds.size != n or length.size < n:
+            raise GqError("one seed and one length per read expected")
+        self._keep = (packed, word_off, length, seeds)
+        self.n_reads = n
+        self._check(self._lib.gq_map_batch_packed(self._h, _ptr(packed, C.c_uint32), _ptr(word_off, C.c_uint32),
+                                                  _ptr(length, C.c_uint32), n, _ptr(seeds, C.c_uint32)))
+
+    def clone(self, device):
+        """A second handle on another GPU of this process (index built once on the host)."""
+        return QuasimapIndex(None, 0, device=device, _clone_of=self)
+
+    # -- multi-GPU: one exchange at the end (include/gq.h) ------------------------------------------
+    def comm_init(self, comm_id, rank, n_ranks):
+        comm_id = np.ascontiguousarray(comm_id, dtype=np.uint8)
+        assert comm_id.size == COMM_ID_BYTES
+        self._check(self._lib.gq_comm_init(self._h, _ptr(comm_id, C.c_uint8), int(rank), int(n_ranks)))
+
+    def coverage_allreduce(self):
+        """In-place sum of the coverage of all ranks (dense counters, stats, sparse groups) over NCCL."""
+        self._check(self._lib.gq_coverage_allreduce(self._h))
+
+    @staticmethod
+    def comm_init_all(handles):
+        lib = load_library()
+        arr = (C.c_void_p * len(handles))(*[h._h for h in handles])
+        if lib.gq_comm_init_all(arr, len(handles)) != 0:
+            raise GqError(lib.gq_last_error().decode())
+
+    @staticmethod
+    def coverage_allreduce_all(handles):
+        lib = load_library()
+        arr = (C.c_void_p * len(handles))(*[h._h for h in handles])
+        if lib.gq_coverage_allreduce_all(arr, len(handles)) != 0:
+            raise GqError(lib.gq_last_error().decode())
+
     def upload(self, bases, offsets, seeds):
         self._check(self._lib.gq_batch_upload(self._h, *self._args(bases, offsets, seeds)))
 
@@ -176,6 +280,14 @@ class QuasimapIndex:
         self._check(self._lib.gq_last_run_info(self._h, a))
         return dict(launches=int(a[0]), rerun_strands=int(a[1]), search_ms=a[2], coverage_ms=a[3],
                     pool_words=int(a[4]), h2d_bytes=int(a[5]), kernels_ms=a[6], enqueue_ms=a[7])
+
+    KERNELS = ["seed_kernel", "verify_kernel", "text_kernel", "search_kernel", "classify_kernel", "coverage_kernel"]
+
+    def kernel_ms(self):
+        """Per-kernel durations of the last single-slice map_resident (CUDA events inside the library)."""
+        a = (C.c_double * 8)()
+        self._check(self._lib.gq_last_kernel_ms(self._h, a))
+        return dict(zip(self.KERNELS, [float(x) for x in a[:6]]))
 
     # -- results -------------------------------------------------------------------------------
     def batch_status(self):

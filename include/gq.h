@@ -58,6 +58,24 @@ int gq_index_per_base_layout(const gq_index* idx, uint64_t* off_len);
 int gq_map_batch(gq_index* idx, const uint8_t* bases, const uint64_t* read_offsets, uint64_t n_reads,
                  const uint32_t* seeds);
 
+/* 2-bit packed form of the same batch (16 bases per uint32, base j of a word at bits [2j, 2j+2), codes 0..3 =
+ * A,C,G,T; read r occupies ceil(len[r] / 16) words from word_off[r]; word_off has n_reads + 1 entries, the last
+ * one = total words). A third of the host-to-device bytes of the unpacked form and no packing pass on the GPU:
+ * this is what a reader thread that runs ahead of the GPU should hand over (replaces the per-read
+ * std::vector<uint8_t> of sequence_read/seqread.hpp:94-180 + quasimap.cpp:126-140). A read emptied by the
+ * encoder has len 0. */
+int gq_map_batch_packed(gq_index* idx, const uint32_t* packed, const uint32_t* word_off, const uint32_t* len,
+                        uint64_t n_reads, const uint32_t* seeds);
+/* Host-side packers producing that layout (OpenMP over reads, n_threads >= 1): from encoded bases 1..4
+ * (encode_dna_bases, utils.cpp:72-81) or straight from sequence text (ACGTacgt; a read with any other character
+ * becomes empty, utils.cpp:13-47,83-92). `packed` must hold gq_packed_words() words, word_off n_reads + 1,
+ * len n_reads. Read r is placed at word (read_offsets[r] >> 4) + r. */
+int gq_packed_words(const uint64_t* read_offsets, uint64_t n_reads, uint64_t* n_words);
+int gq_pack_reads(const uint8_t* bases, const uint64_t* read_offsets, uint64_t n_reads, uint32_t* packed,
+                  uint32_t* word_off, uint32_t* len, int n_threads);
+int gq_pack_ascii(const char* text, const uint64_t* read_offsets, uint64_t n_reads, uint32_t* packed,
+                  uint32_t* word_off, uint32_t* len, int n_threads);
+
 /* Split form of gq_map_batch for callers that keep a batch resident in HBM: upload once ... */
 int gq_batch_upload(gq_index* idx, const uint8_t* bases, const uint64_t* read_offsets, uint64_t n_reads,
                     const uint32_t* seeds);
@@ -88,8 +106,31 @@ int gq_coverage_reset(gq_index* idx);
  * num_sites_total}. Host arithmetic in double, like the reference (not part of the GPU hot path). */
 int gq_read_depth_stats(gq_index* idx, double out[2], uint64_t counts[2]);
 
-/* Multi-GPU: raw device pointers of the additive uint32 accumulators so the host layer can run one
- * NCCL all-reduce(sum) over them (reads are sharded across GPUs, index replicated).
+/* ---- multi-GPU: reads sharded over the GPUs, index replicated, ONE exchange at the end -------
+ * The reference shares one Coverage object between OpenMP threads (quasimap.cpp:90-118); here every GPU
+ * accumulates its own and the totals are formed once, when all reads are mapped:
+ *   - one process per GPU: rank 0 calls gq_comm_unique_id(), hands the id to the other ranks by any means
+ *     (MPI, torch.distributed, a file), every rank calls gq_comm_init(handle, id, rank, n_ranks);
+ *   - one process, several GPUs: gq_index_clone() the index onto each device, gq_comm_init_all(handles, n).
+ * gq_coverage_allreduce() then sums, IN PLACE and over NCCL (NVLink / NVSwitch), the dense uint32 accumulators
+ * (allele_sum | grouped singles | per-base) and the five counters, and merges the sparse multi-allele groups
+ * (exported, all-gathered and inserted on the device). Afterwards every handle holds the totals of the whole job
+ * and gq_coverage_fetch / gq_coverage_grouped apply the uint16 semantics to them. Call it once per job (or after
+ * gq_coverage_reset + mapping): reducing totals again would add the other ranks' share twice. Collective: every
+ * rank must call it. NCCL is loaded at run time (libnccl.so.2); without it these entry points fail, the rest of
+ * the library works. */
+#define GQ_COMM_ID_BYTES 128
+int gq_comm_unique_id(uint8_t id[GQ_COMM_ID_BYTES]);
+int gq_comm_init(gq_index* idx, const uint8_t id[GQ_COMM_ID_BYTES], int rank, int n_ranks);
+int gq_comm_init_all(gq_index** per_gpu, int n);
+int gq_comm_destroy(gq_index* idx);
+int gq_comm_version(int* nccl_version);
+int gq_coverage_allreduce(gq_index* idx);
+int gq_coverage_allreduce_all(gq_index** per_gpu, int n); /* all handles of one gq_comm_init_all, one call */
+/* A second handle on another GPU of this process from an index that is already built (no rebuild on the host). */
+int gq_index_clone(const gq_index* src, int device, gq_index** out);
+
+/* Raw device pointers of the additive uint32 accumulators, for callers that run their own collective.
  * counters = [allele_sum (n_alleles) | grouped_single (n_alleles) | per_base (n_per_base)] in one
  * contiguous allocation of n_counters uint32; stats = 5 x uint64. */
 int gq_coverage_device_ptrs(gq_index* idx, void** counters, uint64_t* n_counters, void** stats);
@@ -101,15 +142,26 @@ int gq_coverage_groups_import(gq_index* idx, const uint32_t* words, uint64_t n_w
 /* Run the kernels on a caller-owned CUDA stream (e.g. torch's current stream) so that the caller's
  * CUDA events bracket them. NULL = the library's own stream. */
 int gq_set_stream(gq_index* idx, void* cuda_stream);
-/* Tunables (name, value): arena_words, n_threads, cov_threads, super_in_smem, rf_thresh, ev_thresh (general
- * kernel); seed_pass (0: every strand through the general kernel), seed_recs_per_read (candidate pool);
- * chunk_reads, tail_chunk_reads (slices of the pipelined host path), resident_slices, overlap_classify.
- * Results never depend on them. */
+/* Tunables (name, value) — results never depend on them:
+ *   general kernel: arena_words (per-lane stack, >= 32), threads (lanes, multiple of 256), super_in_smem,
+ *     rf_thresh, ev_thresh, leave, wait_max; big_arena_words / big_threads (overflow re-runs);
+ *   seed_pass (0: every strand through the general kernel), seed_recs_per_read (candidate pool);
+ *   pool_words_per_read (final-state pool; grows on demand), gtab_cap (initial multi-allele group table; grows);
+ *   chunk_reads, tail_chunk_reads (slices of the pipelined host path), resident_slices (<= 64), overlap_classify.
+ * Parity precondition of the seeded selection (coverage_common.cpp:97-107): the reference's RandomInclusiveInt
+ * is std::uniform_int_distribution over std::mt19937 as libstdc++ >= 11 implements it (Lemire's multiply-shift
+ * with rejection); a reference built against an older libstdc++ or libc++ picks other classes for
+ * multi-mapping reads. */
 int gq_set_option(gq_index* idx, const char* name, int64_t value);
 /* Counters of the last gq_map_* call: [0] kernel launches, [1] overflow re-run strands, [2] search-phase ms
  * and [3] classify + coverage ms (CUDA events; single-slice runs only), [4] pool words used, [5] H2D bytes,
  * [6] all kernels ms (CUDA events on the caller's stream), [7] host ms spent enqueueing the call */
 int gq_last_run_info(gq_index* idx, double info[8]);
+
+/* Per-kernel durations (ms, CUDA events on the launching streams) of the last single-slice gq_map_resident call:
+ * [0] seed_kernel [1] verify_kernel [2] text_kernel [3] search_kernel (general) [4] classify_kernel (runs on a
+ * second stream beside coverage) [5] coverage_kernel; zero when the call was sliced. */
+int gq_last_kernel_ms(gq_index* idx, double ms[8]);
 
 const char* gq_last_error(void);
 

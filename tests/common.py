@@ -86,6 +86,11 @@ def emu_lib():
         lib.emu_path_counters.argtypes = [u64p, C.c_int]
         lib.emu_force_general.argtypes = [C.c_int]
         lib.emu_set_gtab_cap.argtypes = [C.c_void_p, C.c_uint32]
+        lib.emu_track.argtypes = [C.c_int]
+        lib.emu_track_ranges.restype = C.c_int
+        lib.emu_track_range_name.argtypes = [C.c_int]
+        lib.emu_track_range_name.restype = C.c_char_p
+        lib.emu_track_read.argtypes = [u64p, u64p]
         lib.emu_counters_raw.argtypes = [C.c_void_p, u32p]
         lib.emu_groups_raw.argtypes = [C.c_void_p, u32p]
         lib.emu_groups_raw.restype = C.c_uint64
@@ -223,6 +228,24 @@ class Emu:
 
     def force_general(self, on):
         self.lib.emu_force_general(int(on))
+
+    KERNELS = ["seed_kernel", "verify_kernel", "text_kernel", "search_kernel", "classify_kernel", "coverage_kernel"]
+
+    def track(self, on):
+        """Byte model: record the distinct 32 B sectors every unit of work touches (resets the totals)."""
+        self.lib.emu_track(int(on))
+
+    def tracked(self):
+        """-> {kernel: {structure: bytes}}, {kernel: units of work} since track(True)"""
+        n = self.lib.emu_track_ranges()
+        b = np.zeros(6 * max(n, 1), dtype=np.uint64)
+        u = np.zeros(6, dtype=np.uint64)
+        self.lib.emu_track_read(_ptr(b, C.c_uint64), _ptr(u, C.c_uint64))
+        names = [self.lib.emu_track_range_name(i).decode() for i in range(n)]
+        out = {}
+        for k, kn in enumerate(self.KERNELS):
+            out[kn] = {names[i]: int(b[k * n + i]) for i in range(n) if b[k * n + i]}
+        return out, {kn: int(u[k]) for k, kn in enumerate(self.KERNELS)}
 
     def set_gtab_cap(self, cap):
         """Shrink the multi-allele group table (power of two) so that its growth path runs."""

@@ -14,10 +14,64 @@
 #include "../../gramtools_b200/csrc/gq_device.cuh"
 #include "../../gramtools_b200/csrc/index_build.hpp"
 
+#include <unordered_set>
+
 using namespace gq;
 namespace gq {
 unsigned long long gq_emu_counters[32];
+
+// ---- byte model (tools/byte_model.py): distinct 32 B sectors touched per THREAD-SIZED unit of work ------------
+// (one strand in seed / general / classify / coverage, one candidate in verify / text), per kernel and structure.
+// Off unless emu_track(1) was called: the index builder runs through the same accessors.
+constexpr int kKernels = 6, kMaxRanges = 64;
+struct Range {
+  const char* name;
+  uintptr_t lo, hi;
+  unsigned granule;  // 32: random access, a touch costs its whole sector; 4 / 1: per-strand / per-candidate arrays
+                     // that consecutive threads read or write side by side (coalesced): a touch costs its bytes
+};
+static bool g_track = false;
+static int g_kernel = 0, g_n_ranges = 0;
+static Range g_ranges[kMaxRanges];
+static std::unordered_set<uint64_t> g_sectors;                  // (range id << 48) | sector index within the range
+static unsigned long long g_bytes[kKernels][kMaxRanges + 1];  // [kernel][range] (last = unregistered memory)
+static unsigned long long g_units[kKernels];
+
+static void flush_unit() {
+  if (g_sectors.empty()) return;
+  for (uint64_t key : g_sectors) g_bytes[g_kernel][key >> 48] += g_ranges[key >> 48].granule;
+  g_units[g_kernel]++;
+  g_sectors.clear();
 }
+void gq_emu_phase(int kernel) {
+  if (!g_track) return;
+  flush_unit();
+  g_kernel = kernel;
+}
+void gq_emu_touch(const void* p, unsigned bytes) {
+  if (!g_track || bytes == 0) return;
+  const uintptr_t a = (uintptr_t)p;
+  int id = kMaxRanges;
+  for (int i = 0; i < g_n_ranges; ++i)
+    if (a >= g_ranges[i].lo && a < g_ranges[i].hi) {
+      id = i;
+      break;
+    }
+  if (id == kMaxRanges) return;  // host-only scratch (stacks, local arrays): not device-memory traffic
+  // device allocations start on a sector boundary: the offset from the start of the array decides the sector
+  const uintptr_t base = g_ranges[id].lo, g = g_ranges[id].granule;
+  for (uintptr_t s = (a - base) / g; s <= (a + bytes - 1 - base) / g; ++s) g_sectors.insert(((uint64_t)id << 48) | s);
+}
+static void add_range(const char* name, const void* p, size_t bytes, unsigned granule) {
+  if (!bytes || g_n_ranges == kMaxRanges) return;
+  for (int i = 0; i < g_n_ranges; ++i)
+    if (std::string(g_ranges[i].name) == name) {
+      g_ranges[i] = {name, (uintptr_t)p, (uintptr_t)p + bytes, granule};
+      return;
+    }
+  g_ranges[g_n_ranges++] = {name, (uintptr_t)p, (uintptr_t)p + bytes, granule};
+}
+}  // namespace gq
 
 struct Emu {
   HostIndex h;
@@ -154,6 +208,28 @@ int emu_map(void* ev, const uint8_t* bases, const uint64_t* off, uint64_t n_read
     SeedOut pre{seed_rec.data(), (uint32_t)(seed_rec.size() / 4), &pre_small[0], surv_cnt.data(), gen.data(),
                 &pre_small[1]};
     std::vector<uint32_t> arena(arena_words), big;
+    if (g_track) {
+#define REG(name, vec) add_range(name, (vec).data(), (vec).size() * sizeof((vec)[0]), 32)
+#define REGS(name, vec, g) add_range(name, (vec).data(), (vec).size() * sizeof((vec)[0]), g)
+      REGS("packed reads", packed, 4); REGS("read len", len, 4); REGS("read word_off", word_off, 4);
+      add_range("read seeds", seeds, n_reads * 4, 4);
+      REGS("strand status", e->status, 1); REGS("strand st_off", e->st_off, 4); REGS("strand st_words", e->st_words, 4);
+      REGS("strand st_count", e->st_count, 4); REGS("final-state pool", e->pool, 4); REGS("mapped list", mapped, 4);
+      REGS("candidate records", seed_rec, 4); REGS("strand flags (surv_cnt)", surv_cnt, 4); REGS("general list", gen, 4);
+      REG("coverage counters", e->counters); REG("group table", e->gtab); REG("group counts", e->gcount);
+      REG("group pool", e->gpool);
+      REG("rank_blk", h.rank_blk); REG("super_cnt", h.super_cnt); REG("mrank_blk", h.mrank_blk);
+      REG("marker_hit", h.marker_hit); REG("text_grp", h.text_grp); REG("text_super", h.text_super);
+      REG("tmarker_hit", h.tmarker_hit); REG("isa", h.isa); REG("site_sa", h.site_sa); REG("allele_iv", h.allele_iv);
+      REG("par", h.par); REG("tm_odd", h.tm_odd); REG("tm_even_off", h.tm_even_off); REG("tm_even", h.tm_even);
+      REG("entry_next", h.entry_next); REG("site_snp", h.site_snp); REG("sa", h.sa); REG("pos2node", h.pos2node);
+      REG("nodes", h.nodes); REG("edges", h.edges); REG("kmer_bits (smem copy on the device)", h.kmer_bits);
+      REG("kmer_bits_rc", h.kmer_bits_rc); REG("kmer_off", h.kmer_off); REG("kmer_states", h.kmer_states);
+      REG("seed_off", h.seed_off); REG("seed_ent", h.seed_ent); REG("seed_state", h.seed_state);
+      REG("kmer_paths", h.kmer_paths); REG("allele_off", h.allele_off);
+#undef REGS
+#undef REG
+    }
     for (uint32_t s = 0; s < 2 * n_reads; ++s) {
       uint32_t aw = arena_words;
       uint32_t* a = arena.data();
@@ -219,6 +295,7 @@ int emu_map(void* ev, const uint8_t* bases, const uint64_t* off, uint64_t n_read
         a = big.data();
       }
     }
+    if (g_track) gq_emu_phase(0);  // flush the last unit
     for (uint64_t r = 0; r < n_reads; ++r) {
       e->stats[0] += 2;
       for (int s = 0; s < 2; ++s) {
@@ -234,6 +311,22 @@ int emu_map(void* ev, const uint8_t* bases, const uint64_t* off, uint64_t n_read
   } catch (const std::exception& ex) {
     g_err = ex.what();
     return -1;
+  }
+}
+// byte model: switch tracking on/off (resets the totals), and read them: per kernel and structure
+void emu_track(int on) {
+  g_track = on != 0;
+  g_sectors.clear();
+  std::memset(g_bytes, 0, sizeof g_bytes);
+  std::memset(g_units, 0, sizeof g_units);
+  g_kernel = 0;
+}
+int emu_track_ranges() { return g_n_ranges; }
+const char* emu_track_range_name(int i) { return i < g_n_ranges ? g_ranges[i].name : ""; }
+void emu_track_read(unsigned long long* bytes /* kKernels x n_ranges */, unsigned long long* units /* kKernels */) {
+  for (int k = 0; k < kKernels; ++k) {
+    units[k] = g_units[k];
+    for (int i = 0; i < g_n_ranges; ++i) bytes[k * g_n_ranges + i] = g_bytes[k][i];
   }
 }
 // 1: every strand through the general lane machine (as libgq does with the seed_pass option off)

@@ -42,3 +42,33 @@ def test_product_does_not_link_the_oracle(built_lib):
             if f.endswith((".cu", ".cuh", ".cpp", ".hpp", ".py", "Makefile")):
                 txt = open(os.path.join(root, f)).read()
                 assert "oracle/" not in txt and "gq_oracle" not in txt, f
+
+
+def test_host_packers(built_lib):
+    """gq_pack_reads / gq_pack_ascii (host code, no GPU): 16 bases per word, base j at bits [2j, 2j+2), read r at
+    word (offset >> 4) + r; text with a non-ACGT character becomes an empty read (utils.cpp:13-47,83-92)."""
+    from gramtools_b200 import encode_reads, pack_ascii, pack_reads
+    rng = np.random.default_rng(5)
+    reads = ["".join("ACGT"[x] for x in rng.integers(0, 4, int(L))) for L in rng.integers(0, 70, 200)]
+    reads[3] = "ACGTNNACGT"
+    reads[7] = "acgtacgtacgtacgtacgt"
+    bases, offs = encode_reads(reads)
+    packed, word_off, ln = pack_reads(bases, offs, n_threads=3)
+    for r in range(len(reads)):
+        L = int(offs[r + 1] - offs[r])
+        assert ln[r] == L and word_off[r] == (int(offs[r]) >> 4) + r
+        for j in range(L):
+            assert (int(packed[word_off[r] + j // 16]) >> (2 * (j % 16))) & 3 == int(bases[int(offs[r]) + j]) - 1
+    assert word_off[len(reads)] >= word_off[len(reads) - 1] + (int(ln[-1]) + 15) // 16
+    # the same reads from text: identical words for clean reads, length 0 for the read with Ns
+    text = "".join(reads).encode()
+    toff = np.zeros(len(reads) + 1, dtype=np.uint64)
+    np.cumsum([len(r) for r in reads], out=toff[1:])
+    p2, w2, l2 = pack_ascii(text, toff, n_threads=2)
+    assert l2[3] == 0 and l2[7] == 20
+    for r in range(len(reads)):
+        if r == 3:
+            continue
+        assert l2[r] == len(reads[r])
+        for j in range(len(reads[r])):
+            assert (int(p2[w2[r] + j // 16]) >> (2 * (j % 16))) & 3 == "ACGT".index(reads[r][j].upper())

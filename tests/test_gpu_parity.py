@@ -358,3 +358,73 @@ def test_config4_shape_prefix(built_lib):
     bases, offs = synth.sample_reads(haps, 20000, 150, 12)
     got, ref_r = _check(prg, 8, bases, offs, what="config4-shape", threads=os.cpu_count())
     assert ref_r.stats[4] >= 20000
+
+
+def test_packed_host_batch(built_lib):
+    """gq_map_batch_packed (2-bit packed host buffers, no pack kernel) == gq_map_batch on the same reads == oracle,
+    including skipped (empty) reads, reads shorter than k and several pipelined slices."""
+    from gramtools_b200 import pack_reads
+    prg = synth.make_nested_prg(5, 300, 21)
+    bases, offs = _reads_for(prg, 20000, 45, 21, garbage=0.05, n_frac=0.03)
+    seeds = master_seeds(42, offs.size - 1)
+    o = Oracle(prg, 5)
+    o.map(bases, offs, seeds, threads=os.cpu_count())
+    ref = o.result()
+    packed, word_off, ln = pack_reads(bases, offs)
+    for options in ({}, {"chunk_reads": 4096, "tail_chunk_reads": 1024}):
+        idx = QuasimapIndex(prg, 5)
+        for k, v in options.items():
+            idx.set_option(k, v)
+        idx.map_batch_packed(packed, word_off, ln, seeds)
+        assert_parity(gpu_result(idx), ref, f"packed{options}")
+        assert idx.run_info()["h2d_bytes"] < 0.5 * (bases.size + 12 * (offs.size - 1))
+        idx.close()
+
+
+def test_single_rank_communicator(built_lib):
+    """The library's own NCCL path with one rank: communicator from gq_comm_unique_id / gq_comm_init, in-place
+    all-reduce of counters, stats and sparse groups — a no-op on the values."""
+    from gramtools_b200 import comm_unique_id
+    prg = synth.make_nested_prg(3, 250, 31)
+    bases, offs = _reads_for(prg, 3000, 30, 31)
+    seeds = master_seeds(42, offs.size - 1)
+    idx = QuasimapIndex(prg, 4)
+    idx.comm_init(comm_unique_id(), 0, 1)
+    idx.map_batch(bases, offs, seeds)
+    before = gpu_result(idx)
+    idx.coverage_allreduce()
+    after = gpu_result(idx)
+    assert_parity(after, before, "1-rank allreduce")
+    o = Oracle(prg, 4)
+    o.map(bases, offs, seeds)
+    assert_parity(after, o.result(), "1-rank allreduce vs oracle")
+
+
+def test_two_gpus_one_process_allreduce(built_lib):
+    """Reads sharded over two GPUs of this process (index built once, cloned), one NCCL exchange at the end:
+    every handle then holds the job's totals — dense counters, stats and merged multi-allele groups — equal to the
+    oracle's single-process result. Needs two devices (gpurun --gpus 2)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    from gramtools_b200.distributed import shard_bounds
+    prg = synth.make_nested_prg(6, 300, 41)
+    bases, offs = _reads_for(prg, 20000, 40, 41)
+    n = offs.size - 1
+    seeds = master_seeds(42, n)
+    a = QuasimapIndex(prg, 5, device=0)
+    handles = [a, a.clone(1)]
+    QuasimapIndex.comm_init_all(handles)
+    for r, h in enumerate(handles):
+        lo, hi = shard_bounds(n, r, 2)
+        h.map_batch(bases[int(offs[lo]):int(offs[hi])], offs[lo:hi + 1] - offs[lo], seeds[lo:hi])
+    QuasimapIndex.coverage_allreduce_all(handles)
+    o = Oracle(prg, 5)
+    o.map(bases, offs, seeds, threads=os.cpu_count())
+    ref = o.result()
+    for h in handles:
+        al, pb, st = h.coverage()
+        assert np.array_equal(al, ref.allele_sum) and np.array_equal(pb, ref.per_base)
+        assert np.array_equal(h.grouped(), ref.grouped)
+        assert [st.all_reads_count, st.skipped_reads_count, st.missing_kmer_reads_count, st.no_extension_reads_count,
+                st.exact_mapped_reads_count] == ref.stats
