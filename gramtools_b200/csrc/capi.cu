@@ -62,6 +62,8 @@ static void upload_index(gq_index* ix) {
   v.pos2node = upload(ix, h.pos2node);
   v.nodes = upload(ix, h.nodes);
   v.edges = upload(ix, h.edges);
+  v.site_rec = upload(ix, h.site_rec);
+  v.apos = upload(ix, h.apos);
   v.k = h.k;
   v.kmer_bits = upload(ix, h.kmer_bits);
   v.kmer_bits_rc = upload(ix, h.kmer_bits_rc);
@@ -353,9 +355,13 @@ static void do_map(gq_index* ix, const HostBatch* hb = nullptr) {
       CUDA_OK(cudaEventRecord(ix->aux_event, ix->aux_stream));
       CUDA_OK(cudaStreamWaitEvent(cs, ix->aux_event, 0));
     } else {
+      const bool timed = chunks.size() == 1;
+      if (timed) CUDA_OK(cudaEventRecord(ix->kev[4], cs));
       gq::launch_classify(ix->dv, bc, oc, nullptr, 0, cs);
+      if (timed) CUDA_OK(cudaEventRecord(ix->kev[5], cs));
       gq::launch_coverage(ix->dv, bc, oc, c, arena, ix->arena_words, threads2, nullptr, 0,
                           ix->cov_overflow_list.p, ix->small.p + 2, cs);
+      if (timed) CUDA_OK(cudaEventRecord(ix->kev[6], cs));
     }
     launches += 3;
   }
@@ -381,7 +387,7 @@ static void do_map(gq_index* ix, const HostBatch* hb = nullptr) {
     ix->info[2] = ms_s;
     ix->info[3] = ms_c;
     for (auto& m : ix->kernel_ms) m = 0;
-    if (ix->use_seed_pass && !two_streams && ix->overlap_classify) {
+    if (ix->use_seed_pass) {
       auto el = [&](int a, int b) {
         float ms = 0;
         return cudaEventElapsedTime(&ms, ix->kev[a], ix->kev[b]) == cudaSuccess ? (double)ms : 0.0;
@@ -393,9 +399,10 @@ static void do_map(gq_index* ix, const HostBatch* hb = nullptr) {
       cudaEventElapsedTime(&ms_g, ix->kev[3], ix->ev[1]);
       ix->kernel_ms[3] = ms_g;
       ix->kernel_ms[4] = el(4, 5);  // classify (second stream, beside coverage)
+      // coverage: beside classify (second stream) it starts with the search phase's end, else after classify
       float ms_cov = 0;
-      cudaEventElapsedTime(&ms_cov, ix->ev[1], ix->kev[6]);
-      ix->kernel_ms[5] = ms_cov;    // coverage
+      cudaEventElapsedTime(&ms_cov, ix->overlap_classify ? ix->ev[1] : ix->kev[5], ix->kev[6]);
+      ix->kernel_ms[5] = ms_cov;
     }
   }
   // list-mode re-runs below hand out work from counter slot [9] and append to the (already consumed)

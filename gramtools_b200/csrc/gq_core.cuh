@@ -134,6 +134,11 @@ struct IndexView {
   const uint32_t* pos2node;
   const Node* nodes;
   const uint32_t* edges;
+  // per slot {apos offset = allele_off[slot] + slot, per-base offset of the site's first base, text position of
+  // the first allele's first symbol, text position after the site-end marker}, and the text position of every
+  // allele's first symbol (n_alleles + 1 entries per site): coverage of a walk from text positions alone
+  const uint32_t* site_rec;
+  const uint32_t* apos;
   // k-mer index
   uint32_t k;
   const uint32_t* kmer_bits;   // 4^k bits: k-mer has >= 1 state

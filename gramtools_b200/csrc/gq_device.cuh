@@ -18,6 +18,10 @@
 #define GQ_DEV
 #endif
 
+#ifndef GQ_COV_CHUNK
+#define GQ_COV_CHUNK 4  // per-site records fetched together by the coverage table route
+#endif
+
 namespace gq {
 
 // path statistics of the host emulation (tests/emu): which route strands take. No-op on the device.
@@ -1558,41 +1562,85 @@ GQ_DEV bool record_strand(const IndexView& v, const BatchView& b, const SearchOu
     }
   }
   if (npath == 0) return true;
-  // Fast path (nearly every strand of a non-nested PRG): exactly one state, one occurrence. One class and
-  // no non-variant mapping -> generate(1,1) == 1 selects it (coverage_common.cpp:97-107); every locus is
-  // its own level-0 site (no parents), each node is visited once, so no sets / hulls are needed.
+  // Table route (nearly every strand of a non-nested PRG): exactly one state, one occurrence. One class and no
+  // non-variant mapping -> generate(1,1) == 1 selects it (coverage_common.cpp:97-107); every locus is its own
+  // level-0 site, each allele is visited once, so no sets / hulls are needed — and no graph either: the forward
+  // traversal of PbCovRecorder / Traverser (allele_base.cpp:137-296) from the read's first base, choosing the
+  // path's alleles back to front, is arithmetic on text positions: from position p the next site of the path
+  // starts `site start - p` bases further on, the chosen allele a spans [apos[a], apos[a+1] - 1), its bases sit at
+  // per-base offset `site base + (apos[a] - apos[0]) - a`, and the walk continues after the site-end marker. The
+  // per-site records of the path's sites are independent loads (fetched four at a time), where the graph walk
+  // was a chain of ~14 dependent node loads per read.
   if (ns == 1 && !v.any_nested) {
     StateRec st = parse_rec(recs);
     if (st.lo == st.hi && st.ng <= 1) {
-      const uint32_t pos0 = GQ_LDG(v.sa + st.lo);
-      const uint32_t nid0 = GQ_LDG(v.pos2node + pos0);
-      if (st.ng) {
-        const uint32_t site = st.G[0], slot = (site - 5) >> 1, al = (uint32_t)GQ_AT(v.nodes, nid0).allele;
-        gq_red_add(c.allele_sum + GQ_AT(c.allele_off, slot) + al, 1u);
-        gq_red_add(c.grouped_single + GQ_AT(c.allele_off, slot) + al, 1u);
+      uint32_t p = GQ_LDG(v.sa + st.lo);
+      uint32_t remaining = L;
+      const uint32_t n_el = st.nt + st.ng;  // elements in read order: the open site (read starts inside it), then
+                                            // the path back to front
+      constexpr uint32_t kChunk = GQ_COV_CHUNK;
+      for (uint32_t e0 = 0; e0 < n_el; e0 += kChunk) {
+        uint32_t site[kChunk], al[kChunk], r_a2[kChunk], r_cov[kChunk], r_first[kChunk], r_after[kChunk];
+        uint32_t a_lo[kChunk], a_hi[kChunk];
+#pragma unroll
+        for (uint32_t q = 0; q < kChunk; ++q) {
+          const uint32_t e = e0 + q;
+          if (e >= n_el) break;
+          if (st.ng && e == 0) {
+            site[q] = st.G[0];
+            al[q] = kNoAllele;
+          } else {
+            const uint32_t j = st.nt - 1 - (e - st.ng);
+            site[q] = st.T[2 * j];
+            al[q] = st.T[2 * j + 1];
+          }
+          const uint32_t slot = (site[q] - 5) >> 1;
+#if defined(__CUDA_ARCH__)
+          const uint4 r = __ldg(reinterpret_cast<const uint4*>(v.site_rec) + slot);
+          r_a2[q] = r.x, r_cov[q] = r.y, r_first[q] = r.z, r_after[q] = r.w;
+#else
+          GQ_TOUCH(v.site_rec + 4 * (size_t)slot, 16);
+          r_a2[q] = v.site_rec[4 * (size_t)slot], r_cov[q] = v.site_rec[4 * (size_t)slot + 1];
+          r_first[q] = v.site_rec[4 * (size_t)slot + 2], r_after[q] = v.site_rec[4 * (size_t)slot + 3];
+#endif
+        }
+#pragma unroll
+        for (uint32_t q = 0; q < kChunk; ++q) {
+          if (e0 + q >= n_el) break;
+          if (al[q] == kNoAllele) {  // the allele the read starts in: the one whose span holds p
+            uint32_t a = 0;
+            while (p >= GQ_LDG(v.apos + r_a2[q] + a + 1)) ++a;
+            al[q] = a;
+          }
+          a_lo[q] = GQ_LDG(v.apos + r_a2[q] + al[q]);
+          a_hi[q] = GQ_LDG(v.apos + r_a2[q] + al[q] + 1);
+        }
+#pragma unroll
+        for (uint32_t q = 0; q < kChunk; ++q) {
+          const uint32_t e = e0 + q;
+          if (e >= n_el) break;
+          const uint32_t slot = (site[q] - 5) >> 1, ai = r_a2[q] - slot + al[q];  // allele_off[slot] + allele
+          gq_red_add(c.allele_sum + ai, 1u);       // allele_sum.cpp:31-43
+          gq_red_add(c.grouped_single + ai, 1u);   // grouped_allele_counts.cpp:17-49, a one-allele group
+          if (remaining == 0) continue;
+          uint32_t off = 0;
+          if (e == 0 && p >= r_first[q]) off = p - a_lo[q];  // the read starts inside this allele
+          else {
+            const uint32_t gap = r_first[q] - 1 - p;  // bases before the site-entry marker
+            if (remaining <= gap) {
+              remaining = 0;
+              continue;
+            }
+            remaining -= gap;
+          }
+          const uint32_t len = a_hi[q] - 1 - a_lo[q];
+          const uint32_t cnt = len - off < remaining ? len - off : remaining;
+          uint32_t* pb = c.per_base + r_cov[q] + (a_lo[q] - r_first[q]) - al[q] + off;
+          for (uint32_t x = 0; x < cnt; ++x) gq_red_add(pb + x, 1u);  // allele_base.cpp:221-296
+          remaining -= cnt;
+          p = r_after[q];
+        }
       }
-      for (uint32_t j = 0; j < st.nt; ++j) {
-        const uint32_t slot = (st.T[2 * j] - 5) >> 1, al = st.T[2 * j + 1];
-        gq_red_add(c.allele_sum + GQ_AT(c.allele_off, slot) + al, 1u);
-        gq_red_add(c.grouped_single + GQ_AT(c.allele_off, slot) + al, 1u);
-      }
-      Trav t;
-      t.v = &v;
-      t.cur = nid0;
-      t.remaining = L;
-      t.T = st.T;
-      t.ti = st.nt;
-      t.first = true;
-      const Node& nd0 = GQ_AT(v.nodes, nid0);
-      t.start_pos = nd0.len > 1 ? pos0 - nd0.start : 0;
-      t.end_pos = 0;
-      t.bad = false;
-      while (t.next()) {
-        const Node& nd = GQ_AT(v.nodes, t.cur);
-        if (nd.len == 0 || nd.cov_off == kNoAllele) continue;
-        for (uint32_t x = t.start_pos; x <= t.end_pos; ++x) gq_red_add(c.per_base + nd.cov_off + x, 1u);
-      }
-      if (t.bad) gq_atomic_or(c.error_flags, 2u);
       return true;
     }
   }

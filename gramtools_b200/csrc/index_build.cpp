@@ -37,6 +37,8 @@ IndexView HostIndex::view() const {
   v.pos2node = pos2node.data();
   v.nodes = nodes.data();
   v.edges = edges.data();
+  v.site_rec = site_rec.data();
+  v.apos = apos.data();
   v.k = k;
   v.kmer_bits = kmer_bits.data();
   v.kmer_bits_rc = kmer_bits_rc.data();
@@ -258,6 +260,42 @@ void build_graph(HostIndex& ix, std::vector<uint32_t>& hit_marker, std::vector<u
   ix.allele_off.assign(S + 1, 0);
   for (uint32_t s = 0; s < S; ++s) ix.allele_off[s + 1] = ix.allele_off[s] + ix.n_alleles[s];
   if (ix.tm_even.empty()) ix.tm_even.assign(2, 0);
+}
+
+// Per-site text-position tables (record_strand's table route): where every allele starts in the PRG and where its
+// bases sit in the flat per-base vector — which is filled in PRG order by build_graph, so for a site without
+// nested sites the bases of allele a follow those of allele a - 1 directly.
+void build_site_tables(HostIndex& ix) {
+  const auto& prg = ix.prg;
+  const uint32_t S = ix.n_slots;
+  ix.site_rec.assign(4 * (size_t)S + 4, 0);
+  ix.apos.assign((size_t)ix.allele_off[S] + S + 1, 0);
+  std::vector<uint32_t> open, cur_allele(S, 0);
+  uint32_t in_site_bases = 0;
+  for (uint32_t p = 0; p < (uint32_t)prg.size(); ++p) {
+    const uint32_t m = prg[p];
+    if (m <= 4) {
+      if (!open.empty()) ++in_site_bases;
+      continue;
+    }
+    if (m & 1u) {
+      const uint32_t s = (m - 5) / 2, a2 = ix.allele_off[s] + s;
+      open.push_back(s);
+      cur_allele[s] = 0;
+      ix.site_rec[4 * (size_t)s] = a2;
+      ix.site_rec[4 * (size_t)s + 1] = in_site_bases;
+      ix.site_rec[4 * (size_t)s + 2] = p + 1;
+      ix.apos[a2] = p + 1;
+    } else {
+      const uint32_t s = (m - 6) / 2, a2 = ix.allele_off[s] + s;
+      ++cur_allele[s];
+      ix.apos[a2 + cur_allele[s]] = p + 1;
+      if (cur_allele[s] == ix.n_alleles[s]) {
+        ix.site_rec[4 * (size_t)s + 3] = p + 1;
+        open.pop_back();
+      }
+    }
+  }
 }
 
 void build_fm(HostIndex& ix, const std::vector<uint32_t>& hit_marker, const std::vector<uint32_t>& hit_allele) {
@@ -653,6 +691,7 @@ void build_host_index(const uint32_t* prg, uint64_t n_symbols, uint32_t kmer_siz
   ix.prg.assign(prg, prg + n_symbols);
   std::vector<uint32_t> hit_marker, hit_allele;
   build_graph(ix, hit_marker, hit_allele);
+  build_site_tables(ix);
   build_fm(ix, hit_marker, hit_allele);
   build_kmers(ix);
 }

@@ -41,6 +41,11 @@ struct HostIndex {
   std::vector<uint32_t> edges;
   std::vector<uint32_t> site_start_node;  // per slot: bubble start node id
   uint32_t n_per_base = 0;                // number of in-bubble bases (flat per-base layout)
+  // coverage recording without the graph (non-nested PRGs): per slot {apos offset, per-base offset of the site's
+  // first base, text position of its first allele base, text position after its end marker}; apos = text
+  // position of the first symbol of every allele, n_alleles + 1 entries per site (the last = position after the
+  // site-end marker), so allele a spans [apos[a], apos[a + 1] - 1)
+  std::vector<uint32_t> site_rec, apos;
   // k-mer index
   std::vector<uint32_t> kmer_bits, kmer_bits_rc, kmer_off, kmer_paths;
   std::vector<KmerState> kmer_states;

@@ -104,67 +104,6 @@ constexpr int kHotUnroll = GQ_HOT_UNROLL;
 #ifndef GQ_SEARCH_MIN_BLOCKS
 #define GQ_SEARCH_MIN_BLOCKS 5  // 48 registers, 1280 resident lanes per SM
 #endif
-// k-mer filter of one strand by a whole warp. A k-mer code is a bit-field of the packed read (see
-// classify_strand), so each lane takes a RUN of consecutive k-mers: one 64-bit window of the read, then one
-// shift + mask + bit test per k-mer; the reverse strand tests the same windows against the presence set
-// indexed by the reverse complement's code (kmer_bits_rc), so no per-k-mer transform is needed. A ballot ends
-// the strand at the first round that finds a missing k-mer (a 150 bp read is one round). Must be called by all
-// 32 lanes with uniform arguments.
-// `bits`: the presence set to probe (global or a shared-memory copy); `transform`: reverse strand probing the
-// forward-indexed set, so each code is reverse-complemented first.
-// The packed words come from memory (`w`) or, when w == nullptr, from the lanes' registers (`word` = packed word
-// `lane` of the strand, reads of up to 512 bases).
-__device__ __forceinline__ bool warp_any_kmer_missing(uint32_t k, const uint32_t* bits, bool transform, const uint32_t* w,
-                                                      uint32_t word, uint32_t L, uint32_t lane) {
-  const uint32_t mask = (k == 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
-  const uint32_t n_words = (L + 15) >> 4, n_kmers = L - k + 1;
-  // k-mers per lane and round: the run's bases (k + per - 1) must fit the 64-bit window at any 2-bit offset
-  uint32_t per = (n_kmers + 31) >> 5;
-  const uint32_t fit = k < 17 ? 18 - k : 1;
-  per = per < fit ? per : fit;
-  bool missing = false;
-  for (uint32_t j0 = 0; j0 < n_kmers && !missing; j0 += 32 * per) {
-    const uint32_t j = j0 + lane * per;
-    bool absent = false;
-    const uint32_t wi = j >> 4, sh = 2 * (j & 15u);
-    uint32_t lo, hi;
-    if (w) {
-      lo = (j < n_kmers) ? __ldg(w + wi) : 0u;
-      hi = (j < n_kmers && wi + 1 < n_words) ? __ldg(w + wi + 1) : 0u;
-    } else {  // all lanes take part in the shuffles
-      lo = __shfl_sync(0xFFFFFFFFu, word, wi & 31u);
-      hi = __shfl_sync(0xFFFFFFFFu, word, (wi + 1) & 31u);
-      if (wi + 1 >= n_words) hi = 0u;
-    }
-    if (j < n_kmers) {
-      uint64_t win = (((uint64_t)hi << 32) | lo) >> sh;
-      const uint32_t cnt = min(per, n_kmers - j);
-      uint32_t present = 1u;
-      if (transform) {
-        // reverse complement of the whole run (m = k + cnt - 1 bases) once: the reverse-complement code of the
-        // run's k-mer t is then the bit-field of R starting at pair cnt-1-t, so the run's codes are again
-        // consecutive windows (visited in the opposite order, which does not matter)
-        const uint64_t x = ~win;
-        uint64_t r = ((uint64_t)__brev((uint32_t)x) << 32) | __brev((uint32_t)(x >> 32));
-        r = ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);
-        r >>= 64 - 2 * (k + cnt - 1);
-        for (uint32_t t = 0; t < cnt; ++t, r >>= 2) {
-          const uint32_t code = (uint32_t)r & mask;
-          present &= bits[code >> 5] >> (code & 31u);
-        }
-      } else {
-        for (uint32_t t = 0; t < cnt; ++t, win >>= 2) {
-          const uint32_t code = (uint32_t)win & mask;
-          present &= bits[code >> 5] >> (code & 31u);
-        }
-      }
-      absent = !(present & 1u);
-    }
-    missing = __any_sync(0xFFFFFFFFu, absent);
-  }
-  return missing;
-}
-
 // Seed pass. Warp-convergent rounds of 32 strands. Phase A: every lane looks up the seed entries of its strand
 // (preseed_lookup). Phase B: the entries of the round are examined (seed_state_cands) by all lanes —
 //   * few entries per strand (config 2: ~4): the round's entries are spread evenly over the lanes, so lanes
@@ -539,11 +478,18 @@ __global__ void __launch_bounds__(kSearchThreads, GQ_SEARCH_MIN_BLOCKS)
   }
 }
 
-// k-mer filter for failed strands, one WARP per strand (warp_any_kmer_missing). Lanes first vote on 32 statuses
-// at once to find the unclassified strands of the warp's slice. The probes are random 4-byte reads — 32
-// different L1 lines per warp load — so when the 4^k-bit set fits (k <= 10: 128 KB) each CTA keeps a copy in
-// shared memory (one persistent 1024-thread CTA per SM) and the probes become bank-conflict-bound instead.
+// k-mer filter for failed strands (all_read_kmers_occur_in_index, quasimap.cpp:212-225): one LANE per strand, in
+// a flat warp loop with refill. A k-mer code is a bit-field of the packed read (classify_strand), so a lane
+// slides a 64-bit window over its strand — shift, mask, one bit test per k-mer — and stops at the first absent
+// k-mer (a random 150-mer misses the index after ~65 of its 141 10-mers at config 2); a lane that is done takes
+// the next unclassified strand of the warp's current group of 32 statuses, so lanes stay busy whatever the
+// strands' lengths. The probes are random 4-byte reads, so when the 4^k-bit set fits (k <= 10: 128 KB) each CTA
+// keeps a copy in shared memory (one persistent 1024-thread CTA per SM); the reverse strand reverse-complements
+// its code (shared copy) or probes the set indexed by reverse-complement codes (global memory).
+// [v1 gave a whole warp to each strand: 181 warp instructions per strand, mostly per-strand set-up; this form
+// needs ~25.]
 constexpr uint32_t kClassifySmemBytes = 160 * 1024;
+constexpr int kClassifyUnroll = 4;
 
 template <bool SMEM>
 __global__ void __launch_bounds__(SMEM ? 1024 : 256)
@@ -556,47 +502,73 @@ __global__ void __launch_bounds__(SMEM ? 1024 : 256)
     __syncthreads();
   }
   const uint32_t n = list ? n_list : 2 * (b.read_end - b.read_begin);
-  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
   const uint32_t full = 0xFFFFFFFFu;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-  const uint32_t* bits_f = SMEM ? (const uint32_t*)s_bits : v.kmer_bits;
-  for (uint32_t base = warp * 32; base < n; base += n_warps * 32) {
-    const uint32_t i = base + lane;
-    const uint32_t my_strand = i < n ? (list ? list[i] : 2 * b.read_begin + i) : 0;
-    const bool need = i < n && o.status[my_strand] == ST_UNCLASSIFIED;
-    // every lane fetches the metadata of its own strand once; the strands are then classified one after the
-    // other by the whole warp, the packed words of the NEXT strand in flight (one word per lane) while the
-    // current one is probed from registers — no dependent global load left in the per-strand chain
-    const uint32_t my_L = need ? b.len[my_strand >> 1] : 0, my_woff = need ? b.word_off[my_strand >> 1] : 0;
-    uint32_t todo = __ballot_sync(full, need);
-    auto fetch = [&](int src, uint32_t& L) -> uint32_t {
-      L = __shfl_sync(full, my_L, src);
-      const uint32_t woff = __shfl_sync(full, my_woff, src);
-      return lane < ((L + 15) >> 4) ? __ldg(b.packed + woff + lane) : 0u;
-    };
-    int src = todo ? __ffs(todo) - 1 : 0;
-    uint32_t nxt_L = 0, nxt_w = todo ? fetch(src, nxt_L) : 0u;
-    while (todo) {
-      const uint32_t strand = __shfl_sync(full, my_strand, src);
-      const uint32_t L = nxt_L, word = nxt_w;
-      todo &= todo - 1;
-      if (todo) {
-        src = __ffs(todo) - 1;
-        nxt_w = fetch(src, nxt_L);
+  const uint32_t k = v.k, mask = (k == 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u), rsh = 32 - 2 * k;
+  uint32_t group = warp;              // next group of 32 strands this warp looks at
+  uint32_t pend = 0, grp_strand = 0;  // unclassified strands of the current group not yet taken (lane = position)
+  // lane state
+  bool active = false;
+  uint32_t strand = 0, i = 0, n_kmers = 0, n_words = 0;
+  uint64_t win = 0;
+  const uint32_t* w = nullptr;
+  const uint32_t* bits = SMEM ? (const uint32_t*)s_bits : v.kmer_bits;
+  bool transform = false;
+  while (true) {
+    uint32_t idle = __ballot_sync(full, !active);
+    while (idle) {  // hand unclassified strands to idle lanes
+      if (!pend) {
+        if (group * 32u >= n) break;
+        const uint32_t idx = group * 32u + lane;
+        grp_strand = idx < n ? (list ? list[idx] : 2 * b.read_begin + idx) : 0u;
+        pend = __ballot_sync(full, idx < n && o.status[grp_strand] == ST_UNCLASSIFIED);
+        group += n_warps;
+        if (!pend) continue;
       }
-      const bool rc = (strand & 1u) != 0;
-      bool missing;
-      if (L <= 512) {
-        // global: the reverse strand probes the set indexed by reverse-complement codes; shared: one copy of the
-        // forward set, reverse-strand codes transformed
-        missing = SMEM ? warp_any_kmer_missing(v.k, bits_f, rc, nullptr, word, L, lane)
-                       : warp_any_kmer_missing(v.k, rc ? v.kmer_bits_rc : v.kmer_bits, false, nullptr, word, L, lane);
-      } else {  // more than 32 packed words: windows from memory
-        const uint32_t* w = b.packed + b.word_off[strand >> 1];
-        missing = SMEM ? warp_any_kmer_missing(v.k, bits_f, rc, w, 0u, L, lane)
-                       : warp_any_kmer_missing(v.k, rc ? v.kmer_bits_rc : v.kmer_bits, false, w, 0u, L, lane);
+      const uint32_t n_take = min(__popc(idle), __popc(pend));
+      const uint32_t r = __popc(idle & lt);
+      const bool take = !active && r < n_take;
+      const uint32_t src = take ? (uint32_t)__fns(pend, 0, r + 1) : 0u;  // r-th pending strand of the group
+      const uint32_t s_new = __shfl_sync(full, grp_strand, src & 31u);
+      if (take) {
+        strand = s_new;
+        const uint32_t L = b.len[strand >> 1];
+        w = b.packed + b.word_off[strand >> 1];
+        n_words = (L + 15) >> 4;
+        n_kmers = L - k + 1;  // unclassified strands have L >= k
+        win = __ldg(w);
+        if (n_words > 1) win |= (uint64_t)__ldg(w + 1) << 32;
+        i = 0;
+        const bool rc = (strand & 1u) != 0;
+        transform = SMEM && rc;
+        if (!SMEM) bits = rc ? v.kmer_bits_rc : v.kmer_bits;
+        active = true;
       }
-      if (lane == 0) o.status[strand] = missing ? ST_MISSING_KMER : ST_NO_EXTENSION;
+      for (uint32_t j = 0; j < n_take; ++j) {  // the n_take lowest pending strands / idle lanes are served
+        pend &= pend - 1;
+        idle &= idle - 1;
+      }
+    }
+    if (!__any_sync(full, active)) break;
+#pragma unroll
+    for (int u = 0; u < kClassifyUnroll; ++u) {
+      if (active) {
+        uint32_t code = (uint32_t)win & mask;
+        if (transform) code = pair_reverse32(~(uint32_t)win) >> rsh;
+        const bool present = (bits[code >> 5] >> (code & 31u)) & 1u;
+        ++i;
+        if (!present || i == n_kmers) {
+          o.status[strand] = present ? ST_NO_EXTENSION : ST_MISSING_KMER;
+          active = false;
+        } else {
+          win >>= 2;
+          if ((i & 15u) == 0) {  // 16 bases consumed: bring in the next packed word
+            const uint32_t nw = (i >> 4) + 1;
+            if (nw < n_words) win |= (uint64_t)__ldg(w + nw) << 32;
+          }
+        }
+      }
     }
   }
 }

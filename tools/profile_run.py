@@ -20,6 +20,7 @@ idx.upload(bases, offs, seeds)
 for _ in range(iters):
     idx.map_resident()
     print(idx.run_info())
+    print("   kernel ms:", {k: round(v, 4) for k, v in idx.kernel_ms().items()})
 if os.environ.get("GQ_DEBUG"):
     import ctypes as C
     import numpy as np
