@@ -175,9 +175,9 @@ struct HostBatch {
   bool is_packed() const { return packed != nullptr || word_off != nullptr; }
 };
 
-// H2D of one slice of the caller's buffers: bases on `st`, the small per-read arrays on `st_small` (their
-// set-up latency then overlaps the big copy instead of sitting between two of them)
-static void copy_chunk(gq_index* ix, const HostBatch& hb, Chunk c, cudaStream_t st, cudaStream_t st_small) {
+// H2D of one slice of the caller's buffers, all on one stream in slice order
+static void copy_chunk(gq_index* ix, const HostBatch& hb, Chunk c, cudaStream_t st) {
+  cudaStream_t st_small = st;
   const size_t nr = c.r1 - c.r0;
   if (hb.is_packed()) {
     const uint32_t w0 = hb.word_off[c.r0], w1 = hb.word_off[c.r1];
@@ -203,7 +203,7 @@ static void upload_chunk(gq_index* ix, const uint8_t* bases, const uint64_t* off
   hb.bases = bases;
   hb.off = off;
   hb.seeds = seeds;
-  copy_chunk(ix, hb, c, st, st);
+  copy_chunk(ix, hb, c, st);
   gq::launch_pack(ix->bases.p, ix->offsets.p, c.r0, c.r1, ix->word_off.p, ix->packed.p, ix->len.p, st);
 }
 
@@ -267,8 +267,7 @@ static void do_map(gq_index* ix, const HostBatch* hb = nullptr) {
   int launches = 0;
   if (pipelined) {
     if (!ix->copy_stream) CUDA_OK(cudaStreamCreateWithFlags(&ix->copy_stream, cudaStreamNonBlocking));
-    if (!ix->copy_stream2) CUDA_OK(cudaStreamCreateWithFlags(&ix->copy_stream2, cudaStreamNonBlocking));
-    while (ix->chunk_events.size() < 2 * chunks.size()) {
+    while (ix->chunk_events.size() < chunks.size()) {
       cudaEvent_t e;
       CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
       ix->chunk_events.push_back(e);
@@ -276,14 +275,30 @@ static void do_map(gq_index* ix, const HostBatch* hb = nullptr) {
     // the copy streams must not start overwriting buffers the compute stream may still be reading
     CUDA_OK(cudaEventRecord(ix->ev[3], st));
     CUDA_OK(cudaStreamWaitEvent(ix->copy_stream, ix->ev[3], 0));
-    CUDA_OK(cudaStreamWaitEvent(ix->copy_stream2, ix->ev[3], 0));
     // copies only on the copy streams, back to back; packing runs on the compute stream
     for (size_t i = 0; i < chunks.size(); ++i) {
-      copy_chunk(ix, *hb, chunks[i], ix->copy_stream, ix->copy_stream2);
-      CUDA_OK(cudaEventRecord(ix->chunk_events[2 * i], ix->copy_stream));
-      CUDA_OK(cudaEventRecord(ix->chunk_events[2 * i + 1], ix->copy_stream2));
+      // one stream, in slice order: with the small per-read arrays on a second stream the copy engine served that
+      // stream only after ALL the big copies (measured: the first slice's kernels started when the last byte of the
+      // batch had arrived)
+      copy_chunk(ix, *hb, chunks[i], ix->copy_stream);
+      CUDA_OK(cudaEventRecord(ix->chunk_events[i], ix->copy_stream));
+      if (getenv("GQ_TIMELINE")) {
+        cudaEvent_t e;
+        CUDA_OK(cudaEventCreate(&e));
+        CUDA_OK(cudaEventRecord(e, ix->copy_stream));
+        ix->tl_copy.push_back(e);
+      }
     }
   }
+  // developer aid (GQ_TIMELINE=1): when each slice's copy ended and its kernels started / ended, relative to ev[0]
+  static const bool timeline = getenv("GQ_TIMELINE") != nullptr;
+  std::vector<cudaEvent_t> tl;
+  if (timeline && pipelined)
+    for (size_t i = 0; i < 4 * chunks.size(); ++i) {
+      cudaEvent_t e;
+      CUDA_OK(cudaEventCreate(&e));
+      tl.push_back(e);
+    }
   CUDA_OK(cudaEventRecord(ix->ev[0], st));
   // Slices alternate between two compute streams (each with its own arena), so the kernels of slice i+1
   // fill the GPU while slice i's are in their latency-bound tails; the caller's stream joins at the end.
@@ -301,8 +316,8 @@ static void do_map(gq_index* ix, const HostBatch* hb = nullptr) {
     cudaStream_t cs = (two_streams && (i & 1)) ? ix->aux_stream : st;
     uint32_t* arena = (two_streams && (i & 1)) ? ix->arena2.p : ix->arena.p;
     if (pipelined) {
-      CUDA_OK(cudaStreamWaitEvent(cs, ix->chunk_events[2 * i], 0));
-      CUDA_OK(cudaStreamWaitEvent(cs, ix->chunk_events[2 * i + 1], 0));
+      CUDA_OK(cudaStreamWaitEvent(cs, ix->chunk_events[i], 0));
+      if (!tl.empty()) CUDA_OK(cudaEventRecord(tl[4 * i + 1], cs));
       if (!host_packed) {
         gq::launch_pack(ix->bases.p, ix->offsets.p, chunks[i].r0, chunks[i].r1, ix->word_off.p, ix->packed.p, ix->len.p, cs);
         ++launches;
@@ -364,6 +379,7 @@ static void do_map(gq_index* ix, const HostBatch* hb = nullptr) {
       if (timed) CUDA_OK(cudaEventRecord(ix->kev[6], cs));
     }
     launches += 3;
+    if (!tl.empty()) CUDA_OK(cudaEventRecord(tl[4 * i + 2], cs));
   }
   if (two_streams) {
     CUDA_OK(cudaEventRecord(ix->aux_event, ix->aux_stream));
@@ -379,6 +395,19 @@ static void do_map(gq_index* ix, const HostBatch* hb = nullptr) {
     float ms_t = 0;
     cudaEventElapsedTime(&ms_t, ix->ev[0], ix->ev[2]);
     ix->info[6] = ms_t;  // all kernels of the call (CUDA events on the caller's stream)
+  }
+  if (!tl.empty()) {
+    for (size_t i = 0; i < chunks.size(); ++i) {
+      float a = 0, b2 = 0, c2 = 0;
+      cudaEventElapsedTime(&a, ix->ev[3], ix->tl_copy[i]);
+      cudaEventElapsedTime(&b2, ix->ev[3], tl[4 * i + 1]);
+      cudaEventElapsedTime(&c2, ix->ev[3], tl[4 * i + 2]);
+      fprintf(stderr, "slice %zu: %u reads, copy done %.3f ms, kernels %.3f .. %.3f ms (stream %d)\n", i,
+              chunks[i].r1 - chunks[i].r0, a, b2, c2, (int)(i & 1));
+    }
+    for (auto e : tl) cudaEventDestroy(e);
+    for (auto e : ix->tl_copy) cudaEventDestroy(e);
+    ix->tl_copy.clear();
   }
   if (chunks.size() == 1) {
     float ms_s = 0, ms_c = 0;
@@ -648,7 +677,6 @@ int gq_index_destroy(gq_index* ix) {
     if (e) cudaEventDestroy(e);
   for (auto& e : ix->chunk_events) cudaEventDestroy(e);
   if (ix->copy_stream) cudaStreamDestroy(ix->copy_stream);
-  if (ix->copy_stream2) cudaStreamDestroy(ix->copy_stream2);
   if (ix->aux_stream) cudaStreamDestroy(ix->aux_stream);
   if (ix->aux_event) cudaEventDestroy(ix->aux_event);
   ix->arena2.release();

@@ -19,7 +19,7 @@
 #endif
 
 #ifndef GQ_COV_CHUNK
-#define GQ_COV_CHUNK 4  // per-site records fetched together by the coverage table route
+#define GQ_COV_CHUNK 2  // per-site records fetched together by the coverage table route
 #endif
 
 namespace gq {

@@ -67,14 +67,14 @@ struct gq_index {
   uint32_t seed_recs_per_read = 16;  // candidate records per read (set from the index: ~2.5 x mean suffixes per indexed k-mer, both strands); a full pool sends strands to the general kernel
   bool use_seed_pass = true;
   DevBuf<uint32_t> arena, big_arena;
-  cudaStream_t copy_stream = nullptr, copy_stream2 = nullptr;
+  cudaStream_t copy_stream = nullptr;
   cudaStream_t aux_stream = nullptr;  // second compute stream of the pipelined path
   cudaEvent_t aux_event = nullptr;
   DevBuf<uint32_t> arena2;
   void* fetch_host = nullptr;  // pinned staging of gq_coverage_fetch
   size_t fetch_host_bytes = 0;
   DevBuf<uint16_t> fetch_dev;
-  std::vector<cudaEvent_t> chunk_events;
+  std::vector<cudaEvent_t> chunk_events, tl_copy;
   uint32_t chunk_reads = 1u << 18, tail_chunk_reads = 1u << 15;
   uint32_t resident_slices = 1;  // gq_map_resident: slices run on two streams
   bool overlap_classify = true;  // single-slice runs: classify_kernel beside coverage_kernel on a second stream  // slice size of the H2D / compute pipeline in gq_map_batch

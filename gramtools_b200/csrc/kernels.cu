@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(kSearchThreads, GQ_SEARCH_MIN_BLOCKS)
 // the next unclassified strand of the warp's current group of 32 statuses, so lanes stay busy whatever the
 // strands' lengths. The probes are random 4-byte reads, so when the 4^k-bit set fits (k <= 10: 128 KB) each CTA
 // keeps a copy in shared memory (one persistent 1024-thread CTA per SM); the reverse strand reverse-complements
-// its code (shared copy) or probes the set indexed by reverse-complement codes (global memory).
+// windows are probed, as they are, against the set indexed by reverse-complement codes: one launch per orientation.
 // [v1 gave a whole warp to each strand: 181 warp instructions per strand, mostly per-strand set-up; this form
 // needs ~25.]
 constexpr uint32_t kClassifySmemBytes = 160 * 1024;
@@ -493,10 +493,11 @@ constexpr int kClassifyUnroll = 4;
 
 template <bool SMEM>
 __global__ void __launch_bounds__(SMEM ? 1024 : 256)
-    classify_kernel(IndexView v, BatchView b, SearchOut o, const uint32_t* list, uint32_t n_list, uint32_t bits_words) {
+    classify_kernel(IndexView v, BatchView b, SearchOut o, const uint32_t* list, uint32_t n_list, uint32_t bits_words,
+                    const uint32_t* __restrict__ g_bits, uint32_t parity) {
   extern __shared__ __align__(16) uint32_t s_bits[];
   if (SMEM) {
-    const uint4* src = reinterpret_cast<const uint4*>(v.kmer_bits);
+    const uint4* src = reinterpret_cast<const uint4*>(g_bits);
     uint4* dst = reinterpret_cast<uint4*>(s_bits);
     for (uint32_t q = threadIdx.x; q < (bits_words + 3) / 4; q += blockDim.x) dst[q] = __ldg(src + q);
     __syncthreads();
@@ -505,68 +506,107 @@ __global__ void __launch_bounds__(SMEM ? 1024 : 256)
   const uint32_t lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
   const uint32_t full = 0xFFFFFFFFu;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-  const uint32_t k = v.k, mask = (k == 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u), rsh = 32 - 2 * k;
-  uint32_t group = warp;              // next group of 32 strands this warp looks at
-  uint32_t pend = 0, grp_strand = 0;  // unclassified strands of the current group not yet taken (lane = position)
-  // lane state
+  const uint32_t k = v.k, mask = (k == 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
+  // The warp's share: groups of 32 consecutive strands, round-robin over the warps. A group is fetched by the
+  // whole warp (lane = position: status, length, word offset, first two packed words — coalesced) one group
+  // AHEAD of its use, so handing a strand to a free lane is a few shuffles and never waits for memory.
+  struct Group {
+    uint32_t strand, L, woff, w0, w1;
+    bool need;
+  };
+  uint32_t g_load = warp;  // next group to fetch
+  auto fetch = [&](Group& G) {
+    const uint32_t idx = g_load * 32u + lane;
+    g_load += n_warps;
+    G.strand = idx < n ? (list ? list[idx] : 2 * b.read_begin + idx) : 0u;
+    G.need = idx < n && (G.strand & 1u) == parity && o.status[G.strand] == ST_UNCLASSIFIED;
+    G.L = G.woff = G.w0 = G.w1 = 0;
+    if (G.need) {
+      G.L = b.len[G.strand >> 1];
+      G.woff = b.word_off[G.strand >> 1];
+      G.w0 = __ldg(b.packed + G.woff);
+      if (G.L > 16) G.w1 = __ldg(b.packed + G.woff + 1);
+    }
+  };
+  Group cur, nxt;
+  uint32_t cur_first = warp * 32u;  // index of the current group's first strand
+  fetch(cur);
+  fetch(nxt);
+  uint32_t pend = __ballot_sync(full, cur.need);  // strands of the current group not yet handed out
+  // lane state: the strand's k-mers i .. n_kmers-1 are still to be probed; `win` holds the packed bases from k-mer i on
   bool active = false;
   uint32_t strand = 0, i = 0, n_kmers = 0, n_words = 0;
-  uint64_t win = 0;
+  uint32_t wlo = 0, whi = 0;
   const uint32_t* w = nullptr;
-  const uint32_t* bits = SMEM ? (const uint32_t*)s_bits : v.kmer_bits;
-  bool transform = false;
+  auto probe = [&](uint32_t code) -> uint32_t {  // bit `code` of the presence set, in bit 0 of the result
+    const uint32_t word = SMEM ? s_bits[code >> 5] : __ldg(g_bits + (code >> 5));
+    return word >> (code & 31u);
+  };
   while (true) {
     uint32_t idle = __ballot_sync(full, !active);
-    while (idle) {  // hand unclassified strands to idle lanes
-      if (!pend) {
-        if (group * 32u >= n) break;
-        const uint32_t idx = group * 32u + lane;
-        grp_strand = idx < n ? (list ? list[idx] : 2 * b.read_begin + idx) : 0u;
-        pend = __ballot_sync(full, idx < n && o.status[grp_strand] == ST_UNCLASSIFIED);
-        group += n_warps;
-        if (!pend) continue;
+    if (__popc(idle) >= 8 || idle == full) {
+      while (idle) {  // hand unclassified strands to the free lanes
+        if (!pend) {
+          if (cur_first >= n) break;  // the warp's share is used up
+          cur = nxt;
+          cur_first += n_warps * 32u;
+          pend = __ballot_sync(full, cur.need);
+          fetch(nxt);
+          continue;
+        }
+        const uint32_t n_take = min(__popc(idle), __popc(pend));
+        const uint32_t r = __popc(idle & lt);
+        const bool take = !active && r < n_take;
+        const uint32_t src = take ? (uint32_t)__fns(pend, 0, r + 1) & 31u : 0u;  // r-th pending strand of the group
+        const uint32_t s_new = __shfl_sync(full, cur.strand, src), L_new = __shfl_sync(full, cur.L, src),
+                       woff_new = __shfl_sync(full, cur.woff, src), w0_new = __shfl_sync(full, cur.w0, src),
+                       w1_new = __shfl_sync(full, cur.w1, src);
+        if (take) {
+          strand = s_new;
+          w = b.packed + woff_new;
+          n_words = (L_new + 15) >> 4;
+          n_kmers = L_new - k + 1;  // unclassified strands have L >= k
+          wlo = w0_new;
+          whi = w1_new;
+          i = 0;
+          active = true;
+        }
+        for (uint32_t j = 0; j < n_take; ++j) {  // the n_take lowest pending strands / free lanes are served
+          pend &= pend - 1;
+          idle &= idle - 1;
+        }
       }
-      const uint32_t n_take = min(__popc(idle), __popc(pend));
-      const uint32_t r = __popc(idle & lt);
-      const bool take = !active && r < n_take;
-      const uint32_t src = take ? (uint32_t)__fns(pend, 0, r + 1) : 0u;  // r-th pending strand of the group
-      const uint32_t s_new = __shfl_sync(full, grp_strand, src & 31u);
-      if (take) {
-        strand = s_new;
-        const uint32_t L = b.len[strand >> 1];
-        w = b.packed + b.word_off[strand >> 1];
-        n_words = (L + 15) >> 4;
-        n_kmers = L - k + 1;  // unclassified strands have L >= k
-        win = __ldg(w);
-        if (n_words > 1) win |= (uint64_t)__ldg(w + 1) << 32;
-        i = 0;
-        const bool rc = (strand & 1u) != 0;
-        transform = SMEM && rc;
-        if (!SMEM) bits = rc ? v.kmer_bits_rc : v.kmer_bits;
-        active = true;
-      }
-      for (uint32_t j = 0; j < n_take; ++j) {  // the n_take lowest pending strands / idle lanes are served
-        pend &= pend - 1;
-        idle &= idle - 1;
-      }
+      if (!__any_sync(full, active)) break;
     }
-    if (!__any_sync(full, active)) break;
+    // up to 8 k-mers per lane and iteration: four at a time without a test in between while at least four are left
 #pragma unroll
-    for (int u = 0; u < kClassifyUnroll; ++u) {
+    for (int u = 0; u < 2; ++u) {
       if (active) {
-        uint32_t code = (uint32_t)win & mask;
-        if (transform) code = pair_reverse32(~(uint32_t)win) >> rsh;
-        const bool present = (bits[code >> 5] >> (code & 31u)) & 1u;
-        ++i;
-        if (!present || i == n_kmers) {
-          o.status[strand] = present ? ST_NO_EXTENSION : ST_MISSING_KMER;
-          active = false;
-        } else {
-          win >>= 2;
-          if ((i & 15u) == 0) {  // 16 bases consumed: bring in the next packed word
+        bool done;
+        uint32_t present;
+        if (n_kmers - i >= 4) {
+          present = probe(wlo & mask) & probe(__funnelshift_r(wlo, whi, 2) & mask) &
+                    probe(__funnelshift_r(wlo, whi, 4) & mask) & probe(__funnelshift_r(wlo, whi, 6) & mask);
+          wlo = __funnelshift_r(wlo, whi, 8);
+          whi >>= 8;
+          i += 4;
+          if ((i & 15u) == 0) {  // 16 bases consumed: the low word is the next packed word, bring in the one after
             const uint32_t nw = (i >> 4) + 1;
-            if (nw < n_words) win |= (uint64_t)__ldg(w + nw) << 32;
+            whi = nw < n_words ? __ldg(w + nw) : 0u;
           }
+          done = i == n_kmers;
+        } else {  // the last one to three k-mers of the strand
+          present = 1u;
+          for (; i < n_kmers; ++i) {
+            present &= probe(wlo & mask);
+            wlo = __funnelshift_r(wlo, whi, 2);
+            whi >>= 2;
+          }
+          done = true;
+        }
+        if (!(present & 1u) || done) {
+          o.status[strand] = (present & 1u) ? ST_NO_EXTENSION : ST_MISSING_KMER;
+          active = false;
         }
       }
     }
@@ -579,12 +619,17 @@ void launch_classify(const IndexView& v, const BatchView& b, const SearchOut& o,
   if (work == 0) return;
   const uint64_t bits_words = ((1ull << (2 * v.k)) + 31) / 32;
   const uint64_t bytes = ((bits_words + 3) / 4) * 16;
-  if (bytes <= kClassifySmemBytes && work >= 148u * 32u * 4u) {
-    cudaFuncSetAttribute(classify_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClassifySmemBytes);
-    classify_kernel<true><<<148, 1024, bytes, st>>>(v, b, o, list, n_list, (uint32_t)bits_words);
-  } else {
-    uint32_t blocks = min((work + 255) / 256, 148u * 8u);  // 8 warps per CTA, 32 strands per warp round
-    classify_kernel<false><<<blocks, 256, 0, st>>>(v, b, o, list, n_list, (uint32_t)bits_words);
+  // forward strands probe the presence set, reverse strands the same set indexed by reverse-complement codes (the
+  // stored read's windows are tested as they are): one pass per strand orientation, each with its set
+  for (uint32_t parity = 0; parity < 2; ++parity) {
+    const uint32_t* bits = parity ? v.kmer_bits_rc : v.kmer_bits;
+    if (bytes <= kClassifySmemBytes && work >= 148u * 32u * 4u) {
+      cudaFuncSetAttribute(classify_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClassifySmemBytes);
+      classify_kernel<true><<<148, 1024, bytes, st>>>(v, b, o, list, n_list, (uint32_t)bits_words, bits, parity);
+    } else {
+      uint32_t blocks = min((work + 255) / 256, 148u * 8u);
+      classify_kernel<false><<<blocks, 256, 0, st>>>(v, b, o, list, n_list, (uint32_t)bits_words, bits, parity);
+    }
   }
 }
 
