@@ -240,7 +240,7 @@ static void do_map(gq_index* ix, const HostBatch* hb = nullptr) {
   ix->overflow_list.reserve(4 * (size_t)n + 16);  // a strand can be flagged by the text kernel and again by the general one
   ix->cov_overflow_list.reserve(2 * (size_t)n);
   ix->mapped_list.reserve(2 * (size_t)n);
-  ix->small.reserve(8 + 5 * kMaxChunks);
+  ix->small.reserve(8 + 6 * kMaxChunks);
   ix->surv_cnt.reserve(2 * (size_t)n);
   ix->gen_list.reserve(2 * (size_t)n);
   ix->seed_rec.reserve(4 * std::max<size_t>((size_t)n * ix->seed_recs_per_read, 1 << 16));
@@ -257,7 +257,7 @@ static void do_map(gq_index* ix, const HostBatch* hb = nullptr) {
   ix->arena.reserve((size_t)std::max(threads, threads2) * ix->arena_words);
   // small: [0] pool_used [1] n_overflow [2] n_cov_overflow;
   // per chunk c: [8+4c] n_mapped [9+4c] work counter [10+4c] survivor records [11+4c] n_gen (general-kernel work list)
-  CUDA_OK(cudaMemsetAsync(ix->small.p, 0, (8 + 5 * kMaxChunks) * 4, st));
+  CUDA_OK(cudaMemsetAsync(ix->small.p, 0, (8 + 6 * kMaxChunks) * 4, st));
 
   gq::BatchView b{ix->packed.p, ix->word_off.p, ix->len.p, ix->seeds.p, n, 0, n};
   gq::SearchOut o{ix->status.p, ix->st_off.p, ix->st_words.p, ix->st_count.p, ix->pool.p, (uint32_t)ix->pool.cap,
@@ -365,7 +365,7 @@ static void do_map(gq_index* ix, const HostBatch* hb = nullptr) {
       gq::launch_classify(ix->dv, bc, oc, nullptr, 0, ix->aux_stream);
       CUDA_OK(cudaEventRecord(ix->kev[5], ix->aux_stream));
       gq::launch_coverage(ix->dv, bc, oc, c, arena, ix->arena_words, threads2, nullptr, 0,
-                          ix->cov_overflow_list.p, ix->small.p + 2, cs);
+                          ix->cov_overflow_list.p, ix->small.p + 2, ix->small.p + 8 + 5 * kMaxChunks + i, cs);
       CUDA_OK(cudaEventRecord(ix->kev[6], cs));
       CUDA_OK(cudaEventRecord(ix->aux_event, ix->aux_stream));
       CUDA_OK(cudaStreamWaitEvent(cs, ix->aux_event, 0));
@@ -375,7 +375,7 @@ static void do_map(gq_index* ix, const HostBatch* hb = nullptr) {
       gq::launch_classify(ix->dv, bc, oc, nullptr, 0, cs);
       if (timed) CUDA_OK(cudaEventRecord(ix->kev[5], cs));
       gq::launch_coverage(ix->dv, bc, oc, c, arena, ix->arena_words, threads2, nullptr, 0,
-                          ix->cov_overflow_list.p, ix->small.p + 2, cs);
+                          ix->cov_overflow_list.p, ix->small.p + 2, ix->small.p + 8 + 5 * kMaxChunks + i, cs);
       if (timed) CUDA_OK(cudaEventRecord(ix->kev[6], cs));
     }
     launches += 3;
@@ -496,7 +496,7 @@ static void do_map(gq_index* ix, const HostBatch* hb = nullptr) {
     gq::launch_classify(ix->dv, b, o, list.p, n_list, st);
     ++launches;
     gq::launch_coverage(ix->dv, b, o, c, ar, aw, std::min<uint32_t>(bt, threads2), list.p, n_list,
-                        ix->cov_overflow_list.p, ix->small.p + 2, st);
+                        ix->cov_overflow_list.p, ix->small.p + 2, ix->small.p + 8 + 5 * kMaxChunks, st);
     launches += 2;
     CUDA_OK(cudaMemcpyAsync(small, ix->small.p, 16, cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
@@ -528,7 +528,7 @@ static void do_map(gq_index* ix, const HostBatch* hb = nullptr) {
     CUDA_OK(cudaMemcpyAsync(list.p, ix->cov_overflow_list.p, (size_t)n_list * 4, cudaMemcpyDeviceToDevice, st));
     CUDA_OK(cudaMemsetAsync(ix->small.p + 2, 0, 4, st));
     gq::launch_coverage(ix->dv, b, o, c, ix->big_arena.p, big_words, bt, list.p, n_list, ix->cov_overflow_list.p,
-                        ix->small.p + 2, st);
+                        ix->small.p + 2, ix->small.p + 8 + 5 * kMaxChunks, st);
     ++launches;
     CUDA_OK(cudaMemcpyAsync(small, ix->small.p, 16, cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
@@ -541,12 +541,18 @@ static void do_map(gq_index* ix, const HostBatch* hb = nullptr) {
   }
   gq::launch_stats(ix->status.p, ix->len.p, n, ix->stats.p, st);
   ++launches;
+  CUDA_OK(cudaEventRecord(ix->ev[2], st));  // end of the call's device work, re-runs included
   uint32_t gs[2];
   CUDA_OK(cudaMemcpyAsync(gs, ix->gsmall.p, 8, cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaStreamSynchronize(st));
   CUDA_OK(cudaGetLastError());
   if (gs[1] & 1u) throw std::runtime_error("grouped allele count table is full (internal error: flagged strands were not re-run)");
   if (gs[1] & 2u) throw std::runtime_error("inconsistent traversal while recording per-base coverage");
+  {
+    float ms_t = 0;
+    cudaEventElapsedTime(&ms_t, ix->ev[0], ix->ev[2]);
+    ix->info[6] = ms_t;  // all kernels of the call, overflow re-runs included (CUDA events on the caller's stream)
+  }
   ix->info[0] = launches;
   ix->info[1] = (double)rerun;
   ix->info[4] = small[0];
@@ -577,6 +583,9 @@ static void finish_handle(gq_index* ix) {
   }
   alloc_coverage(ix);
   reset_coverage(ix);
+  // nested PRGs: paths of a dozen loci and dozens of states per strand are common — larger per-lane arenas keep
+  // most strands out of the overflow re-runs
+  if (ix->h.is_nested) ix->arena_words = std::max<uint32_t>(ix->arena_words, 2048);
 }
 
 // -------------------------------------------------------------------------------------------------

@@ -1459,28 +1459,46 @@ struct Trav {
   }
 };
 
+// Per-node hulls of one read (PbCovRecorder, allele_base.cpp:221-296): open-addressing table keyed by node id
+// (a strand with dozens of final states visits thousands of nodes; the first version scanned a list per insertion,
+// quadratic in exactly the strands that are slowest anyway).
 struct Hull {
-  uint32_t* e;  // triples (node, start, end)
-  uint32_t n, cap;
+  uint32_t* e;   // cap triples (node, start, end); node == kNoAllele: empty slot
+  uint32_t n, cap, shift;  // cap = 1 << (32 - shift)
   bool overflow;
 };
+GQ_DEV inline void hull_init(Hull& h, uint32_t* mem, uint32_t words) {
+  uint32_t lg = 2;
+  while (lg < 20 && 3u * (2u << lg) <= words) ++lg;
+  h.e = mem;
+  h.cap = 1u << lg;
+  h.shift = 32 - lg;
+  h.n = 0;
+  h.overflow = 3u * h.cap > words;
+  if (!h.overflow)
+    for (uint32_t i = 0; i < h.cap; ++i) mem[3 * i] = kNoAllele;
+}
 GQ_DEV void hull_add(const IndexView& v, Hull& h, uint32_t node, uint32_t s, uint32_t e) {
   if (GQ_AT(v.nodes, node).len == 0) return;  // process_Node :282-287
-  for (uint32_t i = 0; i < h.n; ++i) {
-    if (h.e[3 * i] == node) {
-      if (s < h.e[3 * i + 1]) h.e[3 * i + 1] = s;
-      if (e > h.e[3 * i + 2]) h.e[3 * i + 2] = e;
+  for (uint32_t i = (node * 2654435761u) >> h.shift;; i = (i + 1) & (h.cap - 1)) {
+    uint32_t* t = h.e + 3 * i;
+    if (t[0] == node) {
+      if (s < t[1]) t[1] = s;
+      if (e > t[2]) t[2] = e;
+      return;
+    }
+    if (t[0] == kNoAllele) {
+      if (2 * (h.n + 1) > h.cap) {  // more than half full: the strand is re-run with a larger arena
+        h.overflow = true;
+        return;
+      }
+      t[0] = node;
+      t[1] = s;
+      t[2] = e;
+      ++h.n;
       return;
     }
   }
-  if (h.n >= h.cap) {
-    h.overflow = true;
-    return;
-  }
-  h.e[3 * h.n] = node;
-  h.e[3 * h.n + 1] = s;
-  h.e[3 * h.n + 2] = e;
-  ++h.n;
 }
 
 // `alleles`: n allele ids, `stride` words apart (2 inside a sorted locus list, 1 in a group record)
@@ -1539,6 +1557,178 @@ GQ_DEV uint32_t grouped_find_or_insert(const CoverageView& c, uint32_t slot, con
   if (mine) gq_atomic_cas(c.gpool_used, mine - 1 + n + 2, mine - 1);
   if (found == kNoAllele) gq_atomic_or(c.error_flags, 1u);
   return found;
+}
+
+// The general route of record_strand (several states, several occurrences, nested sites): MappingInstanceSelector,
+// LocusFinder and PbCovRecorder restated over flat scratch. Nothing is committed before every scratch structure has
+// proved large enough, so the caller can run it again (lists in the arena, or a larger arena) without double counting.
+enum RecResult : uint32_t { REC_OK = 0, REC_LISTS = 1 /* LocusFinder's sets overflowed */, REC_ARENA = 2 };
+constexpr uint32_t kLocalLoci = 96;
+
+GQ_DEV uint32_t record_general(const IndexView& v, const BatchView& b, const CoverageView& c, uint32_t strand,
+                               const uint32_t* recs, uint32_t ns, uint32_t L, uint32_t nonvar, uint32_t* arena,
+                               uint32_t arena_words, uint32_t* local_lists) {
+  Scratch sc{arena, 0, arena_words, false};
+  uint32_t* key_off = sc.alloc(2 * ns);  // (offset, len) per state; len = 0xFFFFFFFF for path-less
+  uint32_t* rep = sc.alloc(ns);          // class representative per state
+  if (!key_off || !rep) return REC_ARENA;
+  LocusLists ll;
+  ll.overflow = false;
+  if (local_lists) {  // the small sets of LocusFinder in thread-local memory (L1-resident) ...
+    ll.cap = kLocalLoci;
+    ll.used = local_lists;
+    ll.base = local_lists + kLocalLoci;
+    ll.loci = local_lists + 2 * kLocalLoci;
+  } else {            // ... or, when a strand's sets do not fit there, in the arena
+    const uint32_t cap = (arena_words - sc.used) / 16;
+    ll.cap = cap;
+    ll.used = sc.alloc(cap);
+    ll.base = sc.alloc(cap);
+    ll.loci = sc.alloc(2 * cap);
+    if (sc.overflow) return REC_ARENA;
+  }
+  {
+    const uint32_t* p = recs;
+    for (uint32_t j = 0; j < ns; ++j) {
+      StateRec st = parse_rec(p);
+      p += st.words();
+      if (!(st.nt | st.ng)) {
+        key_off[2 * j] = 0;
+        key_off[2 * j + 1] = 0xFFFFFFFFu;
+        continue;
+      }
+      ll.n_loci = ll.n_base = 0;
+      locus_finder(v, st, ll);
+      if (ll.overflow) return REC_LISTS;
+      sort_u32(ll.base, ll.n_base);
+      uint32_t* k = sc.alloc(ll.n_base);
+      if (!k && ll.n_base) return REC_ARENA;
+      for (uint32_t i = 0; i < ll.n_base; ++i) k[i] = ll.base[i];
+      key_off[2 * j] = (uint32_t)(k - arena);
+      key_off[2 * j + 1] = ll.n_base;
+    }
+  }
+  // class representative of every state with a path = the first state with the same key (compared with the
+  // representatives found so far only), and the number of distinct classes
+  uint32_t ncls = 0;
+  for (uint32_t j = 0; j < ns; ++j) {
+    rep[j] = 0xFFFFFFFFu;
+    if (key_off[2 * j + 1] == 0xFFFFFFFFu) continue;
+    rep[j] = j;
+    for (uint32_t i = 0; i < j; ++i)
+      if (rep[i] == i && cmp_key(arena + key_off[2 * i], key_off[2 * i + 1], arena + key_off[2 * j], key_off[2 * j + 1]) == 0) {
+        rep[j] = i;
+        break;
+      }
+    if (rep[j] == j) ++ncls;
+  }
+  // random_select_entry :97-107
+  uint32_t total = nonvar + ncls;
+  uint32_t pick = total == 1 ? 1u : uniform_1_to(GQ_AT(b.seeds, strand >> 1), total);
+  if (pick <= nonvar) return REC_OK;
+  // the (pick - nonvar - 1)-th class in std::map order: the representative with that many smaller ones
+  uint32_t want = pick - nonvar - 1;
+  int chosen = -1;
+  for (uint32_t j = 0; j < ns && chosen < 0; ++j) {
+    if (rep[j] != j) continue;
+    uint32_t less = 0;
+    for (uint32_t i = 0; i < ns; ++i)
+      if (i != j && rep[i] == i &&
+          cmp_key(arena + key_off[2 * i], key_off[2 * i + 1], arena + key_off[2 * j], key_off[2 * j + 1]) < 0)
+        ++less;
+    if (less == want) chosen = (int)j;
+  }
+  if (chosen < 0) {
+    gq_atomic_or(c.error_flags, 2u);
+    return REC_OK;
+  }
+  // ---- pass 2: loci of the chosen class + per-node hulls (PbCovRecorder :221-296) ----
+  ll.n_loci = 0;
+  Hull hull;
+  hull_init(hull, arena + sc.used, arena_words - sc.used);
+  if (hull.overflow) return REC_ARENA;
+  {
+    const uint32_t* p = recs;
+    for (uint32_t j = 0; j < ns; ++j) {
+      StateRec st = parse_rec(p);
+      p += st.words();
+      if (rep[j] != (uint32_t)chosen) continue;  // not a state of the chosen class (or path-less)
+      ll.n_base = 0;
+      locus_finder(v, st, ll);  // loci accumulate across the class (set union)
+      if (ll.overflow) return REC_LISTS;
+      bool first = true;
+      for (uint32_t occ = st.lo;; ++occ) {
+        uint32_t pos = GQ_LDG(v.sa + occ);
+        uint32_t nid = GQ_LDG(v.pos2node + pos);
+        Trav t;
+        t.v = &v;
+        t.cur = nid;
+        t.remaining = L;
+        t.T = st.T;
+        t.ti = st.nt;
+        t.first = true;
+        const Node& nd = GQ_AT(v.nodes, nid);
+        t.start_pos = nd.len > 1 ? pos - nd.start : 0;  // setup_random_access, coverage_graph.cpp:131-144
+        t.end_pos = 0;
+        t.bad = false;
+        if (first) {
+          first = false;
+          while (t.next()) hull_add(v, hull, t.cur, t.start_pos, t.end_pos);
+        } else if (t.next())
+          hull_add(v, hull, t.cur, t.start_pos, t.end_pos);
+        if (t.bad) gq_atomic_or(c.error_flags, 2u);
+        if (hull.overflow) return REC_ARENA;
+        if (occ == st.hi) break;
+      }
+    }
+  }
+  // sort loci by (site, allele) — std::set<VariantLocus> order
+  for (uint32_t i = 1; i < ll.n_loci; ++i) {
+    uint32_t s0 = ll.loci[2 * i], a0 = ll.loci[2 * i + 1], j = i;
+    while (j > 0 && (ll.loci[2 * (j - 1)] > s0 ||
+                     (ll.loci[2 * (j - 1)] == s0 && (int32_t)ll.loci[2 * (j - 1) + 1] > (int32_t)a0))) {
+      ll.loci[2 * j] = ll.loci[2 * (j - 1)];
+      ll.loci[2 * j + 1] = ll.loci[2 * (j - 1) + 1];
+      --j;
+    }
+    ll.loci[2 * j] = s0;
+    ll.loci[2 * j + 1] = a0;
+  }
+  // multi-allele groups first find (or create) their table slots — kept in `used`, no longer needed by the locus
+  // finder; a full table gives the strand back before any counter is touched (grouped_allele_counts.cpp:17-49)
+  {
+    uint32_t ng = 0;
+    for (uint32_t i = 0; i < ll.n_loci;) {
+      uint32_t e = i;
+      while (e < ll.n_loci && ll.loci[2 * e] == ll.loci[2 * i]) ++e;
+      if (e - i > 1) {
+        if (ng >= ll.cap) return REC_LISTS;
+        const uint32_t h = grouped_find_or_insert(c, (ll.loci[2 * i] - 5) >> 1, ll.loci + 2 * i + 1, e - i, 2);
+        if (h == kNoAllele) return REC_ARENA;
+        ll.used[ng++] = h;
+      }
+      i = e;
+    }
+  }
+  // ---- commit (nothing above touched the counters, so an overflow re-run cannot double count) ----
+  for (uint32_t i = 0, ng = 0; i < ll.n_loci;) {
+    uint32_t site = ll.loci[2 * i], slot = (site - 5) >> 1;
+    uint32_t e = i;
+    while (e < ll.n_loci && ll.loci[2 * e] == site) {
+      gq_red_add(c.allele_sum + GQ_AT(c.allele_off, slot) + ll.loci[2 * e + 1], 1u);  // allele_sum.cpp:31-43
+      ++e;
+    }
+    if (e - i == 1) gq_red_add(c.grouped_single + GQ_AT(c.allele_off, slot) + ll.loci[2 * i + 1], 1u);
+    else gq_red_add(c.gcount + ll.used[ng++], 1u);
+    i = e;
+  }
+  for (uint32_t i = 0; i < hull.cap; ++i) {
+    if (hull.e[3 * i] == kNoAllele) continue;
+    const Node& nd = GQ_AT(v.nodes, hull.e[3 * i]);
+    if (nd.cov_off == kNoAllele) continue;
+    for (uint32_t x = hull.e[3 * i + 1]; x <= hull.e[3 * i + 2]; ++x) gq_red_add(c.per_base + nd.cov_off + x, 1u);
+  }
+  return REC_OK;
 }
 
 GQ_DEV bool record_strand(const IndexView& v, const BatchView& b, const SearchOut& o, const CoverageView& c,
@@ -1644,161 +1834,54 @@ GQ_DEV bool record_strand(const IndexView& v, const BatchView& b, const SearchOu
       return true;
     }
   }
-  uint32_t* key_off = sc.alloc(2 * ns);  // (offset, len) per state; len = 0xFFFFFFFF for path-less
-  uint32_t* rep = sc.alloc(ns);          // class representative per state
-  if (!key_off || !rep) return false;
-  const uint32_t cap = (arena_words - sc.used) / 16;  // list capacities derive from the arena size
-  LocusLists ll;
-  ll.cap = cap;
-  ll.overflow = false;
-  ll.used = sc.alloc(cap);
-  ll.base = sc.alloc(cap);
-  ll.loci = sc.alloc(2 * cap);
-  if (sc.overflow) return false;
-  {
-    const uint32_t* p = recs;
-    for (uint32_t j = 0; j < ns; ++j) {
-      StateRec st = parse_rec(p);
-      p += st.words();
-      if (!(st.nt | st.ng)) {
-        key_off[2 * j] = 0;
-        key_off[2 * j + 1] = 0xFFFFFFFFu;
-        continue;
-      }
-      ll.n_loci = ll.n_base = 0;
-      locus_finder(v, st, ll);
-      if (ll.overflow) return false;
-      sort_u32(ll.base, ll.n_base);
-      uint32_t* k = sc.alloc(ll.n_base);
-      if (!k && ll.n_base) return false;
-      for (uint32_t i = 0; i < ll.n_base; ++i) k[i] = ll.base[i];
-      key_off[2 * j] = (uint32_t)(k - arena);
-      key_off[2 * j + 1] = ll.n_base;
-    }
-  }
-  // class representative of every state with a path = the first state with the same key (compared with the
-  // representatives found so far only), and the number of distinct classes
-  uint32_t ncls = 0;
-  for (uint32_t j = 0; j < ns; ++j) {
-    rep[j] = 0xFFFFFFFFu;
-    if (key_off[2 * j + 1] == 0xFFFFFFFFu) continue;
-    rep[j] = j;
-    for (uint32_t i = 0; i < j; ++i)
-      if (rep[i] == i && cmp_key(arena + key_off[2 * i], key_off[2 * i + 1], arena + key_off[2 * j], key_off[2 * j + 1]) == 0) {
-        rep[j] = i;
-        break;
-      }
-    if (rep[j] == j) ++ncls;
-  }
-  // random_select_entry :97-107
-  uint32_t total = nonvar + ncls;
-  uint32_t pick = total == 1 ? 1u : uniform_1_to(GQ_AT(b.seeds, strand >> 1), total);
-  if (pick <= nonvar) return true;
-  // the (pick - nonvar - 1)-th class in std::map order: the representative with that many smaller ones
-  uint32_t want = pick - nonvar - 1;
-  int chosen = -1;
-  for (uint32_t j = 0; j < ns && chosen < 0; ++j) {
-    if (rep[j] != j) continue;
-    uint32_t less = 0;
-    for (uint32_t i = 0; i < ns; ++i)
-      if (i != j && rep[i] == i &&
-          cmp_key(arena + key_off[2 * i], key_off[2 * i + 1], arena + key_off[2 * j], key_off[2 * j + 1]) < 0)
-        ++less;
-    if (less == want) chosen = (int)j;
-  }
-  if (chosen < 0) {
-    gq_atomic_or(c.error_flags, 2u);
-    return true;
-  }
-  // ---- pass 2: loci of the chosen class + per-node hulls (PbCovRecorder :221-296) ----
-  ll.n_loci = 0;
-  Hull hull;
-  hull.cap = (arena_words - sc.used) / 3;
-  hull.e = arena + sc.used;
-  hull.n = 0;
-  hull.overflow = false;
-  {
-    const uint32_t* p = recs;
-    for (uint32_t j = 0; j < ns; ++j) {
-      StateRec st = parse_rec(p);
-      p += st.words();
-      if (rep[j] != (uint32_t)chosen) continue;  // not a state of the chosen class (or path-less)
-      ll.n_base = 0;
-      locus_finder(v, st, ll);  // loci accumulate across the class (set union)
-      if (ll.overflow) return false;
-      bool first = true;
-      for (uint32_t occ = st.lo;; ++occ) {
-        uint32_t pos = GQ_LDG(v.sa + occ);
-        uint32_t nid = GQ_LDG(v.pos2node + pos);
+  // Nested PRG, one state, one occurrence (about half of the mapped strands of a nested PRG): still a single class
+  // that generate(1,1) selects, and one forward walk that visits every node once — no keys, no hulls. The loci are
+  // the path's sites and their parents (LocusFinder), at most one allele per site, so every group has one allele.
+  if (ns == 1 && v.any_nested) {
+    StateRec st = parse_rec(recs);
+    if (st.lo == st.hi) {
+      constexpr uint32_t kLoc = 40;
+      uint32_t used_l[kLoc], base_l[kLoc], loci_l[2 * kLoc];
+      LocusLists l1;
+      l1.loci = loci_l, l1.base = base_l, l1.used = used_l;
+      l1.n_loci = l1.n_base = l1.n_used = 0;
+      l1.cap = kLoc;
+      l1.overflow = false;
+      locus_finder(v, st, l1);
+      if (!l1.overflow) {
+        for (uint32_t i = 0; i < l1.n_loci; ++i) {
+          const uint32_t ai = GQ_AT(c.allele_off, (l1.loci[2 * i] - 5) >> 1) + l1.loci[2 * i + 1];
+          gq_red_add(c.allele_sum + ai, 1u);
+          gq_red_add(c.grouped_single + ai, 1u);
+        }
+        const uint32_t pos0 = GQ_LDG(v.sa + st.lo);
+        const uint32_t nid0 = GQ_LDG(v.pos2node + pos0);
         Trav t;
         t.v = &v;
-        t.cur = nid;
+        t.cur = nid0;
         t.remaining = L;
         t.T = st.T;
         t.ti = st.nt;
         t.first = true;
-        const Node& nd = GQ_AT(v.nodes, nid);
-        t.start_pos = nd.len > 1 ? pos - nd.start : 0;  // setup_random_access, coverage_graph.cpp:131-144
+        const Node& nd0 = GQ_AT(v.nodes, nid0);
+        t.start_pos = nd0.len > 1 ? pos0 - nd0.start : 0;
         t.end_pos = 0;
         t.bad = false;
-        if (first) {
-          first = false;
-          while (t.next()) hull_add(v, hull, t.cur, t.start_pos, t.end_pos);
-        } else if (t.next())
-          hull_add(v, hull, t.cur, t.start_pos, t.end_pos);
+        while (t.next()) {
+          const Node& nd = GQ_AT(v.nodes, t.cur);
+          if (nd.len == 0 || nd.cov_off == kNoAllele) continue;
+          for (uint32_t x = t.start_pos; x <= t.end_pos; ++x) gq_red_add(c.per_base + nd.cov_off + x, 1u);
+        }
         if (t.bad) gq_atomic_or(c.error_flags, 2u);
-        if (hull.overflow) return false;
-        if (occ == st.hi) break;
+        return true;
       }
     }
   }
-  // sort loci by (site, allele) — std::set<VariantLocus> order
-  for (uint32_t i = 1; i < ll.n_loci; ++i) {
-    uint32_t s0 = ll.loci[2 * i], a0 = ll.loci[2 * i + 1], j = i;
-    while (j > 0 && (ll.loci[2 * (j - 1)] > s0 ||
-                     (ll.loci[2 * (j - 1)] == s0 && (int32_t)ll.loci[2 * (j - 1) + 1] > (int32_t)a0))) {
-      ll.loci[2 * j] = ll.loci[2 * (j - 1)];
-      ll.loci[2 * j + 1] = ll.loci[2 * (j - 1) + 1];
-      --j;
-    }
-    ll.loci[2 * j] = s0;
-    ll.loci[2 * j + 1] = a0;
-  }
-  // multi-allele groups first find (or create) their table slots — kept in `used`, no longer needed by the locus
-  // finder; a full table gives the strand back before any counter is touched (grouped_allele_counts.cpp:17-49)
-  {
-    uint32_t ng = 0;
-    for (uint32_t i = 0; i < ll.n_loci;) {
-      uint32_t e = i;
-      while (e < ll.n_loci && ll.loci[2 * e] == ll.loci[2 * i]) ++e;
-      if (e - i > 1) {
-        if (ng >= ll.cap) return false;
-        const uint32_t h = grouped_find_or_insert(c, (ll.loci[2 * i] - 5) >> 1, ll.loci + 2 * i + 1, e - i, 2);
-        if (h == kNoAllele) return false;
-        ll.used[ng++] = h;
-      }
-      i = e;
-    }
-  }
-  // ---- commit (nothing above touched the counters, so an overflow re-run cannot double count) ----
-  for (uint32_t i = 0, ng = 0; i < ll.n_loci;) {
-    uint32_t site = ll.loci[2 * i], slot = (site - 5) >> 1;
-    uint32_t e = i;
-    while (e < ll.n_loci && ll.loci[2 * e] == site) {
-      gq_red_add(c.allele_sum + GQ_AT(c.allele_off, slot) + ll.loci[2 * e + 1], 1u);  // allele_sum.cpp:31-43
-      ++e;
-    }
-    if (e - i == 1) gq_red_add(c.grouped_single + GQ_AT(c.allele_off, slot) + ll.loci[2 * i + 1], 1u);
-    else gq_red_add(c.gcount + ll.used[ng++], 1u);
-    i = e;
-  }
-  for (uint32_t i = 0; i < hull.n; ++i) {
-    const Node& nd = GQ_AT(v.nodes, hull.e[3 * i]);
-    if (nd.cov_off == kNoAllele) continue;
-    for (uint32_t x = hull.e[3 * i + 1]; x <= hull.e[3 * i + 2]; ++x) gq_red_add(c.per_base + nd.cov_off + x, 1u);
-  }
-  return true;
+  // the general route: LocusFinder's sets first in thread-local memory, in the arena if a strand outgrows that
+  uint32_t local_lists[4 * kLocalLoci];
+  uint32_t r = record_general(v, b, c, strand, recs, ns, L, nonvar, arena, arena_words, local_lists);
+  if (r == REC_LISTS) r = record_general(v, b, c, strand, recs, ns, L, nonvar, arena, arena_words, nullptr);
+  return r == REC_OK;
 }
-
 
 }  // namespace gq

@@ -82,8 +82,8 @@ struct gq_index {
   uint32_t arena_words = 512;
   uint32_t n_threads = 148 * 1280;      // search kernel lanes (5 CTAs of 256 per SM)
   uint32_t cov_threads = 148 * 1024;    // coverage kernel threads
-  uint32_t big_arena_words = 1u << 16;
-  uint32_t big_threads = 2048;
+  uint32_t big_arena_words = 1u << 16;  // overflow re-runs: 4096 lanes x 256 KB, then x4 words and 4x fewer lanes
+  uint32_t big_threads = 4096;
   uint32_t pool_words_per_read = 48;
   bool super_in_smem = true;
   uint32_t rf_thresh = 8, ev_thresh = 8, leave_opt = 0, wait_opt = 0;

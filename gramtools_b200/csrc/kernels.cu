@@ -733,13 +733,15 @@ void launch_search(const IndexView& v, const BatchView& b, const SearchOut& o, u
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
     coverage_kernel(IndexView v, BatchView b, SearchOut o, CoverageView c, uint32_t* arena, uint32_t arena_words,
-                    const uint32_t* list, uint32_t n_list, uint32_t* overflow_list, uint32_t* n_overflow) {
+                    const uint32_t* list, uint32_t n_list, uint32_t* overflow_list, uint32_t* n_overflow,
+                    uint32_t* work_counter) {
   uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t nthreads = gridDim.x * blockDim.x;
   uint32_t* my_arena = arena + (size_t)tid * arena_words;
   const uint32_t* work_list = list ? list : o.mapped_list;
   const uint32_t n = list ? n_list : *o.n_mapped;
-  for (uint32_t i = tid; i < n; i += nthreads) {
+  // strands are handed out one by one: their cost ranges over orders of magnitude on nested PRGs (one state to
+  // dozens), and a static share would leave most threads waiting for the one that drew the heavy strands
+  for (uint32_t i = atomicAdd(work_counter, 1u); i < n; i = atomicAdd(work_counter, 1u)) {
     uint32_t strand = work_list[i];
     if (strand == kNoAllele || o.status[strand] != ST_MAPPED) continue;  // kNoAllele: slot of a lost claim
     if (!record_strand(v, b, o, c, strand, my_arena, arena_words)) overflow_list[atomicAdd(n_overflow, 1u)] = strand;
@@ -748,11 +750,14 @@ __global__ void __launch_bounds__(256)
 
 void launch_coverage(const IndexView& v, const BatchView& b, const SearchOut& o, const CoverageView& c,
                      uint32_t* arena, uint32_t arena_words, uint32_t n_threads, const uint32_t* list,
-                     uint32_t n_list, uint32_t* overflow_list, uint32_t* n_overflow, cudaStream_t st) {
+                     uint32_t n_list, uint32_t* overflow_list, uint32_t* n_overflow, uint32_t* work_counter,
+                     cudaStream_t st) {
   uint32_t work = list ? n_list : 2 * (b.read_end - b.read_begin);
   if (work == 0) return;
   uint32_t blocks = (min(work, n_threads) + 255) / 256;
-  coverage_kernel<<<blocks, 256, 0, st>>>(v, b, o, c, arena, arena_words, list, n_list, overflow_list, n_overflow);
+  cudaMemsetAsync(work_counter, 0, 4, st);
+  coverage_kernel<<<blocks, 256, 0, st>>>(v, b, o, c, arena, arena_words, list, n_list, overflow_list, n_overflow,
+                                          work_counter);
 }
 
 // ------------------------------------------------------------------------------------------------

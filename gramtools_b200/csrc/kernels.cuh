@@ -91,7 +91,8 @@ void launch_search(const IndexView& v, const BatchView& b, const SearchOut& o, u
 // list == nullptr: the strands in o.mapped_list[0, *o.n_mapped); otherwise the listed strands.
 void launch_coverage(const IndexView& v, const BatchView& b, const SearchOut& o, const CoverageView& c,
                      uint32_t* arena, uint32_t arena_words, uint32_t n_threads, const uint32_t* list,
-                     uint32_t n_list, uint32_t* overflow_list, uint32_t* n_overflow, cudaStream_t st);
+                     uint32_t n_list, uint32_t* overflow_list, uint32_t* n_overflow, uint32_t* work_counter,
+                     cudaStream_t st);
 
 // k-mer filter for the strands whose search found nothing (status ST_UNCLASSIFIED -> 1 or 2)
 void launch_classify(const IndexView& v, const BatchView& b, const SearchOut& o, const uint32_t* list, uint32_t n_list,
