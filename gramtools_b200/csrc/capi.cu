@@ -768,6 +768,29 @@ int gq_map_batch(gq_index* ix, const uint8_t* bases, const uint64_t* off, uint64
   GQ_CATCH
 }
 
+// pinned (page-locked) host memory for the buffers handed to gq_map_batch*: asynchronous H2D copies at full PCIe rate
+int gq_host_alloc(uint64_t bytes, void** out) {
+  GQ_TRY
+  if (!out) throw std::runtime_error("null argument");
+  *out = nullptr;
+  CUDA_OK(cudaHostAlloc(out, std::max<uint64_t>(bytes, 1), cudaHostAllocPortable));
+  GQ_CATCH
+}
+
+int gq_host_free(void* p) {
+  GQ_TRY
+  if (p) CUDA_OK(cudaFreeHost(p));
+  GQ_CATCH
+}
+
+int gq_device_count(int* n) {
+  GQ_TRY
+  if (!n) throw std::runtime_error("null argument");
+  *n = 0;
+  if (cudaGetDeviceCount(n) != cudaSuccess) *n = 0;
+  GQ_CATCH
+}
+
 int gq_packed_words(const uint64_t* off, uint64_t n_reads, uint64_t* n_words) {
   GQ_TRY
   if (!n_words || (n_reads && !off)) throw std::runtime_error("null argument");

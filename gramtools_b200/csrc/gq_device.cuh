@@ -1738,7 +1738,6 @@ GQ_DEV bool record_strand(const IndexView& v, const BatchView& b, const SearchOu
   const uint32_t* recs = o.pool + GQ_AT(o.st_off, strand);
   GQ_TOUCH(recs, 4 * GQ_AT(o.st_words, strand));
   const uint32_t L = GQ_AT(b.len, strand >> 1);
-  Scratch sc{arena, 0, arena_words, false};
 
   // ---- pass 1: non-variant mapping count, per-state class keys (MappingInstanceSelector) ----
   uint32_t nonvar = 0, npath = 0;
@@ -1772,7 +1771,9 @@ GQ_DEV bool record_strand(const IndexView& v, const BatchView& b, const SearchOu
       for (uint32_t e0 = 0; e0 < n_el; e0 += kChunk) {
         uint32_t site[kChunk], al[kChunk], r_a2[kChunk], r_cov[kChunk], r_first[kChunk], r_after[kChunk];
         uint32_t a_lo[kChunk], a_hi[kChunk];
+#if defined(__CUDA_ARCH__)
 #pragma unroll
+#endif
         for (uint32_t q = 0; q < kChunk; ++q) {
           const uint32_t e = e0 + q;
           if (e >= n_el) break;
@@ -1794,7 +1795,9 @@ GQ_DEV bool record_strand(const IndexView& v, const BatchView& b, const SearchOu
           r_first[q] = v.site_rec[4 * (size_t)slot + 2], r_after[q] = v.site_rec[4 * (size_t)slot + 3];
 #endif
         }
+#if defined(__CUDA_ARCH__)
 #pragma unroll
+#endif
         for (uint32_t q = 0; q < kChunk; ++q) {
           if (e0 + q >= n_el) break;
           if (al[q] == kNoAllele) {  // the allele the read starts in: the one whose span holds p
@@ -1805,7 +1808,9 @@ GQ_DEV bool record_strand(const IndexView& v, const BatchView& b, const SearchOu
           a_lo[q] = GQ_LDG(v.apos + r_a2[q] + al[q]);
           a_hi[q] = GQ_LDG(v.apos + r_a2[q] + al[q] + 1);
         }
+#if defined(__CUDA_ARCH__)
 #pragma unroll
+#endif
         for (uint32_t q = 0; q < kChunk; ++q) {
           const uint32_t e = e0 + q;
           if (e >= n_el) break;

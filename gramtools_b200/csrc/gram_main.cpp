@@ -18,8 +18,14 @@
 #include <sys/stat.h>
 #include <zlib.h>
 
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <cstdint>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <thread>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -40,13 +46,14 @@ struct Params {
   uint32_t kmer_size = 0, max_threads = 1;
   bool has_seed = false, debug = false;
   uint32_t seed = 0;
+  int devices = 1;  // --devices N (or GQ_DEVICES): GPUs of this node the reads are sharded over; 0 = all
 };
 
 [[noreturn]] void usage_fail(const std::string& msg) {
   std::cout << msg << std::endl;
   std::cout << "genotype options:\n  --gram_dir arg\n  --reads arg [arg…]\n  --sample_id arg\n"
                "  --ploidy arg {haploid, diploid}\n  --kmer_size arg\n  --genotype_dir arg\n"
-               "  --max_threads arg (=1)\n  --seed arg\n";
+               "  --max_threads arg (=1)\n  --seed arg\n  --devices arg (=1; B200 back-end: GPUs to shard the reads over, 0 = all)\n";
   std::exit(1);
 }
 
@@ -72,7 +79,8 @@ Params parse_genotype(int argc, const char* const* argv, int first) {
     else if (a == "--seed") {
       p.seed = (uint32_t)std::stoul(value("seed"));
       p.has_seed = true;
-    } else if (a == "--debug") p.debug = true;
+    } else if (a == "--devices") p.devices = std::stoi(value("devices"));
+    else if (a == "--debug") p.debug = true;
     else usage_fail("unrecognised option '" + a + "'");
   }
   if (p.gram_dir.empty()) usage_fail("the option '--gram_dir' is required but missing");
@@ -185,6 +193,83 @@ void check(int rc) {
 
 std::string join_path(const std::string& a, const std::string& b) { return a + (a.empty() || a.back() == '/' ? "" : "/") + b; }
 
+// ---- ingestion pipeline (replaces SeqRead + the 5000-read buffer, seqread.hpp:94-180 / quasimap.cpp:126-140) ----
+// reader thread: parses the read files, concatenates sequence text, draws the per-read seeds in file order;
+// one worker thread per GPU: packs a batch to 2 bits per base straight from the text (gq_pack_ascii, OpenMP) into
+// pinned buffers and maps it (gq_map_batch_packed). Batches are handed round-robin to whichever worker is free, so
+// parsing, packing, the H2D copy and the kernels of different batches overlap; results do not depend on which GPU
+// maps which batch (seeds travel with the reads, coverage is summed at the end).
+struct Batch {
+  std::string text;               // sequence characters of the batch's reads, concatenated
+  std::vector<uint64_t> offs{0};  // n + 1
+  std::vector<uint32_t> seeds;    // n
+  void clear() {
+    text.clear();
+    offs.assign(1, 0);
+    seeds.clear();
+  }
+};
+
+class BatchQueue {
+ public:
+  explicit BatchQueue(size_t depth) : depth_(depth) {}
+  void push(std::unique_ptr<Batch> b) {
+    std::unique_lock<std::mutex> lk(m_);
+    not_full_.wait(lk, [&] { return q_.size() < depth_; });
+    q_.push_back(std::move(b));
+    not_empty_.notify_one();
+  }
+  std::unique_ptr<Batch> pop() {  // nullptr: the reader is done and the queue is drained
+    std::unique_lock<std::mutex> lk(m_);
+    not_empty_.wait(lk, [&] { return !q_.empty() || closed_; });
+    if (q_.empty()) return nullptr;
+    auto b = std::move(q_.front());
+    q_.pop_front();
+    not_full_.notify_one();
+    return b;
+  }
+  void close() {
+    std::lock_guard<std::mutex> lk(m_);
+    closed_ = true;
+    not_empty_.notify_all();
+  }
+
+ private:
+  std::mutex m_;
+  std::condition_variable not_full_, not_empty_;
+  std::deque<std::unique_ptr<Batch>> q_;
+  size_t depth_;
+  bool closed_ = false;
+};
+
+// pinned packed buffers of one worker, grown on demand
+struct PinnedBatch {
+  uint32_t *packed = nullptr, *word_off = nullptr, *len = nullptr, *seeds = nullptr;
+  uint64_t cap_words = 0, cap_reads = 0;
+  void reserve(uint64_t words, uint64_t reads) {
+    if (words > cap_words) {
+      gq_host_free(packed);
+      check(gq_host_alloc(words * 4, (void**)&packed));
+      cap_words = words;
+    }
+    if (reads > cap_reads) {
+      gq_host_free(word_off);
+      gq_host_free(len);
+      gq_host_free(seeds);
+      check(gq_host_alloc((reads + 1) * 4, (void**)&word_off));
+      check(gq_host_alloc(reads * 4 + 4, (void**)&len));
+      check(gq_host_alloc(reads * 4 + 4, (void**)&seeds));
+      cap_reads = reads;
+    }
+  }
+  ~PinnedBatch() {
+    gq_host_free(packed);
+    gq_host_free(word_off);
+    gq_host_free(len);
+    gq_host_free(seeds);
+  }
+};
+
 }  // namespace
 
 int main(int argc, const char* const* argv) {
@@ -245,60 +330,76 @@ int main(int argc, const char* const* argv) {
 
   std::cout << "Loading PRG data" << std::endl;
   std::vector<uint32_t> prg = read_prg(join_path(p.gram_dir, "prg"));
-  gq_index* idx = nullptr;
-  check(gq_index_build(prg.data(), prg.size(), p.kmer_size, 0, &idx));
+  int n_dev = p.devices;
+  if (const char* e = std::getenv("GQ_DEVICES")) n_dev = std::atoi(e);
+  int have = 0;
+  check(gq_device_count(&have));
+  if (n_dev <= 0 || n_dev > have) n_dev = have > 0 ? (n_dev <= 0 ? have : std::min(n_dev, have)) : 1;
+  std::vector<gq_index*> handles(n_dev, nullptr);
+  check(gq_index_build(prg.data(), prg.size(), p.kmer_size, 0, &handles[0]));  // host index built once ...
+  for (int d = 1; d < n_dev; ++d) check(gq_index_clone(handles[0], d, &handles[d]));  // ... uploaded per GPU
+  if (n_dev > 1) check(gq_comm_init_all(handles.data(), n_dev));
+  gq_index* idx = handles[0];
   gq_layout lay;
   check(gq_index_describe(idx, &lay));
 
   std::cout << "Running quasimap" << std::endl;
   uint32_t master_seed = p.has_seed ? p.seed : std::random_device{}();
   std::cout << "Master random seed for read selection: " << master_seed << std::endl;
-  std::cout << "Maximum thread count: " << p.max_threads << " (ignored: reads are mapped on the GPU)" << std::endl;
+  std::cout << "Maximum thread count: " << p.max_threads << " (host threads packing reads; reads are mapped on " << n_dev
+            << " GPU" << (n_dev > 1 ? "s" : "") << ")" << std::endl;
   std::cout << "Processing reads:" << std::endl;
-  std::mt19937 master;
-  master.seed(master_seed);
   const uint64_t kRefBatch = 5000;       // quasimap.cpp:126-128: seeds are drawn 5000 at a time
-  const uint64_t kGpuBatch = 1u << 20;   // reads per gq_map_batch call
-  uint64_t total_reads = 0;
-  for (const auto& path : p.reads) {
-    ReadFile rf(path);
-    std::vector<uint8_t> bases;
-    std::vector<uint64_t> offs{0};
-    std::vector<uint32_t> seeds;
-    std::string seq, qual;
-    uint64_t in_ref_batch = 0;
-    auto flush = [&]() {
-      if (seeds.empty()) return;
-      check(gq_map_batch(idx, bases.data(), offs.data(), seeds.size(), seeds.data()));
-      total_reads += seeds.size();
-      std::cout << 2 * total_reads << std::endl;
-      bases.clear();
-      offs.assign(1, 0);
-      seeds.clear();
-    };
-    while (rf.next(seq, qual)) {
-      // read j of a 5000-read buffer gets the j-th of the 5000 draws made for that buffer
-      // (quasimap.cpp:132-139): unused draws of the last, partly filled buffer are discarded
-      if (in_ref_batch == kRefBatch) in_ref_batch = 0;
-      seeds.push_back((uint32_t)master());
-      ++in_ref_batch;
-      size_t start = bases.size();
-      bool ok = true;
-      for (char ch : seq) {
-        uint8_t e = encode_base(ch);
-        if (!e) {
-          ok = false;
-          break;
-        }
-        bases.push_back(e);
+  const uint64_t kGpuBatch = 1u << 20;   // reads per gq_map_batch_packed call
+  BatchQueue queue(2 * (size_t)n_dev);
+  std::atomic<uint64_t> total_reads{0};
+  std::mutex print_m;
+  const int pack_threads = std::max<int>(1, (int)p.max_threads / n_dev);
+  std::vector<std::thread> workers;
+  for (int d = 0; d < n_dev; ++d)
+    workers.emplace_back([&, d] {
+      PinnedBatch pin;
+      while (auto b = queue.pop()) {
+        const uint64_t n = b->seeds.size();
+        uint64_t words = 0;
+        check(gq_packed_words(b->offs.data(), n, &words));
+        pin.reserve(words, n);
+        check(gq_pack_ascii(b->text.data(), b->offs.data(), n, pin.packed, pin.word_off, pin.len, pack_threads));
+        std::memcpy(pin.seeds, b->seeds.data(), n * 4);
+        check(gq_map_batch_packed(handles[d], pin.packed, pin.word_off, pin.len, n, pin.seeds));
+        const uint64_t t = total_reads.fetch_add(n) + n;
+        std::lock_guard<std::mutex> lk(print_m);
+        std::cout << 2 * t << std::endl;
       }
-      if (!ok) bases.resize(start);  // non-ACGT: the encoder returns an empty read (utils.cpp:72-81)
-      offs.push_back(bases.size());
-      if (seeds.size() == kGpuBatch) flush();
+    });
+  {  // reader (this thread)
+    std::mt19937 master;
+    master.seed(master_seed);
+    for (const auto& path : p.reads) {
+      ReadFile rf(path);
+      auto cur = std::make_unique<Batch>();
+      std::string seq, qual;
+      uint64_t in_ref_batch = 0;
+      while (rf.next(seq, qual)) {
+        // read j of a 5000-read buffer gets the j-th of the 5000 draws made for that buffer
+        // (quasimap.cpp:132-139): unused draws of the last, partly filled buffer are discarded
+        if (in_ref_batch == kRefBatch) in_ref_batch = 0;
+        cur->seeds.push_back((uint32_t)master());
+        ++in_ref_batch;
+        cur->text += seq;  // non-ACGT characters empty the read in the packer (utils.cpp:72-92)
+        cur->offs.push_back(cur->text.size());
+        if (cur->seeds.size() == kGpuBatch) {
+          queue.push(std::move(cur));
+          cur = std::make_unique<Batch>();
+        }
+      }
+      if (!cur->seeds.empty()) queue.push(std::move(cur));
+      if (in_ref_batch) master.discard(kRefBatch - in_ref_batch);
     }
-    flush();
-    if (in_ref_batch) master.discard(kRefBatch - in_ref_batch);
+    queue.close();
   }
+  for (auto& w : workers) w.join();
+  if (n_dev > 1) check(gq_coverage_allreduce_all(handles.data(), n_dev));  // the one exchange: every handle holds the totals
 
   // ---- outputs -----------------------------------------------------------------------------
   std::vector<uint16_t> allele_sum(lay.n_alleles ? lay.n_alleles : 1), per_base(lay.n_per_base ? lay.n_per_base : 1);
@@ -390,6 +491,6 @@ int main(int argc, const char* const* argv) {
   std::cout << "====================" << std::endl
             << "Genotyping (LevelGenotyper) is not part of the B200 quasimap back-end; coverage files are complete."
             << std::endl;
-  gq_index_destroy(idx);
+  for (gq_index* h : handles) gq_index_destroy(h);
   return 0;
 }

@@ -489,7 +489,6 @@ __global__ void __launch_bounds__(kSearchThreads, GQ_SEARCH_MIN_BLOCKS)
 // [v1 gave a whole warp to each strand: 181 warp instructions per strand, mostly per-strand set-up; this form
 // needs ~25.]
 constexpr uint32_t kClassifySmemBytes = 160 * 1024;
-constexpr int kClassifyUnroll = 4;
 
 template <bool SMEM>
 __global__ void __launch_bounds__(SMEM ? 1024 : 256)

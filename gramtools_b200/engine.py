@@ -47,6 +47,9 @@ def load_library():
         "gq_packed_words": [u64p, C.c_uint64, u64p],
         "gq_pack_reads": [u8p, u64p, C.c_uint64, u32p, u32p, u32p, C.c_int],
         "gq_pack_ascii": [C.c_char_p, u64p, C.c_uint64, u32p, u32p, u32p, C.c_int],
+        "gq_host_alloc": [C.c_uint64, C.POINTER(vp)],
+        "gq_host_free": [vp],
+        "gq_device_count": [C.POINTER(C.c_int)],
         "gq_comm_unique_id": [u8p],
         "gq_comm_init": [vp, u8p, C.c_int, C.c_int],
         "gq_comm_init_all": [C.POINTER(vp), C.c_int],

@@ -76,6 +76,12 @@ int gq_pack_reads(const uint8_t* bases, const uint64_t* read_offsets, uint64_t n
 int gq_pack_ascii(const char* text, const uint64_t* read_offsets, uint64_t n_reads, uint32_t* packed,
                   uint32_t* word_off, uint32_t* len, int n_threads);
 
+/* Page-locked host memory for the buffers handed to gq_map_batch / gq_map_batch_packed (H2D copies of pageable
+ * memory are staged by the driver and do not overlap the kernels), and the number of CUDA devices. */
+int gq_host_alloc(uint64_t bytes, void** out);
+int gq_host_free(void* p);
+int gq_device_count(int* n);
+
 /* Split form of gq_map_batch for callers that keep a batch resident in HBM: upload once ... */
 int gq_batch_upload(gq_index* idx, const uint8_t* bases, const uint64_t* read_offsets, uint64_t n_reads,
                     const uint32_t* seeds);

@@ -27,10 +27,10 @@ def _fastq(path, reads, gz=False):
         open(path, "w").write(txt)
 
 
-def _run(gram_dir, geno_dir, reads, k, seed=42):
+def _run(gram_dir, geno_dir, reads, k, seed=42, extra=(), threads=1):
     cmd = [GRAM, "genotype", "--gram_dir", str(gram_dir), "--reads", *[str(r) for r in reads], "--sample_id", "s",
-           "--ploidy", "haploid", "--kmer_size", str(k), "--genotype_dir", str(geno_dir), "--max_threads", "1",
-           "--seed", str(seed)]
+           "--ploidy", "haploid", "--kmer_size", str(k), "--genotype_dir", str(geno_dir), "--max_threads", str(threads),
+           "--seed", str(seed), *extra]
     return subprocess.run(cmd, capture_output=True, text=True)
 
 
@@ -112,3 +112,33 @@ def test_cli_matches_oracle_two_files_gz_and_seed_batches(built_lib, tmp_path):
     assert f"Count all reads: {ref_r.stats[0]}" in out.stdout
     assert f"Count skipped reads with no sequence: {ref_r.stats[1]}" in out.stdout
     assert f"Count exact mapped reads: {ref_r.stats[4]}" in out.stdout
+
+
+@pytest.mark.gpu
+def test_cli_two_devices_matches_one(built_lib, tmp_path):
+    """`--devices 2`: reads packed by host threads and sharded over two GPUs batch by batch, one NCCL exchange at the
+    end — every output file identical to the single-GPU run (and so to the oracle, checked above)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    prg = synth.make_nested_prg(6, 300, 17)
+    rng = np.random.default_rng(17)
+    haps = [synth.random_haplotype(prg, rng) for _ in range(4)]
+    b, o = synth.sample_reads(haps, 30000, 50, 18)
+    reads = ["".join("?ACGT"[x] for x in b[int(o[i]):int(o[i + 1])]) for i in range(o.size - 1)]
+    gd = tmp_path / "gram"
+    gd.mkdir()
+    _write_prg(gd / "prg", prg)
+    _fastq(tmp_path / "r.fq", reads)
+    outs = []
+    for nd in (1, 2):
+        od = tmp_path / f"geno{nd}"
+        r = _run(gd, od, [tmp_path / "r.fq"], 5, seed=3, extra=["--devices", str(nd)], threads=4)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs.append({f: open(od / "coverage" / f).read() for f in
+                     ("allele_sum_coverage", "allele_base_coverage.json", "grouped_allele_counts_coverage.json")})
+        outs[-1]["counts"] = [ln for ln in r.stdout.splitlines() if ln.startswith("Count ")]
+    assert outs[0]["allele_sum_coverage"] == outs[1]["allele_sum_coverage"]
+    assert outs[0]["counts"] == outs[1]["counts"]
+    assert _grouped(tmp_path / "geno1" / "coverage" / "grouped_allele_counts_coverage.json") == \
+        _grouped(tmp_path / "geno2" / "coverage" / "grouped_allele_counts_coverage.json")
