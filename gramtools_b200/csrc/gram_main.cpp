@@ -350,7 +350,8 @@ int main(int argc, const char* const* argv) {
             << " GPU" << (n_dev > 1 ? "s" : "") << ")" << std::endl;
   std::cout << "Processing reads:" << std::endl;
   const uint64_t kRefBatch = 5000;       // quasimap.cpp:126-128: seeds are drawn 5000 at a time
-  const uint64_t kGpuBatch = 1u << 20;   // reads per gq_map_batch_packed call
+  uint64_t kGpuBatch = 1u << 20;         // reads per gq_map_batch_packed call (GQ_BATCH_READS overrides: tests)
+  if (const char* e = std::getenv("GQ_BATCH_READS")) kGpuBatch = std::max<uint64_t>(1, std::strtoull(e, nullptr, 10));
   BatchQueue queue(2 * (size_t)n_dev);
   std::atomic<uint64_t> total_reads{0};
   std::mutex print_m;

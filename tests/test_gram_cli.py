@@ -27,11 +27,11 @@ def _fastq(path, reads, gz=False):
         open(path, "w").write(txt)
 
 
-def _run(gram_dir, geno_dir, reads, k, seed=42, extra=(), threads=1):
+def _run(gram_dir, geno_dir, reads, k, seed=42, extra=(), threads=1, env=None):
     cmd = [GRAM, "genotype", "--gram_dir", str(gram_dir), "--reads", *[str(r) for r in reads], "--sample_id", "s",
            "--ploidy", "haploid", "--kmer_size", str(k), "--genotype_dir", str(geno_dir), "--max_threads", str(threads),
            "--seed", str(seed), *extra]
-    return subprocess.run(cmd, capture_output=True, text=True)
+    return subprocess.run(cmd, capture_output=True, text=True, env=dict(os.environ, **(env or {})))
 
 
 def _grouped(json_path):
@@ -133,7 +133,8 @@ def test_cli_two_devices_matches_one(built_lib, tmp_path):
     outs = []
     for nd in (1, 2):
         od = tmp_path / f"geno{nd}"
-        r = _run(gd, od, [tmp_path / "r.fq"], 5, seed=3, extra=["--devices", str(nd)], threads=4)
+        r = _run(gd, od, [tmp_path / "r.fq"], 5, seed=3, extra=["--devices", str(nd)], threads=4,
+                 env={"GQ_BATCH_READS": "4096"})  # several batches, so both GPUs get work
         assert r.returncode == 0, r.stdout + r.stderr
         outs.append({f: open(od / "coverage" / f).read() for f in
                      ("allele_sum_coverage", "allele_base_coverage.json", "grouped_allele_counts_coverage.json")})
