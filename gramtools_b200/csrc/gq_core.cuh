@@ -93,11 +93,18 @@ struct KmerState {   // one seed SearchState (reference: kmer_index_types.hpp:24
 //   key = text position SA[i];  aux = 1<<31 | n_ctx << 24 | ctx, base at p-1 in bits 23:22, p-2 in 21:20, ...
 // A wide state: key = lo, aux = hi (bit 31 clear: SA indices are below 2^31). seed_state[e] = index of the
 // entry's state in kmer_states (its path, needed only by candidates that finish).
+// The entries of a k-mer are bucketed by the first d bases of their left context (seed_bucket_bases(k): 2 for
+// k <= 11): seed_off has 4^d + 1 offsets per k-mer — bucket 0 = wide states and suffixes with fewer than d context
+// bases (a marker or the text start right there), bucket 1 + prefix = the rest — so a strand examines the bucket of
+// its own next d bases and bucket 0 instead of every occurrence of its k-mer (a (k+d)-mer seed where the PRG allows
+// it: 16x fewer entries at d = 2).
 struct KmerSeed {
   uint32_t key, aux;
 };
 constexpr uint32_t kSplitWidth = 256;  // states of up to this many suffixes are enumerated in the index
 constexpr uint32_t kSeedCtxBases = 12;
+GQ_HD uint32_t seed_bucket_bases(uint32_t k) { return k <= 11 ? 2u : (k == 12 ? 1u : 0u); }
+GQ_HD uint32_t seed_buckets(uint32_t k) { return (1u << (2 * seed_bucket_bases(k))) + 1u; }
 
 struct IndexView {
   uint32_t n;  // SA size = |prg| + 1
@@ -146,7 +153,7 @@ struct IndexView {
                                // test the stored read's windows as they are)
   const uint32_t* kmer_off;    // 4^k + 1
   const KmerState* kmer_states;
-  const uint32_t* seed_off;    // 4^k + 1
+  const uint32_t* seed_off;    // 4^k * seed_buckets(k) + 1
   const KmerSeed* seed_ent;
   const uint32_t* seed_state;
   const uint32_t* kmer_paths;

@@ -711,12 +711,24 @@ constexpr uint32_t kPreSteps = 8;     // rank steps at most, while the interval 
 constexpr uint32_t kNarrowWidth = 4;  // stop narrowing at this many suffixes
 constexpr uint32_t kMaxSplit = 32;    // wider than this after narrowing: general kernel
 
-// part 1: k-mer lookup. Returns the number of seed entries (0: the strand is already classified).
+// part 1: k-mer lookup. The strand's seed entries are two runs of the seed view: bucket 0 of its k-mer (wide states,
+// suffixes with a marker right to their left) and the bucket of the strand's own next d bases (KmerSeed); entry t
+// of the strand is s0 + t for t < n0, s1 + (t - n0) beyond. Returns n0 + n1 (0: the strand is already classified).
+struct SeedLookup {
+  bool classified;  // the strand's status is settled (skipped / too short / k-mer not indexed): nothing to seed
+  uint32_t s0, n0, s1, n1;
+  uint32_t pos0;  // bases left of the seeding k-mer (L - k)
+  uint32_t ctx;   // the next 12 of them, first one in bits 23:22 (valid where pos0 allows)
+  GQ_DEV inline uint32_t entry(uint32_t t) const { return t < n0 ? s0 + t : s1 + (t - n0); }
+};
+
 GQ_DEV inline uint32_t preseed_lookup(const IndexView& v, const BatchView& b, const SearchOut& o, uint32_t strand,
-                                      uint32_t& sb) {
+                                      SeedLookup& out) {
   const uint32_t r = strand >> 1;
   const uint32_t L = GQ_AT(b.len, r);
   const uint32_t k = v.k;
+  out.s0 = out.n0 = out.s1 = out.n1 = out.pos0 = out.ctx = 0;
+  out.classified = true;
   if (L == 0) {  // non-ACGT read, emptied by the encoder: skipped (quasimap.cpp:108-113)
     GQ_AT(o.status, strand) = ST_SKIPPED;
     return 0;
@@ -734,13 +746,31 @@ GQ_DEV inline uint32_t preseed_lookup(const IndexView& v, const BatchView& b, co
     const uint32_t wlo = GQ_LDG(w + wi), whi = (wi + 1 < n_words) ? GQ_LDG(w + wi + 1) : 0u;
     code = gq_funnelshift_r(wlo, whi, 2 * (j0 & 15u)) & ((k == 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u));
   }
-  sb = GQ_LDG(v.seed_off + code);  // seed-pass view of the k-mer index: entries per suffix / wide state
-  const uint32_t se = GQ_LDG(v.seed_off + code + 1);
-  if (sb == se) {  // the seeding k-mer itself is not indexed: the k-mer filter fails
+  out.pos0 = L - k;
+  if (out.pos0) {
+    ReadCursor rd{w, L, strand & 1u, 0, 0, 0};
+    rd.seek(out.pos0);
+    out.ctx = rd.top32() >> 8;
+  }
+  const uint32_t d = seed_bucket_bases(k), B = seed_buckets(k);
+  const uint32_t* off = v.seed_off + (size_t)code * B;
+  const uint32_t run_b = GQ_LDG(off), run_e = GQ_LDG(off + B);
+  if (run_b == run_e) {  // the seeding k-mer itself is not indexed: the k-mer filter fails
     GQ_AT(o.status, strand) = ST_MISSING_KMER;
     return 0;
   }
-  return se - sb;
+  out.classified = false;  // seeded: possibly with no entry at all in the strand's buckets (then nothing maps)
+  if (out.pos0 < d) {  // fewer bases left than the buckets are keyed on: every entry of the k-mer
+    out.s0 = run_b;
+    out.n0 = run_e - run_b;
+    return out.n0;
+  }
+  const uint32_t q = 1u + (d ? out.ctx >> (24 - 2 * d) : 0u);
+  out.s0 = run_b;
+  out.n0 = GQ_LDG(off + 1) - run_b;
+  out.s1 = GQ_LDG(off + q);
+  out.n1 = GQ_LDG(off + q + 1) - out.s1;
+  return out.n0 + out.n1;
 }
 
 // the strand goes to the general search kernel (once: whoever sets the flag appends it)
@@ -1183,9 +1213,9 @@ GQ_DEV inline void map_strand(const IndexView& v, const uint32_t* super_cnt, con
   bool general = GQ_AT(o.status, strand) == ST_OVERFLOW;  // overflow re-runs always use the general machinery
   if (!general) {
     GQ_PHASE(0);  // seed_kernel
-    uint32_t sb = 0;
-    const uint32_t ns = preseed_lookup(v, b, o, strand, sb);
-    if (ns == 0) return;
+    SeedLookup lk;
+    const uint32_t ns = preseed_lookup(v, b, o, strand, lk);
+    if (lk.classified) return;  // skipped / too short / k-mer not indexed
     GQ_AT(o.status, strand) = ST_UNCLASSIFIED;
     GQ_AT(pre.surv_cnt, strand) = 0;
     // the emulation reuses the candidate pool strand by strand
@@ -1193,10 +1223,10 @@ GQ_DEV inline void map_strand(const IndexView& v, const uint32_t* super_cnt, con
     const uint32_t r = strand >> 1;
     for (uint32_t t = 0; t < ns && !general; ++t) {
       SeedCands cands;
-      const uint32_t cnt = seed_state_cands(v, super_cnt, b.packed + GQ_AT(b.word_off, r), GQ_AT(b.len, r), strand & 1u, sb + t, cands);
+      const uint32_t cnt = seed_state_cands(v, super_cnt, b.packed + GQ_AT(b.word_off, r), GQ_AT(b.len, r), strand & 1u, lk.entry(t), cands);
       if (cnt == kNoAllele || total + cnt > pre.cap) general = true;
       else {
-        seed_write(cands, cnt, pre, strand, GQ_AT(v.seed_state, sb + t), total);
+        seed_write(cands, cnt, pre, strand, GQ_AT(v.seed_state, lk.entry(t)), total);
         total += cnt;
       }
     }

@@ -642,40 +642,56 @@ void build_kmers(HostIndex& ix) {
     ix.kmer_bits_rc[r >> 5] |= 1u << (r & 31);
   }
   // seed-pass view: per k-mer one entry per suffix of its narrow states (text position + left context), one
-  // entry per wide state
-  ix.seed_off.assign(nk + 1, 0);
-  for (uint64_t c = 0; c < nk; ++c) {
-    uint32_t cnt = 0;
-    for (uint32_t j = ix.kmer_off[c]; j < ix.kmer_off[c + 1]; ++j) {
-      const uint32_t wdt = ix.kmer_states[j].hi - ix.kmer_states[j].lo + 1;
-      cnt += wdt <= kSplitWidth ? wdt : 1;
+  // entry per wide state; bucketed by the first d context bases (gq_core.cuh, KmerSeed)
+  const uint32_t d = seed_bucket_bases(k), B = seed_buckets(k);
+  auto entry_of = [&](uint32_t i, uint32_t& bucket) {  // suffix entry of SA index i
+    const uint32_t p = ix.sa[i];
+    uint32_t ctx = 0, nctx = 0;
+    while (nctx < kSeedCtxBases && nctx < p) {
+      const uint32_t sym = ix.prg[p - 1 - nctx];
+      if (sym > 4) break;
+      ctx |= (sym - 1) << (22 - 2 * nctx);
+      ++nctx;
     }
-    ix.seed_off[c + 1] = ix.seed_off[c] + cnt;
-  }
-  ix.seed_ent.assign(std::max<size_t>(ix.seed_off[nk], 1), KmerSeed{0, 0});
-  ix.seed_state.assign(std::max<size_t>(ix.seed_off[nk], 1), 0);
+    bucket = nctx >= d ? 1u + (d ? ctx >> (24 - 2 * d) : 0u) : 0u;
+    return KmerSeed{p, 0x80000000u | (nctx << 24) | ctx};
+  };
+  ix.seed_off.assign(nk * B + 1, 0);
   const int64_t n_codes = (int64_t)nk;
 #pragma omp parallel for schedule(dynamic, 4096)
-  for (int64_t c = 0; c < n_codes; ++c) {
-    uint32_t e = ix.seed_off[c];
+  for (int64_t c = 0; c < n_codes; ++c) {  // bucket sizes (stored one slot ahead, prefix-summed below)
     for (uint32_t j = ix.kmer_off[c]; j < ix.kmer_off[c + 1]; ++j) {
       const KmerState& ks = ix.kmer_states[j];
       if (ks.hi - ks.lo + 1 > kSplitWidth) {
-        ix.seed_ent[e] = KmerSeed{ks.lo, ks.hi};
-        ix.seed_state[e++] = j;
+        ix.seed_off[c * B + 1]++;
         continue;
       }
       for (uint32_t i = ks.lo; i <= ks.hi; ++i) {
-        const uint32_t p = ix.sa[i];
-        uint32_t ctx = 0, nctx = 0;
-        while (nctx < kSeedCtxBases && nctx < p) {
-          const uint32_t sym = ix.prg[p - 1 - nctx];
-          if (sym > 4) break;
-          ctx |= (sym - 1) << (22 - 2 * nctx);
-          ++nctx;
-        }
-        ix.seed_ent[e] = KmerSeed{p, 0x80000000u | (nctx << 24) | ctx};
-        ix.seed_state[e++] = j;
+        uint32_t q;
+        entry_of(i, q);
+        ix.seed_off[c * B + q + 1]++;
+      }
+    }
+  }
+  for (uint64_t t = 0; t < nk * B; ++t) ix.seed_off[t + 1] += ix.seed_off[t];
+  ix.seed_ent.assign(std::max<size_t>(ix.seed_off[nk * B], 1), KmerSeed{0, 0});
+  ix.seed_state.assign(std::max<size_t>(ix.seed_off[nk * B], 1), 0);
+#pragma omp parallel for schedule(dynamic, 4096)
+  for (int64_t c = 0; c < n_codes; ++c) {
+    uint32_t cur[17];
+    for (uint32_t q = 0; q < B; ++q) cur[q] = ix.seed_off[c * B + q];
+    for (uint32_t j = ix.kmer_off[c]; j < ix.kmer_off[c + 1]; ++j) {
+      const KmerState& ks = ix.kmer_states[j];
+      if (ks.hi - ks.lo + 1 > kSplitWidth) {
+        ix.seed_ent[cur[0]] = KmerSeed{ks.lo, ks.hi};
+        ix.seed_state[cur[0]++] = j;
+        continue;
+      }
+      for (uint32_t i = ks.lo; i <= ks.hi; ++i) {
+        uint32_t q;
+        const KmerSeed sd = entry_of(i, q);
+        ix.seed_ent[cur[q]] = sd;
+        ix.seed_state[cur[q]++] = j;
       }
     }
   }

@@ -179,15 +179,34 @@ __global__ void __launch_bounds__(256)
   for (uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; i0 < n; i0 += gridDim.x * blockDim.x) {
     const uint32_t i = i0 + lane;
     const uint32_t strand = 2 * b.read_begin + i;
-    uint32_t sb = 0;
-    const uint32_t ns = i < n ? preseed_lookup(v, b, o, strand, sb) : 0;
+    SeedLookup lk;
+    lk.classified = true;
+    lk.s0 = lk.n0 = lk.s1 = lk.n1 = lk.pos0 = lk.ctx = 0;
+    const uint32_t ns = i < n ? preseed_lookup(v, b, o, strand, lk) : 0;
     uint32_t my_L = 0, my_woff = 0;
-    if (ns) {
+    if (!lk.classified) {
       o.status[strand] = ST_UNCLASSIFIED;  // until a candidate finishes or the general kernel decides
       pre.surv_cnt[strand] = 0;
       my_L = b.len[strand >> 1];
       my_woff = b.word_off[strand >> 1];
     }
+    // (the lookup also left the strand's next 12 bases left of the seeding k-mer in lk.ctx: every suffix entry of
+    // the k-mer is decided by one XOR against its stored left context)
+    const uint32_t my_pos0 = lk.pos0, my_ctx = lk.ctx;
+    // one seed entry: a suffix entry is accepted or rejected from its 8 bytes and the owner strand's context; only
+    // a wide state (more than kSplitWidth suffixes) takes the narrowing path
+    auto examine = [&](uint32_t e, uint32_t o_pos0, uint32_t o_ctx, uint32_t o_woff, uint32_t o_L, uint32_t o_rc,
+                       SeedCands& cands) -> uint32_t {
+      if (o_pos0 == 0) return kNoAllele;  // L == k: the seed states are the final states (general kernel)
+      const uint2 raw = __ldg(reinterpret_cast<const uint2*>(v.seed_ent) + e);
+      if (!(raw.y & 0x80000000u)) return seed_state_cands(v, super_c, b.packed + o_woff, o_L, o_rc, e, cands);
+      uint32_t m = (raw.y >> 24) & 0x7Fu;
+      m = m < o_pos0 ? m : o_pos0;
+      if (m && (((o_ctx ^ raw.y) & ((0xFFFFFFFFu << (24 - 2 * m)) & 0xFFFFFFu)) != 0)) return 0;
+      cands.p[0] = raw.x;
+      cands.w0[0] = o_pos0 | (K_SCAN << 28);
+      return 1;
+    };
     uint32_t incl = ns;  // inclusive warp scan of the entry counts
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -210,13 +229,16 @@ __global__ void __launch_bounds__(256)
         }
         const uint32_t owner = hi_l;
         const uint32_t o_incl = __shfl_sync(full, incl, owner), o_ns = __shfl_sync(full, ns, owner),
-                       o_sb = __shfl_sync(full, sb, owner), o_L = __shfl_sync(full, my_L, owner),
-                       o_woff = __shfl_sync(full, my_woff, owner);
+                       o_s0 = __shfl_sync(full, lk.s0, owner), o_n0 = __shfl_sync(full, lk.n0, owner),
+                       o_s1 = __shfl_sync(full, lk.s1, owner), o_L = __shfl_sync(full, my_L, owner),
+                       o_woff = __shfl_sync(full, my_woff, owner), o_pos0 = __shfl_sync(full, my_pos0, owner),
+                       o_ctx = __shfl_sync(full, my_ctx, owner);
         const uint32_t o_strand = 2 * b.read_begin + i0 + owner;
-        const uint32_t e = o_sb + (t - (o_incl - o_ns));
+        const uint32_t te = t - (o_incl - o_ns);  // entry te of the owner strand: bucket 0 first, then its own bucket
+        const uint32_t e = te < o_n0 ? o_s0 + te : o_s1 + (te - o_n0);
         SeedCands cands;
         uint32_t cnt = 0;
-        if (t < total) cnt = seed_state_cands(v, super_c, b.packed + o_woff, o_L, o_strand & 1u, e, cands);
+        if (t < total) cnt = examine(e, o_pos0, o_ctx, o_woff, o_L, o_strand & 1u, cands);
         const bool bad = cnt == kNoAllele;
         general |= __reduce_or_sync(full, bad ? (1u << owner) : 0u);
         seed_push(stage, pre, v, cands, bad ? 0u : cnt, o_strand, e, lane);
@@ -225,14 +247,17 @@ __global__ void __launch_bounds__(256)
       for (uint32_t owner = 0; owner < 32; ++owner) {
         const uint32_t o_ns = __shfl_sync(full, ns, owner);
         if (o_ns == 0) continue;
-        const uint32_t o_sb = __shfl_sync(full, sb, owner), o_L = __shfl_sync(full, my_L, owner),
-                       o_woff = __shfl_sync(full, my_woff, owner);
+        const uint32_t o_s0 = __shfl_sync(full, lk.s0, owner), o_n0 = __shfl_sync(full, lk.n0, owner),
+                       o_s1 = __shfl_sync(full, lk.s1, owner), o_L = __shfl_sync(full, my_L, owner),
+                       o_woff = __shfl_sync(full, my_woff, owner), o_pos0 = __shfl_sync(full, my_pos0, owner),
+                       o_ctx = __shfl_sync(full, my_ctx, owner);
         const uint32_t o_strand = 2 * b.read_begin + i0 + owner;
         for (uint32_t c0 = 0; c0 < o_ns; c0 += 32) {
-          const uint32_t e = o_sb + c0 + lane;
+          const uint32_t te = c0 + lane;
+          const uint32_t e = te < o_n0 ? o_s0 + te : o_s1 + (te - o_n0);
           SeedCands cands;
           uint32_t cnt = 0;
-          if (c0 + lane < o_ns) cnt = seed_state_cands(v, super_c, b.packed + o_woff, o_L, o_strand & 1u, e, cands);
+          if (c0 + lane < o_ns) cnt = examine(e, o_pos0, o_ctx, o_woff, o_L, o_strand & 1u, cands);
           const bool bad = cnt == kNoAllele;
           if (__any_sync(full, bad)) general |= 1u << owner;
           seed_push(stage, pre, v, cands, bad ? 0u : cnt, o_strand, e, lane);

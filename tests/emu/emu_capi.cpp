@@ -14,6 +14,7 @@
 #include "../../gramtools_b200/csrc/gq_device.cuh"
 #include "../../gramtools_b200/csrc/index_build.hpp"
 
+#include <set>
 #include <unordered_set>
 
 using namespace gq;
@@ -379,27 +380,33 @@ int emu_index_check(void* ev) {
     if (mr != tm) fail("marker count");
     // seed view of the k-mer index
     const uint64_t nk = 1ull << (2 * h.k);
-    if (h.seed_off.size() != nk + 1) fail("seed_off size");
+    const uint32_t sd_d = seed_bucket_bases(h.k), sd_B = seed_buckets(h.k);
+    if (h.seed_off.size() != nk * sd_B + 1) fail("seed_off size");
     for (uint64_t c = 0; c < nk; ++c) {
-      uint32_t ent = h.seed_off[c];
+      // expected entries of the k-mer (state order), then the stored ones bucket by bucket: same multiset, every
+      // entry in the bucket of its first d context bases (bucket 0: wide states / shorter contexts)
+      std::multiset<std::vector<uint32_t>> expect, got;
       for (uint32_t j = h.kmer_off[c]; j < h.kmer_off[c + 1]; ++j) {
         const KmerState& ks = h.kmer_states[j];
         if (ks.hi - ks.lo + 1 > kSplitWidth) {
-          if (h.seed_ent[ent].key != ks.lo || h.seed_ent[ent].aux != ks.hi || h.seed_state[ent] != j) fail("wide seed entry");
-          ++ent;
+          expect.insert({ks.lo, ks.hi, j, 0});
           continue;
         }
-        for (uint32_t i = ks.lo; i <= ks.hi; ++i, ++ent) {
-          const KmerSeed& sd = h.seed_ent[ent];
-          if (!(sd.aux >> 31) || sd.key != h.sa[i] || h.seed_state[ent] != j) fail("suffix seed entry");
-          const uint32_t nctx = (sd.aux >> 24) & 0x7Fu, p = sd.key;
-          if (nctx > kSeedCtxBases || nctx > p) fail("context length");
-          for (uint32_t d = 0; d < nctx; ++d)
-            if (h.prg[p - 1 - d] > 4 || ((sd.aux >> (22 - 2 * d)) & 3u) != h.prg[p - 1 - d] - 1) fail("context base");
-          if (nctx < kSeedCtxBases && nctx < p && h.prg[p - 1 - nctx] <= 4) fail("context ends early");
+        for (uint32_t i = ks.lo; i <= ks.hi; ++i) {
+          const uint32_t p = h.sa[i];
+          uint32_t nctx = 0, ctx = 0;
+          while (nctx < kSeedCtxBases && nctx < p && h.prg[p - 1 - nctx] <= 4) {
+            ctx |= (h.prg[p - 1 - nctx] - 1) << (22 - 2 * nctx);
+            ++nctx;
+          }
+          const uint32_t bucket = nctx >= sd_d ? 1u + (sd_d ? ctx >> (24 - 2 * sd_d) : 0u) : 0u;
+          expect.insert({p, 0x80000000u | (nctx << 24) | ctx, j, bucket});
         }
       }
-      if (ent != h.seed_off[c + 1]) fail("seed_off run length");
+      for (uint32_t q = 0; q < sd_B; ++q)
+        for (uint32_t ent = h.seed_off[c * sd_B + q]; ent < h.seed_off[c * sd_B + q + 1]; ++ent)
+          got.insert({h.seed_ent[ent].key, h.seed_ent[ent].aux, h.seed_state[ent], q});
+      if (expect != got) fail("seed view entries of a k-mer");
       // presence sets
       const bool present = h.kmer_off[c + 1] > h.kmer_off[c];
       if ((((h.kmer_bits[c >> 5] >> (c & 31)) & 1u) != 0) != present) fail("kmer_bits");
