@@ -34,8 +34,9 @@ CONFIGS = {
             text="config2: 4.4 Mb random reference + 100k biallelic SNPs (PRG 4.8M symbols), 1M x 150 bp error-free "
                  "reads per GPU, kmer_size=10, both strands, --seed 42"),
     3: dict(kind="nested", n_loci=200, locus_len=5_000, n_reads=5_000_000, read_len=150, k=10, scaling="weak",
-            text="config3: nested-variant PRG (200 loci x 5 kb, bracket grammar: nesting depth <= 3, 2-4 alleles, empty "
-                 "alleles, adjacent sites; 889k symbols, 44k sites), 5M x 150 bp error-free reads per GPU, kmer_size=10"),
+            text="config3: nested-variant PRG (200 loci x 5 kb, bracket grammar: nesting depth <= 3, 2-4 pairwise distinct "
+                 "alleles per site as make_prg builds them, empty alleles, adjacent sites; 892k symbols, 44k sites), "
+                 "5M x 150 bp error-free reads per GPU, kmer_size=10"),
     4: dict(kind="indel", ref_len=250_000_000, n_sites=5_000_000, n_reads=50_000_000, read_len=150, k=11,
             scaling="strong",
             text="config4: 250 Mb random reference + 5M SNP/indel sites (80/10/10 %), 50M x 150 bp error-free reads "
@@ -59,7 +60,7 @@ def make_prg(config):
         prg, ref, pos, alt = synth.make_snp_prg(c["ref_len"], c["n_sites"], gs)
         return prg, synth.snp_haplotypes(ref, pos, alt, 8, gs + 1)
     if c["kind"] == "nested":
-        prg = synth.make_nested_prg(c["n_loci"], c["locus_len"], gs)
+        prg = synth.make_nested_prg(c["n_loci"], c["locus_len"], gs, distinct=True)
         rng = np.random.default_rng(3)
         return prg, [synth.random_haplotype(prg, rng) for _ in range(8)]
     prg, ref, sites = synth.make_indel_prg_np(c["ref_len"], c["n_sites"], gs)

@@ -174,8 +174,11 @@ def snp_haplotypes(ref, pos, alt, n_hap, seed):
     return haps
 
 
-def make_nested_prg(n_loci, locus_len, seed, max_depth=3, spacer=200):
-    """Bracket-grammar PRG with nesting, empty alleles (direct deletions) and adjacent sites."""
+def make_nested_prg(n_loci, locus_len, seed, max_depth=3, spacer=200, distinct=False):
+    """Bracket-grammar PRG with nesting, empty alleles (direct deletions) and adjacent sites.
+    distinct=True: the alleles of a site are pairwise different, as in a PRG built from an MSA (make_prg collapses
+    identical sequences); with the default, short alleles can coincide, and every such site doubles the search
+    states of the reads crossing it (kept for the tests: it is the worst case for the general machinery)."""
     rng = np.random.default_rng(seed)
     out = []
     next_id = [5]
@@ -189,6 +192,7 @@ def make_nested_prg(n_loci, locus_len, seed, max_depth=3, spacer=200):
         res = [sid]
         n_all = int(rng.integers(2, 5))
         empty_used = False
+        seen = []
         for a in range(n_all):
             if a:
                 res.append(sid + 1)
@@ -196,7 +200,11 @@ def make_nested_prg(n_loci, locus_len, seed, max_depth=3, spacer=200):
             if r < 0.12 and not empty_used and a > 0:
                 empty_used = True  # empty allele = direct deletion
                 continue
-            res += body(depth + 1, max(1, int(budget * rng.uniform(0.2, 0.6))))
+            al = body(depth + 1, max(1, int(budget * rng.uniform(0.2, 0.6))))
+            while distinct and al in seen:
+                al = body(depth + 1, max(2, int(budget * rng.uniform(0.2, 0.6))))
+            seen.append(al)
+            res += al
         res.append(sid + 1)
         return res
 

@@ -338,15 +338,21 @@ def test_state_pool_overflow_multislice(built_lib):
     assert got.extra["rerun_strands"] > 1000
 
 
-def test_config3_shape_prefix(built_lib):
+@pytest.mark.parametrize("distinct", [True, False])
+def test_config3_shape_prefix(built_lib, distinct):
     """BASELINE config 3 at its stated shape (nested PRG, 200 loci x 5 kb, k = 10, 150 bp reads): a 20k-read
-    prefix bit-identical to the oracle — states, all three coverage structures, counters."""
-    prg = synth.make_nested_prg(200, 5000, 0x6772616D + 3)
+    prefix bit-identical to the oracle — states, all three coverage structures, counters. distinct=True is the
+    bench's PRG (pairwise distinct alleles, as make_prg builds them); distinct=False lets short alleles coincide,
+    which multiplies the search states of the reads crossing such sites (up to hundreds per strand): the worst
+    case for the general kernel, the general coverage route and their overflow re-runs."""
+    prg = synth.make_nested_prg(200, 5000, 0x6772616D + 3, distinct=distinct)
     rng = np.random.default_rng(3)
     haps = [synth.random_haplotype(prg, rng) for _ in range(8)]
     bases, offs = synth.sample_reads(haps, 20000, 150, 13)
     got, ref = _check(prg, 10, bases, offs, what="config3-shape", threads=os.cpu_count())
     assert ref.stats[4] >= 20000 and ref.grouped.size > 0
+    if not distinct:
+        assert ref.state_count.max() >= 64
 
 
 def test_config4_shape_prefix(built_lib):

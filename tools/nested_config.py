@@ -15,7 +15,8 @@ from gramtools_b200 import QuasimapIndex, synth  # noqa: E402
 
 n_loci, locus_len, k, n_reads, n_check = [int(x) for x in (sys.argv[1:6] + ["200", "5000", "10", "1000000", "20000"][len(sys.argv) - 1:])]
 t = time.time()
-prg = synth.make_nested_prg(n_loci, locus_len, 0x6772616D + 3)
+distinct = os.environ.get("GQ_DISTINCT", "1") != "0"  # 1: the bench's config-3 PRG; 0: coinciding alleles (stress)
+prg = synth.make_nested_prg(n_loci, locus_len, 0x6772616D + 3, distinct=distinct)
 print(f"PRG: {prg.size} symbols ({time.time() - t:.1f} s)", flush=True)
 rng = np.random.default_rng(3)
 haps = [synth.random_haplotype(prg, rng) for _ in range(8)]
