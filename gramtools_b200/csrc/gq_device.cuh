@@ -1099,6 +1099,265 @@ GQ_DEV inline void fast_event(FastLane& f, const IndexView& v) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Branching walks (nested PRGs). A jump that is not pre-resolved — a marker with another marker on its far side, a
+// site whose alleles can be empty or end in a nested site, several alleles ending in the read's next base — makes
+// the reference push several SearchStates (search_state_vBWT_jumps, vBWT_jump.cpp:134-265). The text walker follows
+// them depth-first: the path so far stays where it is (the branches share it as a prefix), and every alternative
+// becomes a small FORK record — a text position to continue from, or a pending (marker, allele) jump — on a short
+// private stack. What comes out is the same set of (suffix, path) pairs the reference's states hold (DESIGN §3,
+// observation 2); as before, a strand is only finished here when exactly ONE branch of ONE candidate reaches the
+// end of the read — a second finisher (two suffixes of one reference state, or two states) hands the strand to the
+// general kernel, which keeps intervals together.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kFastForks = 10;
+constexpr uint32_t kForkJump = 0xFu;  // `kind` field of a fork that is a pending jump
+
+struct FastForks {
+  uint32_t n;
+  uint32_t w0[kFastForks];   // pos | kind << 28
+  uint32_t a[kFastForks];    // text position to continue from / marker of the pending jump
+  uint32_t b[kFastForks];    // allele of the pending jump
+  uint32_t cnt[kFastForks];  // nt | ng << 8 | ng0 << 16 at the fork
+  uint32_t G[kFastForks][kFastG];
+  bool active;               // the candidate still has a branch walking or waiting
+  bool have_fin;             // one branch has reached the end of the read: kept here while the others are tried
+  bool fin_p_valid;
+  uint32_t fin_lo, fin_p, fin_cnt;
+  uint32_t fin_T[2 * kFastT], fin_G[kFastG];
+};
+
+GQ_DEV inline void forks_init(FastForks& fk, bool active) {
+  fk.n = 0;
+  fk.active = active;
+  fk.have_fin = false;
+}
+
+GQ_DEV inline bool fork_push(FastLane& f, FastForks& fk, uint32_t w0, uint32_t a, uint32_t b) {
+  if (fk.n == kFastForks) {
+    f.result = FAST_BAIL;
+    return false;
+  }
+  const uint32_t i = fk.n++;
+  fk.w0[i] = w0;
+  fk.a[i] = a;
+  fk.b[i] = b;
+  fk.cnt[i] = f.nt | (f.ng << 8) | (f.ng0 << 16);
+  for (uint32_t j = 0; j < kFastG; ++j) fk.G[i][j] = f.G[j];
+  return true;
+}
+
+// Apply the jump (marker, allele) to the walking branch: search_state_vBWT_jumps' worklist for ONE locus, with
+// extend_targets_site_exit (:185-228) and extend_targets_site_entry (:230-265), on the local path.
+GQ_DEV inline void fast_jump(FastLane& f, FastForks& fk, const IndexView& v, uint32_t marker, uint32_t allele) {
+  Lane& ln = f.ln;
+  while (true) {
+    if (marker & 1u) {  // leave site `marker` through `allele`; then whatever sits directly left of the site
+      if (f.nt == kFastT) {
+        f.result = FAST_BAIL;
+        return;
+      }
+      if (f.ng > 0) --f.ng;  // the site being left is the innermost open one
+      else if (f.ng0 > 0) --f.ng0;
+      f.T[2 * f.nt] = marker;
+      f.T[2 * f.nt + 1] = allele;
+      ++f.nt;
+      const uint32_t slot = (marker - 5) >> 1;
+      const uint32_t nxt = GQ_LDG(v.tm_odd + slot);
+      if (nxt == 0) {  // plain exit: the suffix that starts with the site-entry marker
+        ln.p = GQ_LDG(v.site_rec + 4 * (size_t)slot + 2) - 1;
+        ln.kind = K_READY;
+        ln.state = LS_TEXT;
+        return;
+      }
+      if (nxt & 1u) {  // double exit: the parent's allele from par_map
+        allele = GQ_LDG(v.par + 2 * slot + 1);
+        marker = nxt;
+      } else {  // exit followed by an entry
+        marker = nxt;
+        allele = 0;
+      }
+      continue;
+    }
+    // enter site marker - 1 from its right end
+    const uint32_t site = marker - 1, slot = (site - 5) >> 1;
+    if (f.ng == kFastG) {
+      f.result = FAST_BAIL;
+      return;
+    }
+    f.G[f.ng++] = site;
+    // direct deletions and double entries hang off the entered state: pending jumps, no base consumed yet
+    const uint32_t tb = GQ_LDG(v.tm_even_off + slot), te = GQ_LDG(v.tm_even_off + slot + 1);
+    for (uint32_t j = tb; j < te; ++j) {
+      const uint32_t id = GQ_LDG(v.tm_even + 2 * j), del = GQ_LDG(v.tm_even + 2 * j + 1);
+      if (!fork_push(f, fk, ln.pos | (kForkJump << 28), id, (id & 1u) ? del : kNoAllele)) return;
+    }
+    // the alleles that end in the read's next base: one suffix each
+    const uint32_t c = ln.rd.peek();
+    const uint32_t nlo = GQ_LDG(v.entry_next + 8 * slot + 2 * c), nhi = GQ_LDG(v.entry_next + 8 * slot + 2 * c + 1);
+    if (nhi + 1 <= nlo) {  // none: this branch ends here (its forks live on)
+      ln.state = LS_EV_POP;
+      return;
+    }
+    if (ln.pos == 1 && nhi != nlo) {  // the read ends on that base: several suffixes of one state finish together
+      GQ_COUNT(6);
+      f.result = FAST_BAIL;
+      return;
+    }
+    for (uint32_t i = nlo + 1; i <= nhi; ++i)
+      if (!fork_push(f, fk, (ln.pos - 1) | (K_SCAN << 28), GQ_LDG(v.sa + i), 0)) return;
+    ln.rd.advance();
+    ln.kind = K_SCAN;
+    if (--ln.pos == 0) {
+      ln.lo = ln.hi = nlo;
+      f.p_valid = false;
+      ln.state = LS_EV_TOP;
+    } else {
+      ln.p = GQ_LDG(v.sa + nlo);
+      ln.state = LS_TEXT;
+    }
+    return;
+  }
+}
+
+// LS_EV_TSCAN of a branching walk: the pre-resolved shortcuts of fast_event (plain exit, whole-SNP crossing), the
+// jump machinery for everything else
+GQ_DEV inline void fast_event_dfs(FastLane& f, FastForks& fk, const IndexView& v) {
+  Lane& ln = f.ln;
+  const uint32_t* jr = v.tmarker_hit + 8 * (size_t)ln.mr;
+#if defined(__CUDA_ARCH__)
+  const uint4 ja = __ldg(reinterpret_cast<const uint4*>(jr)), jb = __ldg(reinterpret_cast<const uint4*>(jr) + 1);
+  const uint32_t marker = ja.x, allele = ja.y, jlo = ja.z, snp = jb.x, p_jump = jb.z, p_site = jb.w;
+#else
+  GQ_TOUCH(jr, 32);
+  const uint32_t marker = jr[0], allele = jr[1], jlo = jr[2], snp = jr[4], p_jump = jr[6], p_site = jr[7];
+#endif
+  if (marker == 0) {
+    f.result = FAST_DEAD;
+    return;
+  }
+  if (jlo != kNoAllele && (marker & 1u)) {  // exit with nothing adjacent
+    if (f.nt == kFastT) {
+      f.result = FAST_BAIL;
+      return;
+    }
+    if (f.ng > 0) --f.ng;
+    else if (f.ng0 > 0) --f.ng0;
+    f.T[2 * f.nt] = marker;
+    f.T[2 * f.nt + 1] = allele;
+    ++f.nt;
+    ln.p = p_jump;
+    ln.kind = K_READY;
+    ln.state = LS_TEXT;
+    return;
+  }
+  if (jlo != kNoAllele && snp != kNotSnp && ln.pos >= 2) {  // site of distinct single-base alleles: entry, base, exit
+    const uint32_t a = (snp >> (8 * ln.rd.peek())) & 0xFFu;
+    if (a == 0xFFu) {
+      f.result = FAST_DEAD;
+      return;
+    }
+    if (f.nt == kFastT) {
+      f.result = FAST_BAIL;
+      return;
+    }
+    f.T[2 * f.nt] = marker - 1;
+    f.T[2 * f.nt + 1] = a;
+    ++f.nt;
+    ln.p = p_site;
+    ln.pos -= 1;
+    ln.rd.advance();
+    ln.kind = K_READY;
+    ln.state = LS_TEXT;
+    return;
+  }
+  if (jlo == kNoAllele) GQ_COUNT(5);
+  fast_jump(f, fk, v, marker, allele);
+}
+
+// The walking branch has ended (dead, finished, or it needs the general kernel): remember a finisher, take the
+// next fork, or close the candidate. Afterwards either a branch is walking again, or fk.active is false and the lane
+// holds the candidate's outcome for fast_outcome (state LS_EV_TOP = its single finished branch).
+GQ_DEV inline void fast_branch_end(FastLane& f, FastForks& fk, const IndexView& v) {
+  Lane& ln = f.ln;
+  if (f.result == FAST_BAIL) {
+    fk.active = false;
+    return;
+  }
+  if (f.result == FAST_NONE && ln.state == LS_EV_TOP) {  // this branch consumed the whole read
+    if (fk.have_fin) {  // a second one: two suffixes / states finish — the general kernel redoes the strand
+      GQ_COUNT(4);
+      f.result = FAST_BAIL;
+      fk.active = false;
+      return;
+    }
+    fk.have_fin = true;
+    fk.fin_p_valid = f.p_valid;
+    fk.fin_lo = ln.lo;
+    fk.fin_p = ln.p;
+    fk.fin_cnt = f.nt | (f.ng << 8) | (f.ng0 << 16);
+    for (uint32_t j = 0; j < 2 * f.nt; ++j) fk.fin_T[j] = f.T[j];
+    for (uint32_t j = 0; j < kFastG; ++j) fk.fin_G[j] = f.G[j];
+  }
+  f.result = FAST_NONE;
+  while (true) {
+    if (fk.n == 0) {  // nothing left to try: the candidate's outcome
+      fk.active = false;
+      if (fk.have_fin) {
+        f.nt = fk.fin_cnt & 0xFFu;
+        f.ng = (fk.fin_cnt >> 8) & 0xFFu;
+        f.ng0 = fk.fin_cnt >> 16;
+        for (uint32_t j = 0; j < 2 * f.nt; ++j) f.T[j] = fk.fin_T[j];
+        for (uint32_t j = 0; j < kFastG; ++j) f.G[j] = fk.fin_G[j];
+        f.p_valid = fk.fin_p_valid;
+        ln.p = fk.fin_p;
+        ln.lo = ln.hi = fk.fin_lo;
+        ln.pos = 0;
+        ln.state = LS_EV_TOP;
+      } else
+        f.result = FAST_DEAD;
+      return;
+    }
+    const uint32_t i = --fk.n;
+    f.nt = fk.cnt[i] & 0xFFu;
+    f.ng = (fk.cnt[i] >> 8) & 0xFFu;
+    f.ng0 = fk.cnt[i] >> 16;
+    for (uint32_t j = 0; j < kFastG; ++j) f.G[j] = fk.G[i][j];
+    ln.pos = fk.w0[i] & 0x0FFFFFFFu;
+    ln.rd.seek(ln.pos);  // pos >= 1: forks are only made while bases are left
+    f.p_valid = true;
+    if ((fk.w0[i] >> 28) == kForkJump) {
+      fast_jump(f, fk, v, fk.a[i], fk.b[i]);
+      if (f.result == FAST_BAIL) {
+        fk.active = false;
+        return;
+      }
+      if (f.result == FAST_NONE && (ln.state == LS_TEXT || ln.state == LS_EV_TSCAN)) return;  // walking again
+      if (f.result == FAST_NONE && ln.state == LS_EV_TOP) {  // finished inside the jump (read ends on the entered base)
+        if (fk.have_fin) {
+          GQ_COUNT(4);
+          f.result = FAST_BAIL;
+          fk.active = false;
+          return;
+        }
+        fk.have_fin = true;
+        fk.fin_p_valid = f.p_valid;
+        fk.fin_lo = ln.lo;
+        fk.fin_p = ln.p;
+        fk.fin_cnt = f.nt | (f.ng << 8) | (f.ng0 << 16);
+        for (uint32_t j = 0; j < 2 * f.nt; ++j) fk.fin_T[j] = f.T[j];
+        for (uint32_t j = 0; j < kFastG; ++j) fk.fin_G[j] = f.G[j];
+      }
+      f.result = FAST_NONE;  // dead or recorded: next fork
+      continue;
+    }
+    ln.p = fk.a[i];
+    ln.kind = fk.w0[i] >> 28;
+    ln.state = LS_TEXT;
+    return;
+  }
+}
+
 // Verify pass: does the candidate agree with the PRG on kVerifyBases further bases (or to the end of the read,
 // or up to something only the full walk can decide)? False candidates — the other occurrences of the
 // seeding k-mer — end here, so the full walk only sees about one candidate per mappable strand.
@@ -1246,9 +1505,19 @@ GQ_DEV inline void map_strand(const IndexView& v, const uint32_t* super_cnt, con
           GQ_PHASE(2);                            // text_kernel
           fast_begin<true>(f, v, b, pre, i);
         }
-        while (fast_running(f)) {
-          if (f.ln.state == LS_TEXT) lane_text_step(f.ln, v);
-          if (f.ln.state == LS_EV_TSCAN) fast_event<true>(f, v);
+        if (v.any_nested) {  // text_kernel<true>: branching walks
+          FastForks fk;
+          forks_init(fk, true);
+          while (fk.active) {
+            if (fast_running(f) && f.ln.state == LS_TEXT) lane_text_step(f.ln, v);
+            if (fast_running(f) && f.ln.state == LS_EV_TSCAN) fast_event_dfs(f, fk, v);
+            if (!fast_running(f)) fast_branch_end(f, fk, v);
+          }
+        } else {  // text_kernel<false>
+          while (fast_running(f)) {
+            if (f.ln.state == LS_TEXT) lane_text_step(f.ln, v);
+            if (f.ln.state == LS_EV_TSCAN) fast_event<true>(f, v);
+          }
         }
         const uint32_t words = fast_outcome(f, v);
         if (f.result == FAST_MAPPED) {

@@ -2,6 +2,9 @@
 #include "index_build.hpp"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <stdexcept>
@@ -706,10 +709,21 @@ void build_host_index(const uint32_t* prg, uint64_t n_symbols, uint32_t kmer_siz
   ix.k = kmer_size;
   ix.prg.assign(prg, prg + n_symbols);
   std::vector<uint32_t> hit_marker, hit_allele;
+  const bool timing = std::getenv("GQ_BUILD_TIMING") != nullptr;  // developer aid: seconds per phase on stderr
+  auto t0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "index build: %-28s %.2f s\n", what, std::chrono::duration<double>(t1 - t0).count());
+    t0 = t1;
+  };
   build_graph(ix, hit_marker, hit_allele);
   build_site_tables(ix);
+  lap("coverage graph + site tables");
   build_fm(ix, hit_marker, hit_allele);
+  lap("SA + rank blocks + text mode");
   build_kmers(ix);
+  lap("k-mer index + seed view");
 }
 
 }  // namespace gq

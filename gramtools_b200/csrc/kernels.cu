@@ -327,6 +327,7 @@ __global__ void __launch_bounds__(256) verify_kernel(IndexView v, BatchView b, S
 // — text step for the lanes in text mode, then the jump for the lanes that reached a marker — so lanes meet
 // again every iteration; the round ends with a convergent emission phase (one pool allocation and one
 // mapped-list allocation per warp).
+template <bool DFS>
 __global__ void __launch_bounds__(256) text_kernel(IndexView v, BatchView b, SearchOut o, SeedOut pre) {
   const uint32_t n = min(*pre.n_surv, pre.cap);
   const uint32_t lane = threadIdx.x & 31u;
@@ -338,9 +339,19 @@ __global__ void __launch_bounds__(256) text_kernel(IndexView v, BatchView b, Sea
     f.ln.state = LS_IDLE;
     f.ln.strand = 0;
     if (i < n) fast_begin<true>(f, v, b, pre, i);
-    while (__any_sync(full, fast_running(f))) {
-      if (fast_running(f) && f.ln.state == LS_TEXT) lane_text_step(f.ln, v);
-      if (fast_running(f) && f.ln.state == LS_EV_TSCAN) fast_event<true>(f, v);
+    if (DFS) {  // nested PRGs: branching walks (fast_jump), forks on a private stack
+      FastForks fk;
+      forks_init(fk, i < n);
+      while (__any_sync(full, fk.active)) {
+        if (fk.active && fast_running(f) && f.ln.state == LS_TEXT) lane_text_step(f.ln, v);
+        if (fk.active && fast_running(f) && f.ln.state == LS_EV_TSCAN) fast_event_dfs(f, fk, v);
+        if (fk.active && !fast_running(f)) fast_branch_end(f, fk, v);  // next fork, or the candidate's outcome
+      }
+    } else {  // straight walks: a jump that is not pre-resolved hands the strand to the general kernel
+      while (__any_sync(full, fast_running(f))) {
+        if (fast_running(f) && f.ln.state == LS_TEXT) lane_text_step(f.ln, v);
+        if (fast_running(f) && f.ln.state == LS_EV_TSCAN) fast_event<true>(f, v);
+      }
     }
     uint32_t words = i < n ? fast_outcome(f, v) : 0;
     const uint32_t strand = f.ln.strand;
@@ -392,7 +403,8 @@ void launch_text(const IndexView& v, const BatchView& b, const SearchOut& o, con
   SeedOut ver = pre;  // the text kernel's candidates are the verified ones
   ver.rec = surv_rec;
   ver.n_surv = n_verified;
-  text_kernel<<<blocks, 256, 0, st>>>(v, b, o, ver);
+  if (v.any_nested) text_kernel<true><<<blocks, 256, 0, st>>>(v, b, o, ver);
+  else text_kernel<false><<<blocks, 256, 0, st>>>(v, b, o, ver);
 }
 
 #ifdef GQ_DEBUG_COUNTERS
@@ -755,16 +767,120 @@ void launch_search(const IndexView& v, const BatchView& b, const SearchOut& o, u
 // ------------------------------------------------------------------------------------------------
 // Coverage recording, one thread per mapped strand.
 // ------------------------------------------------------------------------------------------------
+// Nested PRG, strand with ONE final state of ONE occurrence, for the 32 strands of a warp side by side (the route
+// record_strand takes for such a strand, restated warp-convergently: lanes left to themselves in its data-dependent
+// loops never met again — 1.6 active lanes per instruction). Every loop below advances all lanes together, one
+// path element / one graph node / one base per iteration. Must be called by all 32 lanes; `strand` = kNoAllele for a
+// lane without work. Returns true for a lane whose strand needs the general route (nothing recorded for it).
+__device__ __forceinline__ bool record_single_nested_warp(const IndexView& v, const BatchView& b, const SearchOut& o,
+                                                          const CoverageView& c, uint32_t strand) {
+  const uint32_t full = 0xFFFFFFFFu;
+  bool valid = strand != kNoAllele;
+  bool general = false;
+  StateRec st{0, 0, 0, 0, nullptr, nullptr};
+  uint32_t L = 0;
+  if (valid) {
+    st = parse_rec(o.pool + o.st_off[strand]);
+    L = b.len[strand >> 1];
+    if (!(st.nt | st.ng)) valid = false;  // a path-less state records nothing (coverage_common.cpp:137-148)
+    else if (st.lo != st.hi) valid = false, general = true;
+  }
+  constexpr uint32_t kLoc = 40;
+  uint32_t used_l[kLoc], base_l[kLoc], loci_l[2 * kLoc];
+  LocusLists l1;
+  l1.loci = loci_l, l1.base = base_l, l1.used = used_l;
+  l1.n_loci = l1.n_base = l1.n_used = 0;
+  l1.cap = kLoc;
+  l1.overflow = false;
+  uint32_t pos0 = 0, nid0 = 0;
+  if (valid) {  // where the read starts; a read that starts inside a site: its allele from the node (LocusFinder :52-74)
+    pos0 = __ldg(v.sa + st.lo);
+    nid0 = __ldg(v.pos2node + pos0);
+    if (st.ng > 0) {
+      const uint32_t seed_site = st.G[2 * (st.ng - 1)], al = (uint32_t)v.nodes[nid0].allele;
+      add_locus(l1, seed_site, al);
+      assign_nested(v, l1, seed_site, al);
+    }
+  }
+  const uint32_t nt = valid ? st.nt : 0;
+  for (uint32_t j = 0; __any_sync(full, j < nt); ++j)
+    if (j < nt) assign_nested(v, l1, st.T[2 * j], st.T[2 * j + 1]);  // LocusFinder :76-83
+  if (valid && l1.overflow) valid = false, general = true;
+  const uint32_t n_loci = valid ? l1.n_loci : 0;
+  for (uint32_t i = 0; __any_sync(full, i < n_loci); ++i)
+    if (i < n_loci) {  // at most one allele per site: single-allele groups
+      const uint32_t ai = c.allele_off[(loci_l[2 * i] - 5) >> 1] + loci_l[2 * i + 1];
+      gq_red_add(c.allele_sum + ai, 1u);
+      gq_red_add(c.grouped_single + ai, 1u);
+    }
+  Trav t;
+  t.v = &v;
+  t.cur = nid0;
+  t.remaining = L;
+  t.T = st.T;
+  t.ti = st.nt;
+  t.first = true;
+  t.start_pos = 0;
+  t.end_pos = 0;
+  t.bad = false;
+  if (valid) {
+    const Node& nd0 = v.nodes[nid0];
+    t.start_pos = nd0.len > 1 ? pos0 - nd0.start : 0;
+  }
+  bool alive = valid;
+  while (__any_sync(full, alive)) {
+    uint32_t cnt = 0;
+    uint32_t* pb = nullptr;
+    if (alive) {
+      alive = t.next();
+      if (alive) {
+        const Node& nd = v.nodes[t.cur];
+        if (nd.len != 0 && nd.cov_off != kNoAllele) {
+          cnt = t.end_pos - t.start_pos + 1;
+          pb = c.per_base + nd.cov_off + t.start_pos;
+        }
+      }
+    }
+    for (uint32_t x = 0; __any_sync(full, x < cnt); ++x)
+      if (x < cnt) gq_red_add(pb + x, 1u);  // allele_base.cpp:221-296
+  }
+  if (valid && t.bad) atomicOr(c.error_flags, 2u);
+  return general;
+}
+
+// mode 0: every strand of the work list, handed out one by one (non-nested PRGs: nearly all strands take the table
+//         route; also the overflow re-runs).
+// mode 1: nested PRGs, first pass — the single-state strands (nine in ten), a warp's 32 strands side by side on the
+//         same route (LocusFinder + one forward walk each); strands with several states are only collected ...
+// mode 2: ... and recorded in a second pass over that list, one by one: their cost ranges over orders of magnitude
+//         (two states to hundreds), and lanes sharing a static batch would wait for the slowest.
 __global__ void __launch_bounds__(256)
     coverage_kernel(IndexView v, BatchView b, SearchOut o, CoverageView c, uint32_t* arena, uint32_t arena_words,
-                    const uint32_t* list, uint32_t n_list, uint32_t* overflow_list, uint32_t* n_overflow,
-                    uint32_t* work_counter) {
+                    const uint32_t* list, uint32_t n_list, const uint32_t* n_list_dev, uint32_t* overflow_list,
+                    uint32_t* n_overflow, uint32_t* work_counter, uint32_t mode, uint32_t* multi_list,
+                    uint32_t* n_multi) {
   uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t* my_arena = arena + (size_t)tid * arena_words;
   const uint32_t* work_list = list ? list : o.mapped_list;
-  const uint32_t n = list ? n_list : *o.n_mapped;
-  // strands are handed out one by one: their cost ranges over orders of magnitude on nested PRGs (one state to
-  // dozens), and a static share would leave most threads waiting for the one that drew the heavy strands
+  const uint32_t n = list ? (n_list_dev ? *n_list_dev : n_list) : *o.n_mapped;
+  if (mode == 1) {
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t i0 = tid & ~31u; i0 < n; i0 += gridDim.x * blockDim.x) {
+      const uint32_t i = i0 + lane;
+      uint32_t strand = i < n ? work_list[i] : kNoAllele;
+      if (strand != kNoAllele && o.status[strand] != ST_MAPPED) strand = kNoAllele;  // kNoAllele: slot of a lost claim
+      bool multi = strand != kNoAllele && o.st_count[strand] != 1;
+      if (record_single_nested_warp(v, b, o, c, multi ? kNoAllele : strand)) multi = true;
+      const uint32_t mm = __ballot_sync(0xFFFFFFFFu, multi);
+      if (mm) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(n_multi, (uint32_t)__popc(mm));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (multi) multi_list[base + __popc(mm & ((1u << lane) - 1u))] = strand;
+      }
+    }
+    return;
+  }
   for (uint32_t i = atomicAdd(work_counter, 1u); i < n; i = atomicAdd(work_counter, 1u)) {
     uint32_t strand = work_list[i];
     if (strand == kNoAllele || o.status[strand] != ST_MAPPED) continue;  // kNoAllele: slot of a lost claim
@@ -775,13 +891,20 @@ __global__ void __launch_bounds__(256)
 void launch_coverage(const IndexView& v, const BatchView& b, const SearchOut& o, const CoverageView& c,
                      uint32_t* arena, uint32_t arena_words, uint32_t n_threads, const uint32_t* list,
                      uint32_t n_list, uint32_t* overflow_list, uint32_t* n_overflow, uint32_t* work_counter,
-                     cudaStream_t st) {
+                     cudaStream_t st, uint32_t* multi_list, uint32_t* n_multi) {
   uint32_t work = list ? n_list : 2 * (b.read_end - b.read_begin);
   if (work == 0) return;
   uint32_t blocks = (min(work, n_threads) + 255) / 256;
   cudaMemsetAsync(work_counter, 0, 4, st);
-  coverage_kernel<<<blocks, 256, 0, st>>>(v, b, o, c, arena, arena_words, list, n_list, overflow_list, n_overflow,
-                                          work_counter);
+  if (v.any_nested && multi_list && !list) {  // nested PRG, main pass: single-state strands, then the others
+    coverage_kernel<<<blocks, 256, 0, st>>>(v, b, o, c, arena, arena_words, nullptr, 0, nullptr, overflow_list, n_overflow,
+                                            work_counter, 1u, multi_list, n_multi);
+    coverage_kernel<<<blocks, 256, 0, st>>>(v, b, o, c, arena, arena_words, multi_list, work, n_multi, overflow_list,
+                                            n_overflow, work_counter, 2u, nullptr, nullptr);
+    return;
+  }
+  coverage_kernel<<<blocks, 256, 0, st>>>(v, b, o, c, arena, arena_words, list, n_list, nullptr, overflow_list, n_overflow,
+                                          work_counter, 0u, nullptr, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------
