@@ -80,146 +80,103 @@ void allreduce(gq_index* const* hs, int n_local) {
   for (int i = 0; i < n_local; ++i)
     if (!hs[i] || !hs[i]->comm) throw std::runtime_error("gq_coverage_allreduce: no communicator on the handle (gq_comm_init)");
   const int n_ranks = hs[0]->comm_ranks;
-  // ---- 1. dense counters + stats: in-place sums ------------------------------------------------------------
-  NCCL_OK(api.GroupStart());
+  // ---- 1. sparse groups exported (table scan; a handful of microseconds when there are none), then ONE NCCL group:
+  //         dense counters + stats summed in place, the ranks' record / word counts gathered ----
   for (int i = 0; i < n_local; ++i) {
     gq_index* ix = hs[i];
     CUDA_OK(cudaSetDevice(ix->device));
+    // bounds from the pool's capacity: a record has one word more than its pool record, a multi-allele pool
+    // record has at least 4 words
+    ix->x_words.reserve(ix->gpool.cap + ix->gpool.cap / 4 + 4);
+    ix->x_off.reserve(ix->gpool.cap / 4 + 4);
+    ix->x_cnt.reserve(2);
+    ix->x_cnt_all.reserve(2 * (size_t)n_ranks);
+    if (!ix->x_counts_host) CUDA_OK(cudaHostAlloc((void**)&ix->x_counts_host, 8 * (size_t)n_ranks, cudaHostAllocDefault));
+    CUDA_OK(cudaMemsetAsync(ix->x_cnt.p, 0, 8, ix->stream));
+    gq::launch_groups_export(cov_view(ix), ix->x_words.p, (uint32_t)ix->x_words.cap, ix->x_off.p, (uint32_t)ix->x_off.cap,
+                             ix->x_cnt.p, ix->stream);
+  }
+  NCCL_OK(api.GroupStart());
+  for (int i = 0; i < n_local; ++i) {
+    gq_index* ix = hs[i];
     const size_t n_cnt = 2 * ix->n_alleles + ix->n_per_base;
     if (n_cnt) NCCL_OK(api.AllReduce(ix->counters.p, ix->counters.p, n_cnt, ncclUint32, ncclSum, (ncclComm_t)ix->comm, ix->stream));
     NCCL_OK(api.AllReduce(ix->stats.p, ix->stats.p, 5, ncclUint64, ncclSum, (ncclComm_t)ix->comm, ix->stream));
+    NCCL_OK(api.AllGather(ix->x_cnt.p, ix->x_cnt_all.p, 2, ncclUint32, (ncclComm_t)ix->comm, ix->stream));
   }
   NCCL_OK(api.GroupEnd());
-  // ---- 2. sparse groups: export, gather sizes, gather records, merge ---------------------------------------
-  std::vector<DevBuf<uint32_t>> exp_words(n_local), exp_off(n_local), cnt_local(n_local), cnt_all(n_local);
-  std::vector<std::vector<uint32_t>> counts(n_local);
-  auto release_all = [&] {
-    for (int i = 0; i < n_local; ++i) {
-      cudaSetDevice(hs[i]->device);
-      exp_words[i].release();
-      exp_off[i].release();
-      cnt_local[i].release();
-      cnt_all[i].release();
-    }
-  };
-  try {
-    for (int i = 0; i < n_local; ++i) {
-      gq_index* ix = hs[i];
-      CUDA_OK(cudaSetDevice(ix->device));
-      uint32_t gs[2];
-      CUDA_OK(cudaMemcpyAsync(gs, ix->gsmall.p, 8, cudaMemcpyDeviceToHost, ix->stream));
-      CUDA_OK(cudaStreamSynchronize(ix->stream));
-      const uint32_t pool_used = (uint32_t)std::min<size_t>(gs[0], ix->gpool.cap);
-      // a record has one word more than its pool record; at most pool_used / 4 records (a pool record of a
-      // multi-allele group has >= 4 words)
-      exp_words[i].reserve((size_t)pool_used + pool_used / 4 + 4);
-      exp_off[i].reserve(pool_used / 4 + 4);
-      cnt_local[i].reserve(2);
-      cnt_all[i].reserve(2 * (size_t)n_ranks);
-      CUDA_OK(cudaMemsetAsync(cnt_local[i].p, 0, 8, ix->stream));
-      if (pool_used)
-        gq::launch_groups_export(cov_view(ix), exp_words[i].p, (uint32_t)exp_words[i].cap, exp_off[i].p, (uint32_t)exp_off[i].cap,
-                                 cnt_local[i].p, ix->stream);
-    }
-    NCCL_OK(api.GroupStart());
-    for (int i = 0; i < n_local; ++i)
-      NCCL_OK(api.AllGather(cnt_local[i].p, cnt_all[i].p, 2, ncclUint32, (ncclComm_t)hs[i]->comm, hs[i]->stream));
-    NCCL_OK(api.GroupEnd());
-    uint32_t max_recs = 0, max_words = 0;
-    uint64_t total_recs = 0, total_words = 0;
-    for (int i = 0; i < n_local; ++i) {
-      counts[i].resize(2 * (size_t)n_ranks);
-      CUDA_OK(cudaSetDevice(hs[i]->device));
-      CUDA_OK(cudaMemcpyAsync(counts[i].data(), cnt_all[i].p, 8 * (size_t)n_ranks, cudaMemcpyDeviceToHost, hs[i]->stream));
-      CUDA_OK(cudaStreamSynchronize(hs[i]->stream));
-    }
-    for (int r = 0; r < n_ranks; ++r) {
-      max_recs = std::max(max_recs, counts[0][2 * r]);
-      max_words = std::max(max_words, counts[0][2 * r + 1]);
-      total_recs += counts[0][2 * r];
-      total_words += counts[0][2 * r + 1];
-    }
-    if (total_recs) {
-      std::vector<DevBuf<uint32_t>> all_words(n_local), all_off(n_local);
-      try {
-        for (int i = 0; i < n_local; ++i) {
-          gq_index* ix = hs[i];
-          CUDA_OK(cudaSetDevice(ix->device));
-          // the send buffers are gathered at a common stride: pad them to the largest rank's size
-          if (exp_words[i].cap < max_words || exp_off[i].cap < max_recs) {
-            DevBuf<uint32_t> w, o;
-            w.reserve(max_words);
-            o.reserve(max_recs);
-            const uint32_t my = (uint32_t)ix->comm_rank;
-            if (counts[i][2 * my + 1]) CUDA_OK(cudaMemcpyAsync(w.p, exp_words[i].p, (size_t)counts[i][2 * my + 1] * 4, cudaMemcpyDeviceToDevice, ix->stream));
-            if (counts[i][2 * my]) CUDA_OK(cudaMemcpyAsync(o.p, exp_off[i].p, (size_t)counts[i][2 * my] * 4, cudaMemcpyDeviceToDevice, ix->stream));
-            CUDA_OK(cudaStreamSynchronize(ix->stream));
-            exp_words[i].release();
-            exp_off[i].release();
-            exp_words[i] = w;
-            exp_off[i] = o;
-          }
-          all_words[i].reserve((size_t)max_words * n_ranks);
-          all_off[i].reserve((size_t)max_recs * n_ranks);
-          // the merged table must hold every rank's groups without running full: pre-size it (keeps its content)
-          if (ix->gtab.cap < 4 * total_recs || ix->gpool.cap < 2 * total_words + 16) {
-            std::map<std::vector<uint32_t>, uint64_t> g;
-            collect_groups(ix, g, true);
-            size_t cap = ix->gtab.cap;
-            while (cap < 4 * total_recs) cap <<= 1;
-            rebuild_groups(ix, g, cap);
-            if (ix->gpool.cap < 2 * total_words + 16) {  // rebuild sized the pool for the local groups only
-              DevBuf<uint32_t> np;
-              np.reserve(2 * total_words + 16);
-              CUDA_OK(cudaMemcpy(np.p, ix->gpool.p, ix->gpool.cap * 4, cudaMemcpyDeviceToDevice));
-              ix->gpool.release();
-              ix->gpool = np;
-            }
-          }
-        }
-        NCCL_OK(api.GroupStart());
-        for (int i = 0; i < n_local; ++i) {
-          NCCL_OK(api.AllGather(exp_words[i].p, all_words[i].p, max_words, ncclUint32, (ncclComm_t)hs[i]->comm, hs[i]->stream));
-          NCCL_OK(api.AllGather(exp_off[i].p, all_off[i].p, max_recs, ncclUint32, (ncclComm_t)hs[i]->comm, hs[i]->stream));
-        }
-        NCCL_OK(api.GroupEnd());
-        for (int i = 0; i < n_local; ++i) {
-          gq_index* ix = hs[i];
-          CUDA_OK(cudaSetDevice(ix->device));
-          gq::launch_groups_import(cov_view(ix), all_words[i].p, max_words, all_off[i].p, max_recs, cnt_all[i].p,
-                                   (uint32_t)n_ranks, (uint32_t)ix->comm_rank, ix->stream);
-        }
-        for (int i = 0; i < n_local; ++i) {
-          CUDA_OK(cudaSetDevice(hs[i]->device));
-          CUDA_OK(cudaStreamSynchronize(hs[i]->stream));
-          CUDA_OK(cudaGetLastError());
-          uint32_t gs[2];
-          CUDA_OK(cudaMemcpy(gs, hs[i]->gsmall.p, 8, cudaMemcpyDeviceToHost));
-          if (gs[1] & 1u) throw std::runtime_error("gq_coverage_allreduce: group table overflow during the merge (internal error)");
-        }
-      } catch (...) {
-        for (int i = 0; i < n_local; ++i) {
-          cudaSetDevice(hs[i]->device);
-          all_words[i].release();
-          all_off[i].release();
-        }
-        throw;
-      }
-      for (int i = 0; i < n_local; ++i) {
-        cudaSetDevice(hs[i]->device);
-        all_words[i].release();
-        all_off[i].release();
-      }
-    }
-    for (int i = 0; i < n_local; ++i) {
-      CUDA_OK(cudaSetDevice(hs[i]->device));
-      CUDA_OK(cudaStreamSynchronize(hs[i]->stream));
-    }
-  } catch (...) {
-    release_all();
-    throw;
+  for (int i = 0; i < n_local; ++i) {
+    CUDA_OK(cudaSetDevice(hs[i]->device));
+    CUDA_OK(cudaMemcpyAsync(hs[i]->x_counts_host, hs[i]->x_cnt_all.p, 8 * (size_t)n_ranks, cudaMemcpyDeviceToHost, hs[i]->stream));
   }
-  release_all();
+  for (int i = 0; i < n_local; ++i) {
+    CUDA_OK(cudaSetDevice(hs[i]->device));
+    CUDA_OK(cudaStreamSynchronize(hs[i]->stream));
+  }
+  const uint32_t* counts = hs[0]->x_counts_host;  // identical on every rank
+  uint32_t max_recs = 0, max_words = 0;
+  uint64_t total_recs = 0, total_words = 0;
+  for (int r = 0; r < n_ranks; ++r) {
+    max_recs = std::max(max_recs, counts[2 * r]);
+    max_words = std::max(max_words, counts[2 * r + 1]);
+    total_recs += counts[2 * r];
+    total_words += counts[2 * r + 1];
+  }
+  if (total_recs == 0) return;  // no multi-allele group anywhere (e.g. a SNP-only PRG): done
+  // ---- 2. sparse groups: records gathered at a common stride, every rank merges the other ranks' into its table ----
+  for (int i = 0; i < n_local; ++i) {
+    gq_index* ix = hs[i];
+    CUDA_OK(cudaSetDevice(ix->device));
+    if (ix->x_words.cap < max_words || ix->x_off.cap < max_recs) {  // send buffers padded to the largest rank's size
+      DevBuf<uint32_t> w, o;
+      w.reserve(max_words);
+      o.reserve(max_recs);
+      const uint32_t my = (uint32_t)ix->comm_rank;
+      if (counts[2 * my + 1]) CUDA_OK(cudaMemcpy(w.p, ix->x_words.p, (size_t)counts[2 * my + 1] * 4, cudaMemcpyDeviceToDevice));
+      if (counts[2 * my]) CUDA_OK(cudaMemcpy(o.p, ix->x_off.p, (size_t)counts[2 * my] * 4, cudaMemcpyDeviceToDevice));
+      ix->x_words.release();
+      ix->x_off.release();
+      ix->x_words = w;
+      ix->x_off = o;
+    }
+    ix->x_all_words.reserve((size_t)max_words * n_ranks);
+    ix->x_all_off.reserve((size_t)max_recs * n_ranks);
+    // the merged table must hold every rank's groups without running full: pre-size it (keeps its content)
+    if (ix->gtab.cap < 4 * total_recs || ix->gpool.cap < 2 * total_words + 16) {
+      std::map<std::vector<uint32_t>, uint64_t> g;
+      collect_groups(ix, g, true);
+      size_t cap = ix->gtab.cap;
+      while (cap < 4 * total_recs) cap <<= 1;
+      rebuild_groups(ix, g, cap);
+      if (ix->gpool.cap < 2 * total_words + 16) {  // rebuild sized the pool for the local groups only
+        DevBuf<uint32_t> np;
+        np.reserve(2 * total_words + 16);
+        CUDA_OK(cudaMemcpy(np.p, ix->gpool.p, ix->gpool.cap * 4, cudaMemcpyDeviceToDevice));
+        ix->gpool.release();
+        ix->gpool = np;
+      }
+    }
+  }
+  NCCL_OK(api.GroupStart());
+  for (int i = 0; i < n_local; ++i) {
+    NCCL_OK(api.AllGather(hs[i]->x_words.p, hs[i]->x_all_words.p, max_words, ncclUint32, (ncclComm_t)hs[i]->comm, hs[i]->stream));
+    NCCL_OK(api.AllGather(hs[i]->x_off.p, hs[i]->x_all_off.p, max_recs, ncclUint32, (ncclComm_t)hs[i]->comm, hs[i]->stream));
+  }
+  NCCL_OK(api.GroupEnd());
+  for (int i = 0; i < n_local; ++i) {
+    gq_index* ix = hs[i];
+    CUDA_OK(cudaSetDevice(ix->device));
+    gq::launch_groups_import(cov_view(ix), ix->x_all_words.p, max_words, ix->x_all_off.p, max_recs, ix->x_cnt_all.p,
+                             (uint32_t)n_ranks, (uint32_t)ix->comm_rank, ix->stream);
+  }
+  for (int i = 0; i < n_local; ++i) {
+    CUDA_OK(cudaSetDevice(hs[i]->device));
+    CUDA_OK(cudaStreamSynchronize(hs[i]->stream));
+    CUDA_OK(cudaGetLastError());
+    uint32_t gs[2];
+    CUDA_OK(cudaMemcpy(gs, hs[i]->gsmall.p, 8, cudaMemcpyDeviceToHost));
+    if (gs[1] & 1u) throw std::runtime_error("gq_coverage_allreduce: group table overflow during the merge (internal error)");
+  }
 }
 
 }  // namespace
@@ -283,6 +240,14 @@ int gq_comm_destroy(gq_index* ix) {
   GQ_TRY
   if (ix && ix->comm) {
     cudaSetDevice(ix->device);
+    ix->x_words.release();
+    ix->x_off.release();
+    ix->x_cnt.release();
+    ix->x_cnt_all.release();
+    ix->x_all_words.release();
+    ix->x_all_off.release();
+    if (ix->x_counts_host) cudaFreeHost(ix->x_counts_host);
+    ix->x_counts_host = nullptr;
     nccl().CommDestroy((ncclComm_t)ix->comm);
     ix->comm = nullptr;
     ix->comm_ranks = 1;

@@ -90,6 +90,8 @@ struct gq_index {
   // multi-GPU (comm.cu): ncclComm_t of this handle, its rank and the number of ranks
   void* comm = nullptr;
   int comm_rank = 0, comm_ranks = 1;
+  DevBuf<uint32_t> x_words, x_off, x_cnt, x_cnt_all, x_all_words, x_all_off;  // exchange buffers, kept between calls
+  uint32_t* x_counts_host = nullptr;                                          // pinned: 2 words per rank
   // run info
   double info[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // per-kernel CUDA events of a single-slice run: before seed, after seed, after verify, after text, after the
