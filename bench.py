@@ -295,6 +295,7 @@ def main():
         if int(flag.item()) == 0:
             raise SystemExit("bench.py: PARITY FAILURE — the GPU coverage of the prefix differs from the oracle's")
         idx.reset_coverage()
+    properties = None
 
     # pinned host copies for the end-to-end arms
     pbases = torch.from_numpy(bases).pin_memory()
@@ -357,6 +358,17 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, reduce_ms = float(t[0].item()), float(t[1].item())
     a_sum, p_base, stats = idx.coverage()
+    if parity is None:
+        # no oracle at this size: size-independent properties of the whole job instead — every error-free read maps
+        # on at least one strand, the five counters add up, and every mapped strand was recorded (allele_sum holds
+        # at least one count per site crossing, per-base coverage is non-empty)
+        status = idx.batch_status().reshape(-1, 2)
+        mapped_reads = int(((status == 3).sum(axis=1) >= 1).sum())
+        tot = stats.skipped_reads_count + stats.missing_kmer_reads_count + stats.no_extension_reads_count + stats.exact_mapped_reads_count
+        properties = {"every_read_maps": mapped_reads == n_reads, "counters_add_up": tot == stats.all_reads_count,
+                      "coverage_recorded": bool(a_sum.astype(np.int64).sum() > 0 and p_base.astype(np.int64).sum() > 0)}
+        if not all(properties.values()):
+            raise SystemExit(f"bench.py: PROPERTY FAILURE {properties}")
 
     # ---------------- end-to-end arm (`e2e`): host buffers in, reduced coverage out, every step -------------
     # step = reset the accumulators, map the batch from pinned HOST buffers (2-bit packed reads: the form a reader
@@ -450,7 +462,10 @@ def main():
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": workload_config(config, world, n_reads), "clocks": clocks, "parity": parity["ok"] if parity else None,
-            "parity_check": parity,
+            "parity_check": parity if parity else {"ok": None, "why": "the CPU oracle builds its index in ~40 min at this size; "
+                                                   "size-independent properties checked instead (bit parity of this site "
+                                                   "mix at the same k-mer frequency: tests/test_gpu_parity.py::test_config4_shape_prefix)",
+                                                   "properties": properties},
             "e2e": {"value": reads_total / (e2e_ms / 1e3), "unit": "reads/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps,
                     "input": "2-bit packed reads + word offsets + lengths + seeds in pinned host memory (gq_map_batch_packed); "

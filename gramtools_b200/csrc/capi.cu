@@ -582,7 +582,9 @@ static void finish_handle(gq_index* ix) {
       sum2 += w * w;
     }
     const double per_read = (sum > 0 ? sum2 / sum : 1.0) + sum / (double)nk;
-    ix->seed_recs_per_read = (uint32_t)std::min(4096.0, 1.3 * per_read + 8.0);
+    // ... of which the left-context check of the seed pass keeps a few per read whatever the k-mer's frequency
+    // (config 2: 1.8); a pool that fills up only sends strands to the general kernel
+    ix->seed_recs_per_read = (uint32_t)std::min(64.0, 8.0 + per_read / 8.0);
   }
   alloc_coverage(ix);
   reset_coverage(ix);
