@@ -312,6 +312,8 @@ def main():
     idx.upload(hb, ho, hs)
     for _ in range(args.warmup):
         idx.map_resident()
+    if world > 1:
+        idx.coverage_allreduce()  # warm the communicator too: NCCL sets its channels up on the first collective
     # per-kernel durations come from a separate, untimed pass in which classify and coverage run one after the other
     # (in the timed steps they share the GPU on two streams, so their own durations overlap)
     idx.set_option("overlap_classify", 0)
