@@ -240,8 +240,11 @@ static void do_map(gq_index* ix, const HostBatch* hb = nullptr) {
   ix->overflow_list.reserve(4 * (size_t)n + 16);  // a strand can be flagged by the text kernel and again by the general one
   ix->cov_overflow_list.reserve(2 * (size_t)n);
   ix->mapped_list.reserve(2 * (size_t)n);
-  if (ix->h.is_nested) ix->multi_list.reserve(2 * (size_t)n);  // strands with several final states (coverage, second pass)
-  ix->small.reserve(8 + 7 * kMaxChunks);
+  if (ix->h.is_nested) {  // strands with several final states (coverage, later passes)
+    ix->multi_list.reserve(2 * (size_t)n);
+    ix->heavy_list.reserve(2 * (size_t)n);
+  }
+  ix->small.reserve(8 + 8 * kMaxChunks);
   ix->surv_cnt.reserve(2 * (size_t)n);
   ix->gen_list.reserve(2 * (size_t)n);
   ix->seed_rec.reserve(4 * std::max<size_t>((size_t)n * ix->seed_recs_per_read, 1 << 16));
@@ -258,7 +261,7 @@ static void do_map(gq_index* ix, const HostBatch* hb = nullptr) {
   ix->arena.reserve((size_t)std::max(threads, threads2) * ix->arena_words);
   // small: [0] pool_used [1] n_overflow [2] n_cov_overflow;
   // per chunk c: [8+4c] n_mapped [9+4c] work counter [10+4c] survivor records [11+4c] n_gen (general-kernel work list)
-  CUDA_OK(cudaMemsetAsync(ix->small.p, 0, (8 + 7 * kMaxChunks) * 4, st));
+  CUDA_OK(cudaMemsetAsync(ix->small.p, 0, (8 + 8 * kMaxChunks) * 4, st));
 
   gq::BatchView b{ix->packed.p, ix->word_off.p, ix->len.p, ix->seeds.p, n, 0, n};
   gq::SearchOut o{ix->status.p, ix->st_off.p, ix->st_words.p, ix->st_count.p, ix->pool.p, (uint32_t)ix->pool.cap,
@@ -367,7 +370,8 @@ static void do_map(gq_index* ix, const HostBatch* hb = nullptr) {
       CUDA_OK(cudaEventRecord(ix->kev[5], ix->aux_stream));
       gq::launch_coverage(ix->dv, bc, oc, c, arena, ix->arena_words, threads2, nullptr, 0,
                           ix->cov_overflow_list.p, ix->small.p + 2, ix->small.p + 8 + 5 * kMaxChunks + i, cs,
-                          ix->multi_list.p + 2 * (size_t)chunks[i].r0, ix->small.p + 8 + 6 * kMaxChunks + i);
+                          ix->multi_list.p + 2 * (size_t)chunks[i].r0, ix->small.p + 8 + 6 * kMaxChunks + i,
+                          ix->heavy_list.p + 2 * (size_t)chunks[i].r0, ix->small.p + 8 + 7 * kMaxChunks + i);
       CUDA_OK(cudaEventRecord(ix->kev[6], cs));
       CUDA_OK(cudaEventRecord(ix->aux_event, ix->aux_stream));
       CUDA_OK(cudaStreamWaitEvent(cs, ix->aux_event, 0));
@@ -378,7 +382,8 @@ static void do_map(gq_index* ix, const HostBatch* hb = nullptr) {
       if (timed) CUDA_OK(cudaEventRecord(ix->kev[5], cs));
       gq::launch_coverage(ix->dv, bc, oc, c, arena, ix->arena_words, threads2, nullptr, 0,
                           ix->cov_overflow_list.p, ix->small.p + 2, ix->small.p + 8 + 5 * kMaxChunks + i, cs,
-                          ix->multi_list.p + 2 * (size_t)chunks[i].r0, ix->small.p + 8 + 6 * kMaxChunks + i);
+                          ix->multi_list.p + 2 * (size_t)chunks[i].r0, ix->small.p + 8 + 6 * kMaxChunks + i,
+                          ix->heavy_list.p + 2 * (size_t)chunks[i].r0, ix->small.p + 8 + 7 * kMaxChunks + i);
       if (timed) CUDA_OK(cudaEventRecord(ix->kev[6], cs));
     }
     launches += 3;
@@ -680,6 +685,7 @@ int gq_index_destroy(gq_index* ix) {
   ix->cov_overflow_list.release();
   ix->mapped_list.release();
   ix->multi_list.release();
+  ix->heavy_list.release();
   ix->seed_rec.release();
   ix->surv_rec.release();
   ix->surv_cnt.release();

@@ -62,7 +62,7 @@ struct gq_index {
   // search outputs
   DevBuf<uint8_t> status;
   DevBuf<uint32_t> st_off, st_words, st_count, pool, small;  // small: [pool_used, n_overflow, n_cov_overflow]
-  DevBuf<uint32_t> overflow_list, cov_overflow_list, mapped_list, multi_list;
+  DevBuf<uint32_t> overflow_list, cov_overflow_list, mapped_list, multi_list, heavy_list;
   DevBuf<uint32_t> seed_rec, surv_rec, surv_cnt, gen_list;  // seed pass (SeedOut): survivor records, per-strand counts, general list
   uint32_t seed_recs_per_read = 16;  // candidate records per read (set from the index: ~2.5 x mean suffixes per indexed k-mer, both strands); a full pool sends strands to the general kernel
   bool use_seed_pass = true;

@@ -848,6 +848,8 @@ __device__ __forceinline__ bool record_single_nested_warp(const IndexView& v, co
   return general;
 }
 
+constexpr uint32_t kHeavyStates = 8;  // nested PRGs: strands with this many final states get a warp each
+
 // mode 0: every strand of the work list, handed out one by one (non-nested PRGs: nearly all strands take the table
 //         route; also the overflow re-runs).
 // mode 1: nested PRGs, first pass — the single-state strands (nine in ten), a warp's 32 strands side by side on the
@@ -858,7 +860,7 @@ __global__ void __launch_bounds__(256)
     coverage_kernel(IndexView v, BatchView b, SearchOut o, CoverageView c, uint32_t* arena, uint32_t arena_words,
                     const uint32_t* list, uint32_t n_list, const uint32_t* n_list_dev, uint32_t* overflow_list,
                     uint32_t* n_overflow, uint32_t* work_counter, uint32_t mode, uint32_t* multi_list,
-                    uint32_t* n_multi) {
+                    uint32_t* n_multi, uint32_t* heavy_list, uint32_t* n_heavy) {
   uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t* my_arena = arena + (size_t)tid * arena_words;
   const uint32_t* work_list = list ? list : o.mapped_list;
@@ -869,14 +871,23 @@ __global__ void __launch_bounds__(256)
       const uint32_t i = i0 + lane;
       uint32_t strand = i < n ? work_list[i] : kNoAllele;
       if (strand != kNoAllele && o.status[strand] != ST_MAPPED) strand = kNoAllele;  // kNoAllele: slot of a lost claim
-      bool multi = strand != kNoAllele && o.st_count[strand] != 1;
+      const uint32_t n_st = strand != kNoAllele ? o.st_count[strand] : 0u;
+      bool multi = n_st > 1;
       if (record_single_nested_warp(v, b, o, c, multi ? kNoAllele : strand)) multi = true;
-      const uint32_t mm = __ballot_sync(0xFFFFFFFFu, multi);
+      const bool heavy = multi && n_st >= kHeavyStates;  // a warp each (coverage_multi_kernel)
+      multi = multi && !heavy;
+      const uint32_t mm = __ballot_sync(0xFFFFFFFFu, multi), mh = __ballot_sync(0xFFFFFFFFu, heavy);
       if (mm) {
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(n_multi, (uint32_t)__popc(mm));
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
         if (multi) multi_list[base + __popc(mm & ((1u << lane) - 1u))] = strand;
+      }
+      if (mh) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(n_heavy, (uint32_t)__popc(mh));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (heavy) heavy_list[base + __popc(mh & ((1u << lane) - 1u))] = strand;
       }
     }
     return;
@@ -888,23 +899,301 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Nested PRGs, strands with MANY final states (kHeavyStates or more; up to hundreds where alleles coincide): one
+// WARP per strand. The general route of record_strand (record_general) runs such a strand on one thread — 10^4 to
+// 10^5 dependent loads, and the kernel lasts as long as its heaviest strand. Here the states are spread over the
+// lanes: class keys (LocusFinder per state) in parallel, class representatives and the seeded pick by comparison
+// across lanes, then the states of the chosen class traverse the graph in parallel into per-warp shared-memory
+// tables — the set of loci (64-bit keys, atomicCAS) and the per-node hulls (atomicCAS on the node id, atomicMin /
+// atomicMax on the range: PbCovRecorder's min/max per node commute). Nothing is committed before every table has
+// proved large enough; a strand that does not fit (more than kMultiStates states, a key of more than kMultiKey
+// level-0 sites, full tables) goes to the overflow list and is recorded by the one-thread route.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kMultiWarps = 8, kMultiHull = 512, kMultiLoci = 256, kMultiKey = 16, kMultiStates = 1024;
+constexpr uint32_t kMultiSmemWordsPerWarp = 3 * kMultiHull + 2 * kMultiLoci;
+
+__global__ void __launch_bounds__(32 * kMultiWarps)
+    coverage_multi_kernel(IndexView v, BatchView b, SearchOut o, CoverageView c, uint32_t* scratch, uint32_t warp_words,
+                          const uint32_t* list, const uint32_t* n_list_dev, uint32_t* overflow_list, uint32_t* n_overflow,
+                          uint32_t* work_counter) {
+  extern __shared__ __align__(16) uint32_t s_multi[];
+  const uint32_t full = 0xFFFFFFFFu;
+  const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  uint32_t* s_hull = s_multi + wib * kMultiSmemWordsPerWarp;                       // triples (node, start, end)
+  unsigned long long* s_loci = reinterpret_cast<unsigned long long*>(s_hull + 3 * kMultiHull);  // site << 32 | allele + 1
+  uint32_t* w_scr = scratch + (size_t)warp * warp_words;
+  const uint32_t n = *n_list_dev;
+  while (true) {
+    uint32_t i = 0;
+    if (lane == 0) i = atomicAdd(work_counter, 1u);
+    i = __shfl_sync(full, i, 0);
+    if (i >= n) break;
+    const uint32_t strand = list[i];
+    if (o.status[strand] != ST_MAPPED) continue;
+    const uint32_t ns = o.st_count[strand];
+    const uint32_t* recs = o.pool + o.st_off[strand];
+    const uint32_t L = b.len[strand >> 1];
+    auto give_back = [&]() {  // the one-thread route takes it (re-run pass of the host)
+      if (lane == 0) overflow_list[atomicAdd(n_overflow, 1u)] = strand;
+    };
+    if (ns > kMultiStates || warp_words < ns * (3 + kMultiKey) + 3 * kMultiLoci) {
+      give_back();
+      continue;
+    }
+    uint32_t* rec_off = w_scr;          // ns
+    uint32_t* key_len = w_scr + ns;     // ns; 0xFFFFFFFF = path-less state
+    uint32_t* rep = w_scr + 2 * ns;     // ns
+    uint32_t* keys = w_scr + 3 * ns;    // ns x kMultiKey
+    if (lane == 0) {
+      uint32_t off = 0;
+      for (uint32_t j = 0; j < ns; ++j) {
+        rec_off[j] = off;
+        off += 4 + 2 * recs[off + 2] + 2 * recs[off + 3];
+      }
+    }
+    __syncwarp();
+    constexpr uint32_t kLoc = 48;
+    uint32_t used_l[kLoc], base_l[kLoc], loci_l[2 * kLoc];
+    LocusLists ll;
+    ll.loci = loci_l, ll.base = base_l, ll.used = used_l;
+    ll.cap = kLoc;
+    // ---- class keys, non-variant mappings (MappingInstanceSelector, coverage_common.cpp:85-164) ----
+    bool bad = false;
+    uint32_t nonvar = 0, npath = 0;
+    for (uint32_t j = lane; j < ns; j += 32) {
+      const StateRec st = parse_rec(recs + rec_off[j]);
+      if (!(st.nt | st.ng)) {
+        key_len[j] = 0xFFFFFFFFu;
+        nonvar += st.hi - st.lo + 1;
+        continue;
+      }
+      ++npath;
+      ll.n_loci = ll.n_base = ll.n_used = 0;
+      ll.overflow = false;
+      locus_finder(v, st, ll);
+      if (ll.overflow || ll.n_base > kMultiKey) {
+        bad = true;
+        key_len[j] = 0;
+        continue;
+      }
+      sort_u32(ll.base, ll.n_base);
+      for (uint32_t q = 0; q < ll.n_base; ++q) keys[j * kMultiKey + q] = ll.base[q];
+      key_len[j] = ll.n_base;
+    }
+    __syncwarp();
+    nonvar = __reduce_add_sync(full, nonvar);
+    npath = __reduce_add_sync(full, npath);
+    if (__any_sync(full, bad)) {
+      give_back();
+      continue;
+    }
+    if (npath == 0) continue;
+    // ---- class representatives: the first state with the same key; number of classes ----
+    uint32_t ncls = 0;
+    for (uint32_t j = lane; j < ns; j += 32) {
+      uint32_t r = 0xFFFFFFFFu;
+      if (key_len[j] != 0xFFFFFFFFu) {
+        r = j;
+        for (uint32_t q = 0; q < j; ++q)
+          if (key_len[q] != 0xFFFFFFFFu && cmp_key(keys + q * kMultiKey, key_len[q], keys + j * kMultiKey, key_len[j]) == 0) {
+            r = q;
+            break;
+          }
+        if (r == j) ++ncls;
+      }
+      rep[j] = r;
+    }
+    __syncwarp();
+    ncls = __reduce_add_sync(full, ncls);
+    // ---- random_select_entry (:97-107): seeded pick among non-variant mappings + classes ----
+    const uint32_t total = nonvar + ncls;
+    uint32_t pick = 1;
+    if (total != 1) {
+      if (lane == 0) pick = uniform_1_to(b.seeds[strand >> 1], total);
+      pick = __shfl_sync(full, pick, 0);
+    }
+    if (pick <= nonvar) continue;
+    const uint32_t want = pick - nonvar - 1;
+    uint32_t chosen = 0xFFFFFFFFu;  // the representative with exactly `want` smaller ones (std::map order)
+    for (uint32_t j = lane; j < ns; j += 32) {
+      if (rep[j] != j) continue;
+      uint32_t less = 0;
+      for (uint32_t q = 0; q < ns; ++q)
+        if (q != j && rep[q] == q && cmp_key(keys + q * kMultiKey, key_len[q], keys + j * kMultiKey, key_len[j]) < 0) ++less;
+      if (less == want) chosen = j;
+    }
+    chosen = __reduce_min_sync(full, chosen);
+    if (chosen == 0xFFFFFFFFu) {
+      if (lane == 0) atomicOr(c.error_flags, 2u);
+      continue;
+    }
+    // ---- loci of the chosen class + per-node hulls (PbCovRecorder, allele_base.cpp:221-296) ----
+    for (uint32_t q = lane; q < kMultiHull; q += 32) {
+      s_hull[3 * q] = kNoAllele;
+      s_hull[3 * q + 1] = 0xFFFFFFFFu;
+      s_hull[3 * q + 2] = 0;
+    }
+    for (uint32_t q = lane; q < kMultiLoci; q += 32) s_loci[q] = 0ull;
+    __syncwarp();
+    uint32_t n_hull = 0;  // this lane's insertions (the table is declared full at half its slots)
+    auto hull_put = [&](uint32_t node, uint32_t s, uint32_t e) {
+      if (v.nodes[node].len == 0) return;  // process_Node :282-287
+      for (uint32_t h = (node * 2654435761u) >> (32 - 9), probes = 0;; h = (h + 1) & (kMultiHull - 1), ++probes) {
+        uint32_t cur = s_hull[3 * h];
+        if (cur == kNoAllele) cur = atomicCAS(&s_hull[3 * h], kNoAllele, node);
+        if (cur == kNoAllele) ++n_hull;
+        if (cur == kNoAllele || cur == node) {
+          atomicMin(&s_hull[3 * h + 1], s);
+          atomicMax(&s_hull[3 * h + 2], e);
+          return;
+        }
+        if (probes > kMultiHull / 2) {
+          bad = true;
+          return;
+        }
+      }
+    };
+    for (uint32_t j = lane; j < ns; j += 32) {
+      if (rep[j] != chosen) continue;
+      const StateRec st = parse_rec(recs + rec_off[j]);
+      ll.n_loci = ll.n_base = ll.n_used = 0;
+      ll.overflow = false;
+      locus_finder(v, st, ll);
+      if (ll.overflow) {
+        bad = true;
+        continue;
+      }
+      for (uint32_t q = 0; q < ll.n_loci; ++q) {  // set union over the class
+        const unsigned long long key = ((unsigned long long)loci_l[2 * q] << 32) | (unsigned long long)(loci_l[2 * q + 1] + 1u);
+        uint32_t h = (uint32_t)((loci_l[2 * q] * 2654435761u + loci_l[2 * q + 1] * 40503u) >> 24) & (kMultiLoci - 1);
+        for (uint32_t probes = 0;; h = (h + 1) & (kMultiLoci - 1), ++probes) {
+          unsigned long long cur = s_loci[h];
+          if (cur == 0ull) cur = atomicCAS(&s_loci[h], 0ull, key);
+          if (cur == 0ull || cur == key) break;
+          if (probes > kMultiLoci / 2) {
+            bad = true;
+            break;
+          }
+        }
+      }
+      bool first = true;
+      for (uint32_t occ = st.lo;; ++occ) {
+        const uint32_t pos = __ldg(v.sa + occ), nid = __ldg(v.pos2node + pos);
+        Trav t;
+        t.v = &v;
+        t.cur = nid;
+        t.remaining = L;
+        t.T = st.T;
+        t.ti = st.nt;
+        t.first = true;
+        const Node& nd = v.nodes[nid];
+        t.start_pos = nd.len > 1 ? pos - nd.start : 0;
+        t.end_pos = 0;
+        t.bad = false;
+        if (first) {  // only the first occurrence of a state gets the full traversal (:246-270)
+          first = false;
+          while (t.next()) hull_put(t.cur, t.start_pos, t.end_pos);
+        } else if (t.next())
+          hull_put(t.cur, t.start_pos, t.end_pos);
+        if (t.bad) atomicOr(c.error_flags, 2u);
+        if (occ == st.hi) break;
+      }
+    }
+    __syncwarp();
+    if (__reduce_add_sync(full, n_hull) > kMultiHull / 2) bad = true;
+    if (__any_sync(full, bad)) {
+      give_back();
+      continue;
+    }
+    // ---- commit: lane 0 sorts the loci and settles the groups (multi-allele groups first find their table slots:
+    //      a full group table gives the strand back before any counter is touched) ----
+    uint32_t ok = 1;
+    if (lane == 0) {
+      uint32_t n_loci = 0;
+      uint32_t* sl = keys + ns * kMultiKey;  // sorted (site, allele) pairs, then the group slots
+      for (uint32_t q = 0; q < kMultiLoci; ++q) {
+        const unsigned long long k64 = s_loci[q];
+        if (k64 == 0ull) continue;
+        const uint32_t s0 = (uint32_t)(k64 >> 32), a0 = (uint32_t)k64 - 1u;
+        uint32_t j = n_loci++;
+        while (j > 0 && (sl[2 * (j - 1)] > s0 || (sl[2 * (j - 1)] == s0 && (int32_t)sl[2 * (j - 1) + 1] > (int32_t)a0))) {
+          sl[2 * j] = sl[2 * (j - 1)];
+          sl[2 * j + 1] = sl[2 * (j - 1) + 1];
+          --j;
+        }
+        sl[2 * j] = s0;
+        sl[2 * j + 1] = a0;
+      }
+      uint32_t* slots = sl + 2 * kMultiLoci;
+      uint32_t ng = 0;
+      for (uint32_t q = 0; q < n_loci && ok;) {
+        uint32_t e = q;
+        while (e < n_loci && sl[2 * e] == sl[2 * q]) ++e;
+        if (e - q > 1) {
+          const uint32_t h = grouped_find_or_insert(c, (sl[2 * q] - 5) >> 1, sl + 2 * q + 1, e - q, 2);
+          if (h == kNoAllele) ok = 0;
+          slots[ng++] = h;
+        }
+        q = e;
+      }
+      if (ok) {
+        ng = 0;
+        for (uint32_t q = 0; q < n_loci;) {
+          const uint32_t site = sl[2 * q], ao = c.allele_off[(site - 5) >> 1];
+          uint32_t e = q;
+          while (e < n_loci && sl[2 * e] == site) {
+            gq_red_add(c.allele_sum + ao + sl[2 * e + 1], 1u);  // allele_sum.cpp:31-43
+            ++e;
+          }
+          if (e - q == 1) gq_red_add(c.grouped_single + ao + sl[2 * q + 1], 1u);
+          else gq_red_add(c.gcount + slots[ng++], 1u);  // grouped_allele_counts.cpp:17-49
+          q = e;
+        }
+      }
+    }
+    ok = __shfl_sync(full, ok, 0);
+    if (!ok) {
+      give_back();
+      continue;
+    }
+    for (uint32_t q = lane; q < kMultiHull; q += 32) {
+      const uint32_t node = s_hull[3 * q];
+      if (node == kNoAllele) continue;
+      const Node& nd = v.nodes[node];
+      if (nd.cov_off == kNoAllele) continue;
+      for (uint32_t x = s_hull[3 * q + 1]; x <= s_hull[3 * q + 2]; ++x) gq_red_add(c.per_base + nd.cov_off + x, 1u);
+    }
+    __syncwarp();
+  }
+}
+
 void launch_coverage(const IndexView& v, const BatchView& b, const SearchOut& o, const CoverageView& c,
                      uint32_t* arena, uint32_t arena_words, uint32_t n_threads, const uint32_t* list,
                      uint32_t n_list, uint32_t* overflow_list, uint32_t* n_overflow, uint32_t* work_counter,
-                     cudaStream_t st, uint32_t* multi_list, uint32_t* n_multi) {
+                     cudaStream_t st, uint32_t* multi_list, uint32_t* n_multi, uint32_t* heavy_list, uint32_t* n_heavy) {
   uint32_t work = list ? n_list : 2 * (b.read_end - b.read_begin);
   if (work == 0) return;
   uint32_t blocks = (min(work, n_threads) + 255) / 256;
   cudaMemsetAsync(work_counter, 0, 4, st);
-  if (v.any_nested && multi_list && !list) {  // nested PRG, main pass: single-state strands, then the others
+  if (v.any_nested && multi_list && !list) {
+    // nested PRG, main pass: single-state strands (warp-convergent), then the strands with many states (a warp
+    // each), then the rest (a thread each, handed out one by one)
     coverage_kernel<<<blocks, 256, 0, st>>>(v, b, o, c, arena, arena_words, nullptr, 0, nullptr, overflow_list, n_overflow,
-                                            work_counter, 1u, multi_list, n_multi);
+                                            work_counter, 1u, multi_list, n_multi, heavy_list, n_heavy);
+    const uint32_t smem = kMultiWarps * kMultiSmemWordsPerWarp * 4;
+    cudaFuncSetAttribute(coverage_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const uint32_t mblocks = min(blocks * 256u / (32u * kMultiWarps), 148u * 3u);
+    coverage_multi_kernel<<<max(mblocks, 1u), 32 * kMultiWarps, smem, st>>>(v, b, o, c, arena, 32u * arena_words, heavy_list,
+                                                                              n_heavy, overflow_list, n_overflow, work_counter);
+    cudaMemsetAsync(work_counter, 0, 4, st);
     coverage_kernel<<<blocks, 256, 0, st>>>(v, b, o, c, arena, arena_words, multi_list, work, n_multi, overflow_list,
-                                            n_overflow, work_counter, 2u, nullptr, nullptr);
+                                            n_overflow, work_counter, 2u, nullptr, nullptr, nullptr, nullptr);
     return;
   }
   coverage_kernel<<<blocks, 256, 0, st>>>(v, b, o, c, arena, arena_words, list, n_list, nullptr, overflow_list, n_overflow,
-                                          work_counter, 0u, nullptr, nullptr);
+                                          work_counter, 0u, nullptr, nullptr, nullptr, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------

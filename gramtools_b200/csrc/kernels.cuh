@@ -92,7 +92,8 @@ void launch_search(const IndexView& v, const BatchView& b, const SearchOut& o, u
 void launch_coverage(const IndexView& v, const BatchView& b, const SearchOut& o, const CoverageView& c,
                      uint32_t* arena, uint32_t arena_words, uint32_t n_threads, const uint32_t* list,
                      uint32_t n_list, uint32_t* overflow_list, uint32_t* n_overflow, uint32_t* work_counter,
-                     cudaStream_t st, uint32_t* multi_list = nullptr, uint32_t* n_multi = nullptr);
+                     cudaStream_t st, uint32_t* multi_list = nullptr, uint32_t* n_multi = nullptr,
+                     uint32_t* heavy_list = nullptr, uint32_t* n_heavy = nullptr);
 
 // k-mer filter for the strands whose search found nothing (status ST_UNCLASSIFIED -> 1 or 2)
 void launch_classify(const IndexView& v, const BatchView& b, const SearchOut& o, const uint32_t* list, uint32_t n_list,
