@@ -848,7 +848,10 @@ __device__ __forceinline__ bool record_single_nested_warp(const IndexView& v, co
   return general;
 }
 
-constexpr uint32_t kHeavyStates = 8;  // nested PRGs: strands with this many final states get a warp each
+#ifndef GQ_HEAVY_STATES
+#define GQ_HEAVY_STATES 4
+#endif
+constexpr uint32_t kHeavyStates = GQ_HEAVY_STATES;  // nested PRGs: strands with this many final states get a warp each
 
 // mode 0: every strand of the work list, handed out one by one (non-nested PRGs: nearly all strands take the table
 //         route; also the overflow re-runs).
