@@ -95,6 +95,8 @@ static void alloc_coverage(gq_index* ix) {
   ix->gpool.reserve((size_t)cap * 4);
   ix->gsmall.reserve(4);
   ix->stats.reserve(8);
+  ix->stats_batch.reserve(8);
+  if (!ix->post_host) CUDA_OK(cudaHostAlloc((void**)&ix->post_host, 64, cudaHostAllocDefault));
 }
 
 static void reset_coverage(gq_index* ix) {
@@ -393,12 +395,21 @@ static void do_map(gq_index* ix, const HostBatch* hb = nullptr) {
     CUDA_OK(cudaEventRecord(ix->aux_event, ix->aux_stream));
     CUDA_OK(cudaStreamWaitEvent(st, ix->aux_event, 0));
   }
+  // the batch's five counters, committed to the totals on the device unless a strand overflowed (then they are
+  // counted again after the re-runs); everything the host needs comes back in ONE pinned copy, one synchronisation
+  CUDA_OK(cudaMemsetAsync(ix->stats_batch.p, 0, 40, st));
+  gq::launch_stats(ix->status.p, ix->len.p, n, ix->stats_batch.p, st);
+  gq::launch_stats_commit(ix->stats_batch.p, ix->stats.p, ix->small.p, st);
+  launches += 2;
   CUDA_OK(cudaEventRecord(ix->ev[2], st));
   ix->info[7] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
-  uint32_t small[4];
+  uint32_t* small = ix->post_host;
+  uint32_t* gs = ix->post_host + 4;
   CUDA_OK(cudaMemcpyAsync(small, ix->small.p, 16, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaMemcpyAsync(gs, ix->gsmall.p, 8, cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaStreamSynchronize(st));
   CUDA_OK(cudaGetLastError());
+  const bool had_reruns = small[1] > 0 || small[2] > 0;
   {
     float ms_t = 0;
     cudaEventElapsedTime(&ms_t, ix->ev[0], ix->ev[2]);
@@ -547,13 +558,16 @@ static void do_map(gq_index* ix, const HostBatch* hb = nullptr) {
       big_threads = std::max<uint32_t>(256, big_threads / 4);
     }
   }
-  gq::launch_stats(ix->status.p, ix->len.p, n, ix->stats.p, st);
-  ++launches;
-  CUDA_OK(cudaEventRecord(ix->ev[2], st));  // end of the call's device work, re-runs included
-  uint32_t gs[2];
-  CUDA_OK(cudaMemcpyAsync(gs, ix->gsmall.p, 8, cudaMemcpyDeviceToHost, st));
-  CUDA_OK(cudaStreamSynchronize(st));
-  CUDA_OK(cudaGetLastError());
+  if (had_reruns) {  // statuses changed: count the batch again, commit, and look at the error flags once more
+    CUDA_OK(cudaMemsetAsync(ix->stats_batch.p, 0, 40, st));
+    gq::launch_stats(ix->status.p, ix->len.p, n, ix->stats_batch.p, st);
+    gq::launch_stats_commit(ix->stats_batch.p, ix->stats.p, nullptr, st);
+    launches += 2;
+    CUDA_OK(cudaEventRecord(ix->ev[2], st));  // end of the call's device work, re-runs included
+    CUDA_OK(cudaMemcpyAsync(gs, ix->gsmall.p, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    CUDA_OK(cudaGetLastError());
+  }
   if (gs[1] & 1u) throw std::runtime_error("grouped allele count table is full (internal error: flagged strands were not re-run)");
   if (gs[1] & 2u) throw std::runtime_error("inconsistent traversal while recording per-base coverage");
   {
@@ -669,6 +683,8 @@ int gq_index_destroy(gq_index* ix) {
   ix->gpool.release();
   ix->gsmall.release();
   ix->stats.release();
+  ix->stats_batch.release();
+  if (ix->post_host) cudaFreeHost(ix->post_host);
   ix->bases.release();
   ix->offsets.release();
   ix->word_off.release();

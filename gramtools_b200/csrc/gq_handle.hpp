@@ -51,7 +51,8 @@ struct gq_index {
   DevBuf<uint32_t> counters;  // allele_sum | grouped_single | per_base
   DevBuf<uint32_t> allele_off;
   DevBuf<uint32_t> gtab, gcount, gpool, gsmall;  // gsmall: [gpool_used, error_flags]
-  DevBuf<unsigned long long> stats;
+  DevBuf<unsigned long long> stats, stats_batch;  // totals; the counters of the batch being mapped
+  uint32_t* post_host = nullptr;                  // pinned: [small 0..3 | gsmall 0..1] read back once per call
   uint64_t n_alleles = 0, n_per_base = 0;
   // batch
   DevBuf<uint8_t> bases;

@@ -1219,6 +1219,18 @@ __global__ void stats_kernel(const uint8_t* status, const uint32_t* len, uint32_
   }
 }
 
+// batch counters -> the handle's totals; with `small` given only when the batch needs no overflow re-run (the host
+// then counts again after the re-runs and commits unconditionally)
+__global__ void stats_commit_kernel(const unsigned long long* __restrict__ batch, unsigned long long* __restrict__ total,
+                                    const uint32_t* __restrict__ small) {
+  if (small && (small[1] | small[2])) return;
+  if (threadIdx.x < 5) total[threadIdx.x] += batch[threadIdx.x];
+}
+
+void launch_stats_commit(const unsigned long long* batch, unsigned long long* total, const uint32_t* small, cudaStream_t st) {
+  stats_commit_kernel<<<1, 32, 0, st>>>(batch, total, small);
+}
+
 void launch_stats(const uint8_t* status, const uint32_t* len, uint32_t n_reads, unsigned long long* stats,
                   cudaStream_t st) {
   if (n_reads == 0) return;

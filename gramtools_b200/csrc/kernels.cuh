@@ -102,6 +102,8 @@ void launch_classify(const IndexView& v, const BatchView& b, const SearchOut& o,
 void launch_stats(const uint8_t* status, const uint32_t* len, uint32_t n_reads, unsigned long long* stats,
                   cudaStream_t st);
 
+void launch_stats_commit(const unsigned long long* batch, unsigned long long* total, const uint32_t* small, cudaStream_t st);
+
 // out[0, n_alleles) = allele_sum mod 65536, out[n_alleles, n_alleles + n_per_base) = min(per_base, 65535)
 void launch_fetch(const uint32_t* allele_sum, uint32_t n_alleles, const uint32_t* per_base, uint32_t n_per_base,
                   uint16_t* out, cudaStream_t st);
