@@ -380,7 +380,9 @@ static void do_map(gq_index* ix, const HostBatch* hb = nullptr) {
     } else {
       const bool timed = chunks.size() == 1;
       if (timed) CUDA_OK(cudaEventRecord(ix->kev[4], cs));
-      gq::launch_classify(ix->dv, bc, oc, nullptr, 0, cs);
+      // sliced batches: the k-mer filter runs ONCE over the whole batch after the last slice (it only reads the
+      // statuses; per slice it paid its fixed cost — two passes, a 128 KB set copied per CTA — seven times)
+      if (chunks.size() == 1) gq::launch_classify(ix->dv, bc, oc, nullptr, 0, cs);
       if (timed) CUDA_OK(cudaEventRecord(ix->kev[5], cs));
       gq::launch_coverage(ix->dv, bc, oc, c, arena, ix->arena_words, threads2, nullptr, 0,
                           ix->cov_overflow_list.p, ix->small.p + 2, ix->small.p + 8 + 5 * kMaxChunks + i, cs,
@@ -395,6 +397,7 @@ static void do_map(gq_index* ix, const HostBatch* hb = nullptr) {
     CUDA_OK(cudaEventRecord(ix->aux_event, ix->aux_stream));
     CUDA_OK(cudaStreamWaitEvent(st, ix->aux_event, 0));
   }
+  if (chunks.size() > 1) gq::launch_classify(ix->dv, b, o, nullptr, 0, st);
   // the batch's five counters, committed to the totals on the device unless a strand overflowed (then they are
   // counted again after the re-runs); everything the host needs comes back in ONE pinned copy, one synchronisation
   CUDA_OK(cudaMemsetAsync(ix->stats_batch.p, 0, 40, st));

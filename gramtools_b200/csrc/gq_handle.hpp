@@ -76,7 +76,7 @@ struct gq_index {
   size_t fetch_host_bytes = 0;
   DevBuf<uint16_t> fetch_dev;
   std::vector<cudaEvent_t> chunk_events, tl_copy;
-  uint32_t chunk_reads = 1u << 18, tail_chunk_reads = 1u << 15;
+  uint32_t chunk_reads = 1u << 18, tail_chunk_reads = 1u << 16;
   uint32_t resident_slices = 1;  // gq_map_resident: slices run on two streams
   bool overlap_classify = true;  // single-slice runs: classify_kernel beside coverage_kernel on a second stream  // slice size of the H2D / compute pipeline in gq_map_batch
   // options
