@@ -1124,6 +1124,7 @@ struct FastForks {
   bool have_fin;             // one branch has reached the end of the read: kept here while the others are tried
   bool fin_p_valid;
   uint32_t fin_lo, fin_p, fin_cnt;
+  uint32_t fin_from;  // first path pair kept in fin_T: the pairs below it are shared with every pending fork and stay in f.T
   uint32_t fin_T[2 * kFastT], fin_G[kFastG];
 };
 
@@ -1275,6 +1276,24 @@ GQ_DEV inline void fast_event_dfs(FastLane& f, FastForks& fk, const IndexView& v
   fast_jump(f, fk, v, marker, allele);
 }
 
+// keep the finished branch aside while the pending forks are tried: only the path pairs a fork can overwrite (those
+// from the smallest fork point on) need a copy
+GQ_DEV inline void fast_keep_finisher(const FastLane& f, FastForks& fk) {
+  fk.have_fin = true;
+  fk.fin_p_valid = f.p_valid;
+  fk.fin_lo = f.ln.lo;
+  fk.fin_p = f.ln.p;
+  fk.fin_cnt = f.nt | (f.ng << 8) | (f.ng0 << 16);
+  uint32_t from = f.nt;
+  for (uint32_t i = 0; i < fk.n; ++i) {
+    const uint32_t nt_i = fk.cnt[i] & 0xFFu;
+    from = nt_i < from ? nt_i : from;
+  }
+  fk.fin_from = from;
+  for (uint32_t j = 2 * from; j < 2 * f.nt; ++j) fk.fin_T[j] = f.T[j];
+  for (uint32_t j = 0; j < kFastG; ++j) fk.fin_G[j] = f.G[j];
+}
+
 // The walking branch has ended (dead, finished, or it needs the general kernel): remember a finisher, take the
 // next fork, or close the candidate. Afterwards either a branch is walking again, or fk.active is false and the lane
 // holds the candidate's outcome for fast_outcome (state LS_EV_TOP = its single finished branch).
@@ -1291,13 +1310,11 @@ GQ_DEV inline void fast_branch_end(FastLane& f, FastForks& fk, const IndexView& 
       fk.active = false;
       return;
     }
-    fk.have_fin = true;
-    fk.fin_p_valid = f.p_valid;
-    fk.fin_lo = ln.lo;
-    fk.fin_p = ln.p;
-    fk.fin_cnt = f.nt | (f.ng << 8) | (f.ng0 << 16);
-    for (uint32_t j = 0; j < 2 * f.nt; ++j) fk.fin_T[j] = f.T[j];
-    for (uint32_t j = 0; j < kFastG; ++j) fk.fin_G[j] = f.G[j];
+    if (fk.n == 0) {  // nothing else to try (the usual case): the lane already holds the candidate's outcome
+      fk.active = false;
+      return;
+    }
+    fast_keep_finisher(f, fk);
   }
   f.result = FAST_NONE;
   while (true) {
@@ -1307,7 +1324,7 @@ GQ_DEV inline void fast_branch_end(FastLane& f, FastForks& fk, const IndexView& 
         f.nt = fk.fin_cnt & 0xFFu;
         f.ng = (fk.fin_cnt >> 8) & 0xFFu;
         f.ng0 = fk.fin_cnt >> 16;
-        for (uint32_t j = 0; j < 2 * f.nt; ++j) f.T[j] = fk.fin_T[j];
+        for (uint32_t j = 2 * fk.fin_from; j < 2 * f.nt; ++j) f.T[j] = fk.fin_T[j];
         for (uint32_t j = 0; j < kFastG; ++j) f.G[j] = fk.fin_G[j];
         f.p_valid = fk.fin_p_valid;
         ln.p = fk.fin_p;
@@ -1340,13 +1357,7 @@ GQ_DEV inline void fast_branch_end(FastLane& f, FastForks& fk, const IndexView& 
           fk.active = false;
           return;
         }
-        fk.have_fin = true;
-        fk.fin_p_valid = f.p_valid;
-        fk.fin_lo = ln.lo;
-        fk.fin_p = ln.p;
-        fk.fin_cnt = f.nt | (f.ng << 8) | (f.ng0 << 16);
-        for (uint32_t j = 0; j < 2 * f.nt; ++j) fk.fin_T[j] = f.T[j];
-        for (uint32_t j = 0; j < kFastG; ++j) fk.fin_G[j] = f.G[j];
+        fast_keep_finisher(f, fk);
       }
       f.result = FAST_NONE;  // dead or recorded: next fork
       continue;
