@@ -228,6 +228,17 @@ def test_frequent_kmers_wide_seed_intervals(shape):
     assert r["fast_finished"] > 2 * r["general"] and r["too_wide"] == 0, r
 
 
+def test_large_k_seed_buckets():
+    """k = 12: the seed view is bucketed by ONE context base (k <= 11: two, k >= 13: none) — index invariants and
+    parity on an indel PRG. (k = 13 was run by hand when the buckets were written: the 4^13 tables make it a
+    30-second oracle build.)"""
+    prg = synth.make_indel_prg(3000, 150, 5)
+    bases, offs = _reads_for(prg, 400, 60, 3, garbage=0.05, n_frac=0.01)
+    Emu(prg, 12).index_check()
+    ro, _ = _check(prg, 12, bases, offs, what="k12")
+    assert ro.stats[4] > 100
+
+
 def test_flat_index_invariants():
     """Text groups, inverse SA, text-order jump records, the seed view (per-suffix entries with left context),
     the reverse-complement presence set and the inline first edge: checked structurally on SNP, nested, indel and
