@@ -211,7 +211,7 @@ def coverage_result(idx):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="gq")
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))

@@ -66,7 +66,6 @@ static void upload_index(gq_index* ix) {
   v.apos = upload(ix, h.apos);
   v.k = h.k;
   v.kmer_bits = upload(ix, h.kmer_bits);
-  v.kmer_bits_rc = upload(ix, h.kmer_bits_rc);
   v.kmer_off = upload(ix, h.kmer_off);
   v.kmer_states = upload(ix, h.kmer_states);
   v.seed_off = upload(ix, h.seed_off);
@@ -133,6 +132,7 @@ static void reserve_batch(gq_index* ix, uint64_t n_reads, uint64_t nb) {
   ix->offsets.reserve(n_reads + 1);
   ix->word_off.reserve(n_reads + 1);
   ix->packed.reserve(max_words);
+  ix->packed_rc.reserve(max_words);
   ix->len.reserve(n_reads);
   ix->seeds.reserve(n_reads);
 }
@@ -265,7 +265,7 @@ static void do_map(gq_index* ix, const HostBatch* hb = nullptr) {
   // per chunk c: [8+4c] n_mapped [9+4c] work counter [10+4c] survivor records [11+4c] n_gen (general-kernel work list)
   CUDA_OK(cudaMemsetAsync(ix->small.p, 0, (8 + 8 * kMaxChunks) * 4, st));
 
-  gq::BatchView b{ix->packed.p, ix->word_off.p, ix->len.p, ix->seeds.p, n, 0, n};
+  gq::BatchView b{ix->packed.p, ix->packed_rc.p, ix->word_off.p, ix->len.p, ix->seeds.p, n, 0, n};
   gq::SearchOut o{ix->status.p, ix->st_off.p, ix->st_words.p, ix->st_count.p, ix->pool.p, (uint32_t)ix->pool.cap,
                   ix->small.p,  ix->overflow_list.p, ix->small.p + 1, ix->mapped_list.p, ix->small.p + 8,
                   ix->small.p + 9, ix->use_seed_pass ? ix->surv_cnt.p : nullptr};
@@ -318,6 +318,8 @@ static void do_map(gq_index* ix, const HostBatch* hb = nullptr) {
     if (!pipelined) CUDA_OK(cudaEventRecord(ix->ev[3], st));
     CUDA_OK(cudaStreamWaitEvent(ix->aux_stream, ix->ev[3], 0));  // after the counters' memset
   }
+  // pipelined batches of four or more slices: the last slice but two ends the early k-mer filter's share
+  const size_t early_upto = (pipelined && ix->early_classify && chunks.size() >= 4) ? chunks.size() - 3 : SIZE_MAX;
   for (size_t i = 0; i < chunks.size(); ++i) {
     cudaStream_t cs = (two_streams && (i & 1)) ? ix->aux_stream : st;
     uint32_t* arena = (two_streams && (i & 1)) ? ix->arena2.p : ix->arena.p;
@@ -332,6 +334,8 @@ static void do_map(gq_index* ix, const HostBatch* hb = nullptr) {
     gq::BatchView bc = b;
     bc.read_begin = chunks[i].r0;
     bc.read_end = chunks[i].r1;
+    gq::launch_revcomp(bc, ix->packed_rc.p, cs);  // the slice's reverse strands
+    ++launches;
     gq::SearchOut oc = o;
     oc.mapped_list = ix->mapped_list.p + 2 * (size_t)chunks[i].r0;
     oc.n_mapped = ix->small.p + 8 + 4 * i;
@@ -392,12 +396,38 @@ static void do_map(gq_index* ix, const HostBatch* hb = nullptr) {
     }
     launches += 3;
     if (!tl.empty()) CUDA_OK(cudaEventRecord(tl[4 * i + 2], cs));
+    if (i == early_upto) {
+      // Pipelined path: the k-mer filter of everything mapped so far runs NOW on a stream of its own, beside the
+      // remaining (small) slices — the call is copy-bound, so the GPU has room — and only the last slices' strands
+      // are left for the pass after the last slice (the filter over the whole batch was 0.13 ms of serial tail).
+      if (!ix->cls_stream) {
+        CUDA_OK(cudaStreamCreateWithFlags(&ix->cls_stream, cudaStreamNonBlocking));
+        for (auto& e : ix->cls_event) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      }
+      CUDA_OK(cudaEventRecord(ix->cls_event[0], st));
+      CUDA_OK(cudaEventRecord(ix->cls_event[1], ix->aux_stream));
+      CUDA_OK(cudaStreamWaitEvent(ix->cls_stream, ix->cls_event[0], 0));
+      CUDA_OK(cudaStreamWaitEvent(ix->cls_stream, ix->cls_event[1], 0));
+      gq::BatchView be = b;
+      be.read_begin = 0;
+      be.read_end = chunks[i].r1;
+      gq::launch_classify(ix->dv, be, o, nullptr, 0, ix->cls_stream);
+      CUDA_OK(cudaEventRecord(ix->cls_event[2], ix->cls_stream));
+      ++launches;
+    }
   }
   if (two_streams) {
     CUDA_OK(cudaEventRecord(ix->aux_event, ix->aux_stream));
     CUDA_OK(cudaStreamWaitEvent(st, ix->aux_event, 0));
   }
-  if (chunks.size() > 1) gq::launch_classify(ix->dv, b, o, nullptr, 0, st);
+  if (chunks.size() > 1) {
+    gq::BatchView bl = b;
+    if (early_upto != SIZE_MAX) {
+      bl.read_begin = chunks[early_upto].r1;
+      CUDA_OK(cudaStreamWaitEvent(st, ix->cls_event[2], 0));
+    }
+    gq::launch_classify(ix->dv, bl, o, nullptr, 0, st);
+  }
   // the batch's five counters, committed to the totals on the device unless a strand overflowed (then they are
   // counted again after the re-runs); everything the host needs comes back in ONE pinned copy, one synchronisation
   CUDA_OK(cudaMemsetAsync(ix->stats_batch.p, 0, 40, st));
@@ -454,6 +484,9 @@ static void do_map(gq_index* ix, const HostBatch* hb = nullptr) {
       float ms_cov = 0;
       cudaEventElapsedTime(&ms_cov, ix->overlap_classify ? ix->ev[1] : ix->kev[5], ix->kev[6]);
       ix->kernel_ms[5] = ms_cov;
+      float ms_rc = 0;  // revcomp: from the start of the call's device work to the seed kernel
+      cudaEventElapsedTime(&ms_rc, ix->ev[0], ix->kev[0]);
+      ix->kernel_ms[6] = ms_rc;
     }
   }
   // list-mode re-runs below hand out work from counter slot [9] and append to the (already consumed)
@@ -692,6 +725,7 @@ int gq_index_destroy(gq_index* ix) {
   ix->offsets.release();
   ix->word_off.release();
   ix->packed.release();
+  ix->packed_rc.release();
   ix->len.release();
   ix->seeds.release();
   ix->status.release();
@@ -719,6 +753,9 @@ int gq_index_destroy(gq_index* ix) {
   if (ix->copy_stream) cudaStreamDestroy(ix->copy_stream);
   if (ix->aux_stream) cudaStreamDestroy(ix->aux_stream);
   if (ix->aux_event) cudaEventDestroy(ix->aux_event);
+  if (ix->cls_stream) cudaStreamDestroy(ix->cls_stream);
+  for (auto e : ix->cls_event)
+    if (e) cudaEventDestroy(e);
   ix->arena2.release();
   if (ix->fetch_host) cudaFreeHost(ix->fetch_host);
   ix->fetch_dev.release();
@@ -899,6 +936,7 @@ int gq_map_batch_packed(gq_index* ix, const uint32_t* packed, const uint32_t* wo
   const uint64_t total_words = n_reads ? word_off[n_reads] : 0;
   ix->word_off.reserve(n_reads + 1);
   ix->packed.reserve(total_words + 2);
+  ix->packed_rc.reserve(total_words + 2);
   ix->len.reserve(n_reads);
   ix->seeds.reserve(n_reads);
   ix->n_reads = (uint32_t)n_reads;
@@ -1290,6 +1328,8 @@ int gq_set_option(gq_index* ix, const char* name, int64_t value) {
     ix->overlap_classify = value != 0;
   } else if (n == "resident_slices") {
     ix->resident_slices = (uint32_t)std::max<int64_t>(value, 1);
+  } else if (n == "early_classify") {
+    ix->early_classify = value != 0;
   } else if (n == "tail_chunk_reads") {
     ix->tail_chunk_reads = (uint32_t)std::max<int64_t>(value, 1024);
   } else if (n == "chunk_reads") {

@@ -149,8 +149,6 @@ struct IndexView {
   // k-mer index
   uint32_t k;
   const uint32_t* kmer_bits;   // 4^k bits: k-mer has >= 1 state
-  const uint32_t* kmer_bits_rc;  // the same set indexed by the code of the reverse complement (reverse strands
-                               // test the stored read's windows as they are)
   const uint32_t* kmer_off;    // 4^k + 1
   const KmerState* kmer_states;
   const uint32_t* seed_off;    // 4^k * seed_buckets(k) + 1

@@ -122,45 +122,47 @@ GQ_DEV inline uint32_t pair_reverse32(uint32_t x) {
   return ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);  // bit reversal, then un-swap inside each pair
 }
 
-// Strand cursor over the 2-bit packed read: the bases of the strand (forward, or reverse complement of
-// the stored read; reverse_complement_read, quasimap.cpp:273-298) are consumed right to left. `cw` is a
-// 64-bit shift register holding the next `left` bases, the next one in its top two bits — for the reverse
-// strand each packed word is complemented and pair-reversed as it is loaded, so peek/advance are identical
-// for both strands. The register is topped up with the following word whenever it holds 16 bases or fewer,
-// so (while the strand has that many left) at least 16 bases are always available to a text step.
+// Word `m` of the reverse complement of a packed read of L bases (reverse_complement_read,
+// quasimap.cpp:273-298): base j of the reverse strand = complement of base L-1-j, stored where a read keeps its
+// base j. revcomp_kernel builds the reverse strands of a batch slice once, so every later pass treats an odd
+// strand exactly like an even one — no per-word complement/reversal in the walks.
+GQ_DEV inline uint32_t revcomp_word(const uint32_t* w, uint32_t L, uint32_t m) {
+  const uint32_t s_hi = L - 1u - 16u * m;  // source base of the word's first base
+  const uint32_t wi = s_hi >> 4, q = s_hi & 15u;
+  // sources s_hi, s_hi-1, ... from the top bit pair down
+  const uint32_t hi = GQ_LDG(w + wi), lo = (wi && q < 15u) ? GQ_LDG(w + wi - 1) : 0u;
+  const uint32_t x = q == 15u ? hi : ((hi << (2 * (15u - q))) | (lo >> (2 * (q + 1u))));
+  const uint32_t c = L - 16u * m;  // bases in this word (>= 1)
+  const uint32_t y = pair_reverse32(~x);
+  return c >= 16u ? y : (y & ((1u << (2 * c)) - 1u));
+}
+
+// Strand cursor over the 2-bit packed strand (the read, or its prepared reverse complement): the bases are
+// consumed right to left (backward search). `cw` is a 64-bit shift register holding the next `left` bases, the
+// next one in its top two bits. The register is topped up with the preceding word whenever it holds 16 bases or
+// fewer, so (while the strand has that many left) at least 16 bases are always available to a text step.
 struct ReadCursor {
   const uint32_t* w;
   uint32_t L;
-  uint32_t rc;
   uint64_t cw;
   uint32_t left, wi;
-  GQ_DEV inline uint32_t word_at(uint32_t i) const {  // branch-free: both strands run the same instructions
-    const uint32_t x = GQ_LDG(w + i) ^ (0u - rc);
-    const uint32_t y = pair_reverse32(x);
-    return rc ? y : x;
-  }
+  uint32_t nw;  // the word the next refill shifts in, loaded one refill ahead (its L1 latency is off the walk's chain)
   GQ_DEV inline void refill() {
-    const uint32_t last = rc ? ((L + 15) >> 4) - 1u : 0u;
-    if (left <= 16 && wi != last) {
-      wi += rc ? 1u : 0xFFFFFFFFu;
-      cw |= (uint64_t)word_at(wi) << (32 - 2 * left);  // left <= 16: the new 16 bases follow the valid ones
+    if (left <= 16 && wi != 0) {
+      --wi;
+      cw |= (uint64_t)nw << (32 - 2 * left);  // left <= 16: the new 16 bases follow the valid ones
       left += 16;
+      nw = wi ? GQ_LDG(w + wi - 1) : 0u;
     }
   }
-  // position the cursor so that peek() returns the base at logical index pos-1 (pos >= 1)
+  // position the cursor so that peek() returns the base at index pos-1 (pos >= 1)
   GQ_DEV inline void seek(uint32_t pos) {
     const uint32_t i = pos - 1;
-    const uint32_t p = rc ? (L - 1 - i) : i;
-    wi = p >> 4;
-    const uint32_t q = p & 15u;
-    const uint32_t word = word_at(wi);
-    if (rc) {
-      cw = (uint64_t)(word << (2 * q)) << 32;
-      left = 16 - q;
-    } else {
-      cw = (uint64_t)(word << (2 * (15 - q))) << 32;
-      left = q + 1;
-    }
+    wi = i >> 4;
+    const uint32_t q = i & 15u;
+    cw = (uint64_t)(GQ_LDG(w + wi) << (2 * (15 - q))) << 32;
+    nw = wi ? GQ_LDG(w + wi - 1) : 0u;
+    left = q + 1;
     refill();
   }
   GQ_DEV inline uint32_t peek() const { return (uint32_t)(cw >> 62); }
@@ -313,6 +315,13 @@ GQ_DEV inline void lane_load_top(Lane& ln) {
 
 constexpr uint32_t kSurvGeneral = 0x10000u;  // SeedOut::surv_cnt flag: the strand is on the general kernel's list
 constexpr uint32_t kSurvListed = 0x20000u;   //  ... the strand is on mapped_list (the coverage work list)
+// bits 18..31 of the same word: candidates of the strand that passed the verify pass (verify_kernel adds one per
+// survivor, fire and forget). A finished candidate that is its strand's ONLY verified one needs no claim — no other
+// candidate of the strand can finish — which spares the common case an atomic round trip. The 14-bit count cannot
+// wrap: strands with kMaxSeedEntries seed entries or more (<= 32 candidates each) take the general kernel.
+constexpr uint32_t kSurvVerifiedShift = 18;
+constexpr uint32_t kSurvVerifiedOne = 1u << kSurvVerifiedShift;
+constexpr uint32_t kMaxSeedEntries = 448;
 
 // append a mapped strand to the coverage work list, once (the text kernel may have listed it already)
 GQ_DEV inline void list_mapped(const SearchOut& o, uint32_t strand) {
@@ -352,6 +361,13 @@ GQ_DEV inline void lane_finish_strand(Lane& ln, const SearchOut& o) {
 }
 
 // Start `strand` on this lane: seed with the index entry of its last k-mer (quasimap.cpp:178,235-241).
+// code of the last k bases of a packed strand (L >= k)
+GQ_DEV inline uint32_t seeding_kmer_code(const uint32_t* w, uint32_t L, uint32_t k) {
+  const uint32_t j0 = L - k, wi = j0 >> 4, n_words = (L + 15) >> 4;
+  const uint32_t wlo = GQ_LDG(w + wi), whi = (wi + 1 < n_words) ? GQ_LDG(w + wi + 1) : 0u;
+  return gq_funnelshift_r(wlo, whi, 2 * (j0 & 15u)) & ((k == 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u));
+}
+
 GQ_DEV inline void lane_refill(Lane& ln, const IndexView& v, const BatchView& b, const SearchOut& o, uint32_t strand,
                                uint32_t* arena, uint32_t arena_words) {
   const uint32_t r = strand >> 1;
@@ -367,18 +383,10 @@ GQ_DEV inline void lane_refill(Lane& ln, const IndexView& v, const BatchView& b,
     GQ_AT(o.status, strand) = ST_MISSING_KMER;
     return;
   }
-  ln.rd = ReadCursor{b.packed + GQ_AT(b.word_off, r), L, strand & 1u, 0, 0, 0};
+  ln.rd = ReadCursor{b.strand_words(strand, GQ_AT(b.word_off, r)), L, 0, 0, 0, 0};
   // seeding k-mer = last k bases of the strand; its code (base j at bits [2j,2j+2)) is a bit-field of the
-  // packed read: the last k pairs for the forward strand, the pair-reversed complement of the first k
-  // pairs for the reverse strand
-  uint32_t code;
-  if (ln.rd.rc) {
-    code = pair_reverse32(~GQ_LDG(ln.rd.w)) >> (32 - 2 * k);
-  } else {
-    const uint32_t j0 = L - k, wi = j0 >> 4, n_words = (L + 15) >> 4;
-    const uint32_t wlo = GQ_LDG(ln.rd.w + wi), whi = (wi + 1 < n_words) ? GQ_LDG(ln.rd.w + wi + 1) : 0u;
-    code = gq_funnelshift_r(wlo, whi, 2 * (j0 & 15u)) & ((k == 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u));
-  }
+  // packed strand
+  const uint32_t code = seeding_kmer_code(ln.rd.w, L, k);
   uint32_t sb = GQ_LDG(v.kmer_off + code), se = GQ_LDG(v.kmer_off + code + 1);
   if (sb == se) {  // the seeding k-mer itself is not indexed: the k-mer filter fails
     GQ_AT(o.status, strand) = ST_MISSING_KMER;
@@ -737,18 +745,11 @@ GQ_DEV inline uint32_t preseed_lookup(const IndexView& v, const BatchView& b, co
     GQ_AT(o.status, strand) = ST_MISSING_KMER;
     return 0;
   }
-  const uint32_t* w = b.packed + GQ_AT(b.word_off, r);
-  uint32_t code;
-  if (strand & 1u) {
-    code = pair_reverse32(~GQ_LDG(w)) >> (32 - 2 * k);
-  } else {
-    const uint32_t j0 = L - k, wi = j0 >> 4, n_words = (L + 15) >> 4;
-    const uint32_t wlo = GQ_LDG(w + wi), whi = (wi + 1 < n_words) ? GQ_LDG(w + wi + 1) : 0u;
-    code = gq_funnelshift_r(wlo, whi, 2 * (j0 & 15u)) & ((k == 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u));
-  }
+  const uint32_t* w = b.strand_words(strand, GQ_AT(b.word_off, r));
+  const uint32_t code = seeding_kmer_code(w, L, k);
   out.pos0 = L - k;
   if (out.pos0) {
-    ReadCursor rd{w, L, strand & 1u, 0, 0, 0};
+    ReadCursor rd{w, L, 0, 0, 0, 0};
     rd.seek(out.pos0);
     out.ctx = rd.top32() >> 8;
   }
@@ -799,14 +800,14 @@ struct SeedPlan {
 };
 
 template <class SuperPtr>
-GQ_DEV inline uint32_t seed_state_plan(const IndexView& v, SuperPtr super_c, const uint32_t* w, uint32_t L, uint32_t rc,
+GQ_DEV inline uint32_t seed_state_plan(const IndexView& v, SuperPtr super_c, const uint32_t* w, uint32_t L,
                                        uint32_t lo, uint32_t hi, SeedPlan& plan) {
   plan.n = 0;
   const uint32_t pos0 = L - v.k;
   uint32_t w0 = pos0 | (K_SCAN << 28), total = 0;
   if (hi - lo >= kNarrowWidth) {
     Lane ln;
-    ln.rd = ReadCursor{w, L, rc, 0, 0, 0};
+    ln.rd = ReadCursor{w, L, 0, 0, 0, 0};
     ln.pos = pos0;
     ln.lo = lo;
     ln.hi = hi;
@@ -868,10 +869,10 @@ struct SeedCands {
   uint32_t p[kMaxCand], w0[kMaxCand];
 };
 
-GQ_DEV inline uint32_t seed_filter(const IndexView& v, const SeedPlan& plan, const uint32_t* w, uint32_t L, uint32_t rc,
+GQ_DEV inline uint32_t seed_filter(const IndexView& v, const SeedPlan& plan, const uint32_t* w, uint32_t L,
                                    SeedCands& out) {
   uint32_t n = 0, cur_pos = 0;
-  ReadCursor rd{w, L, rc, 0, 0, 0};
+  ReadCursor rd{w, L, 0, 0, 0, 0};
   for (uint32_t e = 0; e < plan.n; ++e) {
     const uint32_t w0 = plan.w0[e], pos = w0 & 0x0FFFFFFFu;
     if (pos != cur_pos) {  // entries of one seed state share a few read positions
@@ -901,7 +902,7 @@ GQ_DEV inline uint32_t seed_filter(const IndexView& v, const SeedPlan& plan, con
 // parts 2 + 3 for seed entry j. The common case — a suffix of a narrow state — is decided from its 8-byte
 // entry alone: text position + left context (KmerSeed), compared with the next read bases in registers.
 template <class SuperPtr>
-GQ_DEV inline uint32_t seed_state_cands(const IndexView& v, SuperPtr super_c, const uint32_t* w, uint32_t L, uint32_t rc,
+GQ_DEV inline uint32_t seed_state_cands(const IndexView& v, SuperPtr super_c, const uint32_t* w, uint32_t L,
                                         uint32_t j, SeedCands& out) {
   const uint32_t pos0 = L - v.k;
   if (pos0 == 0) {  // the seed states are the final states
@@ -918,7 +919,7 @@ GQ_DEV inline uint32_t seed_state_cands(const IndexView& v, SuperPtr super_c, co
     uint32_t m = (aux >> 24) & 0x7Fu;  // context bases, up to the first marker / the text start
     m = m < pos0 ? m : pos0;
     if (m) {
-      ReadCursor rd{w, L, rc, 0, 0, 0};
+      ReadCursor rd{w, L, 0, 0, 0, 0};
       rd.seek(pos0);
       const uint32_t x = ((rd.top32() >> 8) ^ aux) & ((0xFFFFFFFFu << (24 - 2 * m)) & 0xFFFFFFu);
       if (x) return 0;  // another occurrence of the k-mer: the read continues differently
@@ -929,8 +930,8 @@ GQ_DEV inline uint32_t seed_state_cands(const IndexView& v, SuperPtr super_c, co
     return 1;
   }
   SeedPlan plan;
-  const uint32_t cnt = seed_state_plan(v, super_c, w, L, rc, key, aux, plan);
-  return cnt == kNoAllele ? cnt : seed_filter(v, plan, w, L, rc, out);
+  const uint32_t cnt = seed_state_plan(v, super_c, w, L, key, aux, plan);
+  return cnt == kNoAllele ? cnt : seed_filter(v, plan, w, L, out);
 }
 
 // candidate record: 4 words {strand, k-mer state index, text position, pos | kind << 28}
@@ -965,6 +966,7 @@ struct FastLane {
   uint32_t path_off;     // ... in kmer_paths
   uint32_t T[2 * kFastT], G[kFastG];
   uint32_t result;  // FAST_NONE while running
+  uint32_t flags0;  // the strand's surv_cnt word when the walk began (text kernel: verified count, general flag)
   bool p_valid;     // ln.p is the text position of the current suffix
 };
 
@@ -990,13 +992,15 @@ GQ_DEV inline void fast_begin(FastLane& f, const IndexView& v, const BatchView& 
   f.p_valid = true;
   f.nt = f.ng = 0;
   f.nt0 = f.ng0 = f.path_off = 0;
+  f.flags0 = 0;
   if (TRACK) {
+    f.flags0 = GQ_AT(pre.surv_cnt, strand);
     const KmerState ks = GQ_AT(v.kmer_states, j);
     f.nt0 = ks.counts & 0xFFFFu;
     f.ng0 = ks.counts >> 16;
     f.path_off = ks.path_off;
   }
-  f.ln.rd = ReadCursor{b.packed + woff, L, strand & 1u, 0, 0, 0};
+  f.ln.rd = ReadCursor{b.strand_words(strand, woff), L, 0, 0, 0, 0};
   f.ln.pos = w0 & 0x0FFFFFFFu;
   f.ln.kind = w0 >> 28;
   f.ln.p = p;
@@ -1431,7 +1435,8 @@ GQ_DEV inline void fast_emit(const FastLane& f, const IndexView& v, const Search
 
 // a finished candidate claims its strand: 0 = first one (emit), otherwise the strand is (or becomes) the
 // general kernel's
-GQ_DEV inline bool fast_claim(const SeedOut& pre, uint32_t strand) {
+GQ_DEV inline bool fast_claim(const SeedOut& pre, uint32_t strand, uint32_t flags_at_begin) {
+  if ((flags_at_begin >> kSurvVerifiedShift) == 1u) return !(flags_at_begin & kSurvGeneral);  // the only verified candidate
   const uint32_t old = gq_atomic_add(pre.surv_cnt + strand, 1u);
   if (old & kSurvGeneral) return false;
   if (old & 0xFFFFu) {
@@ -1446,22 +1451,18 @@ GQ_DEV inline bool fast_claim(const SeedOut& pre, uint32_t strand) {
 // any k-mer absent from the index -> missing_kmer, else no_extension (quasimap.cpp:170-186).
 // The k-mer code convention (base j at bits [2j,2j+2)) makes the code of the window starting at base i
 // a plain bit-field of the 2-bit packed read, so the loop slides a 64-bit window by one base per
-// iteration. The reverse strand holds exactly the reverse complements of the forward windows
-// (complement = bitwise NOT of the 2-bit code, reversal = pair-reversal), and "any k-mer missing"
-// does not depend on the order in which windows are visited.
+// iteration ("any k-mer missing" does not depend on the order in which windows are visited).
 GQ_DEV inline void classify_strand(const IndexView& v, const BatchView& b, const SearchOut& o, uint32_t strand) {
   const uint32_t r = strand >> 1;
   const uint32_t L = GQ_AT(b.len, r), k = v.k;
-  const uint32_t* w = b.packed + GQ_AT(b.word_off, r);
-  const bool rc = (strand & 1u) != 0;
+  const uint32_t* w = b.strand_words(strand, GQ_AT(b.word_off, r));
   const uint32_t mask = (k == 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
   const uint32_t n_words = (L + 15) >> 4;
   uint64_t win = GQ_LDG(w);
   if (n_words > 1) win |= (uint64_t)GQ_LDG(w + 1) << 32;
   bool missing = false;
   for (uint32_t i = 0; i + k <= L; ++i) {
-    uint32_t code = (uint32_t)win & mask;
-    if (rc) code = pair_reverse32(~(uint32_t)win) >> (32 - 2 * k);
+    const uint32_t code = (uint32_t)win & mask;
     if (!((GQ_LDG(v.kmer_bits + (code >> 5)) >> (code & 31u)) & 1u)) {
       missing = true;
       break;
@@ -1493,29 +1494,38 @@ GQ_DEV inline void map_strand(const IndexView& v, const uint32_t* super_cnt, con
     const uint32_t r = strand >> 1;
     for (uint32_t t = 0; t < ns && !general; ++t) {
       SeedCands cands;
-      const uint32_t cnt = seed_state_cands(v, super_cnt, b.packed + GQ_AT(b.word_off, r), GQ_AT(b.len, r), strand & 1u, lk.entry(t), cands);
+      const uint32_t cnt = seed_state_cands(v, super_cnt, b.strand_words(strand, GQ_AT(b.word_off, r)), GQ_AT(b.len, r), lk.entry(t), cands);
       if (cnt == kNoAllele || total + cnt > pre.cap) general = true;
       else {
         seed_write(cands, cnt, pre, strand, GQ_AT(v.seed_state, lk.entry(t)), total);
         total += cnt;
       }
     }
+    if (!general && ns >= kMaxSeedEntries) general = true;  // (seed_kernel: bounds the verified-candidate count)
     if (!general) {
+      // verify pass over all candidates of the strand first (verify_kernel: survivors counted in the strand's flag
+      // word), then the full walks from the start (text_kernel)
       for (uint32_t i = 0; i < total; ++i) {
         FastLane f;
         GQ_PHASE(1);  // verify_kernel
         fast_begin<false>(f, v, b, pre, i);
-        {  // verify pass (verify_kernel), then the full walk from the start (text_kernel)
-          const uint32_t pos0 = f.ln.pos;
-          for (uint32_t it = 0; it < kVerifyIters && !fast_verified(f, pos0); ++it) {
-            if (f.ln.state == LS_TEXT) lane_text_step(f.ln, v);
-            if (fast_running(f) && f.ln.state == LS_EV_TSCAN) fast_event<false>(f, v);
-          }
-          if (!fast_alive(f)) continue;
-          GQ_TOUCH(pre.rec + 4 * (size_t)i, 16);  // the survivor is copied to the text kernel's list
-          GQ_PHASE(2);                            // text_kernel
-          fast_begin<true>(f, v, b, pre, i);
+        const uint32_t pos0 = f.ln.pos;
+        for (uint32_t it = 0; it < kVerifyIters && !fast_verified(f, pos0); ++it) {
+          if (f.ln.state == LS_TEXT) lane_text_step(f.ln, v);
+          if (fast_running(f) && f.ln.state == LS_EV_TSCAN) fast_event<false>(f, v);
         }
+        if (!fast_alive(f)) {
+          pre.rec[4 * (size_t)i] = kNoAllele;  // (the kernel compacts the survivors instead)
+          continue;
+        }
+        GQ_TOUCH(pre.rec + 4 * (size_t)i, 16);  // the survivor is copied to the text kernel's list
+        gq_red_add(pre.surv_cnt + strand, kSurvVerifiedOne);
+      }
+      for (uint32_t i = 0; i < total; ++i) {
+        if (pre.rec[4 * (size_t)i] == kNoAllele) continue;
+        FastLane f;
+        GQ_PHASE(2);  // text_kernel
+        fast_begin<true>(f, v, b, pre, i);
         if (v.any_nested) {  // text_kernel<true>: branching walks
           FastForks fk;
           forks_init(fk, true);
@@ -1532,7 +1542,7 @@ GQ_DEV inline void map_strand(const IndexView& v, const uint32_t* super_cnt, con
         }
         const uint32_t words = fast_outcome(f, v);
         if (f.result == FAST_MAPPED) {
-          if (!fast_claim(pre, strand)) continue;
+          if (!fast_claim(pre, strand, f.flags0)) continue;
           const uint32_t off = gq_atomic_add(o.pool_used, words);
           if (off + words > o.pool_cap) {
             GQ_AT(o.status, strand) = ST_OVERFLOW;

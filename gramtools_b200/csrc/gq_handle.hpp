@@ -57,7 +57,7 @@ struct gq_index {
   // batch
   DevBuf<uint8_t> bases;
   DevBuf<uint64_t> offsets;
-  DevBuf<uint32_t> word_off, packed, len, seeds;
+  DevBuf<uint32_t> word_off, packed, packed_rc, len, seeds;
   uint32_t n_reads = 0;
   uint32_t total_words = 0;
   // search outputs
@@ -71,6 +71,9 @@ struct gq_index {
   cudaStream_t copy_stream = nullptr;
   cudaStream_t aux_stream = nullptr;  // second compute stream of the pipelined path
   cudaEvent_t aux_event = nullptr;
+  cudaStream_t cls_stream = nullptr;  // early k-mer filter of the pipelined path (beside the later slices)
+  cudaEvent_t cls_event[3] = {nullptr, nullptr, nullptr};
+  uint32_t early_classify = 1;
   DevBuf<uint32_t> arena2;
   void* fetch_host = nullptr;  // pinned staging of gq_coverage_fetch
   size_t fetch_host_bytes = 0;

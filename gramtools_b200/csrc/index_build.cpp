@@ -44,7 +44,6 @@ IndexView HostIndex::view() const {
   v.apos = apos.data();
   v.k = k;
   v.kmer_bits = kmer_bits.data();
-  v.kmer_bits_rc = kmer_bits_rc.data();
   v.kmer_off = kmer_off.data();
   v.kmer_states = kmer_states.data();
   v.seed_off = seed_off.data();
@@ -322,8 +321,8 @@ void build_fm(HostIndex& ix, const std::vector<uint32_t>& hit_marker, const std:
     for (uint32_t i = 0; i + 1 < n; ++i) text[i] = tab[prg[i]];
     text[n - 1] = 0;
   }
-  std::vector<int32_t> sa = suffix_array(text, sigma);
-  ix.sa.assign(sa.begin(), sa.end());
+  // 32-bit SA-IS below 2^31 symbols, 64-bit indices inside above (GQ_SAIS64=1 forces the latter: tests)
+  ix.sa = suffix_array_u32(text, sigma, std::getenv("GQ_SAIS64") != nullptr);
   // C array
   std::vector<uint32_t> C(sigma + 1, 0);
   for (uint32_t i = 0; i < n; ++i) C[text[i] + 1]++;
@@ -612,13 +611,17 @@ void build_kmers(HostIndex& ix) {
   // merge into CSR ordered by k-mer code
   for (auto& o : outs)
     for (size_t i = 0; i < o.codes.size(); ++i) ix.kmer_off[o.codes[i] + 1] += o.n_states[i];
+  uint64_t n_states_total = 0;
   for (uint64_t c = 0; c < nk; ++c) {
     if (ix.kmer_off[c + 1]) ix.kmer_bits[c >> 5] |= 1u << (c & 31);
+    n_states_total += ix.kmer_off[c + 1];
     ix.kmer_off[c + 1] += ix.kmer_off[c];
   }
+  if (n_states_total >= 0xFFFFFFFFull) throw std::runtime_error("k-mer index exceeds 2^32 states; use a larger kmer_size");
   ix.kmer_states.assign(ix.kmer_off[nk], KmerState{});
   size_t total_paths = 0;
   for (auto& o : outs) total_paths += o.paths.size();
+  if (total_paths >= 0xFFFFFFFFull) throw std::runtime_error("k-mer index paths exceed 2^32 words");
   ix.kmer_paths.clear();
   ix.kmer_paths.reserve(total_paths + 1);
   for (auto& o : outs) {
@@ -636,14 +639,6 @@ void build_kmers(HostIndex& ix) {
   }
   if (ix.kmer_paths.empty()) ix.kmer_paths.push_back(0);
   if (ix.kmer_states.empty()) ix.kmer_states.push_back(KmerState{});
-  // presence set indexed by the reverse complement's code: bits_rc[c] = bits[revcomp_k(c)]
-  ix.kmer_bits_rc.assign(ix.kmer_bits.size(), 0);
-  for (uint64_t c = 0; c < nk; ++c) {
-    if (!((ix.kmer_bits[c >> 5] >> (c & 31)) & 1u)) continue;
-    uint64_t r = 0, x = ~c;
-    for (uint32_t i = 0; i < k; ++i) r |= ((x >> (2 * i)) & 3ull) << (2 * (k - 1 - i));
-    ix.kmer_bits_rc[r >> 5] |= 1u << (r & 31);
-  }
   // seed-pass view: per k-mer one entry per suffix of its narrow states (text position + left context), one
   // entry per wide state; bucketed by the first d context bases (gq_core.cuh, KmerSeed)
   const uint32_t d = seed_bucket_bases(k), B = seed_buckets(k);
@@ -676,7 +671,12 @@ void build_kmers(HostIndex& ix) {
       }
     }
   }
-  for (uint64_t t = 0; t < nk * B; ++t) ix.seed_off[t + 1] += ix.seed_off[t];
+  uint64_t n_seed_total = 0;
+  for (uint64_t t = 0; t < nk * B; ++t) {
+    n_seed_total += ix.seed_off[t + 1];
+    ix.seed_off[t + 1] += ix.seed_off[t];
+  }
+  if (n_seed_total >= 0xFFFFFFFFull) throw std::runtime_error("seed view exceeds 2^32 entries; use a larger kmer_size");
   ix.seed_ent.assign(std::max<size_t>(ix.seed_off[nk * B], 1), KmerSeed{0, 0});
   ix.seed_state.assign(std::max<size_t>(ix.seed_off[nk * B], 1), 0);
 #pragma omp parallel for schedule(dynamic, 4096)
@@ -704,7 +704,8 @@ void build_kmers(HostIndex& ix) {
 
 void build_host_index(const uint32_t* prg, uint64_t n_symbols, uint32_t kmer_size, HostIndex& ix) {
   if (n_symbols == 0) throw std::runtime_error("empty PRG");
-  if (n_symbols >= (1ull << 31) - 2) throw std::runtime_error("PRG too long for 32-bit suffix indices");
+  // positions, SA indices and marker ranks are unsigned 32-bit words on the device, 0xFFFFFFFF is "none"
+  if (n_symbols >= (1ull << 32) - 3) throw std::runtime_error("PRG too long: text positions are 32-bit words (max 2^32 - 4 symbols)");
   ix = HostIndex{};
   ix.k = kmer_size;
   ix.prg.assign(prg, prg + n_symbols);

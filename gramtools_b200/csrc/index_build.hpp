@@ -47,7 +47,7 @@ struct HostIndex {
   // site-end marker), so allele a spans [apos[a], apos[a + 1] - 1)
   std::vector<uint32_t> site_rec, apos;
   // k-mer index
-  std::vector<uint32_t> kmer_bits, kmer_bits_rc, kmer_off, kmer_paths;
+  std::vector<uint32_t> kmer_bits, kmer_off, kmer_paths;
   std::vector<KmerState> kmer_states;
   std::vector<uint32_t> seed_off, seed_state;  // seed-pass view (KmerSeed)
   std::vector<KmerSeed> seed_ent;

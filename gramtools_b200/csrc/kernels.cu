@@ -58,6 +58,34 @@ void launch_pack(const uint8_t* bases, const uint64_t* offsets, uint32_t r0, uin
   pack_kernel<<<blocks, 256, 0, st>>>(bases, offsets, r0, r1, word_off, packed, len);
 }
 
+// Reverse strands of a slice, once per batch: a thread per read, eight output words per round with all their source
+// loads issued together (the pass is a dependent chain len/word_off -> words -> store per read, so what it needs is
+// loads in flight, not threads). Every later kernel walks an odd strand through packed_rc with the code of an
+// even one.
+__global__ void __launch_bounds__(256)
+    revcomp_kernel(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ word_off,
+                   const uint32_t* __restrict__ len, uint32_t r0, uint32_t r1, uint32_t* __restrict__ packed_rc) {
+  const uint32_t r = r0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= r1) return;
+  const uint32_t L = __ldg(len + r), woff = __ldg(word_off + r), nw = (L + 15) >> 4;
+  const uint32_t* w = packed + woff;
+  uint32_t* out = packed_rc + woff;
+  for (uint32_t m0 = 0; m0 < nw; m0 += 8) {
+    uint32_t y[8];
+#pragma unroll
+    for (uint32_t j = 0; j < 8; ++j) y[j] = m0 + j < nw ? revcomp_word(w, L, m0 + j) : 0u;
+#pragma unroll
+    for (uint32_t j = 0; j < 8; ++j)
+      if (m0 + j < nw) out[m0 + j] = y[j];
+  }
+}
+
+void launch_revcomp(const BatchView& b, uint32_t* packed_rc, cudaStream_t st) {
+  if (b.read_end <= b.read_begin) return;
+  const uint32_t blocks = (b.read_end - b.read_begin + 255) / 256;
+  revcomp_kernel<<<blocks, 256, 0, st>>>(b.packed, b.word_off, b.len, b.read_begin, b.read_end, packed_rc);
+}
+
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_stage_super(uint32_t* s_super, const uint32_t* g_super, uint32_t bytes,
                                                 uint64_t* bar) {
@@ -182,7 +210,9 @@ __global__ void __launch_bounds__(256)
     SeedLookup lk;
     lk.classified = true;
     lk.s0 = lk.n0 = lk.s1 = lk.n1 = lk.pos0 = lk.ctx = 0;
-    const uint32_t ns = i < n ? preseed_lookup(v, b, o, strand, lk) : 0;
+    uint32_t ns = i < n ? preseed_lookup(v, b, o, strand, lk) : 0;
+    const bool too_many = ns >= kMaxSeedEntries;  // bounds the strand's candidates (kSurvVerifiedShift): general kernel
+    if (too_many) ns = 0;
     uint32_t my_L = 0, my_woff = 0;
     if (!lk.classified) {
       o.status[strand] = ST_UNCLASSIFIED;  // until a candidate finishes or the general kernel decides
@@ -195,11 +225,11 @@ __global__ void __launch_bounds__(256)
     const uint32_t my_pos0 = lk.pos0, my_ctx = lk.ctx;
     // one seed entry: a suffix entry is accepted or rejected from its 8 bytes and the owner strand's context; only
     // a wide state (more than kSplitWidth suffixes) takes the narrowing path
-    auto examine = [&](uint32_t e, uint32_t o_pos0, uint32_t o_ctx, uint32_t o_woff, uint32_t o_L, uint32_t o_rc,
+    auto examine = [&](uint32_t e, uint32_t o_pos0, uint32_t o_ctx, uint32_t o_woff, uint32_t o_L, uint32_t o_strand,
                        SeedCands& cands) -> uint32_t {
       if (o_pos0 == 0) return kNoAllele;  // L == k: the seed states are the final states (general kernel)
       const uint2 raw = __ldg(reinterpret_cast<const uint2*>(v.seed_ent) + e);
-      if (!(raw.y & 0x80000000u)) return seed_state_cands(v, super_c, b.packed + o_woff, o_L, o_rc, e, cands);
+      if (!(raw.y & 0x80000000u)) return seed_state_cands(v, super_c, b.strand_words(o_strand, o_woff), o_L, e, cands);
       uint32_t m = (raw.y >> 24) & 0x7Fu;
       m = m < o_pos0 ? m : o_pos0;
       if (m && (((o_ctx ^ raw.y) & ((0xFFFFFFFFu << (24 - 2 * m)) & 0xFFFFFFu)) != 0)) return 0;
@@ -238,7 +268,7 @@ __global__ void __launch_bounds__(256)
         const uint32_t e = te < o_n0 ? o_s0 + te : o_s1 + (te - o_n0);
         SeedCands cands;
         uint32_t cnt = 0;
-        if (t < total) cnt = examine(e, o_pos0, o_ctx, o_woff, o_L, o_strand & 1u, cands);
+        if (t < total) cnt = examine(e, o_pos0, o_ctx, o_woff, o_L, o_strand, cands);
         const bool bad = cnt == kNoAllele;
         general |= __reduce_or_sync(full, bad ? (1u << owner) : 0u);
         seed_push(stage, pre, v, cands, bad ? 0u : cnt, o_strand, e, lane);
@@ -257,14 +287,14 @@ __global__ void __launch_bounds__(256)
           const uint32_t e = te < o_n0 ? o_s0 + te : o_s1 + (te - o_n0);
           SeedCands cands;
           uint32_t cnt = 0;
-          if (c0 + lane < o_ns) cnt = examine(e, o_pos0, o_ctx, o_woff, o_L, o_strand & 1u, cands);
+          if (c0 + lane < o_ns) cnt = examine(e, o_pos0, o_ctx, o_woff, o_L, o_strand, cands);
           const bool bad = cnt == kNoAllele;
           if (__any_sync(full, bad)) general |= 1u << owner;
           seed_push(stage, pre, v, cands, bad ? 0u : cnt, o_strand, e, lane);
         }
       }
     }
-    if ((general >> lane) & 1u) send_to_general(pre, strand);
+    if (((general >> lane) & 1u) || too_many) send_to_general(pre, strand);
   }
   seed_flush(stage, pre, lane);
 }
@@ -272,7 +302,8 @@ __global__ void __launch_bounds__(256)
 void launch_seed(const IndexView& v, const BatchView& b, const SearchOut& o, const SeedOut& pre, cudaStream_t st) {
   uint32_t work = 2 * (b.read_end - b.read_begin);
   if (work == 0) return;
-  uint32_t blocks = min((work + 255) / 256, 148u * 8u);
+  static const int smode = getenv("GQ_SEED_GRID") ? atoi(getenv("GQ_SEED_GRID")) : 0;
+  uint32_t blocks = smode ? (work + 255) / 256 : min((work + 255) / 256, 148u * 8u);
   uint32_t n_super = (v.n >> kSuperShift) + 1;
   if (n_super <= (uint32_t)kMaxSuperSmem)
     seed_kernel<true><<<blocks, 256, n_super * 16, st>>>(v, b, o, pre, n_super);
@@ -307,6 +338,7 @@ __global__ void __launch_bounds__(256) verify_kernel(IndexView v, BatchView b, S
       if (!fast_verified(f, pos0) && f.ln.state == LS_EV_TSCAN) fast_event<false>(f, v);
     }
     const bool alive = rec.x != kNoAllele && fast_alive(f);
+    if (alive) gq_red_add(pre.surv_cnt + rec.x, kSurvVerifiedOne);  // verified candidates of the strand (fast_claim)
     const uint32_t mm = __ballot_sync(full, alive);
     if (pend_mask) {  // flush the previous round
       const uint32_t base = __shfl_sync(full, pend_base, 0);
@@ -359,7 +391,7 @@ __global__ void __launch_bounds__(256) text_kernel(IndexView v, BatchView b, Sea
     // A finished candidate claims its strand; a second one (reads in repeats) makes the strand the general
     // kernel's. Only claim winners take pool space and a mapped-list slot: a strand can have many finished
     // candidates, the list holds one entry per strand.
-    bool emit = f.result == FAST_MAPPED && fast_claim(pre, strand);
+    bool emit = f.result == FAST_MAPPED && fast_claim(pre, strand, f.flags0);
     if (!emit) words = 0;
     uint32_t incl = words;  // pool space for the round: warp scan + one atomic
 #pragma unroll
@@ -368,27 +400,26 @@ __global__ void __launch_bounds__(256) text_kernel(IndexView v, BatchView b, Sea
       if (lane >= (uint32_t)d) incl += t;
     }
     const uint32_t total = __shfl_sync(full, incl, 31);
-    uint32_t base = 0;
+    // pool space and mapped-list slots of the round: two atomics, issued together (one round trip, not two)
+    const uint32_t mm = __ballot_sync(full, emit);
+    uint32_t base = 0, mbase = 0;
     if (total && lane == 31) base = atomicAdd(o.pool_used, total);
+    if (mm && lane == 0) mbase = atomicAdd(o.n_mapped, (uint32_t)__popc(mm));
     base = __shfl_sync(full, base, 31);
+    mbase = __shfl_sync(full, mbase, 0);
     if (emit) {
       const uint32_t off = base + incl - words;
       if (off + words > o.pool_cap) {  // final-state pool full: re-run after the host has grown it
         o.status[strand] = ST_OVERFLOW;
         o.overflow_list[atomicAdd(o.n_overflow, 1u)] = strand;
-        emit = false;
       } else {
         fast_emit(f, v, o, off);
         o.status[strand] = ST_MAPPED;
         atomicOr(pre.surv_cnt + strand, kSurvListed);
       }
-    }
-    const uint32_t mm = __ballot_sync(full, emit);
-    if (mm) {
-      uint32_t mbase = 0;
-      if (lane == 0) mbase = atomicAdd(o.n_mapped, (uint32_t)__popc(mm));
-      mbase = __shfl_sync(full, mbase, 0);
-      if (emit) o.mapped_list[mbase + __popc(mm & ((1u << lane) - 1u))] = strand;
+      // (the slot of an overflowed strand stays in the list: the coverage pass skips entries whose status is not
+      // ST_MAPPED, and the re-run records the strand from its own list)
+      o.mapped_list[mbase + __popc(mm & ((1u << lane) - 1u))] = strand;
     }
   }
 }
@@ -398,13 +429,27 @@ void launch_text(const IndexView& v, const BatchView& b, const SearchOut& o, con
   uint32_t work = 2 * (b.read_end - b.read_begin);
   if (work == 0) return;
   uint32_t blocks = min((work + 255) / 256, 148u * 8u);
-  verify_kernel<<<blocks, 256, 0, st>>>(v, b, pre, surv_rec, n_verified);
+  // one block per 256 (verify) / 128 (text) candidate slots instead of a grid-stride loop over a resident grid: the
+  // block scheduler then hands out the walks dynamically (walk lengths vary; measured 0.073 -> 0.065 and
+  // 0.282 -> 0.259 ms per 1 M reads at config 2); blocks beyond the device-side candidate count exit at once
+  static const int vmode = getenv("GQ_VERIFY_GRID") ? atoi(getenv("GQ_VERIFY_GRID")) : 1;
+  static const int tmode = getenv("GQ_TEXT_GRID") ? atoi(getenv("GQ_TEXT_GRID")) : 2;
+  const uint32_t cand_cap = pre.cap;
+  auto grid_of = [&](int mode, uint32_t& thr) {
+    thr = mode == 2 ? 128u : (mode == 3 ? 64u : 256u);
+    if (mode == 0) return blocks;
+    const uint64_t items = min((uint64_t)cand_cap, (uint64_t)work * 2);  // candidates: a device-side count
+    return (uint32_t)max((uint64_t)1, (items + thr - 1) / thr);
+  };
+  uint32_t vthr, tthr;
+  const uint32_t vblocks = grid_of(vmode, vthr), tblocks = grid_of(tmode, tthr);
+  verify_kernel<<<vblocks, vthr, 0, st>>>(v, b, pre, surv_rec, n_verified);
   if (between) cudaEventRecord(between, st);
   SeedOut ver = pre;  // the text kernel's candidates are the verified ones
   ver.rec = surv_rec;
   ver.n_surv = n_verified;
-  if (v.any_nested) text_kernel<true><<<blocks, 256, 0, st>>>(v, b, o, ver);
-  else text_kernel<false><<<blocks, 256, 0, st>>>(v, b, o, ver);
+  if (v.any_nested) text_kernel<true><<<tblocks, tthr, 0, st>>>(v, b, o, ver);
+  else text_kernel<false><<<tblocks, tthr, 0, st>>>(v, b, o, ver);
 }
 
 #ifdef GQ_DEBUG_COUNTERS
@@ -530,7 +575,7 @@ constexpr uint32_t kClassifySmemBytes = 160 * 1024;
 template <bool SMEM>
 __global__ void __launch_bounds__(SMEM ? 1024 : 256)
     classify_kernel(IndexView v, BatchView b, SearchOut o, const uint32_t* list, uint32_t n_list, uint32_t bits_words,
-                    const uint32_t* __restrict__ g_bits, uint32_t parity) {
+                    const uint32_t* __restrict__ g_bits) {
   extern __shared__ __align__(16) uint32_t s_bits[];
   if (SMEM) {
     const uint4* src = reinterpret_cast<const uint4*>(g_bits);
@@ -555,13 +600,14 @@ __global__ void __launch_bounds__(SMEM ? 1024 : 256)
     const uint32_t idx = g_load * 32u + lane;
     g_load += n_warps;
     G.strand = idx < n ? (list ? list[idx] : 2 * b.read_begin + idx) : 0u;
-    G.need = idx < n && (G.strand & 1u) == parity && o.status[G.strand] == ST_UNCLASSIFIED;
+    G.need = idx < n && o.status[G.strand] == ST_UNCLASSIFIED;
     G.L = G.woff = G.w0 = G.w1 = 0;
     if (G.need) {
       G.L = b.len[G.strand >> 1];
       G.woff = b.word_off[G.strand >> 1];
-      G.w0 = __ldg(b.packed + G.woff);
-      if (G.L > 16) G.w1 = __ldg(b.packed + G.woff + 1);
+      const uint32_t* gw = b.strand_words(G.strand, G.woff);
+      G.w0 = __ldg(gw);
+      if (G.L > 16) G.w1 = __ldg(gw + 1);
     }
   };
   Group cur, nxt;
@@ -599,7 +645,7 @@ __global__ void __launch_bounds__(SMEM ? 1024 : 256)
                        w1_new = __shfl_sync(full, cur.w1, src);
         if (take) {
           strand = s_new;
-          w = b.packed + woff_new;
+          w = b.strand_words(s_new, woff_new);
           n_words = (L_new + 15) >> 4;
           n_kmers = L_new - k + 1;  // unclassified strands have L >= k
           wlo = w0_new;
@@ -655,17 +701,13 @@ void launch_classify(const IndexView& v, const BatchView& b, const SearchOut& o,
   if (work == 0) return;
   const uint64_t bits_words = ((1ull << (2 * v.k)) + 31) / 32;
   const uint64_t bytes = ((bits_words + 3) / 4) * 16;
-  // forward strands probe the presence set, reverse strands the same set indexed by reverse-complement codes (the
-  // stored read's windows are tested as they are): one pass per strand orientation, each with its set
-  for (uint32_t parity = 0; parity < 2; ++parity) {
-    const uint32_t* bits = parity ? v.kmer_bits_rc : v.kmer_bits;
-    if (bytes <= kClassifySmemBytes && work >= 148u * 32u * 4u) {
-      cudaFuncSetAttribute(classify_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClassifySmemBytes);
-      classify_kernel<true><<<148, 1024, bytes, st>>>(v, b, o, list, n_list, (uint32_t)bits_words, bits, parity);
-    } else {
-      uint32_t blocks = min((work + 255) / 256, 148u * 8u);
-      classify_kernel<false><<<blocks, 256, 0, st>>>(v, b, o, list, n_list, (uint32_t)bits_words, bits, parity);
-    }
+  // both strand orientations in one pass: the reverse strands exist as packed reads of their own (packed_rc)
+  if (bytes <= kClassifySmemBytes && work >= 148u * 32u * 4u) {
+    cudaFuncSetAttribute(classify_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClassifySmemBytes);
+    classify_kernel<true><<<148, 1024, bytes, st>>>(v, b, o, list, n_list, (uint32_t)bits_words, v.kmer_bits);
+  } else {
+    uint32_t blocks = min((work + 255) / 256, 148u * 8u);
+    classify_kernel<false><<<blocks, 256, 0, st>>>(v, b, o, list, n_list, (uint32_t)bits_words, v.kmer_bits);
   }
 }
 

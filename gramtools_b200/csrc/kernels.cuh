@@ -16,11 +16,17 @@ enum StrandStatus : uint8_t {
 
 struct BatchView {               // one batch of reads, resident in HBM
   const uint32_t* packed;        // 2-bit base codes, 16 per word, every read starts on a word
+  const uint32_t* packed_rc;     // the reverse complements in the same layout (revcomp_kernel, once per batch slice):
+                                 //  both strands of a read are walked by the same instructions
   const uint32_t* word_off;      // n_reads + 1
   const uint32_t* len;           // n_reads (0 = skipped read)
   const uint32_t* seeds;         // n_reads (selection seed, shared by both strands)
   uint32_t n_reads;              // reads in the whole batch (arrays above are indexed by read id)
   uint32_t read_begin, read_end; // the slice of the batch this launch works on (H2D/compute pipelining)
+  // the packed words of a strand (even = the read as stored, odd = its reverse complement)
+  GQ_HD const uint32_t* strand_words(uint32_t strand, uint32_t woff) const {
+    return ((strand & 1u) ? packed_rc : packed) + woff;
+  }
 };
 
 struct SearchOut {
@@ -71,6 +77,9 @@ struct CoverageView {
 // (offsets[r] >> 4) + r: word-aligned and non-overlapping without a prefix sum (<= 1 word wasted per read).
 void launch_pack(const uint8_t* bases, const uint64_t* offsets, uint32_t r0, uint32_t r1, uint32_t* word_off,
                  uint32_t* packed, uint32_t* len, cudaStream_t st);
+
+// packed_rc for reads [b.read_begin, b.read_end) from packed (reverse_complement_read, quasimap.cpp:273-298)
+void launch_revcomp(const BatchView& b, uint32_t* packed_rc, cudaStream_t st);
 
 // Seed pass over the strands of the slice b.read_begin..b.read_end.
 void launch_seed(const IndexView& v, const BatchView& b, const SearchOut& o, const SeedOut& pre, cudaStream_t st);

@@ -284,13 +284,14 @@ class QuasimapIndex:
         return dict(launches=int(a[0]), rerun_strands=int(a[1]), search_ms=a[2], coverage_ms=a[3],
                     pool_words=int(a[4]), h2d_bytes=int(a[5]), kernels_ms=a[6], enqueue_ms=a[7])
 
-    KERNELS = ["seed_kernel", "verify_kernel", "text_kernel", "search_kernel", "classify_kernel", "coverage_kernel"]
+    KERNELS = ["seed_kernel", "verify_kernel", "text_kernel", "search_kernel", "classify_kernel", "coverage_kernel",
+               "revcomp_kernel"]
 
     def kernel_ms(self):
         """Per-kernel durations of the last single-slice map_resident (CUDA events inside the library)."""
         a = (C.c_double * 8)()
         self._check(self._lib.gq_last_kernel_ms(self._h, a))
-        return dict(zip(self.KERNELS, [float(x) for x in a[:6]]))
+        return dict(zip(self.KERNELS, [float(x) for x in a[:7]]))
 
     # -- results -------------------------------------------------------------------------------
     def batch_status(self):

@@ -153,7 +153,8 @@ int gq_set_stream(gq_index* idx, void* cuda_stream);
  *     rf_thresh, ev_thresh, leave, wait_max; big_arena_words / big_threads (overflow re-runs);
  *   seed_pass (0: every strand through the general kernel), seed_recs_per_read (candidate pool);
  *   pool_words_per_read (final-state pool; grows on demand), gtab_cap (initial multi-allele group table; grows);
- *   chunk_reads, tail_chunk_reads (slices of the pipelined host path), resident_slices (<= 64), overlap_classify.
+ *   chunk_reads, tail_chunk_reads (slices of the pipelined host path), resident_slices (<= 64), overlap_classify,
+ *   early_classify (pipelined path: k-mer filter of the early slices beside the late ones).
  * Parity precondition of the seeded selection (coverage_common.cpp:97-107): the reference's RandomInclusiveInt
  * is std::uniform_int_distribution over std::mt19937 as libstdc++ >= 11 implements it (Lemire's multiply-shift
  * with rejection); a reference built against an older libstdc++ or libc++ picks other classes for
@@ -166,7 +167,7 @@ int gq_last_run_info(gq_index* idx, double info[8]);
 
 /* Per-kernel durations (ms, CUDA events on the launching streams) of the last single-slice gq_map_resident call:
  * [0] seed_kernel [1] verify_kernel [2] text_kernel [3] search_kernel (general) [4] classify_kernel (runs on a
- * second stream beside coverage) [5] coverage_kernel; zero when the call was sliced. */
+ * second stream beside coverage) [5] coverage_kernel [6] revcomp_kernel; zero when the call was sliced. */
 int gq_last_kernel_ms(gq_index* idx, double ms[8]);
 
 const char* gq_last_error(void);

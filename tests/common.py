@@ -70,6 +70,7 @@ def emu_lib():
         lib.emu_kmer_states.argtypes = [C.c_void_p, u32p]
         lib.emu_kmer_states.restype = C.c_uint64
         lib.emu_sa.argtypes = [C.c_void_p, u32p]
+        lib.emu_sais64_agrees.argtypes = [C.POINTER(C.c_int32), C.c_uint64, C.c_int32]
         lib.emu_map.argtypes = [C.c_void_p, u8p, u64p, C.c_uint64, u32p, C.c_uint32]
         lib.emu_reruns.argtypes = [C.c_void_p]
         lib.emu_reruns.restype = C.c_uint64

@@ -13,6 +13,7 @@
 #define GQ_EMU_COUNTERS 1
 #include "../../gramtools_b200/csrc/gq_device.cuh"
 #include "../../gramtools_b200/csrc/index_build.hpp"
+#include "../../gramtools_b200/csrc/sais.hpp"
 
 #include <set>
 #include <unordered_set>
@@ -155,6 +156,16 @@ uint64_t emu_kmer_states(void* ev, uint32_t* words) {
   }
   return t;
 }
+// SA-IS with 64-bit indices (texts beyond 2^31 symbols) against the 32-bit instantiation on the same text
+int emu_sais64_agrees(const int32_t* text, uint64_t n, int32_t sigma) {
+  std::vector<int32_t> t(text, text + n);
+  std::vector<int32_t> a = suffix_array(t, sigma);
+  std::vector<int64_t> b = suffix_array64(t, sigma);
+  std::vector<uint32_t> c = suffix_array_u32(t, sigma, true);
+  for (uint64_t i = 0; i < n; ++i)
+    if ((int64_t)a[i] != b[i] || (uint32_t)a[i] != c[i]) return 0;
+  return 1;
+}
 void emu_sa(void* ev, uint32_t* out) {
   auto* e = (Emu*)ev;
   std::memcpy(out, e->h.sa.data(), e->h.sa.size() * 4);
@@ -180,6 +191,16 @@ int emu_map(void* ev, const uint8_t* bases, const uint64_t* off, uint64_t n_read
     }
     word_off[n_reads] = (uint32_t)packed.size();
     packed.push_back(0);
+    // reverse strands as revcomp_kernel builds them — and checked here base by base against the definition
+    std::vector<uint32_t> packed_rc(packed.size(), 0);
+    for (uint64_t r = 0; r < n_reads; ++r)
+      for (uint32_t m = 0; m < (len[r] + 15) / 16; ++m) {
+        packed_rc[word_off[r] + m] = revcomp_word(packed.data() + word_off[r], len[r], m);
+        uint32_t want = 0;
+        for (uint32_t j = 16 * m; j < 16 * m + 16 && j < len[r]; ++j)
+          want |= (3u - (((uint32_t)bases[off[r] + len[r] - 1 - j] - 1) & 3u)) << (2 * (j & 15u));
+        if (packed_rc[word_off[r] + m] != want) throw std::runtime_error("revcomp_word disagrees with the definition");
+      }
     e->n_reads = (uint32_t)n_reads;
     e->status.assign(2 * n_reads, 0);
     e->st_off.assign(2 * n_reads, 0);
@@ -187,7 +208,7 @@ int emu_map(void* ev, const uint8_t* bases, const uint64_t* off, uint64_t n_read
     e->st_count.assign(2 * n_reads, 0);
     e->pool.assign(std::max<size_t>(1 << 16, n_reads * 256), 0);
     std::vector<uint32_t> small(8, 0), ovf(2 * n_reads + 1), cov_ovf(2 * n_reads + 1), mapped(4 * n_reads + 1);
-    BatchView b{packed.data(), word_off.data(), len.data(), seeds, (uint32_t)n_reads, 0, (uint32_t)n_reads};
+    BatchView b{packed.data(), packed_rc.data(), word_off.data(), len.data(), seeds, (uint32_t)n_reads, 0, (uint32_t)n_reads};
     std::vector<uint32_t> seed_rec(4 * 4096), surv_cnt(2 * n_reads + 1, 0), gen(2 * n_reads + 1), pre_small(2, 0);
     SearchOut o{e->status.data(), e->st_off.data(), e->st_words.data(), e->st_count.data(), e->pool.data(),
                 (uint32_t)e->pool.size(), &small[0], ovf.data(), &small[1], mapped.data(), &small[3], &small[4],
@@ -212,7 +233,7 @@ int emu_map(void* ev, const uint8_t* bases, const uint64_t* off, uint64_t n_read
     if (g_track) {
 #define REG(name, vec) add_range(name, (vec).data(), (vec).size() * sizeof((vec)[0]), 32)
 #define REGS(name, vec, g) add_range(name, (vec).data(), (vec).size() * sizeof((vec)[0]), g)
-      REGS("packed reads", packed, 4); REGS("read len", len, 4); REGS("read word_off", word_off, 4);
+      REGS("packed reads", packed, 4); REGS("packed reverse strands", packed_rc, 4); REGS("read len", len, 4); REGS("read word_off", word_off, 4);
       add_range("read seeds", seeds, n_reads * 4, 4);
       REGS("strand status", e->status, 1); REGS("strand st_off", e->st_off, 4); REGS("strand st_words", e->st_words, 4);
       REGS("strand st_count", e->st_count, 4); REGS("final-state pool", e->pool, 4); REGS("mapped list", mapped, 4);
@@ -225,7 +246,7 @@ int emu_map(void* ev, const uint8_t* bases, const uint64_t* off, uint64_t n_read
       REG("par", h.par); REG("tm_odd", h.tm_odd); REG("tm_even_off", h.tm_even_off); REG("tm_even", h.tm_even);
       REG("entry_next", h.entry_next); REG("site_snp", h.site_snp); REG("sa", h.sa); REG("pos2node", h.pos2node);
       REG("nodes", h.nodes); REG("edges", h.edges); REG("kmer_bits (smem copy on the device)", h.kmer_bits);
-      REG("kmer_bits_rc", h.kmer_bits_rc); REG("kmer_off", h.kmer_off); REG("kmer_states", h.kmer_states);
+      REG("kmer_off", h.kmer_off); REG("kmer_states", h.kmer_states);
       REG("seed_off", h.seed_off); REG("seed_ent", h.seed_ent); REG("seed_state", h.seed_state);
       REG("kmer_paths", h.kmer_paths); REG("allele_off", h.allele_off);
 #undef REGS
@@ -407,12 +428,9 @@ int emu_index_check(void* ev) {
         for (uint32_t ent = h.seed_off[c * sd_B + q]; ent < h.seed_off[c * sd_B + q + 1]; ++ent)
           got.insert({h.seed_ent[ent].key, h.seed_ent[ent].aux, h.seed_state[ent], q});
       if (expect != got) fail("seed view entries of a k-mer");
-      // presence sets
+      // presence set
       const bool present = h.kmer_off[c + 1] > h.kmer_off[c];
       if ((((h.kmer_bits[c >> 5] >> (c & 31)) & 1u) != 0) != present) fail("kmer_bits");
-      uint64_t r = 0, x = ~c;
-      for (uint32_t i = 0; i < h.k; ++i) r |= ((x >> (2 * i)) & 3ull) << (2 * (h.k - 1 - i));
-      if ((((h.kmer_bits_rc[r >> 5] >> (r & 31)) & 1u) != 0) != present) fail("kmer_bits_rc");
     }
     for (const Node& nd : h.nodes)
       if (nd.n_edges && nd.next0 != h.edges[nd.edge_off]) fail("next0");

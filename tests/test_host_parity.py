@@ -4,6 +4,8 @@ the oracle. Bit-exact: integer path, no tolerance."""
 import json
 import os
 
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -151,6 +153,32 @@ def test_suffix_array_matches_oracle_order():
         m = min(ta.size, tb.size)
         d = np.nonzero(ta[:m] != tb[:m])[0]
         assert d.size and ta[d[0]] < tb[d[0]]
+
+
+def test_suffix_array_64bit_indices(monkeypatch):
+    """SA-IS with 64-bit indices (the instantiation texts beyond 2^31 symbols take, BASELINE config 5) gives the
+    suffix array of the 32-bit one — on random texts over small and large alphabets, on runs, and on PRGs; and an
+    index built through it maps like the oracle."""
+    from common import emu_lib
+    lib = emu_lib()
+    rng = np.random.default_rng(5)
+    texts = []
+    for sigma, n in ((2, 1), (3, 2), (3, 500), (5, 4000), (50, 3000), (1000, 20000), (6, 100000)):
+        t = rng.integers(1, sigma, size=n).astype(np.int32) if sigma > 2 else np.ones(n, dtype=np.int32)
+        texts.append((np.concatenate([t, [0]]).astype(np.int32), sigma))
+    texts.append((np.concatenate([np.tile([1, 2], 5000), [0]]).astype(np.int32), 3))  # deep recursion: periodic text
+    texts.append((np.concatenate([np.full(10000, 3), [0]]).astype(np.int32), 4))
+    for prg in (synth.make_nested_prg(11, 400, 6), synth.make_snp_prg(5000, 200, 3)[0]):
+        present = np.unique(prg)
+        comp = np.searchsorted(present, prg).astype(np.int32) + 1
+        texts.append((np.concatenate([comp, [0]]).astype(np.int32), int(present.size) + 1))
+    for t, sigma in texts:
+        t = np.ascontiguousarray(t)
+        assert lib.emu_sais64_agrees(t.ctypes.data_as(C.POINTER(C.c_int32)), t.size, sigma) == 1, (t.size, sigma)
+    monkeypatch.setenv("GQ_SAIS64", "1")
+    prg = synth.make_nested_prg(2, 300, 4)
+    bases, offs = encode_reads(_reads_for(prg, 200, 40, 9))
+    _check(prg, 4, bases, offs, what="index built with 64-bit SA-IS")
 
 
 def test_malformed_prgs_rejected():

@@ -36,6 +36,13 @@ for config in [int(x) for x in sys.argv[1:]] or [1, 2, 3]:
     e.map(bases, offs, seeds, arena_words=512)
     by_kernel, units = e.tracked()
     e.track(False)
+    # revcomp_kernel (not a per-strand device function of the emulation): streams the slice's packed words in and
+    # their reverse complements out, plus len and word_off
+    import numpy as np  # noqa: E402
+    words = int(((np.diff(offs.astype(np.int64)) + 15) // 16).sum())
+    by_kernel["revcomp_kernel"] = {"packed reads": 4.0 * words, "packed reverse strands": 4.0 * words, "read len": 4.0 * n,
+                                   "read word_off": 4.0 * n}
+    units["revcomp_kernel"] = n
     smem = {}
     for kn, d in by_kernel.items():  # the presence set lives in shared memory on the device
         smem[kn] = sum(v for s, v in d.items() if "smem copy" in s)

@@ -36,6 +36,10 @@ def timed(fn, n=10):
 
 
 print(f"reset_coverage {timed(idx.reset_coverage):.3f} ms; coverage fetch {timed(idx.coverage):.3f} ms")
+for kv in os.environ.get("GQ_OPTIONS", "").split(","):
+    if "=" in kv:
+        k_, v_ = kv.split("=")
+        idx.set_option(k_, int(v_))
 for spec in os.environ.get("GQ_CHUNKS", "1048576:1048576,524288:65536,262144:32768,131072:32768,65536:32768").split(","):
     chunk, tail = (int(x) for x in (spec.split(":") + [spec])[:2])
     idx.set_option("chunk_reads", chunk)
