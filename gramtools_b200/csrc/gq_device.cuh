@@ -146,13 +146,11 @@ struct ReadCursor {
   uint32_t L;
   uint64_t cw;
   uint32_t left, wi;
-  uint32_t nw;  // the word the next refill shifts in, loaded one refill ahead (its L1 latency is off the walk's chain)
   GQ_DEV inline void refill() {
     if (left <= 16 && wi != 0) {
       --wi;
-      cw |= (uint64_t)nw << (32 - 2 * left);  // left <= 16: the new 16 bases follow the valid ones
+      cw |= (uint64_t)GQ_LDG(w + wi) << (32 - 2 * left);  // left <= 16: the new 16 bases follow the valid ones
       left += 16;
-      nw = wi ? GQ_LDG(w + wi - 1) : 0u;
     }
   }
   // position the cursor so that peek() returns the base at index pos-1 (pos >= 1)
@@ -161,7 +159,6 @@ struct ReadCursor {
     wi = i >> 4;
     const uint32_t q = i & 15u;
     cw = (uint64_t)(GQ_LDG(w + wi) << (2 * (15 - q))) << 32;
-    nw = wi ? GQ_LDG(w + wi - 1) : 0u;
     left = q + 1;
     refill();
   }
@@ -315,13 +312,6 @@ GQ_DEV inline void lane_load_top(Lane& ln) {
 
 constexpr uint32_t kSurvGeneral = 0x10000u;  // SeedOut::surv_cnt flag: the strand is on the general kernel's list
 constexpr uint32_t kSurvListed = 0x20000u;   //  ... the strand is on mapped_list (the coverage work list)
-// bits 18..31 of the same word: candidates of the strand that passed the verify pass (verify_kernel adds one per
-// survivor, fire and forget). A finished candidate that is its strand's ONLY verified one needs no claim — no other
-// candidate of the strand can finish — which spares the common case an atomic round trip. The 14-bit count cannot
-// wrap: strands with kMaxSeedEntries seed entries or more (<= 32 candidates each) take the general kernel.
-constexpr uint32_t kSurvVerifiedShift = 18;
-constexpr uint32_t kSurvVerifiedOne = 1u << kSurvVerifiedShift;
-constexpr uint32_t kMaxSeedEntries = 448;
 
 // append a mapped strand to the coverage work list, once (the text kernel may have listed it already)
 GQ_DEV inline void list_mapped(const SearchOut& o, uint32_t strand) {
@@ -383,7 +373,7 @@ GQ_DEV inline void lane_refill(Lane& ln, const IndexView& v, const BatchView& b,
     GQ_AT(o.status, strand) = ST_MISSING_KMER;
     return;
   }
-  ln.rd = ReadCursor{b.strand_words(strand, GQ_AT(b.word_off, r)), L, 0, 0, 0, 0};
+  ln.rd = ReadCursor{b.strand_words(strand, GQ_AT(b.word_off, r)), L, 0, 0, 0};
   // seeding k-mer = last k bases of the strand; its code (base j at bits [2j,2j+2)) is a bit-field of the
   // packed strand
   const uint32_t code = seeding_kmer_code(ln.rd.w, L, k);
@@ -749,7 +739,7 @@ GQ_DEV inline uint32_t preseed_lookup(const IndexView& v, const BatchView& b, co
   const uint32_t code = seeding_kmer_code(w, L, k);
   out.pos0 = L - k;
   if (out.pos0) {
-    ReadCursor rd{w, L, 0, 0, 0, 0};
+    ReadCursor rd{w, L, 0, 0, 0};
     rd.seek(out.pos0);
     out.ctx = rd.top32() >> 8;
   }
@@ -807,7 +797,7 @@ GQ_DEV inline uint32_t seed_state_plan(const IndexView& v, SuperPtr super_c, con
   uint32_t w0 = pos0 | (K_SCAN << 28), total = 0;
   if (hi - lo >= kNarrowWidth) {
     Lane ln;
-    ln.rd = ReadCursor{w, L, 0, 0, 0, 0};
+    ln.rd = ReadCursor{w, L, 0, 0, 0};
     ln.pos = pos0;
     ln.lo = lo;
     ln.hi = hi;
@@ -872,7 +862,7 @@ struct SeedCands {
 GQ_DEV inline uint32_t seed_filter(const IndexView& v, const SeedPlan& plan, const uint32_t* w, uint32_t L,
                                    SeedCands& out) {
   uint32_t n = 0, cur_pos = 0;
-  ReadCursor rd{w, L, 0, 0, 0, 0};
+  ReadCursor rd{w, L, 0, 0, 0};
   for (uint32_t e = 0; e < plan.n; ++e) {
     const uint32_t w0 = plan.w0[e], pos = w0 & 0x0FFFFFFFu;
     if (pos != cur_pos) {  // entries of one seed state share a few read positions
@@ -919,7 +909,7 @@ GQ_DEV inline uint32_t seed_state_cands(const IndexView& v, SuperPtr super_c, co
     uint32_t m = (aux >> 24) & 0x7Fu;  // context bases, up to the first marker / the text start
     m = m < pos0 ? m : pos0;
     if (m) {
-      ReadCursor rd{w, L, 0, 0, 0, 0};
+      ReadCursor rd{w, L, 0, 0, 0};
       rd.seek(pos0);
       const uint32_t x = ((rd.top32() >> 8) ^ aux) & ((0xFFFFFFFFu << (24 - 2 * m)) & 0xFFFFFFu);
       if (x) return 0;  // another occurrence of the k-mer: the read continues differently
@@ -966,7 +956,6 @@ struct FastLane {
   uint32_t path_off;     // ... in kmer_paths
   uint32_t T[2 * kFastT], G[kFastG];
   uint32_t result;  // FAST_NONE while running
-  uint32_t flags0;  // the strand's surv_cnt word when the walk began (text kernel: verified count, general flag)
   bool p_valid;     // ln.p is the text position of the current suffix
 };
 
@@ -992,15 +981,13 @@ GQ_DEV inline void fast_begin(FastLane& f, const IndexView& v, const BatchView& 
   f.p_valid = true;
   f.nt = f.ng = 0;
   f.nt0 = f.ng0 = f.path_off = 0;
-  f.flags0 = 0;
   if (TRACK) {
-    f.flags0 = GQ_AT(pre.surv_cnt, strand);
     const KmerState ks = GQ_AT(v.kmer_states, j);
     f.nt0 = ks.counts & 0xFFFFu;
     f.ng0 = ks.counts >> 16;
     f.path_off = ks.path_off;
   }
-  f.ln.rd = ReadCursor{b.strand_words(strand, woff), L, 0, 0, 0, 0};
+  f.ln.rd = ReadCursor{b.strand_words(strand, woff), L, 0, 0, 0};
   f.ln.pos = w0 & 0x0FFFFFFFu;
   f.ln.kind = w0 >> 28;
   f.ln.p = p;
@@ -1435,8 +1422,7 @@ GQ_DEV inline void fast_emit(const FastLane& f, const IndexView& v, const Search
 
 // a finished candidate claims its strand: 0 = first one (emit), otherwise the strand is (or becomes) the
 // general kernel's
-GQ_DEV inline bool fast_claim(const SeedOut& pre, uint32_t strand, uint32_t flags_at_begin) {
-  if ((flags_at_begin >> kSurvVerifiedShift) == 1u) return !(flags_at_begin & kSurvGeneral);  // the only verified candidate
+GQ_DEV inline bool fast_claim(const SeedOut& pre, uint32_t strand) {
   const uint32_t old = gq_atomic_add(pre.surv_cnt + strand, 1u);
   if (old & kSurvGeneral) return false;
   if (old & 0xFFFFu) {
@@ -1501,10 +1487,9 @@ GQ_DEV inline void map_strand(const IndexView& v, const uint32_t* super_cnt, con
         total += cnt;
       }
     }
-    if (!general && ns >= kMaxSeedEntries) general = true;  // (seed_kernel: bounds the verified-candidate count)
     if (!general) {
-      // verify pass over all candidates of the strand first (verify_kernel: survivors counted in the strand's flag
-      // word), then the full walks from the start (text_kernel)
+      // verify pass over all candidates of the strand first (verify_kernel), then the full walks of the survivors from
+      // the start (text_kernel)
       for (uint32_t i = 0; i < total; ++i) {
         FastLane f;
         GQ_PHASE(1);  // verify_kernel
@@ -1519,7 +1504,6 @@ GQ_DEV inline void map_strand(const IndexView& v, const uint32_t* super_cnt, con
           continue;
         }
         GQ_TOUCH(pre.rec + 4 * (size_t)i, 16);  // the survivor is copied to the text kernel's list
-        gq_red_add(pre.surv_cnt + strand, kSurvVerifiedOne);
       }
       for (uint32_t i = 0; i < total; ++i) {
         if (pre.rec[4 * (size_t)i] == kNoAllele) continue;
@@ -1542,7 +1526,7 @@ GQ_DEV inline void map_strand(const IndexView& v, const uint32_t* super_cnt, con
         }
         const uint32_t words = fast_outcome(f, v);
         if (f.result == FAST_MAPPED) {
-          if (!fast_claim(pre, strand, f.flags0)) continue;
+          if (!fast_claim(pre, strand)) continue;
           const uint32_t off = gq_atomic_add(o.pool_used, words);
           if (off + words > o.pool_cap) {
             GQ_AT(o.status, strand) = ST_OVERFLOW;

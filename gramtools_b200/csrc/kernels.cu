@@ -210,9 +210,7 @@ __global__ void __launch_bounds__(256)
     SeedLookup lk;
     lk.classified = true;
     lk.s0 = lk.n0 = lk.s1 = lk.n1 = lk.pos0 = lk.ctx = 0;
-    uint32_t ns = i < n ? preseed_lookup(v, b, o, strand, lk) : 0;
-    const bool too_many = ns >= kMaxSeedEntries;  // bounds the strand's candidates (kSurvVerifiedShift): general kernel
-    if (too_many) ns = 0;
+    const uint32_t ns = i < n ? preseed_lookup(v, b, o, strand, lk) : 0;
     uint32_t my_L = 0, my_woff = 0;
     if (!lk.classified) {
       o.status[strand] = ST_UNCLASSIFIED;  // until a candidate finishes or the general kernel decides
@@ -294,7 +292,7 @@ __global__ void __launch_bounds__(256)
         }
       }
     }
-    if (((general >> lane) & 1u) || too_many) send_to_general(pre, strand);
+    if ((general >> lane) & 1u) send_to_general(pre, strand);
   }
   seed_flush(stage, pre, lane);
 }
@@ -338,7 +336,6 @@ __global__ void __launch_bounds__(256) verify_kernel(IndexView v, BatchView b, S
       if (!fast_verified(f, pos0) && f.ln.state == LS_EV_TSCAN) fast_event<false>(f, v);
     }
     const bool alive = rec.x != kNoAllele && fast_alive(f);
-    if (alive) gq_red_add(pre.surv_cnt + rec.x, kSurvVerifiedOne);  // verified candidates of the strand (fast_claim)
     const uint32_t mm = __ballot_sync(full, alive);
     if (pend_mask) {  // flush the previous round
       const uint32_t base = __shfl_sync(full, pend_base, 0);
@@ -391,7 +388,7 @@ __global__ void __launch_bounds__(256) text_kernel(IndexView v, BatchView b, Sea
     // A finished candidate claims its strand; a second one (reads in repeats) makes the strand the general
     // kernel's. Only claim winners take pool space and a mapped-list slot: a strand can have many finished
     // candidates, the list holds one entry per strand.
-    bool emit = f.result == FAST_MAPPED && fast_claim(pre, strand, f.flags0);
+    bool emit = f.result == FAST_MAPPED && fast_claim(pre, strand);
     if (!emit) words = 0;
     uint32_t incl = words;  // pool space for the round: warp scan + one atomic
 #pragma unroll
