@@ -225,7 +225,7 @@ def main():
     import torch
     import torch.distributed as dist
     from gramtools_b200 import QuasimapIndex, comm_unique_id, pack_reads
-    from gramtools_b200.distributed import shard_bounds
+    from gramtools_b200.distributed import bind_to_device_numa, shard_bounds
 
     config = args.config
     cfg = CONFIGS[config]
@@ -238,6 +238,9 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
+    # one process per GPU: keep each rank's threads and pinned buffers on its GPU's NUMA node (the end-to-end arm is
+    # bound by eight ranks pulling reads from host memory at once); the CPU legs get the full affinity back
+    full_affinity = bind_to_device_numa(local) if (world > 1 and not os.environ.get("GQ_NO_NUMA_BIND")) else None
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
@@ -281,11 +284,15 @@ def main():
         got = coverage_result(idx)
         if rank == 0:
             from common import Oracle
+            if full_affinity:
+                os.sched_setaffinity(0, full_affinity)
             oracle = Oracle(prg, cfg["k"])
             oracle.map(pb_, po_, ps_, threads=os.cpu_count() or 1, want_states=False)
             ref = oracle.result(want_states=False)
             ok = (np.array_equal(got[0], ref.allele_sum) and np.array_equal(got[1], ref.per_base)
                   and np.array_equal(got[2], ref.grouped) and got[3] == ref.stats)
+            if full_affinity:
+                bind_to_device_numa(local)
             parity = {"ok": bool(ok), "reads": m, "ranks": world,
                       "checked": "allele_sum, per-base, grouped allele counts, 5 counters vs the CPU oracle"
                                  + (" after the in-library NCCL all-reduce" if world > 1 else "")}
@@ -416,6 +423,8 @@ def main():
         cpu = cpu1 = None
         ref_alg_bytes = None
         if oracle is not None:
+            if full_affinity:
+                os.sched_setaffinity(0, full_affinity)
             cores = os.cpu_count() or 1
             sample = min(reference_sample(config), n_reads)
             b, of, sd = bases[:int(offs[sample])], offs[:sample + 1], seeds[:sample]
@@ -474,6 +483,7 @@ def main():
                              "each step: reset, map, " + ("NCCL all-reduce, " if world > 1 else "") + "fetch coverage to the host"},
             "e2e_u8": {"value": reads_total / (e2e_u8_ms / 1e3), "unit": "reads/s", "h2d_bytes_per_step": int(h2d_u8),
                        "ms_per_step": e2e_u8_ms / args.steps, "input": "1 byte per base (gq_map_batch), packed on the GPU"},
+            "numa_bound": bool(full_affinity),
             "gpu_launches": int(launches),
             "roofline": roof, "phases": phases, "cpu_baseline": cpu, "cpu_baseline_1t": cpu1,
             "kernels": {"search_ms": search_ms / args.steps, "classify_coverage_ms": cov_ms / args.steps,

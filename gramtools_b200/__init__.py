@@ -9,11 +9,11 @@ There is no CPU fallback: importing works anywhere, but every compute call needs
 library and a CUDA device and raises otherwise.
 """
 from .engine import (GqError, QuasimapIndex, QuasimapReadsStats, comm_unique_id, encode_reads, lib_path,  # noqa: F401
-                     load_library, pack_ascii, pack_reads)
+                     load_library, pack_ascii, pack_reads, suffix_array)
 from .synth import (make_snp_prg, make_indel_prg, make_nested_prg, sample_reads, master_seeds)  # noqa: F401
 
 __all__ = [
     "GqError", "QuasimapIndex", "QuasimapReadsStats", "comm_unique_id", "encode_reads", "lib_path", "load_library",
-    "pack_ascii", "pack_reads",
+    "pack_ascii", "pack_reads", "suffix_array",
     "make_snp_prg", "make_indel_prg", "make_nested_prg", "sample_reads", "master_seeds",
 ]

@@ -675,7 +675,14 @@ int gq_index_build(const uint32_t* prg, uint64_t n_symbols, uint32_t kmer_size, 
   if (device < 0 || device >= ndev) throw std::runtime_error("invalid device ordinal");
   ix = new gq_index();
   ix->device = device;
-  gq::build_host_index(prg, n_symbols, kmer_size, ix->h);
+  // suffix array on the GPU (sa_gpu.cu) unless GQ_HOST_SA is set (developer switch: host SA-IS, for comparison)
+  struct SaCtx {
+    int device;
+  } sctx{device};
+  gq::SaBuilder sab = [](const std::vector<int32_t>& text, int32_t sigma, void* c) {
+    return gq::gpu_suffix_array(text, sigma, ((SaCtx*)c)->device);
+  };
+  gq::build_host_index(prg, n_symbols, kmer_size, ix->h, getenv("GQ_HOST_SA") ? nullptr : sab, &sctx);
   finish_handle(ix);
   *out = ix;
   }
@@ -685,6 +692,22 @@ int gq_index_build(const uint32_t* prg, uint64_t n_symbols, uint32_t kmer_size, 
     return -1;
   }
   return 0;
+}
+
+int gq_suffix_array(const uint32_t* prg, uint64_t n_symbols, int device, uint32_t* sa_out, int* rounds) {
+  GQ_TRY
+  if (!prg || !sa_out || n_symbols == 0) throw std::runtime_error("null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    throw std::runtime_error("no CUDA device: libgq has no CPU fallback");
+  if (device < 0 || device >= ndev) throw std::runtime_error("invalid device ordinal");
+  if (n_symbols >= (1ull << 32) - 3) throw std::runtime_error("PRG too long: text positions are 32-bit words");
+  std::vector<uint32_t> present;
+  std::vector<int32_t> text;
+  const int32_t sigma = gq::compress_text(prg, n_symbols, present, text);
+  std::vector<uint32_t> sa = gq::gpu_suffix_array(text, sigma, device, rounds);
+  std::copy(sa.begin(), sa.end(), sa_out);
+  GQ_CATCH
 }
 
 int gq_index_clone(const gq_index* src, int device, gq_index** out) {

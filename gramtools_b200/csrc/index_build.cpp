@@ -53,6 +53,21 @@ IndexView HostIndex::view() const {
   return v;
 }
 
+int32_t compress_text(const uint32_t* prg, uint64_t n_symbols, std::vector<uint32_t>& present, std::vector<int32_t>& text) {
+  present.assign(prg, prg + n_symbols);
+  std::sort(present.begin(), present.end());
+  present.erase(std::unique(present.begin(), present.end()), present.end());
+  const int32_t sigma = (int32_t)present.size() + 1;
+  text.assign(n_symbols + 1, 0);
+  // symbols are dense near 1..4 and markers; a direct table avoids n binary searches
+  const uint32_t maxs = present.empty() ? 0 : present.back();
+  std::vector<int32_t> tab((size_t)maxs + 1, 0);
+  for (size_t i = 0; i < present.size(); ++i) tab[present[i]] = (int32_t)i + 1;
+  for (uint64_t i = 0; i < n_symbols; ++i) text[i] = tab[prg[i]];
+  text[n_symbols] = 0;  // the sentinel sdsl appends
+  return sigma;
+}
+
 namespace {
 
 struct OpenSite {
@@ -300,29 +315,25 @@ void build_site_tables(HostIndex& ix) {
   }
 }
 
-void build_fm(HostIndex& ix, const std::vector<uint32_t>& hit_marker, const std::vector<uint32_t>& hit_allele) {
+void build_fm(HostIndex& ix, const std::vector<uint32_t>& hit_marker, const std::vector<uint32_t>& hit_allele,
+              SaBuilder sa_builder, void* sa_ctx) {
   const auto& prg = ix.prg;
   const uint32_t n = (uint32_t)prg.size() + 1;
   ix.n = n;
   // compressed alphabet: rank among the symbols present (sdsl's char2comp)
-  std::vector<uint32_t> present(prg);
-  std::sort(present.begin(), present.end());
-  present.erase(std::unique(present.begin(), present.end()), present.end());
-  const int32_t sigma = (int32_t)present.size() + 1;
+  std::vector<uint32_t> present;
+  std::vector<int32_t> text;
+  const int32_t sigma = compress_text(prg.data(), prg.size(), present, text);
   auto comp = [&](uint32_t sym) {
     return (int32_t)(std::lower_bound(present.begin(), present.end(), sym) - present.begin()) + 1;
   };
-  std::vector<int32_t> text(n);
-  {
-    // symbols are dense near 1..4 and markers; a direct table avoids n binary searches
-    uint32_t maxs = present.empty() ? 0 : present.back();
-    std::vector<int32_t> tab(maxs + 1, 0);
-    for (size_t i = 0; i < present.size(); ++i) tab[present[i]] = (int32_t)i + 1;
-    for (uint32_t i = 0; i + 1 < n; ++i) text[i] = tab[prg[i]];
-    text[n - 1] = 0;
-  }
-  // 32-bit SA-IS below 2^31 symbols, 64-bit indices inside above (GQ_SAIS64=1 forces the latter: tests)
-  ix.sa = suffix_array_u32(text, sigma, std::getenv("GQ_SAIS64") != nullptr);
+  const auto t_sa0 = std::chrono::steady_clock::now();
+  if (sa_builder) ix.sa = sa_builder(text, sigma, sa_ctx);
+  else ix.sa = suffix_array_u32(text, sigma, std::getenv("GQ_SAIS64") != nullptr);
+  if (ix.sa.size() != n) throw std::runtime_error("suffix array builder returned a wrong size");
+  if (std::getenv("GQ_BUILD_TIMING"))
+    fprintf(stderr, "index build:   %-26s %.2f s\n", sa_builder ? "suffix array (GPU)" : "suffix array (SA-IS)",
+            std::chrono::duration<double>(std::chrono::steady_clock::now() - t_sa0).count());
   // C array
   std::vector<uint32_t> C(sigma + 1, 0);
   for (uint32_t i = 0; i < n; ++i) C[text[i] + 1]++;
@@ -560,6 +571,14 @@ void kmer_recurse(const IndexView& v, uint32_t k, uint32_t depth, uint32_t code,
 }
 
 void build_kmers(HostIndex& ix) {
+  const bool timing = std::getenv("GQ_BUILD_TIMING") != nullptr;
+  auto t0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "index build:   %-26s %.2f s\n", what, std::chrono::duration<double>(t1 - t0).count());
+    t0 = t1;
+  };
   const uint32_t k = ix.k;
   if (k < 1 || k > 14) throw std::runtime_error("kmer_size must be in [1,14]");  // command_setup.py:97-99
   const uint64_t nk = 1ull << (2 * k);
@@ -608,6 +627,7 @@ void build_kmers(HostIndex& ix) {
     }
   }
   if (!err.empty()) throw std::runtime_error(err);
+  lap("k-mer searches (DFS)");
   // merge into CSR ordered by k-mer code
   for (auto& o : outs)
     for (size_t i = 0; i < o.codes.size(); ++i) ix.kmer_off[o.codes[i] + 1] += o.n_states[i];
@@ -639,6 +659,7 @@ void build_kmers(HostIndex& ix) {
   }
   if (ix.kmer_paths.empty()) ix.kmer_paths.push_back(0);
   if (ix.kmer_states.empty()) ix.kmer_states.push_back(KmerState{});
+  lap("k-mer CSR merge");
   // seed-pass view: per k-mer one entry per suffix of its narrow states (text position + left context), one
   // entry per wide state; bucketed by the first d context bases (gq_core.cuh, KmerSeed)
   const uint32_t d = seed_bucket_bases(k), B = seed_buckets(k);
@@ -698,11 +719,13 @@ void build_kmers(HostIndex& ix) {
       }
     }
   }
+  lap("seed view");
 }
 
 }  // namespace
 
-void build_host_index(const uint32_t* prg, uint64_t n_symbols, uint32_t kmer_size, HostIndex& ix) {
+void build_host_index(const uint32_t* prg, uint64_t n_symbols, uint32_t kmer_size, HostIndex& ix, SaBuilder sa_builder,
+                      void* sa_ctx) {
   if (n_symbols == 0) throw std::runtime_error("empty PRG");
   // positions, SA indices and marker ranks are unsigned 32-bit words on the device, 0xFFFFFFFF is "none"
   if (n_symbols >= (1ull << 32) - 3) throw std::runtime_error("PRG too long: text positions are 32-bit words (max 2^32 - 4 symbols)");
@@ -721,7 +744,7 @@ void build_host_index(const uint32_t* prg, uint64_t n_symbols, uint32_t kmer_siz
   build_graph(ix, hit_marker, hit_allele);
   build_site_tables(ix);
   lap("coverage graph + site tables");
-  build_fm(ix, hit_marker, hit_allele);
+  build_fm(ix, hit_marker, hit_allele, sa_builder, sa_ctx);
   lap("SA + rank blocks + text mode");
   build_kmers(ix);
   lap("k-mer index + seed view");

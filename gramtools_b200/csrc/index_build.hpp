@@ -57,6 +57,16 @@ struct HostIndex {
 
 // Throws std::runtime_error on malformed PRGs (same conditions as the reference:
 // linearised_prg.cpp:52-80, coverage_graph.cpp:215-221,330-338).
-void build_host_index(const uint32_t* prg, uint64_t n_symbols, uint32_t kmer_size, HostIndex& out);
+// `sa_builder` (optional): suffix array of the compressed text (symbols in [0, sigma), unique minimum at the end);
+// libgq passes the GPU builder (sa_gpu.cu), the test emulation leaves it null and gets the host SA-IS (sais.hpp).
+using SaBuilder = std::vector<uint32_t> (*)(const std::vector<int32_t>& text, int32_t sigma, void* ctx);
+void build_host_index(const uint32_t* prg, uint64_t n_symbols, uint32_t kmer_size, HostIndex& out,
+                      SaBuilder sa_builder = nullptr, void* sa_ctx = nullptr);
+
+// PRG symbols -> ranks among the symbols present + 1 (sdsl's char2comp), sentinel 0 appended; returns sigma
+int32_t compress_text(const uint32_t* prg, uint64_t n_symbols, std::vector<uint32_t>& present, std::vector<int32_t>& text);
+
+// sa_gpu.cu (libgq only): prefix doubling with radix sorts on `device`; rounds_out = sort rounds it took
+std::vector<uint32_t> gpu_suffix_array(const std::vector<int32_t>& text, int32_t sigma, int device, int* rounds_out = nullptr);
 
 }  // namespace gq

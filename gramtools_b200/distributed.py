@@ -5,7 +5,46 @@ keeps the j-th draw of the master mt19937 (quasimap.cpp:136-137), so results do 
 sharding. The only exchange: one all-reduce(sum) of the dense uint32 accumulators plus a gather/merge
 of the sparse multi-allele groups; uint16 semantics are applied once on the reduced totals.
 """
+import os
+
 import numpy as np
+
+
+def bind_to_device_numa(device):
+    """Pin this process (its threads and, by first touch, the pinned buffers it allocates afterwards) to the CPUs of
+    the NUMA node GPU `device` hangs off. With one process per GPU all pulling reads from host memory at PCIe rate,
+    buffers on the far socket cross the inter-socket link and the ranks' copies slow each other down. Returns the
+    previous affinity (restore it with os.sched_setaffinity before CPU-bound legs) or None when nothing was done:
+    the topology is read from NVML + sysfs and any missing piece leaves the process as it was."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = device
+        if vis:  # CUDA ordinal -> NVML index when the visible set is a list of ordinals
+            ids = [x.strip() for x in vis.split(",") if x.strip()]
+            if device < len(ids) and ids[device].isdigit():
+                index = int(ids[device])
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:  # NVML prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        old = os.sched_getaffinity(0)
+        cpus &= old
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return old
+    except Exception:
+        return None
 
 
 def shard_bounds(n_reads, rank, world):

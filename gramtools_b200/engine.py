@@ -39,6 +39,7 @@ def load_library():
     sig = {
         "gq_index_build": [u32p, C.c_uint64, C.c_uint32, C.c_int, C.POINTER(vp)],
         "gq_index_destroy": [vp],
+        "gq_suffix_array": [u32p, C.c_uint64, C.c_int, u32p, C.POINTER(C.c_int)],
         "gq_index_describe": [vp, C.POINTER(GqLayout)],
         "gq_index_allele_offsets": [vp, u64p],
         "gq_index_per_base_layout": [vp, u64p],
@@ -137,6 +138,17 @@ def comm_unique_id():
     if lib.gq_comm_unique_id(_ptr(a, C.c_uint8)) != 0:
         raise GqError(lib.gq_last_error().decode())
     return a
+
+
+def suffix_array(prg, device=0):
+    """gq_suffix_array: SA of the PRG (+ sentinel) built on the GPU by prefix doubling -> (sa uint32[n + 1], rounds)."""
+    lib = load_library()
+    prg = np.ascontiguousarray(prg, dtype=np.uint32)
+    sa = np.zeros(prg.size + 1, dtype=np.uint32)
+    rounds = C.c_int(0)
+    if lib.gq_suffix_array(_ptr(prg, C.c_uint32), prg.size, device, _ptr(sa, C.c_uint32), C.byref(rounds)) != 0:
+        raise GqError(lib.gq_last_error().decode())
+    return sa, rounds.value
 
 
 def pack_reads(bases, offsets, n_threads=None, out=None):

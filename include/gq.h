@@ -42,6 +42,11 @@ typedef struct gq_layout {
  * LE uint32, linearised_prg.cpp:8-45) and uploads them to GPU `device`. */
 int gq_index_build(const uint32_t* prg, uint64_t n_symbols, uint32_t kmer_size, int device, gq_index** out);
 int gq_index_destroy(gq_index* idx);
+/* The suffix array alone — what sdsl::construct computes first (make_data_structures.cpp:9-33) — built on GPU
+ * `device` by prefix doubling (one radix sort per round; 28 bytes of HBM per symbol: a 3.3e9-symbol whole-genome
+ * PRG takes 92 GB, one B200). sa_out: n_symbols + 1 entries (the sentinel suffix first), 32-bit text positions;
+ * n_symbols < 2^32 - 3. rounds (may be NULL) = sort rounds taken. gq_index_build uses the same builder. */
+int gq_suffix_array(const uint32_t* prg, uint64_t n_symbols, int device, uint32_t* sa_out, int* rounds);
 int gq_index_describe(const gq_index* idx, gq_layout* out);
 /* allele_off[n_site_slots + 1]: offset of each site's alleles in the flat allele_sum vector. */
 int gq_index_allele_offsets(const gq_index* idx, uint64_t* allele_off);

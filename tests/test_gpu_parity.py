@@ -434,3 +434,29 @@ def test_two_gpus_one_process_allreduce(built_lib):
         assert np.array_equal(h.grouped(), ref.grouped)
         assert [st.all_reads_count, st.skipped_reads_count, st.missing_kmer_reads_count, st.no_extension_reads_count,
                 st.exact_mapped_reads_count] == ref.stats
+
+
+def test_gpu_suffix_array(built_lib):
+    """The GPU suffix array (prefix doubling, sa_gpu.cu — what gq_index_build uses) against the host SA-IS of the
+    test emulation: random SNP / indel / nested PRGs, long exact repeats (many doubling rounds), a periodic text,
+    a one-symbol PRG."""
+    from common import Emu
+    from gramtools_b200 import suffix_array
+    rng = np.random.default_rng(3)
+    rep = rng.integers(1, 5, size=3000).astype(np.uint32)
+    prgs = {
+        "snp": synth.make_snp_prg(200_000, 5_000, 1)[0],
+        "indel": synth.make_indel_prg(50_000, 2_000, 2)[0],
+        "nested": synth.make_nested_prg(20, 800, 3),
+        "nested, coinciding alleles": synth.make_nested_prg(6, 500, 4, distinct=False),
+        "repeats": np.concatenate([rep, rng.integers(1, 5, size=100).astype(np.uint32), rep, rep[:1500], rep]),
+        "periodic": np.tile(np.asarray([1, 2, 3], dtype=np.uint32), 4000),
+        "one symbol": np.asarray([3], dtype=np.uint32),
+        "run": np.full(5000, 2, dtype=np.uint32),
+    }
+    for name, prg in prgs.items():
+        prg = np.ascontiguousarray(prg, dtype=np.uint32)
+        sa, rounds = suffix_array(prg)
+        want = Emu(prg, 1 if prg.size < 4 else 3).sa()
+        assert np.array_equal(sa, want), name
+        assert rounds >= 1
