@@ -353,67 +353,95 @@ void build_fm(HostIndex& ix, const std::vector<uint32_t>& hit_marker, const std:
     ix.allele_iv[2 * s] = C[ce];          // get_allele_marker_sa_interval, vBWT_jump.cpp:3-21
     ix.allele_iv[2 * s + 1] = C[ce + 1] - 1;
   }
-  // rank blocks, marker ranks and marker targets in BWT order
+  // rank blocks, marker ranks and marker targets in BWT order — two passes over the blocks of 64 BWT positions, both
+  // parallel: (1) the bit planes of every block and its per-base / marker counts, (2) after a prefix sum over the
+  // block counts, the counters in front of every block and the jump records of its markers at their BWT rank
   const uint32_t nblk = (n >> kBlkShift) + 1;
   const uint32_t nsuper = (n >> kSuperShift) + 1;
   ix.rank_blk.assign(nblk, RankBlk{});
   ix.super_cnt.assign(4 * (size_t)nsuper, 0);
   ix.mrank_blk.assign(nblk, 0);
-  ix.marker_hit.clear();
-  uint32_t tot[4] = {0, 0, 0, 0}, sup[4] = {0, 0, 0, 0}, nmark = 0;
-  std::vector<uint32_t> bwt_marker_pos;  // text position of the marker behind each BWT marker occurrence
-  for (uint32_t i = 0; i <= n; ++i) {
-    if ((i & ((1u << kSuperShift) - 1)) == 0) {
-      for (int c = 0; c < 4; ++c) sup[c] = tot[c], ix.super_cnt[4 * (size_t)(i >> kSuperShift) + c] = ix.c_base[c] + tot[c];
+  std::vector<uint32_t> blk_cnt(5 * (size_t)nblk + 5, 0);  // per block: A, C, G, T, markers (then prefix sums)
+  const int64_t nblk_i = (int64_t)nblk;
+#pragma omp parallel for schedule(static)
+  for (int64_t bi = 0; bi < nblk_i; ++bi) {
+    RankBlk& b = ix.rank_blk[bi];
+    uint32_t cnt[5] = {0, 0, 0, 0, 0};
+    const uint64_t i0 = (uint64_t)bi << kBlkShift, i1 = std::min<uint64_t>(i0 + 64, n);
+    for (uint64_t i = i0; i < i1; ++i) {
+      const uint32_t p = ix.sa[i];
+      const uint32_t sym = p ? prg[p - 1] : 0;
+      const uint64_t bit = 1ull << (i & 63u);
+      if (sym >= 1 && sym <= 4) {
+        const uint32_t c = sym - 1;
+        if (c & 1) b.p0 |= bit;
+        if (c & 2) b.p1 |= bit;
+        cnt[c]++;
+      } else {
+        b.p2 |= bit;
+        if (sym > 4) {
+          b.p0 |= bit;
+          cnt[4]++;
+        }
+      }
     }
-    if ((i & 63u) == 0) {
-      RankBlk& b = ix.rank_blk[i >> kBlkShift];
-      b.cnt = 0;
-      for (int c = 0; c < 4; ++c) b.cnt |= (uint64_t)((tot[c] - sup[c]) & 0xFFFFu) << (16 * c);
-      ix.mrank_blk[i >> kBlkShift] = nmark;
-    }
-    if (i == n) break;
-    uint32_t p = ix.sa[i];
-    uint32_t sym = p ? prg[p - 1] : 0;
-    RankBlk& b = ix.rank_blk[i >> kBlkShift];
-    uint64_t bit = 1ull << (i & 63u);
-    if (sym >= 1 && sym <= 4) {
-      uint32_t c = sym - 1;
-      if (c & 1) b.p0 |= bit;
-      if (c & 2) b.p1 |= bit;
-      tot[c]++;
-    } else {
-      b.p2 |= bit;
-      if (sym > 4) {
-        b.p0 |= bit;
-        ++nmark;
-        bwt_marker_pos.push_back(p - 1);
-        bool at_base = p < prg.size() && prg[p] <= 4;
-        uint32_t hm = at_base ? hit_marker[p] : 0, ha = at_base ? hit_allele[p] : 0;
-        uint32_t jlo = kNoAllele, jhi = kNoAllele;
-        if (hm > 4) {
-          if (hm & 1u) {  // exit: simple when nothing is adjacent to the left of the site (tm_odd empty)
-            uint32_t slot = (hm - 5) / 2;
-            if (ix.tm_odd[slot] == 0) jlo = jhi = ix.site_sa[slot];
-          } else {  // entry: simple when the site has no empty allele / nested site at an allele end
-            uint32_t slot = (hm - 6) / 2;
-            if (ix.tm_even_off[slot + 1] == ix.tm_even_off[slot]) {
-              jlo = ix.allele_iv[2 * slot];
-              jhi = ix.allele_iv[2 * slot + 1];
-            }
+    for (int c = 0; c < 5; ++c) blk_cnt[5 * (size_t)bi + c] = cnt[c];
+  }
+  {  // exclusive prefix sums over the blocks (n / 64 entries: serial)
+    uint32_t run[5] = {0, 0, 0, 0, 0};
+    for (size_t bi = 0; bi < nblk; ++bi)
+      for (int c = 0; c < 5; ++c) {
+        const uint32_t x = blk_cnt[5 * bi + c];
+        blk_cnt[5 * bi + c] = run[c];
+        run[c] += x;
+      }
+    for (int c = 0; c < 5; ++c) blk_cnt[5 * (size_t)nblk + c] = run[c];
+  }
+  const uint32_t nmark_total = blk_cnt[5 * (size_t)nblk + 4];
+  ix.marker_hit.assign(8 * (size_t)nmark_total, 0);
+  std::vector<uint32_t> bwt_marker_pos(nmark_total);  // text position of the marker behind each BWT marker occurrence
+  constexpr uint32_t kBlkPerSuper = 1u << (kSuperShift - kBlkShift);
+#pragma omp parallel for schedule(static)
+  for (int64_t bi = 0; bi < nblk_i; ++bi) {
+    const uint32_t* tot = &blk_cnt[5 * (size_t)bi];
+    const uint32_t* sup = &blk_cnt[5 * (size_t)(bi & ~(int64_t)(kBlkPerSuper - 1))];  // counts at the superblock's start
+    if ((bi & (kBlkPerSuper - 1)) == 0)
+      for (int c = 0; c < 4; ++c) ix.super_cnt[4 * (size_t)(bi >> (kSuperShift - kBlkShift)) + c] = ix.c_base[c] + tot[c];
+    RankBlk& b = ix.rank_blk[bi];
+    b.cnt = 0;
+    for (int c = 0; c < 4; ++c) b.cnt |= (uint64_t)((tot[c] - sup[c]) & 0xFFFFu) << (16 * c);
+    uint32_t nmark = tot[4];
+    ix.mrank_blk[bi] = nmark;
+    uint64_t mbits = b.p2 & b.p0;  // the block's markers, in BWT order
+    while (mbits) {
+      const uint64_t i = ((uint64_t)bi << kBlkShift) + (uint64_t)__builtin_ctzll(mbits);
+      mbits &= mbits - 1;
+      const uint32_t p = ix.sa[i];
+      bwt_marker_pos[nmark] = p - 1;
+      const bool at_base = p < prg.size() && prg[p] <= 4;
+      const uint32_t hm = at_base ? hit_marker[p] : 0, ha = at_base ? hit_allele[p] : 0;
+      uint32_t jlo = kNoAllele, jhi = kNoAllele;
+      if (hm > 4) {
+        if (hm & 1u) {  // exit: simple when nothing is adjacent to the left of the site (tm_odd empty)
+          const uint32_t slot = (hm - 5) / 2;
+          if (ix.tm_odd[slot] == 0) jlo = jhi = ix.site_sa[slot];
+        } else {  // entry: simple when the site has no empty allele / nested site at an allele end
+          const uint32_t slot = (hm - 6) / 2;
+          if (ix.tm_even_off[slot + 1] == ix.tm_even_off[slot]) {
+            jlo = ix.allele_iv[2 * slot];
+            jhi = ix.allele_iv[2 * slot + 1];
           }
         }
-        ix.marker_hit.push_back(hm);
-        ix.marker_hit.push_back(ha);
-        ix.marker_hit.push_back(jlo);
-        ix.marker_hit.push_back(jhi);
-        // words 4,5 (SNP crossing table, site_sa of the entered site) are filled once the per-site
-        // tables exist; 6,7 pad the record to one 32 B sector
-        ix.marker_hit.push_back(kNotSnp);
-        ix.marker_hit.push_back(0);
-        ix.marker_hit.push_back(0);
-        ix.marker_hit.push_back(0);
       }
+      // words 4,5 (SNP crossing table, site_sa of the entered site) are filled once the per-site tables exist; 6,7
+      // (text positions behind the post-jump SA indices) below: the record is one 32 B sector
+      uint32_t* rec = &ix.marker_hit[8 * (size_t)nmark];
+      rec[0] = hm;
+      rec[1] = ha;
+      rec[2] = jlo;
+      rec[3] = jhi;
+      rec[4] = kNotSnp;
+      ++nmark;
     }
   }
   if (ix.marker_hit.empty()) ix.marker_hit.assign(8, 0);
@@ -450,7 +478,9 @@ void build_fm(HostIndex& ix, const std::vector<uint32_t>& hit_marker, const std:
     }
     if (ok) ix.site_snp[s] = tab;
   }
-  for (size_t m = 0; m + 7 < ix.marker_hit.size(); m += 8) {
+  const int64_t n_hit_words = (int64_t)ix.marker_hit.size();
+#pragma omp parallel for schedule(static)
+  for (int64_t m = 0; m < n_hit_words - 7; m += 8) {
     uint32_t hm = ix.marker_hit[m];
     if (hm > 4 && (hm & 1u) == 0 && ix.marker_hit[m + 2] != kNoAllele) {  // simple entry
       uint32_t slot = (hm - 6) / 2;
@@ -465,7 +495,9 @@ void build_fm(HostIndex& ix, const std::vector<uint32_t>& hit_marker, const std:
   // ---- text mode: the PRG as 2-bit codes + marker flags, jump records in text order, inverse SA ----
   const uint32_t L = (uint32_t)prg.size();
   ix.isa.assign(n, 0);
-  for (uint32_t i = 0; i < n; ++i) ix.isa[ix.sa[i]] = i;
+  const int64_t n_i = (int64_t)n;
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n_i; ++i) ix.isa[ix.sa[i]] = (uint32_t)i;
   const uint32_t ngrp = (L >> 4) + 1;
   ix.text_grp.assign(ngrp, TextGrp{0, 0});
   ix.text_super.assign((L >> kTextSuperShift) + 1, 0);
