@@ -1770,15 +1770,21 @@ struct Hull {
   uint32_t* e;   // cap triples (node, start, end); node == kNoAllele: empty slot
   uint32_t n, cap, shift;  // cap = 1 << (32 - shift)
   bool overflow;
+  bool at_limit;  // no larger table fits the memory it was given
 };
-GQ_DEV inline void hull_init(Hull& h, uint32_t* mem, uint32_t words) {
+// A table of at most 2^want_lg slots (fewer if `words` cannot hold them). The table is sized for what a walk
+// touches — a 150-base read visits a few dozen nodes — not for the arena: clearing and, at the end, scanning a table
+// that filled the whole arena cost every strand 512 stores + 512 loads (65536 each in the large-arena re-runs).
+// record_general starts small and rebuilds the table four times larger when it fills up.
+GQ_DEV inline void hull_init(Hull& h, uint32_t* mem, uint32_t words, uint32_t want_lg) {
   uint32_t lg = 2;
-  while (lg < 20 && 3u * (2u << lg) <= words) ++lg;
+  while (lg < 20 && lg < want_lg && 3u * (2u << lg) <= words) ++lg;
   h.e = mem;
   h.cap = 1u << lg;
   h.shift = 32 - lg;
   h.n = 0;
   h.overflow = 3u * h.cap > words;
+  h.at_limit = lg < want_lg;  // the arena holds no larger table
   if (!h.overflow)
     for (uint32_t i = 0; i < h.cap; ++i) mem[3 * i] = kNoAllele;
 }
@@ -1947,13 +1953,13 @@ GQ_DEV uint32_t record_general(const IndexView& v, const BatchView& b, const Cov
     return REC_OK;
   }
   // ---- pass 2: loci of the chosen class + per-node hulls (PbCovRecorder :221-296) ----
-  ll.n_loci = 0;
   Hull hull;
-  hull_init(hull, arena + sc.used, arena_words - sc.used);
-  if (hull.overflow) return REC_ARENA;
-  {
+  for (uint32_t hull_lg = 6;; hull_lg += 2) {  // 64 slots first; a table that fills up is rebuilt four times larger
+    ll.n_loci = 0;
+    hull_init(hull, arena + sc.used, arena_words - sc.used, hull_lg);
+    if (hull.overflow) return REC_ARENA;
     const uint32_t* p = recs;
-    for (uint32_t j = 0; j < ns; ++j) {
+    for (uint32_t j = 0; j < ns && !hull.overflow; ++j) {
       StateRec st = parse_rec(p);
       p += st.words();
       if (rep[j] != (uint32_t)chosen) continue;  // not a state of the chosen class (or path-less)
@@ -1977,14 +1983,15 @@ GQ_DEV uint32_t record_general(const IndexView& v, const BatchView& b, const Cov
         t.bad = false;
         if (first) {
           first = false;
-          while (t.next()) hull_add(v, hull, t.cur, t.start_pos, t.end_pos);
+          while (!hull.overflow && t.next()) hull_add(v, hull, t.cur, t.start_pos, t.end_pos);
         } else if (t.next())
           hull_add(v, hull, t.cur, t.start_pos, t.end_pos);
         if (t.bad) gq_atomic_or(c.error_flags, 2u);
-        if (hull.overflow) return REC_ARENA;
-        if (occ == st.hi) break;
+        if (hull.overflow || occ == st.hi) break;
       }
     }
+    if (!hull.overflow) break;
+    if (hull.at_limit) return REC_ARENA;  // the arena holds no larger table: re-run with a larger arena
   }
   // sort loci by (site, allele) — std::set<VariantLocus> order
   for (uint32_t i = 1; i < ll.n_loci; ++i) {
