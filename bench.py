@@ -224,6 +224,11 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # torchrun sets OMP_NUM_THREADS=1 for every rank unless the caller chose a value: the index build (host, OpenMP)
+    # then runs on one thread (config 4: 300 s instead of ~60). Give every rank its share of the host's cores instead.
+    n_local = env_int("LOCAL_WORLD_SIZE", env_int("WORLD_SIZE", 1))
+    if n_local > 1 and os.environ.get("OMP_NUM_THREADS", "1") == "1":
+        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // n_local))
     import torch
     import torch.distributed as dist
     from gramtools_b200 import QuasimapIndex, comm_unique_id, pack_reads
