@@ -84,6 +84,8 @@ def emu_lib():
         lib.emu_grouped.restype = C.c_uint64
         lib.emu_stats.argtypes = [C.c_void_p, u64p]
         lib.emu_index_check.argtypes = [C.c_void_p]
+        lib.emu_index_digest.argtypes = [C.c_void_p]
+        lib.emu_index_digest.restype = C.c_uint64
         lib.emu_path_counters.argtypes = [u64p, C.c_int]
         lib.emu_force_general.argtypes = [C.c_int]
         lib.emu_set_gtab_cap.argtypes = [C.c_void_p, C.c_uint32]
@@ -222,6 +224,10 @@ class Emu:
         c = np.zeros(32, dtype=np.uint64)
         self.lib.emu_path_counters(_ptr(c, C.c_uint64), int(reset))
         return {k: int(v) for k, v in zip(self.ROUTES, c) if k != "-"}
+
+    def index_digest(self):
+        """FNV-1a over every array of the flat index."""
+        return int(self.lib.emu_index_digest(self.h))
 
     def index_check(self):
         if self.lib.emu_index_check(self.h) != 0:

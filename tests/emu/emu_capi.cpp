@@ -362,6 +362,27 @@ void emu_path_counters(uint64_t* out32, int reset) {
 }
 // Structural invariants of the flat index (what the kernels assume about text mode, the seed view, ...),
 // checked directly on the host copy. Returns 0, or -1 with the first violation in emu_last_error().
+// FNV-1a over every array of the flat index: two builds of one PRG must give the same value whatever the thread
+// count, the suffix-array builder or the build order inside the parallel passes
+uint64_t emu_index_digest(void* ev) {
+  const HostIndex& h = ((Emu*)ev)->h;
+  uint64_t d = 1469598103934665603ull;
+  auto mix = [&](const void* p, size_t bytes) {
+    const uint8_t* b = (const uint8_t*)p;
+    for (size_t i = 0; i < bytes; ++i) d = (d ^ b[i]) * 1099511628211ull;
+    d = (d ^ bytes) * 1099511628211ull;
+  };
+#define MIX(vec) mix((vec).data(), (vec).size() * sizeof((vec)[0]))
+  MIX(h.prg); MIX(h.sa); MIX(h.isa); MIX(h.rank_blk); MIX(h.super_cnt); MIX(h.mrank_blk); MIX(h.marker_hit);
+  MIX(h.tmarker_hit); MIX(h.text_grp); MIX(h.text_super); MIX(h.pos2node); MIX(h.nodes); MIX(h.edges);
+  MIX(h.site_sa); MIX(h.allele_iv); MIX(h.entry_next); MIX(h.site_snp); MIX(h.allele_off); MIX(h.n_alleles);
+  MIX(h.kmer_bits); MIX(h.kmer_off); MIX(h.kmer_states); MIX(h.kmer_paths); MIX(h.seed_off); MIX(h.seed_ent);
+  MIX(h.seed_state); MIX(h.site_rec); MIX(h.apos);
+#undef MIX
+  mix(h.c_base, sizeof(h.c_base));
+  return d;
+}
+
 int emu_index_check(void* ev) {
   auto* e = (Emu*)ev;
   const HostIndex& h = e->h;

@@ -316,3 +316,22 @@ def test_random_shapes():
         o.map(bases, offs, seeds)
         e.map(bases, offs, seeds, arena_words=int(rng.choice([64, 256, 1024])))
         assert_parity(e.result(), o.result(), f"random-shape-{case}")
+
+
+def test_index_independent_of_threads_and_sa_builder():
+    """The flat index is a pure function of (PRG, k): the parallel passes of the builder (rank blocks, marker records,
+    ISA, k-mer subtrees, seed view) give the same bytes on 1 and on 8 threads, and with the 64-bit SA-IS."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "from common import Emu\nfrom gramtools_b200 import synth\n"
+            "for prg, k in ((synth.make_nested_prg(12, 600, 5), 6), (synth.make_snp_prg(120000, 4000, 2)[0], 8),\n"
+            "               (synth.make_indel_prg(30000, 1500, 3)[0], 7)):\n"
+            "    print(Emu(prg, k).index_digest())\n") % (ROOT, os.path.join(ROOT, "tests"))
+    outs = []
+    for env_extra in ({"OMP_NUM_THREADS": "1"}, {"OMP_NUM_THREADS": "8"}, {"OMP_NUM_THREADS": "3", "GQ_SAIS64": "1"}):
+        env = dict(os.environ, **env_extra)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout.split())
+    assert len(outs[0]) == 3 and outs[0] == outs[1] == outs[2], outs
