@@ -457,4 +457,33 @@ GQ_HD void run_stack(Stack& s, const IndexView& v, const uint32_t* super_cnt, Re
   }
 }
 
+// One-base steps for ALL four bases at once (k-mer index construction, index_build.cpp): the marker processing of a
+// state — scan, jumps, the states they spawn — does not depend on the base that is consumed next, so it runs once;
+// every entry that reaches its extension point (pos == 1) is handed to `ready(entry, lo, hi)` instead of being extended,
+// in the order run_stack would have extended (and then emitted) it. The caller extends each ready state by the
+// four bases with rank queries.
+#if defined(__CUDACC__)
+#pragma nv_exec_check_disable
+#endif
+template <class ReadyFn>
+GQ_HD void run_stack_ready(Stack& s, const IndexView& v, ReadyFn& ready) {
+  while (!stack_empty(s) && !s.overflow) {
+    uint32_t* t = s.mem + s.top;
+    uint32_t w0 = t[0];
+    uint32_t kind = w0 >> 28, pos = w0 & 0x0FFFFFFFu;
+    if (kind == K_JUMP) {
+      process_jump(s, v);
+      continue;
+    }
+    uint32_t lo = t[1], hi = t[2];
+    if (kind == K_SCAN && interval_has_marker(v, lo, hi)) {
+      t[0] = pos | (K_READY << 28);
+      scan_markers(s, v, pos, lo, hi);
+      continue;
+    }
+    ready(t, lo, hi);
+    pop(s);
+  }
+}
+
 }  // namespace gq

@@ -2,6 +2,7 @@
 #include "index_build.hpp"
 
 #include <algorithm>
+#include <array>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -520,34 +521,54 @@ void build_fm(HostIndex& ix, const std::vector<uint32_t>& hit_marker, const std:
 }
 
 // ---- all-k-mers index (reference: src/build/kmer_index/build.cpp:18-148) ---------------------
-struct HState {
-  uint32_t lo, hi;
-  std::vector<uint32_t> path;  // nt pairs then ng sites
-  uint32_t counts;
+// The search states of one k-mer prefix: fixed-size records + one pool of path words (nt pairs, then ng sites) — no
+// allocation per state (a std::vector per state made malloc the hot spot of the build).
+struct HRec {
+  uint32_t lo, hi, counts, path_off;
 };
-
-struct OneBaseRead {
-  uint32_t c;
-  uint32_t operator()(uint32_t) const { return c; }
-};
-struct Collect {
-  std::vector<HState>* out;
-  void operator()(const uint32_t* t) {
-    HState h;
-    h.lo = t[1];
-    h.hi = t[2];
-    h.counts = t[3];
-    uint32_t w = entry_words(t[3]);
-    h.path.assign(t + kHdr, t + w);
-    out->push_back(std::move(h));
+struct StateList {
+  std::vector<HRec> recs;
+  std::vector<uint32_t> pool;
+  void clear() {
+    recs.clear();
+    pool.clear();
+  }
+  bool empty() const { return recs.empty(); }
+  void swap(StateList& o) {
+    recs.swap(o.recs);
+    pool.swap(o.pool);
   }
 };
 
-// all successors of `in` after consuming base code c (marker processing first unless `first`)
-void step_states(const IndexView& v, const std::vector<HState>& in, uint32_t c, bool first,
-                 std::vector<uint32_t>& arena, std::vector<HState>& out) {
-  out.clear();
-  for (const auto& st : in) {
+// All successors of `in` after consuming each of the four bases (marker processing first unless `first`): the marker
+// processing of a state does not depend on the base consumed next, so it runs once (run_stack_ready) and every
+// resulting state is extended by A, C, G and T with one pair of rank-block loads. out[c] keeps, per base, the order in
+// which the reference's breadth-first pass would have produced the states (build.cpp:55-131).
+struct ReadyCollect {
+  const IndexView* v;
+  StateList* out;  // [4]
+  void operator()(const uint32_t* t, uint32_t lo, uint32_t hi) {
+    const uint32_t b0 = lo >> kBlkShift, b1 = (hi + 1) >> kBlkShift;
+    const RankBlk B0 = load_blk(v->rank_blk + b0);
+    const RankBlk B1 = (b1 == b0) ? B0 : load_blk(v->rank_blk + b1);
+    const uint32_t* s0 = v->super_cnt + 4 * (b0 >> (kSuperShift - kBlkShift));
+    const uint32_t* s1 = v->super_cnt + 4 * (b1 >> (kSuperShift - kBlkShift));
+    const uint32_t w = entry_words(t[3]);
+    for (uint32_t c = 0; c < 4; ++c) {
+      const uint32_t r0 = rank_in_blk(B0, s0, c, lo), r1 = rank_in_blk(B1, s1, c, hi + 1);
+      if (r1 <= r0) continue;
+      StateList& o = out[c];
+      o.recs.push_back(HRec{r0, r1 - 1, t[3], (uint32_t)o.pool.size()});  // C[c] is folded into the superblock counters
+      o.pool.insert(o.pool.end(), t + kHdr, t + w);
+    }
+  }
+};
+
+void step_states4(const IndexView& v, const StateList& in, bool first, std::vector<uint32_t>& arena,
+                  StateList* out /* [4] */) {
+  for (uint32_t c = 0; c < 4; ++c) out[c].clear();
+  for (const HRec& st : in.recs) {
+    const uint32_t pw = entry_words(st.counts) - kHdr;
     while (true) {
       Stack s;
       s.mem = arena.data();
@@ -560,13 +581,13 @@ void step_states(const IndexView& v, const std::vector<HState>& in, uint32_t c, 
       t[2] = st.hi;
       t[3] = st.counts;
       t[4] = kNoAllele;
-      std::copy(st.path.begin(), st.path.end(), t + kHdr);
-      OneBaseRead rd{c};
-      size_t mark = out.size();
-      Collect col{&out};
-      run_stack(s, v, v.super_cnt, rd, col);
+      std::copy(in.pool.begin() + st.path_off, in.pool.begin() + st.path_off + pw, t + kHdr);
+      size_t mark[4], pmark[4];
+      for (uint32_t c = 0; c < 4; ++c) mark[c] = out[c].recs.size(), pmark[c] = out[c].pool.size();
+      ReadyCollect col{&v, out};
+      run_stack_ready(s, v, col);
       if (!s.overflow) break;
-      out.resize(mark);
+      for (uint32_t c = 0; c < 4; ++c) out[c].recs.resize(mark[c]), out[c].pool.resize(pmark[c]);
       arena.resize(arena.size() * 2);
     }
   }
@@ -577,28 +598,24 @@ struct KmerOut {
   std::vector<uint32_t> n_states;  // states in that run
   std::vector<KmerState> states;   // path_off relative to this thread's `paths`
   std::vector<uint32_t> paths;
+  void add(uint32_t code, const StateList& l) {
+    codes.push_back(code);
+    n_states.push_back((uint32_t)l.recs.size());
+    const uint32_t base = (uint32_t)paths.size();
+    paths.insert(paths.end(), l.pool.begin(), l.pool.end());
+    for (const HRec& h : l.recs) states.push_back(KmerState{h.lo, h.hi, base + h.path_off, h.counts});
+  }
 };
 
-void kmer_recurse(const IndexView& v, uint32_t k, uint32_t depth, uint32_t code, const std::vector<HState>& cur,
-                  std::vector<std::vector<HState>>& levels, std::vector<uint32_t>& arena, KmerOut& out) {
+void kmer_recurse(const IndexView& v, uint32_t k, uint32_t depth, uint32_t code, const StateList& cur,
+                  std::vector<std::array<StateList, 4>>& levels, std::vector<uint32_t>& arena, KmerOut& out) {
+  std::array<StateList, 4>& nxt = levels[depth];
+  step_states4(v, cur, depth == 0, arena, nxt.data());
   for (uint32_t c = 0; c < 4; ++c) {
-    std::vector<HState>& nxt = levels[depth];
-    step_states(v, cur, c, depth == 0, arena, nxt);
-    if (nxt.empty()) continue;
+    if (nxt[c].empty()) continue;
     uint32_t ncode = code | (c << (2 * (k - 1 - depth)));  // base j of the k-mer sits at bits [2j, 2j+2)
-    if (depth + 1 == k) {
-      out.codes.push_back(ncode);
-      out.n_states.push_back((uint32_t)nxt.size());
-      for (auto& h : nxt) {
-        KmerState ks{h.lo, h.hi, (uint32_t)out.paths.size(), h.counts};
-        out.paths.insert(out.paths.end(), h.path.begin(), h.path.end());
-        out.states.push_back(ks);
-      }
-    } else {
-      std::vector<HState> keep;
-      keep.swap(nxt);  // levels[depth] is reused by the siblings' children
-      kmer_recurse(v, k, depth + 1, ncode, keep, levels, arena, out);
-    }
+    if (depth + 1 == k) out.add(ncode, nxt[c]);
+    else kmer_recurse(v, k, depth + 1, ncode, nxt[c], levels, arena, out);  // levels[depth] stays live for the siblings
   }
 }
 
@@ -617,42 +634,62 @@ void build_kmers(HostIndex& ix) {
   ix.kmer_bits.assign((((nk + 31) / 32) + 3) & ~3ull, 0);  // whole 16-byte groups: copied to shared memory as uint4
   ix.kmer_off.assign(nk + 1, 0);
   IndexView v = ix.view();
-  // independent subtrees: the first min(k,2) bases (rightmost of the k-mer)
-  const uint32_t pre = std::min<uint32_t>(k, 2);
+  // The first `pre` bases (rightmost of the k-mer) are expanded breadth first, every prefix node once — these levels
+  // hold the wide intervals whose marker scans are the expensive ones — then the 4^pre subtrees are independent tasks,
+  // handed out dynamically (256 of them for k >= 4: hosts with more than 16 cores stay busy, heavy subtrees do not
+  // serialise the tail). Task results are merged in the order of a depth-first walk with the second base as the
+  // outermost loop, which is the order this builder has always produced (the path pool's layout depends on it).
+  const uint32_t pre = std::min<uint32_t>(k, 4);
   const uint32_t ntask = 1u << (2 * pre);
-  std::vector<KmerOut> outs(ntask);
   std::string err;
+  std::vector<StateList> level(1);
+  level[0].recs.push_back(HRec{0, ix.n - 1, 0, 0});
+  for (uint32_t d = 0; d < pre && err.empty(); ++d) {  // node index: first consumed base = most significant digit
+    std::vector<StateList> next(level.size() * 4);
+    const int n_nodes = (int)level.size();
 #pragma omp parallel for schedule(dynamic, 1)
-  for (int task = 0; task < (int)ntask; ++task) {
+    for (int node = 0; node < n_nodes; ++node) {
+      if (level[node].empty()) continue;
+      try {
+        std::vector<uint32_t> arena(1u << 16);
+        std::array<StateList, 4> out4;
+        step_states4(v, level[node], d == 0, arena, out4.data());
+        for (uint32_t c = 0; c < 4; ++c) next[4 * (size_t)node + c].swap(out4[c]);
+      } catch (const std::exception& e) {
+#pragma omp critical
+        err = e.what();
+      }
+    }
+    level.swap(next);
+  }
+  if (!err.empty()) throw std::runtime_error(err);
+  // merge order: tasks sorted by (second base, first base, third, fourth, ...)
+  std::vector<uint32_t> order(ntask);
+  for (uint32_t t = 0; t < ntask; ++t) order[t] = t;
+  auto digit = [&](uint32_t node, uint32_t d) { return (node >> (2 * (pre - 1 - d))) & 3u; };  // d-th consumed base
+  auto merge_key = [&](uint32_t node) {
+    uint32_t key = 0;
+    for (uint32_t d = 0; d < pre; ++d) {
+      const uint32_t src = d == 0 ? (pre > 1 ? 1u : 0u) : (d == 1 ? 0u : d);
+      key = key * 4 + digit(node, src);
+    }
+    return key;
+  };
+  std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b2) { return merge_key(a) < merge_key(b2); });
+  std::vector<KmerOut> outs(ntask);  // outs[i] = result of task order[i]
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int ti = 0; ti < (int)ntask; ++ti) {
+    const uint32_t node = order[ti];
+    if (level[node].empty()) continue;
     try {
       std::vector<uint32_t> arena(1u << 16);
-      std::vector<std::vector<HState>> levels(k);
-      std::vector<HState> cur{HState{0, ix.n - 1, {}, 0}};
-      std::vector<HState> nxt;
+      std::vector<std::array<StateList, 4>> levels(k);
       uint32_t code = 0;
-      bool dead = false;
-      for (uint32_t d = 0; d < pre; ++d) {
-        uint32_t c = ((uint32_t)task >> (2 * d)) & 3u;
-        step_states(v, cur, c, d == 0, arena, nxt);
-        code |= c << (2 * (k - 1 - d));
-        cur.swap(nxt);
-        if (cur.empty()) {
-          dead = true;
-          break;
-        }
-      }
-      if (dead) continue;
-      KmerOut& out = outs[task];
-      if (pre == k) {
-        out.codes.push_back(code);
-        out.n_states.push_back((uint32_t)cur.size());
-        for (auto& h : cur) {
-          KmerState ks{h.lo, h.hi, (uint32_t)out.paths.size(), h.counts};
-          out.paths.insert(out.paths.end(), h.path.begin(), h.path.end());
-          out.states.push_back(ks);
-        }
-      } else
-        kmer_recurse(v, k, pre, code, cur, levels, arena, out);
+      for (uint32_t d = 0; d < pre; ++d) code |= digit(node, d) << (2 * (k - 1 - d));
+      KmerOut& out = outs[ti];
+      if (pre == k) out.add(code, level[node]);
+      else kmer_recurse(v, k, pre, code, level[node], levels, arena, out);
+      level[node].clear();
     } catch (const std::exception& e) {
 #pragma omp critical
       err = e.what();

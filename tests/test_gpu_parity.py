@@ -446,7 +446,7 @@ def test_gpu_suffix_array(built_lib):
     rep = rng.integers(1, 5, size=3000).astype(np.uint32)
     prgs = {
         "snp": synth.make_snp_prg(200_000, 5_000, 1)[0],
-        "indel": synth.make_indel_prg(50_000, 2_000, 2)[0],
+        "indel": synth.make_indel_prg(50_000, 2_000, 2),
         "nested": synth.make_nested_prg(20, 800, 3),
         "nested, coinciding alleles": synth.make_nested_prg(6, 500, 4, distinct=False),
         "repeats": np.concatenate([rep, rng.integers(1, 5, size=100).astype(np.uint32), rep, rep[:1500], rep]),

@@ -326,7 +326,7 @@ def test_index_independent_of_threads_and_sa_builder():
     code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
             "from common import Emu\nfrom gramtools_b200 import synth\n"
             "for prg, k in ((synth.make_nested_prg(12, 600, 5), 6), (synth.make_snp_prg(120000, 4000, 2)[0], 8),\n"
-            "               (synth.make_indel_prg(30000, 1500, 3)[0], 7)):\n"
+            "               (synth.make_indel_prg(30000, 1500, 3), 7)):\n"
             "    print(Emu(prg, k).index_digest())\n") % (ROOT, os.path.join(ROOT, "tests"))
     outs = []
     for env_extra in ({"OMP_NUM_THREADS": "1"}, {"OMP_NUM_THREADS": "8"}, {"OMP_NUM_THREADS": "3", "GQ_SAIS64": "1"}):
