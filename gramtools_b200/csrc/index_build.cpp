@@ -55,16 +55,36 @@ IndexView HostIndex::view() const {
 }
 
 int32_t compress_text(const uint32_t* prg, uint64_t n_symbols, std::vector<uint32_t>& present, std::vector<int32_t>& text) {
-  present.assign(prg, prg + n_symbols);
-  std::sort(present.begin(), present.end());
-  present.erase(std::unique(present.begin(), present.end()), present.end());
+  uint32_t maxs = 0;
+  const int64_t n_i = (int64_t)n_symbols;
+#pragma omp parallel for reduction(max : maxs) schedule(static)
+  for (int64_t i = 0; i < n_i; ++i) maxs = std::max(maxs, prg[i]);
+  present.clear();
+  if ((uint64_t)maxs <= 4 * n_symbols + 1024) {
+    // symbols are dense (bases and consecutive markers): a presence table instead of sorting a copy of the PRG
+    std::vector<uint8_t> seen((size_t)maxs + 1, 0);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n_i; ++i)
+      if (!seen[prg[i]]) seen[prg[i]] = 1;  // benign race: every writer stores 1
+    for (uint64_t sym = 0; sym <= maxs; ++sym)
+      if (seen[sym]) present.push_back((uint32_t)sym);
+  } else {
+    present.assign(prg, prg + n_symbols);
+    std::sort(present.begin(), present.end());
+    present.erase(std::unique(present.begin(), present.end()), present.end());
+  }
   const int32_t sigma = (int32_t)present.size() + 1;
   text.assign(n_symbols + 1, 0);
-  // symbols are dense near 1..4 and markers; a direct table avoids n binary searches
-  const uint32_t maxs = present.empty() ? 0 : present.back();
-  std::vector<int32_t> tab((size_t)maxs + 1, 0);
-  for (size_t i = 0; i < present.size(); ++i) tab[present[i]] = (int32_t)i + 1;
-  for (uint64_t i = 0; i < n_symbols; ++i) text[i] = tab[prg[i]];
+  if ((uint64_t)maxs <= 4 * n_symbols + 1024) {
+    std::vector<int32_t> tab((size_t)maxs + 1, 0);
+    for (size_t i = 0; i < present.size(); ++i) tab[present[i]] = (int32_t)i + 1;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n_i; ++i) text[i] = tab[prg[i]];
+  } else {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n_i; ++i)
+      text[i] = (int32_t)(std::lower_bound(present.begin(), present.end(), prg[i]) - present.begin()) + 1;
+  }
   text[n_symbols] = 0;  // the sentinel sdsl appends
   return sigma;
 }

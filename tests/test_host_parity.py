@@ -89,6 +89,24 @@ def test_edge_cases():
     _check(prg, k, bases, offs, what="empty-batch")
 
 
+def test_sparse_marker_ids():
+    """Alphabet compression (sdsl's char2comp) with marker ids that are far apart — the presence-table branch and, for
+    large ids, the sort-based one: the suffix array is the brute-force one and the flat index passes its invariants.
+    (Coverage for such PRGs is undefined in the reference: its vectors are indexed by (site - 5) / 2.)"""
+    base = np.asarray(synth.make_snp_prg(400, 12, 8)[0]).astype(np.int64)
+    for stride, offset in ((1, 0), (3, 0), (50, 1000), (20000, 0)):
+        prg = base.copy()
+        m = prg >= 5
+        site = (prg[m] - 5) // 2
+        prg[m] = 5 + 2 * (site * stride + offset) + ((prg[m] - 5) % 2)
+        prg = prg.astype(np.uint32)
+        e = Emu(prg, 4)
+        e.index_check()
+        text = np.concatenate([prg.astype(np.int64), [0]])
+        want = sorted(range(text.size), key=lambda i: text[i:].tolist())
+        assert e.sa().tolist() == want, (stride, offset)
+
+
 def test_reference_test_prgs():
     """PRGs + reads of the reference's quasimap tests (test_quasimap.cpp), both strands, incl. the seed-dependent
     selections (seeds 42 / 150 / 29 / 200)."""
