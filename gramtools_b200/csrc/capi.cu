@@ -665,7 +665,31 @@ const char* gq_last_error(void) { return g_err.c_str(); }
 // developer hook (not in gq.h): warp-loop statistics when built with -DGQ_DEBUG_COUNTERS
 void gq_debug_counters(unsigned long long* out32) { gq::debug_counters(out32); }
 
+static int index_build_impl(const uint32_t* prg, uint64_t n_symbols, uint32_t kmer_size, int device, const char* kmer_dir,
+                            gq_index** out);
+
 int gq_index_build(const uint32_t* prg, uint64_t n_symbols, uint32_t kmer_size, int device, gq_index** out) {
+  return index_build_impl(prg, n_symbols, kmer_size, device, nullptr, out);
+}
+
+int gq_index_build_from_gram_dir(const uint32_t* prg, uint64_t n_symbols, uint32_t kmer_size, int device,
+                                 const char* gram_dir, gq_index** out) {
+  if (!gram_dir) {
+    g_err = "null argument";
+    return -1;
+  }
+  return index_build_impl(prg, n_symbols, kmer_size, device, gram_dir, out);
+}
+
+int gq_kmer_index_dump(const gq_index* ix, const char* gram_dir) {
+  GQ_TRY
+  if (!ix || !gram_dir) throw std::runtime_error("null argument");
+  gq::kmer_index_dump(ix->h, gram_dir);
+  GQ_CATCH
+}
+
+static int index_build_impl(const uint32_t* prg, uint64_t n_symbols, uint32_t kmer_size, int device, const char* kmer_dir,
+                            gq_index** out) {
   gq_index* ix = nullptr;
   GQ_TRY
   if (!prg || !out) throw std::runtime_error("null argument");
@@ -682,7 +706,7 @@ int gq_index_build(const uint32_t* prg, uint64_t n_symbols, uint32_t kmer_size, 
   gq::SaBuilder sab = [](const std::vector<int32_t>& text, int32_t sigma, void* c) {
     return gq::gpu_suffix_array(text, sigma, ((SaCtx*)c)->device);
   };
-  gq::build_host_index(prg, n_symbols, kmer_size, ix->h, getenv("GQ_HOST_SA") ? nullptr : sab, &sctx);
+  gq::build_host_index(prg, n_symbols, kmer_size, ix->h, getenv("GQ_HOST_SA") ? nullptr : sab, &sctx, kmer_dir);
   finish_handle(ix);
   *out = ix;
   }

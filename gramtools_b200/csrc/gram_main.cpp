@@ -13,8 +13,10 @@
 //   G/read_stats.json                              (read_stats.cpp:162-209)
 // and prints the five counters as genotype.cpp:55-66 does. The genotyping step that follows in the
 // reference (LevelGenotyper, genotype.cpp:68-118) is out of scope of this back-end.
-// Only gram_dir/prg is consumed: the SDSL / Boost files next to it are third-party formats and the
-// index is rebuilt from the PRG.
+// gram_dir/prg is what is consumed: FM-index, masks and coverage graph are rebuilt from it (their SDSL / Boost
+// archives are third-party formats); the k-mer index is searched again or, with
+// --kmer_index_from_gram_dir, loaded from gram_dir's kmers / kmers_stats / sa_intervals / paths. `gram build` writes
+// those four files.
 #include <sys/stat.h>
 #include <zlib.h>
 
@@ -47,13 +49,15 @@ struct Params {
   bool has_seed = false, debug = false;
   uint32_t seed = 0;
   int devices = 1;  // --devices N (or GQ_DEVICES): GPUs of this node the reads are sharded over; 0 = all
+  bool kmers_from_gram_dir = false;  // --kmer_index_from_gram_dir: load kmers / kmers_stats / sa_intervals / paths
 };
 
 [[noreturn]] void usage_fail(const std::string& msg) {
   std::cout << msg << std::endl;
   std::cout << "genotype options:\n  --gram_dir arg\n  --reads arg [arg…]\n  --sample_id arg\n"
                "  --ploidy arg {haploid, diploid}\n  --kmer_size arg\n  --genotype_dir arg\n"
-               "  --max_threads arg (=1)\n  --seed arg\n  --devices arg (=1; B200 back-end: GPUs to shard the reads over, 0 = all)\n";
+               "  --max_threads arg (=1)\n  --seed arg\n  --devices arg (=1; B200 back-end: GPUs to shard the reads over, 0 = all)\n"
+               "  --kmer_index_from_gram_dir (B200 back-end: load the k-mer index files of gram_dir instead of rebuilding it)\n";
   std::exit(1);
 }
 
@@ -80,6 +84,7 @@ Params parse_genotype(int argc, const char* const* argv, int first) {
       p.seed = (uint32_t)std::stoul(value("seed"));
       p.has_seed = true;
     } else if (a == "--devices") p.devices = std::stoi(value("devices"));
+    else if (a == "--kmer_index_from_gram_dir") p.kmers_from_gram_dir = true;
     else if (a == "--debug") p.debug = true;
     else usage_fail("unrecognised option '" + a + "'");
   }
@@ -272,6 +277,40 @@ struct PinnedBatch {
 
 }  // namespace
 
+// `gram build --gram_dir D --kmer_size K`: the k-mer index part of commands::build::run (build.cpp:8-71,
+// kmer_index::build + dump): reads D/prg (as written by the Python front-end / an earlier reference build), builds the
+// index on GPU 0 and leaves D/kmers, D/kmers_stats, D/sa_intervals, D/paths in the reference's sdsl format. The other
+// files of a reference gram_dir (fm_index, masks, cov_graph: SDSL / Boost archives) are not written — this back-end
+// rebuilds them from D/prg at `genotype` time. Options the reference's build takes and this one does not need
+// (--ref, --prg, --max_threads, --all_kmers, ...) are accepted and ignored.
+int run_build(int argc, const char* const* argv, int first) {
+  std::string gram_dir;
+  uint32_t kmer_size = 0;
+  bool got_k = false;
+  for (int i = first; i < argc; ++i) {
+    const std::string a = argv[i];
+    if (a == "--gram_dir" && i + 1 < argc) gram_dir = argv[++i];
+    else if (a == "--kmer_size" && i + 1 < argc) {
+      kmer_size = (uint32_t)std::stoul(argv[++i]);
+      got_k = true;
+    } else if (a.rfind("--", 0) == 0 && i + 1 < argc && std::strncmp(argv[i + 1], "--", 2) != 0) ++i;  // ignored option + value
+  }
+  if (gram_dir.empty() || !got_k) {
+    std::cout << "build options:\n  --gram_dir arg\n  --kmer_size arg\n";
+    return 1;
+  }
+  std::cout << "Executing build command" << std::endl;
+  std::vector<uint32_t> prg = read_prg(join_path(gram_dir, "prg"));
+  gq_index* idx = nullptr;
+  check(gq_index_build(prg.data(), prg.size(), kmer_size, 0, &idx));
+  check(gq_kmer_index_dump(idx, gram_dir.c_str()));
+  gq_layout lay;
+  check(gq_index_describe(idx, &lay));
+  std::cout << "Indexed kmers search states: " << lay.n_kmer_states << std::endl;
+  check(gq_index_destroy(idx));
+  return 0;
+}
+
 int main(int argc, const char* const* argv) {
   // main.cpp:51-100: `gram` alone prints the global help and exits 0 (gramtools_main.py:80-90 relies on it)
   std::string cmd;
@@ -291,12 +330,12 @@ int main(int argc, const char* const* argv) {
   if (cmd.empty()) {
     std::cout << "Gramtools! Global options:\n  --command arg   command to execute: {build, genotype, simulate}\n"
                  "  --help          Produce this help message\n  --debug         Turn on debug output\n"
-                 "(B200 quasimap back-end: only `genotype` is served)\n";
+                 "(B200 quasimap back-end: `genotype` (quasimap part) and `build` (k-mer index files) are served)\n";
     return 0;
   }
+  if (cmd == "build") return run_build(argc, argv, first);
   if (cmd != "genotype") {
-    std::cout << (cmd == "build" || cmd == "simulate" ? "Command not served by the B200 quasimap back-end: "
-                                                      : "Unrecognised command: ")
+    std::cout << (cmd == "simulate" ? "Command not served by the B200 quasimap back-end: " : "Unrecognised command: ")
               << cmd << std::endl;
     return 1;
   }
@@ -336,7 +375,12 @@ int main(int argc, const char* const* argv) {
   check(gq_device_count(&have));
   if (n_dev <= 0 || n_dev > have) n_dev = have > 0 ? (n_dev <= 0 ? have : std::min(n_dev, have)) : 1;
   std::vector<gq_index*> handles(n_dev, nullptr);
-  check(gq_index_build(prg.data(), prg.size(), p.kmer_size, 0, &handles[0]));  // host index built once ...
+  // host index built once ... (k-mer index searched, or — as kmer_index::load does, genotype.cpp:40 — taken from the
+  // sdsl files `gram build` left in gram_dir)
+  if (p.kmers_from_gram_dir || std::getenv("GQ_KMER_INDEX_FROM_GRAM_DIR"))
+    check(gq_index_build_from_gram_dir(prg.data(), prg.size(), p.kmer_size, 0, p.gram_dir.c_str(), &handles[0]));
+  else
+    check(gq_index_build(prg.data(), prg.size(), p.kmer_size, 0, &handles[0]));
   for (int d = 1; d < n_dev; ++d) check(gq_index_clone(handles[0], d, &handles[d]));  // ... uploaded per GPU
   if (n_dev > 1) check(gq_comm_init_all(handles.data(), n_dev));
   gq_index* idx = handles[0];

@@ -60,8 +60,17 @@ struct HostIndex {
 // `sa_builder` (optional): suffix array of the compressed text (symbols in [0, sigma), unique minimum at the end);
 // libgq passes the GPU builder (sa_gpu.cu), the test emulation leaves it null and gets the host SA-IS (sais.hpp).
 using SaBuilder = std::vector<uint32_t> (*)(const std::vector<int32_t>& text, int32_t sigma, void* ctx);
+// `kmer_index_dir` (optional): take the k-mer index from the four sdsl files of a gram_dir (kmers, kmers_stats,
+// sa_intervals, paths — kmer_index::load, load.cpp:161-173) instead of running the k-mer searches.
 void build_host_index(const uint32_t* prg, uint64_t n_symbols, uint32_t kmer_size, HostIndex& out,
-                      SaBuilder sa_builder = nullptr, void* sa_ctx = nullptr);
+                      SaBuilder sa_builder = nullptr, void* sa_ctx = nullptr, const char* kmer_index_dir = nullptr);
+
+// The k-mer index as the reference's gram_dir files (dump.cpp:27-141 / load.cpp:11-173); sdsl::int_vector
+// serialisation restated in index_build.cpp (parity unpinned: no SDSL here).
+void kmer_index_dump(const HostIndex& ix, const std::string& dir);
+void kmer_index_load(HostIndex& ix, const std::string& dir);
+void write_int_vector(const std::string& path, const std::vector<uint64_t>& values, uint32_t width, bool fixed_width);
+std::vector<uint64_t> read_int_vector(const std::string& path, uint32_t fixed_width, uint32_t* width_out);
 
 // PRG symbols -> ranks among the symbols present + 1 (sdsl's char2comp), sentinel 0 appended; returns sigma
 int32_t compress_text(const uint32_t* prg, uint64_t n_symbols, std::vector<uint32_t>& present, std::vector<int32_t>& text);

@@ -40,6 +40,8 @@ def load_library():
         "gq_index_build": [u32p, C.c_uint64, C.c_uint32, C.c_int, C.POINTER(vp)],
         "gq_index_destroy": [vp],
         "gq_suffix_array": [u32p, C.c_uint64, C.c_int, u32p, C.POINTER(C.c_int)],
+        "gq_kmer_index_dump": [vp, C.c_char_p],
+        "gq_index_build_from_gram_dir": [u32p, C.c_uint64, C.c_uint32, C.c_int, C.c_char_p, C.POINTER(vp)],
         "gq_index_describe": [vp, C.POINTER(GqLayout)],
         "gq_index_allele_offsets": [vp, u64p],
         "gq_index_per_base_layout": [vp, u64p],
@@ -188,12 +190,17 @@ def pack_ascii(text, offsets, n_threads=None):
 class QuasimapIndex:
     """One PRG index resident on one GPU + its coverage accumulators."""
 
-    def __init__(self, prg, kmer_size, device=0, _clone_of=None):
+    def __init__(self, prg, kmer_size, device=0, _clone_of=None, kmer_index_dir=None):
+        """kmer_index_dir: take the k-mer index from the sdsl files of that gram_dir (gq_index_build_from_gram_dir)."""
         self._lib = load_library()
         h = C.c_void_p()
         self._h = None
         if _clone_of is not None:
             self._check(self._lib.gq_index_clone(_clone_of._h, int(device), C.byref(h)))
+        elif kmer_index_dir is not None:
+            prg = np.ascontiguousarray(prg, dtype=np.uint32)
+            self._check(self._lib.gq_index_build_from_gram_dir(_ptr(prg, C.c_uint32), prg.size, int(kmer_size), int(device),
+                                                              os.fsencode(kmer_index_dir), C.byref(h)))
         else:
             prg = np.ascontiguousarray(prg, dtype=np.uint32)
             self._check(self._lib.gq_index_build(_ptr(prg, C.c_uint32), prg.size, int(kmer_size), int(device), C.byref(h)))
@@ -207,6 +214,10 @@ class QuasimapIndex:
     def _check(self, rc):
         if rc != 0:
             raise GqError(self._lib.gq_last_error().decode())
+
+    def kmer_index_dump(self, gram_dir):
+        """Write kmers / kmers_stats / sa_intervals / paths (the reference's gram_dir files of the k-mer index)."""
+        self._check(self._lib.gq_kmer_index_dump(self._h, os.fsencode(gram_dir)))
 
     def close(self):
         if getattr(self, "_h", None):

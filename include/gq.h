@@ -42,6 +42,16 @@ typedef struct gq_layout {
  * LE uint32, linearised_prg.cpp:8-45) and uploads them to GPU `device`. */
 int gq_index_build(const uint32_t* prg, uint64_t n_symbols, uint32_t kmer_size, int device, gq_index** out);
 int gq_index_destroy(gq_index* idx);
+/* The k-mer index as the reference keeps it in gram_dir: the four sdsl::int_vector files `kmers`, `kmers_stats`,
+ * `sa_intervals`, `paths` (written by kmer_index::dump, build/kmer_index/dump.cpp:27-141; read by kmer_index::load,
+ * load.cpp:11-173). gq_kmer_index_dump writes them from a built index (what `gram build` leaves behind);
+ * gq_index_build_from_gram_dir is gq_index_build with the k-mer searches replaced by loading those files (what
+ * `gram genotype` does, genotype.cpp:40) — FM-index, graph and masks are still rebuilt from `prg`. The sdsl
+ * serialisation is restated in index_build.cpp; PARITY UNPINNED (no SDSL in this environment, no serialised fixture
+ * in the reference): checked by hand-written golden bytes and round trips only. */
+int gq_kmer_index_dump(const gq_index* idx, const char* gram_dir);
+int gq_index_build_from_gram_dir(const uint32_t* prg, uint64_t n_symbols, uint32_t kmer_size, int device,
+                                 const char* gram_dir, gq_index** out);
 /* The suffix array alone — what sdsl::construct computes first (make_data_structures.cpp:9-33) — built on GPU
  * `device` by prefix doubling (one radix sort per round; 28 bytes of HBM per symbol: a 3.3e9-symbol whole-genome
  * PRG takes 92 GB, one B200). sa_out: n_symbols + 1 entries (the sentinel suffix first), 32-bit text positions;

@@ -64,6 +64,12 @@ def emu_lib():
         lib = C.CDLL(p)
         lib.emu_new.restype = C.c_void_p
         lib.emu_new.argtypes = [u32p, C.c_uint64, C.c_uint32]
+        lib.emu_new_from.restype = C.c_void_p
+        lib.emu_new_from.argtypes = [u32p, C.c_uint64, C.c_uint32, C.c_char_p]
+        lib.emu_kmer_index_dump.argtypes = [C.c_void_p, C.c_char_p]
+        lib.emu_write_int_vector.argtypes = [C.c_char_p, u64p, C.c_uint64, C.c_uint32, C.c_int]
+        lib.emu_read_int_vector.argtypes = [C.c_char_p, C.c_uint32, u64p, C.c_uint64, C.POINTER(C.c_uint32)]
+        lib.emu_read_int_vector.restype = C.c_int64
         lib.emu_free.argtypes = [C.c_void_p]
         lib.emu_last_error.restype = C.c_char_p
         lib.emu_sizes.argtypes = [C.c_void_p, u64p]
@@ -86,6 +92,8 @@ def emu_lib():
         lib.emu_index_check.argtypes = [C.c_void_p]
         lib.emu_index_digest.argtypes = [C.c_void_p]
         lib.emu_index_digest.restype = C.c_uint64
+        lib.emu_index_digest2.argtypes = [C.c_void_p, C.c_int]
+        lib.emu_index_digest2.restype = C.c_uint64
         lib.emu_path_counters.argtypes = [u64p, C.c_int]
         lib.emu_force_general.argtypes = [C.c_int]
         lib.emu_set_gtab_cap.argtypes = [C.c_void_p, C.c_uint32]
@@ -185,10 +193,11 @@ class Oracle:
 
 
 class Emu:
-    def __init__(self, prg, k):
+    def __init__(self, prg, k, kmer_index_dir=None):
         self.lib = emu_lib()
         prg = np.ascontiguousarray(prg, dtype=np.uint32)
-        self.h = self.lib.emu_new(_ptr(prg, C.c_uint32), prg.size, k)
+        self.h = self.lib.emu_new_from(_ptr(prg, C.c_uint32), prg.size, k,
+                                       os.fsencode(kmer_index_dir) if kmer_index_dir else None)
         if not self.h:
             raise RuntimeError(self.lib.emu_last_error().decode())
         s = np.zeros(6, dtype=np.uint64)
@@ -225,9 +234,15 @@ class Emu:
         self.lib.emu_path_counters(_ptr(c, C.c_uint64), int(reset))
         return {k: int(v) for k, v in zip(self.ROUTES, c) if k != "-"}
 
-    def index_digest(self):
-        """FNV-1a over every array of the flat index."""
-        return int(self.lib.emu_index_digest(self.h))
+    def kmer_index_dump(self, gram_dir):
+        """kmers / kmers_stats / sa_intervals / paths in the reference's sdsl format (dump.cpp:27-141)."""
+        if self.lib.emu_kmer_index_dump(self.h, os.fsencode(gram_dir)) != 0:
+            raise RuntimeError(self.lib.emu_last_error().decode())
+
+    def index_digest(self, layout_free=False):
+        """FNV-1a over every array of the flat index (layout_free: k-mer states with their path words inline, so the
+        order of the paths in the pool does not matter)."""
+        return int(self.lib.emu_index_digest2(self.h, 1 if layout_free else 0))
 
     def index_check(self):
         if self.lib.emu_index_check(self.h) != 0:

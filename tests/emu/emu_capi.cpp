@@ -91,10 +91,13 @@ static int g_force_general = 0;
 extern "C" {
 const char* emu_last_error() { return g_err.c_str(); }
 
-void* emu_new(const uint32_t* prg, uint64_t n, uint32_t k) {
+void* emu_new_from(const uint32_t* prg, uint64_t n, uint32_t k, const char* kmer_index_dir);
+void* emu_new(const uint32_t* prg, uint64_t n, uint32_t k) { return emu_new_from(prg, n, k, nullptr); }
+// kmer_index_dir != NULL: the k-mer index comes from the sdsl files of that gram_dir (kmer_index::load)
+void* emu_new_from(const uint32_t* prg, uint64_t n, uint32_t k, const char* kmer_index_dir) {
   try {
     auto* e = new Emu();
-    build_host_index(prg, n, k, e->h);
+    build_host_index(prg, n, k, e->h, nullptr, nullptr, kmer_index_dir);
     uint64_t na = e->h.allele_off.back();
     e->counters.assign(2 * na + e->h.n_per_base + 1, 0);
     uint32_t cap = 1024;
@@ -110,6 +113,35 @@ void* emu_new(const uint32_t* prg, uint64_t n, uint32_t k) {
   }
 }
 void emu_free(void* e) { delete (Emu*)e; }
+int emu_kmer_index_dump(void* ev, const char* dir) {
+  try {
+    kmer_index_dump(((Emu*)ev)->h, dir);
+    return 0;
+  } catch (const std::exception& ex) {
+    g_err = ex.what();
+    return -1;
+  }
+}
+// sdsl::int_vector serialisation as restated in index_build.cpp (width 0 on read = run-time width from the file)
+int emu_write_int_vector(const char* path, const uint64_t* values, uint64_t n, uint32_t width, int fixed_width) {
+  try {
+    write_int_vector(path, std::vector<uint64_t>(values, values + n), width, fixed_width != 0);
+    return 0;
+  } catch (const std::exception& ex) {
+    g_err = ex.what();
+    return -1;
+  }
+}
+int64_t emu_read_int_vector(const char* path, uint32_t fixed_width, uint64_t* out, uint64_t cap, uint32_t* width) {
+  try {
+    std::vector<uint64_t> v = read_int_vector(path, fixed_width, width);
+    for (uint64_t i = 0; i < v.size() && i < cap; ++i) out[i] = v[i];
+    return (int64_t)v.size();
+  } catch (const std::exception& ex) {
+    g_err = ex.what();
+    return -1;
+  }
+}
 // test hook: shrink the multi-allele group table (power of two) so that its growth path runs
 void emu_set_gtab_cap(void* ev, uint32_t cap) {
   auto* e = (Emu*)ev;
@@ -364,7 +396,11 @@ void emu_path_counters(uint64_t* out32, int reset) {
 // checked directly on the host copy. Returns 0, or -1 with the first violation in emu_last_error().
 // FNV-1a over every array of the flat index: two builds of one PRG must give the same value whatever the thread
 // count, the suffix-array builder or the build order inside the parallel passes
-uint64_t emu_index_digest(void* ev) {
+// layout_free != 0: the k-mer states are mixed in as (lo, hi, counts, path words) instead of (lo, hi, path_off, counts) +
+// the path pool, so that two indexes that differ only in where the paths sit in the pool give the same value
+uint64_t emu_index_digest2(void* ev, int layout_free);
+uint64_t emu_index_digest(void* ev) { return emu_index_digest2(ev, 0); }
+uint64_t emu_index_digest2(void* ev, int layout_free) {
   const HostIndex& h = ((Emu*)ev)->h;
   uint64_t d = 1469598103934665603ull;
   auto mix = [&](const void* p, size_t bytes) {
@@ -376,7 +412,18 @@ uint64_t emu_index_digest(void* ev) {
   MIX(h.prg); MIX(h.sa); MIX(h.isa); MIX(h.rank_blk); MIX(h.super_cnt); MIX(h.mrank_blk); MIX(h.marker_hit);
   MIX(h.tmarker_hit); MIX(h.text_grp); MIX(h.text_super); MIX(h.pos2node); MIX(h.nodes); MIX(h.edges);
   MIX(h.site_sa); MIX(h.allele_iv); MIX(h.entry_next); MIX(h.site_snp); MIX(h.allele_off); MIX(h.n_alleles);
-  MIX(h.kmer_bits); MIX(h.kmer_off); MIX(h.kmer_states); MIX(h.kmer_paths); MIX(h.seed_off); MIX(h.seed_ent);
+  MIX(h.kmer_bits); MIX(h.kmer_off); MIX(h.seed_off); MIX(h.seed_ent);
+  if (!layout_free) {
+    MIX(h.kmer_states); MIX(h.kmer_paths);
+  } else {
+    const uint64_t n_states = h.kmer_off.empty() ? 0 : h.kmer_off.back();
+    for (uint64_t j = 0; j < n_states; ++j) {
+      const KmerState& ks = h.kmer_states[j];
+      const uint32_t head[3] = {ks.lo, ks.hi, ks.counts};
+      mix(head, sizeof(head));
+      mix(h.kmer_paths.data() + ks.path_off, 4 * (size_t)(2 * (ks.counts & 0xFFFFu) + (ks.counts >> 16)));
+    }
+  }
   MIX(h.seed_state); MIX(h.site_rec); MIX(h.apos);
 #undef MIX
   mix(h.c_base, sizeof(h.c_base));

@@ -52,6 +52,19 @@ def test_gram_genotype_missing_arguments_exits_nonzero(built_lib):
     assert out.returncode == 1
 
 
+def test_gram_build_arguments_and_no_cpu_fallback(built_lib, tmp_path):
+    out = subprocess.run([GRAM, "build"], capture_output=True, text=True)
+    assert out.returncode == 1 and "--kmer_size" in out.stdout
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    np.asarray([1, 2, 5, 3, 6, 4, 6, 1, 2, 3, 4, 1], dtype="<u4").tofile(tmp_path / "prg")
+    out = subprocess.run([GRAM, "build", "--gram_dir", str(tmp_path), "--kmer_size", "3", "--max_threads", "2"],
+                         capture_output=True, text=True)
+    assert out.returncode != 0 and "no CUDA device" in (out.stdout + out.stderr)
+    assert not (tmp_path / "kmers").exists()
+
+
 @pytest.mark.gpu
 def test_integration_fixtures_through_cli(built_lib, tmp_path):
     fx = json.load(open(os.path.join(ROOT, "tests", "golden", "it_fixtures.json")))
