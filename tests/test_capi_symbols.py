@@ -72,3 +72,16 @@ def test_host_packers(built_lib):
         assert l2[r] == len(reads[r])
         for j in range(len(reads[r])):
             assert (int(p2[w2[r] + j // 16]) >> (2 * (j % 16))) & 3 == "ACGT".index(reads[r][j].upper())
+
+
+def test_plain_c_client_compiles_links_and_runs(built_lib, tmp_path):
+    """include/gq.h is a C header (C99, no C++), libgq.so links from C, host entry points work without a GPU."""
+    import subprocess
+    exe = str(tmp_path / "client")
+    lib_dir = os.path.dirname(built_lib)
+    cmd = ["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "c_client", "client.c"), "-o", exe, "-L", lib_dir, "-lgq", f"-Wl,-rpath,{lib_dir}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "c client ok" in r.stdout, (r.returncode, r.stdout, r.stderr)
