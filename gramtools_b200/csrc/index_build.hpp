@@ -65,8 +65,11 @@ using SaBuilder = std::vector<uint32_t> (*)(const std::vector<int32_t>& text, in
 void build_host_index(const uint32_t* prg, uint64_t n_symbols, uint32_t kmer_size, HostIndex& out,
                       SaBuilder sa_builder = nullptr, void* sa_ctx = nullptr, const char* kmer_index_dir = nullptr);
 
+// Seed-pass view (seed_off / seed_ent / seed_state) of a finished k-mer index (kmer_off / kmer_states / kmer_paths)
+void build_seed_view(HostIndex& ix);
+
 // The k-mer index as the reference's gram_dir files (dump.cpp:27-141 / load.cpp:11-173); sdsl::int_vector
-// serialisation restated in index_build.cpp (parity unpinned: no SDSL here).
+// serialisation restated in kmer_index_files.cpp (parity unpinned: no SDSL here).
 void kmer_index_dump(const HostIndex& ix, const std::string& dir);
 void kmer_index_load(HostIndex& ix, const std::string& dir);
 void write_int_vector(const std::string& path, const std::vector<uint64_t>& values, uint32_t width, bool fixed_width);
