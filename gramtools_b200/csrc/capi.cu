@@ -241,7 +241,9 @@ static void do_map(gq_index* ix, const HostBatch* hb = nullptr) {
   ix->st_count.reserve(2 * (size_t)n);
   ix->overflow_list.reserve(4 * (size_t)n + 16);  // a strand can be flagged by the text kernel and again by the general one
   ix->cov_overflow_list.reserve(2 * (size_t)n);
-  ix->mapped_list.reserve(2 * (size_t)n);
+  // one entry per mapped strand, plus a second one for a strand whose final state overflowed the pool in the text
+  // kernel (its slot stays in the list, the re-run appends it again)
+  ix->mapped_list.reserve(4 * (size_t)n + 16);
   if (ix->h.is_nested) {  // strands with several final states (coverage, later passes)
     ix->multi_list.reserve(2 * (size_t)n);
     ix->heavy_list.reserve(2 * (size_t)n);
