@@ -717,9 +717,14 @@ void build_kmers(HostIndex& ix) {
   }
   if (!err.empty()) throw std::runtime_error(err);
   lap("k-mer searches (DFS)");
-  // merge into CSR ordered by k-mer code
-  for (auto& o : outs)
-    for (size_t i = 0; i < o.codes.size(); ++i) ix.kmer_off[o.codes[i] + 1] += o.n_states[i];
+  // merge into CSR ordered by k-mer code: every k-mer belongs to exactly one task, so the tasks write disjoint
+  // ranges — counts, then (after the prefix sums) states and paths, in parallel over the tasks
+  const int n_outs = (int)outs.size();
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int t = 0; t < n_outs; ++t) {
+    const KmerOut& o = outs[t];
+    for (size_t i = 0; i < o.codes.size(); ++i) ix.kmer_off[o.codes[i] + 1] = o.n_states[i];
+  }
   uint64_t n_states_total = 0;
   for (uint64_t c = 0; c < nk; ++c) {
     if (ix.kmer_off[c + 1]) ix.kmer_bits[c >> 5] |= 1u << (c & 31);
@@ -728,23 +733,26 @@ void build_kmers(HostIndex& ix) {
   }
   if (n_states_total >= 0xFFFFFFFFull) throw std::runtime_error("k-mer index exceeds 2^32 states; use a larger kmer_size");
   ix.kmer_states.assign(ix.kmer_off[nk], KmerState{});
-  size_t total_paths = 0;
-  for (auto& o : outs) total_paths += o.paths.size();
+  std::vector<uint64_t> path_base(outs.size() + 1, 0);  // the path pool keeps the tasks' merge order
+  for (size_t t = 0; t < outs.size(); ++t) path_base[t + 1] = path_base[t] + outs[t].paths.size();
+  const uint64_t total_paths = path_base.back();
   if (total_paths >= 0xFFFFFFFFull) throw std::runtime_error("k-mer index paths exceed 2^32 words");
-  ix.kmer_paths.clear();
-  ix.kmer_paths.reserve(total_paths + 1);
-  for (auto& o : outs) {
-    uint32_t base = (uint32_t)ix.kmer_paths.size();
-    ix.kmer_paths.insert(ix.kmer_paths.end(), o.paths.begin(), o.paths.end());
+  ix.kmer_paths.assign(total_paths, 0);
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int t = 0; t < n_outs; ++t) {
+    KmerOut& o = outs[t];
+    const uint32_t base = (uint32_t)path_base[t];
+    std::copy(o.paths.begin(), o.paths.end(), ix.kmer_paths.begin() + base);
     size_t si = 0;
     for (size_t i = 0; i < o.codes.size(); ++i) {
-      uint32_t dst = ix.kmer_off[o.codes[i]];
+      const uint32_t dst = ix.kmer_off[o.codes[i]];
       for (uint32_t j = 0; j < o.n_states[i]; ++j, ++si) {
         KmerState ks = o.states[si];
         ks.path_off += base;
         ix.kmer_states[dst + j] = ks;
       }
     }
+    o = KmerOut{};  // free the task's buffers as soon as they are merged
   }
   if (ix.kmer_paths.empty()) ix.kmer_paths.push_back(0);
   if (ix.kmer_states.empty()) ix.kmer_states.push_back(KmerState{});
