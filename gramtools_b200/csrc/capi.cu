@@ -683,6 +683,43 @@ int gq_index_build_from_gram_dir(const uint32_t* prg, uint64_t n_symbols, uint32
   return index_build_impl(prg, n_symbols, kmer_size, device, gram_dir, out);
 }
 
+int gq_index_save(const gq_index* ix, const char* path) {
+  GQ_TRY
+  if (!ix || !path) throw std::runtime_error("null argument");
+  gq::host_index_save(ix->h, path);
+  GQ_CATCH
+}
+
+int gq_index_load(const char* path, int device, gq_index** out) {
+  gq_index* ix = nullptr;
+  GQ_TRY
+  if (!path || !out) throw std::runtime_error("null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    throw std::runtime_error("no CUDA device: libgq has no CPU fallback");
+  if (device < 0 || device >= ndev) throw std::runtime_error("invalid device ordinal");
+  ix = new gq_index();
+  ix->device = device;
+  gq::host_index_load(ix->h, path);
+  finish_handle(ix);
+  *out = ix;
+  }
+  catch (const std::exception& e) {
+    g_err = e.what();
+    if (ix) gq_index_destroy(ix);
+    return -1;
+  }
+  return 0;
+}
+
+int gq_index_prg(const gq_index* ix, uint32_t* prg_out, uint64_t* n_symbols) {
+  GQ_TRY
+  if (!ix || !n_symbols) throw std::runtime_error("null argument");
+  *n_symbols = ix->h.prg.size();
+  if (prg_out) std::copy(ix->h.prg.begin(), ix->h.prg.end(), prg_out);
+  GQ_CATCH
+}
+
 int gq_kmer_index_dump(const gq_index* ix, const char* gram_dir) {
   GQ_TRY
   if (!ix || !gram_dir) throw std::runtime_error("null argument");

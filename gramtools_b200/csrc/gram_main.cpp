@@ -15,8 +15,8 @@
 // reference (LevelGenotyper, genotype.cpp:68-118) is out of scope of this back-end.
 // gram_dir/prg is what is consumed: FM-index, masks and coverage graph are rebuilt from it (their SDSL / Boost
 // archives are third-party formats); the k-mer index is searched again or, with
-// --kmer_index_from_gram_dir, loaded from gram_dir's kmers / kmers_stats / sa_intervals / paths. `gram build` writes
-// those four files.
+// --kmer_index_from_gram_dir, loaded from gram_dir's kmers / kmers_stats / sa_intervals / paths; with --gq_index the
+// whole index comes from gram_dir/gq_index. `gram build` writes those files.
 #include <sys/stat.h>
 #include <zlib.h>
 
@@ -50,6 +50,7 @@ struct Params {
   uint32_t seed = 0;
   int devices = 1;  // --devices N (or GQ_DEVICES): GPUs of this node the reads are sharded over; 0 = all
   bool kmers_from_gram_dir = false;  // --kmer_index_from_gram_dir: load kmers / kmers_stats / sa_intervals / paths
+  bool use_gq_index = false;         // --gq_index: load gram_dir/gq_index (the whole index, written by `gram build`)
 };
 
 [[noreturn]] void usage_fail(const std::string& msg) {
@@ -57,7 +58,8 @@ struct Params {
   std::cout << "genotype options:\n  --gram_dir arg\n  --reads arg [arg…]\n  --sample_id arg\n"
                "  --ploidy arg {haploid, diploid}\n  --kmer_size arg\n  --genotype_dir arg\n"
                "  --max_threads arg (=1)\n  --seed arg\n  --devices arg (=1; B200 back-end: GPUs to shard the reads over, 0 = all)\n"
-               "  --kmer_index_from_gram_dir (B200 back-end: load the k-mer index files of gram_dir instead of rebuilding it)\n";
+               "  --kmer_index_from_gram_dir (B200 back-end: load the k-mer index files of gram_dir instead of rebuilding it)\n"
+               "  --gq_index (B200 back-end: load gram_dir/gq_index, the whole index as `gram build` wrote it)\n";
   std::exit(1);
 }
 
@@ -85,6 +87,7 @@ Params parse_genotype(int argc, const char* const* argv, int first) {
       p.has_seed = true;
     } else if (a == "--devices") p.devices = std::stoi(value("devices"));
     else if (a == "--kmer_index_from_gram_dir") p.kmers_from_gram_dir = true;
+    else if (a == "--gq_index") p.use_gq_index = true;
     else if (a == "--debug") p.debug = true;
     else usage_fail("unrecognised option '" + a + "'");
   }
@@ -279,9 +282,9 @@ struct PinnedBatch {
 
 // `gram build --gram_dir D --kmer_size K`: the k-mer index part of commands::build::run (build.cpp:8-71,
 // kmer_index::build + dump): reads D/prg (as written by the Python front-end / an earlier reference build), builds the
-// index on GPU 0 and leaves D/kmers, D/kmers_stats, D/sa_intervals, D/paths in the reference's sdsl format. The other
-// files of a reference gram_dir (fm_index, masks, cov_graph: SDSL / Boost archives) are not written — this back-end
-// rebuilds them from D/prg at `genotype` time. Options the reference's build takes and this one does not need
+// index on GPU 0 and leaves D/kmers, D/kmers_stats, D/sa_intervals, D/paths in the reference's sdsl format, plus
+// D/gq_index: the whole flat index in this back-end's own format (`gram genotype --gq_index` then rebuilds nothing).
+// The other files of a reference gram_dir (fm_index, masks, cov_graph: SDSL / Boost archives) are not written. Options the reference's build takes and this one does not need
 // (--ref, --prg, --max_threads, --all_kmers, ...) are accepted and ignored.
 int run_build(int argc, const char* const* argv, int first) {
   std::string gram_dir;
@@ -304,6 +307,7 @@ int run_build(int argc, const char* const* argv, int first) {
   gq_index* idx = nullptr;
   check(gq_index_build(prg.data(), prg.size(), kmer_size, 0, &idx));
   check(gq_kmer_index_dump(idx, gram_dir.c_str()));
+  check(gq_index_save(idx, join_path(gram_dir, "gq_index").c_str()));  // the whole index, for `gram genotype --gq_index`
   gq_layout lay;
   check(gq_index_describe(idx, &lay));
   std::cout << "Indexed kmers search states: " << lay.n_kmer_states << std::endl;
@@ -377,7 +381,21 @@ int main(int argc, const char* const* argv) {
   std::vector<gq_index*> handles(n_dev, nullptr);
   // host index built once ... (k-mer index searched, or — as kmer_index::load does, genotype.cpp:40 — taken from the
   // sdsl files `gram build` left in gram_dir)
-  if (p.kmers_from_gram_dir || std::getenv("GQ_KMER_INDEX_FROM_GRAM_DIR"))
+  if (p.use_gq_index) {
+    // nothing is rebuilt; the stored index must be the one of this gram_dir/prg and this kmer_size
+    check(gq_index_load(join_path(p.gram_dir, "gq_index").c_str(), 0, &handles[0]));
+    gq_layout l0;
+    check(gq_index_describe(handles[0], &l0));
+    uint64_t n_stored = 0;
+    check(gq_index_prg(handles[0], nullptr, &n_stored));
+    std::vector<uint32_t> stored(n_stored ? n_stored : 1);
+    check(gq_index_prg(handles[0], stored.data(), &n_stored));
+    stored.resize(n_stored);
+    if (l0.kmer_size != p.kmer_size || stored != prg) {
+      std::cout << "gram_dir/gq_index was built from another PRG or kmer_size: run `gram build` again" << std::endl;
+      return 1;
+    }
+  } else if (p.kmers_from_gram_dir || std::getenv("GQ_KMER_INDEX_FROM_GRAM_DIR"))
     check(gq_index_build_from_gram_dir(prg.data(), prg.size(), p.kmer_size, 0, p.gram_dir.c_str(), &handles[0]));
   else
     check(gq_index_build(prg.data(), prg.size(), p.kmer_size, 0, &handles[0]));

@@ -72,6 +72,10 @@ void build_seed_view(HostIndex& ix);
 // serialisation restated in kmer_index_files.cpp (parity unpinned: no SDSL here).
 void kmer_index_dump(const HostIndex& ix, const std::string& dir);
 void kmer_index_load(HostIndex& ix, const std::string& dir);
+// The whole flat index as one file of this back-end's own format (kmer_index_files.cpp): what `gram build` leaves in
+// gram_dir/gq_index so that `gram genotype` does not rebuild anything. Checksummed; load throws on any mismatch.
+void host_index_save(const HostIndex& ix, const std::string& path);
+void host_index_load(HostIndex& ix, const std::string& path);
 void write_int_vector(const std::string& path, const std::vector<uint64_t>& values, uint32_t width, bool fixed_width);
 std::vector<uint64_t> read_int_vector(const std::string& path, uint32_t fixed_width, uint32_t* width_out);
 

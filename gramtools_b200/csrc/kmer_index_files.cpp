@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -201,6 +202,127 @@ void kmer_index_load(HostIndex& ix, const std::string& dir) {
   }
   if (ix.kmer_paths.empty()) ix.kmer_paths.push_back(0);
   build_seed_view(ix);
+}
+
+// ---- the whole flat index as one file (this back-end's own format; `gram build` writes gram_dir/gq_index) ------------
+// [magic "GQINDEX1"][record sizes of the structs][scalars][every array: u64 count + raw little-endian elements]
+// [u64 word-wise checksum of everything before it]. Loading replaces the whole host build (suffix array, FM tables,
+// graph, k-mer searches, seed view); the arrays are then uploaded exactly as after a build.
+namespace {
+struct IoHash {
+  uint64_t h = 0x9E3779B97F4A7C15ull;
+  void mix(const void* p, size_t bytes) {
+    const uint8_t* b = (const uint8_t*)p;
+    size_t i = 0;
+    for (; i + 8 <= bytes; i += 8) {
+      uint64_t w;
+      std::memcpy(&w, b + i, 8);
+      h = (h ^ w) * 0xD6E8FEB86659FD93ull;
+      h ^= h >> 32;
+    }
+    for (; i < bytes; ++i) h = (h ^ b[i]) * 0x100000001B3ull;
+  }
+};
+struct Writer {
+  FILE* f;
+  IoHash hash;
+  bool ok = true;
+  void raw(const void* p, size_t bytes) {
+    if (bytes && fwrite(p, 1, bytes, f) != bytes) ok = false;
+    hash.mix(p, bytes);
+  }
+  template <class T>
+  void scalar(T& x) { raw(&x, sizeof(T)); }
+  template <class T>
+  void vec(std::vector<T>& v) {
+    uint64_t n = v.size();
+    raw(&n, 8);
+    raw(v.data(), n * sizeof(T));
+  }
+};
+struct Reader {
+  FILE* f;
+  IoHash hash;
+  uint64_t left;  // bytes of the file not yet consumed (bounds every count read from it)
+  void raw(void* p, size_t bytes) {
+    if (bytes > left || (bytes && fread(p, 1, bytes, f) != bytes)) throw std::runtime_error("gq_index file: truncated");
+    left -= bytes;
+    hash.mix(p, bytes);
+  }
+  template <class T>
+  void scalar(T& x) { raw(&x, sizeof(T)); }
+  template <class T>
+  void vec(std::vector<T>& v) {
+    uint64_t n = 0;
+    raw(&n, 8);
+    if (n > left / sizeof(T)) throw std::runtime_error("gq_index file: corrupt array length");
+    v.resize(n);
+    raw(v.data(), n * sizeof(T));
+  }
+};
+// every member of HostIndex, in one place for the writer and the reader
+template <class Io>
+void visit_index(HostIndex& h, Io& io) {
+  io.scalar(h.n); io.scalar(h.k); io.scalar(h.c_base); io.scalar(h.n_slots); io.scalar(h.n_sites);
+  uint32_t nested = h.is_nested ? 1u : 0u;
+  io.scalar(nested);
+  h.is_nested = nested != 0;
+  io.scalar(h.n_per_base);
+  io.vec(h.prg); io.vec(h.sa); io.vec(h.rank_blk); io.vec(h.super_cnt); io.vec(h.mrank_blk); io.vec(h.marker_hit);
+  io.vec(h.text_grp); io.vec(h.text_super); io.vec(h.tmarker_hit); io.vec(h.isa);
+  io.vec(h.site_sa); io.vec(h.allele_iv); io.vec(h.par); io.vec(h.tm_odd); io.vec(h.tm_even_off); io.vec(h.tm_even);
+  io.vec(h.entry_next); io.vec(h.site_snp); io.vec(h.site_start_pos); io.vec(h.n_alleles); io.vec(h.allele_off);
+  io.vec(h.pos2node); io.vec(h.nodes); io.vec(h.edges); io.vec(h.site_start_node); io.vec(h.site_rec); io.vec(h.apos);
+  io.vec(h.kmer_bits); io.vec(h.kmer_off); io.vec(h.kmer_paths); io.vec(h.kmer_states); io.vec(h.seed_off);
+  io.vec(h.seed_state); io.vec(h.seed_ent);
+}
+const char kIndexMagic[8] = {'G', 'Q', 'I', 'N', 'D', 'E', 'X', '1'};
+const uint32_t kRecordSizes[6] = {(uint32_t)sizeof(RankBlk), (uint32_t)sizeof(Node),     (uint32_t)sizeof(KmerState),
+                                  (uint32_t)sizeof(KmerSeed), (uint32_t)sizeof(TextGrp), 0x01020304u /* byte order */};
+}  // namespace
+
+void host_index_save(const HostIndex& ix, const std::string& path) {
+  FILE* f = fopen(path.c_str(), "wb");
+  if (!f) throw std::runtime_error("cannot write " + path);
+  Writer w{f};
+  w.raw(kIndexMagic, 8);
+  w.raw(kRecordSizes, sizeof(kRecordSizes));
+  visit_index(const_cast<HostIndex&>(ix), w);  // the writer only reads
+  const uint64_t sum = w.hash.h;
+  const bool ok = w.ok && fwrite(&sum, 8, 1, f) == 1;
+  if (fclose(f) != 0 || !ok) throw std::runtime_error("write error on " + path);
+}
+
+void host_index_load(HostIndex& ix, const std::string& path) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) throw std::runtime_error("cannot read " + path);
+  try {
+    fseek(f, 0, SEEK_END);
+    const long size = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    if (size < 8 + (long)sizeof(kRecordSizes) + 8) throw std::runtime_error("gq_index file: too short");
+    Reader r{f, IoHash{}, (uint64_t)size - 8};
+    char magic[8];
+    uint32_t sizes[6];
+    r.raw(magic, 8);
+    r.raw(sizes, sizeof(sizes));
+    if (std::memcmp(magic, kIndexMagic, 8) != 0) throw std::runtime_error("gq_index file: not a gq index (or another version)");
+    if (std::memcmp(sizes, kRecordSizes, sizeof(sizes)) != 0) throw std::runtime_error("gq_index file: written with another record layout");
+    ix = HostIndex{};
+    visit_index(ix, r);
+    if (r.left != 0) throw std::runtime_error("gq_index file: trailing bytes");
+    uint64_t sum = 0;
+    if (fread(&sum, 8, 1, f) != 1 || sum != r.hash.h) throw std::runtime_error("gq_index file: checksum mismatch");
+    // the cheap consistency checks a corrupted-but-checksummed file could not fail, a foreign one could
+    const uint64_t nk = 1ull << (2 * ix.k);
+    if (ix.k < 1 || ix.k > 14 || ix.sa.size() != ix.n || ix.isa.size() != ix.n || ix.prg.size() + 1 != ix.n ||
+        ix.kmer_off.size() != nk + 1 || ix.allele_off.size() != (size_t)ix.n_slots + 1)
+      throw std::runtime_error("gq_index file: inconsistent sizes");
+  } catch (...) {
+    fclose(f);
+    throw;
+  }
+  fclose(f);
 }
 
 }  // namespace gq

@@ -41,6 +41,9 @@ def load_library():
         "gq_index_destroy": [vp],
         "gq_suffix_array": [u32p, C.c_uint64, C.c_int, u32p, C.POINTER(C.c_int)],
         "gq_kmer_index_dump": [vp, C.c_char_p],
+        "gq_index_save": [vp, C.c_char_p],
+        "gq_index_load": [C.c_char_p, C.c_int, C.POINTER(vp)],
+        "gq_index_prg": [vp, u32p, u64p],
         "gq_index_build_from_gram_dir": [u32p, C.c_uint64, C.c_uint32, C.c_int, C.c_char_p, C.POINTER(vp)],
         "gq_index_describe": [vp, C.POINTER(GqLayout)],
         "gq_index_allele_offsets": [vp, u64p],
@@ -190,12 +193,15 @@ def pack_ascii(text, offsets, n_threads=None):
 class QuasimapIndex:
     """One PRG index resident on one GPU + its coverage accumulators."""
 
-    def __init__(self, prg, kmer_size, device=0, _clone_of=None, kmer_index_dir=None):
-        """kmer_index_dir: take the k-mer index from the sdsl files of that gram_dir (gq_index_build_from_gram_dir)."""
+    def __init__(self, prg, kmer_size, device=0, _clone_of=None, kmer_index_dir=None, index_file=None):
+        """kmer_index_dir: take the k-mer index from the sdsl files of that gram_dir (gq_index_build_from_gram_dir);
+        index_file: load a whole index written by save() (gq_index_load; prg / kmer_size are ignored)."""
         self._lib = load_library()
         h = C.c_void_p()
         self._h = None
-        if _clone_of is not None:
+        if index_file is not None:
+            self._check(self._lib.gq_index_load(os.fsencode(index_file), int(device), C.byref(h)))
+        elif _clone_of is not None:
             self._check(self._lib.gq_index_clone(_clone_of._h, int(device), C.byref(h)))
         elif kmer_index_dir is not None:
             prg = np.ascontiguousarray(prg, dtype=np.uint32)
@@ -214,6 +220,17 @@ class QuasimapIndex:
     def _check(self, rc):
         if rc != 0:
             raise GqError(self._lib.gq_last_error().decode())
+
+    def save(self, path):
+        """gq_index_save: the whole flat index as one checksummed file."""
+        self._check(self._lib.gq_index_save(self._h, os.fsencode(path)))
+
+    def prg(self):
+        n = C.c_uint64()
+        self._check(self._lib.gq_index_prg(self._h, None, C.byref(n)))
+        out = np.zeros(max(n.value, 1), dtype=np.uint32)
+        self._check(self._lib.gq_index_prg(self._h, _ptr(out, C.c_uint32), C.byref(n)))
+        return out[:n.value]
 
     def kmer_index_dump(self, gram_dir):
         """Write kmers / kmers_stats / sa_intervals / paths (the reference's gram_dir files of the k-mer index)."""

@@ -52,6 +52,14 @@ int gq_index_destroy(gq_index* idx);
 int gq_kmer_index_dump(const gq_index* idx, const char* gram_dir);
 int gq_index_build_from_gram_dir(const uint32_t* prg, uint64_t n_symbols, uint32_t kmer_size, int device,
                                  const char* gram_dir, gq_index** out);
+/* The whole index as one file of this back-end's own format (checksummed): gq_index_save after a build (`gram build`
+ * writes gram_dir/gq_index), gq_index_load instead of gq_index_build — nothing is rebuilt, the arrays are uploaded as
+ * they were. A file that is truncated, corrupted, of another version or record layout is refused. gq_index_prg
+ * returns the PRG the index was built from (prg_out may be NULL to ask for the length): callers compare it with the
+ * gram_dir/prg at hand before trusting a stored index. */
+int gq_index_save(const gq_index* idx, const char* path);
+int gq_index_load(const char* path, int device, gq_index** out);
+int gq_index_prg(const gq_index* idx, uint32_t* prg_out, uint64_t* n_symbols);
 /* The suffix array alone — what sdsl::construct computes first (make_data_structures.cpp:9-33) — built on GPU
  * `device` by prefix doubling (one radix sort per round; 28 bytes of HBM per symbol: a 3.3e9-symbol whole-genome
  * PRG takes 92 GB, one B200). sa_out: n_symbols + 1 entries (the sentinel suffix first), 32-bit text positions;

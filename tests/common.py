@@ -67,6 +67,9 @@ def emu_lib():
         lib.emu_new_from.restype = C.c_void_p
         lib.emu_new_from.argtypes = [u32p, C.c_uint64, C.c_uint32, C.c_char_p]
         lib.emu_kmer_index_dump.argtypes = [C.c_void_p, C.c_char_p]
+        lib.emu_index_save.argtypes = [C.c_void_p, C.c_char_p]
+        lib.emu_load.restype = C.c_void_p
+        lib.emu_load.argtypes = [C.c_char_p]
         lib.emu_write_int_vector.argtypes = [C.c_char_p, u64p, C.c_uint64, C.c_uint32, C.c_int]
         lib.emu_read_int_vector.argtypes = [C.c_char_p, C.c_uint32, u64p, C.c_uint64, C.POINTER(C.c_uint32)]
         lib.emu_read_int_vector.restype = C.c_int64
@@ -193,11 +196,14 @@ class Oracle:
 
 
 class Emu:
-    def __init__(self, prg, k, kmer_index_dir=None):
+    def __init__(self, prg, k, kmer_index_dir=None, index_file=None):
         self.lib = emu_lib()
-        prg = np.ascontiguousarray(prg, dtype=np.uint32)
-        self.h = self.lib.emu_new_from(_ptr(prg, C.c_uint32), prg.size, k,
-                                       os.fsencode(kmer_index_dir) if kmer_index_dir else None)
+        if index_file is not None:  # a whole index written by index_save()
+            self.h = self.lib.emu_load(os.fsencode(index_file))
+        else:
+            prg = np.ascontiguousarray(prg, dtype=np.uint32)
+            self.h = self.lib.emu_new_from(_ptr(prg, C.c_uint32), prg.size, k,
+                                           os.fsencode(kmer_index_dir) if kmer_index_dir else None)
         if not self.h:
             raise RuntimeError(self.lib.emu_last_error().decode())
         s = np.zeros(6, dtype=np.uint64)
@@ -233,6 +239,11 @@ class Emu:
         c = np.zeros(32, dtype=np.uint64)
         self.lib.emu_path_counters(_ptr(c, C.c_uint64), int(reset))
         return {k: int(v) for k, v in zip(self.ROUTES, c) if k != "-"}
+
+    def index_save(self, path):
+        """The whole flat index as one checksummed file (host_index_save)."""
+        if self.lib.emu_index_save(self.h, os.fsencode(path)) != 0:
+            raise RuntimeError(self.lib.emu_last_error().decode())
 
     def kmer_index_dump(self, gram_dir):
         """kmers / kmers_stats / sa_intervals / paths in the reference's sdsl format (dump.cpp:27-141)."""

@@ -91,6 +91,8 @@ static int g_force_general = 0;
 extern "C" {
 const char* emu_last_error() { return g_err.c_str(); }
 
+struct Emu;
+void* emu_finish(Emu* e);
 void* emu_new_from(const uint32_t* prg, uint64_t n, uint32_t k, const char* kmer_index_dir);
 void* emu_new(const uint32_t* prg, uint64_t n, uint32_t k) { return emu_new_from(prg, n, k, nullptr); }
 // kmer_index_dir != NULL: the k-mer index comes from the sdsl files of that gram_dir (kmer_index::load)
@@ -98,21 +100,44 @@ void* emu_new_from(const uint32_t* prg, uint64_t n, uint32_t k, const char* kmer
   try {
     auto* e = new Emu();
     build_host_index(prg, n, k, e->h, nullptr, nullptr, kmer_index_dir);
-    uint64_t na = e->h.allele_off.back();
-    e->counters.assign(2 * na + e->h.n_per_base + 1, 0);
-    uint32_t cap = 1024;
-    while (cap < 4 * na) cap <<= 1;
-    e->gtab.assign(cap, 0);
-    e->gcount.assign(cap, 0);
-    e->gpool.assign((size_t)cap * 4, 0);
-    e->gsmall.assign(4, 0);
-    return e;
+    return emu_finish(e);
   } catch (const std::exception& ex) {
     g_err = ex.what();
     return nullptr;
   }
 }
+// coverage accumulators of a freshly built / loaded index
+void* emu_finish(Emu* e) {
+  uint64_t na = e->h.allele_off.back();
+  e->counters.assign(2 * na + e->h.n_per_base + 1, 0);
+  uint32_t cap = 1024;
+  while (cap < 4 * na) cap <<= 1;
+  e->gtab.assign(cap, 0);
+  e->gcount.assign(cap, 0);
+  e->gpool.assign((size_t)cap * 4, 0);
+  e->gsmall.assign(4, 0);
+  return e;
+}
 void emu_free(void* e) { delete (Emu*)e; }
+int emu_index_save(void* ev, const char* path) {
+  try {
+    host_index_save(((Emu*)ev)->h, path);
+    return 0;
+  } catch (const std::exception& ex) {
+    g_err = ex.what();
+    return -1;
+  }
+}
+void* emu_load(const char* path) {
+  try {
+    auto* e = new Emu();
+    host_index_load(e->h, path);
+    return emu_finish(e);
+  } catch (const std::exception& ex) {
+    g_err = ex.what();
+    return nullptr;
+  }
+}
 int emu_kmer_index_dump(void* ev, const char* dir) {
   try {
     kmer_index_dump(((Emu*)ev)->h, dir);

@@ -61,7 +61,8 @@ def test_gram_build_then_genotype_from_its_kmer_index(built_lib, tmp_path):
             s0 = int(rng.integers(0, hap.size - 60))
             f.write(f"@r{i}\n" + "".join("?ACGT"[x] for x in hap[s0:s0 + 60]) + "\n+\n" + "I" * 60 + "\n")
     dumps = []
-    for extra in ([], ["--kmer_index_from_gram_dir"]):
+    assert (gram_dir / "gq_index").stat().st_size > 1000
+    for extra in ([], ["--kmer_index_from_gram_dir"], ["--gq_index"]):
         geno = tmp_path / ("geno" + str(len(extra)))
         out = subprocess.run([GRAM, "genotype", "--gram_dir", str(gram_dir), "--reads", str(fq), "--sample_id", "s",
                               "--ploidy", "haploid", "--kmer_size", "5", "--genotype_dir", str(geno), "--seed", "42"] + extra,
@@ -69,4 +70,29 @@ def test_gram_build_then_genotype_from_its_kmer_index(built_lib, tmp_path):
         assert out.returncode == 0, out.stdout + out.stderr
         dumps.append([open(geno / "coverage" / n).read() for n in
                       ("allele_sum_coverage", "allele_base_coverage.json", "grouped_allele_counts_coverage.json")])
-    assert dumps[0] == dumps[1]
+    assert dumps[0] == dumps[1] == dumps[2]
+    # a stored index of another kmer_size is refused
+    out = subprocess.run([GRAM, "genotype", "--gram_dir", str(gram_dir), "--reads", str(fq), "--sample_id", "s", "--ploidy",
+                          "haploid", "--kmer_size", "6", "--genotype_dir", str(tmp_path / "g6"), "--gq_index"],
+                         capture_output=True, text=True)
+    assert out.returncode != 0 and "gram build" in out.stdout
+
+
+@pytest.mark.gpu
+def test_whole_index_file_round_trip_gpu(built_lib, tmp_path):
+    """gq_index_save -> gq_index_load: the loaded index maps like the oracle and knows its PRG."""
+    prg, k = synth.make_nested_prg(4, 300, 12), 4
+    built = QuasimapIndex(prg, k, device=0)
+    path = str(tmp_path / "gq_index")
+    built.save(path)
+    loaded = QuasimapIndex(None, 0, device=0, index_file=path)
+    assert np.array_equal(loaded.prg(), np.asarray(prg, dtype=np.uint32))
+    assert loaded.layout.kmer_size == k and loaded.layout.n_kmer_states == built.layout.n_kmer_states
+    bases, offs = _reads_for(prg, 300, 40, 8)
+    seeds = master_seeds(42, offs.size - 1)
+    loaded.map_batch(bases, offs, seeds)
+    o = Oracle(prg, k)
+    o.map(bases, offs, seeds)
+    assert_parity(gpu_result(loaded), o.result(), "index loaded from a gq_index file")
+    built.close()
+    loaded.close()

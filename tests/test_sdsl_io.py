@@ -129,3 +129,33 @@ def test_malformed_files_rejected(tmp_path):
         Emu(prg, k + 1, kmer_index_dir=str(tmp_path))  # files of another kmer_size
     with pytest.raises(RuntimeError):
         Emu(prg, k, kmer_index_dir=str(tmp_path / "missing"))
+
+
+def test_whole_index_file_round_trip(tmp_path):
+    """gq_index (this back-end's own format: every array of the flat index + a checksum): save -> load gives the same
+    bytes in memory (full digest), maps like the oracle, and damaged files are refused."""
+    prg, k = synth.make_nested_prg(6, 350, 4), 5
+    e = Emu(prg, k)
+    path = str(tmp_path / "gq_index")
+    e.index_save(path)
+    e2 = Emu(None, 0, index_file=path)
+    assert e2.index_digest() == e.index_digest()
+    assert (e2.n_sites, e2.n_alleles, e2.n_per_base, e2.sa_size, e2.n_kmer_states) == \
+           (e.n_sites, e.n_alleles, e.n_per_base, e.sa_size, e.n_kmer_states)
+    rng = np.random.default_rng(5)
+    haps = [synth.random_haplotype(prg, rng) for _ in range(3)]
+    bases, offs = synth.sample_reads(haps, 200, 50, 6)
+    seeds = master_seeds(7, offs.size - 1)
+    o = Oracle(prg, k)
+    o.map(bases, offs, seeds)
+    e2.map(bases, offs, seeds)
+    assert_parity(e2.result(), o.result(), "index loaded from a gq_index file")
+    raw = open(path, "rb").read()
+    for name, data in (("truncated", raw[:len(raw) // 2]), ("flipped", raw[:1000] + bytes([raw[1000] ^ 1]) + raw[1001:]),
+                       ("magic", b"NOTANIDX" + raw[8:]), ("trailing", raw + b"\0" * 8), ("empty", b"")):
+        bad = str(tmp_path / name)
+        open(bad, "wb").write(data)
+        with pytest.raises(RuntimeError):
+            Emu(None, 0, index_file=bad)
+    with pytest.raises(RuntimeError):
+        Emu(None, 0, index_file=str(tmp_path / "missing"))
