@@ -39,6 +39,7 @@
 #include <vector>
 
 #include "../../include/gq.h"
+#include "read_file.hpp"
 
 namespace {
 
@@ -120,67 +121,15 @@ std::vector<uint32_t> read_prg(const std::string& path) {
   return prg;
 }
 
-// Minimal sequence reader with the behaviour of SeqRead / seq_file.h that matters here
-// (include/sequence_read/seqread.hpp:94-180, seq_file.h:247-335): format sniffed from the first byte
-// ('@' FASTQ, '>' FASTA, else one read per line), multi-line records joined, gz transparently
-// inflated, a malformed record ends the file.
-class ReadFile {
- public:
-  explicit ReadFile(const std::string& path) {
-    gz_ = gzopen(path.c_str(), "rb");
-    if (!gz_) {
-      std::cout << "Cannot open reads file " << path << std::endl;
-      std::exit(1);
-    }
-    gzbuffer(gz_, 1 << 20);
-    have_line_ = next_line(line_);
-    if (have_line_) fmt_ = line_.empty() ? 'p' : (line_[0] == '@' ? 'q' : (line_[0] == '>' ? 'a' : 'p'));
+// sequence reader (read_file.hpp): SeqRead / seq_file.h behaviour, lines as views into one inflate buffer
+std::unique_ptr<gq::ReadFile> open_reads(const std::string& path) {
+  try {
+    return std::make_unique<gq::ReadFile>(path);
+  } catch (const std::exception& e) {
+    std::cout << e.what() << std::endl;
+    std::exit(1);
   }
-  ~ReadFile() {
-    if (gz_) gzclose(gz_);
-  }
-  bool next(std::string& seq, std::string& qual) {
-    seq.clear();
-    qual.clear();
-    if (!have_line_) return false;
-    if (fmt_ == 'p') {
-      seq = line_;
-      have_line_ = next_line(line_);
-      return true;
-    }
-    if (fmt_ == 'a') {
-      if (line_.empty() || line_[0] != '>') return false;
-      while ((have_line_ = next_line(line_)) && (line_.empty() || line_[0] != '>')) seq += line_;
-      return true;
-    }
-    if (line_.empty() || line_[0] != '@') return false;
-    while ((have_line_ = next_line(line_)) && (line_.empty() || line_[0] != '+')) seq += line_;
-    if (!have_line_) return false;  // no '+' line: malformed
-    while (qual.size() < seq.size() && (have_line_ = next_line(line_))) qual += line_;
-    if (qual.size() != seq.size()) return false;
-    have_line_ = next_line(line_);
-    return true;
-  }
-
- private:
-  bool next_line(std::string& out) {
-    out.clear();
-    char buf[1 << 16];
-    while (gzgets(gz_, buf, sizeof buf)) {
-      size_t n = std::strlen(buf);
-      bool eol = n && buf[n - 1] == '\n';
-      if (eol) --n;
-      if (n && buf[n - 1] == '\r') --n;
-      out.append(buf, n);
-      if (eol) return true;
-    }
-    return !out.empty();
-  }
-  gzFile gz_ = nullptr;
-  std::string line_;
-  bool have_line_ = false;
-  char fmt_ = 'p';
-};
+}
 
 inline uint8_t encode_base(char c) {  // encode_char, utils.cpp:13-47
   switch (c) {
@@ -356,9 +305,9 @@ int main(int argc, const char* const* argv) {
   uint64_t max_read_length = 0, num_bases = 0, no_qual_reads = 0, informative = 0;
   double running_qual = 0;
   {
-    ReadFile rf(p.reads[0]);
+    auto rf = open_reads(p.reads[0]);
     std::string seq, qual;
-    while (informative < 10000 && rf.next(seq, qual)) {
+    while (informative < 10000 && rf->next(seq, qual)) {
       if (seq.size() > max_read_length) max_read_length = seq.size();
       if (qual.empty()) {
         ++no_qual_reads;
@@ -439,18 +388,18 @@ int main(int argc, const char* const* argv) {
     std::mt19937 master;
     master.seed(master_seed);
     for (const auto& path : p.reads) {
-      ReadFile rf(path);
+      auto rf = open_reads(path);
       auto cur = std::make_unique<Batch>();
-      std::string seq, qual;
+      size_t seq_len = 0;
       uint64_t in_ref_batch = 0;
-      while (rf.next(seq, qual)) {
+      // the record's sequence goes straight from the inflate buffer into the batch text (qualities are only counted)
+      while (rf->next_seq(cur->text, seq_len)) {
         // read j of a 5000-read buffer gets the j-th of the 5000 draws made for that buffer
         // (quasimap.cpp:132-139): unused draws of the last, partly filled buffer are discarded
         if (in_ref_batch == kRefBatch) in_ref_batch = 0;
         cur->seeds.push_back((uint32_t)master());
         ++in_ref_batch;
-        cur->text += seq;  // non-ACGT characters empty the read in the packer (utils.cpp:72-92)
-        cur->offs.push_back(cur->text.size());
+        cur->offs.push_back(cur->text.size());  // non-ACGT characters empty the read in the packer (utils.cpp:72-92)
         if (cur->seeds.size() == kGpuBatch) {
           queue.push(std::move(cur));
           cur = std::make_unique<Batch>();

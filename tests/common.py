@@ -68,6 +68,7 @@ def emu_lib():
         lib.emu_new_from.argtypes = [u32p, C.c_uint64, C.c_uint32, C.c_char_p]
         lib.emu_kmer_index_dump.argtypes = [C.c_void_p, C.c_char_p]
         lib.emu_index_save.argtypes = [C.c_void_p, C.c_char_p]
+        lib.emu_read_file.argtypes = [C.c_char_p, C.c_int, C.c_uint64, u64p]
         lib.emu_load.restype = C.c_void_p
         lib.emu_load.argtypes = [C.c_char_p]
         lib.emu_write_int_vector.argtypes = [C.c_char_p, u64p, C.c_uint64, C.c_uint32, C.c_int]

@@ -18,6 +18,9 @@
 #include <set>
 #include <unordered_set>
 
+#include "../../gramtools_b200/csrc/read_file.hpp"
+#include "old_read_file.hpp"
+
 using namespace gq;
 namespace gq {
 unsigned long long gq_emu_counters[32];
@@ -119,6 +122,55 @@ void* emu_finish(Emu* e) {
   return e;
 }
 void emu_free(void* e) { delete (Emu*)e; }
+// Reader equivalence (tests/test_read_file.py). mode 0: the old line-by-line reader; 1: ReadFile::next; 2:
+// ReadFile::next_seq (sequence appended to one text, qualities only counted). out = {records, bases, digest of the
+// sequences (length-prefixed), digest of the qualities (modes 0 and 1)}; buffer_bytes = inflate buffer of the new reader
+// (tiny values force lines to straddle refills). Returns -1 when the file cannot be opened.
+int emu_read_file(const char* path, int mode, uint64_t buffer_bytes, uint64_t out[4]) {
+  auto fnv = [](uint64_t& d, const char* p, size_t n) {
+    d = (d ^ n) * 1099511628211ull;
+    for (size_t i = 0; i < n; ++i) d = (d ^ (uint8_t)p[i]) * 1099511628211ull;
+  };
+  out[0] = out[1] = 0;
+  out[2] = out[3] = 1469598103934665603ull;
+  try {
+    std::string seq, qual;
+    if (mode == 0) {
+      OldReadFile rf(path);
+      while (rf.next(seq, qual)) {
+        ++out[0];
+        out[1] += seq.size();
+        fnv(out[2], seq.data(), seq.size());
+        fnv(out[3], qual.data(), qual.size());
+      }
+    } else if (mode == 1) {
+      gq::ReadFile rf(path, buffer_bytes ? buffer_bytes : (size_t(4) << 20));
+      while (rf.next(seq, qual)) {
+        ++out[0];
+        out[1] += seq.size();
+        fnv(out[2], seq.data(), seq.size());
+        fnv(out[3], qual.data(), qual.size());
+      }
+    } else {
+      gq::ReadFile rf(path, buffer_bytes ? buffer_bytes : (size_t(4) << 20));
+      std::string text;
+      size_t len = 0, at = 0;
+      while (rf.next_seq(text, len)) {
+        ++out[0];
+        out[1] += len;
+        if (text.size() != at + len) return -2;
+        fnv(out[2], text.data() + at, len);
+        at += len;
+        if (text.size() > (1u << 20)) text.clear(), at = 0;
+      }
+      if (text.size() != at) return -3;  // a rejected record must leave nothing behind
+    }
+    return 0;
+  } catch (const std::exception& ex) {
+    g_err = ex.what();
+    return -1;
+  }
+}
 int emu_index_save(void* ev, const char* path) {
   try {
     host_index_save(((Emu*)ev)->h, path);
