@@ -62,8 +62,8 @@ def test_gram_build_then_genotype_from_its_kmer_index(built_lib, tmp_path):
             f.write(f"@r{i}\n" + "".join("?ACGT"[x] for x in hap[s0:s0 + 60]) + "\n+\n" + "I" * 60 + "\n")
     dumps = []
     assert (gram_dir / "gq_index").stat().st_size > 1000
-    for extra in ([], ["--kmer_index_from_gram_dir"], ["--gq_index"]):
-        geno = tmp_path / ("geno" + str(len(extra)))
+    for leg, extra in enumerate(([], ["--kmer_index_from_gram_dir"], ["--gq_index"])):
+        geno = tmp_path / f"geno{leg}"
         out = subprocess.run([GRAM, "genotype", "--gram_dir", str(gram_dir), "--reads", str(fq), "--sample_id", "s",
                               "--ploidy", "haploid", "--kmer_size", "5", "--genotype_dir", str(geno), "--seed", "42"] + extra,
                              capture_output=True, text=True)
