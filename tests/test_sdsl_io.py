@@ -159,3 +159,22 @@ def test_whole_index_file_round_trip(tmp_path):
             Emu(None, 0, index_file=bad)
     with pytest.raises(RuntimeError):
         Emu(None, 0, index_file=str(tmp_path / "missing"))
+
+
+def test_int_vector_random_round_trips(tmp_path):
+    """Every width 1..64, random lengths and values: the bytes are the big-integer packing (element i at bit i * width,
+    LSB first) and reading gives the values back."""
+    rng = np.random.default_rng(9)
+    for width in list(range(1, 65)):
+        n = int(rng.integers(0, 40))
+        vals = [int(rng.integers(0, 2 ** min(width, 63))) | ((int(rng.integers(0, 2)) << 63) if width == 64 else 0)
+                for _ in range(n)]
+        for fixed in (False, True):
+            p = str(tmp_path / f"w{width}{'f' if fixed else 'v'}")
+            _write(p, vals, width, fixed)
+            raw = open(p, "rb").read()
+            big = sum(v << (width * i) for i, v in enumerate(vals))
+            n_words = (n * width + 63) // 64
+            want = struct.pack("<Q", n * width) + (b"" if fixed else bytes([width])) + big.to_bytes(8 * n_words, "little")
+            assert raw == want, (width, fixed)
+            assert _read(p, width if fixed else 0) == (vals, width)
