@@ -64,8 +64,8 @@ int32_t compress_text(const uint32_t* prg, uint64_t n_symbols, std::vector<uint3
     // symbols are dense (bases and consecutive markers): a presence table instead of sorting a copy of the PRG
     std::vector<uint8_t> seen((size_t)maxs + 1, 0);
 #pragma omp parallel for schedule(static)
-    for (int64_t i = 0; i < n_i; ++i)
-      if (!seen[prg[i]]) seen[prg[i]] = 1;  // benign race: every writer stores 1
+    for (int64_t i = 0; i < n_i; ++i)  // relaxed atomic byte accesses: several threads may mark the same symbol
+      if (!__atomic_load_n(&seen[prg[i]], __ATOMIC_RELAXED)) __atomic_store_n(&seen[prg[i]], (uint8_t)1, __ATOMIC_RELAXED);
     for (uint64_t sym = 0; sym <= maxs; ++sym)
       if (seen[sym]) present.push_back((uint32_t)sym);
   } else {
