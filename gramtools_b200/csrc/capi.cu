@@ -954,6 +954,19 @@ int gq_packed_words(const uint64_t* off, uint64_t n_reads, uint64_t* n_words) {
 
 // read r starts at word (off[r] >> 4) + r: word-aligned, non-overlapping, computable per read without a prefix
 // sum (at most one word wasted per read) — the layout pack_kernel produces on the device
+// ASCII -> 2-bit code (A/a 0, C/c 1, G/g 2, T/t 3), 0x80 for every other character (encode_char, utils.cpp:13-47)
+struct AsciiLut {
+  uint8_t t[256];
+  AsciiLut() {
+    for (int i = 0; i < 256; ++i) t[i] = 0x80;
+    t['A'] = t['a'] = 0;
+    t['C'] = t['c'] = 1;
+    t['G'] = t['g'] = 2;
+    t['T'] = t['t'] = 3;
+  }
+};
+static const AsciiLut kAsciiLut;
+
 int gq_pack_reads(const uint8_t* bases, const uint64_t* off, uint64_t n_reads, uint32_t* packed, uint32_t* word_off,
                   uint32_t* len, int n_threads) {
   GQ_TRY
@@ -968,11 +981,17 @@ int gq_pack_reads(const uint8_t* bases, const uint64_t* off, uint64_t n_reads, u
     word_off[r] = w0;
     len[r] = L;
     const uint8_t* src = bases + b0;
-    for (uint32_t w = 0; w < (L + 15) / 16; ++w) {
-      const uint32_t cnt = std::min<uint32_t>(16, L - 16 * w);
+    const uint32_t full = L >> 4;
+    for (uint32_t w = 0; w < full; ++w) {  // whole words: 16 bases, unrolled
+      const uint8_t* s16 = src + 16 * w;
       uint32_t x = 0;
-      for (uint32_t j = 0; j < cnt; ++j) x |= ((uint32_t)(src[16 * w + j] - 1) & 3u) << (2 * j);
+      for (uint32_t j = 0; j < 16; ++j) x |= ((uint32_t)(s16[j] - 1) & 3u) << (2 * j);
       packed[w0 + w] = x;
+    }
+    if (L & 15u) {
+      uint32_t x = 0;
+      for (uint32_t j = 0; j < (L & 15u); ++j) x |= ((uint32_t)(src[16 * full + j] - 1) & 3u) << (2 * j);
+      packed[w0 + full] = x;
     }
   }
   if (word_off) word_off[n_reads] = (uint32_t)((n_reads ? (off[n_reads] >> 4) : 0) + n_reads);
@@ -980,7 +999,9 @@ int gq_pack_reads(const uint8_t* bases, const uint64_t* off, uint64_t n_reads, u
 }
 
 // the same from ASCII sequence text (FASTQ / FASTA sequence lines): upper or lower case ACGT; a read holding any
-// other character becomes EMPTY, as encode_dna_bases does (utils.cpp:13-47,72-92) — len 0, counted as skipped
+// other character becomes EMPTY, as encode_dna_bases does (utils.cpp:13-47,72-92) — len 0, counted as skipped.
+// One table look-up per character, 16 per packed word, validity OR-ed over the whole read (the ingestion pipeline of
+// `gram genotype` runs this on every read: 0.6 -> several M reads/s per thread against a compare chain per base).
 int gq_pack_ascii(const char* text, const uint64_t* off, uint64_t n_reads, uint32_t* packed, uint32_t* word_off,
                   uint32_t* len, int n_threads) {
   GQ_TRY
@@ -988,26 +1009,35 @@ int gq_pack_ascii(const char* text, const uint64_t* off, uint64_t n_reads, uint3
   if (n_reads && ((off[n_reads] >> 4) + n_reads + 1 >= (1ull << 32))) throw std::runtime_error("batch too large (packed words exceed 2^32)");
   const int nt = n_threads > 0 ? n_threads : 1;
   (void)nt;
+  const uint8_t* lut = kAsciiLut.t;
 #pragma omp parallel for schedule(static) num_threads(nt)
   for (int64_t r = 0; r < (int64_t)n_reads; ++r) {
     const uint64_t b0 = off[r];
     const uint32_t L = (uint32_t)(off[r + 1] - b0), w0 = (uint32_t)(b0 >> 4) + (uint32_t)r;
     word_off[r] = w0;
-    const char* src = text + b0;
-    bool ok = true;
-    for (uint32_t w = 0; w < (L + 15) / 16 && ok; ++w) {
-      const uint32_t cnt = std::min<uint32_t>(16, L - 16 * w);
+    const unsigned char* src = (const unsigned char*)text + b0;
+    const uint32_t full = L >> 4;
+    uint32_t bad = 0;
+    for (uint32_t w = 0; w < full; ++w) {
+      const unsigned char* s16 = src + 16 * w;
       uint32_t x = 0;
-      for (uint32_t j = 0; j < cnt; ++j) {
-        // A/a 0, C/c 1, G/g 2, T/t 3: bits 1-2 of the ASCII code give 0,1,3,2 for A,C,G,T
-        const unsigned char ch = (unsigned char)src[16 * w + j], up = ch & 0xDFu;
-        const uint32_t code = up == 'A' ? 0u : up == 'C' ? 1u : up == 'G' ? 2u : up == 'T' ? 3u : 4u;
-        ok &= code < 4u;
-        x |= (code & 3u) << (2 * j);
+      for (uint32_t j = 0; j < 16; ++j) {
+        const uint32_t c = lut[s16[j]];
+        bad |= c;
+        x |= (c & 3u) << (2 * j);
       }
       packed[w0 + w] = x;
     }
-    len[r] = ok ? L : 0u;
+    if (L & 15u) {
+      uint32_t x = 0;
+      for (uint32_t j = 0; j < (L & 15u); ++j) {
+        const uint32_t c = lut[src[16 * full + j]];
+        bad |= c;
+        x |= (c & 3u) << (2 * j);
+      }
+      packed[w0 + full] = x;
+    }
+    len[r] = (bad & 0x80u) ? 0u : L;
   }
   if (word_off) word_off[n_reads] = (uint32_t)((n_reads ? (off[n_reads] >> 4) : 0) + n_reads);
   GQ_CATCH
