@@ -110,14 +110,21 @@ void make_dir(const std::string& d) {
 
 // PRG_String(file) (linearised_prg.cpp:8-45): little-endian uint32 stream
 std::vector<uint32_t> read_prg(const std::string& path) {
-  std::ifstream in(path, std::ios::binary);
-  if (!in) {
+  FILE* f = std::fopen(path.c_str(), "rb");
+  if (!f) {
     std::cout << "PRG String file not found: " << path << std::endl;
     std::exit(1);
   }
-  std::vector<uint32_t> prg;
-  unsigned char b[4];
-  while (in.read((char*)b, 4)) prg.push_back((uint32_t)b[0] | (uint32_t)b[1] << 8 | (uint32_t)b[2] << 16 | (uint32_t)b[3] << 24);
+  std::fseek(f, 0, SEEK_END);
+  const long bytes = std::ftell(f);
+  std::fseek(f, 0, SEEK_SET);
+  std::vector<uint32_t> prg((size_t)(bytes > 0 ? bytes : 0) / 4);  // a trailing partial word is ignored
+  const size_t got = prg.empty() ? 0 : std::fread(prg.data(), 4, prg.size(), f);  // one read, not one per symbol
+  std::fclose(f);
+  prg.resize(got);
+  const uint32_t probe = 1;
+  if (*(const unsigned char*)&probe != 1)  // big-endian host: the file is little-endian
+    for (auto& w : prg) w = (w >> 24) | ((w >> 8) & 0xFF00u) | ((w << 8) & 0xFF0000u) | (w << 24);
   return prg;
 }
 
@@ -253,6 +260,7 @@ int run_build(int argc, const char* const* argv, int first) {
   }
   std::cout << "Executing build command" << std::endl;
   std::vector<uint32_t> prg = read_prg(join_path(gram_dir, "prg"));
+  std::cout << "Loaded PRG: " << prg.size() << " symbols" << std::endl;
   gq_index* idx = nullptr;
   check(gq_index_build(prg.data(), prg.size(), kmer_size, 0, &idx));
   check(gq_kmer_index_dump(idx, gram_dir.c_str()));

@@ -62,6 +62,11 @@ def test_gram_build_arguments_and_no_cpu_fallback(built_lib, tmp_path):
     out = subprocess.run([GRAM, "build", "--gram_dir", str(tmp_path), "--kmer_size", "3", "--max_threads", "2"],
                          capture_output=True, text=True)
     assert out.returncode != 0 and "no CUDA device" in (out.stdout + out.stderr)
+    assert "Loaded PRG: 12 symbols" in out.stdout  # the whole file in one read, a trailing partial word ignored
+    with open(tmp_path / "prg", "ab") as f:
+        f.write(b"\x01\x00")
+    out = subprocess.run([GRAM, "build", "--gram_dir", str(tmp_path), "--kmer_size", "3"], capture_output=True, text=True)
+    assert "Loaded PRG: 12 symbols" in out.stdout
     assert not (tmp_path / "kmers").exists()
 
 
