@@ -431,7 +431,7 @@ int main(int argc, const char* const* argv) {
     std::ofstream f(join_path(cov_dir, "allele_sum_coverage"));
     for (uint32_t s = 0; s < lay.n_site_slots; ++s) {
       for (uint64_t a = allele_off[s]; a < allele_off[s + 1]; ++a) f << allele_sum[a] << (a + 1 < allele_off[s + 1] ? " " : "");
-      f << std::endl;
+      f << "\n";  // (no flush per site)
     }
   }
   {  // allele_base.cpp:91-107; empty by convention for nested PRGs (:10-14)
