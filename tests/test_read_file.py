@@ -108,3 +108,24 @@ def test_malformed_record_ends_the_file(tmp_path):
         assert new[0] == expect[name], (name, new)
     with pytest.raises(AssertionError):
         _read(tmp_path / "missing.fastq", 1)
+
+
+def test_random_bytes_fuzz(tmp_path):
+    """Arbitrary line soup over an alphabet rich in '@', '+', '>' and '\\r': whatever the old reader makes of it (records
+    until the first malformed one), the new reader makes the same of it, at every buffer size."""
+    rng = np.random.default_rng(21)
+    alphabet = np.frombuffer(b"ACGTNacgt@+>I#\r ", dtype=np.uint8)
+    for case in range(150):
+        first = [b"@", b">", b"A", b""][case % 4]
+        lines = [first + bytes(rng.choice(alphabet, int(rng.integers(0, 30)))) for _ in range(int(rng.integers(0, 40)))]
+        if case % 3 == 0:  # mostly well-formed FASTQ with a few random lines thrown in
+            lines = []
+            for i in range(int(rng.integers(1, 12))):
+                L = int(rng.integers(0, 25))
+                lines += [b"@r%d" % i, bytes(rng.choice(alphabet[:9], L)), b"+", bytes(rng.choice(alphabet, L)).replace(b"\r", b"I")]
+                if rng.random() < 0.15:
+                    lines.insert(int(rng.integers(0, len(lines))), bytes(rng.choice(alphabet, int(rng.integers(0, 10)))))
+        data = b"\n".join(lines) + (b"\n" if case % 5 else b"")
+        p = tmp_path / f"fuzz{case}"
+        p.write_bytes(data)
+        _same_everywhere(p)
