@@ -47,8 +47,9 @@ int gq_index_destroy(gq_index* idx);
  * load.cpp:11-173). gq_kmer_index_dump writes them from a built index (what `gram build` leaves behind);
  * gq_index_build_from_gram_dir is gq_index_build with the k-mer searches replaced by loading those files (what
  * `gram genotype` does, genotype.cpp:40) — FM-index, graph and masks are still rebuilt from `prg`. The sdsl
- * serialisation is restated in kmer_index_files.cpp; PARITY UNPINNED (no SDSL in this environment, no serialised fixture
- * in the reference): checked by hand-written golden bytes and round trips only. */
+ * serialisation is restated in kmer_index_files.cpp. The contents of the four vectors are pinned by the literals of the
+ * reference's tests/build/kmer_index/test_dump_and_load.cpp; the byte serialisation is PARITY UNPINNED (no SDSL in this
+ * environment, no serialised fixture in the reference): checked by hand-written golden bytes and round trips only. */
 int gq_kmer_index_dump(const gq_index* idx, const char* gram_dir);
 int gq_index_build_from_gram_dir(const uint32_t* prg, uint64_t n_symbols, uint32_t kmer_size, int device,
                                  const char* gram_dir, gq_index** out);

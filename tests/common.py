@@ -68,6 +68,7 @@ def emu_lib():
         lib.emu_new_from.argtypes = [u32p, C.c_uint64, C.c_uint32, C.c_char_p]
         lib.emu_kmer_index_dump.argtypes = [C.c_void_p, C.c_char_p]
         lib.emu_index_save.argtypes = [C.c_void_p, C.c_char_p]
+        lib.emu_set_kmer_index.argtypes = [C.c_void_p, u32p, C.c_uint64]
         lib.emu_read_file.argtypes = [C.c_char_p, C.c_int, C.c_uint64, u64p]
         lib.emu_load.restype = C.c_void_p
         lib.emu_load.argtypes = [C.c_char_p]
@@ -240,6 +241,18 @@ class Emu:
         c = np.zeros(32, dtype=np.uint64)
         self.lib.emu_path_counters(_ptr(c, C.c_uint64), int(reset))
         return {k: int(v) for k, v in zip(self.ROUTES, c) if k != "-"}
+
+    def set_kmer_index(self, words):
+        """Replace the k-mer index by records [code, lo, hi, nt, ng, (site, allele) * nt, (site, _) * ng]."""
+        w = np.ascontiguousarray(words, dtype=np.uint32)
+        if self.lib.emu_set_kmer_index(self.h, _ptr(w, C.c_uint32), w.size) != 0:
+            raise RuntimeError("bad k-mer records")
+
+    def kmer_states(self):
+        n = self.lib.emu_kmer_states(self.h, None)
+        w = np.zeros(max(n, 1), dtype=np.uint32)
+        self.lib.emu_kmer_states(self.h, _ptr(w, C.c_uint32))
+        return w[:n].tolist()
 
     def index_save(self, path):
         """The whole flat index as one checksummed file (host_index_save)."""

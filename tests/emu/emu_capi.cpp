@@ -265,6 +265,38 @@ uint64_t emu_kmer_states(void* ev, uint32_t* words) {
   }
   return t;
 }
+// Replace the k-mer index by hand-written states (tests of the gram_dir files against the literals of the reference's
+// test_dump_and_load.cpp): words = records [code, lo, hi, nt, ng, (site, allele) * nt, (site, ignored) * ng], any order
+// of k-mers, states of one k-mer in the order given. The seed view is not rebuilt (the states need not exist in the PRG).
+int emu_set_kmer_index(void* ev, const uint32_t* words, uint64_t n_words) {
+  auto* e = (Emu*)ev;
+  HostIndex& h = e->h;
+  const uint64_t nk = 1ull << (2 * h.k);
+  std::vector<std::vector<const uint32_t*>> per_code(nk);
+  for (uint64_t t = 0; t < n_words;) {
+    const uint32_t* r = words + t;
+    if (r[0] >= nk) return -1;
+    per_code[r[0]].push_back(r);
+    t += 5 + 2 * r[3] + 2 * r[4];
+  }
+  h.kmer_off.assign(nk + 1, 0);
+  h.kmer_states.clear();
+  h.kmer_paths.clear();
+  std::fill(h.kmer_bits.begin(), h.kmer_bits.end(), 0u);
+  for (uint64_t c = 0; c < nk; ++c) {
+    for (const uint32_t* r : per_code[c]) {
+      const uint32_t nt = r[3], ng = r[4];
+      h.kmer_states.push_back(KmerState{r[1], r[2], (uint32_t)h.kmer_paths.size(), nt | (ng << 16)});
+      for (uint32_t i = 0; i < 2 * nt; ++i) h.kmer_paths.push_back(r[5 + i]);
+      for (uint32_t i = 0; i < ng; ++i) h.kmer_paths.push_back(r[5 + 2 * nt + 2 * i]);
+    }
+    h.kmer_off[c + 1] = (uint32_t)h.kmer_states.size();
+    if (!per_code[c].empty()) h.kmer_bits[c >> 5] |= 1u << (c & 31);
+  }
+  if (h.kmer_paths.empty()) h.kmer_paths.push_back(0);
+  if (h.kmer_states.empty()) h.kmer_states.push_back(KmerState{});
+  return 0;
+}
 // SA-IS with 64-bit indices (texts beyond 2^31 symbols) against the 32-bit instantiation on the same text
 int emu_sais64_agrees(const int32_t* text, uint64_t n, int32_t sigma) {
   std::vector<int32_t> t(text, text + n);

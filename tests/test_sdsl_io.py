@@ -178,3 +178,74 @@ def test_int_vector_random_round_trips(tmp_path):
             want = struct.pack("<Q", n * width) + (b"" if fixed else bytes([width])) + big.to_bytes(8 * n_words, "little")
             assert raw == want, (width, fixed)
             assert _read(p, width if fixed else 0) == (vals, width)
+
+
+# ---- the k-mer indexes of the reference's own dump / load tests (tests/build/kmer_index/test_dump_and_load.cpp) ----
+# Each literal is (k-mer bases 1..4, [(lo, hi, traversed [(site, allele)...], traversing [site...])...]); the expected file
+# contents follow dump.cpp:27-141 (k base codes per k-mer; per k-mer the state count then one path length per state;
+# (lo, hi) per state; (site, allele + 1) per traversed locus then (site, 0) per traversing one).
+_UNK = 0xFFFFFFFF
+REFERENCE_DUMP_CASES = {
+    # DumpKmers.GivenTwoKmers_CorrectAllKmersStructure (:14-28): all_kmers == {1,2,3,4, 2,4,3,4} in either order
+    "two_kmers": [((1, 2, 3, 4), [(1, 1, [], [])]), ((2, 4, 3, 4), [(2, 2, [], [])])],
+    # DumpAndLoadIndex.SearchStatesWithNoVariants (:82-98)
+    "no_variants": [((4, 4, 4, 4), [(20000, 22000, [], []), (52, 53, [], []), (62, 63, [], [])])],
+    # DumpAndLoadIndex.SearchStateVariantsWithLargeIndices (:100-126): > 1 billion sites / alleles
+    "large_indices": [((1, 2, 3, 4), [(6, 6, [(1200000000, 0)], []), (7, 42, [(5, 1200000000)], [])])],
+    # DumpAndLoadIndex.TwoPathsWithMultipleElements (:128-144)
+    "two_paths": [((1, 2, 3, 4), [(6, 6, [(5, 1)], []), (7, 42, [(7, 3), (5, 2)], [9])])],
+    # DumpAndLoadIndex.TwoKmersWithMultipleSearchStates (:146-182)
+    "two_kmers_states": [((1, 2, 3, 4), [(6, 6, [(5, 0)], []), (7, 7, [(5, 1)], []), (8, 8, [(5, 1)], [])]),
+                         ((2, 4, 3, 4), [(9, 10, [], []), (11, 11, [(5, 1), (7, 1)], [])])],
+    # DumpAndLoadIndex.WithTraversingPaths (:184-208)
+    "traversing": [((1, 2, 3, 4), [(6, 6, [(5, 0)], [7]), (7, 7, [(5, 1)], []), (8, 8, [(5, 1)], [11, 9])])],
+}
+
+
+def _code(bases):
+    return sum((b - 1) << (2 * j) for j, b in enumerate(bases))
+
+
+@pytest.mark.parametrize("name", sorted(REFERENCE_DUMP_CASES))
+def test_reference_dump_and_load_literals(tmp_path, name):
+    case = REFERENCE_DUMP_CASES[name]
+    k = len(case[0][0])
+    prg = synth.make_snp_prg(30000, 10, 1)[0]  # only its size matters: the literals' SA indices go up to 22000
+    e = Emu(prg, k)
+    words = []
+    for bases, states in case:
+        for lo, hi, trav, ing in states:
+            words += [_code(bases), lo, hi, len(trav), len(ing)] + [x for loc in trav for x in loc] + [x for s in ing for x in (s, _UNK)]
+    e.set_kmer_index(words)
+    e.kmer_index_dump(str(tmp_path))
+    kmers, _ = _read(str(tmp_path / "kmers"), 3)
+    stats, _ = _read(str(tmp_path / "kmers_stats"), 0)
+    sa_iv, _ = _read(str(tmp_path / "sa_intervals"), 0)
+    paths, _ = _read(str(tmp_path / "paths"), 0)
+    by_code = sorted(case, key=lambda c: _code(c[0]))  # this writer's order (the reference's is its hash map's)
+    assert kmers == [b for bases, _ in by_code for b in bases]
+    assert stats == [x for _, states in by_code for x in [len(states)] + [len(t) + len(g) for _, _, t, g in states]]
+    assert sa_iv == [x for _, states in by_code for lo, hi, _, _ in states for x in (lo, hi)]
+    assert paths == [x for _, states in by_code for _, _, t, g in states
+                     for x in [y for site, al in t for y in (site, al + 1)] + [y for site in g for y in (site, 0)]]
+    # load gives the index back (DumpAndLoadIndex: EXPECT_EQ(load(dump(index)), index))
+    loaded = Emu(prg, k, kmer_index_dir=str(tmp_path))
+    want = []
+    for bases, states in by_code:
+        for lo, hi, trav, ing in states:
+            want += [_code(bases), lo, hi, len(trav), len(ing)] + [x for loc in trav for x in loc] + [x for s in ing for x in (s, _UNK)]
+    assert loaded.kmer_states() == want
+
+
+def test_reference_deserialize_next_stats_layout(tmp_path):
+    """DeserializeNextStats (:34-72): kmers_stats {3, 1, 42, 7, 2, 11, 33} = a k-mer with three states of path lengths
+    1, 42, 7, then one with two states of path lengths 11, 33 — the layout this reader consumes."""
+    p = str(tmp_path / "kmers_stats")
+    _write(p, [3, 1, 42, 7, 2, 11, 33], 6, False)
+    vals, width = _read(p, 0)
+    assert (vals, width) == ([3, 1, 42, 7, 2, 11, 33], 6)
+    i, got = 0, []
+    while i < len(vals):
+        got.append((vals[i], vals[i + 1:i + 1 + vals[i]]))
+        i += 1 + vals[i]
+    assert got == [(3, [1, 42, 7]), (2, [11, 33])]
