@@ -11,8 +11,9 @@
 //   G/coverage/allele_base_coverage.json           (allele_base.cpp:91-107)
 //   G/coverage/grouped_allele_counts_coverage.json (grouped_allele_counts.cpp:93-111)
 //   G/read_stats.json                              (read_stats.cpp:162-209)
-// and prints the five counters as genotype.cpp:55-66 does. The genotyping step that follows in the
-// reference (LevelGenotyper, genotype.cpp:68-118) is out of scope of this back-end.
+// and prints the five counters as genotype.cpp:55-66 does; then the genotyping step of the reference (LevelGenotyper,
+// genotype.cpp:68-118; level_genotyper.cpp, host code) writes G/genotype/genotyped.json, personalised_reference.fasta
+// and genotyped.vcf.gz (and, with --debug, G/site_gtyping_debug_info.txt).
 // gram_dir/prg is what is consumed: FM-index, masks and coverage graph are rebuilt from it (their SDSL / Boost
 // archives are third-party formats); the k-mer index is searched again or, with
 // --kmer_index_from_gram_dir, loaded from gram_dir's kmers / kmers_stats / sa_intervals / paths; with --gq_index the
@@ -291,7 +292,7 @@ int main(int argc, const char* const* argv) {
   if (cmd.empty()) {
     std::cout << "Gramtools! Global options:\n  --command arg   command to execute: {build, genotype, simulate}\n"
                  "  --help          Produce this help message\n  --debug         Turn on debug output\n"
-                 "(B200 quasimap back-end: `genotype` (quasimap part) and `build` (k-mer index files) are served)\n";
+                 "(B200 quasimap back-end: `genotype` and `build` (k-mer index files) are served)\n";
     return 0;
   }
   if (cmd == "build") return run_build(argc, argv, first);
@@ -311,7 +312,7 @@ int main(int argc, const char* const* argv) {
 
   // ReadStats::compute_base_error_rate on the first reads file (genotype.cpp:32-34, read_stats.cpp:21-70)
   uint64_t max_read_length = 0, num_bases = 0, no_qual_reads = 0, informative = 0;
-  double running_qual = 0;
+  float running_qual = 0.0f;  // a float in the reference as well (read_stats.cpp:33): the rounding of its sum is kept
   {
     auto rf = open_reads(p.reads[0]);
     std::string seq, qual;
@@ -321,12 +322,16 @@ int main(int argc, const char* const* argv) {
         ++no_qual_reads;
         continue;
       }
-      for (char q : qual) running_qual += (float)(q - 33);
+      for (char q : qual) running_qual += (q - 33);
       num_bases += qual.size();
       ++informative;
     }
   }
-  double mean_pb_error = num_bases ? std::pow(10.0, -(running_qual / (double)num_bases) / 10.0) : 0.0;
+  double mean_pb_error = 0.0;
+  if (num_bases) {  // read_stats.cpp:62-65: float / int64 is a float division
+    const double mean_qual = running_qual / (int64_t)num_bases;
+    mean_pb_error = std::pow(10, -mean_qual / 10);
+  }
 
   std::cout << "Loading PRG data" << std::endl;
   std::vector<uint32_t> prg = read_prg(join_path(p.gram_dir, "prg"));
@@ -452,11 +457,13 @@ int main(int argc, const char* const* argv) {
     }
     f << "]}" << std::endl;
   }
+  std::vector<uint32_t> grouped_records;  // kept for the genotyper
   {  // grouped_allele_counts.cpp:51-111 (group ids numbered by first appearance, sites in order)
     uint64_t nw = 0;
     check(gq_coverage_grouped(idx, nullptr, &nw));
     std::vector<uint32_t> w(nw ? nw : 1);
     check(gq_coverage_grouped(idx, w.data(), &nw));
+    grouped_records.assign(w.begin(), w.begin() + nw);
     std::map<std::vector<uint32_t>, uint64_t> group_id;
     std::vector<std::map<std::string, uint32_t>> site_counts(lay.n_site_slots);
     for (uint64_t t = 0; t < nw;) {
@@ -490,8 +497,8 @@ int main(int argc, const char* const* argv) {
     }
     f << "]}}" << std::endl;
   }
+  double depth[2];
   {  // read_stats.cpp:162-209
-    double depth[2];
     uint64_t cnt[2];
     check(gq_read_depth_stats(idx, depth, cnt));
     const std::string path = join_path(p.genotype_dir, "read_stats.json");
@@ -508,9 +515,22 @@ int main(int argc, const char* const* argv) {
   std::cout << "Count reads with >0 kmers not in kmer index: " << st[2] << std::endl;
   std::cout << "Count reads with no exact mapping: " << st[3] << std::endl;
   std::cout << "Count exact mapped reads: " << st[4] << std::endl;
-  std::cout << "====================" << std::endl
-            << "Genotyping (LevelGenotyper) is not part of the B200 quasimap back-end; coverage files are complete."
-            << std::endl;
-  for (gq_index* h : handles) gq_index_destroy(h);
+  for (gq_index* h : handles) gq_index_destroy(h);  // the device is not needed any more
+  handles.clear();
+
+  // ---- genotyping (genotype.cpp:68-118): LevelGenotyper on the fetched coverage, host code of libgq.so ----------
+  std::cout << "====================" << std::endl << "Running genotyping" << std::endl;
+  const std::string debug_file = p.debug ? join_path(p.genotype_dir, "site_gtyping_debug_info.txt") : std::string();
+  if (p.debug) std::cout << "Logging debug genotyping stats to " << debug_file << std::endl;
+  std::cout << "Running genotyping model" << std::endl;
+  {
+    const uint64_t nw = grouped_records.size();
+    const double stats3[3] = {depth[0], depth[1], mean_pb_error};
+    std::cout << "Producing json vcf, personalised reference, vcf" << std::endl;
+    check(gq_level_genotype(prg.data(), prg.size(), lay.n_per_base ? per_base.data() : nullptr, lay.n_per_base,
+                            nw ? grouped_records.data() : nullptr, nw, stats3, p.ploidy == "haploid" ? 1 : 2,
+                            p.sample_id.c_str(), join_path(p.gram_dir, "prg_coords.tsv").c_str(),
+                            join_path(p.genotype_dir, "genotype").c_str(), p.debug ? debug_file.c_str() : nullptr, 42));
+  }
   return 0;
 }

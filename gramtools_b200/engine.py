@@ -80,6 +80,11 @@ def load_library():
         "gq_set_option": [vp, C.c_char_p, C.c_int64],
         "gq_last_run_info": [vp, C.POINTER(C.c_double)],
         "gq_last_kernel_ms": [vp, C.POINTER(C.c_double)],
+        "gq_level_genotype": [u32p, C.c_uint64, u16p, C.c_uint64, u32p, C.c_uint64, C.POINTER(C.c_double), C.c_int,
+                              C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint32],
+        "gq_level_genotype_json": [u32p, C.c_uint64, u16p, C.c_uint64, u32p, C.c_uint64, C.POINTER(C.c_double), C.c_int,
+                                   C.c_char_p, C.c_uint32, C.c_char_p, u64p],
+        "gq_read_depth_stats_host": [u32p, C.c_uint64, u16p, C.c_uint64, u32p, C.c_uint64, C.POINTER(C.c_double), u64p],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)
@@ -406,3 +411,57 @@ class QuasimapIndex:
         words = np.ascontiguousarray(words, dtype=np.uint32)
         self._check(self._lib.gq_coverage_groups_import(self._h, _ptr(words, C.c_uint32) if words.size else None,
                                                         words.size, int(bool(replace))))
+
+
+# ---- genotyping step (host code of libgq.so; genotype.cpp:68-118) ----------------------------------------------
+
+def _cov_args(prg, per_base, grouped):
+    prg = np.ascontiguousarray(prg, dtype=np.uint32)
+    per_base = np.ascontiguousarray(per_base, dtype=np.uint16)
+    grouped = np.ascontiguousarray(grouped, dtype=np.uint32)
+    pb = per_base if per_base.size else np.zeros(1, np.uint16)
+    gw = grouped if grouped.size else np.zeros(1, np.uint32)
+    keep = (prg, pb, gw)
+    return keep, (_ptr(prg, C.c_uint32), prg.size, _ptr(pb, C.c_uint16), per_base.size, _ptr(gw, C.c_uint32), grouped.size)
+
+
+def read_depth_stats_host(prg, per_base, grouped):
+    """ReadStats::compute_coverage_depth (read_stats.cpp:119-160) from fetched coverage, without a device handle."""
+    lib = load_library()
+    keep, args = _cov_args(prg, per_base, grouped)
+    d = (C.c_double * 2)()
+    c = np.zeros(2, dtype=np.uint64)
+    if lib.gq_read_depth_stats_host(*args, d, _ptr(c, C.c_uint64)) != 0:
+        raise GqError(lib.gq_last_error().decode())
+    return {"mean": d[0], "variance": d[1], "num_sites_noCov": int(c[0]), "num_sites_total": int(c[1])}
+
+
+def level_genotype_json(prg, per_base, grouped, mean_cov, var_cov, mean_pb_error, ploidy="haploid", sample_id="sample",
+                        gcp_seed=42):
+    """LevelGenotyper + make_json_prg (runner.cpp:27-97, make_json.cpp:7-25): the text of genotyped.json."""
+    lib = load_library()
+    keep, args = _cov_args(prg, per_base, grouped)
+    stats = (C.c_double * 3)(mean_cov, var_cov, mean_pb_error)
+    pl = {"haploid": 1, "diploid": 2}[ploidy]
+    n = np.zeros(1, dtype=np.uint64)
+    if lib.gq_level_genotype_json(*args, stats, pl, sample_id.encode(), gcp_seed, None, _ptr(n, C.c_uint64)) != 0:
+        raise GqError(lib.gq_last_error().decode())
+    buf = C.create_string_buffer(int(n[0]))
+    if lib.gq_level_genotype_json(*args, stats, pl, sample_id.encode(), gcp_seed, buf, _ptr(n, C.c_uint64)) != 0:
+        raise GqError(lib.gq_last_error().decode())
+    return buf.value.decode()
+
+
+def level_genotype(prg, per_base, grouped, mean_cov, var_cov, mean_pb_error, genotype_dir, ploidy="haploid",
+                   sample_id="sample", prg_coords_path=None, debug_path=None, gcp_seed=42):
+    """The genotyping half of commands::genotype::run (genotype.cpp:68-118): writes genotyped.json,
+    personalised_reference.fasta and genotyped.vcf.gz into `genotype_dir`."""
+    lib = load_library()
+    keep, args = _cov_args(prg, per_base, grouped)
+    stats = (C.c_double * 3)(mean_cov, var_cov, mean_pb_error)
+    pl = {"haploid": 1, "diploid": 2}[ploidy]
+    rc = lib.gq_level_genotype(*args, stats, pl, sample_id.encode(),
+                               os.fsencode(prg_coords_path) if prg_coords_path else None, os.fsencode(genotype_dir),
+                               os.fsencode(debug_path) if debug_path else None, gcp_seed)
+    if rc != 0:
+        raise GqError(lib.gq_last_error().decode())

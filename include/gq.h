@@ -169,6 +169,31 @@ int gq_coverage_device_ptrs(gq_index* idx, void** counters, uint64_t* n_counters
 int gq_coverage_groups_export(gq_index* idx, uint32_t* words, uint64_t* n_words);
 int gq_coverage_groups_import(gq_index* idx, const uint32_t* words, uint64_t n_words, int replace);
 
+/* ---- genotyping: what commands::genotype::run does once quasimap has returned (genotype.cpp:68-118) ----
+ * LevelGenotyper (infer/level_genotyping/{runner,model,probabilities}.cpp, infer/allele_extracter.cpp) on the coverage
+ * of one sample, then the three files of geno_dir/genotype: genotyped.json (output_specs/make_json.cpp),
+ * personalised_reference.fasta (personalised_reference.cpp) and genotyped.vcf.gz (output_specs/make_vcf.cpp, BGZF).
+ * Host code: no device is needed. prg: the linearised PRG; per_base / n_per_base: the flat per-base vector of
+ * gq_coverage_fetch (gq_layout.n_per_base entries); grouped / n_grouped_words: the records of gq_coverage_grouped;
+ * stats = {mean coverage, coverage variance (gq_read_depth_stats), mean per-base error rate (ReadStats,
+ * read_stats.cpp:21-70)}; ploidy 1 or 2; prg_coords_path: gram_dir/prg_coords.tsv (NULL or missing: one segment
+ * named gramtools_prg); debug_path: NULL, or the file the per-site debug lines are appended to (--debug);
+ * gcp_seed: seed of the genotype-confidence simulation (GCP::Model's default is 42, lib/GCP/GCP.h:26).
+ * Doubles follow the reference's arithmetic operation for operation; the VCF text is what htslib would print, restated
+ * (htslib is absent here: parity unpinned, like the sdsl files). */
+int gq_level_genotype(const uint32_t* prg, uint64_t n_symbols, const uint16_t* per_base, uint64_t n_per_base,
+                      const uint32_t* grouped, uint64_t n_grouped_words, const double stats[3], int ploidy,
+                      const char* sample_id, const char* prg_coords_path, const char* genotype_dir,
+                      const char* debug_path, uint32_t gcp_seed);
+/* gq_read_depth_stats without a handle: the same arithmetic from the PRG and fetched coverage (host code). */
+int gq_read_depth_stats_host(const uint32_t* prg, uint64_t n_symbols, const uint16_t* per_base, uint64_t n_per_base,
+                             const uint32_t* grouped, uint64_t n_grouped_words, double out[2], uint64_t counts[2]);
+/* The same run, returning only the text of genotyped.json (one segment): json_out may be NULL to ask for the size;
+ * *json_bytes is the capacity on entry and the size (with the terminating 0) on return. */
+int gq_level_genotype_json(const uint32_t* prg, uint64_t n_symbols, const uint16_t* per_base, uint64_t n_per_base,
+                           const uint32_t* grouped, uint64_t n_grouped_words, const double stats[3], int ploidy,
+                           const char* sample_id, uint32_t gcp_seed, char* json_out, uint64_t* json_bytes);
+
 /* Run the kernels on a caller-owned CUDA stream (e.g. torch's current stream) so that the caller's
  * CUDA events bracket them. NULL = the library's own stream. */
 int gq_set_stream(gq_index* idx, void* cuda_stream);

@@ -3,6 +3,7 @@
 // legs. Never linked into libgq.so.
 #include <omp.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cstring>
 #include <string>
@@ -57,6 +58,43 @@ void gqo_sizes(void* hv, uint64_t out[6]) {
   uint64_t ks = 0;
   for (auto& e : h->m.kmers) ks += e.second.size();
   out[5] = ks;
+}
+
+// The k-mer index as flat records [code, lo, hi, nt, ng, (site, allele) * nt, (site, 0xFFFFFFFF) * ng], k-mers by
+// ascending code (base j of the k-mer at bits [2j, 2j + 2)), the states of a k-mer in the index's own order
+// (build.cpp's worklist order, pinned by test_build.cpp:404-429). words == NULL: only the size.
+uint64_t gqo_kmer_states(void* hv, uint32_t* words) {
+  auto* h = (OracleHandle*)hv;
+  std::vector<std::pair<uint64_t, const SearchStates*>> by_code;
+  for (auto& e : h->m.kmers) {
+    uint64_t code = 0;
+    for (size_t j = 0; j < e.first.size(); ++j) code |= (uint64_t)(e.first[j] - 1) << (2 * j);
+    by_code.emplace_back(code, &e.second);
+  }
+  std::sort(by_code.begin(), by_code.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+  uint64_t t = 0;
+  for (auto& kv : by_code)
+    for (const SearchState& st : *kv.second) {
+      const uint32_t nt = (uint32_t)st.traversed.size(), ng = (uint32_t)st.traversing.size();
+      if (words) {
+        words[t] = (uint32_t)kv.first;
+        words[t + 1] = (uint32_t)st.lo;
+        words[t + 2] = (uint32_t)st.hi;
+        words[t + 3] = nt;
+        words[t + 4] = ng;
+        uint64_t q = t + 5;
+        for (auto& loc : st.traversed) {
+          words[q++] = (uint32_t)loc.first;
+          words[q++] = (uint32_t)loc.second;
+        }
+        for (auto& loc : st.traversing) {
+          words[q++] = (uint32_t)loc.first;
+          words[q++] = 0xFFFFFFFFu;
+        }
+      }
+      t += 5 + 2 * nt + 2 * ng;
+    }
+  return t;
 }
 
 // handle_reads_buffer (quasimap.cpp:82-118) over one batch; threads = omp threads (1 = serial)

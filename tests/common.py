@@ -39,6 +39,8 @@ def oracle_lib():
         lib.gqo_last_error.restype = C.c_char_p
         lib.gqo_master_seeds.argtypes = [C.c_uint32, C.c_uint64, u32p]
         lib.gqo_sizes.argtypes = [C.c_void_p, u64p]
+        lib.gqo_kmer_states.argtypes = [C.c_void_p, u32p]
+        lib.gqo_kmer_states.restype = C.c_uint64
         lib.gqo_map.argtypes = [C.c_void_p, u8p, u64p, C.c_uint64, u32p, C.c_int, C.c_int, C.c_int]
         lib.gqo_last_seconds.argtypes = [C.c_void_p]
         lib.gqo_last_seconds.restype = C.c_double
@@ -150,6 +152,14 @@ class Oracle:
         s = np.zeros(6, dtype=np.uint64)
         self.lib.gqo_sizes(self.h, _ptr(s, C.c_uint64))
         self.n_sites, self.n_alleles, self.n_per_base, self.is_nested, self.sa_size, self.n_kmer_states = [int(x) for x in s]
+
+    def kmer_states(self):
+        """The oracle's k-mer index: [code, lo, hi, nt, ng, (site, allele) * nt, (site, ~0) * ng] records, k-mers by
+        ascending code, states in the reference's order."""
+        n = self.lib.gqo_kmer_states(self.h, None)
+        w = np.zeros(max(n, 1), dtype=np.uint32)
+        self.lib.gqo_kmer_states(self.h, _ptr(w, C.c_uint32))
+        return w[:n].tolist()
 
     def __del__(self):
         if getattr(self, "h", None):
