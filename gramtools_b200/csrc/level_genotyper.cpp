@@ -4,6 +4,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <charconv>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -865,10 +866,9 @@ std::string json_number(double v) {
     v = -v;
   }
   char buf[40];
-  int prec = 0;
-  for (; prec < 17; ++prec) {
-    std::snprintf(buf, sizeof buf, "%.*e", prec, v);
-    if (std::strtod(buf, nullptr) == v) break;
+  {  // shortest digits that round-trip, in scientific form: d[.ddd]e±XX
+    auto r = std::to_chars(buf, buf + sizeof buf - 1, v, std::chars_format::scientific);
+    *r.ptr = 0;
   }
   std::string digits;
   const char* e = std::strchr(buf, 'e');
@@ -974,20 +974,50 @@ std::string LevelGenotyper::json(const std::string& sample_id, SegmentTracker& t
        ",\"FT\":" + desc(kDescFT) + ",\"GT\":" + desc(kDescGT) + ",\"GT_CONF\":" + desc(kDescGTCONF) +
        ",\"GT_CONF_PERCENTILE\":" + desc(kDescGCP) + ",\"HAPG\":" + desc("Sample haplogroups of genotyped alleles") +
        ",\"POS\":" + desc("Position on reference or pseudo-reference") + ",\"SEG\":" + desc("Segment ID") + "},\"Sites\":[";
+  o.reserve(o.size() + 192 * sites_.size());
+  auto ints = [&o](const std::vector<int32_t>& v) {
+    o += '[';
+    for (size_t i = 0; i < v.size(); ++i) {
+      if (i) o += ',';
+      o += std::to_string(v[i]);
+    }
+    o += ']';
+  };
   for (size_t i = 0; i < sites_.size(); ++i) {
     const Site& s = sites_[i];
-    const std::string seg = tracker.get_id(s.pos);
+    const std::string& seg = tracker.get_id(s.pos);
     const uint64_t pos = tracker.relative_pos(s.pos) + 1;
-    o += i ? ",{" : "{";
-    o += "\"ALS\":" + json_array(s.alleles, [](const Allele& a) { return json_string(a.seq); });
-    o += ",\"COV\":[" + json_array(s.allele_covs, [](double c) { return json_number(c); }) + "]";
-    o += ",\"DP\":[" + std::to_string(s.total_coverage) + "]";
-    o += ",\"FT\":[" + json_array(s.filters, [](const std::string& f) { return json_string(f); }) + "]";
-    o += ",\"GT\":[" + (s.is_null() ? std::string("[null]") : json_array(s.genotype, [](int32_t g) { return std::to_string(g); })) + "]";
-    o += ",\"GT_CONF\":[" + json_number(s.gt_conf) + "]";
-    o += ",\"GT_CONF_PERCENTILE\":[" + json_number(s.gt_conf_percentile) + "]";
-    o += ",\"HAPG\":[" + json_array(s.haplogroups, [](int32_t h) { return std::to_string(h); }) + "]";
-    o += ",\"POS\":" + std::to_string(pos) + ",\"SEG\":" + json_string(seg) + "}";
+    o += i ? ",{\"ALS\":[" : "{\"ALS\":[";
+    for (size_t a = 0; a < s.alleles.size(); ++a) {
+      if (a) o += ',';
+      o += json_string(s.alleles[a].seq);
+    }
+    o += "],\"COV\":[[";
+    for (size_t c = 0; c < s.allele_covs.size(); ++c) {
+      if (c) o += ',';
+      o += json_number(s.allele_covs[c]);
+    }
+    o += "]],\"DP\":[";
+    o += std::to_string(s.total_coverage);
+    o += "],\"FT\":[[";
+    for (size_t f = 0; f < s.filters.size(); ++f) {
+      if (f) o += ',';
+      o += json_string(s.filters[f]);
+    }
+    o += "]],\"GT\":[";
+    if (s.is_null()) o += "[null]";
+    else ints(s.genotype);
+    o += "],\"GT_CONF\":[";
+    o += json_number(s.gt_conf);
+    o += "],\"GT_CONF_PERCENTILE\":[";
+    o += json_number(s.gt_conf_percentile);
+    o += "],\"HAPG\":[";
+    ints(s.haplogroups);
+    o += "],\"POS\":";
+    o += std::to_string(pos);
+    o += ",\"SEG\":";
+    o += json_string(seg);
+    o += '}';
   }
   return o + "]}";
 }
