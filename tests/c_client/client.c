@@ -26,6 +26,23 @@ int main(void) {
     uint32_t sa[9];
     if (gq_suffix_array(prg, 8, 0, sa, NULL) == 0) return 7;
   }
+  { /* the genotyping step is host code: a two-allele site with 9 reads on allele 1 and 1 read on allele 0 */
+    const uint32_t prg[] = {1, 2, 5, 3, 6, 4, 6, 1};
+    const uint16_t per_base[] = {1, 9};
+    const uint32_t grouped[] = {0, 1, 1, 0, /* site 0: {0} x 1 */ 0, 9, 1, 1 /* {1} x 9 */};
+    const double stats[3] = {9.0, 0.0, 0.001};
+    double depth[2];
+    uint64_t counts[2], bytes = 0;
+    char* json;
+    if (gq_read_depth_stats_host(prg, 8, per_base, 2, grouped, 8, depth, counts) != 0) return 8;
+    if (depth[0] != 9.0 || counts[0] != 0 || counts[1] != 1) return 9;
+    if (gq_level_genotype_json(prg, 8, per_base, 2, grouped, 8, stats, 1, "c", 42, NULL, &bytes) != 0 || bytes < 100) return 10;
+    json = (char*)malloc(bytes);
+    if (gq_level_genotype_json(prg, 8, per_base, 2, grouped, 8, stats, 1, "c", 42, json, &bytes) != 0) return 11;
+    if (strstr(json, "\"ALS\":[\"G\",\"T\"]") == NULL || strstr(json, "\"GT\":[[1]]") == NULL) return 12;
+    free(json);
+    if (gq_level_genotype_json(prg, 6, per_base, 2, grouped, 8, stats, 1, "c", 42, NULL, &bytes) == 0) return 13; /* a site with one allele */
+  }
   free(packed);
   printf("c client ok (%d CUDA devices)\n", n_dev);
   return 0;
