@@ -295,6 +295,27 @@ def test_flat_index_invariants():
         Emu(prg, k).index_check()
 
 
+def test_kmer_index_holds_the_oracles_states():
+    """index_kmers (build.cpp:101-131): k-mer by k-mer, the product's index holds exactly the SearchStates the oracle's
+    vBWT searches end with — SA interval, traversed loci in order, traversing sites. The ORDER of a k-mer's states in
+    the reference's list is a by-product of its worklist (and never read by quasimap: classes are selected through a
+    std::map, coverage_common.cpp:166-177); the flat index keeps them in DFS order, so k-mers are compared as sets."""
+    def records(words):
+        out, i = [], 0
+        while i < len(words):
+            n = 5 + 2 * words[i + 3] + 2 * words[i + 4]
+            out.append(tuple(words[i:i + n]))
+            i += n
+        return out
+    for prg, k in ((synth.make_snp_prg(2000, 80, 3)[0], 5), (synth.make_nested_prg(5, 300, 9), 4),
+                   (synth.make_indel_prg(2000, 60, 5), 5),
+                   (np.asarray([1, 2, 3, 4, 5, 1, 6, 2, 6, 3, 3, 7, 4, 8, 8, 1], dtype=np.uint32), 2)):
+        want, got = records(Oracle(prg, k).kmer_states()), records(Emu(prg, k).kmer_states())
+        assert len(want) == len(got) and len(want) > 0
+        assert sorted(want) == sorted(got)
+        assert [r[0] for r in want] == sorted(r[0] for r in want)  # both by ascending k-mer code
+
+
 def test_long_reads_host():
     prg = synth.make_snp_prg(30000, 1200, 21)[0]
     bases, offs = _reads_for(prg, 300, 700, 21, garbage=0.3, n_frac=0.0)
