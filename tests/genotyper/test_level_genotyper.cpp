@@ -377,6 +377,28 @@ static void test_allele_extraction() {
   }
 }
 
+static void test_site_interface() {
+  CASE("GetUniqueGenotypedAlleles / NonGenotypedHaplogroups (test_interfaces.cpp:9-86), Alleles (test_types.cpp:6-19)");
+  Alleles three{{"CCC", {1, 1, 1}}, {"GGG", {1, 1, 1}}, {"TTT", {1, 1, 1}}};
+  CHECK(same_alleles(mock_site(three, {0, 0, 1}).unique_genotyped_alleles(), Alleles{three[0], three[1]}));
+  CHECK(same_alleles(mock_site(three, {2, 0}).unique_genotyped_alleles(), Alleles{three[0], three[2]}));
+  CHECK(mock_site(three, {-1}).unique_genotyped_alleles().empty());
+  Site s = mock_site({{"ACGT", {1, 1, 1, 1}, 0}, {"TTTA", {1, 8, 1, 1}, 1}, {"TATA", {1, 8, 2, 1}, 1}}, {1, 2});
+  s.num_haplogroups = 5;
+  CHECK((s.non_genotyped_haplogroups() == std::vector<int32_t>{0, 2, 3, 4}));
+  Allele joined = Allele{"ATA", {0, 1, 0}, 0}.joined(Allele{"TT", {2, 0}, 1});
+  CHECK(joined == (Allele{"ATATT", {0, 1, 0, 2, 0}, 0}));
+  CHECK((Allele{"ATAT", {2, 5, 0, 3}, 0}.mean_cov() == 2.5));
+  Site called = mock_site(three, {1});
+  called.total_coverage = 7;
+  called.gt_conf = 3.5;
+  called.allele_covs = {1., 6.};
+  called.haplogroups = {1};
+  called.make_null();  // interfaces.hpp:83-87, site.cpp:45-48: only the genotype, the depth and the confidences go
+  CHECK(called.is_null() && called.total_coverage == 0 && called.gt_conf == 0. && called.alleles.size() == 3);
+  CHECK(called.allele_covs.size() == 2 && called.haplogroups.size() == 1);
+}
+
 static void test_runner_logic() {
   CASE("LevelGenotyperInvalidation (test_runner.cpp:173-192)");
   {
@@ -525,6 +547,7 @@ int main() {
   test_model_coverages();
   test_model_calls();
   test_allele_extraction();
+  test_site_interface();
   test_runner_logic();
   test_segments_and_outputs();
   std::printf("%d checks, %d failed\n", g_checks, g_failed);

@@ -91,6 +91,12 @@ def test_two_site_non_nested_prg(built_lib):
     assert sorted(j["Site_Fields"]) == ["ALS", "COV", "DP", "FT", "GT", "GT_CONF", "GT_CONF_PERCENTILE", "HAPG", "POS", "SEG"]
     for s in j["Sites"]:
         assert s["GT_CONF"][0] > 0 and 0 < s["GT_CONF_PERCENTILE"][0] <= 100
+    # the confidence, recomputed independently (model.cpp:238-282): Poisson(5.5) depth model, error rate 1e-3,
+    # log likelihood = wrong reads * ln(error) + ln pmf(mean allele coverage) (+ gap penalty: none here)
+    from scipy.stats import poisson
+    ll = lambda own, other: other * np.log(1e-3) + poisson.logpmf(own, 5.5)
+    assert abs(j["Sites"][0]["GT_CONF"][0] - (ll(5, 1) - ll(1, 5))) < 1e-9
+    assert abs(j["Sites"][1]["GT_CONF"][0] - (ll(6, 0) - (ll(0, 6) + poisson.logpmf(0, 5.5)))) < 1e-9  # G: 1 of 1 bases uncovered
 
 
 def test_two_site_nested_prg(built_lib):
@@ -142,6 +148,14 @@ def test_diploid_heterozygous_call(built_lib):
     j, _, _, _ = genotype(prg, ["AATAACAATT"] * 10 + ["AATAAGAATT"] * 9, "?", ploidy="diploid")
     s = j["Sites"][0]
     assert s["GT"] == [[0, 1]] and s["ALS"] == ["C", "G"] and s["HAPG"] == [[0, 1]] and s["COV"] == [[10.0, 9.0]]
+    # one site: depth mean 10 (the C allele), variance 0 -> Poisson(10); het 0/1 against the best homozygous call
+    # (model.cpp:284-335: a homozygous call halves the haplogroup's coverage between its two copies but scores each
+    # copy on the allele's full mean per-base coverage)
+    from scipy.stats import poisson
+    lp = lambda c: poisson.logpmf(c, 10.0)
+    het = 0 * np.log(1e-3) + lp(10) + lp(9)
+    hom_c = 9 * np.log(1e-3) + 2 * lp(10)
+    assert abs(s["GT_CONF"][0] - (het - hom_c)) < 1e-9
 
 
 def test_ambiguous_site_is_filtered_and_filter_propagates(built_lib):
