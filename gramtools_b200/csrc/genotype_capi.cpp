@@ -1,6 +1,7 @@
 // genotype_capi.cpp — C entry points of the genotyping step (level_genotyper.cpp): host code, no device needed.
 #include <cstdint>
 #include <fstream>
+#include <future>
 #include <sstream>
 #include <stdexcept>
 #include <string>
@@ -30,7 +31,7 @@ void spit(const std::string& path, const std::string& text) {
 
 gq::lg::LevelGenotyper run(const uint32_t* prg, uint64_t n_symbols, const uint16_t* per_base, uint64_t n_per_base,
                            const uint32_t* grouped, uint64_t n_grouped_words, const double stats[3], int ploidy,
-                           uint32_t gcp_seed, bool debug) {
+                           uint32_t gcp_seed, bool debug, int n_threads) {
   if (!prg || !stats || (n_grouped_words && !grouped)) throw std::runtime_error("null argument");
   if (ploidy != 1 && ploidy != 2) throw std::runtime_error("ploidy must be 1 (haploid) or 2 (diploid)");
   gq::lg::PrgSites ps = gq::lg::parse_prg_sites(prg, n_symbols);
@@ -45,6 +46,7 @@ gq::lg::LevelGenotyper run(const uint32_t* prg, uint64_t n_symbols, const uint16
   opt.ploidy = ploidy == 1 ? gq::lg::Ploidy::Haploid : gq::lg::Ploidy::Diploid;
   opt.gcp_seed = gcp_seed;
   opt.debug = debug;
+  opt.n_threads = n_threads;
   return gq::lg::LevelGenotyper(std::move(ps), per_base, grouped, n_grouped_words, stats[0], stats[1], stats[2], opt);
 }
 
@@ -55,21 +57,38 @@ extern "C" {
 int gq_level_genotype(const uint32_t* prg, uint64_t n_symbols, const uint16_t* per_base, uint64_t n_per_base,
                       const uint32_t* grouped, uint64_t n_grouped_words, const double stats[3], int ploidy,
                       const char* sample_id, const char* prg_coords_path, const char* genotype_dir,
-                      const char* debug_path, uint32_t gcp_seed) {
+                      const char* debug_path, uint32_t gcp_seed, int n_threads) {
   try {
     if (!sample_id || !genotype_dir) throw std::runtime_error("null argument");
     const bool debug = debug_path && *debug_path;
     gq::lg::LevelGenotyper g =
-        run(prg, n_symbols, per_base, n_per_base, grouped, n_grouped_words, stats, ploidy, gcp_seed, debug);
-    const std::string dir = std::string(genotype_dir) + "/";
-    gq::lg::SegmentTracker tracker(slurp(prg_coords_path));
-    spit(dir + "genotyped.json", g.json(sample_id, tracker) + "\n");  // genotype.cpp:92-98
-    tracker.reset();
-    spit(dir + "personalised_reference.fasta",  // genotype.cpp:100-108
-         gq::lg::deduped_fasta_text(g.personalised_reference(tracker),
-                                    std::string(sample_id) + " personalised reference made by gramtools genotype"));
-    tracker.reset();
-    spit(dir + "genotyped.vcf.gz", gq::lg::bgzf_compress(g.vcf(sample_id, tracker)));  // genotype.cpp:110-112
+        run(prg, n_symbols, per_base, n_per_base, grouped, n_grouped_words, stats, ploidy, gcp_seed, debug, n_threads);
+    const std::string dir = std::string(genotype_dir) + "/", coords = slurp(prg_coords_path), sample = sample_id;
+    // the three files are independent of one another (each walks the sites with its own segment tracker)
+    const auto policy = n_threads == 1 ? std::launch::deferred : std::launch::async;
+    auto json = std::async(policy, [&] {  // genotype.cpp:92-98
+      gq::lg::SegmentTracker tracker(coords);
+      spit(dir + "genotyped.json", g.json(sample, tracker) + "\n");
+    });
+    auto fasta = std::async(policy, [&] {  // genotype.cpp:100-108
+      gq::lg::SegmentTracker tracker(coords);
+      spit(dir + "personalised_reference.fasta",
+           gq::lg::deduped_fasta_text(g.personalised_reference(tracker),
+                                      sample + " personalised reference made by gramtools genotype"));
+    });
+    auto vcf = std::async(policy, [&] {  // genotype.cpp:110-112
+      gq::lg::SegmentTracker tracker(coords);
+      spit(dir + "genotyped.vcf.gz", gq::lg::bgzf_compress(g.vcf(sample, tracker)));
+    });
+    std::string failure;
+    for (auto* f : {&json, &fasta, &vcf}) {
+      try {
+        f->get();
+      } catch (const std::exception& e) {
+        if (failure.empty()) failure = e.what();
+      }
+    }
+    if (!failure.empty()) throw std::runtime_error(failure);
     if (debug) {
       std::ofstream f(debug_path, std::ios::app);  // runner.cpp:45-50: appended
       f << g.debug_text();
@@ -103,11 +122,12 @@ int gq_read_depth_stats_host(const uint32_t* prg, uint64_t n_symbols, const uint
 
 int gq_level_genotype_json(const uint32_t* prg, uint64_t n_symbols, const uint16_t* per_base, uint64_t n_per_base,
                            const uint32_t* grouped, uint64_t n_grouped_words, const double stats[3], int ploidy,
-                           const char* sample_id, uint32_t gcp_seed, char* json_out, uint64_t* json_bytes) {
+                           const char* sample_id, uint32_t gcp_seed, int n_threads, char* json_out,
+                           uint64_t* json_bytes) {
   try {
     if (!sample_id || !json_bytes) throw std::runtime_error("null argument");
     gq::lg::LevelGenotyper g =
-        run(prg, n_symbols, per_base, n_per_base, grouped, n_grouped_words, stats, ploidy, gcp_seed, false);
+        run(prg, n_symbols, per_base, n_per_base, grouped, n_grouped_words, stats, ploidy, gcp_seed, false, n_threads);
     gq::lg::SegmentTracker tracker;
     const std::string text = g.json(sample_id, tracker);
     if (json_out) {

@@ -530,7 +530,8 @@ int main(int argc, const char* const* argv) {
     check(gq_level_genotype(prg.data(), prg.size(), lay.n_per_base ? per_base.data() : nullptr, lay.n_per_base,
                             nw ? grouped_records.data() : nullptr, nw, stats3, p.ploidy == "haploid" ? 1 : 2,
                             p.sample_id.c_str(), join_path(p.gram_dir, "prg_coords.tsv").c_str(),
-                            join_path(p.genotype_dir, "genotype").c_str(), p.debug ? debug_file.c_str() : nullptr, 42));
+                            join_path(p.genotype_dir, "genotype").c_str(), p.debug ? debug_file.c_str() : nullptr, 42,
+                            (int)p.max_threads));
   }
   return 0;
 }

@@ -2,6 +2,9 @@
 #include "level_genotyper.hpp"
 
 #include <zlib.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #include <algorithm>
 #include <charconv>
@@ -712,22 +715,52 @@ LevelGenotyper::LevelGenotyper(PrgSites ps, const Cov* per_base, const uint32_t*
   std::iota(order.begin(), order.end(), 0u);
   std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return ps_.sites[a].entry > ps_.sites[b].entry; });
   static const Cov kNoCov = 0;
-  for (uint32_t s : order) {
-    Alleles alleles = extract_alleles(ps_, s, per_base ? per_base : &kNoCov, sites_);
-    SiteModel model(alleles, counts[s], ploidy_, &l_stats_, opt.debug);
-    Site site = model.site();
-    site.pos = ps_.sites[s].pos;
-    site.end_text = ps_.sites[s].end;
-    site.end_pos = ps_.sites[s].end_pos;
-    if (opt.debug) {
-      debug_text_ += "site index: \t" + std::to_string(s);
-      debug_text_ += site.is_null() ? std::string("\tnull gt \n") : site.debug_info + "\n";
+  const Cov* pb = per_base ? per_base : &kNoCov;
+  // a level-1 site and everything nested in it form one unit of work: in `order` its descendants come right before
+  // it, so the units are consecutive runs ending with a site that has no parent. Units are independent (allele
+  // extraction, invalidation and filter propagation stay inside one), so they are genotyped in parallel; each thread
+  // memoises the pmf in its own copy of the likelihood parameters. Debug output is ordered: one thread.
+  std::vector<uint32_t> unit_end;
+  for (uint32_t i = 0; i < S; ++i)
+    if (ps_.sites[order[i]].parent < 0) unit_end.push_back(i + 1);
+  int n_threads = opt.debug ? 1 : opt.n_threads;
+#ifdef _OPENMP
+  if (n_threads <= 0) n_threads = omp_get_max_threads();
+#else
+  n_threads = 1;
+#endif
+  n_threads = std::max(1, std::min<int>(n_threads, (int)unit_end.size() / 64 + 1));
+  std::string first_error;
+#pragma omp parallel num_threads(n_threads)
+  {
+    LStats local = n_threads > 1 ? make_l_stats(mean_cov, var_cov, mean_pb_error) : l_stats_;
+#pragma omp for schedule(dynamic, 64)
+    for (int64_t u = 0; u < (int64_t)unit_end.size(); ++u) {
+      try {
+        for (uint32_t i = u ? unit_end[(size_t)u - 1] : 0; i < unit_end[(size_t)u]; ++i) {
+          const uint32_t s = order[i];
+          Alleles alleles = extract_alleles(ps_, s, pb, sites_);
+          SiteModel model(alleles, counts[s], ploidy_, &local, opt.debug);
+          Site site = model.site();
+          site.pos = ps_.sites[s].pos;
+          site.end_text = ps_.sites[s].end;
+          site.end_pos = ps_.sites[s].end_pos;
+          if (opt.debug) {
+            debug_text_ += "site index: \t" + std::to_string(s);
+            debug_text_ += site.is_null() ? std::string("\tnull gt \n") : site.debug_info + "\n";
+          }
+          sites_[s] = std::move(site);
+          run_invalidation(s);
+          if (sites_[s].has_filter("AMBIG")) downpropagate_filter("AMBIG", s);
+          else uppropagate_filter("AMBIG", s);
+        }
+      } catch (const std::exception& e) {
+#pragma omp critical(gq_lg_error)
+        if (first_error.empty()) first_error = e.what();
+      }
     }
-    sites_[s] = std::move(site);
-    run_invalidation(s);
-    if (sites_[s].has_filter("AMBIG")) downpropagate_filter("AMBIG", s);
-    else uppropagate_filter("AMBIG", s);
   }
+  if (!first_error.empty()) throw std::runtime_error(first_error);
   if (opt.with_percentiles && S > 0) {
     Percentiler pc(gtconf_distribution(sites_, l_stats_, ploidy_, opt.gcp_seed));
     for (auto& s : sites_) s.gt_conf_percentile = pc.percentile(s.gt_conf);
@@ -1145,32 +1178,52 @@ std::string LevelGenotyper::vcf(const std::string& sample_id, SegmentTracker& tr
   o += meta_line("FORMAT", "FT", kDescFT, "1", "String", 0);
   o += meta_line("FILTER", "AMBIG", kDescAMBIG, "", "", 0);
   o += "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + sample_id + "\n";
+  o.reserve(o.size() + 96 * sites_.size());
   for (size_t i = 0; i < sites_.size(); ++i) {
     if (ps_.sites[i].parent >= 0) continue;  // next_valid_idx (:52-64)
     const Site& s = sites_[i];
-    const std::string chrom = tracker.get_id(s.pos);
-    const uint64_t pos = tracker.relative_pos(s.pos) + 1;
-    std::string alt;
-    for (size_t a = 1; a < s.alleles.size(); ++a) alt += (a > 1 ? "," : "") + s.alleles[a].seq;
-    if (s.alleles.size() < 2) alt = ".";
-    std::string gt;
-    if (s.is_null())
-      gt = ".";
+    o += tracker.get_id(s.pos);
+    o += '\t';
+    o += std::to_string(tracker.relative_pos(s.pos) + 1);
+    o += "\t.\t";
+    if (s.alleles.empty()) o += '.';
+    else o += s.alleles[0].seq;
+    o += '\t';
+    if (s.alleles.size() < 2) o += '.';
+    for (size_t a = 1; a < s.alleles.size(); ++a) {
+      if (a > 1) o += ',';
+      o += s.alleles[a].seq;
+    }
+    // FORMAT keys in the order they are set; COV is absent when the site never had coverages
+    o += s.allele_covs.empty() ? "\t.\t.\t.\tGT:DP:FT:GT_CONF:GT_CONF_PERCENTILE\t"
+                               : "\t.\t.\t.\tGT:DP:COV:FT:GT_CONF:GT_CONF_PERCENTILE\t";
+    if (s.is_null()) o += '.';
     else
-      for (size_t g = 0; g < s.genotype.size(); ++g) gt += (g ? "/" : "") + std::to_string(s.genotype[g]);
-    std::string keys = "GT:DP", vals = gt + ":" + std::to_string(s.total_coverage);
+      for (size_t g = 0; g < s.genotype.size(); ++g) {
+        if (g) o += '/';
+        o += std::to_string(s.genotype[g]);
+      }
+    o += ':';
+    o += std::to_string(s.total_coverage);
     if (!s.allele_covs.empty()) {
-      keys += ":COV";
-      vals += ":";
-      for (size_t c = 0; c < s.allele_covs.size(); ++c) vals += (c ? "," : "") + vcf_float(s.allele_covs[c]);
+      o += ':';
+      for (size_t c = 0; c < s.allele_covs.size(); ++c) {
+        if (c) o += ',';
+        o += vcf_float(s.allele_covs[c]);
+      }
     }
     // only the first string reaches bcf_update_format_string (n = 1); with several filters it carries its comma
-    keys += ":FT";
-    vals += ":" + (s.filters.empty() ? std::string("PASS") : s.filters[0] + (s.filters.size() > 1 ? "," : ""));
-    keys += ":GT_CONF:GT_CONF_PERCENTILE";
-    vals += ":" + vcf_float(s.gt_conf) + ":" + vcf_float(s.gt_conf_percentile);
-    o += chrom + "\t" + std::to_string(pos) + "\t.\t" + (s.alleles.empty() ? std::string(".") : s.alleles[0].seq) + "\t" +
-         alt + "\t.\t.\t.\t" + keys + "\t" + vals + "\n";
+    o += ':';
+    if (s.filters.empty()) o += "PASS";
+    else {
+      o += s.filters[0];
+      if (s.filters.size() > 1) o += ',';
+    }
+    o += ':';
+    o += vcf_float(s.gt_conf);
+    o += ':';
+    o += vcf_float(s.gt_conf_percentile);
+    o += '\n';
   }
   return o;
 }

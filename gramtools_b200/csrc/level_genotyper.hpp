@@ -240,6 +240,7 @@ struct RunOptions {
   bool with_percentiles = true;  // get_gcp
   bool debug = false;
   uint32_t gcp_seed = 42;        // GCP::Model's default seed (GCP.h:26)
+  int n_threads = 1;             // level-1 sites are independent: genotyped in parallel (0 = all the threads OpenMP gives)
 };
 
 // LevelGenotyper (runner.cpp:27-107)

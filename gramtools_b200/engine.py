@@ -81,9 +81,9 @@ def load_library():
         "gq_last_run_info": [vp, C.POINTER(C.c_double)],
         "gq_last_kernel_ms": [vp, C.POINTER(C.c_double)],
         "gq_level_genotype": [u32p, C.c_uint64, u16p, C.c_uint64, u32p, C.c_uint64, C.POINTER(C.c_double), C.c_int,
-                              C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint32],
+                              C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint32, C.c_int],
         "gq_level_genotype_json": [u32p, C.c_uint64, u16p, C.c_uint64, u32p, C.c_uint64, C.POINTER(C.c_double), C.c_int,
-                                   C.c_char_p, C.c_uint32, C.c_char_p, u64p],
+                                   C.c_char_p, C.c_uint32, C.c_int, C.c_char_p, u64p],
         "gq_read_depth_stats_host": [u32p, C.c_uint64, u16p, C.c_uint64, u32p, C.c_uint64, C.POINTER(C.c_double), u64p],
     }
     for name, args in sig.items():
@@ -437,23 +437,23 @@ def read_depth_stats_host(prg, per_base, grouped):
 
 
 def level_genotype_json(prg, per_base, grouped, mean_cov, var_cov, mean_pb_error, ploidy="haploid", sample_id="sample",
-                        gcp_seed=42):
+                        gcp_seed=42, n_threads=1):
     """LevelGenotyper + make_json_prg (runner.cpp:27-97, make_json.cpp:7-25): the text of genotyped.json."""
     lib = load_library()
     keep, args = _cov_args(prg, per_base, grouped)
     stats = (C.c_double * 3)(mean_cov, var_cov, mean_pb_error)
     pl = {"haploid": 1, "diploid": 2}[ploidy]
     n = np.zeros(1, dtype=np.uint64)
-    if lib.gq_level_genotype_json(*args, stats, pl, sample_id.encode(), gcp_seed, None, _ptr(n, C.c_uint64)) != 0:
+    if lib.gq_level_genotype_json(*args, stats, pl, sample_id.encode(), gcp_seed, n_threads, None, _ptr(n, C.c_uint64)) != 0:
         raise GqError(lib.gq_last_error().decode())
     buf = C.create_string_buffer(int(n[0]))
-    if lib.gq_level_genotype_json(*args, stats, pl, sample_id.encode(), gcp_seed, buf, _ptr(n, C.c_uint64)) != 0:
+    if lib.gq_level_genotype_json(*args, stats, pl, sample_id.encode(), gcp_seed, n_threads, buf, _ptr(n, C.c_uint64)) != 0:
         raise GqError(lib.gq_last_error().decode())
     return buf.value.decode()
 
 
 def level_genotype(prg, per_base, grouped, mean_cov, var_cov, mean_pb_error, genotype_dir, ploidy="haploid",
-                   sample_id="sample", prg_coords_path=None, debug_path=None, gcp_seed=42):
+                   sample_id="sample", prg_coords_path=None, debug_path=None, gcp_seed=42, n_threads=1):
     """The genotyping half of commands::genotype::run (genotype.cpp:68-118): writes genotyped.json,
     personalised_reference.fasta and genotyped.vcf.gz into `genotype_dir`."""
     lib = load_library()
@@ -462,6 +462,6 @@ def level_genotype(prg, per_base, grouped, mean_cov, var_cov, mean_pb_error, gen
     pl = {"haploid": 1, "diploid": 2}[ploidy]
     rc = lib.gq_level_genotype(*args, stats, pl, sample_id.encode(),
                                os.fsencode(prg_coords_path) if prg_coords_path else None, os.fsencode(genotype_dir),
-                               os.fsencode(debug_path) if debug_path else None, gcp_seed)
+                               os.fsencode(debug_path) if debug_path else None, gcp_seed, n_threads)
     if rc != 0:
         raise GqError(lib.gq_last_error().decode())

@@ -178,13 +178,14 @@ int gq_coverage_groups_import(gq_index* idx, const uint32_t* words, uint64_t n_w
  * stats = {mean coverage, coverage variance (gq_read_depth_stats), mean per-base error rate (ReadStats,
  * read_stats.cpp:21-70)}; ploidy 1 or 2; prg_coords_path: gram_dir/prg_coords.tsv (NULL or missing: one segment
  * named gramtools_prg); debug_path: NULL, or the file the per-site debug lines are appended to (--debug);
- * gcp_seed: seed of the genotype-confidence simulation (GCP::Model's default is 42, lib/GCP/GCP.h:26).
+ * gcp_seed: seed of the genotype-confidence simulation (GCP::Model's default is 42, lib/GCP/GCP.h:26); n_threads: host
+ * threads (level-1 sites are independent and are genotyped in parallel; 0 = all; the result does not depend on it).
  * Doubles follow the reference's arithmetic operation for operation; the VCF text is what htslib would print, restated
  * (htslib is absent here: parity unpinned, like the sdsl files). */
 int gq_level_genotype(const uint32_t* prg, uint64_t n_symbols, const uint16_t* per_base, uint64_t n_per_base,
                       const uint32_t* grouped, uint64_t n_grouped_words, const double stats[3], int ploidy,
                       const char* sample_id, const char* prg_coords_path, const char* genotype_dir,
-                      const char* debug_path, uint32_t gcp_seed);
+                      const char* debug_path, uint32_t gcp_seed, int n_threads);
 /* gq_read_depth_stats without a handle: the same arithmetic from the PRG and fetched coverage (host code). */
 int gq_read_depth_stats_host(const uint32_t* prg, uint64_t n_symbols, const uint16_t* per_base, uint64_t n_per_base,
                              const uint32_t* grouped, uint64_t n_grouped_words, double out[2], uint64_t counts[2]);
@@ -192,7 +193,8 @@ int gq_read_depth_stats_host(const uint32_t* prg, uint64_t n_symbols, const uint
  * *json_bytes is the capacity on entry and the size (with the terminating 0) on return. */
 int gq_level_genotype_json(const uint32_t* prg, uint64_t n_symbols, const uint16_t* per_base, uint64_t n_per_base,
                            const uint32_t* grouped, uint64_t n_grouped_words, const double stats[3], int ploidy,
-                           const char* sample_id, uint32_t gcp_seed, char* json_out, uint64_t* json_bytes);
+                           const char* sample_id, uint32_t gcp_seed, int n_threads, char* json_out,
+                           uint64_t* json_bytes);
 
 /* Run the kernels on a caller-owned CUDA stream (e.g. torch's current stream) so that the caller's
  * CUDA events bracket them. NULL = the library's own stream. */

@@ -36,12 +36,12 @@ int main(void) {
     char* json;
     if (gq_read_depth_stats_host(prg, 8, per_base, 2, grouped, 8, depth, counts) != 0) return 8;
     if (depth[0] != 9.0 || counts[0] != 0 || counts[1] != 1) return 9;
-    if (gq_level_genotype_json(prg, 8, per_base, 2, grouped, 8, stats, 1, "c", 42, NULL, &bytes) != 0 || bytes < 100) return 10;
+    if (gq_level_genotype_json(prg, 8, per_base, 2, grouped, 8, stats, 1, "c", 42, 1, NULL, &bytes) != 0 || bytes < 100) return 10;
     json = (char*)malloc(bytes);
-    if (gq_level_genotype_json(prg, 8, per_base, 2, grouped, 8, stats, 1, "c", 42, json, &bytes) != 0) return 11;
+    if (gq_level_genotype_json(prg, 8, per_base, 2, grouped, 8, stats, 1, "c", 42, 2, json, &bytes) != 0) return 11;
     if (strstr(json, "\"ALS\":[\"G\",\"T\"]") == NULL || strstr(json, "\"GT\":[[1]]") == NULL) return 12;
     free(json);
-    if (gq_level_genotype_json(prg, 6, per_base, 2, grouped, 8, stats, 1, "c", 42, NULL, &bytes) == 0) return 13; /* a site with one allele */
+    if (gq_level_genotype_json(prg, 6, per_base, 2, grouped, 8, stats, 1, "c", 42, 1, NULL, &bytes) == 0) return 13; /* a site with one allele */
   }
   free(packed);
   printf("c client ok (%d CUDA devices)\n", n_dev);

@@ -21,7 +21,7 @@ from gramtools_b200 import encode_reads, level_genotype, level_genotype_json, re
 def test_reference_unit_expectations(built_lib):
     out = os.path.join(ROOT, "tests", "_build", "test_level_genotyper")
     os.makedirs(os.path.dirname(out), exist_ok=True)
-    subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-Wall", "-o", out,
+    subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-Wall", "-fopenmp", "-o", out,
                     os.path.join(ROOT, "tests", "genotyper", "test_level_genotyper.cpp"),
                     os.path.join(ROOT, "gramtools_b200", "csrc", "level_genotyper.cpp"), "-lz"], check=True)
     r = subprocess.run([out], capture_output=True, text=True)
@@ -219,6 +219,28 @@ def test_depth_statistics_follow_the_most_covered_path(built_lib):
     # site 0: path TC G TC with 7 reads on every base -> 7; site 3: direct deletion with 3 reads -> 3
     assert d["num_sites_total"] == 2 and d["num_sites_noCov"] == 0
     assert d["mean"] == 5.0 and d["variance"] == 4.0
+
+
+def test_result_does_not_depend_on_threads(built_lib, tmp_path):
+    """Level-1 sites (with what is nested in them) are genotyped in parallel: same files for any thread count."""
+    from gramtools_b200 import master_seeds, synth
+    for prg, k, seed in ((synth.make_snp_prg(6000, 400, 2)[0], 6, 2), (synth.make_nested_prg(90, 120, 4), 5, 4)):
+        rng = np.random.default_rng(seed)
+        haps = [synth.random_haplotype(prg, rng) for _ in range(2)]
+        b, o = synth.sample_reads(haps, 8000, 50, seed + 1)
+        orc = Oracle(prg, k)
+        orc.map(b, o, master_seeds(seed, 8000), threads=4, want_states=False)
+        res = orc.result(want_states=False)
+        depth = read_depth_stats_host(prg, res.per_base, res.grouped)
+        files = []
+        for nt in (1, 4, 0):
+            out = tmp_path / f"g{seed}_{nt}"
+            out.mkdir()
+            level_genotype(prg, res.per_base, res.grouped, depth["mean"], depth["variance"], 1e-3, str(out),
+                           ploidy="diploid", n_threads=nt)
+            files.append([(out / f).read_bytes() for f in ("genotyped.json", "personalised_reference.fasta", "genotyped.vcf.gz")])
+        assert files[0] == files[1] == files[2]
+        assert len(json.loads(files[0][0])["Sites"]) >= 90
 
 
 def test_bad_input_is_refused(built_lib):
