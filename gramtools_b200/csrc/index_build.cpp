@@ -562,8 +562,9 @@ struct StateList {
 
 // All successors of `in` after consuming each of the four bases (marker processing first unless `first`): the marker
 // processing of a state does not depend on the base consumed next, so it runs once (run_stack_ready) and every
-// resulting state is extended by A, C, G and T with one pair of rank-block loads. out[c] keeps, per base, the order in
-// which the reference's breadth-first pass would have produced the states (build.cpp:55-131).
+// resulting state is extended by A, C, G and T with one pair of rank-block loads. out[c] holds, per base, the same
+// states as the reference's pass (build.cpp:55-131), each input state followed by the ones its markers give (the
+// reference lists the marker-derived states after ALL the extended ones; quasimap never reads the order).
 struct ReadyCollect {
   const IndexView* v;
   StateList* out;  // [4]
