@@ -769,64 +769,72 @@ LevelGenotyper::LevelGenotyper(PrgSites ps, const Cov* per_base, const uint32_t*
 
 // ------------------------------------------------------------------------------------------------ read depth
 
-DepthStats read_depth_stats(const PrgSites& ps, const Cov* per_base, const std::vector<GroupCounts>& counts) {
-  // ReadStats::compute_coverage_depth (read_stats.cpp:72-160): per level-1 site the mean per-base coverage along the
-  // most covered haplogroup (of the site and of every site met on the way), or that haplogroup's count when the path
-  // holds no base; sites taken in ascending order, as gq_read_depth_stats does
-  auto max_hapg = [&](uint32_t s) {  // get_max_cov_haplogroup (:72-93): 16-bit sums, first maximum in id order
-    std::map<int32_t, Cov> per;
-    for (auto& e : counts.at(s))
-      for (int32_t id : e.first) per[id] = (Cov)(per[id] + e.second);
-    std::pair<int32_t, Cov> best{0, 0};
-    bool first = true;
-    for (auto& kv : per)
-      if (first || kv.second > best.second) best = kv, first = false;
-    return best;
+std::pair<int32_t, Cov> max_cov_haplogroup(const GroupCounts& counts) {
+  // get_max_cov_haplogroup (read_stats.cpp:72-93): 16-bit sums per allele id, the first maximum in id order
+  std::map<int32_t, Cov> per;
+  for (auto& e : counts)
+    for (int32_t id : e.first) per[id] = (Cov)(per[id] + e.second);
+  std::pair<int32_t, Cov> best{0, 0};
+  bool first = true;
+  for (auto& kv : per)
+    if (first || kv.second > best.second) best = kv, first = false;
+  return best;
+}
+
+std::pair<Allele, Cov> extract_max_coverage_allele(const PrgSites& ps, uint32_t s, const Cov* per_base,
+                                                   const std::vector<GroupCounts>& counts) {
+  // extract_max_coverage_allele (read_stats.cpp:95-117): through site s along its most covered haplogroup, and
+  // along the most covered haplogroup of every site met on the way; the count returned is that of site s
+  const auto top = max_cov_haplogroup(counts.at(s));
+  Allele path;
+  struct Open {  // a site open on the chosen path: the allele wanted of it, the allele the scan is in
+    uint32_t site;
+    int32_t want, cur;
   };
+  std::vector<Open> open{{s, top.first, 0}};
+  if (top.first >= (int32_t)ps.sites[s].n_alleles) throw std::runtime_error("inconsistent grouped allele counts");
+  uint32_t pb = ps.sites[s].pb_entry;
+  for (uint32_t p = ps.sites[s].entry + 1; !open.empty(); ++p) {
+    const uint32_t m = ps.prg[p];
+    Open& o = open.back();
+    if (m <= 4) {
+      if (o.cur == o.want) {
+        path.seq.push_back(base_char(m));
+        path.pb.push_back(per_base[pb]);
+      }
+      ++pb;
+    } else if (m & 1u) {
+      const uint32_t t = (m - 5) / 2;
+      if (o.cur == o.want) {
+        const int32_t want = max_cov_haplogroup(counts.at(t)).first;
+        if (want >= (int32_t)ps.sites[t].n_alleles) throw std::runtime_error("inconsistent grouped allele counts");
+        open.push_back({t, want, 0});
+      } else {  // a site on an allele that is not walked
+        p = ps.sites[t].end;
+        pb = ps.sites[t].pb_exit;
+      }
+    } else if (p == ps.sites[o.site].end)
+      open.pop_back();
+    else
+      ++o.cur;
+  }
+  return {path, top.second};
+}
+
+DepthStats read_depth_stats(const PrgSites& ps, const Cov* per_base, const std::vector<GroupCounts>& counts) {
+  // ReadStats::compute_coverage_depth (read_stats.cpp:119-160): per level-1 site the mean per-base coverage of that
+  // path, or the haplogroup's count when the path holds no base (direct deletion); then mean and (population)
+  // variance over the sites, taken in ascending order as gq_read_depth_stats does
   DepthStats out;
   std::vector<double> covs;
   double total = 0;
   for (uint32_t s = 0; s < ps.sites.size(); ++s) {
     if (ps.sites[s].parent >= 0) continue;
-    const Cov top_cov = max_hapg(s).second;
-    double sum = 0;
-    uint64_t n_bases = 0;
-    // (site, wanted allele, current allele) of the sites open on the chosen path
-    struct Open {
-      uint32_t site;
-      int32_t want, cur;
-    };
-    std::vector<Open> open{{s, max_hapg(s).first, 0}};
-    if (open.back().want >= (int32_t)ps.sites[s].n_alleles) throw std::runtime_error("inconsistent grouped allele counts");
-    uint32_t pb = ps.sites[s].pb_entry;
-    for (uint32_t p = ps.sites[s].entry + 1; !open.empty(); ++p) {
-      const uint32_t m = ps.prg[p];
-      Open& o = open.back();
-      if (m <= 4) {
-        if (o.cur == o.want) {
-          sum += per_base[pb];
-          ++n_bases;
-        }
-        ++pb;
-      } else if (m & 1u) {
-        const uint32_t t = (m - 5) / 2;
-        if (o.cur == o.want) {
-          const int32_t want = max_hapg(t).first;
-          if (want >= (int32_t)ps.sites[t].n_alleles) throw std::runtime_error("inconsistent grouped allele counts");
-          open.push_back({t, want, 0});
-        } else {  // a site on an allele that is not walked
-          p = ps.sites[t].end;
-          pb = ps.sites[t].pb_exit;
-        }
-      } else if (p == ps.sites[o.site].end)
-        open.pop_back();
-      else
-        ++o.cur;
-    }
-    const double site_cov = n_bases ? sum / (double)n_bases : (double)top_cov;
+    const auto extraction = extract_max_coverage_allele(ps, s, per_base, counts);
+    const double site_cov = extraction.first.pb.empty() ? (double)extraction.second : extraction.first.mean_cov();
     total += site_cov;
     covs.push_back(site_cov);
-    if (top_cov == 0) ++out.num_sites_no_cov;
+    if (extraction.second == 0) ++out.num_sites_no_cov;
   }
   out.num_sites_total = covs.size();
   out.mean = total / (double)covs.size();

@@ -207,6 +207,9 @@ struct DepthStats {
   uint64_t num_sites_no_cov = 0, num_sites_total = 0;
 };
 DepthStats read_depth_stats(const PrgSites& ps, const Cov* per_base, const std::vector<GroupCounts>& counts);
+std::pair<int32_t, Cov> max_cov_haplogroup(const GroupCounts& counts);  // read_stats.cpp:72-93
+std::pair<Allele, Cov> extract_max_coverage_allele(const PrgSites& ps, uint32_t site, const Cov* per_base,
+                                                   const std::vector<GroupCounts>& counts);  // read_stats.cpp:95-117
 
 // segment_tracker.hpp
 class SegmentTracker {

@@ -138,6 +138,25 @@ int gqo_map(void* hv, const uint8_t* bases, const uint64_t* off, uint64_t n_read
     return -1;
   }
 }
+// quasimap_read on the reads as given, no reverse complement: what the reference's test helper prg_setup::quasimap_reads
+// does (tests/test_resources/test_resources.cpp:48-56); coverage accumulates in the handle. Used by the tests that
+// transcribe reference cases built on that helper (read statistics, genotyping).
+int gqo_map_forward(void* hv, const uint8_t* bases, const uint64_t* off, uint64_t n_reads, const uint32_t* seeds) {
+  auto* h = (OracleHandle*)hv;
+  try {
+    h->status.assign(2 * n_reads, 0);
+    h->states.assign(0, {});
+    h->state_count.assign(2 * n_reads, 0);
+    for (uint64_t i = 0; i < n_reads; ++i) {
+      Sequence read(bases + off[i], bases + off[i + 1]);
+      h->status[2 * i] = (uint8_t)h->m.quasimap_read(read, seeds[i], false, nullptr);
+    }
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
 double gqo_last_seconds(void* hv) { return ((OracleHandle*)hv)->last_seconds; }
 
 void gqo_status(void* hv, uint8_t* out) {

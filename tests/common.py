@@ -42,6 +42,7 @@ def oracle_lib():
         lib.gqo_kmer_states.argtypes = [C.c_void_p, u32p]
         lib.gqo_kmer_states.restype = C.c_uint64
         lib.gqo_map.argtypes = [C.c_void_p, u8p, u64p, C.c_uint64, u32p, C.c_int, C.c_int, C.c_int]
+        lib.gqo_map_forward.argtypes = [C.c_void_p, u8p, u64p, C.c_uint64, u32p]
         lib.gqo_last_seconds.argtypes = [C.c_void_p]
         lib.gqo_last_seconds.restype = C.c_double
         lib.gqo_status.argtypes = [C.c_void_p, u8p]
@@ -177,6 +178,16 @@ class Oracle:
             raise RuntimeError(self.lib.gqo_last_error().decode())
         self.n_reads = n
         return self.lib.gqo_last_seconds(self.h)
+
+    def map_forward(self, bases, offsets, seeds):
+        """quasimap_read on the forward strand only (the reference's test helper, test_resources.cpp:48-56)."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+        n = offsets.size - 1
+        if self.lib.gqo_map_forward(self.h, _ptr(bases, C.c_uint8), _ptr(offsets, C.c_uint64), n, _ptr(seeds, C.c_uint32)) != 0:
+            raise RuntimeError(self.lib.gqo_last_error().decode())
+        self.n_reads = n
 
     def result(self, want_states=True):
         n = self.n_reads

@@ -399,6 +399,35 @@ static void test_site_interface() {
   CHECK(called.allele_covs.size() == 2 && called.haplogroups.size() == 1);
 }
 
+static void test_read_depth() {
+  CASE("MaxHaplogroupCoverage (test_read_stats.cpp:50-62)");
+  CHECK((max_cov_haplogroup({}) == std::pair<int32_t, Cov>{0, 0}));
+  CHECK((max_cov_haplogroup({{{0, 1}, 2}, {{0}, 3}, {{1}, 4}}) == std::pair<int32_t, Cov>{1, 6}));
+  CHECK((max_cov_haplogroup({{{0}, 4}, {{1}, 4}}) == std::pair<int32_t, Cov>{0, 4}));  // a tie: the lower id
+  CASE("TestReadMappingStats.ExtractMaxCovAllele* (test_read_stats.cpp:64-115)");
+  {
+    PrgSites ps = parsed("[AC[T,G]AC,GT[A,T]T]A[AA,C]T");
+    std::vector<GroupCounts> counts{{{{1}, 60}}, {{{1}, 2}, {{0}, 1}}, {{{0}, 19}, {{0, 1}, 1}}, {}};
+    std::vector<Cov> cov(32, 0);
+    auto e = extract_max_coverage_allele(ps, 1, cov.data(), counts);
+    CHECK(e.first.seq == "G" && e.second == 2);
+    e = extract_max_coverage_allele(ps, 2, cov.data(), counts);
+    CHECK(e.first.seq == "A" && e.second == 20);
+    e = extract_max_coverage_allele(ps, 3, cov.data(), counts);
+    CHECK(e.first.seq == "AA" && e.second == 0);
+    e = extract_max_coverage_allele(ps, 0, cov.data(), counts);
+    CHECK(e.first.seq == "GTAT" && e.second == 60);
+  }
+  CASE("TestMeanAndVarCovComputation (test_read_stats.cpp:117-134): sites with coverage 15 and a deletion with 5 reads");
+  {
+    PrgSites ps = parsed("A[AT,T]C[T,]");
+    std::vector<Cov> cov{10, 20, 0, 0};
+    std::vector<GroupCounts> counts{{{{0}, 20}}, {{{1}, 5}}};
+    DepthStats d = read_depth_stats(ps, cov.data(), counts);
+    CHECK(d.mean == 10 && d.variance == 25 && d.num_sites_total == 2 && d.num_sites_no_cov == 0);
+  }
+}
+
 static void test_runner_logic() {
   CASE("LevelGenotyperInvalidation (test_runner.cpp:173-192)");
   {
@@ -548,6 +577,7 @@ int main() {
   test_model_calls();
   test_allele_extraction();
   test_site_interface();
+  test_read_depth();
   test_runner_logic();
   test_segments_and_outputs();
   std::printf("%d checks, %d failed\n", g_checks, g_failed);
