@@ -42,6 +42,8 @@ gq::lg::LevelGenotyper run(const uint32_t* prg, uint64_t n_symbols, const uint16
     throw std::runtime_error("per-base vector has " + std::to_string(n_per_base) + " entries, the PRG has " +
                              std::to_string(in_site) + " bases inside sites");
   if (n_per_base && !per_base) throw std::runtime_error("null argument");
+  if (!ps.sites.empty() && (!(stats[0] >= 0) || !(stats[1] >= 0) || !(stats[2] >= 0 && stats[2] <= 1)))
+    throw std::runtime_error("stats must be {mean coverage >= 0, coverage variance >= 0, error rate in [0, 1]}");
   gq::lg::RunOptions opt;
   opt.ploidy = ploidy == 1 ? gq::lg::Ploidy::Haploid : gq::lg::Ploidy::Diploid;
   opt.gcp_seed = gcp_seed;

@@ -670,10 +670,23 @@ std::vector<double> LevelGenotyper::gtconf_distribution(const std::vector<Site>&
     std::vector<double> simulated;
     simulated.reserve(kSize - at);
     for (size_t i = at; i < kSize; ++i) {
+      // the reference draws 16-bit counts (std::…_distribution<CovCount>); libstdc++'s Poisson rejection loop never
+      // ends once its mean passes the type's maximum, which a gamma-mixed draw reaches when the depth is in the
+      // thousands. Beyond 1000x (no sequencing run; reachable through the C ABI) the draw is made 32 bits wide and
+      // clamped, so the call always returns; below, the reference's own distributions are used as they are.
+      const bool wide = !(ls.mean_cov <= 1000.0);
       Cov correct;
       if (ls.pmf_full_depth->is_poisson()) {
-        std::poisson_distribution<Cov> d(ls.mean_cov);
-        correct = d(gen);
+        if (wide) {
+          std::poisson_distribution<uint32_t> d(std::min(ls.mean_cov, 1e9));
+          correct = (Cov)std::min<uint32_t>(d(gen), 65535u);
+        } else {
+          std::poisson_distribution<Cov> d(ls.mean_cov);
+          correct = d(gen);
+        }
+      } else if (wide) {
+        std::negative_binomial_distribution<uint32_t> d((uint32_t)(Cov)ls.num_successes, ls.success_prob);
+        correct = (Cov)std::min<uint32_t>(d(gen), 65535u);
       } else {
         std::negative_binomial_distribution<Cov> d(ls.num_successes, ls.success_prob);
         correct = d(gen);
@@ -736,9 +749,10 @@ LevelGenotyper::LevelGenotyper(PrgSites ps, const Cov* per_base, const uint32_t*
     LStats local = n_threads > 1 ? make_l_stats(mean_cov, var_cov, mean_pb_error) : l_stats_;
 #pragma omp for schedule(dynamic, 64)
     for (int64_t u = 0; u < (int64_t)unit_end.size(); ++u) {
+      uint32_t at = 0;
       try {
         for (uint32_t i = u ? unit_end[(size_t)u - 1] : 0; i < unit_end[(size_t)u]; ++i) {
-          const uint32_t s = order[i];
+          const uint32_t s = at = order[i];
           Alleles alleles = extract_alleles(ps_, s, pb, sites_);
           SiteModel model(alleles, counts[s], ploidy_, &local, opt.debug);
           Site site = model.site();
@@ -756,7 +770,7 @@ LevelGenotyper::LevelGenotyper(PrgSites ps, const Cov* per_base, const uint32_t*
         }
       } catch (const std::exception& e) {
 #pragma omp critical(gq_lg_error)
-        if (first_error.empty()) first_error = e.what();
+        if (first_error.empty()) first_error = "site " + std::to_string(at) + ": " + e.what();
       }
     }
   }

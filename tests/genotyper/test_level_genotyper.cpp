@@ -475,6 +475,15 @@ static void test_runner_logic() {
     conf = LevelGenotyper::gtconf_distribution(sites, lnb, Ploidy::Diploid, 42);
     CHECK(conf.size() == 10000 && conf.back() > 0);
   }
+  CASE("confidence simulation at a depth where 16-bit Poisson draws of libstdc++ would never be accepted");
+  {
+    LStats deep = make_l_stats(29733.4, 112328443.1, 0.2);
+    auto conf = LevelGenotyper::gtconf_distribution(std::vector<Site>(27), deep, Ploidy::Haploid, 42);
+    CHECK(conf.size() == 10000);
+    LStats deep_pois = make_l_stats(50000, 10, 0.01);
+    conf = LevelGenotyper::gtconf_distribution(std::vector<Site>(3), deep_pois, Ploidy::Diploid, 42);
+    CHECK(conf.size() == 10000);
+  }
   CASE("Percentiler (lib/GCP/GCP.h:104-183)");
   {
     Percentiler p({1, 2, 2, 2, 3, 4, 5, 6, 7, 10});
