@@ -563,11 +563,13 @@ struct StateList {
 // All successors of `in` after consuming each of the four bases (marker processing first unless `first`): the marker
 // processing of a state does not depend on the base consumed next, so it runs once (run_stack_ready) and every
 // resulting state is extended by A, C, G and T with one pair of rank-block loads. out[c] holds, per base, the same
-// states as the reference's pass (build.cpp:55-131), each input state followed by the ones its markers give (the
-// reference lists the marker-derived states after ALL the extended ones; quasimap never reads the order).
+// states as the reference's pass (build.cpp:55-131) and, when no jumps are chained, in its order: the extended input
+// states, then the marker-derived ones (tests/test_host_parity.py::test_kmer_index_holds_the_oracles_states).
 struct ReadyCollect {
   const IndexView* v;
-  StateList* out;  // [4]
+  StateList* out;      // [4]: extensions of the input state itself
+  StateList* derived;  // [4]: extensions of the states its markers give
+  uint32_t in_lo, in_hi, in_counts;
   void operator()(const uint32_t* t, uint32_t lo, uint32_t hi) {
     const uint32_t b0 = lo >> kBlkShift, b1 = (hi + 1) >> kBlkShift;
     const RankBlk B0 = load_blk(v->rank_blk + b0);
@@ -575,10 +577,12 @@ struct ReadyCollect {
     const uint32_t* s0 = v->super_cnt + 4 * (b0 >> (kSuperShift - kBlkShift));
     const uint32_t* s1 = v->super_cnt + 4 * (b1 >> (kSuperShift - kBlkShift));
     const uint32_t w = entry_words(t[3]);
+    // every jump lengthens the path, so the input state is the one record that still has its interval and counts
+    StateList* dst = (lo == in_lo && hi == in_hi && t[3] == in_counts) ? out : derived;
     for (uint32_t c = 0; c < 4; ++c) {
       const uint32_t r0 = rank_in_blk(B0, s0, c, lo), r1 = rank_in_blk(B1, s1, c, hi + 1);
       if (r1 <= r0) continue;
-      StateList& o = out[c];
+      StateList& o = dst[c];
       o.recs.push_back(HRec{r0, r1 - 1, t[3], (uint32_t)o.pool.size()});  // C[c] is folded into the superblock counters
       o.pool.insert(o.pool.end(), t + kHdr, t + w);
     }
@@ -587,6 +591,10 @@ struct ReadyCollect {
 
 void step_states4(const IndexView& v, const StateList& in, bool first, std::vector<uint32_t>& arena,
                   StateList* out /* [4] */) {
+  // the reference appends the marker-derived states of ALL input states after the input states themselves
+  // (process_markers_search_states splices them at the end, vBWT_jump.cpp:119-132) and then extends the list in
+  // order: per base, out[c] = extensions of the inputs, then extensions of the derived states
+  StateList derived[4];
   for (uint32_t c = 0; c < 4; ++c) out[c].clear();
   for (const HRec& st : in.recs) {
     const uint32_t pw = entry_words(st.counts) - kHdr;
@@ -603,14 +611,28 @@ void step_states4(const IndexView& v, const StateList& in, bool first, std::vect
       t[3] = st.counts;
       t[4] = kNoAllele;
       std::copy(in.pool.begin() + st.path_off, in.pool.begin() + st.path_off + pw, t + kHdr);
-      size_t mark[4], pmark[4];
-      for (uint32_t c = 0; c < 4; ++c) mark[c] = out[c].recs.size(), pmark[c] = out[c].pool.size();
-      ReadyCollect col{&v, out};
+      size_t mark[8], pmark[8];
+      for (uint32_t c = 0; c < 4; ++c) {
+        mark[c] = out[c].recs.size(), pmark[c] = out[c].pool.size();
+        mark[4 + c] = derived[c].recs.size(), pmark[4 + c] = derived[c].pool.size();
+      }
+      ReadyCollect col{&v, out, derived, st.lo, st.hi, st.counts};
       run_stack_ready(s, v, col);
       if (!s.overflow) break;
-      for (uint32_t c = 0; c < 4; ++c) out[c].recs.resize(mark[c]), out[c].pool.resize(pmark[c]);
+      for (uint32_t c = 0; c < 4; ++c) {
+        out[c].recs.resize(mark[c]), out[c].pool.resize(pmark[c]);
+        derived[c].recs.resize(mark[4 + c]), derived[c].pool.resize(pmark[4 + c]);
+      }
       arena.resize(arena.size() * 2);
     }
+  }
+  for (uint32_t c = 0; c < 4; ++c) {
+    const uint32_t shift = (uint32_t)out[c].pool.size();
+    for (HRec h : derived[c].recs) {
+      h.path_off += shift;
+      out[c].recs.push_back(h);
+    }
+    out[c].pool.insert(out[c].pool.end(), derived[c].pool.begin(), derived[c].pool.end());
   }
 }
 
