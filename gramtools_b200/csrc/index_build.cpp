@@ -563,8 +563,8 @@ struct StateList {
 // All successors of `in` after consuming each of the four bases (marker processing first unless `first`): the marker
 // processing of a state does not depend on the base consumed next, so it runs once (run_stack_ready) and every
 // resulting state is extended by A, C, G and T with one pair of rank-block loads. out[c] holds, per base, the same
-// states as the reference's pass (build.cpp:55-131) and, when no jumps are chained, in its order: the extended input
-// states, then the marker-derived ones (tests/test_host_parity.py::test_kmer_index_holds_the_oracles_states).
+// states as the reference's pass (build.cpp:55-131), in its order: the extended input states, then the marker-derived
+// ones as its worklist commits them (tests/test_host_parity.py::test_kmer_index_holds_the_oracles_states).
 struct ReadyCollect {
   const IndexView* v;
   StateList* out;      // [4]: extensions of the input state itself
@@ -578,16 +578,67 @@ struct ReadyCollect {
     const uint32_t* s1 = v->super_cnt + 4 * (b1 >> (kSuperShift - kBlkShift));
     const uint32_t w = entry_words(t[3]);
     // every jump lengthens the path, so the input state is the one record that still has its interval and counts
-    StateList* dst = (lo == in_lo && hi == in_hi && t[3] == in_counts) ? out : derived;
+    const bool is_input = lo == in_lo && hi == in_hi && t[3] == in_counts;
+    StateList* dst = is_input ? out : derived;
     for (uint32_t c = 0; c < 4; ++c) {
       const uint32_t r0 = rank_in_blk(B0, s0, c, lo), r1 = rank_in_blk(B1, s1, c, hi + 1);
       if (r1 <= r0) continue;
       StateList& o = dst[c];
-      o.recs.push_back(HRec{r0, r1 - 1, t[3], (uint32_t)o.pool.size()});  // C[c] is folded into the superblock counters
+      const HRec rec{r0, r1 - 1, t[3], (uint32_t)o.pool.size()};  // C[c] is folded into the superblock counters
+      // a state is emitted after the states chained to it (they sit above it on the stack); the reference commits
+      // it before them: `before` = where its chain began in this list
+      if (!is_input && before && before[c] < o.recs.size()) o.recs.insert(o.recs.begin() + before[c], rec);
+      else o.recs.push_back(rec);
       o.pool.insert(o.pool.end(), t + kHdr, t + w);
     }
   }
+  const size_t* before = nullptr;  // set by run_stack_in_reference_order around a call
 };
+
+// run_stack_ready (gq_core.cuh) with the reference's commit order: search_state_vBWT_jumps commits an entered / exited
+// state when it is made, BEFORE the loci chained to it are processed (vBWT_jump.cpp:155-183); the stack machine emits
+// it when it comes back to the top, after them. The list positions at which an entry's processing began are kept per
+// stack offset, and the entry's record is inserted there.
+void run_stack_in_reference_order(Stack& s, const IndexView& v, ReadyCollect& col) {
+  struct Open {
+    uint32_t offset;
+    size_t at[4];
+  };
+  std::vector<Open> open;
+  while (!stack_empty(s) && !s.overflow) {
+    uint32_t* t = s.mem + s.top;
+    const uint32_t w0 = t[0], kind = w0 >> 28, pos = w0 & 0x0FFFFFFFu;
+    if (kind == K_JUMP) {
+      bool known = false;
+      for (auto& o : open) known |= o.offset == s.top;
+      if (!known) {
+        Open o{s.top, {0, 0, 0, 0}};
+        for (uint32_t c = 0; c < 4; ++c) o.at[c] = col.derived[c].recs.size();
+        open.push_back(o);
+      }
+      process_jump(s, v);
+      continue;
+    }
+    const uint32_t lo = t[1], hi = t[2];
+    if (kind == K_SCAN && interval_has_marker(v, lo, hi)) {
+      t[0] = pos | (K_READY << 28);
+      scan_markers(s, v, pos, lo, hi);
+      continue;
+    }
+    col.before = nullptr;
+    for (size_t i = 0; i < open.size(); ++i)
+      if (open[i].offset == s.top) {
+        col.before = open[i].at;
+        col(t, lo, hi);
+        open.erase(open.begin() + (long)i);
+        col.before = nullptr;
+        t = nullptr;
+        break;
+      }
+    if (t) col(t, lo, hi);
+    pop(s);
+  }
+}
 
 void step_states4(const IndexView& v, const StateList& in, bool first, std::vector<uint32_t>& arena,
                   StateList* out /* [4] */) {
@@ -617,7 +668,7 @@ void step_states4(const IndexView& v, const StateList& in, bool first, std::vect
         mark[4 + c] = derived[c].recs.size(), pmark[4 + c] = derived[c].pool.size();
       }
       ReadyCollect col{&v, out, derived, st.lo, st.hi, st.counts};
-      run_stack_ready(s, v, col);
+      run_stack_in_reference_order(s, v, col);
       if (!s.overflow) break;
       for (uint32_t c = 0; c < 4; ++c) {
         out[c].recs.resize(mark[c]), out[c].pool.resize(pmark[c]);
