@@ -316,7 +316,8 @@ def test_kmer_index_holds_the_oracles_states():
     cases += [(synth.make_nested_prg(6, 250, 20 + sd), 3 + sd % 3) for sd in range(6)]
     cases += [(np.asarray(c["prg"], dtype=np.uint32), c["kmer_size"]) for c in
               json.load(open(os.path.join(ROOT, "tests", "golden", "it_fixtures.json"))).values()]
-    for prg, k in cases:
+    cases += [(prg, k) for _, prg, k, _, _ in reference_test_cases()]  # test_quasimap.cpp: adjacent sites, direct
+    for prg, k in cases:                                                # deletions, doubly nested sites, empty alleles
         want, got = records(Oracle(prg, k).kmer_states()), records(Emu(prg, k).kmer_states())
         assert len(want) > 0 and want == got
 
