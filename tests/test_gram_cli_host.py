@@ -78,3 +78,39 @@ def test_small_batches_and_threads(built_lib, tmp_path, preloaded, monkeypatch):
                       ("genotype", "genotyped.json"), ("genotype", "personalised_reference.fasta"))})
         outs[-1]["counts"] = [ln for ln in r.stdout.splitlines() if ln.startswith("Count ")]
     assert outs[0] == outs[1]
+
+
+def test_argv_of_the_python_front_end(built_lib, tmp_path, preloaded):
+    """The exact command lines gramtools' Python front-end builds (commands/build/build.py:65-80,
+    commands/genotype/genotype.py:71-93), --debug included: build leaves the k-mer index files, genotype the whole
+    geno_dir layout (paths.py:131-152) that genotype.py reads next."""
+    import numpy as np
+    from gramtools_b200 import synth
+    gd, od = tmp_path / "gram", tmp_path / "geno"
+    gd.mkdir()
+    prg = synth.make_snp_prg(2000, 60, 3)[0]
+    cli._write_prg(gd / "prg", prg)
+    (gd / "prg_coords.tsv").write_text("ref1\t2000\n")
+    rng = np.random.default_rng(3)
+    hap = synth.random_haplotype(prg, rng)
+    reads = ["".join("?ACGT"[x] for x in hap[s0:s0 + 70]) for s0 in rng.integers(0, hap.size - 70, 600)]
+    cli._fastq(tmp_path / "r.fq", reads)
+    out = subprocess.run([cli.GRAM, "build", "--gram_dir", str(gd), "--ref", str(tmp_path / "ref.fa"), "--kmer_size", "5",
+                          "--max_threads", "2", "--all_kmers", "--debug"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert all((gd / f).stat().st_size > 8 for f in ("kmers", "kmers_stats", "sa_intervals", "paths"))
+    out = subprocess.run([cli.GRAM, "genotype", "--gram_dir", str(gd), "--reads", str(tmp_path / "r.fq"), "--sample_id",
+                          "sample one", "--ploidy", "diploid", "--kmer_size", "5", "--genotype_dir", str(od),
+                          "--max_threads", "2", "--seed", "42", "--debug"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    for f in ("read_stats.json", "site_gtyping_debug_info.txt", "coverage/allele_sum_coverage",
+              "coverage/allele_base_coverage.json", "coverage/grouped_allele_counts_coverage.json",
+              "genotype/genotyped.json", "genotype/genotyped.vcf.gz", "genotype/personalised_reference.fasta"):
+        assert (od / f).stat().st_size > 0, f
+    rs = json.load(open(od / "read_stats.json"))
+    assert rs["Read_depth"]["num_sites_total"] == 60 and rs["Read_depth"]["num_sites_noCov"] < 30  # genotype.py:95-118
+    j = json.load(open(od / "genotype" / "genotyped.json"))
+    assert j["Samples"][0]["Name"] == "sample one" and all(s["SEG"] == "ref1" for s in j["Sites"])
+    fasta = (od / "genotype" / "personalised_reference.fasta").read_text()
+    assert fasta.startswith(">ref1_1 sample one personalised reference made by gramtools genotype\n")
+    assert len("".join(fasta.split(">")[1].split("\n")[1:])) == 2000
