@@ -362,3 +362,17 @@ def test_inputs_of_the_cli_tests(built_lib, tmp_path):
                 for hapg, kids in by_hapg.items():
                     if int(hapg) not in ps["HAPG"][0]:
                         assert all(j["Sites"][c]["GT"] == [[None]] for c in kids)
+
+
+def test_prg_without_sites(built_lib, tmp_path):
+    """No site: depth statistics are 0 / 0 (as the reference computes them), nothing to genotype, the personalised
+    reference is the PRG itself and the VCF has only its header."""
+    prg = np.asarray([1, 2, 3, 4, 1, 1], dtype=np.uint32)
+    none16, none32 = np.zeros(0, np.uint16), np.zeros(0, np.uint32)
+    d = read_depth_stats_host(prg, none16, none32)
+    assert np.isnan(d["mean"]) and d["num_sites_total"] == 0
+    j = json.loads(level_genotype_json(prg, none16, none32, d["mean"], d["variance"], 0.001))
+    assert j["Sites"] == [] and j["Lvl1_Sites"] == ["all"]
+    level_genotype(prg, none16, none32, d["mean"], d["variance"], 0.001, str(tmp_path))
+    assert (tmp_path / "personalised_reference.fasta").read_text().split("\n")[1] == "ACGTAA"
+    assert gzip.decompress((tmp_path / "genotyped.vcf.gz").read_bytes()).decode().splitlines()[-1].startswith("#CHROM")
