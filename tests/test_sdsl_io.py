@@ -249,3 +249,31 @@ def test_reference_deserialize_next_stats_layout(tmp_path):
         got.append((vals[i], vals[i + 1:i + 1 + vals[i]]))
         i += 1 + vals[i]
     assert got == [(3, [1, 42, 7]), (2, [11, 33])]
+
+
+def test_dumped_vectors_are_those_of_the_oracles_index(tmp_path):
+    """gram build's four k-mer index files for a real PRG: the vectors hold what dump.cpp:27-141 prescribes for the
+    ORACLE's k-mer index — every k-mer's states in the reference's list order (k-mers by ascending code here, in hash-map
+    order in the reference: load.cpp takes either)."""
+    for n, (prg, k) in enumerate(((synth.make_snp_prg(3000, 120, 6)[0], 5), (synth.make_nested_prg(6, 250, 21), 4))):
+        d = tmp_path / f"gram{n}"
+        d.mkdir()
+        Emu(prg, k).kmer_index_dump(str(d))
+        words = Oracle(prg, k).kmer_states()
+        by_kmer, i = {}, 0   # code -> [(lo, hi, [(site, allele)...], [site...])]
+        while i < len(words):
+            code, lo, hi, nt, ng = words[i:i + 5]
+            trav = [(words[i + 5 + 2 * j], words[i + 6 + 2 * j]) for j in range(nt)]
+            ing = [words[i + 5 + 2 * nt + 2 * j] for j in range(ng)]
+            by_kmer.setdefault(code, []).append((lo, hi, trav, ing))
+            i += 5 + 2 * nt + 2 * ng
+        codes = sorted(by_kmer)
+        kmers, _ = _read(str(d / "kmers"), 3)
+        stats, _ = _read(str(d / "kmers_stats"), 0)
+        sa_iv, _ = _read(str(d / "sa_intervals"), 0)
+        paths, _ = _read(str(d / "paths"), 0)
+        assert kmers == [((c >> (2 * j)) & 3) + 1 for c in codes for j in range(k)]
+        assert stats == [x for c in codes for x in [len(by_kmer[c])] + [len(t) + len(g) for _, _, t, g in by_kmer[c]]]
+        assert sa_iv == [x for c in codes for lo, hi, _, _ in by_kmer[c] for x in (lo, hi)]
+        assert paths == [x for c in codes for _, _, t, g in by_kmer[c]
+                         for x in [y for site, al in t for y in (site, al + 1)] + [y for site in g for y in (site, 0)]]
